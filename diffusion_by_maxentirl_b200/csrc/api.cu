@@ -1,0 +1,329 @@
+// extern "C" surface of libdxmi_b200.so (see include/dxmi_b200.h for the contract of every entry point).
+#include <cstdio>
+#include <cstring>
+
+#include "engine.cuh"
+
+using namespace dxmi;
+
+struct dxmi_net_s {
+    Net net;
+};
+
+static thread_local char g_api_err[768] = "";
+static void set_err(const char* m) { snprintf(g_api_err, sizeof g_api_err, "%s", m); }
+
+extern "C" {
+
+const char* dxmi_last_error(void) { return g_api_err; }
+long long dxmi_launch_count(void) { return total_launches(); }
+
+int dxmi_set_option(const char* name, int value) {
+    if (!strcmp(name, "block_n_256")) {
+        set_block_n_256(value);
+        return 0;
+    }
+    set_err("unknown option");
+    return -1;
+}
+
+int dxmi_create(const dxmi_arch_desc* desc, int device, dxmi_net_t* out) {
+    if (!desc || !out) {
+        set_err("dxmi_create: null argument");
+        return -1;
+    }
+    dxmi_net_s* h = new dxmi_net_s();
+    h->net.a = *desc;
+    h->net.device = device;
+    switch (desc->arch) {
+        case DXMI_ARCH_DDPM_UNET: spec_ddpm(h->net); break;
+        case DXMI_ARCH_IGEBM_V2: spec_igebm(h->net); break;
+        case DXMI_ARCH_ADM_UNET: spec_adm(h->net); break;
+        default:
+            delete h;
+            set_err("dxmi_create: unknown arch");
+            return -2;
+    }
+    *out = h;
+    return 0;
+}
+
+void dxmi_destroy(dxmi_net_t net) { delete net; }
+
+int dxmi_num_weights(dxmi_net_t net) { return net ? (int)net->net.keys.size() : -1; }
+
+int dxmi_weight_key(dxmi_net_t net, int i, char* buf, int buflen) {
+    if (!net || i < 0 || i >= (int)net->net.keys.size()) return -1;
+    snprintf(buf, buflen, "%s", net->net.keys[i].c_str());
+    return 0;
+}
+
+int dxmi_weight_shape(dxmi_net_t net, int i, int64_t* shape, int* ndim) {
+    if (!net || i < 0 || i >= (int)net->net.keys.size()) return -1;
+    const auto& s = net->net.expect[net->net.keys[i]];
+    *ndim = (int)s.size();
+    for (size_t k = 0; k < s.size(); ++k) shape[k] = s[k];
+    return 0;
+}
+
+int dxmi_bind_weight(dxmi_net_t net, const char* key, const void* dev_ptr, int dtype, const int64_t* shape, int ndim) {
+    if (!net || !key || !dev_ptr) {
+        set_err("dxmi_bind_weight: null argument");
+        return -1;
+    }
+    auto it = net->net.expect.find(key);
+    if (it == net->net.expect.end()) {
+        // keys the sampler injects into the net (log_betas, std) are not consumed by the network kernels
+        if (!strcmp(key, "log_betas") || !strcmp(key, "std")) return 0;
+        snprintf(g_api_err, sizeof g_api_err, "dxmi_bind_weight: unexpected key '%s'", key);
+        return -3;
+    }
+    const auto& es = it->second;
+    bool ok = (int)es.size() == ndim;
+    for (int i = 0; ok && i < ndim; ++i) ok = es[i] == shape[i];
+    if (!ok) {
+        snprintf(g_api_err, sizeof g_api_err, "dxmi_bind_weight: shape mismatch for '%s'", key);
+        return -4;
+    }
+    if (dtype != DXMI_F32 && dtype != DXMI_F16) {
+        snprintf(g_api_err, sizeof g_api_err, "dxmi_bind_weight: dtype of '%s' must be fp32 or fp16", key);
+        return -5;
+    }
+    Bound& b = net->net.bound[key];
+    const bool dtype_changed = b.ptr && b.dtype != dtype;
+    b.ptr = dev_ptr;
+    b.dtype = dtype;
+    b.shape.assign(shape, shape + ndim);
+    if (dtype_changed && net->net.finalized) {
+        set_err("dxmi_bind_weight: dtype changed after finalize; create a new handle");
+        return -6;
+    }
+    return 0;
+}
+
+static int run_pack(Net& n, cudaStream_t st) {
+    for (auto& j : n.pack_jobs) j(st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_err(cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+static Plan* get_plan(Net& n, int B) {
+    auto it = n.plans.find(B);
+    if (it != n.plans.end()) return it->second.get();
+    cudaSetDevice(n.device);
+    std::unique_ptr<Plan> p(new Plan());
+    p->B = B;
+    const size_t jobs_before = n.pack_jobs.size();
+    int r = build_plan(n, *p);
+    if (r) {
+        set_err(engine_last_error());
+        if (p->arena) cudaFree(p->arena);
+        return nullptr;
+    }
+    (void)jobs_before;
+    Plan* raw = p.get();
+    n.plans[B] = std::move(p);
+    return raw;
+}
+
+int dxmi_finalize(dxmi_net_t net, dxmi_stream_t stream) {
+    if (!net) return -1;
+    Net& n = net->net;
+    for (auto& k : n.keys) {
+        auto it = n.bound.find(k);
+        if (it == n.bound.end() || !it->second.ptr) {
+            snprintf(g_api_err, sizeof g_api_err, "dxmi_finalize: state_dict key '%s' was never bound", k.c_str());
+            return -7;
+        }
+    }
+    if (!n.finalized) {
+        // building the B=1 plan registers every packed / derived weight and its pack job
+        if (!get_plan(n, 1)) return -8;
+        n.finalized = true;
+    }
+    return run_pack(n, (cudaStream_t)stream);
+}
+
+int dxmi_repack(dxmi_net_t net, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_repack: handle not finalized");
+        return -1;
+    }
+    return run_pack(net->net, (cudaStream_t)stream);
+}
+
+size_t dxmi_workspace_bytes(dxmi_net_t net, int B) {
+    if (!net) return 0;
+    Plan* p = get_plan(net->net, B);
+    return p ? p->arena_bytes : 0;
+}
+
+static int run_plan(Net& n, Plan* p, cudaStream_t st) {
+    for (auto& f : p->ops) {
+        int r = f(st);
+        if (r) {
+            snprintf(g_api_err, sizeof g_api_err, "kernel launch failed (%d): %s | %s", r,
+                     cudaGetErrorString((cudaError_t)r), gemm_op_last_error());
+            return r;
+        }
+    }
+    count_launches(p->launches_per_run);
+    return 0;
+}
+
+int dxmi_unet_forward(dxmi_net_t net, const float* x, const float* x_scale, const float* t, const int64_t* y, float* out,
+                      int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_unet_forward: handle not finalized");
+        return -1;
+    }
+    if (net->net.a.arch == DXMI_ARCH_IGEBM_V2) {
+        set_err("dxmi_unet_forward called on a value-net handle");
+        return -2;
+    }
+    Plan* p = get_plan(net->net, B);
+    if (!p) return -3;
+    p->x = x;
+    p->x_scale = x_scale;
+    p->t = t;
+    p->y = y;
+    p->out = out;
+    return run_plan(net->net, p, (cudaStream_t)stream);
+}
+
+int dxmi_value_forward(dxmi_net_t net, const float* x, float* out, int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_value_forward: handle not finalized");
+        return -1;
+    }
+    if (net->net.a.arch != DXMI_ARCH_IGEBM_V2) {
+        set_err("dxmi_value_forward called on a U-Net handle");
+        return -2;
+    }
+    Plan* p = get_plan(net->net, B);
+    if (!p) return -3;
+    p->x = x;
+    p->out = out;
+    return run_plan(net->net, p, (cudaStream_t)stream);
+}
+
+int dxmi_var_step(const float* x, const float* eps, const float* z, const float* a, const float* c, const float* sigma,
+                  float* x_next, float* mean, float* control, float* logp, int B, int chw, dxmi_stream_t stream) {
+    if (chw % 4) {
+        set_err("dxmi_var_step: C*H*W must be a multiple of 4");
+        return -1;
+    }
+    var_step(x, eps, z, a, c, sigma, x_next, mean, control, logp, B, chw, (cudaStream_t)stream);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+int dxmi_edm_step(const float* x, const float* F, const float* z, const float* coef, float* x_next, float* mean, int B,
+                  int chw, dxmi_stream_t stream) {
+    if (chw % 4) {
+        set_err("dxmi_edm_step: C*H*W must be a multiple of 4");
+        return -1;
+    }
+    edm_step(x, F, z, coef, x_next, mean, B, chw, (cudaStream_t)stream);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, float* l_sample, float* mean,
+                     float* control, float* logp, int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized || net->net.a.arch != DXMI_ARCH_DDPM_UNET) {
+        set_err("dxmi_var_rollout: needs a finalized DDPM U-Net handle");
+        return -1;
+    }
+    Net& n = net->net;
+    Plan* p = get_plan(n, B);
+    if (!p) return -3;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long chw = (long long)n.a.in_channels * n.a.resolution * n.a.resolution;
+    const long long bchw = chw * B;
+    // x_0 = first noise tensor (var_sampler.py:242)
+    cudaMemcpyAsync(l_sample, noise, bchw * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    for (int i = 0; i < T; ++i) {
+        const float tau = sched_host[4 * i + 0], a = sched_host[4 * i + 1], c = sched_host[4 * i + 2],
+                    sg = sched_host[4 * i + 3];
+        fill_f32(p->tbuf, tau, B, st);
+        fill_f32(p->coef, a, B, st);
+        fill_f32(p->coef + B, c, B, st);
+        fill_f32(p->coef + 2 * B, sg, B, st);
+        count_launches(4);
+        const float* xi = l_sample + (long long)i * bchw;
+        p->x = xi;
+        p->x_scale = nullptr;
+        p->t = p->tbuf;
+        p->y = nullptr;
+        p->out = p->eps;
+        int r = run_plan(n, p, st);
+        if (r) return r;
+        var_step(xi, p->eps, noise + (long long)(i + 1) * bchw, p->coef, p->coef + B, p->coef + 2 * B,
+                 l_sample + (long long)(i + 1) * bchw, mean ? mean + (long long)i * bchw : nullptr,
+                 control ? control + (long long)i * bchw : nullptr, logp ? logp + (long long)i * B : nullptr, B, (int)chw,
+                 st);
+        count_launches(1);
+    }
+    return (int)cudaGetLastError();
+}
+
+int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, const int64_t* y,
+                     float* l_sample, float* mean, int B, dxmi_stream_t stream) {
+    (void)net; (void)sched_host; (void)T; (void)noise; (void)y; (void)l_sample; (void)mean; (void)B; (void)stream;
+    set_err("dxmi_edm_rollout: ADM U-Net path not built yet");
+    return -100;
+}
+
+int dxmi_quantize_u8(const float* x, uint8_t* out, long long nelem, dxmi_stream_t stream) {
+    quantize_u8(x, out, nelem, (cudaStream_t)stream);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ kernel-level ops
+
+int dxmi_op_conv_gemm(const dxmi_gemm_desc* d, dxmi_stream_t stream) {
+    GemmOp op;
+    int r = prepare_gemm(*d, &op);
+    if (r) {
+        set_err(gemm_op_last_error());
+        return r;
+    }
+    r = run_gemm(op, (cudaStream_t)stream);
+    if (r) set_err(gemm_op_last_error());
+    count_launches(1);
+    return r;
+}
+
+int dxmi_op_pack_conv_weight(const void* w, int dtype, int Cout, int Cin, int kh, int kw, int c_off, int c_cnt,
+                             void* dst_bf16, long long ldk, long long k_off, dxmi_stream_t stream) {
+    pack_conv_weight(w, dtype == DXMI_F16, Cout, Cin, kh, kw, c_off, c_cnt, (bf16*)dst_bf16, ldk, k_off,
+                     (cudaStream_t)stream);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+int dxmi_op_gn_ws_floats(int N, int HW, int groups) { return N * gn_num_slabs(N, HW) * 2 * groups; }
+
+int dxmi_op_group_norm(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int N, int HW, int groups,
+                       float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
+                       float* partial_ws, void* out, dxmi_stream_t stream) {
+    if (groups > 32 || (C1 + C2) % (8) || C1 % 8 || (C1 + C2) > 2048 || (C1 + C2) % groups) {
+        set_err("dxmi_op_group_norm: unsupported channel / group configuration");
+        return -1;
+    }
+    const int slabs = gn_num_slabs(N, HW);
+    gn_stats((const bf16*)x1, C1, ld1, (const bf16*)x2, C2, ld2, N, HW, groups, partial_ws, slabs, (cudaStream_t)stream);
+    gn_apply((const bf16*)x1, C1, ld1, (const bf16*)x2, C2, ld2, N, HW, groups, eps, gamma, beta, film, film_ld, silu,
+             partial_ws, slabs, (bf16*)out, (cudaStream_t)stream);
+    count_launches(2);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
+

@@ -1,0 +1,930 @@
+// Plan builders for the three networks on the DxMI sampler path.
+//   DDPM U-Net   models/DxMI/unet_small.py:194-332
+//   IGEBM V2     models/modules.py:104-163 (+ models/value.py:8-12)
+//   ADM U-Net    models/cm/unet.py:523-790            (engine_adm.cu)
+#include "engine.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace dxmi {
+
+static thread_local char g_eng_err[768] = "";
+const char* engine_last_error() { return g_eng_err; }
+void engine_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_eng_err, sizeof g_eng_err, fmt, ap);
+    va_end(ap);
+}
+static long long g_launches = 0;
+void count_launches(long long n) { g_launches += n; }
+long long total_launches() { return g_launches; }
+
+Net::~Net() {
+    for (void* p : owned) cudaFree(p);
+    for (auto& kv : plans)
+        if (kv.second && kv.second->arena) cudaFree(kv.second->arena);
+}
+
+// ================================================================================================ specs
+
+static void expect_key(Net& net, const std::string& k, std::vector<int64_t> shape) {
+    net.keys.push_back(k);
+    net.expect[k] = std::move(shape);
+}
+static void expect_conv(Net& net, const std::string& p, int co, int ci, int k, bool bias = true) {
+    expect_key(net, p + ".weight", {co, ci, k, k});
+    if (bias) expect_key(net, p + ".bias", {co});
+}
+static void expect_linear(Net& net, const std::string& p, int o, int i) {
+    expect_key(net, p + ".weight", {o, i});
+    expect_key(net, p + ".bias", {o});
+}
+static void expect_norm(Net& net, const std::string& p, int c) {
+    expect_key(net, p + ".weight", {c});
+    expect_key(net, p + ".bias", {c});
+}
+
+static bool has_attn(const dxmi_arch_desc& a, int v) {
+    for (int i = 0; i < a.n_attn; ++i)
+        if (a.attn_resolutions[i] == v) return true;
+    return false;
+}
+
+static void spec_ddpm_resblock(Net& net, const std::string& p, int cin, int cout, int temb) {
+    expect_norm(net, p + ".norm1", cin);
+    expect_conv(net, p + ".conv1", cout, cin, 3);
+    expect_linear(net, p + ".temb_proj", cout, temb);
+    expect_norm(net, p + ".norm2", cout);
+    expect_conv(net, p + ".conv2", cout, cout, 3);
+    if (cin != cout) expect_conv(net, p + ".nin_shortcut", cout, cin, 1);
+}
+static void spec_ddpm_attn(Net& net, const std::string& p, int c) {
+    expect_norm(net, p + ".norm", c);
+    expect_conv(net, p + ".q", c, c, 1);
+    expect_conv(net, p + ".k", c, c, 1);
+    expect_conv(net, p + ".v", c, c, 1);
+    expect_conv(net, p + ".proj_out", c, c, 1);
+}
+
+// Same module registration order as unet_small.Model.__init__ (unet_small.py:195-289) so state_dict order matches.
+void spec_ddpm(Net& net) {
+    const dxmi_arch_desc& a = net.a;
+    const int ch = a.ch, temb = 4 * ch;
+    expect_linear(net, "temb.dense.0", temb, ch);
+    expect_linear(net, "temb.dense.1", temb, temb);
+    expect_conv(net, "conv_in", ch, a.in_channels, 3);
+    int res = a.resolution, block_in = ch;
+    for (int l = 0; l < a.n_levels; ++l) {
+        const int block_out = ch * a.ch_mult[l];
+        block_in = ch * (l == 0 ? 1 : a.ch_mult[l - 1]);
+        const std::string lp = "down." + std::to_string(l);
+        for (int b = 0; b < a.num_res_blocks; ++b) {
+            spec_ddpm_resblock(net, lp + ".block." + std::to_string(b), block_in, block_out, temb);
+            block_in = block_out;
+        }
+        if (has_attn(a, res))
+            for (int b = 0; b < a.num_res_blocks; ++b) spec_ddpm_attn(net, lp + ".attn." + std::to_string(b), block_out);
+        if (l != a.n_levels - 1) {
+            expect_conv(net, lp + ".downsample.conv", block_in, block_in, 3);
+            res /= 2;
+        }
+    }
+    spec_ddpm_resblock(net, "mid.block_1", block_in, block_in, temb);
+    spec_ddpm_attn(net, "mid.attn_1", block_in);
+    spec_ddpm_resblock(net, "mid.block_2", block_in, block_in, temb);
+    // `up` modules are inserted at the front of the ModuleList while iterating levels in reverse, so the
+    // state_dict lists up.0 first; the channel bookkeeping still runs from the deepest level upward.
+    std::vector<std::vector<std::pair<std::string, std::vector<int>>>> per_level(a.n_levels);
+    {
+        int bi = block_in;
+        int r = res;
+        for (int l = a.n_levels - 1; l >= 0; --l) {
+            const int block_out = ch * a.ch_mult[l];
+            int skip_in = ch * a.ch_mult[l];
+            for (int b = 0; b <= a.num_res_blocks; ++b) {
+                if (b == a.num_res_blocks) skip_in = ch * (l == 0 ? 1 : a.ch_mult[l - 1]);
+                per_level[l].push_back({"block", {bi + skip_in, block_out}});
+                bi = block_out;
+            }
+            if (has_attn(a, r))
+                for (int b = 0; b <= a.num_res_blocks; ++b) per_level[l].push_back({"attn", {block_out}});
+            if (l != 0) {
+                per_level[l].push_back({"upsample", {bi}});
+                r *= 2;
+            }
+        }
+    }
+    for (int l = 0; l < a.n_levels; ++l) {
+        const std::string lp = "up." + std::to_string(l);
+        int bidx = 0, aidx = 0;
+        for (auto& e : per_level[l]) {
+            if (e.first == "block")
+                spec_ddpm_resblock(net, lp + ".block." + std::to_string(bidx++), e.second[0], e.second[1], temb);
+            else if (e.first == "attn")
+                spec_ddpm_attn(net, lp + ".attn." + std::to_string(aidx++), e.second[0]);
+            else
+                expect_conv(net, lp + ".upsample.conv", e.second[0], e.second[0], 3);
+        }
+    }
+    expect_norm(net, "norm_out", ch * a.ch_mult[0]);
+    expect_conv(net, "conv_out", a.out_channels, ch * a.ch_mult[0], 3);
+}
+
+// IGEBMEncoderV2(use_spectral_norm=False, keepdim=False, n_class=None) (modules.py:108-140)
+void spec_igebm(Net& net) {
+    const int nh = net.a.ch;
+    expect_conv(net, "conv1", nh, net.a.in_channels, 3);
+    const int cin[6] = {nh, nh, nh, 2 * nh, 2 * nh, 2 * nh};
+    const int cout[6] = {nh, nh, 2 * nh, 2 * nh, 2 * nh, 2 * nh};
+    const bool down[6] = {true, false, true, false, true, false};
+    for (int i = 0; i < 6; ++i) {
+        const std::string p = "blocks." + std::to_string(i);
+        expect_conv(net, p + ".conv1", cout[i], cin[i], 3);
+        expect_conv(net, p + ".conv2", cout[i], cout[i], 3);
+        if (cin[i] != cout[i] || down[i]) expect_conv(net, p + ".skip.0", cout[i], cin[i], 1, /*bias=*/false);
+    }
+    expect_linear(net, "linear", net.a.out_channels, 2 * nh);
+    if (net.a.learn_out_scale) expect_linear(net, "out_scale", 1, 1);
+}
+
+// ================================================================================================ builder
+
+struct Builder {
+    Net& net;
+    Plan& plan;
+    bool dry;
+    int B;
+    size_t off = 0;
+    static constexpr int NSLOT = 8;
+    size_t scratch_max[NSLOT] = {0};
+    size_t scratch_base[NSLOT] = {0};
+    int err = 0;
+
+    Builder(Net& n, Plan& p, bool d) : net(n), plan(p), dry(d), B(p.B) {}
+
+    static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+    void* alloc(size_t bytes) {
+        void* r = dry ? nullptr : plan.arena + off;
+        off += align_up(bytes);
+        return r;
+    }
+    void* scratch(int slot, size_t bytes) {
+        bytes = align_up(bytes);
+        if (dry) {
+            if (bytes > scratch_max[slot]) scratch_max[slot] = bytes;
+            return nullptr;
+        }
+        return plan.arena + scratch_base[slot];
+    }
+    bf16* act_alloc(int C, int H, int W) { return (bf16*)alloc((size_t)B * H * W * C * sizeof(bf16)); }
+
+    void fail(const char* what) {
+        if (!err) {
+            err = -20;
+            engine_set_error("%s", what);
+        }
+    }
+
+    // ---------------------------------------------------------------- weights
+    const Bound* get(const std::string& key) {
+        auto it = net.bound.find(key);
+        if (it == net.bound.end() || !it->second.ptr) {
+            if (!dry) {
+                std::string m = "weight not bound: " + key;
+                fail(m.c_str());
+            }
+            return nullptr;
+        }
+        return &it->second;
+    }
+    // fp32 view of a bound tensor: the borrowed pointer itself when fp32, else a converted (owned) copy.
+    const float* f32(const std::string& key) {
+        if (dry) return nullptr;
+        const Bound* b = get(key);
+        if (!b) return nullptr;
+        if (b->dtype == DXMI_F32) return (const float*)b->ptr;
+        auto it = net.derived.find("f32:" + key);
+        if (it != net.derived.end()) return (const float*)it->second;
+        long long n = 1;
+        for (auto s : b->shape) n *= s;
+        float* d = nullptr;
+        cudaMalloc(&d, n * sizeof(float));
+        net.owned.push_back(d);
+        net.derived["f32:" + key] = d;
+        Net* np = &net;
+        net.pack_jobs.push_back([np, key, d, n](cudaStream_t st) {
+            const Bound& bb = np->bound[key];
+            cast_to_f32(bb.ptr, bb.dtype == DXMI_F16, d, n, st);
+            count_launches(1);
+        });
+        return d;
+    }
+    void* derived_buf(const std::string& name, size_t bytes, bool* fresh) {
+        auto it = net.derived.find(name);
+        if (it != net.derived.end()) {
+            *fresh = false;
+            return it->second;
+        }
+        void* d = nullptr;
+        if (cudaMalloc(&d, bytes) != cudaSuccess) {
+            fail("cudaMalloc failed for packed weights");
+            return nullptr;
+        }
+        net.owned.push_back(d);
+        net.derived[name] = d;
+        *fresh = true;
+        return d;
+    }
+    struct PackPart {
+        std::string key;  // conv weight key
+        int c_off, c_cnt; // input-channel slice
+    };
+    // bf16 [rows, K] with K = sum over parts of taps*c_cnt; rows stacked from `row_parts` groups when stacking q|k|v.
+    bf16* packed_rows(const std::string& name, const std::vector<std::vector<PackPart>>& row_groups, long long* K_out,
+                      int* rows_out) {
+        if (dry) return nullptr;
+        // geometry
+        long long K = 0;
+        int rows = 0;
+        for (size_t g = 0; g < row_groups.size(); ++g) {
+            long long kg = 0;
+            int rg = 0;
+            for (auto& part : row_groups[g]) {
+                const Bound* b = get(part.key);
+                if (!b) return nullptr;
+                const int taps = (int)(b->shape.size() == 4 ? b->shape[2] * b->shape[3] : 1);
+                kg += (long long)taps * part.c_cnt;
+                rg = (int)b->shape[0];
+            }
+            if (g == 0) K = kg;
+            if (kg != K) {
+                fail("packed_rows: inconsistent K across row groups");
+                return nullptr;
+            }
+            rows += rg;
+        }
+        if (K_out) *K_out = K;
+        if (rows_out) *rows_out = rows;
+        bool fresh = false;
+        bf16* d = (bf16*)derived_buf("w:" + name, (size_t)rows * K * sizeof(bf16), &fresh);
+        if (!d || !fresh) return d;
+        Net* np = &net;
+        int row0 = 0;
+        for (auto& grp : row_groups) {
+            long long k_off = 0;
+            int rg = 0;
+            for (auto& part : grp) {
+                const Bound* b = get(part.key);
+                const int kh = b->shape.size() == 4 ? (int)b->shape[2] : 1;
+                const int kw = b->shape.size() == 4 ? (int)b->shape[3] : 1;
+                const int Cout = (int)b->shape[0], Cin = (int)b->shape[1];
+                bf16* dst = d + (long long)row0 * K;
+                const std::string key = part.key;
+                const int c_off = part.c_off, c_cnt = part.c_cnt;
+                net.pack_jobs.push_back([np, key, Cout, Cin, kh, kw, c_off, c_cnt, dst, K, k_off](cudaStream_t st) {
+                    const Bound& bb = np->bound[key];
+                    pack_conv_weight(bb.ptr, bb.dtype == DXMI_F16, Cout, Cin, kh, kw, c_off, c_cnt, dst, K, k_off, st);
+                    count_launches(1);
+                });
+                k_off += (long long)kh * kw * c_cnt;
+                rg = Cout;
+            }
+            row0 += rg;
+        }
+        return d;
+    }
+    // fp32 concatenation of several bound vectors / matrices (row-stacked)
+    float* concat_f32(const std::string& name, const std::vector<std::string>& keys) {
+        if (dry) return nullptr;
+        long long total = 0;
+        std::vector<long long> sizes;
+        for (auto& k : keys) {
+            const Bound* b = get(k);
+            if (!b) return nullptr;
+            long long n = 1;
+            for (auto s : b->shape) n *= s;
+            sizes.push_back(n);
+            total += n;
+        }
+        bool fresh = false;
+        float* d = (float*)derived_buf("cat:" + name, total * sizeof(float), &fresh);
+        if (!d || !fresh) return d;
+        Net* np = &net;
+        long long o = 0;
+        for (size_t i = 0; i < keys.size(); ++i) {
+            const std::string key = keys[i];
+            float* dst = d + o;
+            const long long n = sizes[i];
+            net.pack_jobs.push_back([np, key, dst, n](cudaStream_t st) {
+                const Bound& bb = np->bound[key];
+                cast_to_f32(bb.ptr, bb.dtype == DXMI_F16, dst, n, st);
+                count_launches(1);
+            });
+            o += n;
+        }
+        return d;
+    }
+    float* sum_f32(const std::string& name, const std::string& ka, const std::string& kb, long long n) {
+        if (dry) return nullptr;
+        bool fresh = false;
+        float* d = (float*)derived_buf("sum:" + name, n * sizeof(float), &fresh);
+        if (!d || !fresh) return d;
+        const float* pa = f32(ka);
+        const float* pb = f32(kb);
+        Net* np = &net;
+        (void)np;
+        // note: f32() of an fp16 tensor registered its cast job *before* this one, so ordering is correct
+        net.pack_jobs.push_back([pa, pb, d, n](cudaStream_t st) {
+            vec_add_f32(pa, pb, d, n, st);
+            count_launches(1);
+        });
+        return d;
+    }
+
+    // ---------------------------------------------------------------- op emission
+    void op(std::function<int(cudaStream_t)> f, int launches = 1) {
+        if (dry) return;
+        plan.ops.push_back(std::move(f));
+        plan.launches_per_run += launches;
+    }
+    void gemm(const dxmi_gemm_desc& d) {
+        if (dry || err) return;
+        GemmOp g;
+        int r = prepare_gemm(d, &g);
+        if (r) {
+            err = r;
+            engine_set_error("prepare_gemm: %s", gemm_op_last_error());
+            return;
+        }
+        plan.gemm_flops += g.flops;
+        op([g](cudaStream_t st) { return run_gemm(g, st); });
+    }
+    dxmi_gemm_desc conv_desc(int H, int W) {
+        dxmi_gemm_desc d;
+        memset(&d, 0, sizeof d);
+        d.N = B;
+        d.H = H;
+        d.W = W;
+        d.out_H = H;
+        d.out_W = W;
+        d.stride = 1;
+        d.batch = 1;
+        d.alpha = 1.f;
+        d.rows_per_image = H * W;
+        return d;
+    }
+    static void set_src(dxmi_gemm_desc& d, int i, const bf16* p, int C, int ld) {
+        d.a_ptr[i] = p;
+        d.a_C[i] = C;
+        d.a_ld[i] = ld;
+    }
+    static void add_seg(dxmi_gemm_desc& d, int src, int taps) {
+        d.seg_src[d.nseg] = src;
+        d.seg_taps[d.nseg] = taps;
+        d.nseg++;
+    }
+
+    // GroupNorm(32) over concat(x1, x2) -> out (scratch slot), optional SiLU / FiLM
+    void group_norm(Act x1, Act x2, const std::string& pfx, float eps, int silu, const float* film, int film_ld,
+                    bf16* out) {
+        const int HW = x1.H * x1.W;
+        const int slabs = gn_num_slabs(B, HW);
+        float* ws = (float*)scratch(5, (size_t)B * slabs * 64 * sizeof(float));
+        const float* gamma = f32(pfx + ".weight");
+        const float* beta = f32(pfx + ".bias");
+        const bf16 *p1 = x1.p, *p2 = x2.p;
+        const int C1 = x1.C, C2 = x2.C;
+        const int Bn = B;
+        if ((C1 + C2) % 8 || (C1 % 8) || (C1 + C2) > 2048) fail("group_norm: unsupported channel count");
+        op([=](cudaStream_t st) {
+            gn_stats(p1, C1, C1, p2, C2, C2, Bn, HW, 32, ws, slabs, st);
+            gn_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, ws, slabs, out, st);
+            return (int)cudaGetLastError();
+        },
+           2);
+    }
+};
+
+// ================================================================================================ DDPM U-Net
+
+struct DdpmBuilder : Builder {
+    using Builder::Builder;
+    float* tproj = nullptr;
+    int tproj_ld = 0;
+    int tproj_off = 0;
+    std::vector<std::string> tproj_w, tproj_b;
+
+    Act resblock(const std::string& p, Act xa, Act xb, int Cout) {
+        const int H = xa.H, W = xa.W, HW = H * W;
+        const int Cin = xa.C + xb.C;
+        bf16* g1 = (bf16*)scratch(0, (size_t)B * HW * Cin * 2);
+        group_norm(xa, xb, p + ".norm1", 1e-6f, 1, nullptr, 0, g1);
+        bf16* h1 = (bf16*)scratch(1, (size_t)B * HW * Cout * 2);
+        {
+            long long K;
+            int rows;
+            bf16* w = packed_rows(p + ".conv1", {{{p + ".conv1.weight", 0, Cin}}}, &K, &rows);
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, g1, Cin, Cin);
+            add_seg(d, 0, 9);
+            d.b_ptr = w;
+            d.b_rows = Cout;
+            d.b_ld = 9LL * Cin;
+            d.bias = f32(p + ".conv1.bias");
+            d.rowvec = tproj ? tproj + tproj_off : nullptr;
+            d.ldrv = tproj_ld;
+            d.out = h1;
+            d.ldo = Cout;
+            gemm(d);
+        }
+        tproj_off += Cout;
+        bf16* g2 = (bf16*)scratch(0, (size_t)B * HW * Cout * 2);
+        Act h1a{h1, Cout, H, W};
+        group_norm(h1a, Act{}, p + ".norm2", 1e-6f, 1, nullptr, 0, g2);
+        Act out{act_alloc(Cout, H, W), Cout, H, W};
+        {
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, g2, Cout, Cout);
+            add_seg(d, 0, 9);
+            long long K = 9LL * Cout;
+            if (Cin != Cout) {
+                // conv2(h) + nin_shortcut(cat(xa, xb)) in one accumulator (unet_small.py:128-136)
+                std::vector<PackPart> parts = {{p + ".conv2.weight", 0, Cout}, {p + ".nin_shortcut.weight", 0, xa.C}};
+                set_src(d, 1, xa.p, xa.C, xa.C);
+                add_seg(d, 1, 1);
+                K += xa.C;
+                if (xb.C) {
+                    parts.push_back({p + ".nin_shortcut.weight", xa.C, xb.C});
+                    set_src(d, 2, xb.p, xb.C, xb.C);
+                    add_seg(d, 2, 1);
+                    K += xb.C;
+                }
+                d.b_ptr = packed_rows(p + ".conv2+nin", {parts}, nullptr, nullptr);
+                d.bias = sum_f32(p + ".conv2+nin.bias", p + ".conv2.bias", p + ".nin_shortcut.bias", Cout);
+            } else {
+                d.b_ptr = packed_rows(p + ".conv2", {{{p + ".conv2.weight", 0, Cout}}}, nullptr, nullptr);
+                d.bias = f32(p + ".conv2.bias");
+                d.residual = xa.p;
+                d.ldr = Cout;
+            }
+            d.b_rows = Cout;
+            d.b_ld = K;
+            d.out = out.p;
+            d.ldo = Cout;
+            gemm(d);
+        }
+        return out;
+    }
+
+    Act attn(const std::string& p, Act x) {
+        const int C = x.C, H = x.H, W = x.W, HW = H * W;
+        bf16* hn = (bf16*)scratch(0, (size_t)B * HW * C * 2);
+        group_norm(x, Act{}, p + ".norm", 1e-6f, 0, nullptr, 0, hn);
+        Act out{act_alloc(C, H, W), C, H, W};
+        bf16* o = (bf16*)scratch(4, (size_t)B * HW * C * 2);
+        const float scale = 1.f / sqrtf((float)C);
+        if (HW <= 64) {
+            // q|k|v in one GEMM, then the whole-sequence-in-one-CTA kernel
+            bf16* qkv = (bf16*)scratch(1, (size_t)B * HW * 3 * C * 2);
+            bf16* w = packed_rows(p + ".qkv",
+                                  {{{p + ".q.weight", 0, C}}, {{p + ".k.weight", 0, C}}, {{p + ".v.weight", 0, C}}},
+                                  nullptr, nullptr);
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, hn, C, C);
+            add_seg(d, 0, 1);
+            d.b_ptr = w;
+            d.b_rows = 3 * C;
+            d.b_ld = C;
+            d.bias = concat_f32(p + ".qkv.bias", {p + ".q.bias", p + ".k.bias", p + ".v.bias"});
+            d.out = qkv;
+            d.ldo = 3 * C;
+            gemm(d);
+            const int Bn = B;
+            op([=](cudaStream_t st) {
+                attn_small(qkv, qkv + C, qkv + 2 * C, 3 * C, o, C, Bn, 1, HW, C, scale, st);
+                return (int)cudaGetLastError();
+            });
+        } else if (HW == 128 || HW == 256) {
+            bf16* qk = (bf16*)scratch(1, (size_t)B * HW * 2 * C * 2);
+            bf16* vT = (bf16*)scratch(2, (size_t)B * HW * C * 2);
+            bf16* P = (bf16*)scratch(3, (size_t)B * HW * HW * 2);
+            {   // q | k  = hn . [Wq; Wk]^T
+                bf16* w = packed_rows(p + ".qk", {{{p + ".q.weight", 0, C}}, {{p + ".k.weight", 0, C}}}, nullptr, nullptr);
+                dxmi_gemm_desc d = conv_desc(H, W);
+                set_src(d, 0, hn, C, C);
+                add_seg(d, 0, 1);
+                d.b_ptr = w;
+                d.b_rows = 2 * C;
+                d.b_ld = C;
+                d.bias = concat_f32(p + ".qk.bias", {p + ".q.bias", p + ".k.bias"});
+                d.out = qk;
+                d.ldo = 2 * C;
+                gemm(d);
+            }
+            {   // V^T[b] = Wv . hn[b]^T  (weights as the A operand, so V lands key-major for the P.V GEMM)
+                bf16* w = packed_rows(p + ".v", {{{p + ".v.weight", 0, C}}}, nullptr, nullptr);
+                dxmi_gemm_desc d;
+                memset(&d, 0, sizeof d);
+                d.N = 1;
+                d.H = 1;
+                d.W = C;  // rows of Wv
+                d.out_H = 1;
+                d.out_W = C;
+                d.stride = 1;
+                set_src(d, 0, w, C, C);
+                add_seg(d, 0, 1);
+                d.b_ptr = hn;
+                d.b_rows = HW;
+                d.b_ld = C;
+                d.b_batch_stride = (long long)HW * C;
+                d.batch = B;
+                d.b_batched = 1;
+                d.bias = f32(p + ".v.bias");
+                d.bias_along_m = 1;
+                d.out = vT;
+                d.ldo = HW;
+                d.out_batch_stride = (long long)C * HW;
+                d.alpha = 1.f;
+                d.rows_per_image = 1;
+                gemm(d);
+            }
+            {   // P = softmax(scale * q k^T)   (row softmax fused in the epilogue; whole row lives in TMEM)
+                dxmi_gemm_desc d;
+                memset(&d, 0, sizeof d);
+                d.N = B;
+                d.H = 1;
+                d.W = HW;
+                d.out_H = 1;
+                d.out_W = HW;
+                d.stride = 1;
+                set_src(d, 0, qk, C, 2 * C);
+                add_seg(d, 0, 1);
+                d.a_batched = 1;
+                d.b_ptr = qk + C;
+                d.b_rows = HW;
+                d.b_ld = 2 * C;
+                d.b_batch_stride = (long long)HW * 2 * C;
+                d.b_batched = 1;
+                d.batch = B;
+                d.alpha = scale;
+                d.softmax = 1;
+                d.out = P;
+                d.ldo = HW;
+                d.out_batch_stride = (long long)HW * HW;
+                d.rows_per_image = 1;
+                gemm(d);
+            }
+            {   // O = P . V
+                dxmi_gemm_desc d;
+                memset(&d, 0, sizeof d);
+                d.N = B;
+                d.H = 1;
+                d.W = HW;
+                d.out_H = 1;
+                d.out_W = HW;
+                d.stride = 1;
+                set_src(d, 0, P, HW, HW);
+                add_seg(d, 0, 1);
+                d.a_batched = 1;
+                d.b_ptr = vT;
+                d.b_rows = C;
+                d.b_ld = HW;
+                d.b_batch_stride = (long long)C * HW;
+                d.b_batched = 1;
+                d.batch = B;
+                d.alpha = 1.f;
+                d.out = o;
+                d.ldo = C;
+                d.out_batch_stride = (long long)HW * C;
+                d.rows_per_image = 1;
+                gemm(d);
+            }
+        } else {
+            fail("DDPM attention: unsupported sequence length");
+        }
+        {   // proj_out + residual
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, o, C, C);
+            add_seg(d, 0, 1);
+            d.b_ptr = packed_rows(p + ".proj_out", {{{p + ".proj_out.weight", 0, C}}}, nullptr, nullptr);
+            d.b_rows = C;
+            d.b_ld = C;
+            d.bias = f32(p + ".proj_out.bias");
+            d.residual = x.p;
+            d.ldr = C;
+            d.out = out.p;
+            d.ldo = C;
+            gemm(d);
+        }
+        return out;
+    }
+
+    Act downsample(const std::string& p, Act x) {
+        const int C = x.C;
+        Act out{act_alloc(C, x.H / 2, x.W / 2), C, x.H / 2, x.W / 2};
+        dxmi_gemm_desc d = conv_desc(x.H, x.W);
+        d.out_H = x.H / 2;
+        d.out_W = x.W / 2;
+        d.stride = 2;
+        d.rows_per_image = (x.H / 2) * (x.W / 2);
+        set_src(d, 0, x.p, C, C);
+        add_seg(d, 0, 9);
+        d.b_ptr = packed_rows(p + ".conv", {{{p + ".conv.weight", 0, C}}}, nullptr, nullptr);
+        d.b_rows = C;
+        d.b_ld = 9LL * C;
+        d.bias = f32(p + ".conv.bias");
+        d.out = out.p;
+        d.ldo = C;
+        gemm(d);
+        return out;
+    }
+
+    Act upsample(const std::string& p, Act x) {
+        const int C = x.C, H2 = x.H * 2, W2 = x.W * 2;
+        bf16* up = (bf16*)scratch(1, (size_t)B * H2 * W2 * C * 2);
+        const bf16* xp = x.p;
+        const int Bn = B, H = x.H, W = x.W;
+        op([=](cudaStream_t st) {
+            upsample2x(xp, up, Bn, H, W, C, st);
+            return (int)cudaGetLastError();
+        });
+        Act out{act_alloc(C, H2, W2), C, H2, W2};
+        dxmi_gemm_desc d = conv_desc(H2, W2);
+        set_src(d, 0, up, C, C);
+        add_seg(d, 0, 9);
+        d.b_ptr = packed_rows(p + ".conv", {{{p + ".conv.weight", 0, C}}}, nullptr, nullptr);
+        d.b_rows = C;
+        d.b_ld = 9LL * C;
+        d.bias = f32(p + ".conv.bias");
+        d.out = out.p;
+        d.ldo = C;
+        gemm(d);
+        return out;
+    }
+
+    void build() {
+        const dxmi_arch_desc& a = net.a;
+        const int ch = a.ch, temb_ch = 4 * ch, R = a.resolution;
+        Plan* pl = &plan;
+        const int Bn = B;
+        // rollout scratch
+        plan.eps = (float*)alloc((size_t)B * a.out_channels * R * R * sizeof(float));
+        plan.tbuf = (float*)alloc((size_t)B * sizeof(float));
+        plan.coef = (float*)alloc((size_t)B * 8 * sizeof(float));
+
+        // ---- collect temb_proj layers in execution order (needed before emitting the single batched projection)
+        std::vector<std::string> rb;  // resblock prefixes in execution order
+        {
+            int res = R;
+            for (int l = 0; l < a.n_levels; ++l) {
+                for (int b = 0; b < a.num_res_blocks; ++b) rb.push_back("down." + std::to_string(l) + ".block." + std::to_string(b));
+                if (l != a.n_levels - 1) res /= 2;
+            }
+            rb.push_back("mid.block_1");
+            rb.push_back("mid.block_2");
+            for (int l = a.n_levels - 1; l >= 0; --l)
+                for (int b = 0; b <= a.num_res_blocks; ++b) rb.push_back("up." + std::to_string(l) + ".block." + std::to_string(b));
+        }
+        int TP = 0;
+        if (!dry) {
+            for (auto& p : rb) {
+                const Bound* bw = get(p + ".temb_proj.weight");
+                if (!bw) return;
+                TP += (int)bw->shape[0];
+            }
+        } else {
+            TP = 1;  // size refined below (dry pass only needs an upper bound; computed exactly from arch)
+            int tot = 0;
+            for (int l = 0; l < a.n_levels; ++l) tot += a.num_res_blocks * ch * a.ch_mult[l];
+            tot += 2 * ch * a.ch_mult[a.n_levels - 1];
+            for (int l = a.n_levels - 1; l >= 0; --l) tot += (a.num_res_blocks + 1) * ch * a.ch_mult[l];
+            TP = tot;
+        }
+        // ---- timestep embedding MLP + all temb_proj at once (unet_small.py:296-299, :123)
+        float* te = (float*)alloc((size_t)B * ch * 4);
+        float* t1 = (float*)alloc((size_t)B * temb_ch * 4);
+        float* temb = (float*)alloc((size_t)B * temb_ch * 4);
+        tproj = (float*)alloc((size_t)B * TP * 4);
+        tproj_ld = TP;
+        {
+            std::vector<std::string> wk, bk;
+            for (auto& p : rb) {
+                wk.push_back(p + ".temb_proj.weight");
+                bk.push_back(p + ".temb_proj.bias");
+            }
+            const float* Wc = concat_f32("temb_proj.weight", wk);
+            const float* bc = concat_f32("temb_proj.bias", bk);
+            const float* w0 = f32("temb.dense.0.weight");
+            const float* b0 = f32("temb.dense.0.bias");
+            const float* w1 = f32("temb.dense.1.weight");
+            const float* b1 = f32("temb.dense.1.bias");
+            float* tp = tproj;
+            op([=](cudaStream_t st) {
+                timestep_embedding(pl->t, te, Bn, ch, 0, st);
+                linear_f32(te, ch, w0, b0, t1, temb_ch, Bn, ch, temb_ch, 0, 0, st);
+                linear_f32(t1, temb_ch, w1, b1, temb, temb_ch, Bn, temb_ch, temb_ch, 2, 0, st);
+                linear_f32(temb, temb_ch, Wc, bc, tp, TP, Bn, temb_ch, TP, 2, 0, st);
+                return (int)cudaGetLastError();
+            },
+               4);
+        }
+        // ---- conv_in
+        Act h0{act_alloc(ch, R, R), ch, R, R};
+        {
+            const float* w = f32("conv_in.weight");
+            const float* b = f32("conv_in.bias");
+            bf16* o = h0.p;
+            const int Cin = a.in_channels;
+            op([=](cudaStream_t st) {
+                conv3x3_first(pl->x, pl->x_scale, w, b, o, Bn, Cin, R, R, ch, 0, st);
+                return (int)cudaGetLastError();
+            });
+        }
+        // ---- down path
+        std::vector<Act> hs{h0};
+        int res = R;
+        for (int l = 0; l < a.n_levels; ++l) {
+            const int cout = ch * a.ch_mult[l];
+            const std::string lp = "down." + std::to_string(l);
+            for (int b = 0; b < a.num_res_blocks; ++b) {
+                Act h = resblock(lp + ".block." + std::to_string(b), hs.back(), Act{}, cout);
+                if (has_attn(a, res)) h = attn(lp + ".attn." + std::to_string(b), h);
+                hs.push_back(h);
+            }
+            if (l != a.n_levels - 1) {
+                hs.push_back(downsample(lp + ".downsample", hs.back()));
+                res /= 2;
+            }
+        }
+        // ---- middle
+        Act h = hs.back();
+        h = resblock("mid.block_1", h, Act{}, h.C);
+        h = attn("mid.attn_1", h);
+        h = resblock("mid.block_2", h, Act{}, h.C);
+        // ---- up path
+        for (int l = a.n_levels - 1; l >= 0; --l) {
+            const int cout = ch * a.ch_mult[l];
+            const std::string lp = "up." + std::to_string(l);
+            for (int b = 0; b <= a.num_res_blocks; ++b) {
+                Act skip = hs.back();
+                hs.pop_back();
+                h = resblock(lp + ".block." + std::to_string(b), h, skip, cout);
+                if (has_attn(a, res)) h = attn(lp + ".attn." + std::to_string(b), h);
+            }
+            if (l != 0) {
+                h = upsample(lp + ".upsample", h);
+                res *= 2;
+            }
+        }
+        // ---- head
+        bf16* g = (bf16*)scratch(0, (size_t)B * R * R * h.C * 2);
+        group_norm(h, Act{}, "norm_out", 1e-6f, 1, nullptr, 0, g);
+        {
+            const float* w = f32("conv_out.weight");
+            const float* b = f32("conv_out.bias");
+            const int C = h.C, Co = a.out_channels;
+            op([=](cudaStream_t st) {
+                conv3x3_last(g, w, b, pl->out, Bn, C, R, R, Co, st);
+                return (int)cudaGetLastError();
+            });
+        }
+    }
+};
+
+// ================================================================================================ IGEBM V2 value net
+
+struct IgebmBuilder : Builder {
+    using Builder::Builder;
+
+    void build() {
+        const dxmi_arch_desc& a = net.a;
+        const int nh = a.ch, R = a.resolution;
+        Plan* pl = &plan;
+        const int Bn = B;
+        Act h{act_alloc(nh, R, R), nh, R, R};
+        {
+            const float* w = f32("conv1.weight");
+            const float* b = f32("conv1.bias");
+            bf16* o = h.p;
+            const int Cin = a.in_channels;
+            op([=](cudaStream_t st) {
+                conv3x3_first(pl->x, nullptr, w, b, o, Bn, Cin, R, R, nh, ACT_LRELU02, st);
+                return (int)cudaGetLastError();
+            });
+        }
+        const int cin[6] = {nh, nh, nh, 2 * nh, 2 * nh, 2 * nh};
+        const int cout[6] = {nh, nh, 2 * nh, 2 * nh, 2 * nh, 2 * nh};
+        const bool down[6] = {true, false, true, false, true, false};
+        for (int i = 0; i < 6; ++i) {
+            const std::string p = "blocks." + std::to_string(i);
+            const int H = h.H, W = h.W, Ci = cin[i], Co = cout[i];
+            const bool has_skip = (Ci != Co) || down[i];
+            bf16* h1 = (bf16*)scratch(1, (size_t)B * H * W * Co * 2);
+            {
+                dxmi_gemm_desc d = conv_desc(H, W);
+                set_src(d, 0, h.p, Ci, Ci);
+                add_seg(d, 0, 9);
+                d.b_ptr = packed_rows(p + ".conv1", {{{p + ".conv1.weight", 0, Ci}}}, nullptr, nullptr);
+                d.b_rows = Co;
+                d.b_ld = 9LL * Ci;
+                d.bias = f32(p + ".conv1.bias");
+                d.act = ACT_LRELU02;
+                d.out = h1;
+                d.ldo = Co;
+                gemm(d);
+            }
+            bf16* o = down[i] ? (bf16*)scratch(2, (size_t)B * H * W * Co * 2) : act_alloc(Co, H, W);
+            {
+                dxmi_gemm_desc d = conv_desc(H, W);
+                set_src(d, 0, h1, Co, Co);
+                add_seg(d, 0, 9);
+                long long K = 9LL * Co;
+                if (has_skip) {
+                    set_src(d, 1, h.p, Ci, Ci);
+                    add_seg(d, 1, 1);
+                    K += Ci;
+                    d.b_ptr = packed_rows(p + ".conv2+skip", {{{p + ".conv2.weight", 0, Co}, {p + ".skip.0.weight", 0, Ci}}},
+                                          nullptr, nullptr);
+                } else {
+                    d.b_ptr = packed_rows(p + ".conv2", {{{p + ".conv2.weight", 0, Co}}}, nullptr, nullptr);
+                    d.residual = h.p;
+                    d.ldr = Co;
+                }
+                d.b_rows = Co;
+                d.b_ld = K;
+                d.bias = f32(p + ".conv2.bias");
+                d.act = down[i] ? ACT_NONE : ACT_LRELU02;  // avg_pool comes before the activation (modules.py:96-99)
+                d.out = o;
+                d.ldo = Co;
+                gemm(d);
+            }
+            if (down[i]) {
+                Act nx{act_alloc(Co, H / 2, W / 2), Co, H / 2, W / 2};
+                bf16* dst = nx.p;
+                op([=](cudaStream_t st) {
+                    avgpool2(o, dst, Bn, H, W, Co, ACT_LRELU02, st);
+                    return (int)cudaGetLastError();
+                });
+                h = nx;
+            } else {
+                h = Act{o, Co, H, W};
+            }
+        }
+        {
+            const float* lw = f32("linear.weight");
+            const float* lb = f32("linear.bias");
+            const float* sw = a.learn_out_scale ? f32("out_scale.weight") : nullptr;
+            const float* sb = a.learn_out_scale ? f32("out_scale.bias") : nullptr;
+            const bf16* hp = h.p;
+            const int HW = h.H * h.W, C = h.C;
+            op([=](cudaStream_t st) {
+                value_head(hp, Bn, HW, C, lw, lb, sw, sb, pl->out, st);
+                return (int)cudaGetLastError();
+            });
+        }
+    }
+};
+
+int build_adm(Net& net, Plan& plan, bool dry, size_t* persist, size_t* scratch_max);  // engine_adm.cu
+
+template <typename BuilderT>
+static int build_two_pass(Net& net, Plan& plan) {
+    BuilderT dryb(net, plan, true);
+    dryb.build();
+    size_t total = dryb.off;
+    size_t base[Builder::NSLOT];
+    for (int s = 0; s < Builder::NSLOT; ++s) {
+        base[s] = total;
+        total += dryb.scratch_max[s];
+    }
+    plan.arena_bytes = total + 256;
+    cudaError_t e = cudaMalloc((void**)&plan.arena, plan.arena_bytes);
+    if (e != cudaSuccess) {
+        engine_set_error("cudaMalloc(%zu bytes) for the B=%d activation arena failed: %s", plan.arena_bytes, plan.B,
+                         cudaGetErrorString(e));
+        return (int)e;
+    }
+    BuilderT b(net, plan, false);
+    for (int s = 0; s < Builder::NSLOT; ++s) b.scratch_base[s] = base[s];
+    b.build();
+    if (b.err) return b.err;
+    if (b.off != dryb.off) {
+        engine_set_error("internal: dry/real arena mismatch (%zu vs %zu)", dryb.off, b.off);
+        return -21;
+    }
+    return 0;
+}
+
+int build_plan(Net& net, Plan& plan) {
+    switch (net.a.arch) {
+        case DXMI_ARCH_DDPM_UNET: return build_two_pass<DdpmBuilder>(net, plan);
+        case DXMI_ARCH_IGEBM_V2: return build_two_pass<IgebmBuilder>(net, plan);
+        default: engine_set_error("architecture %d not implemented yet", net.a.arch); return -22;
+    }
+}
+
+}  // namespace dxmi

@@ -1,0 +1,78 @@
+// Network plans: a Net owns the borrowed state_dict tensors, their packed bf16 copies and one launch plan per
+// batch size.  A plan is a flat list of kernel launches (closures) over a bump-allocated activation arena; TMA
+// tensor maps are encoded once at plan-build time.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dxmi_b200.h"
+#include "gemm_op.cuh"
+#include "kernels.cuh"
+
+namespace dxmi {
+
+struct Bound {
+    const void* ptr = nullptr;
+    int dtype = DXMI_F32;
+    std::vector<int64_t> shape;
+};
+
+struct Act {  // NHWC bf16 activation
+    bf16* p = nullptr;
+    int C = 0, H = 0, W = 0;
+};
+
+struct Plan {
+    int B = 0;
+    std::vector<std::function<int(cudaStream_t)>> ops;
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    // per-call I/O (read by the closures at launch time)
+    const float* x = nullptr;
+    const float* x_scale = nullptr;
+    const float* t = nullptr;
+    const int64_t* y = nullptr;
+    float* out = nullptr;
+    long long launches_per_run = 0;
+    double gemm_flops = 0;
+    // rollout scratch (allocated with the plan)
+    float* eps = nullptr;   // [B, Cout, H, W]
+    float* tbuf = nullptr;  // [B]
+    float* coef = nullptr;  // [B, 8]
+};
+
+struct Net {
+    dxmi_arch_desc a;
+    int device = 0;
+    std::vector<std::string> keys;
+    std::unordered_map<std::string, std::vector<int64_t>> expect;
+    std::unordered_map<std::string, Bound> bound;
+    // packed / derived weights
+    std::unordered_map<std::string, void*> derived;  // name -> device buffer (owned)
+    std::vector<std::function<void(cudaStream_t)>> pack_jobs;
+    std::vector<void*> owned;
+    bool finalized = false;
+    std::map<int, std::unique_ptr<Plan>> plans;
+    ~Net();
+};
+
+// spec (expected keys) builders
+void spec_ddpm(Net& net);
+void spec_igebm(Net& net);
+void spec_adm(Net& net);
+
+// plan builders (dry = size-only pass)
+int build_plan(Net& net, Plan& plan);
+
+const char* engine_last_error();
+void engine_set_error(const char* fmt, ...);
+void count_launches(long long n);
+long long total_launches();
+
+}  // namespace dxmi

@@ -1,0 +1,117 @@
+// dxmi_gemm_desc (raw pointers + geometry) -> prepared tcgen05 launch (encoded TMA maps + grid).
+#include "gemm_op.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace dxmi {
+
+static int g_opt_block_n_256 = 1;
+void set_block_n_256(int v) { g_opt_block_n_256 = v; }
+
+static thread_local char g_op_err[512] = "";
+const char* gemm_op_last_error() { return g_op_err[0] ? g_op_err : gemm_last_error(); }
+
+int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
+    g_op_err[0] = 0;
+    ConvGemmParams& p = op->p;
+    memset(&p, 0, sizeof(p));
+    const int bw = d.out_W < 128 ? d.out_W : 128;
+    int bh = 128 / bw;
+    if (bh > d.out_H) bh = d.out_H;
+    const int bn = 128 / (bw * bh);
+    if (bw * bh * bn != 128 || d.out_W % bw || d.out_H % bh) {
+        snprintf(g_op_err, sizeof g_op_err, "unsupported output geometry %dx%d (need power-of-two tiles of 128 pixels)",
+                 d.out_H, d.out_W);
+        return -10;
+    }
+    p.bw = bw;
+    p.bh = bh;
+    p.bn = bn;
+    p.tiles_w = d.out_W / bw;
+    p.tiles_h = d.out_H / bh;
+    p.stride = d.stride > 0 ? d.stride : 1;
+    p.a_batched = d.a_batched;
+    p.b_batched = d.b_batched;
+    int m_tiles;
+    if (d.a_batched) {
+        m_tiles = p.tiles_w * p.tiles_h;
+        p.M_total = d.out_H * d.out_W;
+    } else {
+        const int n_blks = (d.N + bn - 1) / bn;
+        m_tiles = n_blks * p.tiles_w * p.tiles_h;
+        p.M_total = d.N * d.out_H * d.out_W;
+    }
+    long long k_total = 0;
+    p.nseg = d.nseg;
+    bool used[3] = {false, false, false};
+    for (int s = 0; s < d.nseg; ++s) {
+        const int src = d.seg_src[s];
+        if (src < 0 || src > 2 || d.a_C[src] % 64 != 0 || (d.seg_taps[s] != 1 && d.seg_taps[s] != 9)) {
+            snprintf(g_op_err, sizeof g_op_err, "bad K segment %d (src %d, C %d, taps %d): channels must be a multiple of 64",
+                     s, src, src >= 0 && src <= 2 ? d.a_C[src] : -1, d.seg_taps[s]);
+            return -11;
+        }
+        p.seg[s].map = src;
+        p.seg[s].ntaps = d.seg_taps[s];
+        p.seg[s].nchunks = d.a_C[src] / 64;
+        p.seg[s].pad = (d.seg_taps[s] == 9 && p.stride == 1) ? 1 : 0;
+        k_total += (long long)d.seg_taps[s] * d.a_C[src];
+        used[src] = true;
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!used[i]) continue;
+        const long long ld = d.a_ld[i];
+        // a strided (Downsample) conv only strides the 9-tap source
+        int r = make_act_map(&p.a_map[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.N, ld, ld * d.W, ld * d.W * d.H, bw, bh, bn,
+                             p.stride);
+        if (r) return r;
+    }
+    p.N_total = d.b_rows;
+    int block_n = d.block_n;
+    if (block_n == 0) {
+        if (d.softmax)
+            block_n = d.b_rows;
+        else if (d.b_rows % 256 == 0 && g_opt_block_n_256)
+            block_n = 256;
+        else if (d.b_rows >= 128)
+            block_n = 128;
+        else if (d.b_rows >= 64)
+            block_n = 64;
+        else
+            block_n = 32;
+    }
+    const int n_tiles = (d.b_rows + block_n - 1) / block_n;
+    int r = make_mat_map(&p.b_map, d.b_ptr, (int)k_total, d.b_rows, d.b_batched ? d.batch : 1, d.b_ld, d.b_batch_stride,
+                         block_n);
+    if (r) return r;
+
+    p.out = d.out;
+    p.ldo = d.ldo;
+    p.out_batch_stride = d.out_batch_stride;
+    p.out_fp32 = d.out_fp32;
+    p.bias = d.bias;
+    p.bias_along_m = d.bias_along_m;
+    p.rowvec = d.rowvec;
+    p.ldrv = d.ldrv;
+    p.rows_per_image = d.rows_per_image > 0 ? d.rows_per_image : 1;
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
+    p.ldr = d.ldr;
+    p.res_batch_stride = d.res_batch_stride;
+    p.act = d.act;
+    p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
+    p.softmax = d.softmax;
+
+    op->block_n = block_n;
+    op->m_tiles = m_tiles;
+    op->n_tiles = n_tiles;
+    op->batch = d.batch > 0 ? d.batch : 1;
+    op->flops = 2.0 * (double)p.M_total * op->batch * (double)d.b_rows * (double)k_total;
+    return 0;
+}
+
+int run_gemm(const GemmOp& op, cudaStream_t st) {
+    return launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
+}
+
+}  // namespace dxmi

@@ -1,0 +1,18 @@
+#pragma once
+#include "../../include/dxmi_b200.h"
+#include "gemm_tc.cuh"
+
+namespace dxmi {
+
+struct GemmOp {
+    ConvGemmParams p;
+    int block_n, m_tiles, n_tiles, batch;
+    double flops;  // algorithmic 2*M*N*K of this launch
+};
+
+int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op);
+int run_gemm(const GemmOp& op, cudaStream_t st);
+void set_block_n_256(int v);
+const char* gemm_op_last_error();
+
+}  // namespace dxmi

@@ -1,0 +1,72 @@
+// Implicit-GEMM convolution / batched GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   D[128 x BLOCK_N] (fp32, TMEM)  =  sum_k  A[128 x 64] (bf16, smem via TMA)  *  B[BLOCK_N x 64]^T (bf16, smem via TMA)
+//
+// A rows are *output pixels*.  A is never materialised as an im2col matrix: the activation tensor is
+// NHWC bf16 and described by a rank-4 TMA tensor map (c, w, h, n).  An output tile is a box of
+// bn x bh x bw = 128 pixels; for filter tap (r, s) the producer loads the same box shifted by
+// (r - pad, s - pad) and TMA zero-fills whatever falls outside the image, which *is* the conv padding.
+// The K loop runs over "segments" (source tensor, taps, channel chunks) so that
+//   * conv(cat[a, b])            = two segments over two tensor maps (no concat copy),
+//   * conv3x3(h) + conv1x1(x)    = one accumulator (ResnetBlock conv2 + nin_shortcut, unet_small.py:128-136),
+//   * stride-2 convs             = a tensor map with elementStrides = 2 (unet_small.py:69-73),
+//   * plain / batched GEMMs      = one segment with a single tap (attention, 1x1 convs).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace dxmi {
+
+struct GemmSeg {
+    int map;      // index into a_map[]
+    int ntaps;    // 1 or 9
+    int nchunks;  // channels / 64
+    int pad;      // 1 for 3x3 "same", 0 otherwise
+};
+
+enum GemmAct { ACT_NONE = 0, ACT_LRELU02 = 1, ACT_SILU = 2 };
+
+struct ConvGemmParams {
+    CUtensorMap a_map[3];
+    CUtensorMap b_map;
+    GemmSeg seg[3];
+    int nseg;
+    int stride;                // conv stride in w/h (1 or 2)
+    int bw, bh, bn;            // output-pixel box of one tile: bw*bh*bn == 128
+    int tiles_w, tiles_h;      // tiles per image along w / h
+    int M_total;               // valid rows per batch entry
+    int N_total;               // valid output columns
+    int a_batched, b_batched;  // does blockIdx.z index the n coordinate of A / the batch coordinate of B?
+    // ---- epilogue
+    void* out;                 // bf16 (or fp32 if out_fp32) [row * ldo + col]
+    long long out_batch_stride;
+    int ldo;
+    int out_fp32;
+    const float* bias;         // per column (or per row if bias_along_m), may be null
+    int bias_along_m;
+    const float* rowvec;       // per-image per-column add, [image * ldrv + col], may be null
+    int ldrv;
+    int rows_per_image;
+    const __nv_bfloat16* residual;  // same indexing as out (ld = ldr), may be null
+    long long res_batch_stride;
+    int ldr;
+    int act;
+    float alpha;               // accumulator scale (applied first)
+    int softmax;               // row softmax over the BLOCK_N columns (needs N_total == BLOCK_N)
+};
+
+// Launches the kernel; block_n in {32, 64, 128, 256}. Returns cudaError_t as int.
+int launch_conv_gemm(const ConvGemmParams& p, int block_n, int m_tiles, int n_tiles, int batch, cudaStream_t stream);
+
+// Host helper: encode a rank-4 (c, w, h, n) bf16 activation map. Strides in elements. Box = (64, bw*stride, bh*stride, bn).
+int make_act_map(CUtensorMap* out, const void* base, int C, int W, int H, int N, long long w_stride, long long h_stride,
+                 long long n_stride, int bw, int bh, int bn, int stride);
+// Host helper: encode a rank-3 (k, rows, batch) bf16 K-major operand map. Box = (64, box_rows, 1).
+int make_mat_map(CUtensorMap* out, const void* base, int K, int rows, int batch, long long row_stride,
+                 long long batch_stride, int box_rows);
+
+const char* gemm_last_error();
+
+}  // namespace dxmi

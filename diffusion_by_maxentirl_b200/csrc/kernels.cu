@@ -1,0 +1,708 @@
+// HBM-bound / small kernels of the DxMI sampler path. See kernels.cuh for contracts.
+#include "kernels.cuh"
+
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+namespace dxmi {
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float act_f(float v, int act) {
+    if (act == 1) return v > 0.f ? v : 0.2f * v;
+    if (act == 2) return silu_f(v);
+    return v;
+}
+
+struct alignas(16) bf16x8 {
+    __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __bfloat1622float2(p.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+    bf16x8 p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+__device__ __forceinline__ bf16x8 ld8(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+__device__ __forceinline__ void st8(bf16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum, result valid in thread 0 (blockDim.x multiple of 32, <= 1024)
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (w == 0) {
+        r = (l < (blockDim.x >> 5)) ? sh[l] : 0.f;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+}  // namespace
+
+// ============================================================================================ weight packing
+
+template <typename T>
+__global__ void pack_conv_weight_k(const T* __restrict__ w, int Cout, int Cin, int taps, int c_off, int c_cnt,
+                                   bf16* __restrict__ dst, long long ldk, long long k_off) {
+    const long long total = (long long)Cout * taps * c_cnt;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c_cnt);
+        const long long r = i / c_cnt;
+        const int tap = (int)(r % taps);
+        const int o = (int)(r / taps);
+        const float v = (float)w[((long long)o * Cin + c_off + cc) * taps + tap];
+        dst[o * ldk + k_off + (long long)tap * c_cnt + cc] = __float2bfloat16_rn(v);
+    }
+}
+
+void pack_conv_weight(const void* w, int w_is_half, int Cout, int Cin, int kh, int kw, int c_off, int c_cnt, bf16* dst,
+                      long long ldk, long long k_off, cudaStream_t st) {
+    const long long total = (long long)Cout * kh * kw * c_cnt;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    if (w_is_half)
+        pack_conv_weight_k<__half><<<blocks, 256, 0, st>>>((const __half*)w, Cout, Cin, kh * kw, c_off, c_cnt, dst, ldk, k_off);
+    else
+        pack_conv_weight_k<float><<<blocks, 256, 0, st>>>((const float*)w, Cout, Cin, kh * kw, c_off, c_cnt, dst, ldk, k_off);
+}
+
+template <typename T>
+__global__ void cast_to_f32_k(const T* __restrict__ s, float* __restrict__ d, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        d[i] = (float)s[i];
+}
+void cast_to_f32(const void* src, int src_is_half, float* dst, long long n, cudaStream_t st) {
+    const int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
+    if (src_is_half)
+        cast_to_f32_k<__half><<<blocks, 256, 0, st>>>((const __half*)src, dst, n);
+    else
+        cast_to_f32_k<float><<<blocks, 256, 0, st>>>((const float*)src, dst, n);
+}
+
+// ============================================================================================ first / last conv
+
+// block = 256 threads; thread -> (pixel lane, 8-channel group). Weights staged in smem as [tap*Cin + ci][Cout].
+__global__ void conv3x3_first_k(const float* __restrict__ x, const float* __restrict__ in_scale,
+                                const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out, int N,
+                                int Cin, int H, int W, int Cout, int act) {
+    extern __shared__ float sw[];  // [9*Cin][Cout] + bias[Cout]
+    const int K = 9 * Cin;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+        const int o = i % Cout, k = i / Cout;  // k = tap*Cin + ci
+        const int tap = k / Cin, ci = k % Cin;
+        sw[i] = w[((long long)o * Cin + ci) * 9 + tap];
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[K * Cout + i] = b ? b[i] : 0.f;
+    __syncthreads();
+
+    const int groups = Cout / 8;
+    const int plane = blockDim.x / groups;
+    const int g = threadIdx.x % groups;
+    const int pl = threadIdx.x / groups;
+    if (pl >= plane) return;
+    const long long HW = (long long)H * W;
+    const long long total = (long long)N * HW;
+    for (long long p = blockIdx.x * (long long)plane + pl; p < total; p += (long long)gridDim.x * plane) {
+        const int n = (int)(p / HW);
+        const int hw = (int)(p % HW);
+        const int h = hw / W, wx = hw % W;
+        const float sc = in_scale ? in_scale[n] : 1.f;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = sw[K * Cout + g * 8 + j];
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h + tap / 3 - 1, ww = wx + tap % 3 - 1;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float xv = x[((long long)n * Cin + ci) * HW + (long long)hh * W + ww] * sc;
+                const float* wr = sw + (tap * Cin + ci) * Cout + g * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = act_f(acc[j], act);
+        st8(out + p * Cout + g * 8, pack8(acc));
+    }
+}
+
+void conv3x3_first(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, int N, int Cin,
+                   int H, int W, int Cout, int act, cudaStream_t st) {
+    const int groups = Cout / 8;
+    const int plane = 256 / groups;
+    const long long total = (long long)N * H * W;
+    long long blocks = (total + plane - 1) / plane;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
+    conv3x3_first_k<<<(int)blocks, 256, smem, st>>>(x, in_scale, w, b, out, N, Cin, H, W, Cout, act);
+}
+
+// One warp per output pixel; lanes stride over (tap, 8-channel vector) work items. Weights in smem [o][tap][C].
+__global__ void conv3x3_last_k(const bf16* __restrict__ hin, const float* __restrict__ w, const float* __restrict__ b,
+                               float* __restrict__ out, int N, int C, int H, int W, int Cout) {
+    extern __shared__ float sw[];  // [Cout][9][C]
+    for (int i = threadIdx.x; i < Cout * 9 * C; i += blockDim.x) {
+        const int c = i % C;
+        const int tap = (i / C) % 9;
+        const int o = i / (9 * C);
+        sw[i] = w[((long long)o * C + c) * 9 + tap];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long HW = (long long)H * W;
+    const long long total = (long long)N * HW;
+    const int CV = C / 8;
+    for (long long p = blockIdx.x * (long long)warps_per_block + (threadIdx.x >> 5); p < total;
+         p += (long long)gridDim.x * warps_per_block) {
+        const int n = (int)(p / HW);
+        const int hw = (int)(p % HW);
+        const int h = hw / W, wx = hw % W;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int item = lane; item < 9 * CV; item += 32) {
+            const int tap = item / CV, cv = item % CV;
+            const int hh = h + tap / 3 - 1, ww = wx + tap % 3 - 1;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            float f[8];
+            unpack8(ld8(hin + ((long long)n * HW + (long long)hh * W + ww) * C + cv * 8), f);
+            for (int o = 0; o < Cout; ++o) {
+                const float* wr = sw + (o * 9 + tap) * C + cv * 8;
+                float s = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s = fmaf(f[j], wr[j], s);
+                acc[o] += s;
+            }
+        }
+        for (int o = 0; o < Cout; ++o) {
+            const float s = warp_sum(acc[o]);
+            if (lane == 0) out[((long long)n * Cout + o) * HW + hw] = s + (b ? b[o] : 0.f);
+        }
+    }
+}
+
+void conv3x3_last(const bf16* h, const float* w, const float* b, float* out, int N, int C, int H, int W, int Cout,
+                  cudaStream_t st) {
+    const long long total = (long long)N * H * W;
+    long long blocks = (total + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    const size_t smem = (size_t)Cout * 9 * C * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv3x3_last_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        configured = true;
+    }
+    conv3x3_last_k<<<(int)blocks, 256, smem, st>>>(h, w, b, out, N, C, H, W, Cout);
+}
+
+// ============================================================================================ GroupNorm
+
+int gn_num_slabs(int N, int HW) {
+    int slabs = 1;
+    while (N * slabs < 592 && HW / (slabs * 2) >= 16) slabs *= 2;
+    return slabs;
+}
+
+static constexpr int GN_THREADS = 256;
+
+__device__ __forceinline__ const bf16* gn_src(const bf16* x1, int C1, int ld1, const bf16* x2, int ld2, long long pix,
+                                              int c) {
+    return (c < C1) ? x1 + pix * ld1 + c : x2 + pix * ld2 + (c - C1);
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_k(const bf16* __restrict__ x1, int C1, int ld1,
+                                                        const bf16* __restrict__ x2, int C2, int ld2, int HW, int groups,
+                                                        float* __restrict__ partial, int slabs) {
+    __shared__ float s_sum[GN_THREADS * 8];
+    __shared__ float s_sq[GN_THREADS * 8];
+    const int C = C1 + C2;
+    const int CV = C / 8;
+    const int PL = GN_THREADS / CV;
+    const int n = blockIdx.x, slab = blockIdx.y;
+    const int pix_per_slab = HW / slabs;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+    if (pl < PL) {
+        const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
+        for (int p = pl; p < pix_per_slab; p += PL) {
+            float f[8];
+            unpack8(ld8(gn_src(x1, C1, ld1, x2, ld2, base + p, cv * 8)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sum[j] += f[j];
+                sq[j] = fmaf(f[j], f[j], sq[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s_sum[pl * C + cv * 8 + j] = sum[j];
+            s_sq[pl * C + cv * 8 + j] = sq[j];
+        }
+    }
+    __syncthreads();
+    // per-group reduction in a fixed order (deterministic): 2 * groups threads
+    const int cpg = C / groups;
+    if (threadIdx.x < 2 * groups) {
+        const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const float* src = which ? s_sq : s_sum;
+        float a = 0.f;
+        for (int q = 0; q < PL; ++q)
+            for (int c = 0; c < cpg; ++c) a += src[q * C + g * cpg + c];
+        partial[((long long)n * slabs + slab) * (2 * groups) + g * 2 + which] = a;
+    }
+}
+
+void gn_stats(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
+              float* partial, int slabs, cudaStream_t st) {
+    dim3 grid(N, slabs);
+    gn_stats_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, groups, partial, slabs);
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_k(const bf16* __restrict__ x1, int C1, int ld1,
+                                                        const bf16* __restrict__ x2, int C2, int ld2, int HW, int groups,
+                                                        float eps, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ film,
+                                                        int film_ld, int silu, const float* __restrict__ partial,
+                                                        int slabs, bf16* __restrict__ out) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int C = C1 + C2;
+    const int CV = C / 8;
+    const int PL = GN_THREADS / CV;
+    const int n = blockIdx.x, slab = blockIdx.y;
+    const int pix_per_slab = HW / slabs;
+    const int cpg = C / groups;
+    if (threadIdx.x < groups) {
+        float s = 0.f, q = 0.f;
+        for (int i = 0; i < slabs; ++i) {
+            s += partial[((long long)n * slabs + i) * (2 * groups) + threadIdx.x * 2];
+            q += partial[((long long)n * slabs + i) * (2 * groups) + threadIdx.x * 2 + 1];
+        }
+        const float cnt = (float)cpg * (float)HW;
+        const float mean = s / cnt;
+        const float var = fmaxf(q / cnt - mean * mean, 0.f);
+        s_mean[threadIdx.x] = mean;
+        s_rstd[threadIdx.x] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    if (pl >= PL) return;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j;
+        const int g = c / cpg;
+        float aa = s_rstd[g] * gamma[c];
+        float bb = beta[c] - s_mean[g] * aa;
+        if (film) {
+            const float sc = 1.f + film[(long long)n * film_ld + c];
+            const float sh = film[(long long)n * film_ld + C + c];
+            aa *= sc;
+            bb = bb * sc + sh;
+        }
+        a[j] = aa;
+        b[j] = bb;
+    }
+    const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
+    for (int p = pl; p < pix_per_slab; p += PL) {
+        float f[8];
+        unpack8(ld8(gn_src(x1, C1, ld1, x2, ld2, base + p, cv * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = fmaf(f[j], a[j], b[j]);
+            f[j] = silu ? silu_f(v) : v;
+        }
+        st8(out + (base + p) * C + cv * 8, pack8(f));
+    }
+}
+
+void gn_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups, float eps,
+              const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* partial,
+              int slabs, bf16* out, cudaStream_t st) {
+    dim3 grid(N, slabs);
+    gn_apply_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, groups, eps, gamma, beta, film, film_ld, silu,
+                                             partial, slabs, out);
+}
+
+// ============================================================================================ small dense helpers
+
+__global__ void timestep_embedding_k(const float* __restrict__ t, float* __restrict__ out, int N, int dim, int order) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * half) return;
+    const int n = i / half, j = i % half;
+    // same fp32 arithmetic as the reference: exp(arange * -(ln 1e4 / denom)) then t * freq
+    float freq;
+    if (order == 0) {
+        const float e = logf(10000.f) / (float)(half - 1);
+        freq = expf((float)j * -e);
+    } else {
+        freq = expf(-logf(10000.f) * (float)j / (float)half);
+    }
+    const float a = t[n] * freq;
+    const float s = sinf(a), c = cosf(a);
+    if (order == 0) {
+        out[(long long)n * dim + j] = s;
+        out[(long long)n * dim + half + j] = c;
+    } else {
+        out[(long long)n * dim + j] = c;
+        out[(long long)n * dim + half + j] = s;
+    }
+}
+void timestep_embedding(const float* t, float* out, int N, int dim, int order, cudaStream_t st) {
+    const int total = N * (dim / 2);
+    timestep_embedding_k<<<(total + 127) / 128, 128, 0, st>>>(t, out, N, dim, order);
+}
+
+static constexpr int LIN_ROWS = 16;
+// block = 8 warps; each warp produces one output column for LIN_ROWS rows; x tile staged (activated) in smem.
+__global__ void linear_f32_k(const float* __restrict__ x, int ldx, const float* __restrict__ W,
+                             const float* __restrict__ b, float* __restrict__ y, int ldy, int N, int K, int O,
+                             int act_in, int act_out) {
+    extern __shared__ float sx[];  // [LIN_ROWS][K]
+    const int row0 = blockIdx.y * LIN_ROWS;
+    for (int i = threadIdx.x; i < LIN_ROWS * K; i += blockDim.x) {
+        const int r = i / K, k = i % K;
+        float v = (row0 + r < N) ? x[(long long)(row0 + r) * ldx + k] : 0.f;
+        sx[i] = act_f(v, act_in);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= O) return;
+    float acc[LIN_ROWS];
+#pragma unroll
+    for (int r = 0; r < LIN_ROWS; ++r) acc[r] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = W[(long long)o * K + k];
+#pragma unroll
+        for (int r = 0; r < LIN_ROWS; ++r) acc[r] = fmaf(wv, sx[r * K + k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < LIN_ROWS; ++r) {
+        const float s = warp_sum(acc[r]);
+        if (lane == 0 && row0 + r < N) y[(long long)(row0 + r) * ldy + o] = act_f(s + (b ? b[o] : 0.f), act_out);
+    }
+}
+void linear_f32(const float* x, int ldx, const float* W, const float* b, float* y, int ldy, int N, int K, int O,
+                int act_in, int act_out, cudaStream_t st) {
+    dim3 grid((O + 7) / 8, (N + LIN_ROWS - 1) / LIN_ROWS);
+    const size_t smem = (size_t)LIN_ROWS * K * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(linear_f32_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        configured = true;
+    }
+    linear_f32_k<<<grid, 256, smem, st>>>(x, ldx, W, b, y, ldy, N, K, O, act_in, act_out);
+}
+
+__global__ void embedding_add_k(float* __restrict__ emb, const float* __restrict__ table,
+                                const long long* __restrict__ idx, int N, int D) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)N * D) return;
+    const int n = (int)(i / D), d = (int)(i % D);
+    emb[i] += table[idx[n] * D + d];
+}
+void embedding_add(float* emb, const float* table, const long long* idx, int N, int D, cudaStream_t st) {
+    const long long total = (long long)N * D;
+    embedding_add_k<<<(int)((total + 255) / 256), 256, 0, st>>>(emb, table, idx, N, D);
+}
+
+// ============================================================================================ resampling
+
+__global__ void upsample2x_k(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int CV) {
+    const long long total = (long long)N * (2 * H) * (2 * W) * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long r = i / CV;
+        const int ow = (int)(r % (2 * W));
+        r /= (2 * W);
+        const int oh = (int)(r % (2 * H));
+        const int n = (int)(r / (2 * H));
+        const bf16x8 v = ld8(x + ((((long long)n * H + (oh >> 1)) * W + (ow >> 1)) * CV + cv) * 8);
+        st8(out + i * 8, v);
+    }
+}
+void upsample2x(const bf16* x, bf16* out, int N, int H, int W, int C, cudaStream_t st) {
+    const long long total = (long long)N * 4 * H * W * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    upsample2x_k<<<(int)blocks, 256, 0, st>>>(x, out, N, H, W, C / 8);
+}
+
+__global__ void avgpool2_k(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int CV, int act) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)N * OH * OW * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long r = i / CV;
+        const int ow = (int)(r % OW);
+        r /= OW;
+        const int oh = (int)(r % OH);
+        const int n = (int)(r / OH);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float f[8];
+                unpack8(ld8(x + ((((long long)n * H + 2 * oh + dy) * W + 2 * ow + dx) * CV + cv) * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = act_f(acc[j] * 0.25f, act);
+        st8(out + i * 8, pack8(acc));
+    }
+}
+void avgpool2(const bf16* x, bf16* out, int N, int H, int W, int C, int act, cudaStream_t st) {
+    const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    avgpool2_k<<<(int)blocks, 256, 0, st>>>(x, out, N, H, W, C / 8, act);
+}
+
+// ============================================================================================ tiny attention
+
+// one CTA per (image, head); q/k/v tiles in smem as bf16, scores fp32. seq <= 64.
+__global__ void attn_small_k(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, int ld,
+                             bf16* __restrict__ out, int ldo, int heads, int seq, int d, float scale) {
+    extern __shared__ uint8_t smraw[];
+    bf16* sq = reinterpret_cast<bf16*>(smraw);
+    bf16* sk = sq + seq * d;
+    bf16* sv = sk + seq * d;
+    float* ss = reinterpret_cast<float*>(sv + seq * d);  // [seq][seq]
+    const int n = blockIdx.x / heads, h = blockIdx.x % heads;
+    const long long base = (long long)n * seq * ld + (long long)h * d;
+    for (int i = threadIdx.x; i < seq * d; i += blockDim.x) {
+        const int t = i / d, c = i % d;
+        sq[i] = q[base + (long long)t * ld + c];
+        sk[i] = k[base + (long long)t * ld + c];
+        sv[i] = v[base + (long long)t * ld + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < seq * seq; i += blockDim.x) {
+        const int a = i / seq, b = i % seq;
+        float s = 0.f;
+        for (int c = 0; c < d; ++c) s = fmaf(__bfloat162float(sq[a * d + c]), __bfloat162float(sk[b * d + c]), s);
+        ss[i] = s * scale;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int a = threadIdx.x >> 5; a < seq; a += blockDim.x >> 5) {
+        float m = -CUDART_INF_F;
+        for (int b = lane; b < seq; b += 32) m = fmaxf(m, ss[a * seq + b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float l = 0.f;
+        for (int b = lane; b < seq; b += 32) {
+            const float e = __expf(ss[a * seq + b] - m);
+            ss[a * seq + b] = e;
+            l += e;
+        }
+        l = warp_sum(l);
+        const float inv = 1.f / l;
+        for (int b = lane; b < seq; b += 32) ss[a * seq + b] *= inv;
+    }
+    __syncthreads();
+    const long long obase = (long long)n * seq * ldo + (long long)h * d;
+    for (int i = threadIdx.x; i < seq * d; i += blockDim.x) {
+        const int a = i / d, c = i % d;
+        float s = 0.f;
+        for (int b = 0; b < seq; ++b) s = fmaf(ss[a * seq + b], __bfloat162float(sv[b * d + c]), s);
+        out[obase + (long long)a * ldo + c] = __float2bfloat16_rn(s);
+    }
+}
+void attn_small(const bf16* q, const bf16* k, const bf16* v, int ld, bf16* out, int ldo, int N, int heads, int seq,
+                int d, float scale, cudaStream_t st) {
+    const size_t smem = (size_t)3 * seq * d * sizeof(bf16) + (size_t)seq * seq * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(attn_small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        configured = true;
+    }
+    attn_small_k<<<N * heads, 256, smem, st>>>(q, k, v, ld, out, ldo, heads, seq, d, scale);
+}
+
+// ============================================================================================ sampler transitions
+
+// one CTA per sample (logp is a per-sample reduction).
+__global__ void var_step_k(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z,
+                           const float* __restrict__ a, const float* __restrict__ c, const float* __restrict__ sigma,
+                           float* __restrict__ xn, float* __restrict__ mean, float* __restrict__ control,
+                           float* __restrict__ logp, int CHW) {
+    __shared__ float sh[32];
+    const int n = blockIdx.x;
+    const float an = a[n], cn = c[n], sn = sigma[n];
+    const float inv2var = 1.f / (2.f * sn * sn);
+    const float cst = -logf(sn) - 0.9189385332046727f;  // -ln(sigma) - 0.5 ln(2 pi)
+    const long long base = (long long)n * CHW;
+    float acc = 0.f;
+    for (int i = threadIdx.x * 4; i < CHW; i += blockDim.x * 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + base + i);
+        const float4 ev = *reinterpret_cast<const float4*>(eps + base + i);
+        const float4 zv = *reinterpret_cast<const float4*>(z + base + i);
+        float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w};
+        float ctl[4], mu[4], nx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float xm = xs[j] * an;       // x *= x_prev_multiplier
+            ctl[j] = cn * es[j];               // control = c * eps
+            mu[j] = xm + ctl[j];               // pred_mean
+            nx[j] = xm + (ctl[j] + sn * zs[j]);  // x += control + sigma * z   (reference association order)
+            const float dlt = nx[j] - mu[j];
+            acc += -(dlt * dlt) * inv2var + cst;
+        }
+        *reinterpret_cast<float4*>(xn + base + i) = make_float4(nx[0], nx[1], nx[2], nx[3]);
+        if (mean) *reinterpret_cast<float4*>(mean + base + i) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+        if (control) *reinterpret_cast<float4*>(control + base + i) = make_float4(ctl[0], ctl[1], ctl[2], ctl[3]);
+    }
+    const float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0 && logp) logp[n] = tot / (float)CHW;
+}
+void var_step(const float* x, const float* eps, const float* z, const float* a, const float* c, const float* sigma,
+              float* xn, float* mean, float* control, float* logp, int N, int CHW, cudaStream_t st) {
+    var_step_k<<<N, 256, 0, st>>>(x, eps, z, a, c, sigma, xn, mean, control, logp, CHW);
+}
+
+__global__ void edm_step_k(const float* __restrict__ x, const float* __restrict__ F, const float* __restrict__ z,
+                           const float* __restrict__ coef, float* __restrict__ xn, float* __restrict__ mean, int CHW4,
+                           long long total4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / CHW4);
+        const float c_skip = coef[n * 5 + 0], c_out = coef[n * 5 + 1], sg = coef[n * 5 + 2], sd = coef[n * 5 + 3],
+                    sn = coef[n * 5 + 4];
+        const float4 xv = reinterpret_cast<const float4*>(x)[i];
+        const float4 fv = reinterpret_cast<const float4*>(F)[i];
+        const float4 zv = reinterpret_cast<const float4*>(z)[i];
+        float xs[4] = {xv.x, xv.y, xv.z, xv.w}, fs[4] = {fv.x, fv.y, fv.z, fv.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w};
+        float mu[4], nx[4];
+        const float dt = sd - sg;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float D = c_out * fs[j] + c_skip * xs[j];
+            const float dd = (xs[j] - D) / sg;
+            mu[j] = xs[j] + dd * dt;
+            nx[j] = mu[j] + zs[j] * sn;
+        }
+        reinterpret_cast<float4*>(xn)[i] = make_float4(nx[0], nx[1], nx[2], nx[3]);
+        if (mean) reinterpret_cast<float4*>(mean)[i] = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    }
+}
+void edm_step(const float* x, const float* F, const float* z, const float* coef, float* xn, float* mean, int N, int CHW,
+              cudaStream_t st) {
+    const long long total4 = (long long)N * CHW / 4;
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    edm_step_k<<<(int)blocks, 256, 0, st>>>(x, F, z, coef, xn, mean, CHW / 4, total4);
+}
+
+// ============================================================================================ value head
+
+__global__ void value_head_k(const bf16* __restrict__ h, int HW, int C, const float* __restrict__ lin_w,
+                             const float* __restrict__ lin_b, const float* __restrict__ scale_w,
+                             const float* __restrict__ scale_b, float* __restrict__ out) {
+    __shared__ float sh[32];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < HW; ++p) s += fmaxf(__bfloat162float(h[((long long)n * HW + p) * C + c]), 0.f);
+        acc = fmaf(s, lin_w[c], acc);
+    }
+    const float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+        float v = tot + lin_b[0];
+        if (scale_w) v = v * scale_w[0] + scale_b[0];
+        out[n] = v;
+    }
+}
+void value_head(const bf16* h, int N, int HW, int C, const float* lin_w, const float* lin_b, const float* scale_w,
+                const float* scale_b, float* out, cudaStream_t st) {
+    value_head_k<<<N, 256, 0, st>>>(h, HW, C, lin_w, lin_b, scale_w, scale_b, out);
+}
+
+// ============================================================================================ tiny utilities
+
+__global__ void fill_f32_k(float* p, float v, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+void fill_f32(float* p, float v, long long n, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    fill_f32_k<<<(int)blocks, 256, 0, st>>>(p, v, n);
+}
+__global__ void vec_add_f32_k(const float* a, const float* b, float* out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = a[i] + b[i];
+}
+void vec_add_f32(const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    vec_add_f32_k<<<(int)blocks, 256, 0, st>>>(a, b, out, n);
+}
+
+// ============================================================================================ layout helpers
+
+__global__ void nhwc_bf16_to_nchw_f32_k(const bf16* __restrict__ x, float* __restrict__ out, int C, int HW, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        long long r = i / HW;
+        const int c = (int)(r % C);
+        const long long n = r / C;
+        out[i] = __bfloat162float(x[(n * HW + p) * C + c]);
+    }
+}
+void nhwc_bf16_to_nchw_f32(const bf16* x, float* out, int N, int C, int HW, cudaStream_t st) {
+    const long long total = (long long)N * C * HW;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    nhwc_bf16_to_nchw_f32_k<<<(int)blocks, 256, 0, st>>>(x, out, C, HW, total);
+}
+__global__ void nchw_f32_to_nhwc_bf16_k(const float* __restrict__ x, bf16* __restrict__ out, int C, int HW, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int p = (int)(r % HW);
+        const long long n = r / HW;
+        out[i] = __float2bfloat16_rn(x[(n * C + c) * HW + p]);
+    }
+}
+void nchw_f32_to_nhwc_bf16(const float* x, bf16* out, int N, int C, int HW, cudaStream_t st) {
+    const long long total = (long long)N * C * HW;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    nchw_f32_to_nhwc_bf16_k<<<(int)blocks, 256, 0, st>>>(x, out, C, HW, total);
+}
+
+__global__ void quantize_u8_k(const float* __restrict__ x, uint8_t* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = (x[i] + 1.f) * 127.5f;
+        v = fminf(fmaxf(v, 0.f), 255.f);
+        out[i] = (uint8_t)v;  // truncation == torch .to(uint8)
+    }
+}
+void quantize_u8(const float* x, uint8_t* out, long long n, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    quantize_u8_k<<<(int)blocks, 256, 0, st>>>(x, out, n);
+}
+
+}  // namespace dxmi

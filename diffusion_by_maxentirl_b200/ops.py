@@ -1,0 +1,134 @@
+"""Kernel-level operators of libdxmi_b200.so on torch tensors (used by the parity tests and by profiling scripts).
+
+Layouts: activations are NHWC bf16 (`[N, H, W, C]` contiguous, or channel slices of such a tensor); packed weights are
+bf16 `[Cout, K]` with `K = sum_segments taps * C_segment` (tap-major, channel-minor inside a segment).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def pack_conv_weight(w, parts=None):
+    """OIHW conv weight(s) -> bf16 [Cout, K].  `parts` = list of (weight, c_off, c_cnt) concatenated along K."""
+    if parts is None:
+        parts = [(w, 0, w.shape[1])]
+    cout = parts[0][0].shape[0]
+    K = sum(p[0].shape[2] * p[0].shape[3] * p[2] for p in parts)
+    dst = torch.empty(cout, K, dtype=torch.bfloat16, device=parts[0][0].device)
+    k_off = 0
+    for wt, c_off, c_cnt in parts:
+        wt = wt.contiguous()
+        dt = L.F16 if wt.dtype == torch.float16 else L.F32
+        assert wt.dtype in (torch.float16, torch.float32)
+        L.check(
+            L.lib().dxmi_op_pack_conv_weight(
+                L.ptr(wt), dt, wt.shape[0], wt.shape[1], wt.shape[2], wt.shape[3], c_off, c_cnt, L.ptr(dst), K, k_off,
+                L.stream_ptr(),
+            ),
+            "pack_conv_weight",
+        )
+        k_off += wt.shape[2] * wt.shape[3] * c_cnt
+    return dst
+
+
+def conv_gemm(
+    srcs,
+    segs,
+    w_packed,
+    N,
+    H,
+    W,
+    out_H=None,
+    out_W=None,
+    stride=1,
+    bias=None,
+    rowvec=None,
+    rows_per_image=None,
+    residual=None,
+    act=0,
+    out=None,
+    out_fp32=False,
+    block_n=0,
+    batch=1,
+    a_batched=False,
+    b_batched=False,
+    b_rows=None,
+    b_ld=None,
+    b_batch_stride=0,
+    ldo=None,
+    out_batch_stride=0,
+    bias_along_m=False,
+    alpha=1.0,
+    softmax=False,
+    res_batch_stride=0,
+):
+    """srcs: list of (tensor, C_used, ld) NHWC bf16 sources; segs: list of (src_index, taps)."""
+    d = L.GemmDesc()
+    for i, (t, c, ld) in enumerate(srcs):
+        assert t.dtype == torch.bfloat16
+        d.a_ptr[i] = t.data_ptr()
+        d.a_C[i] = c
+        d.a_ld[i] = ld
+    d.N, d.H, d.W = N, H, W
+    d.nseg = len(segs)
+    for i, (s, taps) in enumerate(segs):
+        d.seg_src[i] = s
+        d.seg_taps[i] = taps
+    d.stride = stride
+    d.out_H = out_H if out_H is not None else H
+    d.out_W = out_W if out_W is not None else W
+    d.b_ptr = w_packed.data_ptr()
+    d.b_rows = b_rows if b_rows is not None else w_packed.shape[-2]
+    d.b_ld = b_ld if b_ld is not None else w_packed.shape[-1]
+    d.b_batch_stride = b_batch_stride
+    d.batch = batch
+    d.a_batched = int(a_batched)
+    d.b_batched = int(b_batched)
+    rows = (d.out_H * d.out_W) if a_batched else N * d.out_H * d.out_W
+    if out is None:
+        shape = (batch, rows, d.b_rows) if batch > 1 else (rows, d.b_rows)
+        out = torch.empty(shape, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=w_packed.device)
+        if batch > 1:
+            out_batch_stride = rows * d.b_rows
+    d.out = out.data_ptr()
+    d.ldo = ldo if ldo is not None else d.b_rows
+    d.out_batch_stride = out_batch_stride
+    d.out_fp32 = int(out_fp32)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+        d.bias = bias.data_ptr()
+    d.bias_along_m = int(bias_along_m)
+    if rowvec is not None:
+        assert rowvec.dtype == torch.float32
+        d.rowvec = rowvec.data_ptr()
+        d.ldrv = rowvec.stride(0)
+    d.rows_per_image = rows_per_image if rows_per_image is not None else d.out_H * d.out_W
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16
+        d.residual = residual.data_ptr()
+        d.ldr = residual.shape[-1]
+        d.res_batch_stride = res_batch_stride
+    d.act = act
+    d.alpha = alpha
+    d.softmax = int(softmax)
+    d.block_n = block_n
+    L.check(L.lib().dxmi_op_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
+    return out
+
+
+def group_norm(x1, gamma, beta, eps, silu, x2=None, film=None, groups=32):
+    """GroupNorm(+SiLU)(+FiLM) over the channel concat of NHWC bf16 x1 (and x2) -> NHWC bf16."""
+    N, H, W, C1 = x1.shape
+    C2 = x2.shape[-1] if x2 is not None else 0
+    out = torch.empty(N, H, W, C1 + C2, dtype=torch.bfloat16, device=x1.device)
+    ws = torch.empty(L.lib().dxmi_op_gn_ws_floats(N, H * W, groups), dtype=torch.float32, device=x1.device)
+    L.check(
+        L.lib().dxmi_op_group_norm(
+            L.ptr(x1), C1, C1, L.ptr(x2), C2, C2, N, H * W, groups, eps, L.ptr(gamma), L.ptr(beta), L.ptr(film),
+            film.stride(0) if film is not None else 0, int(silu), L.ptr(ws), L.ptr(out), L.stream_ptr(),
+        ),
+        "group_norm",
+    )
+    return out

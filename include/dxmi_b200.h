@@ -1,0 +1,163 @@
+/*
+ * dxmi_b200.h - C ABI of the B200-native DxMI sampler-rollout path (libdxmi_b200.so).
+ *
+ * The reference (swyoon/Diffusion-by-MaxEntIRL) has NO native / FFI boundary: its hot path is three Python
+ * nn.Module-level interfaces.  This header is the boundary we introduce *underneath* those interfaces; every
+ * entry point names the reference call it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain C types only (no torch types); all pointers are CUDA device pointers unless marked "host";
+ * every call returns 0 on success or a negative/cuda error code and never throws; dxmi_last_error() gives the
+ * message; work is enqueued on the caller's stream and the library never calls cudaDeviceSynchronize();
+ * a handle is bound to one device and is not thread-safe (one process per GPU, like the reference under torchrun).
+ * Network inputs/outputs and sampler states are fp32 NCHW contiguous (the reference's layout); weights are
+ * borrowed by pointer in the reference's state_dict layout (OIHW fp32/fp16 convs, [out,in] linears) and re-packed
+ * to bf16 K-major on the device by dxmi_finalize()/dxmi_repack().
+ */
+#ifndef DXMI_B200_H
+#define DXMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dxmi_net_s* dxmi_net_t;
+typedef void* dxmi_stream_t; /* cudaStream_t */
+
+enum dxmi_arch_kind {
+    DXMI_ARCH_DDPM_UNET = 0, /* models/DxMI/unet_small.py:194-332  Model            */
+    DXMI_ARCH_ADM_UNET = 1,  /* models/cm/unet.py:523-790          UNetModel        */
+    DXMI_ARCH_IGEBM_V2 = 2   /* models/modules.py:104-163          IGEBMEncoderV2   */
+};
+
+enum dxmi_dtype { DXMI_F32 = 0, DXMI_F16 = 1, DXMI_I64 = 2 };
+
+/* Constructor arguments of the three reference networks (configs/.../T*.yaml), flattened. */
+typedef struct {
+    int arch;               /* dxmi_arch_kind */
+    int resolution;         /* DDPM: resolution; ADM: image_size; IGEBM: input H=W */
+    int in_channels;
+    int out_channels;
+    int ch;                 /* DDPM: ch; ADM: model_channels; IGEBM: nh */
+    int n_levels;
+    int ch_mult[8];
+    int num_res_blocks;
+    int n_attn;             /* number of entries in attn_resolutions */
+    int attn_resolutions[8];/* DDPM: feature-map sizes (16); ADM: downsample rates ds (image_size // res) */
+    int num_classes;        /* ADM: 0 = unconditional */
+    int num_head_channels;  /* ADM: 64 */
+    int num_heads;          /* ADM: used when num_head_channels == -1 */
+    int use_scale_shift_norm;
+    int resblock_updown;
+    int learn_out_scale;    /* IGEBM: out_scale Linear(1,1) present */
+} dxmi_arch_desc;
+
+/* -------------------------------------------------------------------------------------------- lifecycle */
+/* Replaces nn.Module construction (generate_cifar10.py:143, script_util.py:104-158, value: T10.yaml:20-31). */
+int dxmi_create(const dxmi_arch_desc* desc, int device, dxmi_net_t* out);
+void dxmi_destroy(dxmi_net_t net);
+/* Replaces load_state_dict()/parameters(): borrow one state_dict tensor (generate_cifar10.py:148-149). */
+int dxmi_bind_weight(dxmi_net_t net, const char* key, const void* dev_ptr, int dtype, const int64_t* shape, int ndim);
+/* Number of state_dict keys the architecture expects; key i is written to buf (for the host-side mirror). */
+int dxmi_num_weights(dxmi_net_t net);
+int dxmi_weight_key(dxmi_net_t net, int i, char* buf, int buflen);
+int dxmi_weight_shape(dxmi_net_t net, int i, int64_t* shape, int* ndim);
+/* Verify every expected key is bound and pack weights (bf16, K-major). Call again (or dxmi_repack) after an
+ * optimizer step changed the borrowed tensors (trainer.py:389). */
+int dxmi_finalize(dxmi_net_t net, dxmi_stream_t stream);
+int dxmi_repack(dxmi_net_t net, dxmi_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------- networks */
+/* unet_small.Model.forward(x, t) (unet_small.py:292-332) and UNetModel.forward(x, timesteps, y) (cm/unet.py:761-790).
+ * x [B,Cin,H,W] fp32, t [B] fp32, y [B] int64 or NULL, out [B,Cout,H,W] fp32.  x_scale: optional [B] fp32 factor
+ * applied to x on load (EDM c_in, karras_diffusion.py:349) or NULL. */
+int dxmi_unet_forward(dxmi_net_t net, const float* x, const float* x_scale, const float* t, const int64_t* y,
+                      float* out, int B, dxmi_stream_t stream);
+/* TimeIndependentValue.forward(x, t) -> IGEBMEncoderV2.forward (value.py:8-12, modules.py:142-163). out [B] fp32. */
+int dxmi_value_forward(dxmi_net_t net, const float* x, float* out, int B, dxmi_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------- transitions */
+/* One VARSampler transition given eps (var_sampler.py:262-289 / :375-404). a, c, sigma: per-sample [B] fp32.
+ * mean / control / logp may be NULL. */
+int dxmi_var_step(const float* x, const float* eps, const float* z, const float* a, const float* c,
+                  const float* sigma, float* x_next, float* mean, float* control, float* logp, int B, int chw,
+                  dxmi_stream_t stream);
+/* One OpenAIDiffusion transition given the raw net output F (openai_diffusion.py:75-94, karras_diffusion.py:350).
+ * coef [B,5] fp32 = {c_skip, c_out, sigma, sigma_down, sigma_noise}. mean may be NULL. */
+int dxmi_edm_step(const float* x, const float* F, const float* z, const float* coef, float* x_next, float* mean,
+                  int B, int chw, dxmi_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------- rollouts */
+/* VARSampler.sample() (var_sampler.py:411-428 -> VAR_sampling :204-297): the whole T-step loop in one call.
+ * sched (host) [T,4] fp32 rows {tau_i, a_i, c_i * adhoc_scale1, sigma_i} (Appendix E.1 of SURVEY.md);
+ * noise [T+1,B,C,H,W] fp32: noise[0] = x_0, noise[1+i] = z of step i (host-supplied noise is part of the parity
+ * contract); l_sample [T+1,B,C,H,W]; mean, control [T,B,C,H,W] or NULL; logp [T,B] or NULL. */
+int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, float* l_sample, float* mean,
+                     float* control, float* logp, int B, dxmi_stream_t stream);
+/* OpenAIDiffusion.sample() (openai_diffusion.py:101-127). sched (host) [T,7] fp32 rows
+ * {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down, sigma_noise}; noise[0] = x_0 (already scaled by sigma_max). */
+int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, const int64_t* y,
+                     float* l_sample, float* mean, int B, dxmi_stream_t stream);
+
+/* samples in [-1,1] -> uint8 ((x+1)*127.5 clamp), generate_large.py:43 */
+int dxmi_quantize_u8(const float* x, uint8_t* out, long long n, dxmi_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------- kernel-level ops
+ * (exposed for parity tests and profiling of the individual kernels) */
+typedef struct {
+    /* A: up to three NHWC bf16 sources sharing the same (N, H, W) */
+    const void* a_ptr[3];
+    int a_C[3];              /* channels used from each source */
+    int a_ld[3];             /* pixel stride in elements */
+    int N, H, W;             /* input images / spatial size */
+    int nseg;
+    int seg_src[3], seg_taps[3]; /* source index and 1|9 taps per K segment */
+    int stride;              /* 1 | 2 (2 = Downsample with pad (0,1,0,1), unet_small.py:69-73) */
+    int out_H, out_W;
+    /* B: packed bf16 [rows, K_total] (+ batch) */
+    const void* b_ptr;
+    int b_rows;
+    long long b_ld;
+    long long b_batch_stride;
+    int batch;               /* grid.z; 1 for convs */
+    int a_batched, b_batched;
+    /* epilogue */
+    void* out;
+    int ldo;
+    long long out_batch_stride;
+    int out_fp32;
+    const float* bias;
+    int bias_along_m;
+    const float* rowvec;
+    int ldrv;
+    int rows_per_image;
+    const void* residual;
+    int ldr;
+    long long res_batch_stride;
+    int act;                 /* 0 none, 1 leaky-relu(0.2), 2 silu */
+    float alpha;
+    int softmax;
+    int block_n;             /* 0 = auto */
+} dxmi_gemm_desc;
+
+int dxmi_op_conv_gemm(const dxmi_gemm_desc* d, dxmi_stream_t stream);
+int dxmi_op_pack_conv_weight(const void* w, int dtype, int Cout, int Cin, int kh, int kw, int c_off, int c_cnt,
+                             void* dst_bf16, long long ldk, long long k_off, dxmi_stream_t stream);
+int dxmi_op_group_norm(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int N, int HW, int groups,
+                       float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
+                       float* partial_ws, void* out, dxmi_stream_t stream);
+int dxmi_op_gn_ws_floats(int N, int HW, int groups);
+
+/* -------------------------------------------------------------------------------------------- misc */
+const char* dxmi_last_error(void);
+int dxmi_set_option(const char* name, int value); /* e.g. "block_n_256" */
+/* number of kernels launched by this library since process start (bench.py "gpu_launches") */
+long long dxmi_launch_count(void);
+size_t dxmi_workspace_bytes(dxmi_net_t net, int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXMI_B200_H */

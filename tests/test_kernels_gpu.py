@@ -1,0 +1,171 @@
+"""Kernel-level parity: the tcgen05 implicit-GEMM conv / batched GEMM and GroupNorm against torch fp32 math on the
+same bf16-rounded inputs.  Tolerances: outputs are bf16 (rel 2^-8 per element); we assert rel-L2 <= 4e-3 which is
+the bf16 output rounding floor, i.e. the accumulation itself must be exact to fp32."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def nhwc(x):  # NCHW fp32 -> NHWC bf16
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def ref_conv(x_bf, w, b=None, stride=1, pad=1, asym=False):
+    """x_bf: NHWC bf16; w OIHW fp32 (rounded to bf16 like the packed copy)."""
+    x = x_bf.float().permute(0, 3, 1, 2)
+    wq = w.to(torch.bfloat16).float()
+    if asym:
+        x = F.pad(x, (0, 1, 0, 1))
+        y = F.conv2d(x, wq, b, stride=2, padding=0)
+    else:
+        y = F.conv2d(x, wq, b, stride=stride, padding=pad)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffusion_by_maxentirl_b200 import ops as o
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return o
+
+
+@pytest.mark.parametrize(
+    "N,H,Cin,Cout,block_n",
+    [
+        (2, 16, 128, 128, 0),
+        (2, 32, 128, 128, 128),
+        (4, 16, 256, 256, 256),
+        (4, 16, 256, 256, 128),
+        (8, 8, 256, 256, 0),
+        (3, 8, 256, 256, 128),   # odd image count: tile spans 2 images, tail masked
+        (16, 4, 256, 256, 0),
+        (5, 4, 512, 256, 0),
+        (2, 16, 64, 64, 64),
+        (2, 64, 192, 192, 64),   # ImageNet-64 geometry
+    ],
+)
+def test_conv3x3(ops, N, H, Cin, Cout, block_n):
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = nhwc(torch.randn(N, Cin, H, H, device=dev))
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin**0.5)
+    b = torch.randn(Cout, device=dev)
+    wp = ops.pack_conv_weight(w)
+    y = ops.conv_gemm([(x, Cin, Cin)], [(0, 9)], wp, N, H, H, bias=b, block_n=block_n)
+    torch.cuda.synchronize()
+    ref = ref_conv(x, w, b)
+    assert rel_l2(y.view(N, H, H, Cout), ref) < 4e-3
+    yf = ops.conv_gemm([(x, Cin, Cin)], [(0, 9)], wp, N, H, H, bias=b, block_n=block_n, out_fp32=True)
+    assert rel_l2(yf.view(N, H, H, Cout), ref) < 2e-5
+
+
+def test_conv1x1_plain_gemm(ops):
+    torch.manual_seed(1)
+    dev = "cuda"
+    N, H, Cin, Cout = 4, 16, 256, 768
+    x = nhwc(torch.randn(N, Cin, H, H, device=dev))
+    w = torch.randn(Cout, Cin, 1, 1, device=dev) / Cin**0.5
+    b = torch.randn(Cout, device=dev)
+    wp = ops.pack_conv_weight(w)
+    y = ops.conv_gemm([(x, Cin, Cin)], [(0, 1)], wp, N, H, H, bias=b, out_fp32=True)
+    ref = ref_conv(x, w, b, pad=0)
+    assert rel_l2(y.view(N, H, H, Cout), ref) < 2e-5
+
+
+@pytest.mark.parametrize("N,H,C", [(2, 32, 128), (4, 16, 256), (8, 8, 256)])
+def test_conv_stride2_asym_pad(ops, N, H, C):
+    """Downsample: pad (0,1,0,1) then 3x3 stride 2 (unet_small.py:69-73) through a TMA map with elementStrides=2."""
+    torch.manual_seed(2)
+    dev = "cuda"
+    x = nhwc(torch.randn(N, C, H, H, device=dev))
+    w = torch.randn(C, C, 3, 3, device=dev) / (3 * C**0.5)
+    b = torch.randn(C, device=dev)
+    wp = ops.pack_conv_weight(w)
+    y = ops.conv_gemm([(x, C, C)], [(0, 9)], wp, N, H, H, out_H=H // 2, out_W=H // 2, stride=2, bias=b, out_fp32=True)
+    ref = ref_conv(x, w, b, asym=True)
+    assert rel_l2(y.view(N, H // 2, H // 2, C), ref) < 2e-5
+
+
+def test_resblock_conv2_fused_shortcut_and_epilogue(ops):
+    """conv3x3(g) + nin_shortcut(cat(xa, xb)) in one accumulator, + bias; and conv1-style bias + temb rowvec + SiLU."""
+    torch.manual_seed(3)
+    dev = "cuda"
+    N, H, Ca, Cb, Co = 4, 16, 256, 128, 256
+    g = nhwc(torch.randn(N, Co, H, H, device=dev))
+    xa = nhwc(torch.randn(N, Ca, H, H, device=dev))
+    xb = nhwc(torch.randn(N, Cb, H, H, device=dev))
+    w2 = torch.randn(Co, Co, 3, 3, device=dev) / (3 * Co**0.5)
+    wn = torch.randn(Co, Ca + Cb, 1, 1, device=dev) / (Ca + Cb) ** 0.5
+    b = torch.randn(Co, device=dev)
+    wp = ops.pack_conv_weight(None, parts=[(w2, 0, Co), (wn, 0, Ca), (wn, Ca, Cb)])
+    y = ops.conv_gemm([(g, Co, Co), (xa, Ca, Ca), (xb, Cb, Cb)], [(0, 9), (1, 1), (2, 1)], wp, N, H, H, bias=b,
+                      out_fp32=True)
+    ref = ref_conv(g, w2, b) + ref_conv(torch.cat([xa, xb], -1), wn, None, pad=0)
+    assert rel_l2(y.view(N, H, H, Co), ref) < 2e-5
+
+    # bias + per-image row vector + residual + leaky relu
+    rowvec = torch.randn(N, 3 * Co, device=dev)[:, Co:2 * Co]  # strided view, ld = 3*Co
+    res = nhwc(torch.randn(N, Co, H, H, device=dev))
+    wp2 = ops.pack_conv_weight(w2)
+    y2 = ops.conv_gemm([(g, Co, Co)], [(0, 9)], wp2, N, H, H, bias=b, rowvec=rowvec, residual=res, act=1, out_fp32=True)
+    ref2 = F.leaky_relu(ref_conv(g, w2, b) + rowvec[:, None, None, :] + res.float(), 0.2)
+    assert rel_l2(y2.view(N, H, H, Co), ref2) < 2e-5
+
+
+def test_attention_gemms(ops):
+    """q k^T with fused row softmax, V^T with weights as the A operand, and P V - the DDPM AttnBlock at 16x16."""
+    torch.manual_seed(4)
+    dev = "cuda"
+    B, S, Cc = 3, 256, 256
+    hn = (torch.randn(B, S, Cc, device=dev)).to(torch.bfloat16)
+    qk = (torch.randn(B, S, 2 * Cc, device=dev)).to(torch.bfloat16)
+    scale = Cc**-0.5
+    # S = softmax(scale q k^T)
+    P = torch.empty(B, S, S, dtype=torch.bfloat16, device=dev)
+    ops.conv_gemm([(qk, Cc, 2 * Cc)], [(0, 1)], qk[:, :, Cc:], B, 1, S, batch=B, a_batched=True, b_batched=True,
+                  b_rows=S, b_ld=2 * Cc, b_batch_stride=S * 2 * Cc, alpha=scale, softmax=True, out=P, ldo=S,
+                  out_batch_stride=S * S, rows_per_image=1)
+    q, k = qk[..., :Cc].float(), qk[..., Cc:].float()
+    Pref = torch.softmax(scale * q @ k.transpose(1, 2), dim=-1)
+    assert rel_l2(P, Pref) < 4e-3
+    # V^T[b] = Wv hn[b]^T + bv (bias along M)
+    wv = (torch.randn(Cc, Cc, device=dev) / Cc**0.5).to(torch.bfloat16)
+    bv = torch.randn(Cc, device=dev)
+    vT = torch.empty(B, Cc, S, dtype=torch.bfloat16, device=dev)
+    ops.conv_gemm([(wv, Cc, Cc)], [(0, 1)], hn, 1, 1, Cc, batch=B, b_batched=True, b_rows=S, b_ld=Cc,
+                  b_batch_stride=S * Cc, bias=bv, bias_along_m=True, out=vT, ldo=S, out_batch_stride=Cc * S,
+                  rows_per_image=1)
+    vTref = wv.float() @ hn.float().transpose(1, 2) + bv[None, :, None]
+    assert rel_l2(vT, vTref) < 4e-3
+    # O = P V
+    O = torch.empty(B, S, Cc, dtype=torch.bfloat16, device=dev)
+    ops.conv_gemm([(P, S, S)], [(0, 1)], vT, B, 1, S, batch=B, a_batched=True, b_batched=True, b_rows=Cc, b_ld=S,
+                  b_batch_stride=Cc * S, out=O, ldo=Cc, out_batch_stride=S * Cc, rows_per_image=1)
+    Oref = P.float() @ vT.float().transpose(1, 2)
+    assert rel_l2(O, Oref) < 4e-3
+
+
+@pytest.mark.parametrize("N,H,C1,C2,silu", [(4, 32, 128, 0, 1), (4, 16, 256, 128, 1), (3, 8, 256, 256, 0), (2, 4, 256, 0, 1)])
+def test_group_norm(ops, N, H, C1, C2, silu):
+    torch.manual_seed(5)
+    dev = "cuda"
+    x1 = nhwc(torch.randn(N, C1, H, H, device=dev) * 2 + 0.5)
+    x2 = nhwc(torch.randn(N, C2, H, H, device=dev)) if C2 else None
+    C = C1 + C2
+    gamma = torch.randn(C, device=dev)
+    beta = torch.randn(C, device=dev)
+    y = ops.group_norm(x1, gamma, beta, 1e-6, silu, x2=x2)
+    xc = torch.cat([x1, x2], -1) if C2 else x1
+    ref = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-6)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_l2(y, ref.permute(0, 2, 3, 1)) < 4e-3
