@@ -1,0 +1,118 @@
+"""Drop-in for the reference's models/DxMI/var_sampler.py::VARSampler (:300-444) on the B200 path.
+
+`sample()` is one `dxmi_var_rollout` call (T x [U-Net forward + fused transition kernel]); `sample_step()` is one
+U-Net forward plus one `dxmi_var_step`.  Schedule tables come from `diffusion_by_maxentirl_b200.schedule`.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from diffusion_by_maxentirl_b200 import _lib as L
+from diffusion_by_maxentirl_b200.models.modules import process_single_t
+from diffusion_by_maxentirl_b200.schedule import VarSchedule
+
+
+def _inner(net):
+    return net.module if hasattr(net, "module") else net
+
+
+class VARSampler(nn.Module):
+    def __init__(self, net, n_timesteps, sample_shape, trainable_beta=True, adhoc_scale1=1.0, adhoc_scale2=1.0):
+        super().__init__()
+        assert trainable_beta in {True, False, "fix_last"}
+        self.net = net
+        self.n_timesteps = n_timesteps
+        self.sample_shape = sample_shape
+        self.adhoc_scale1 = adhoc_scale1
+        self.adhoc_scale2 = adhoc_scale2
+        self.trainable_beta = trainable_beta
+        self.kappa = 1.0
+        s = VarSchedule(n_timesteps, self.kappa)
+        self.user_defined_eta = s.user_defined_eta
+        self.register_buffer("continuous_steps", s.continuous_steps)
+        self.register_buffer("Gamma_bar", s.Gamma_bar)
+        if trainable_beta:
+            _inner(self.net).log_betas = nn.Parameter(torch.log(s.std * adhoc_scale2))  # "log sigma", reference :354-355
+        self.register_buffer("x_prev_multiplier", s.x_prev_multiplier)
+        self.register_buffer("theta_multiplier", s.theta_multiplier)
+        self.register_buffer("std", s.std.clone())
+        self.register_buffer("diffusion_steps_list", s.diffusion_steps_list)
+        if trainable_beta == "fix_last":
+            _inner(self.net).register_buffer("std", s.std.clone())
+
+    # ------------------------------------------------------------------ per-step noise scale (reference :268-283)
+    def _sigmas(self):
+        net = _inner(self.net)
+        if self.trainable_beta == "fix_last":
+            return torch.exp(torch.cat([net.log_betas[:-1], net.std[-1].log().unsqueeze(0)])).detach()
+        if self.trainable_beta:
+            return torch.exp(net.log_betas).detach()
+        return self.std
+
+    def _forward_net(self, x, t):
+        # go through self.net (possibly DDP-wrapped) so hooks / wrappers behave as with the reference
+        return self.net(x, t)
+
+    # ------------------------------------------------------------------ rollout
+    def sample(self, n_sample, device="cpu", enable_grad=False, noise=None):
+        """Reference VARSampler.sample (:411-428).  `noise` (optional, parity contract): [T+1, B, C, H, W] or a list of
+        T+1 tensors; noise[0] is x_0.  Without it, T+1 `torch.randn` draws are made in the reference's order."""
+        if enable_grad:
+            raise NotImplementedError("enable_grad=True (backward through the rollout) is not built on the B200 path")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("VARSampler.sample runs on CUDA only (no CPU fallback)")
+        T, B = self.n_timesteps, int(n_sample)
+        shape = tuple(self.sample_shape)
+        net = _inner(self.net)
+        net._check_eval()
+        if noise is None:
+            noise_t = torch.empty(T + 1, B, *shape, device=device)
+            for i in range(T + 1):
+                noise_t[i] = torch.randn(B, *shape, device=device)
+        else:
+            noise_t = (torch.stack(list(noise)) if not torch.is_tensor(noise) else noise).to(device=device, dtype=torch.float32).contiguous()
+            assert noise_t.shape == (T + 1, B, *shape)
+        h = net._ensure_handle(device)
+        sig = self._sigmas().float().cpu()
+        sched = torch.stack([self.continuous_steps.cpu().float(), self.x_prev_multiplier.cpu(),
+                             self.theta_multiplier.cpu() * self.adhoc_scale1, sig], dim=1).contiguous()
+        l_sample = torch.empty(T + 1, B, *shape, device=device)
+        mean = torch.empty(T, B, *shape, device=device)
+        control = torch.empty(T, B, *shape, device=device)
+        logp = torch.empty(T, B, device=device)
+        L.check(
+            L.lib().dxmi_var_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), T, L.ptr(noise_t),
+                                     L.ptr(l_sample), L.ptr(mean), L.ptr(control), L.ptr(logp), B, L.stream_ptr()),
+            "dxmi_var_rollout")
+        sig_dev = sig.to(device)
+        return {
+            "sample": l_sample[T],
+            "l_sample": [l_sample[i] for i in range(T + 1)],
+            "logp": [logp[i] for i in range(T)],
+            "logp_terminal": torch.zeros(B, device=device),
+            "mean": [mean[i] for i in range(T)],
+            "sigma": [sig_dev[i].repeat(B)[:, None, None, None] for i in range(T)],
+            "control": [control[i] for i in range(T)],
+        }
+
+    def sample_step(self, x, t, y=None, noise=None):
+        """Reference VARSampler.sample_step (:357-408): per-sample integer step index t."""
+        device = x.device
+        t = process_single_t(x, t).to(device)
+        B = x.shape[0]
+        x = x.detach().contiguous().float()
+        eps = self._forward_net(x, self.continuous_steps.to(device)[t])
+        sig = self._sigmas().to(device)[t].float().contiguous()
+        a = self.x_prev_multiplier.to(device)[t].contiguous()
+        c = (self.theta_multiplier.to(device)[t] * self.adhoc_scale1).contiguous()
+        z = torch.randn_like(x) if noise is None else noise.to(device=device, dtype=torch.float32).contiguous()
+        xn, mean, control = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        logp = torch.empty(B, device=device)
+        chw = x[0].numel()
+        L.check(L.lib().dxmi_var_step(L.ptr(x), L.ptr(eps), L.ptr(z), L.ptr(a), L.ptr(c), L.ptr(sig), L.ptr(xn),
+                                      L.ptr(mean), L.ptr(control), L.ptr(logp), B, chw, L.stream_ptr()), "dxmi_var_step")
+        sigma = sig[:, None, None, None]
+        return {"sample": xn, "logp": logp, "logp_terminal": torch.zeros(B, device=device), "mean": mean, "sigma": sigma,
+                "entropy": torch.log(sigma), "control": control}

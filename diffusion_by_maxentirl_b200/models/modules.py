@@ -1,0 +1,52 @@
+"""Drop-in for the reference's models/modules.py: the energy / value network IGEBMEncoderV2 (:104-163) and
+`process_single_t` (:183-186) on the B200 path."""
+import torch
+
+from diffusion_by_maxentirl_b200 import _lib as L
+from diffusion_by_maxentirl_b200.native import NativeNet
+
+
+def process_single_t(x, t):
+    """Broadcast a scalar step index to a [B] long tensor on x's device (reference modules.py:183-186)."""
+    if isinstance(t, int) or t.dim() == 0 or len(t) == 1:
+        t = torch.ones([x.shape[0]], dtype=torch.long, device=x.device) * t
+    return t
+
+
+class IGEBMEncoderV2(NativeNet):
+    """conv3 -> lrelu -> 6 ResBlockV2 -> relu -> sum over HW -> Linear(2nh, 1) -> Linear(1, 1); `forward(x)` -> [B, 1].
+    Only the configuration every DxMI YAML uses is built (no spectral norm, no class embedding, keepdim=False,
+    linear output)."""
+
+    def __init__(self, in_chan=3, out_chan=1, n_class=None, use_spectral_norm=False, keepdim=True,
+                 out_activation="linear", avg_pool_dim=1, learn_out_scale=False, nh=128):
+        if use_spectral_norm or n_class is not None or keepdim or out_activation != "linear" or out_chan != 1:
+            raise NotImplementedError(
+                "B200 IGEBMEncoderV2 supports use_spectral_norm=False, n_class=None, keepdim=False, "
+                "out_activation='linear', out_chan=1 (the value-net settings of every DxMI config)")
+        d = L.ArchDesc()
+        d.arch = L.ARCH_IGEBM_V2
+        d.in_channels, d.out_channels, d.ch = int(in_chan), int(out_chan), int(nh)
+        d.resolution = 0  # set per call from the input
+        d.learn_out_scale = int(bool(learn_out_scale))
+        super().__init__(d)
+        self.keepdim = keepdim
+        self.learn_out_scale = learn_out_scale
+        self.pre_activation = None
+        self._by_res = {}
+
+    def forward(self, input, y=None):
+        if y is not None:
+            raise NotImplementedError("class-conditional value net is not used by the built configs")
+        B, _, H, W = input.shape
+        assert H == W and H % 8 == 0
+        if self._desc.resolution != H:
+            # the plan is resolution specific: (re)create the handle for this input size
+            self.release()
+            self._desc.resolution = H
+        h = self._ensure_handle(input.device)
+        x = input.detach().contiguous().float()
+        out = torch.empty(B, 1, device=x.device)
+        L.check(L.lib().dxmi_value_forward(h, L.ptr(x), L.ptr(out), B, L.stream_ptr()), "dxmi_value_forward")
+        self.pre_activation = out
+        return out

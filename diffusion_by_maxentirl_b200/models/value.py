@@ -1,0 +1,11 @@
+"""Drop-in for the reference's models/value.py::TimeIndependentValue (:3-14)."""
+import torch.nn as nn
+
+
+class TimeIndependentValue(nn.Module):
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, x, t, y=None):
+        return self.net(x, y) if y is not None else self.net(x)
