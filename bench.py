@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py - the DxMI sampler-rollout benchmark (BASELINE.json metric: T-step sampling images/sec).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--T T]
+  (N > 1: launched by the driver as  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" is one rollout of the hot path over one batch of synthetic inputs: T U-Net denoising steps, each followed
+by the Gaussian transition with its learned sigma, then the energy / value net on the final samples.
+Workload (config.workload): BASELINE.json configs[1] - CIFAR-10, T=4, batch 256 per GPU, bf16 tensor-core math.
+The DDGAN backbone that config names is not in the reference tree, so the in-tree stand-in
+`VARSampler(n_timesteps=4)` + `unet_small.Model` is used and labelled as such.
+
+Numbers printed (one JSON line from rank 0):
+  value        images/s, inputs (noise) resident in HBM, CUDA-event time of K steps, max over ranks
+  e2e          images/s through the public API (`sampler.sample` + `value`) from PINNED HOST noise, with the H2D copy
+               of every step's noise and the D2H read of samples + energies inside the timed region
+  roofline     the tcgen05 implicit-GEMM kernel: algorithmic FLOPs / CUDA-event time of every GEMM launch, measured
+               live in a separate pass of the same workload, against MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle port of the same rollout on the host cores (bounded sample)
+--impl reference times the reference algorithm's CPU implementation (oracle port, all host threads) per step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "dxmi_rollout_images_per_sec"
+UNIT = "images/s"
+GF_PER_IMAGE_UNET = 12.444  # algorithmic GFLOP / image / forward
+GF_PER_IMAGE_VALUE = 1.613
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rollout_fn(T):
+    """The reference algorithm on the CPU (oracle port): returns f(B) -> seconds for one rollout + energy."""
+    import torch
+
+    from common import DDPM_CFG  # noqa: F401
+    from oracle import nets, samplers, synth
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    shapes_net = json.load(open(os.path.join(ROOT, "tests", "golden", "ddpm_shapes.json")))
+    sd = synth.synth_state_dict({k: tuple(v) for k, v in shapes_net["net"].items()})
+    vsd = synth.synth_state_dict({k: tuple(v) for k, v in shapes_net["value"].items()}, seed=1)
+    sched = samplers.var_schedule(T)
+    log_betas = sched["log_betas_init"]
+
+    def run(B, seed=0):
+        noise = synth.synth_noise(T, B, (3, 32, 32), seed=seed)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            d = samplers.var_rollout(lambda x, t: nets.ddpm_unet_forward(sd, x, t), sched, log_betas, noise)
+            nets.value_forward(vsd, d["sample"])
+        return time.perf_counter() - t0
+
+    return run
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    T, Bs = args.T, 8
+    run = cpu_oracle_rollout_fn(T)
+    for _ in range(max(1, min(args.warmup, 2))):
+        run(Bs)
+    steps = max(1, min(args.steps, 10))
+    t = [run(Bs, seed=i) for i in range(steps)]
+    tot = sum(t)
+    v = Bs * steps / tot
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CIFAR-10 DDPM U-Net (DDGAN stand-in) DxMI T={T} rollout + energy, CPU oracle port of "
+                               f"the reference algorithm, bounded sample of {Bs} images per step",
+                   "T": T, "batch_per_step": Bs},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} rollouts x {Bs} images, torch {torch.__version__} CPU fp32, {cores} threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--T", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-n-256", type=int, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from common import build_ddpm
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+    if args.block_n_256 is not None:
+        lib.dxmi_set_option(b"block_n_256", args.block_n_256)
+
+    T, B, K, W = args.T, args.batch, args.steps, args.warmup
+    net, sampler, value, sd, vsd = build_ddpm(T, device=dev)
+    shape = (3, 32, 32)
+    g = torch.Generator().manual_seed(1234 + rank)
+    n_host_bufs = 2
+    host_noise = [torch.randn(T + 1, B, *shape, generator=g).pin_memory() for _ in range(n_host_bufs)]
+    dev_noise = host_noise[0].to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gathered_s = torch.empty(world, B, *shape, dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered_e = torch.empty(world, B, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def rollout_resident():
+        d = sampler.sample(B, device=dev, noise=dev_noise)
+        e = value(d["sample"], T)
+        if world > 1:
+            # the path's only collective: all-gather of u8 samples and energies (generate_large.py:43-50)
+            u8 = torch.empty(B, *shape, dtype=torch.uint8, device=dev)
+            L.check(lib.dxmi_quantize_u8(L.ptr(d["sample"]), L.ptr(u8), u8.numel(), L.stream_ptr()))
+            dist.all_gather_into_tensor(gathered_s.view(-1), u8.view(-1))
+            dist.all_gather_into_tensor(gathered_e.view(-1), e.view(-1))
+        return d, e
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- warm-up
+    for _ in range(W):
+        rollout_resident()
+    sync_all()
+
+    # ---------------------------------------------------------------- value: device-timed, inputs resident in HBM
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.dxmi_launch_count()
+    evs = []
+    sync_all()
+    for _ in range(K):
+        flush.fill_(1)  # L2 flush between timed iterations (untimed)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rollout_resident()
+        b.record()
+        evs.append((a, b))
+    sync_all()
+    launches = lib.dxmi_launch_count() - launches0
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value_ips = world * B * K / (ms_total / 1e3)
+
+    # ---------------------------------------------------------------- e2e: public API from pinned host noise
+    d2h_samples = torch.empty(B, *shape).pin_memory()
+    d2h_energy = torch.empty(B, 1).pin_memory()
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(K):
+        nz = host_noise[i % n_host_bufs].to(dev, non_blocking=True)
+        d = sampler.sample(B, device=dev, noise=nz)
+        e = value(d["sample"], T)
+        if world > 1:
+            u8 = torch.empty(B, *shape, dtype=torch.uint8, device=dev)
+            L.check(lib.dxmi_quantize_u8(L.ptr(d["sample"]), L.ptr(u8), u8.numel(), L.stream_ptr()))
+            dist.all_gather_into_tensor(gathered_s.view(-1), u8.view(-1))
+            dist.all_gather_into_tensor(gathered_e.view(-1), e.view(-1))
+        d2h_samples.copy_(d["sample"], non_blocking=True)
+        d2h_energy.copy_(e, non_blocking=True)
+        torch.cuda.synchronize()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ips = world * B * K / float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0, live)
+    roof = None
+    if rank == 0:
+        pk, pk_kind = peaks()
+        lib.dxmi_set_option(b"time_gemms", 1)
+        kk = max(2, min(K, 5))
+        for _ in range(kk):
+            d = sampler.sample(B, device=dev, noise=dev_noise)
+            value(d["sample"], T)
+        torch.cuda.synchronize()
+        ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
+        L.check(lib.dxmi_gemm_timing(C.byref(ms), C.byref(fl), C.byref(nl)))
+        lib.dxmi_set_option(b"time_gemms", 0)
+        achieved = fl.value / (ms.value * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv / attention GEMM launches)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained",
+                "gemm_launches_per_step": nl.value // kk, "gemm_ms_per_step": ms.value / kk,
+                "gemm_share_of_step": (ms.value / kk) / (ms_total / K),
+                "algorithmic_gflop_per_step": fl.value / kk / 1e9}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        run = cpu_oracle_rollout_fn(T)
+        Bs = 8
+        run(Bs)
+        ts, t_begin = [], time.perf_counter()
+        while len(ts) < 3 or (time.perf_counter() - t_begin < 10 and len(ts) < 20):
+            ts.append(run(Bs, seed=len(ts)))
+        cores = torch.get_num_threads()
+        cpu = {"value": Bs * len(ts) / sum(ts), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{len(ts)} rollouts x {Bs} images (T={T} + energy), oracle port, torch CPU fp32, {cores} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value_ips, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"CIFAR-10 DDPM U-Net (in-tree stand-in for the absent DDGAN backbone) DxMI T={T} "
+                                   f"sampler rollout + energy eval, batch {B}/GPU, bf16 tcgen05 (BASELINE.json configs[1])",
+                       "T": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "256 MiB write between timed steps (L2 flush)",
+                       "collective": "all_gather(u8 samples, fp32 energies) per step" if world > 1 else "none"},
+            "e2e": {"value": e2e_ips, "unit": UNIT, "h2d_bytes_per_step": host_noise[0].numel() * 4,
+                    "d2h_bytes_per_step": d2h_samples.numel() * 4 + d2h_energy.numel() * 4},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "model_tflops": value_ips * (T * GF_PER_IMAGE_UNET + GF_PER_IMAGE_VALUE) / 1e3,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,8 @@ SYMBOLS = {
     "dxmi_last_error": (C.c_char_p, []),
     "dxmi_set_option": (_I, [C.c_char_p, _I]),
     "dxmi_launch_count": (_LL, []),
+    "dxmi_gemm_timing": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL)]),
+    "dxmi_plan_gemm_flops": (C.c_double, [_VP, _I]),
     "dxmi_workspace_bytes": (C.c_size_t, [_VP, _I]),
 }
 

@@ -23,8 +23,22 @@ int dxmi_set_option(const char* name, int value) {
         set_block_n_256(value);
         return 0;
     }
+    if (!strcmp(name, "time_gemms")) {
+        set_time_gemms(value);
+        return 0;
+    }
     set_err("unknown option");
     return -1;
+}
+
+int dxmi_gemm_timing(double* ms_total, double* flops_total, long long* launches) {
+    return gemm_timing_collect(ms_total, flops_total, launches);
+}
+
+double dxmi_plan_gemm_flops(dxmi_net_t net, int B) {
+    if (!net) return 0;
+    auto it = net->net.plans.find(B);
+    return it == net->net.plans.end() ? 0.0 : it->second->gemm_flops;
 }
 
 int dxmi_create(const dxmi_arch_desc* desc, int device, dxmi_net_t* out) {

@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace dxmi {
 
@@ -110,8 +111,44 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     return 0;
 }
 
+// ---- optional per-launch timing (bench.py roofline leg): CUDA events around every tcgen05 GEMM launch
+static int g_time_gemms = 0;
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    double flops;
+};
+static std::vector<TimedLaunch> g_timed;
+void set_time_gemms(int v) { g_time_gemms = v; }
+int gemm_timing_collect(double* ms_total, double* flops_total, long long* launches) {
+    double ms = 0, fl = 0;
+    for (auto& t : g_timed) {
+        cudaError_t e = cudaEventSynchronize(t.b);
+        if (e != cudaSuccess) return (int)e;
+        float m = 0.f;
+        cudaEventElapsedTime(&m, t.a, t.b);
+        ms += m;
+        fl += t.flops;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    *ms_total = ms;
+    *flops_total = fl;
+    *launches = (long long)g_timed.size();
+    g_timed.clear();
+    return 0;
+}
+
 int run_gemm(const GemmOp& op, cudaStream_t st) {
-    return launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
+    if (!g_time_gemms) return launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
+    TimedLaunch t;
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    t.flops = op.flops;
+    cudaEventRecord(t.a, st);
+    int r = launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
+    cudaEventRecord(t.b, st);
+    g_timed.push_back(t);
+    return r;
 }
 
 }  // namespace dxmi

@@ -13,6 +13,8 @@ struct GemmOp {
 int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op);
 int run_gemm(const GemmOp& op, cudaStream_t st);
 void set_block_n_256(int v);
+void set_time_gemms(int v);
+int gemm_timing_collect(double* ms_total, double* flops_total, long long* launches);
 const char* gemm_op_last_error();
 
 }  // namespace dxmi

@@ -152,7 +152,12 @@ int dxmi_op_gn_ws_floats(int N, int HW, int groups);
 
 /* -------------------------------------------------------------------------------------------- misc */
 const char* dxmi_last_error(void);
-int dxmi_set_option(const char* name, int value); /* e.g. "block_n_256" */
+int dxmi_set_option(const char* name, int value); /* "block_n_256" (tile width), "time_gemms" (event-time every GEMM) */
+/* with "time_gemms" on: summed CUDA-event duration / algorithmic FLOPs / count of the tcgen05 GEMM launches since
+ * the last call (synchronises on the recorded events) */
+int dxmi_gemm_timing(double* ms_total, double* flops_total, long long* launches);
+/* algorithmic 2*M*N*K FLOPs of all tcgen05 GEMM launches of one forward at batch B (0 if that plan is not built) */
+double dxmi_plan_gemm_flops(dxmi_net_t net, int B);
 /* number of kernels launched by this library since process start (bench.py "gpu_launches") */
 long long dxmi_launch_count(void);
 size_t dxmi_workspace_bytes(dxmi_net_t net, int B);

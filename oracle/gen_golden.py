@@ -106,6 +106,11 @@ def gen_ddpm(T, B):
     sampler.eval()
     value.eval()
 
+    import json
+    with open(os.path.join(GOLD, "ddpm_shapes.json"), "w") as f:  # lets the CPU legs rebuild the synthetic weights
+        json.dump({"net": {k: list(v.shape) for k, v in net.state_dict().items() if k not in ("log_betas", "std")},
+                   "value": {k: list(v.shape) for k, v in value.state_dict().items()}}, f)
+
     # ---- schedule: oracle restatement must equal the reference buffers exactly
     sched = samplers.var_schedule(T)
     for name in ("continuous_steps", "Gamma_bar", "x_prev_multiplier", "theta_multiplier", "std"):

@@ -1,0 +1,37 @@
+"""Minimal workload for ncu captures: one warm-up rollout + one profiled rollout of the bench workload
+(CIFAR DDPM U-Net, T=4, batch 256, + value net).  Usage (under gpurun):
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+      python tools/profile_rollout.py [--batch 256] [--T 4] [--rollouts 1]
+"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+from common import build_ddpm  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--T", type=int, default=4)
+ap.add_argument("--rollouts", type=int, default=1)
+ap.add_argument("--warmup", type=int, default=1)
+args = ap.parse_args()
+
+net, sampler, value, sd, vsd = build_ddpm(args.T, device="cuda")
+noise = torch.randn(args.T + 1, args.batch, 3, 32, 32, device="cuda")
+for _ in range(args.warmup):
+    d = sampler.sample(args.batch, device="cuda", noise=noise)
+    value(d["sample"], args.T)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_push("profiled_rollouts")
+for _ in range(args.rollouts):
+    d = sampler.sample(args.batch, device="cuda", noise=noise)
+    e = value(d["sample"], args.T)
+torch.cuda.synchronize()
+torch.cuda.nvtx.range_pop()
+print("energy mean", float(e.mean()))
