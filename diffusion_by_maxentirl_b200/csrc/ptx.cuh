@@ -3,6 +3,7 @@
 // Everything here is device-only and header-only.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -52,8 +53,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded wait: a pipeline bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+            printf("dxmi: mbarrier wait timed out (block %d,%d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x, parity);
+            __trap();
+        }
     }
 }
 

@@ -273,6 +273,6 @@ if __name__ == "__main__":
         gen_ddpm(T=4, B=2)
     if args.edm:
         gen_edm("in64", B=2, T=4, small=dict(image_size=32, num_channels=64, num_res_blocks=1,
-                                             attention_resolutions="16,8,4"))
+                                             channel_mult="1,2,3,4", attention_resolutions="16,8,4"))
     if args.edm_full:
         gen_edm("in64", B=1, T=2)
