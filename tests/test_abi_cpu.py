@@ -1,0 +1,106 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol include/dxmi_b200.h declares, the drop-in
+modules publish the reference's state_dict layout, and the product fails loudly without a GPU (no CPU fallback).
+No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from common import DDPM_CFG, VALUE_CFG, golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "dxmi_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dxmi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    assert os.path.exists(L.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    raw = C.CDLL(L.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/dxmi_b200.h but not exported"
+    assert set(L.SYMBOLS) == set(names), set(L.SYMBOLS) ^ set(names)
+
+
+def test_struct_mirrors_match_header_sizes():
+    """ctypes mirrors of dxmi_arch_desc / dxmi_gemm_desc stay in sync with the header (field count and order)."""
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    src = open(os.path.join(ROOT, "include", "dxmi_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    blocks = {name: body for body, name in re.findall(r"typedef struct \{([^}]*)\} (\w+);", src)}
+    for cname, cls in (("dxmi_arch_desc", L.ArchDesc), ("dxmi_gemm_desc", L.GemmDesc)):
+        fields = []
+        for decl in blocks[cname].split(";"):
+            for piece in decl.split(","):
+                m = re.search(r"([A-Za-z_]\w*)\s*(?:\[\d+\])?\s*$", piece.strip())
+                if m:
+                    fields.append(m.group(1))
+        assert fields == [f[0] for f in cls._fields_], (cname, fields)
+
+
+def test_dropin_state_dict_layout_matches_reference():
+    """Key names, order and shapes of the drop-in modules == the reference's, including the
+    `log_betas` parameter and `std` buffer VARSampler injects into the net."""
+    from diffusion_by_maxentirl_b200.models.DxMI.unet_small import Model
+    from diffusion_by_maxentirl_b200.models.DxMI.var_sampler import VARSampler
+    from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
+    from diffusion_by_maxentirl_b200.models.value import TimeIndependentValue
+
+    g = golden("ddpm_T10_B2.npz")
+    net = Model(**DDPM_CFG)
+    sampler = VARSampler(net, n_timesteps=10, sample_shape=[3, 32, 32], trainable_beta="fix_last")
+    ref_keys = [str(k) for k in g["state_dict_keys"]]
+    assert sorted(net.state_dict().keys()) == sorted(ref_keys)
+    assert len(ref_keys) == 330
+    assert isinstance(net.log_betas, torch.nn.Parameter) and "std" in dict(net.named_buffers())
+    assert np.array_equal(net.log_betas.detach().numpy(), g["log_betas"])
+    assert np.array_equal(sampler.continuous_steps.numpy(), g["continuous_steps"])
+    assert sum(p.numel() for k, p in net.named_parameters() if k != "log_betas") == 35746307
+    value = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
+    assert list(value.state_dict().keys()) == [str(k) for k in g["value_state_dict_keys"]]
+    assert sum(p.numel() for p in value.parameters()) == 5134595
+    import json
+
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "ddpm_shapes.json")))
+    for k, v in net.state_dict().items():
+        if k not in ("log_betas", "std"):
+            assert list(v.shape) == shapes["net"][k], k
+    for k, v in value.state_dict().items():
+        assert list(v.shape) == shapes["value"][k], k
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on a CPU tensor instead of silently computing somewhere else."""
+    from diffusion_by_maxentirl_b200.models.DxMI.unet_small import Model
+    from diffusion_by_maxentirl_b200.models.DxMI.var_sampler import VARSampler
+
+    net = Model(**DDPM_CFG).eval()
+    with pytest.raises(RuntimeError, match="no CPU"):
+        net(torch.zeros(1, 3, 32, 32), torch.zeros(1))
+    sampler = VARSampler(net, n_timesteps=4, sample_shape=[3, 32, 32], trainable_beta="fix_last").eval()
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        sampler.sample(1, device="cpu")
+    net.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        net._check_eval()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "diffusion_by_maxentirl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
+                assert "/root/reference" not in text, os.path.join(dirpath, f)
