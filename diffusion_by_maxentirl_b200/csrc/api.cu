@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "attn_tc.cuh"
 #include "engine.cuh"
 
 using namespace dxmi;
@@ -288,9 +289,39 @@ int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, int T, const float
 
 int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, const int64_t* y,
                      float* l_sample, float* mean, int B, dxmi_stream_t stream) {
-    (void)net; (void)sched_host; (void)T; (void)noise; (void)y; (void)l_sample; (void)mean; (void)B; (void)stream;
-    set_err("dxmi_edm_rollout: ADM U-Net path not built yet");
-    return -100;
+    if (!net || !net->net.finalized || net->net.a.arch != DXMI_ARCH_ADM_UNET) {
+        set_err("dxmi_edm_rollout: needs a finalized ADM U-Net handle");
+        return -1;
+    }
+    Net& n = net->net;
+    if ((n.a.num_classes > 0) != (y != nullptr)) {
+        set_err("dxmi_edm_rollout: must specify y if and only if the model is class-conditional");  // cm/unet.py:770-772
+        return -2;
+    }
+    Plan* p = get_plan(n, B);
+    if (!p) return -3;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long chw = (long long)n.a.in_channels * n.a.resolution * n.a.resolution;
+    const long long bchw = chw * B;
+    cudaMemcpyAsync(l_sample, noise, bchw * sizeof(float), cudaMemcpyDeviceToDevice, st);  // x_0 (already sigma_max * z)
+    for (int i = 0; i < T; ++i) {
+        float* coef = p->coef;           // [B, 5]
+        float* x_scale = p->coef + 5 * B;  // [B]
+        edm_fill(coef, x_scale, p->tbuf, B, sched_host + 7 * i, st);
+        count_launches(1);
+        const float* xi = l_sample + (long long)i * bchw;
+        p->x = xi;
+        p->x_scale = x_scale;
+        p->t = p->tbuf;
+        p->y = y;
+        p->out = p->eps;
+        int r = run_plan(n, p, st);
+        if (r) return r;
+        edm_step(xi, p->eps, noise + (long long)(i + 1) * bchw, coef, l_sample + (long long)(i + 1) * bchw,
+                 mean ? mean + (long long)i * bchw : nullptr, B, (int)chw, st);
+        count_launches(1);
+    }
+    return (int)cudaGetLastError();
 }
 
 int dxmi_quantize_u8(const float* x, uint8_t* out, long long nelem, dxmi_stream_t stream) {
@@ -337,6 +368,16 @@ int dxmi_op_group_norm(const void* x1, int C1, int ld1, const void* x2, int C2, 
              partial_ws, slabs, (bf16*)out, (cudaStream_t)stream);
     count_launches(2);
     return (int)cudaGetLastError();
+}
+
+int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
+                      int heads, int seq, float scale, dxmi_stream_t stream) {
+    AttnOp op;
+    int r = prepare_attn(qk, ld_qk, q_col0, k_col0, vt, out, ldo, B, heads, seq, 64, scale, &op);
+    if (!r) r = run_attn(op, (cudaStream_t)stream);
+    if (r) set_err(attn_last_error());
+    count_launches(1);
+    return r;
 }
 
 }  // extern "C"

@@ -1,0 +1,304 @@
+// Plan-builder base shared by the three network builders (engine.cu: DDPM U-Net + IGEBM value net, engine_adm.cu:
+// ADM / EDM U-Net): bump-allocated activation arena (dry pass sizes it, real pass fills it), packed-weight cache and
+// launch-closure emission.
+#pragma once
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace dxmi {
+
+struct Builder {
+    Net& net;
+    Plan& plan;
+    bool dry;
+    int B;
+    size_t off = 0;
+    static constexpr int NSLOT = 8;
+    size_t scratch_max[NSLOT] = {0};
+    size_t scratch_base[NSLOT] = {0};
+    int err = 0;
+
+    Builder(Net& n, Plan& p, bool d) : net(n), plan(p), dry(d), B(p.B) {}
+
+    static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+    void* alloc(size_t bytes) {
+        void* r = dry ? nullptr : plan.arena + off;
+        off += align_up(bytes);
+        return r;
+    }
+    void* scratch(int slot, size_t bytes) {
+        bytes = align_up(bytes);
+        if (dry) {
+            if (bytes > scratch_max[slot]) scratch_max[slot] = bytes;
+            return nullptr;
+        }
+        return plan.arena + scratch_base[slot];
+    }
+    bf16* act_alloc(int C, int H, int W) { return (bf16*)alloc((size_t)B * H * W * C * sizeof(bf16)); }
+
+    void fail(const char* what) {
+        if (!err) {
+            err = -20;
+            engine_set_error("%s", what);
+        }
+    }
+
+    // ---------------------------------------------------------------- weights
+    const Bound* get(const std::string& key) {
+        auto it = net.bound.find(key);
+        if (it == net.bound.end() || !it->second.ptr) {
+            if (!dry) {
+                std::string m = "weight not bound: " + key;
+                fail(m.c_str());
+            }
+            return nullptr;
+        }
+        return &it->second;
+    }
+    // fp32 view of a bound tensor: the borrowed pointer itself when fp32, else a converted (owned) copy.
+    const float* f32(const std::string& key) {
+        if (dry) return nullptr;
+        const Bound* b = get(key);
+        if (!b) return nullptr;
+        if (b->dtype == DXMI_F32) return (const float*)b->ptr;
+        auto it = net.derived.find("f32:" + key);
+        if (it != net.derived.end()) return (const float*)it->second;
+        long long n = 1;
+        for (auto s : b->shape) n *= s;
+        float* d = nullptr;
+        cudaMalloc(&d, n * sizeof(float));
+        net.owned.push_back(d);
+        net.derived["f32:" + key] = d;
+        Net* np = &net;
+        net.pack_jobs.push_back([np, key, d, n](cudaStream_t st) {
+            const Bound& bb = np->bound[key];
+            cast_to_f32(bb.ptr, bb.dtype == DXMI_F16, d, n, st);
+            count_launches(1);
+        });
+        return d;
+    }
+    void* derived_buf(const std::string& name, size_t bytes, bool* fresh) {
+        auto it = net.derived.find(name);
+        if (it != net.derived.end()) {
+            *fresh = false;
+            return it->second;
+        }
+        void* d = nullptr;
+        if (cudaMalloc(&d, bytes) != cudaSuccess) {
+            fail("cudaMalloc failed for packed weights");
+            return nullptr;
+        }
+        net.owned.push_back(d);
+        net.derived[name] = d;
+        *fresh = true;
+        return d;
+    }
+    struct PackPart {
+        std::string key;  // conv weight key
+        int c_off, c_cnt; // input-channel slice
+        int row_off = 0, row_cnt = 0;  // output-row slice (row_cnt == 0: all rows)
+    };
+    // bf16 [rows, K] with K = sum over parts of taps*c_cnt; rows stacked from `row_parts` groups when stacking q|k|v.
+    bf16* packed_rows(const std::string& name, const std::vector<std::vector<PackPart>>& row_groups, long long* K_out,
+                      int* rows_out) {
+        if (dry) return nullptr;
+        // geometry
+        long long K = 0;
+        int rows = 0;
+        for (size_t g = 0; g < row_groups.size(); ++g) {
+            long long kg = 0;
+            int rg = 0;
+            for (auto& part : row_groups[g]) {
+                const Bound* b = get(part.key);
+                if (!b) return nullptr;
+                const int taps = (int)(b->shape.size() == 4 ? b->shape[2] * b->shape[3] : 1);
+                kg += (long long)taps * part.c_cnt;
+                rg = part.row_cnt ? part.row_cnt : (int)b->shape[0];
+            }
+            if (g == 0) K = kg;
+            if (kg != K) {
+                fail("packed_rows: inconsistent K across row groups");
+                return nullptr;
+            }
+            rows += rg;
+        }
+        if (K_out) *K_out = K;
+        if (rows_out) *rows_out = rows;
+        bool fresh = false;
+        bf16* d = (bf16*)derived_buf("w:" + name, (size_t)rows * K * sizeof(bf16), &fresh);
+        if (!d || !fresh) return d;
+        Net* np = &net;
+        int row0 = 0;
+        for (auto& grp : row_groups) {
+            long long k_off = 0;
+            int rg = 0;
+            for (auto& part : grp) {
+                const Bound* b = get(part.key);
+                const int kh = b->shape.size() == 4 ? (int)b->shape[2] : 1;
+                const int kw = b->shape.size() == 4 ? (int)b->shape[3] : 1;
+                const int Cin = (int)b->shape[1];
+                const int Cout = part.row_cnt ? part.row_cnt : (int)b->shape[0];
+                const long long w_off = (long long)part.row_off * Cin * kh * kw;  // elements into the OIHW tensor
+                bf16* dst = d + (long long)row0 * K;
+                const std::string key = part.key;
+                const int c_off = part.c_off, c_cnt = part.c_cnt;
+                net.pack_jobs.push_back([np, key, Cout, Cin, kh, kw, c_off, c_cnt, dst, K, k_off, w_off](cudaStream_t st) {
+                    const Bound& bb = np->bound[key];
+                    const bool half = bb.dtype == DXMI_F16;
+                    const char* src = (const char*)bb.ptr + w_off * (half ? 2 : 4);
+                    pack_conv_weight(src, half, Cout, Cin, kh, kw, c_off, c_cnt, dst, K, k_off, st);
+                    count_launches(1);
+                });
+                k_off += (long long)kh * kw * c_cnt;
+                rg = Cout;
+            }
+            row0 += rg;
+        }
+        return d;
+    }
+    // fp32 concatenation of several bound vectors / matrices (row-stacked)
+    float* concat_f32(const std::string& name, const std::vector<std::string>& keys) {
+        if (dry) return nullptr;
+        long long total = 0;
+        std::vector<long long> sizes;
+        for (auto& k : keys) {
+            const Bound* b = get(k);
+            if (!b) return nullptr;
+            long long n = 1;
+            for (auto s : b->shape) n *= s;
+            sizes.push_back(n);
+            total += n;
+        }
+        bool fresh = false;
+        float* d = (float*)derived_buf("cat:" + name, total * sizeof(float), &fresh);
+        if (!d || !fresh) return d;
+        Net* np = &net;
+        long long o = 0;
+        for (size_t i = 0; i < keys.size(); ++i) {
+            const std::string key = keys[i];
+            float* dst = d + o;
+            const long long n = sizes[i];
+            net.pack_jobs.push_back([np, key, dst, n](cudaStream_t st) {
+                const Bound& bb = np->bound[key];
+                cast_to_f32(bb.ptr, bb.dtype == DXMI_F16, dst, n, st);
+                count_launches(1);
+            });
+            o += n;
+        }
+        return d;
+    }
+    float* sum_f32(const std::string& name, const std::string& ka, const std::string& kb, long long n) {
+        if (dry) return nullptr;
+        bool fresh = false;
+        float* d = (float*)derived_buf("sum:" + name, n * sizeof(float), &fresh);
+        if (!d || !fresh) return d;
+        const float* pa = f32(ka);
+        const float* pb = f32(kb);
+        Net* np = &net;
+        (void)np;
+        // note: f32() of an fp16 tensor registered its cast job *before* this one, so ordering is correct
+        net.pack_jobs.push_back([pa, pb, d, n](cudaStream_t st) {
+            vec_add_f32(pa, pb, d, n, st);
+            count_launches(1);
+        });
+        return d;
+    }
+
+    // ---------------------------------------------------------------- op emission
+    void op(std::function<int(cudaStream_t)> f, int launches = 1) {
+        if (dry) return;
+        plan.ops.push_back(std::move(f));
+        plan.launches_per_run += launches;
+    }
+    void gemm(const dxmi_gemm_desc& d) {
+        if (dry || err) return;
+        GemmOp g;
+        int r = prepare_gemm(d, &g);
+        if (r) {
+            err = r;
+            engine_set_error("prepare_gemm: %s", gemm_op_last_error());
+            return;
+        }
+        plan.gemm_flops += g.flops;
+        op([g](cudaStream_t st) { return run_gemm(g, st); });
+    }
+    dxmi_gemm_desc conv_desc(int H, int W) {
+        dxmi_gemm_desc d;
+        memset(&d, 0, sizeof d);
+        d.N = B;
+        d.H = H;
+        d.W = W;
+        d.out_H = H;
+        d.out_W = W;
+        d.stride = 1;
+        d.batch = 1;
+        d.alpha = 1.f;
+        d.rows_per_image = H * W;
+        return d;
+    }
+    static void set_src(dxmi_gemm_desc& d, int i, const bf16* p, int C, int ld) {
+        d.a_ptr[i] = p;
+        d.a_C[i] = C;
+        d.a_ld[i] = ld;
+    }
+    static void add_seg(dxmi_gemm_desc& d, int src, int taps) {
+        d.seg_src[d.nseg] = src;
+        d.seg_taps[d.nseg] = taps;
+        d.nseg++;
+    }
+
+    // GroupNorm(32) over concat(x1, x2) -> out (scratch slot), optional SiLU / FiLM
+    void group_norm(Act x1, Act x2, const std::string& pfx, float eps, int silu, const float* film, int film_ld,
+                    bf16* out) {
+        const int HW = x1.H * x1.W;
+        const int slabs = gn_num_slabs(B, HW);
+        float* ws = (float*)scratch(5, (size_t)B * slabs * 64 * sizeof(float));
+        const float* gamma = f32(pfx + ".weight");
+        const float* beta = f32(pfx + ".bias");
+        const bf16 *p1 = x1.p, *p2 = x2.p;
+        const int C1 = x1.C, C2 = x2.C;
+        const int Bn = B;
+        if ((C1 + C2) % 8 || (C1 % 8) || (C1 + C2) > 2048) fail("group_norm: unsupported channel count");
+        op([=](cudaStream_t st) {
+            gn_stats(p1, C1, C1, p2, C2, C2, Bn, HW, 32, ws, slabs, st);
+            gn_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, ws, slabs, out, st);
+            return (int)cudaGetLastError();
+        },
+           2);
+    }
+};
+
+
+template <typename BuilderT>
+int build_two_pass(Net& net, Plan& plan) {
+    BuilderT dryb(net, plan, true);
+    dryb.build();
+    size_t total = dryb.off;
+    size_t base[Builder::NSLOT];
+    for (int s = 0; s < Builder::NSLOT; ++s) {
+        base[s] = total;
+        total += dryb.scratch_max[s];
+    }
+    plan.arena_bytes = total + 256;
+    cudaError_t e = cudaMalloc((void**)&plan.arena, plan.arena_bytes);
+    if (e != cudaSuccess) {
+        engine_set_error("cudaMalloc(%zu bytes) for the B=%d activation arena failed: %s", plan.arena_bytes, plan.B,
+                         cudaGetErrorString(e));
+        return (int)e;
+    }
+    BuilderT b(net, plan, false);
+    for (int s = 0; s < Builder::NSLOT; ++s) b.scratch_base[s] = base[s];
+    b.build();
+    if (b.err) return b.err;
+    if (b.off != dryb.off) {
+        engine_set_error("internal: dry/real arena mismatch (%zu vs %zu)", dryb.off, b.off);
+        return -21;
+    }
+    return 0;
+}
+
+
+}  // namespace dxmi

@@ -21,7 +21,8 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     int bh = 128 / bw;
     if (bh > d.out_H) bh = d.out_H;
     const int bn = 128 / (bw * bh);
-    if (bw * bh * bn != 128 || d.out_W % bw || d.out_H % bh) {
+    const bool ragged_1d = d.out_H == 1 && d.N == 1 && !d.a_batched;  // plain GEMM rows: the last tile may be partial
+    if (bw * bh * bn != 128 || (d.out_W % bw && !ragged_1d) || d.out_H % bh) {
         snprintf(g_op_err, sizeof g_op_err, "unsupported output geometry %dx%d (need power-of-two tiles of 128 pixels)",
                  d.out_H, d.out_W);
         return -10;
@@ -29,7 +30,7 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     p.bw = bw;
     p.bh = bh;
     p.bn = bn;
-    p.tiles_w = d.out_W / bw;
+    p.tiles_w = (d.out_W + bw - 1) / bw;
     p.tiles_h = d.out_H / bh;
     p.stride = d.stride > 0 ? d.stride : 1;
     p.a_batched = d.a_batched;
@@ -75,6 +76,8 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             block_n = d.b_rows;
         else if (d.b_rows % 256 == 0 && g_opt_block_n_256)
             block_n = 256;
+        else if (d.b_rows % 192 == 0)
+            block_n = 192;
         else if (d.b_rows >= 128)
             block_n = 128;
         else if (d.b_rows >= 64)

@@ -27,7 +27,7 @@ struct TileCfg {
     // Keep >= 2 CTAs per SM for BLOCK_N <= 128 (3 x 32 KB = 96 KB) and a 4-deep ring for BLOCK_N = 256.
     static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 3 : 4);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
-    static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;  // power of two
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -370,6 +370,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int block_n, int m_tiles, int n_ti
         case 32: return launch_t<32>(p, m_tiles, n_tiles, batch, stream);
         case 64: return launch_t<64>(p, m_tiles, n_tiles, batch, stream);
         case 128: return launch_t<128>(p, m_tiles, n_tiles, batch, stream);
+        case 192: return launch_t<192>(p, m_tiles, n_tiles, batch, stream);
         case 256: return launch_t<256>(p, m_tiles, n_tiles, batch, stream);
         default:
             snprintf(g_err, sizeof g_err, "unsupported block_n %d", block_n);

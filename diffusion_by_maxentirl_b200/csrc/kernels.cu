@@ -614,6 +614,24 @@ void edm_step(const float* x, const float* F, const float* z, const float* coef,
     edm_step_k<<<(int)blocks, 256, 0, st>>>(x, F, z, coef, xn, mean, CHW / 4, total4);
 }
 
+// per-step coefficient broadcast for the EDM rollout: coef[n] = v[2..6], x_scale[n] = v[0], t[n] = v[1]
+struct Coef7 {
+    float v[7];
+};
+__global__ void edm_fill_k(float* __restrict__ coef, float* __restrict__ x_scale, float* __restrict__ t, int N, Coef7 c) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    x_scale[n] = c.v[0];
+    t[n] = c.v[1];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) coef[n * 5 + j] = c.v[2 + j];
+}
+void edm_fill(float* coef, float* x_scale, float* t, int N, const float* row7, cudaStream_t st) {
+    Coef7 c;
+    for (int j = 0; j < 7; ++j) c.v[j] = row7[j];
+    edm_fill_k<<<(N + 127) / 128, 128, 0, st>>>(coef, x_scale, t, N, c);
+}
+
 // ============================================================================================ value head
 
 __global__ void value_head_k(const bf16* __restrict__ h, int HW, int C, const float* __restrict__ lin_w,

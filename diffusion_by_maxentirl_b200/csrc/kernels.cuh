@@ -66,6 +66,9 @@ void var_step(const float* x, const float* eps, const float* z, const float* a, 
 void edm_step(const float* x, const float* F, const float* z, const float* coef, float* xn, float* mean, int N, int CHW,
               cudaStream_t st);
 
+// broadcast one EDM schedule row {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down, sigma_noise} to per-sample tables
+void edm_fill(float* coef, float* x_scale, float* t, int N, const float* row7, cudaStream_t st);
+
 // ---- value head (modules.py:150-158): relu -> sum over HW -> Linear(C,1) -> Linear(1,1) ---------------------------------
 void value_head(const bf16* h, int N, int HW, int C, const float* lin_w, const float* lin_b, const float* scale_w,
                 const float* scale_b, float* out, cudaStream_t st);

@@ -1,0 +1,127 @@
+"""Drop-in for the reference's models/DxMI/openai_diffusion.py::OpenAIDiffusion (:10-127) on the B200 path.
+
+`sample()` is one `dxmi_edm_rollout` call (T x [c_in-scaled U-Net forward + fused EDM ancestral transition]);
+`sample_step()` is one U-Net forward plus one `dxmi_edm_step`."""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from diffusion_by_maxentirl_b200 import _lib as L
+from diffusion_by_maxentirl_b200.schedule import EdmSchedule
+
+
+def _inner(net):
+    return net.module if hasattr(net, "module") else net
+
+
+class OpenAIDiffusion:
+    def __init__(self, model, diffusion, n_timesteps, sample_shape, class_cond=False, num_classes=0,
+                 trainable_beta=False, sigma_min=0.002, sigma_max=80., stochastic_last=False, rho=7.0):
+        self.net = model
+        self.diffusion = diffusion
+        self.class_cond = class_cond
+        self.num_classes = num_classes
+        self.sample_shape = sample_shape
+        self.n_timesteps = n_timesteps
+        self.sigma_max = sigma_max
+        s = EdmSchedule(n_timesteps, sigma_min, sigma_max, rho, stochastic_last)
+        self.sigmas, self.sigma_down, self.sigma_up = s.sigmas, s.sigma_down, s.sigma_up
+        self.trainable_beta = trainable_beta
+        if trainable_beta:
+            self.net.register_parameter("log_betas", nn.Parameter(torch.log(self.sigma_up.clamp(1e-3))))
+        else:
+            self.net.register_buffer("log_betas", torch.log(self.sigma_up))
+
+    def get_ancestral_step(self, sigmas):
+        sigma_from, sigma_to = sigmas[:-1], sigmas[1:]
+        sigma_up = (sigma_to**2 * (sigma_from**2 - sigma_to**2) / sigma_from**2) ** 0.5
+        sigma_down = (sigma_to**2 - sigma_up**2) ** 0.5
+        return sigma_down, sigma_up
+
+    def train(self):
+        self.net.train()
+
+    def eval(self):
+        self.net.eval()
+
+    def parameters(self):
+        return self.net.parameters()
+
+    # ------------------------------------------------------------------ noise scale actually applied (reference :79-92)
+    def _noise_sigma(self, indices):
+        """indices: CPU long tensor [B] -> CPU float tensor [B] of the per-step noise scale."""
+        sigma_up = self.sigma_up[indices]
+        if not self.trainable_beta:
+            return sigma_up
+        sigma = torch.exp(_inner(self.net).log_betas.detach().float().cpu()[indices])
+        if self.trainable_beta == "fix_last":
+            terminal = indices == self.n_timesteps - 1
+            sigma = sigma * ~terminal + sigma_up * terminal
+        elif self.trainable_beta == "fix_last3":
+            non_terminal = indices < self.n_timesteps - 3
+            sigma = sigma * non_terminal + sigma_up * (~non_terminal)
+        return sigma
+
+    def sample_step(self, x, indices, noise=None, **model_kwargs):
+        device = x.device
+        indices = indices.cpu()
+        B = x.shape[0]
+        x = x.detach().contiguous().float()
+        sigma = self.sigmas[indices]
+        c_skip, c_out, c_in = self.diffusion.get_scalings(sigma)
+        rescaled_t = 1000 * 0.25 * torch.log(sigma + 1e-44)
+        F = self.net(x, rescaled_t.to(device), x_scale=c_in.to(device), **model_kwargs)
+        s_noise = self._noise_sigma(indices)
+        coef = torch.stack([c_skip, c_out, sigma, self.sigma_down[indices], s_noise], dim=1).float().contiguous().to(device)
+        z = torch.randn_like(x) if noise is None else noise.to(device=device, dtype=torch.float32).contiguous()
+        xn, mu = torch.empty_like(x), torch.empty_like(x)
+        L.check(L.lib().dxmi_edm_step(L.ptr(x), L.ptr(F), L.ptr(z), L.ptr(coef), L.ptr(xn), L.ptr(mu), B, x[0].numel(),
+                                      L.stream_ptr()), "dxmi_edm_step")
+        return {"sample": xn, "mean": mu, "sigma": s_noise.to(device).clamp(1e-4, None)}
+
+    def sample(self, n_sample, device, i_class=None, enable_grad=False, x0=None, noise=None):
+        """Reference OpenAIDiffusion.sample (:101-127).  `noise` (optional, parity contract): the T per-step z tensors
+        ([T, B, C, H, W] or a list); without it, `torch.randn_like` draws are made in the reference's order."""
+        if enable_grad:
+            raise NotImplementedError("enable_grad=True (backward through the rollout) is not built on the B200 path")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("OpenAIDiffusion.sample runs on CUDA only (no CPU fallback)")
+        T, B = self.n_timesteps, int(n_sample)
+        shape = tuple(self.sample_shape)
+        if self.class_cond:
+            if i_class is None:
+                i_class = torch.randint(0, self.num_classes, (B,), device=device)
+            elif isinstance(i_class, int):
+                i_class = torch.tensor([i_class] * B, device=device, dtype=torch.long)
+            i_class = i_class.to(device=device, dtype=torch.long).contiguous()
+        else:
+            i_class = None
+        net = _inner(self.net)
+        net._check_eval()
+        buf = torch.empty(T + 1, B, *shape, device=device)
+        buf[0] = (torch.randn(B, *shape, device=device) * self.sigma_max) if x0 is None else x0.to(device)
+        if noise is None:
+            for i in range(T):
+                buf[1 + i] = torch.randn(B, *shape, device=device)
+        else:
+            nz = (torch.stack(list(noise)) if not torch.is_tensor(noise) else noise).to(device=device, dtype=torch.float32)
+            assert nz.shape == (T, B, *shape)
+            buf[1:] = nz
+        h = net._ensure_handle(device)
+        idx = torch.arange(T)
+        sigma = self.sigmas[idx]
+        c_skip, c_out, c_in = self.diffusion.get_scalings(sigma)
+        s_noise = self._noise_sigma(idx)
+        sched = torch.stack([c_in, 1000 * 0.25 * torch.log(sigma + 1e-44), c_skip, c_out, sigma, self.sigma_down[idx],
+                             s_noise], dim=1).float().contiguous()
+        l_sample = torch.empty(T + 1, B, *shape, device=device)
+        mean = torch.empty(T, B, *shape, device=device)
+        L.check(
+            L.lib().dxmi_edm_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), T, L.ptr(buf), L.ptr(i_class),
+                                     L.ptr(l_sample), L.ptr(mean), B, L.stream_ptr()),
+            "dxmi_edm_rollout")
+        sig_dev = s_noise.clamp(1e-4, None).to(device)
+        return {"sample": l_sample[T], "l_sample": [l_sample[i] for i in range(T + 1)], "y": i_class,
+                "mean": [mean[i] for i in range(T)], "sigma": [sig_dev[i].repeat(B) for i in range(T)]}

@@ -132,3 +132,14 @@ def group_norm(x1, gamma, beta, eps, silu, x2=None, film=None, groups=32):
         "group_norm",
     )
     return out
+
+
+def attention(qk, vt, heads, scale, q_col0=0, k_col0=None):
+    """Fused d=64 attention: qk bf16 [B, seq, 2C] (q | k, head-major), vt bf16 [B, C, seq] -> bf16 [B, seq, C]."""
+    B, seq, ld = qk.shape
+    Cc = heads * 64
+    assert vt.shape == (B, Cc, seq) and qk.dtype == vt.dtype == torch.bfloat16
+    out = torch.empty(B, seq, Cc, dtype=torch.bfloat16, device=qk.device)
+    L.check(L.lib().dxmi_op_attention(L.ptr(qk), ld, q_col0, Cc if k_col0 is None else k_col0, L.ptr(vt), L.ptr(out), Cc, B,
+                                      heads, seq, scale, L.stream_ptr()), "attention")
+    return out

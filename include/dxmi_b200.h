@@ -149,6 +149,11 @@ int dxmi_op_group_norm(const void* x1, int C1, int ld1, const void* x2, int C2, 
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
                        float* partial_ws, void* out, dxmi_stream_t stream);
 int dxmi_op_gn_ws_floats(int N, int HW, int groups);
+/* Fused d=64 multi-head attention (QKVAttentionLegacy.forward, models/cm/unet.py:413-441): qk bf16 [B, seq, ld_qk] with
+ * head h's queries at column q_col0 + 64h and keys at k_col0 + 64h; vt bf16 [B, heads*64, seq] (V transposed);
+ * out bf16 [B, seq, ldo], head h at column 64h; scale multiplies the logits (d^-1/2). seq % 128 == 0. */
+int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
+                      int heads, int seq, float scale, dxmi_stream_t stream);
 
 /* -------------------------------------------------------------------------------------------- misc */
 const char* dxmi_last_error(void);
