@@ -1,6 +1,35 @@
 """B200-native (sm_100a) implementation of the DxMI few-step sampler rollout hot path.
 
 Public surface mirrors the reference's module interfaces (see `models/` for the drop-in classes) on top of the
-C-ABI library `libdxmi_b200.so` (`include/dxmi_b200.h`).
+C-ABI library `libdxmi_b200.so` (`include/dxmi_b200.h`).  `install()` binds the drop-ins into an importable checkout
+of the reference (swyoon/Diffusion-by-MaxEntIRL) so its unchanged scripts and YAML `_target_`s resolve to this path.
 """
+import importlib
+
 __version__ = "0.1.0"
+
+# (reference module, attribute) -> (drop-in module, attribute): exactly the symbols on the hot path
+_BINDINGS = [
+    ("models.DxMI.unet_small", "Model", "models.DxMI.unet_small", "Model"),
+    ("models.DxMI.var_sampler", "VARSampler", "models.DxMI.var_sampler", "VARSampler"),
+    ("models.DxMI.openai_diffusion", "OpenAIDiffusion", "models.DxMI.openai_diffusion", "OpenAIDiffusion"),
+    ("models.cm.unet", "UNetModel", "models.cm.unet", "UNetModel"),
+    ("models.cm.karras_diffusion", "KarrasDenoiser", "models.cm.karras_diffusion", "KarrasDenoiser"),
+    ("models.cm.script_util", "create_model", "models.cm.script_util", "create_model"),
+    ("models.cm.script_util", "create_model_and_diffusion", "models.cm.script_util", "create_model_and_diffusion"),
+    ("models.modules", "IGEBMEncoderV2", "models.modules", "IGEBMEncoderV2"),
+]
+
+
+def install():
+    """Rebind the hot-path classes of the reference's `models` package (which must be importable, i.e. the reference
+    checkout is on sys.path) to the B200 drop-ins, in place.  Everything else in the reference (trainer, CLIs, FID,
+    loaders, `models.value.TimeIndependentValue`, ...) is left untouched and keeps calling the same names.
+    Returns the list of rebound `module.attr` names."""
+    done = []
+    for ref_mod, ref_attr, our_mod, our_attr in _BINDINGS:
+        ref = importlib.import_module(ref_mod)
+        ours = importlib.import_module(__name__ + "." + our_mod)
+        setattr(ref, ref_attr, getattr(ours, our_attr))
+        done.append(f"{ref_mod}.{ref_attr}")
+    return done

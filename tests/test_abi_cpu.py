@@ -104,3 +104,35 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
                 assert "/root/reference" not in text, os.path.join(dirpath, f)
+
+
+def test_install_rebinds_reference_symbols():
+    """`install()` patches the reference's own module objects in place (runs only where a reference checkout exists -
+    the build container; the GPU box has none and nothing else in the suite needs it)."""
+    import sys
+
+    ref = os.environ.get("DXMI_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "models")):
+        pytest.skip("no reference checkout here")
+    import subprocess
+
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import diffusion_by_maxentirl_b200 as pkg\n"
+        "b = pkg.install()\n"
+        "import models.DxMI.unet_small as u, models.cm.script_util as s, models.modules as m, models.value as v\n"
+        "from diffusion_by_maxentirl_b200.native import NativeNet\n"
+        "assert issubclass(u.Model, NativeNet) and issubclass(m.IGEBMEncoderV2, NativeNet)\n"
+        "net, diff = s.create_model_and_diffusion(image_size=64, class_cond=True, learn_sigma=False, num_channels=64,"
+        " num_res_blocks=1, channel_mult='1,2', num_heads=4, num_head_channels=64, num_heads_upsample=-1,"
+        " attention_resolutions='32', dropout=0.0, use_checkpoint=False, use_scale_shift_norm=True,"
+        " resblock_updown=True, use_fp16=True, use_new_attention_order=False, weight_schedule='uniform')\n"
+        "assert isinstance(net, NativeNet)\n"
+        "val = v.TimeIndependentValue(m.IGEBMEncoderV2(in_chan=3, out_chan=1, use_spectral_norm=False, keepdim=False,"
+        " out_activation='linear', avg_pool_dim=1, learn_out_scale=True, nh=128))\n"
+        "assert hasattr(m, 'ResBlockV2') and hasattr(m, 'process_single_t')\n"
+        "print(len(b))\n" % (ref, ROOT)
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().endswith("8")
