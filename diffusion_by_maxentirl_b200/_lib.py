@@ -72,6 +72,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("softmax", C.c_int),
         ("block_n", C.c_int),
+        ("gn_stats", C.c_void_p),
     ]
 
 
@@ -102,6 +103,7 @@ SYMBOLS = {
     "dxmi_op_attention": (_I, [_VP, _LL, _I, _I, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
     "dxmi_last_error": (C.c_char_p, []),
     "dxmi_set_option": (_I, [C.c_char_p, _I]),
+    "dxmi_set_debug_buffer": (_I, [_VP]),
     "dxmi_launch_count": (_LL, []),
     "dxmi_gemm_timing": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL)]),
     "dxmi_plan_gemm_flops": (C.c_double, [_VP, _I]),

@@ -24,12 +24,25 @@ int dxmi_set_option(const char* name, int value) {
         set_block_n_256(value);
         return 0;
     }
+    if (!strcmp(name, "gemm_version")) {
+        set_gemm_version(value);
+        return 0;
+    }
+    if (!strcmp(name, "dbg_mode")) {
+        set_dbg_mode(value);
+        return 0;
+    }
     if (!strcmp(name, "time_gemms")) {
         set_time_gemms(value);
         return 0;
     }
     set_err("unknown option");
     return -1;
+}
+
+int dxmi_set_debug_buffer(void* dev_ptr) {
+    set_dbg_times(dev_ptr);
+    return 0;
 }
 
 int dxmi_gemm_timing(double* ms_total, double* flops_total, long long* launches) {

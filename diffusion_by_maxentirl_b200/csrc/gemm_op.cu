@@ -8,6 +8,12 @@
 namespace dxmi {
 
 static int g_opt_block_n_256 = 1;
+static int g_opt_dbg_mode = 0;
+static int g_opt_gemm_v = 2;
+void set_gemm_version(int v) { g_opt_gemm_v = v; }
+static long long* g_dbg_times = nullptr;
+void set_dbg_times(void* p) { g_dbg_times = (long long*)p; }
+void set_dbg_mode(int v) { g_opt_dbg_mode = v; }
 void set_block_n_256(int v) { g_opt_block_n_256 = v; }
 
 static thread_local char g_op_err[512] = "";
@@ -105,11 +111,32 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     p.act = d.act;
     p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
     p.softmax = d.softmax;
+    p.dbg_mode = g_opt_dbg_mode;
+    p.dbg_times = g_dbg_times;
 
     op->block_n = block_n;
     op->m_tiles = m_tiles;
     op->n_tiles = n_tiles;
     op->batch = d.batch > 0 ? d.batch : 1;
+    p.m_tiles = m_tiles;
+    p.n_tiles = n_tiles;
+    p.batch_count = op->batch;
+    p.stats = nullptr;
+    op->use_v2 = 0;
+    if (g_opt_gemm_v == 2 && conv_gemm_v2_supported(p, block_n)) {
+        const int eb = p.out_fp32 ? 4 : 2;
+        r = make_out_map(&p.out_map, p.out, eb, p.N_total, p.M_total, op->batch, p.ldo, p.out_batch_stride);
+        if (r) return r;
+        if (p.residual) {
+            r = make_out_map(&p.res_map, p.residual, 2, p.N_total, p.M_total, op->batch, p.ldr, p.res_batch_stride);
+            if (r) return r;
+        }
+        p.stats = d.gn_stats;
+        op->use_v2 = 1;
+    } else if (d.gn_stats) {
+        snprintf(g_op_err, sizeof g_op_err, "gn_stats requested but the persistent kernel does not support this GEMM");
+        return -12;
+    }
     op->flops = 2.0 * (double)p.M_total * op->batch * (double)d.b_rows * (double)k_total;
     return 0;
 }
@@ -141,14 +168,19 @@ int gemm_timing_collect(double* ms_total, double* flops_total, long long* launch
     return 0;
 }
 
+static int launch_any(const GemmOp& op, cudaStream_t st) {
+    if (op.use_v2) return launch_conv_gemm_v2(op.p, op.block_n, st);
+    return launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
+}
+
 int run_gemm(const GemmOp& op, cudaStream_t st) {
-    if (!g_time_gemms) return launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
+    if (!g_time_gemms) return launch_any(op, st);
     TimedLaunch t;
     cudaEventCreate(&t.a);
     cudaEventCreate(&t.b);
     t.flops = op.flops;
     cudaEventRecord(t.a, st);
-    int r = launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
+    int r = launch_any(op, st);
     cudaEventRecord(t.b, st);
     g_timed.push_back(t);
     return r;

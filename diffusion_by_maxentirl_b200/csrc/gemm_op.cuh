@@ -7,12 +7,16 @@ namespace dxmi {
 struct GemmOp {
     ConvGemmParams p;
     int block_n, m_tiles, n_tiles, batch;
+    int use_v2;  // persistent kernel (gemm_tc2.cu)
     double flops;  // algorithmic 2*M*N*K of this launch
 };
 
 int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op);
 int run_gemm(const GemmOp& op, cudaStream_t st);
 void set_block_n_256(int v);
+void set_dbg_mode(int v);
+void set_gemm_version(int v);
+void set_dbg_times(void* p);
 void set_time_gemms(int v);
 int gemm_timing_collect(double* ms_total, double* flops_total, long long* launches);
 const char* gemm_op_last_error();

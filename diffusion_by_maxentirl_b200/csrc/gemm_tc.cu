@@ -30,6 +30,17 @@ struct TileCfg {
     static constexpr int TMEM_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;  // power of two
 };
 
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_STAMP(slot)                                                                                      \
+    if (p.dbg_times) {                                                                                       \
+        const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z); \
+        p.dbg_times[cta * 8 + (slot)] = gtimer();                                                            \
+    }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_LRELU02) return v > 0.f ? v : 0.2f * v;
     if (act == ACT_SILU) return v / (1.f + __expf(-v));
@@ -52,6 +63,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { DBG_STAMP(0); }
 
     const int m_tile = blockIdx.x;
     const int n_tile = blockIdx.y;
@@ -80,6 +92,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_kernel(const __grid_con
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    if (threadIdx.x == 0) { DBG_STAMP(1); }
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -125,18 +138,22 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_kernel(const __grid_con
                 const uint32_t ph = (it / STAGES) & 1;
                 ptx::mbar_wait(&full_bar[stage], ph);
                 ptx::tc_fence_after();
+                if (it == 0) { DBG_STAMP(2); }
                 const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 const uint32_t sb = sa + A_STAGE_BYTES;
                 const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
                 const uint64_t db = ptx::make_kmajor_sw128_desc(sb);
+                if (p.dbg_mode != 1) {
 #pragma unroll
-                for (int k = 0; k < TILE_K / 16; ++k) {
-                    // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                    ptx::umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TILE_K / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                        ptx::umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
                 ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
             }
             ptx::umma_commit(&tmem_full_bar);  // accumulator complete
+            DBG_STAMP(3);
         }
         __syncwarp();
     } else {
@@ -149,6 +166,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_kernel(const __grid_con
 
         ptx::mbar_wait(&tmem_full_bar, 0);
         ptx::tc_fence_after();
+        if (threadIdx.x == 64) { DBG_STAMP(4); }
 
         const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         const float bias_m = (p.bias && p.bias_along_m && row_ok) ? p.bias[row] : 0.f;
@@ -266,6 +284,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_kernel(const __grid_con
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) { DBG_STAMP(5); }
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -337,6 +356,31 @@ int make_mat_map(CUtensorMap* out, const void* base, int K, int rows, int batch,
     }
     return 0;
 }
+
+int make_out_map(CUtensorMap* out, const void* base, int elem_bytes, int cols, int rows, int batch, long long row_stride,
+                 long long batch_stride) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return -1;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride * elem_bytes,
+                             (cuuint64_t)(batch > 1 ? batch_stride : row_stride * rows) * elem_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / elem_bytes), 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled(out) failed: %d (cols=%d rows=%d batch=%d rs=%lld bs=%lld eb=%d)",
+                 (int)r, cols, rows, batch, row_stride, batch_stride, elem_bytes);
+        return -2;
+    }
+    return 0;
+}
+
+void gemm_set_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); }
 
 template <int BLOCK_N>
 static int launch_t(const ConvGemmParams& p, int m_tiles, int n_tiles, int batch, cudaStream_t stream) {

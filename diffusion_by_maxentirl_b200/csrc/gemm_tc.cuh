@@ -55,6 +55,13 @@ struct ConvGemmParams {
     int act;
     float alpha;               // accumulator scale (applied first)
     int softmax;               // row softmax over the BLOCK_N columns (needs N_total == BLOCK_N)
+    // ---- persistent kernel (gemm_tc2.cu) only
+    CUtensorMap out_map;       // (cols, rows, batch) over `out`, box (128 bytes of columns, 128 rows, 1), SWIZZLE_128B
+    CUtensorMap res_map;       // same geometry over `residual` (bf16)
+    int m_tiles, n_tiles, batch_count;
+    float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/32][N_total][2] (sum, sumsq) or null
+    long long* dbg_times;      // profiling only: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA, or null
+    int dbg_mode;              // profiling only: 1 = skip the MMAs (TMA ring throughput), 2 = skip the epilogue stores
 };
 
 // Launches the kernel; block_n in {32, 64, 128, 256}. Returns cudaError_t as int.
@@ -66,6 +73,13 @@ int make_act_map(CUtensorMap* out, const void* base, int C, int W, int H, int N,
 // Host helper: encode a rank-3 (k, rows, batch) bf16 K-major operand map. Box = (64, box_rows, 1).
 int make_mat_map(CUtensorMap* out, const void* base, int K, int rows, int batch, long long row_stride,
                  long long batch_stride, int box_rows);
+
+// Persistent variant (gemm_tc2.cu): TMEM double buffering, TMA-store epilogue, fused GroupNorm partial statistics.
+int launch_conv_gemm_v2(const ConvGemmParams& p, int block_n, cudaStream_t stream);
+bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n);
+// Host helper: (cols, rows, batch) map with a 128-byte x 128-row box for the epilogue (elem_bytes 2 = bf16, 4 = fp32).
+int make_out_map(CUtensorMap* out, const void* base, int elem_bytes, int cols, int rows, int batch, long long row_stride,
+                 long long batch_stride);
 
 const char* gemm_last_error();
 

@@ -63,6 +63,7 @@ def conv_gemm(
     alpha=1.0,
     softmax=False,
     res_batch_stride=0,
+    gn_stats=None,
 ):
     """srcs: list of (tensor, C_used, ld) NHWC bf16 sources; segs: list of (src_index, taps)."""
     d = L.GemmDesc()
@@ -114,6 +115,9 @@ def conv_gemm(
     d.alpha = alpha
     d.softmax = int(softmax)
     d.block_n = block_n
+    if gn_stats is not None:
+        assert gn_stats.dtype == torch.float32
+        d.gn_stats = gn_stats.data_ptr()
     L.check(L.lib().dxmi_op_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
 

@@ -140,6 +140,7 @@ typedef struct {
     float alpha;
     int softmax;
     int block_n;             /* 0 = auto */
+    float* gn_stats;         /* optional: GroupNorm partials of the bf16 output, [rows/32][b_rows][2] (sum, sumsq) */
 } dxmi_gemm_desc;
 
 int dxmi_op_conv_gemm(const dxmi_gemm_desc* d, dxmi_stream_t stream);
@@ -157,7 +158,10 @@ int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, c
 
 /* -------------------------------------------------------------------------------------------- misc */
 const char* dxmi_last_error(void);
-int dxmi_set_option(const char* name, int value); /* "block_n_256" (tile width), "time_gemms" (event-time every GEMM) */
+int dxmi_set_option(const char* name, int value);
+/* profiling only: device buffer of 8 int64 per CTA that the GEMM kernel fills with per-phase globaltimer stamps (NULL = off) */
+int dxmi_set_debug_buffer(void* dev_ptr); /* "block_n_256" (tile width), "time_gemms" (event-time every GEMM), "gemm_version" (1 = one tile per CTA,
+ * 2 = persistent kernel, default), "dbg_mode" (profiling) */
 /* with "time_gemms" on: summed CUDA-event duration / algorithmic FLOPs / count of the tcgen05 GEMM launches since
  * the last call (synchronises on the recorded events) */
 int dxmi_gemm_timing(double* ms_total, double* flops_total, long long* launches);

@@ -169,3 +169,45 @@ def test_group_norm(ops, N, H, C1, C2, silu):
     if silu:
         ref = F.silu(ref)
     assert rel_l2(y, ref.permute(0, 2, 3, 1)) < 4e-3
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_both_gemm_kernel_versions(ops, version):
+    """gemm_version 1 (one tile per CTA, direct stores) and 2 (persistent, TMA-store epilogue) agree with torch."""
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    L.lib().dxmi_set_option(b"gemm_version", version)
+    try:
+        torch.manual_seed(7)
+        dev = "cuda"
+        N, H, Cin, Cout = 6, 16, 128, 192
+        x = nhwc(torch.randn(N, Cin, H, H, device=dev))
+        w = torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin**0.5)
+        b = torch.randn(Cout, device=dev)
+        res = nhwc(torch.randn(N, Cout, H, H, device=dev))
+        wp = ops.pack_conv_weight(w)
+        ref = F.silu(ref_conv(x, w, b) + res.float())
+        for bn in (0, 64, 128, 256):
+            y = ops.conv_gemm([(x, Cin, Cin)], [(0, 9)], wp, N, H, H, bias=b, residual=res, act=2, block_n=bn)
+            assert rel_l2(y.view(N, H, H, Cout), ref) < 4e-3, bn
+    finally:
+        L.lib().dxmi_set_option(b"gemm_version", 2)
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout", [(4, 16, 128, 256), (3, 32, 64, 128), (5, 8, 256, 192)])
+def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
+    """The persistent kernel's fused statistics: per 32-row segment and column, (sum, sumsq) of the bf16 outputs."""
+    torch.manual_seed(8)
+    dev = "cuda"
+    x = nhwc(torch.randn(N, Cin, H, H, device=dev))
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin**0.5)
+    b = torch.randn(Cout, device=dev)
+    wp = ops.pack_conv_weight(w)
+    M = N * H * H
+    stats = torch.full((M // 32, Cout, 2), float("nan"), device=dev)
+    y = ops.conv_gemm([(x, Cin, Cin)], [(0, 9)], wp, N, H, H, bias=b, gn_stats=stats)
+    torch.cuda.synchronize()
+    yf = y.float().view(M // 32, 32, Cout)
+    assert torch.isfinite(stats).all()
+    assert torch.allclose(stats[..., 0], yf.sum(1), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[..., 1], (yf * yf).sum(1), rtol=1e-4, atol=1e-3)
