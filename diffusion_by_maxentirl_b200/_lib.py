@@ -72,6 +72,7 @@ class GemmDesc(C.Structure):
         ("alpha", C.c_float),
         ("softmax", C.c_int),
         ("block_n", C.c_int),
+        ("out_nchw", C.c_int),
         ("gn_stats", C.c_void_p),
     ]
 

@@ -38,6 +38,21 @@ struct Builder {
         return plan.arena + scratch_base[slot];
     }
     bf16* act_alloc(int C, int H, int W) { return (bf16*)alloc((size_t)B * H * W * C * sizeof(bf16)); }
+    // GroupNorm partial-statistics buffer for a GEMM output of B*H*W rows x C columns (null when the fused path
+    // cannot be used for this geometry: a 32-row segment must not straddle two images)
+    float* stats_alloc(int C, int H, int W) {
+        if ((H * W) % 32) return nullptr;
+        return (float*)alloc((size_t)B * H * W / 32 * C * 2 * sizeof(float));
+    }
+    Act new_act(int C, int H, int W, bool want_stats = true) {
+        Act a;
+        a.p = act_alloc(C, H, W);
+        a.C = C;
+        a.H = H;
+        a.W = W;
+        a.stats = want_stats ? stats_alloc(C, H, W) : nullptr;
+        return a;
+    }
 
     void fail(const char* what) {
         if (!err) {
@@ -225,6 +240,79 @@ struct Builder {
         plan.gemm_flops += g.flops;
         op([g](cudaStream_t st) { return run_gemm(g, st); });
     }
+    // GEMM whose fp32 NCHW output pointer is the per-call network output (plan.out)
+    void gemm_to_plan_out(const dxmi_gemm_desc& d) {
+        if (dry || err) return;
+        GemmOp g;
+        int r = prepare_gemm(d, &g);
+        if (r) {
+            err = r;
+            engine_set_error("prepare_gemm: %s", gemm_op_last_error());
+            return;
+        }
+        if (g.use_v2) {
+            fail("internal: network-output GEMM must use the direct-store kernel");
+            return;
+        }
+        plan.gemm_flops += g.flops;
+        Plan* pl = &plan;
+        op([g, pl](cudaStream_t st) {
+            GemmOp g2 = g;
+            g2.p.out = pl->out;
+            return run_gemm(g2, st);
+        });
+    }
+    // last 3x3 convolution of a network: NHWC bf16 -> fp32 NCHW [B, Cout, H, W] at plan.out
+    void conv_out_nchw(const bf16* src, int C, int H, int W, const std::string& wkey, const std::string& bkey, int Cout) {
+        dxmi_gemm_desc d = conv_desc(H, W);
+        set_src(d, 0, src, C, C);
+        add_seg(d, 0, 9);
+        d.b_ptr = packed_rows(wkey, {{{wkey, 0, C}}}, nullptr, nullptr);
+        d.b_rows = Cout;
+        d.b_ld = 9LL * C;
+        d.bias = f32(bkey);
+        d.out = (void*)16;  // placeholder, patched per call
+        d.ldo = Cout;
+        d.out_fp32 = 1;
+        d.out_nchw = 1;
+        d.block_n = 32;
+        gemm_to_plan_out(d);
+    }
+    // Y[B, O] (fp32) = silu(X[B, K]) . W^T + b for a row-stack of Linear layers (every ResBlock's time-embedding
+    // projection in one tensor-core GEMM; unet_small.py:123, cm/unet.py:203-209)
+    void batched_emb_projection(const float* x, int K, const std::string& name, const std::vector<std::string>& wkeys,
+                                const std::vector<std::string>& bkeys, float* y, int O) {
+        bf16* xb = (bf16*)alloc((size_t)B * K * sizeof(bf16));
+        const int Bn = B;
+        op([=](cudaStream_t st) {
+            silu_to_bf16(x, xb, (long long)Bn * K, st);
+            return (int)cudaGetLastError();
+        });
+        std::vector<std::vector<PackPart>> groups;
+        for (auto& k : wkeys) groups.push_back({{k, 0, K}});
+        dxmi_gemm_desc d;
+        memset(&d, 0, sizeof d);
+        d.N = 1;
+        d.H = 1;
+        d.W = B;
+        d.out_H = 1;
+        d.out_W = B;
+        d.stride = 1;
+        d.batch = 1;
+        set_src(d, 0, xb, K, K);
+        add_seg(d, 0, 1);
+        d.b_ptr = packed_rows(name + ".weight", groups, nullptr, nullptr);
+        d.b_rows = O;
+        d.b_ld = K;
+        d.bias = concat_f32(name + ".bias", bkeys);
+        d.out = y;
+        d.ldo = O;
+        d.out_fp32 = 1;
+        d.alpha = 1.f;
+        d.rows_per_image = 1;
+        if (K % 64 || O % 8) fail("batched_emb_projection: K must be a multiple of 64 and O of 8");
+        gemm(d);
+    }
     dxmi_gemm_desc conv_desc(int H, int W) {
         dxmi_gemm_desc d;
         memset(&d, 0, sizeof d);
@@ -262,6 +350,17 @@ struct Builder {
         const int C1 = x1.C, C2 = x2.C;
         const int Bn = B;
         if ((C1 + C2) % 8 || (C1 % 8) || (C1 + C2) > 2048) fail("group_norm: unsupported channel count");
+        const float* st1 = x1.stats;
+        const float* st2 = x2.stats;
+        const long long pairs = (long long)(HW / 32) * ((C1 + C2) / 32);
+        if (st1 && (C2 == 0 || st2) && HW % 32 == 0 && pairs <= 4096) {
+            // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
+            op([=](cudaStream_t st) {
+                gn_apply_fused(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, st2, out, st);
+                return (int)cudaGetLastError();
+            });
+            return;
+        }
         op([=](cudaStream_t st) {
             gn_stats(p1, C1, C1, p2, C2, C2, Bn, HW, 32, ws, slabs, st);
             gn_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, ws, slabs, out, st);

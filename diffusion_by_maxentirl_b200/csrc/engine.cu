@@ -167,6 +167,7 @@ struct DdpmBuilder : Builder {
         bf16* g1 = (bf16*)scratch(0, (size_t)B * HW * Cin * 2);
         group_norm(xa, xb, p + ".norm1", 1e-6f, 1, nullptr, 0, g1);
         bf16* h1 = (bf16*)scratch(1, (size_t)B * HW * Cout * 2);
+        float* h1_stats = (HW % 32 == 0) ? (float*)scratch(6, (size_t)B * HW / 32 * Cout * 2 * sizeof(float)) : nullptr;
         {
             long long K;
             int rows;
@@ -182,13 +183,14 @@ struct DdpmBuilder : Builder {
             d.ldrv = tproj_ld;
             d.out = h1;
             d.ldo = Cout;
+            d.gn_stats = h1_stats;
             gemm(d);
         }
         tproj_off += Cout;
         bf16* g2 = (bf16*)scratch(0, (size_t)B * HW * Cout * 2);
-        Act h1a{h1, Cout, H, W};
+        Act h1a{h1, Cout, H, W, h1_stats};
         group_norm(h1a, Act{}, p + ".norm2", 1e-6f, 1, nullptr, 0, g2);
-        Act out{act_alloc(Cout, H, W), Cout, H, W};
+        Act out = new_act(Cout, H, W);
         {
             dxmi_gemm_desc d = conv_desc(H, W);
             set_src(d, 0, g2, Cout, Cout);
@@ -218,6 +220,7 @@ struct DdpmBuilder : Builder {
             d.b_ld = K;
             d.out = out.p;
             d.ldo = Cout;
+            d.gn_stats = out.stats;
             gemm(d);
         }
         return out;
@@ -227,7 +230,7 @@ struct DdpmBuilder : Builder {
         const int C = x.C, H = x.H, W = x.W, HW = H * W;
         bf16* hn = (bf16*)scratch(0, (size_t)B * HW * C * 2);
         group_norm(x, Act{}, p + ".norm", 1e-6f, 0, nullptr, 0, hn);
-        Act out{act_alloc(C, H, W), C, H, W};
+        Act out = new_act(C, H, W);
         bf16* o = (bf16*)scratch(4, (size_t)B * HW * C * 2);
         const float scale = 1.f / sqrtf((float)C);
         if (HW <= 64) {
@@ -361,6 +364,7 @@ struct DdpmBuilder : Builder {
             d.ldr = C;
             d.out = out.p;
             d.ldo = C;
+            d.gn_stats = out.stats;
             gemm(d);
         }
         return out;
@@ -368,7 +372,7 @@ struct DdpmBuilder : Builder {
 
     Act downsample(const std::string& p, Act x) {
         const int C = x.C;
-        Act out{act_alloc(C, x.H / 2, x.W / 2), C, x.H / 2, x.W / 2};
+        Act out = new_act(C, x.H / 2, x.W / 2);
         dxmi_gemm_desc d = conv_desc(x.H, x.W);
         d.out_H = x.H / 2;
         d.out_W = x.W / 2;
@@ -382,6 +386,7 @@ struct DdpmBuilder : Builder {
         d.bias = f32(p + ".conv.bias");
         d.out = out.p;
         d.ldo = C;
+        d.gn_stats = out.stats;
         gemm(d);
         return out;
     }
@@ -395,7 +400,7 @@ struct DdpmBuilder : Builder {
             upsample2x(xp, up, Bn, H, W, C, st);
             return (int)cudaGetLastError();
         });
-        Act out{act_alloc(C, H2, W2), C, H2, W2};
+        Act out = new_act(C, H2, W2);
         dxmi_gemm_desc d = conv_desc(H2, W2);
         set_src(d, 0, up, C, C);
         add_seg(d, 0, 9);
@@ -405,6 +410,7 @@ struct DdpmBuilder : Builder {
         d.bias = f32(p + ".conv.bias");
         d.out = out.p;
         d.ldo = C;
+        d.gn_stats = out.stats;
         gemm(d);
         return out;
     }
@@ -459,24 +465,22 @@ struct DdpmBuilder : Builder {
                 wk.push_back(p + ".temb_proj.weight");
                 bk.push_back(p + ".temb_proj.bias");
             }
-            const float* Wc = concat_f32("temb_proj.weight", wk);
-            const float* bc = concat_f32("temb_proj.bias", bk);
             const float* w0 = f32("temb.dense.0.weight");
             const float* b0 = f32("temb.dense.0.bias");
             const float* w1 = f32("temb.dense.1.weight");
             const float* b1 = f32("temb.dense.1.bias");
-            float* tp = tproj;
             op([=](cudaStream_t st) {
                 timestep_embedding(pl->t, te, Bn, ch, 0, st);
                 linear_f32(te, ch, w0, b0, t1, temb_ch, Bn, ch, temb_ch, 0, 0, st);
                 linear_f32(t1, temb_ch, w1, b1, temb, temb_ch, Bn, temb_ch, temb_ch, 2, 0, st);
-                linear_f32(temb, temb_ch, Wc, bc, tp, TP, Bn, temb_ch, TP, 2, 0, st);
                 return (int)cudaGetLastError();
             },
-               4);
+               3);
+            batched_emb_projection(temb, temb_ch, "temb_proj", wk, bk, tproj, TP);
         }
         // ---- conv_in
-        Act h0{act_alloc(ch, R, R), ch, R, R};
+        if (a.in_channels != 3 || ch % 32 || ch > 512 || (R * R) % 128) fail("DDPM conv_in: unsupported geometry");
+        Act h0 = new_act(ch, R, R, /*want_stats=*/false);
         {
             const float* w = f32("conv_in.weight");
             const float* b = f32("conv_in.bias");
@@ -526,15 +530,7 @@ struct DdpmBuilder : Builder {
         // ---- head
         bf16* g = (bf16*)scratch(0, (size_t)B * R * R * h.C * 2);
         group_norm(h, Act{}, "norm_out", 1e-6f, 1, nullptr, 0, g);
-        {
-            const float* w = f32("conv_out.weight");
-            const float* b = f32("conv_out.bias");
-            const int C = h.C, Co = a.out_channels;
-            op([=](cudaStream_t st) {
-                conv3x3_last(g, w, b, pl->out, Bn, C, R, R, Co, st);
-                return (int)cudaGetLastError();
-            });
-        }
+        conv_out_nchw(g, h.C, R, R, "conv_out.weight", "conv_out.bias", a.out_channels);
     }
 };
 
@@ -548,7 +544,8 @@ struct IgebmBuilder : Builder {
         const int nh = a.ch, R = a.resolution;
         Plan* pl = &plan;
         const int Bn = B;
-        Act h{act_alloc(nh, R, R), nh, R, R};
+        if (a.in_channels != 3 || nh % 32 || nh > 512 || (R * R) % 128) fail("IGEBM conv1: unsupported geometry");
+        Act h = new_act(nh, R, R, false);
         {
             const float* w = f32("conv1.weight");
             const float* b = f32("conv1.bias");

@@ -26,6 +26,7 @@ struct Bound {
 struct Act {  // NHWC bf16 activation
     bf16* p = nullptr;
     int C = 0, H = 0, W = 0;
+    float* stats = nullptr;  // GroupNorm partials written by the producing GEMM: [B*H*W/32][C][2], or null
 };
 
 struct Plan {

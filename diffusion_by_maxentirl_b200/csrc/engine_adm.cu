@@ -162,6 +162,7 @@ struct AdmBuilder : Builder {
             xs = Act{xp, Cin, Ho, Wo};
         }
         bf16* h1 = (bf16*)scratch(1, (size_t)B * Ho * Wo * Cout * 2);
+        float* h1_stats = ((Ho * Wo) % 32 == 0) ? (float*)scratch(6, (size_t)B * Ho * Wo / 32 * Cout * 2 * sizeof(float)) : nullptr;
         {
             dxmi_gemm_desc d = conv_desc(Ho, Wo);
             set_src(d, 0, conv_in, Cin, Cin);
@@ -176,13 +177,14 @@ struct AdmBuilder : Builder {
             }
             d.out = h1;
             d.ldo = Cout;
+            d.gn_stats = h1_stats;
             gemm(d);
         }
         bf16* g2 = (bf16*)scratch(0, (size_t)B * Ho * Wo * Cout * 2);
-        group_norm(Act{h1, Cout, Ho, Wo}, Act{}, p + ".out_layers.0", EPS, 1, film_mode && film ? film + film_off : nullptr,
+        group_norm(Act{h1, Cout, Ho, Wo, h1_stats}, Act{}, p + ".out_layers.0", EPS, 1, film_mode && film ? film + film_off : nullptr,
                    film_ld, g2);
         film_off += emb_cols;
-        Act out{act_alloc(Cout, Ho, Wo), Cout, Ho, Wo};
+        Act out = new_act(Cout, Ho, Wo);
         {
             dxmi_gemm_desc d = conv_desc(Ho, Wo);
             set_src(d, 0, g2, Cout, Cout);
@@ -213,6 +215,7 @@ struct AdmBuilder : Builder {
             d.b_ld = K;
             d.out = out.p;
             d.ldo = Cout;
+            d.gn_stats = out.stats;
             gemm(d);
         }
         return out;
@@ -301,7 +304,7 @@ struct AdmBuilder : Builder {
         } else {
             fail("ADM attention: unsupported (sequence length, head dim) combination");
         }
-        Act out{act_alloc(C, H, W), C, H, W};
+        Act out = new_act(C, H, W);
         {
             dxmi_gemm_desc d = conv_desc(H, W);
             set_src(d, 0, o, C, C);
@@ -314,6 +317,7 @@ struct AdmBuilder : Builder {
             d.ldr = C;
             d.out = out.p;
             d.ldo = C;
+            d.gn_stats = out.stats;
             gemm(d);
         }
         return out;
@@ -373,14 +377,11 @@ struct AdmBuilder : Builder {
         film_ld = TP;
         film_off = 0;
         {
-            const float* Wc = concat_f32("emb_layers.weight", wk);
-            const float* bc = concat_f32("emb_layers.bias", bk);
             const float* w0 = f32("time_embed.0.weight");
             const float* b0 = f32("time_embed.0.bias");
             const float* w2 = f32("time_embed.2.weight");
             const float* b2 = f32("time_embed.2.bias");
             const float* table = a.num_classes > 0 ? f32("label_emb.weight") : nullptr;
-            float* fl = film;
             op([=](cudaStream_t st) {
                 // models/cm/unet.py:775-779: emb = time_embed(timestep_embedding(t)) (+ label_emb(y)), all fp32
                 timestep_embedding(pl->t, te, Bn, mc, 1, st);
@@ -390,18 +391,19 @@ struct AdmBuilder : Builder {
                     if (!pl->y) return (int)cudaErrorInvalidValue;  // class-conditional net needs labels
                     embedding_add(emb, table, (const long long*)pl->y, Bn, ted, st);
                 }
-                linear_f32(emb, ted, Wc, bc, fl, TP, Bn, ted, TP, 2, 0, st);  // emb_layers = SiLU -> Linear (:203-209)
                 return (int)cudaGetLastError();
-            }, table ? 5 : 4);
+            }, table ? 4 : 3);
+            // emb_layers = SiLU -> Linear (cm/unet.py:203-209), every ResBlock at once on the tensor cores
+            batched_emb_projection(emb, ted, "emb_layers", wk, bk, film, TP);
         }
         // ---- input conv (x * c_in folded into the load, karras_diffusion.py:349)
-        Act h{act_alloc(inputs[0][0].cout, R, R), inputs[0][0].cout, R, R};
+        Act h = new_act(inputs[0][0].cout, R, R, /*want_stats=*/false);
         {
             const float* w = f32("input_blocks.0.0.weight");
             const float* b = f32("input_blocks.0.0.bias");
             bf16* o = h.p;
             const int Cin = a.in_channels, Co = h.C;
-            if (Co % 8 || Co > 2048) fail("ADM input conv: unsupported channel count");
+            if (Cin != 3 || Co % 32 || Co > 512 || (R * R) % 128) fail("ADM input conv: unsupported geometry");
             op([=](cudaStream_t st) {
                 conv3x3_first(pl->x, pl->x_scale, w, b, o, Bn, Cin, R, R, Co, 0, st);
                 return (int)cudaGetLastError();
@@ -421,15 +423,7 @@ struct AdmBuilder : Builder {
         // ---- head: GN32 -> SiLU -> conv3 (fp32, models/cm/unet.py:738-742, :789-790)
         bf16* g = (bf16*)scratch(0, (size_t)B * R * R * h.C * 2);
         group_norm(h, Act{}, "out.0", EPS, 1, nullptr, 0, g);
-        {
-            const float* w = f32("out.2.weight");
-            const float* b = f32("out.2.bias");
-            const int C = h.C, Co = a.out_channels;
-            op([=](cudaStream_t st) {
-                conv3x3_last(g, w, b, pl->out, Bn, C, R, R, Co, st);
-                return (int)cudaGetLastError();
-            });
-        }
+        conv_out_nchw(g, h.C, R, R, "out.2.weight", "out.2.bias", a.out_channels);
     }
 };
 

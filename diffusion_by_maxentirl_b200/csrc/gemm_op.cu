@@ -23,11 +23,11 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     g_op_err[0] = 0;
     ConvGemmParams& p = op->p;
     memset(&p, 0, sizeof(p));
-    const int bw = d.out_W < 128 ? d.out_W : 128;
+    const bool ragged_1d = d.out_H == 1 && d.N == 1 && !d.a_batched;  // plain GEMM rows: the last tile may be partial
+    const int bw = ragged_1d ? 128 : (d.out_W < 128 ? d.out_W : 128);
     int bh = 128 / bw;
     if (bh > d.out_H) bh = d.out_H;
     const int bn = 128 / (bw * bh);
-    const bool ragged_1d = d.out_H == 1 && d.N == 1 && !d.a_batched;  // plain GEMM rows: the last tile may be partial
     if (bw * bh * bn != 128 || (d.out_W % bw && !ragged_1d) || d.out_H % bh) {
         snprintf(g_op_err, sizeof g_op_err, "unsupported output geometry %dx%d (need power-of-two tiles of 128 pixels)",
                  d.out_H, d.out_W);
@@ -100,6 +100,7 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     p.ldo = d.ldo;
     p.out_batch_stride = d.out_batch_stride;
     p.out_fp32 = d.out_fp32;
+    p.out_nchw = d.out_nchw;
     p.bias = d.bias;
     p.bias_along_m = d.bias_along_m;
     p.rowvec = d.rowvec;

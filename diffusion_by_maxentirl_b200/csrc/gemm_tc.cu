@@ -248,7 +248,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_kernel(const __grid_con
                     for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
                 }
             }
-            if (p.out_fp32) {
+            if (p.out_nchw) {
+                // lanes are consecutive pixels of one image: each column store is a coalesced 128-byte line
+                const long long img = row / p.rows_per_image;
+                const long long pix = row - img * p.rows_per_image;
+                float* o = reinterpret_cast<float*>(p.out) + (img * p.N_total + col) * p.rows_per_image + pix;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (col + j < p.N_total) o[(long long)j * p.rows_per_image] = f[j];
+            } else if (p.out_fp32) {
                 float* o = reinterpret_cast<float*>(p.out) + batch * p.out_batch_stride + row * p.ldo + col;
                 if (col + 32 <= p.N_total && (p.ldo & 3) == 0) {
 #pragma unroll

@@ -44,6 +44,7 @@ struct ConvGemmParams {
     long long out_batch_stride;
     int ldo;
     int out_fp32;
+    int out_nchw;              // fp32 [image][col][pixel] (network output layout); one-tile-per-CTA kernel only
     const float* bias;         // per column (or per row if bias_along_m), may be null
     int bias_along_m;
     const float* rowvec;       // per-image per-column add, [image * ldrv + col], may be null

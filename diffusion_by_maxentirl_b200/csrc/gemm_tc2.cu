@@ -401,7 +401,7 @@ bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n) {
     const int eb = p.out_fp32 ? 4 : 2;
     if ((static_cast<long long>(p.ldo) * eb) % 16 || (reinterpret_cast<uintptr_t>(p.out) & 15)) return false;
     if (p.out_batch_stride && (p.out_batch_stride * eb) % 16) return false;
-    if (p.N_total % 8) return false;
+    if (p.N_total % 8 || p.out_nchw) return false;
     if (p.residual && ((static_cast<long long>(p.ldr) * 2) % 16 || (reinterpret_cast<uintptr_t>(p.residual) & 15) || p.out_fp32))
         return false;
     if (p.softmax && p.N_total != block_n) return false;

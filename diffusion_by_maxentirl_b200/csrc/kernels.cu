@@ -98,60 +98,99 @@ void cast_to_f32(const void* src, int src_is_half, float* dst, long long n, cuda
 
 // ============================================================================================ first / last conv
 
-// block = 256 threads; thread -> (pixel lane, 8-channel group). Weights staged in smem as [tap*Cin + ci][Cout].
+// Tile = 128 consecutive output pixels of one image (th rows x tw columns). The zero-padded fp32 input patch and the
+// weights ([tap*Cin + ci][Cout]) are staged in shared memory; a thread owns 2 pixels x 32 output channels, so every
+// weight vector read from smem (broadcast) feeds 8 FMAs and every input value 32.
+template <int CIN>
 __global__ void conv3x3_first_k(const float* __restrict__ x, const float* __restrict__ in_scale,
-                                const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out, int N,
-                                int Cin, int H, int W, int Cout, int act) {
-    extern __shared__ float sw[];  // [9*Cin][Cout] + bias[Cout]
-    const int K = 9 * Cin;
+                                const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out, int H,
+                                int W, int Cout, int act, int th, int tw) {
+    extern __shared__ float sm[];
+    const int K = 9 * CIN;
+    float* sw = sm;                   // [K][Cout]
+    float* sb = sw + K * Cout;        // [Cout]
+    float* sx = sb + Cout;            // [CIN][th+2][tw+2]
+    const int pw = tw + 2, ph = th + 2;
+    const int tiles_w = W / tw, tiles_h = H / th;
+    const int n = blockIdx.x / (tiles_w * tiles_h);
+    const int trem = blockIdx.x % (tiles_w * tiles_h);
+    const int h0 = (trem / tiles_w) * th, w0 = (trem % tiles_w) * tw;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-        const int o = i % Cout, k = i / Cout;  // k = tap*Cin + ci
-        const int tap = k / Cin, ci = k % Cin;
-        sw[i] = w[((long long)o * Cin + ci) * 9 + tap];
+        const int o = i % Cout, kk = i / Cout;  // kk = tap*CIN + ci
+        const int tap = kk / CIN, ci = kk % CIN;
+        sw[i] = w[((long long)o * CIN + ci) * 9 + tap];
     }
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[K * Cout + i] = b ? b[i] : 0.f;
-    __syncthreads();
-
-    const int groups = Cout / 8;
-    const int plane = blockDim.x / groups;
-    const int g = threadIdx.x % groups;
-    const int pl = threadIdx.x / groups;
-    if (pl >= plane) return;
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = b ? b[i] : 0.f;
+    const float sc = in_scale ? in_scale[n] : 1.f;
     const long long HW = (long long)H * W;
-    const long long total = (long long)N * HW;
-    for (long long p = blockIdx.x * (long long)plane + pl; p < total; p += (long long)gridDim.x * plane) {
-        const int n = (int)(p / HW);
-        const int hw = (int)(p % HW);
-        const int h = hw / W, wx = hw % W;
-        const float sc = in_scale ? in_scale[n] : 1.f;
-        float acc[8];
+    for (int i = threadIdx.x; i < CIN * ph * pw; i += blockDim.x) {
+        const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
+        const int hh = h0 + r - 1, ww = w0 + c - 1;
+        sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((long long)n * CIN + ci) * HW + (long long)hh * W + ww] * sc : 0.f;
+    }
+    __syncthreads();
+    const int pp = threadIdx.x & 63;       // pixels pp and pp + 64 of the tile
+    const int cg = threadIdx.x >> 6;       // channels cg*32 .. +31
+    float acc[2][32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = sw[K * Cout + g * 8 + j];
-        for (int tap = 0; tap < 9; ++tap) {
-            const int hh = h + tap / 3 - 1, ww = wx + tap % 3 - 1;
-            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-            for (int ci = 0; ci < Cin; ++ci) {
-                const float xv = x[((long long)n * Cin + ci) * HW + (long long)hh * W + ww] * sc;
-                const float* wr = sw + (tap * Cin + ci) * Cout + g * 8;
+    for (int j = 0; j < 32; ++j) acc[0][j] = acc[1][j] = sb[cg * 32 + j];
+    int pr[2], pc[2];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+    for (int q = 0; q < 2; ++q) {
+        const int pix = pp + 64 * q;
+        pr[q] = pix / tw;
+        pc[q] = pix % tw;
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dr = tap / 3, dc = tap % 3;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const float x0 = sx[(ci * ph + pr[0] + dr) * pw + pc[0] + dc];
+            const float x1 = sx[(ci * ph + pr[1] + dr) * pw + pc[1] + dc];
+            const float4* wr = reinterpret_cast<const float4*>(sw + (tap * CIN + ci) * Cout + cg * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 w4 = wr[q];
+                acc[0][4 * q] = fmaf(x0, w4.x, acc[0][4 * q]);
+                acc[0][4 * q + 1] = fmaf(x0, w4.y, acc[0][4 * q + 1]);
+                acc[0][4 * q + 2] = fmaf(x0, w4.z, acc[0][4 * q + 2]);
+                acc[0][4 * q + 3] = fmaf(x0, w4.w, acc[0][4 * q + 3]);
+                acc[1][4 * q] = fmaf(x1, w4.x, acc[1][4 * q]);
+                acc[1][4 * q + 1] = fmaf(x1, w4.y, acc[1][4 * q + 1]);
+                acc[1][4 * q + 2] = fmaf(x1, w4.z, acc[1][4 * q + 2]);
+                acc[1][4 * q + 3] = fmaf(x1, w4.w, acc[1][4 * q + 3]);
             }
         }
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = act_f(acc[j], act);
-        st8(out + p * Cout + g * 8, pack8(acc));
+    for (int q = 0; q < 2; ++q) {
+        const long long p = (long long)n * HW + (long long)(h0 + pr[q]) * W + w0 + pc[q];
+        bf16* o = out + p * Cout + cg * 32;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = act_f(acc[q][v * 8 + j], act);
+            st8(o + v * 8, pack8(f));
+        }
     }
 }
 
 void conv3x3_first(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, int N, int Cin,
                    int H, int W, int Cout, int act, cudaStream_t st) {
-    const int groups = Cout / 8;
-    const int plane = 256 / groups;
-    const long long total = (long long)N * H * W;
-    long long blocks = (total + plane - 1) / plane;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    const size_t smem = (size_t)(9 * Cin * Cout + Cout) * sizeof(float);
-    conv3x3_first_k<<<(int)blocks, 256, smem, st>>>(x, in_scale, w, b, out, N, Cin, H, W, Cout, act);
+    // requirements (checked by the plan builders): Cin == 3, Cout % 32 == 0, Cout <= 512, H*W % 128 == 0, W power of two
+    const int tw = W < 128 ? W : 128;
+    const int th = 128 / tw;
+    const int threads = 64 * (Cout / 32);
+    const size_t smem = (size_t)(9 * Cin * Cout + Cout + Cin * (th + 2) * (tw + 2)) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv3x3_first_k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        configured = true;
+    }
+    const int blocks = N * (H / th) * (W / tw);
+    conv3x3_first_k<3><<<blocks, threads, smem, st>>>(x, in_scale, w, b, out, H, W, Cout, act, th, tw);
 }
 
 // One warp per output pixel; lanes stride over (tap, 8-channel vector) work items. Weights in smem [o][tap][C].
@@ -339,6 +378,128 @@ void gn_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, 
     dim3 grid(N, slabs);
     gn_apply_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, groups, eps, gamma, beta, film, film_ld, silu,
                                              partial, slabs, out);
+}
+
+// GroupNorm apply with the statistics taken from the producer GEMMs' fused partials (gemm_tc2.cu):
+// st1 / st2 = [rows/32][C1 or C2][2] (sum, sumsq) of the two concatenated sources. Thread (g = tid/8, sub = tid%8)
+// sums its share of (segment, channel) pairs in a fixed order, then a fixed-order shuffle tree: deterministic.
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __restrict__ x1, int C1, int ld1,
+                                                              const bf16* __restrict__ x2, int C2, int ld2, int HW,
+                                                              int groups, float eps, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              const float* __restrict__ film, int film_ld, int silu,
+                                                              const float* __restrict__ st1,
+                                                              const float* __restrict__ st2, int slabs,
+                                                              bf16* __restrict__ out) {
+    __shared__ float s_mean[32], s_rstd[32];
+    const int C = C1 + C2;
+    const int CV = C / 8;
+    const int PL = GN_THREADS / CV;
+    const int n = blockIdx.x, slab = blockIdx.y;
+    const int pix_per_slab = HW / slabs;
+    const int cpg = C / groups;
+    {
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;  // 32 groups x 8 partial lanes
+        const int P = HW / 32;
+        float s = 0.f, q = 0.f;
+        if (g < groups) {
+            const int pairs = P * cpg;
+            for (int i = sub; i < pairs; i += 8) {
+                const int seg = i / cpg, c = g * cpg + i % cpg;
+                const float2 v = (c < C1)
+                    ? *reinterpret_cast<const float2*>(st1 + (((long long)n * P + seg) * C1 + c) * 2)
+                    : *reinterpret_cast<const float2*>(st2 + (((long long)n * P + seg) * C2 + (c - C1)) * 2);
+                s += v.x;
+                q += v.y;
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && sub == 0) {
+            const float cnt = (float)cpg * (float)HW;
+            const float mean = s / cnt;
+            const float var = fmaxf(q / cnt - mean * mean, 0.f);
+            s_mean[g] = mean;
+            s_rstd[g] = rsqrtf(var + eps);
+        }
+    }
+    __syncthreads();
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    if (pl >= PL) return;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j;
+        const int g = c / cpg;
+        float aa = s_rstd[g] * gamma[c];
+        float bb = beta[c] - s_mean[g] * aa;
+        if (film) {
+            const float sc = 1.f + film[(long long)n * film_ld + c];
+            const float sh = film[(long long)n * film_ld + C + c];
+            aa *= sc;
+            bb = bb * sc + sh;
+        }
+        a[j] = aa;
+        b[j] = bb;
+    }
+    const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
+    int p = pl;
+    for (; p + 3 * PL < pix_per_slab; p += 4 * PL) {
+        bf16x8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + p + u * PL, cv * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(f[j], a[j], b[j]);
+                f[j] = silu ? silu_f(t) : t;
+            }
+            st8(out + (base + p + u * PL) * C + cv * 8, pack8(f));
+        }
+    }
+    for (; p < pix_per_slab; p += PL) {
+        float f[8];
+        unpack8(ld8(gn_src(x1, C1, ld1, x2, ld2, base + p, cv * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(f[j], a[j], b[j]);
+            f[j] = silu ? silu_f(t) : t;
+        }
+        st8(out + (base + p) * C + cv * 8, pack8(f));
+    }
+}
+
+int gn_apply_slabs(int N, int HW, int C) {
+    // enough CTAs for ~16 per SM, but keep >= 4 pixels per pixel-lane per slab so the unrolled loop has work
+    const int PL = GN_THREADS / (C / 8) > 0 ? GN_THREADS / (C / 8) : 1;
+    int slabs = 1;
+    while (N * slabs < 2368 && HW / (slabs * 2) >= 4 * PL && HW % (slabs * 2) == 0) slabs *= 2;
+    return slabs;
+}
+
+void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups, float eps,
+                    const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* st1,
+                    const float* st2, bf16* out, cudaStream_t st) {
+    const int slabs = gn_apply_slabs(N, HW, C1 + C2);
+    dim3 grid(N, slabs);
+    gn_apply_fused_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, groups, eps, gamma, beta, film, film_ld, silu,
+                                                   st1, st2, slabs, out);
+}
+
+__global__ void silu_to_bf16_k(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(silu_f(x[i]));
+}
+void silu_to_bf16(const float* x, bf16* y, long long n, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    silu_to_bf16_k<<<(int)blocks, 256, 0, st>>>(x, y, n);
 }
 
 // ============================================================================================ small dense helpers

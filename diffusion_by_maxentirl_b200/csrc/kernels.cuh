@@ -37,6 +37,13 @@ void gn_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, 
               const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* partial,
               int slabs, bf16* out, cudaStream_t st);
 
+// apply with statistics from the producer GEMMs' fused partials st1 / st2 = [N*HW/32][C1|C2][2] (gemm_tc2.cu); needs HW % 32 == 0
+void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups, float eps,
+                    const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* st1,
+                    const float* st2, bf16* out, cudaStream_t st);
+// y = bf16(silu(x))  (A operand of the batched temb / emb projection GEMM)
+void silu_to_bf16(const float* x, bf16* y, long long n, cudaStream_t st);
+
 // ---- small dense helpers (fp32 SIMT) -----------------------------------------------------------------------------------
 // sinusoidal features: out[n, :] = [sin | cos] (order 0, DDPM: freq = exp(-ln(1e4) * i / (half-1)))
 //                                  [cos | sin] (order 1, ADM:  freq = exp(-ln(1e4) * i / half))

@@ -140,6 +140,7 @@ typedef struct {
     float alpha;
     int softmax;
     int block_n;             /* 0 = auto */
+    int out_nchw;            /* fp32 output in [image][b_rows][rows_per_image] order (network output layout) */
     float* gn_stats;         /* optional: GroupNorm partials of the bf16 output, [rows/32][b_rows][2] (sum, sumsq) */
 } dxmi_gemm_desc;
 
