@@ -74,6 +74,7 @@ class GemmDesc(C.Structure):
         ("block_n", C.c_int),
         ("out_nchw", C.c_int),
         ("gn_stats", C.c_void_p),
+        ("gn_seg", C.c_int),
     ]
 
 
@@ -105,6 +106,7 @@ SYMBOLS = {
     "dxmi_last_error": (C.c_char_p, []),
     "dxmi_set_option": (_I, [C.c_char_p, _I]),
     "dxmi_set_debug_buffer": (_I, [_VP]),
+    "dxmi_set_timing_dump": (_I, [C.c_char_p]),
     "dxmi_launch_count": (_LL, []),
     "dxmi_gemm_timing": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL)]),
     "dxmi_plan_gemm_flops": (C.c_double, [_VP, _I]),

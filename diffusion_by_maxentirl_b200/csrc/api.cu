@@ -40,6 +40,11 @@ int dxmi_set_option(const char* name, int value) {
     return -1;
 }
 
+int dxmi_set_timing_dump(const char* path) {
+    set_timing_dump(path);
+    return 0;
+}
+
 int dxmi_set_debug_buffer(void* dev_ptr) {
     set_dbg_times(dev_ptr);
     return 0;

@@ -40,9 +40,11 @@ struct Builder {
     bf16* act_alloc(int C, int H, int W) { return (bf16*)alloc((size_t)B * H * W * C * sizeof(bf16)); }
     // GroupNorm partial-statistics buffer for a GEMM output of B*H*W rows x C columns (null when the fused path
     // cannot be used for this geometry: a 32-row segment must not straddle two images)
+    static int stats_seg(int HW) { return HW % 128 == 0 ? 128 : (HW % 64 == 0 ? 64 : (HW % 32 == 0 ? 32 : 0)); }
+    static size_t stats_bytes(int rows, int HW, int C) { return (size_t)rows / stats_seg(HW) * C * 2 * sizeof(float); }
     float* stats_alloc(int C, int H, int W) {
-        if ((H * W) % 32) return nullptr;
-        return (float*)alloc((size_t)B * H * W / 32 * C * 2 * sizeof(float));
+        if (!stats_seg(H * W)) return nullptr;
+        return (float*)alloc(stats_bytes(B * H * W, H * W, C));
     }
     Act new_act(int C, int H, int W, bool want_stats = true) {
         Act a;
@@ -228,8 +230,10 @@ struct Builder {
         plan.ops.push_back(std::move(f));
         plan.launches_per_run += launches;
     }
-    void gemm(const dxmi_gemm_desc& d) {
+    void gemm(const dxmi_gemm_desc& d_in) {
         if (dry || err) return;
+        dxmi_gemm_desc d = d_in;
+        if (d.gn_stats) d.gn_seg = stats_seg(d.rows_per_image);
         GemmOp g;
         int r = prepare_gemm(d, &g);
         if (r) {
@@ -352,11 +356,25 @@ struct Builder {
         if ((C1 + C2) % 8 || (C1 % 8) || (C1 + C2) > 2048) fail("group_norm: unsupported channel count");
         const float* st1 = x1.stats;
         const float* st2 = x2.stats;
-        const long long pairs = (long long)(HW / 32) * ((C1 + C2) / 32);
-        if (st1 && (C2 == 0 || st2) && HW % 32 == 0 && pairs <= 4096) {
+        if (st1 && (C2 == 0 || st2) && stats_seg(HW)) {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
+            int P = HW / stats_seg(HW);
+            if (P > 8) {
+                // large maps: collapse the row-segment partials once so the apply CTAs' prologue stays tiny
+                float* c1 = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
+                float* c2 = c1 ? c1 + (size_t)B * C1 * 2 : nullptr;
+                const int Pin = P;
+                op([=](cudaStream_t st) {
+                    gn_collapse(st1, c1, Bn, Pin, C1, st);
+                    if (C2) gn_collapse(st2, c2, Bn, Pin, C2, st);
+                    return (int)cudaGetLastError();
+                }, C2 ? 2 : 1);
+                st1 = c1;
+                st2 = c2;
+                P = 1;
+            }
             op([=](cudaStream_t st) {
-                gn_apply_fused(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, st2, out, st);
+                gn_apply_fused(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P, st2, P, out, st);
                 return (int)cudaGetLastError();
             });
             return;

@@ -167,7 +167,7 @@ struct DdpmBuilder : Builder {
         bf16* g1 = (bf16*)scratch(0, (size_t)B * HW * Cin * 2);
         group_norm(xa, xb, p + ".norm1", 1e-6f, 1, nullptr, 0, g1);
         bf16* h1 = (bf16*)scratch(1, (size_t)B * HW * Cout * 2);
-        float* h1_stats = (HW % 32 == 0) ? (float*)scratch(6, (size_t)B * HW / 32 * Cout * 2 * sizeof(float)) : nullptr;
+        float* h1_stats = stats_seg(HW) ? (float*)scratch(6, stats_bytes(B * HW, HW, Cout)) : nullptr;
         {
             long long K;
             int rows;

@@ -162,7 +162,7 @@ struct AdmBuilder : Builder {
             xs = Act{xp, Cin, Ho, Wo};
         }
         bf16* h1 = (bf16*)scratch(1, (size_t)B * Ho * Wo * Cout * 2);
-        float* h1_stats = ((Ho * Wo) % 32 == 0) ? (float*)scratch(6, (size_t)B * Ho * Wo / 32 * Cout * 2 * sizeof(float)) : nullptr;
+        float* h1_stats = stats_seg(Ho * Wo) ? (float*)scratch(6, stats_bytes(B * Ho * Wo, Ho * Wo, Cout)) : nullptr;
         {
             dxmi_gemm_desc d = conv_desc(Ho, Wo);
             set_src(d, 0, conv_in, Cin, Cin);

@@ -125,14 +125,12 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     p.stats = nullptr;
     op->use_v2 = 0;
     if (g_opt_gemm_v == 2 && conv_gemm_v2_supported(p, block_n)) {
-        const int eb = p.out_fp32 ? 4 : 2;
-        r = make_out_map(&p.out_map, p.out, eb, p.N_total, p.M_total, op->batch, p.ldo, p.out_batch_stride);
-        if (r) return r;
-        if (p.residual) {
-            r = make_out_map(&p.res_map, p.residual, 2, p.N_total, p.M_total, op->batch, p.ldr, p.res_batch_stride);
-            if (r) return r;
+        p.stats = p.softmax ? nullptr : d.gn_stats;
+        p.stats_seg = d.gn_seg;
+        if (p.stats && (p.stats_seg != 32 && p.stats_seg != 64 && p.stats_seg != 128)) {
+            snprintf(g_op_err, sizeof g_op_err, "gn_seg must be 32, 64 or 128");
+            return -13;
         }
-        p.stats = d.gn_stats;
         op->use_v2 = 1;
     } else if (d.gn_stats) {
         snprintf(g_op_err, sizeof g_op_err, "gn_stats requested but the persistent kernel does not support this GEMM");
@@ -147,9 +145,16 @@ static int g_time_gemms = 0;
 struct TimedLaunch {
     cudaEvent_t a, b;
     double flops;
+    int M, N, K, batch, block_n, v2;
 };
 static std::vector<TimedLaunch> g_timed;
 void set_time_gemms(int v) { g_time_gemms = v; }
+static FILE* g_timing_dump = nullptr;
+void set_timing_dump(const char* path) {
+    if (g_timing_dump) fclose(g_timing_dump);
+    g_timing_dump = path ? fopen(path, "w") : nullptr;
+    if (g_timing_dump) fprintf(g_timing_dump, "M,N,K,batch,block_n,persistent,us,gflop\n");
+}
 int gemm_timing_collect(double* ms_total, double* flops_total, long long* launches) {
     double ms = 0, fl = 0;
     for (auto& t : g_timed) {
@@ -157,6 +162,8 @@ int gemm_timing_collect(double* ms_total, double* flops_total, long long* launch
         if (e != cudaSuccess) return (int)e;
         float m = 0.f;
         cudaEventElapsedTime(&m, t.a, t.b);
+        if (g_timing_dump)
+            fprintf(g_timing_dump, "%d,%d,%d,%d,%d,%d,%.2f,%.3f\n", t.M, t.N, t.K, t.batch, t.block_n, t.v2, m * 1e3, t.flops / 1e9);
         ms += m;
         fl += t.flops;
         cudaEventDestroy(t.a);
@@ -166,6 +173,7 @@ int gemm_timing_collect(double* ms_total, double* flops_total, long long* launch
     *flops_total = fl;
     *launches = (long long)g_timed.size();
     g_timed.clear();
+    if (g_timing_dump) fflush(g_timing_dump);
     return 0;
 }
 
@@ -180,6 +188,12 @@ int run_gemm(const GemmOp& op, cudaStream_t st) {
     cudaEventCreate(&t.a);
     cudaEventCreate(&t.b);
     t.flops = op.flops;
+    t.M = op.p.M_total;
+    t.N = op.p.N_total;
+    t.K = (int)(op.flops / (2.0 * op.p.M_total * op.batch * op.p.N_total) + 0.5);
+    t.batch = op.batch;
+    t.block_n = op.block_n;
+    t.v2 = op.use_v2;
     cudaEventRecord(t.a, st);
     int r = launch_any(op, st);
     cudaEventRecord(t.b, st);

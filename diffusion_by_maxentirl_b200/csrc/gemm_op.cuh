@@ -18,6 +18,7 @@ void set_dbg_mode(int v);
 void set_gemm_version(int v);
 void set_dbg_times(void* p);
 void set_time_gemms(int v);
+void set_timing_dump(const char* path);
 int gemm_timing_collect(double* ms_total, double* flops_total, long long* launches);
 const char* gemm_op_last_error();
 

@@ -60,7 +60,8 @@ struct ConvGemmParams {
     CUtensorMap out_map;       // (cols, rows, batch) over `out`, box (128 bytes of columns, 128 rows, 1), SWIZZLE_128B
     CUtensorMap res_map;       // same geometry over `residual` (bf16)
     int m_tiles, n_tiles, batch_count;
-    float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/32][N_total][2] (sum, sumsq) or null
+    float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/stats_seg][N_total][2] (sum, sumsq) or null
+    int stats_seg;             // rows per partial: 32, 64 or 128 (a segment never straddles two images)
     long long* dbg_times;      // profiling only: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA, or null
     int dbg_mode;              // profiling only: 1 = skip the MMAs (TMA ring throughput), 2 = skip the epilogue stores
 };

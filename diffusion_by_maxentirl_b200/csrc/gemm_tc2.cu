@@ -5,15 +5,16 @@
 //   * one CTA per SM, looping over output tiles (static round-robin), so barrier init / TMEM alloc / descriptor
 //     prefetch are paid once per SM instead of once per tile;
 //   * two TMEM accumulators: the MMA warp starts tile i+1 while the epilogue warps drain tile i;
-//   * the epilogue stages 128-byte-wide column chunks in swizzled shared memory and writes them with TMA stores (full
-//     128-byte lines, bounds clipped by the tensor map); residual tiles arrive the same way through TMA loads, one
-//     chunk ahead;
+//   * the epilogue is two-phase: accumulator rows go through a swizzled shared-memory staging slot, then 8 lanes per
+//     row add the residual (prefetched with coalesced loads), apply the activation and store full 128-byte lines.
+//     (A TMA-store epilogue was measured first: its stores queue behind the producer's loads in the TMA unit and cost
+//     1.4 us per 16 KB chunk, profiles/r01_cta_timeline_v2.txt);
 //   * optional fused GroupNorm partial statistics: per 32-row segment and output column, (sum, sumsq) of the
 //     bf16-rounded outputs via a warp reduce-scatter (31 shuffles per 32 columns), so the consumer GroupNorm needs no
 //     statistics pass over HBM.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..5 epilogue
-// (warp w owns TMEM lanes 32*(w%4)..+31; lane 0 of warp 2 issues the epilogue's TMA loads / stores).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..9 epilogue
+// (warp w may read TMEM lanes 32*(w%4)..+31).
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 
@@ -24,42 +25,275 @@ namespace dxmi {
 static constexpr int TILE_M = 128;
 static constexpr int TILE_K = 64;
 static constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;  // 16 KB
-static constexpr int NUM_THREADS = 192;
+static constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 static constexpr int EPI_SLOT_BYTES = 128 * 128;  // 128 rows x 128 bytes
 
 template <int BLOCK_N>
 struct Cfg2 {
     static constexpr int B_STAGE_BYTES = BLOCK_N * TILE_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = BLOCK_N > 192 ? 3 : (BLOCK_N > 128 ? 4 : (BLOCK_N > 64 ? 4 : 6));
+    static constexpr int STAGES = BLOCK_N > 128 ? 4 : (BLOCK_N > 64 ? 6 : 8);
     static constexpr int ACC_COLS = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     static constexpr int SM_OUT = RING_BYTES;                       // 2 output staging slots
-    static constexpr int SM_RES = SM_OUT + 2 * EPI_SLOT_BYTES;      // 2 residual staging slots
-    static constexpr int SM_BAR = SM_RES + 2 * EPI_SLOT_BYTES;      // mbarriers + TMEM slot
+    static constexpr int SM_STAT = SM_OUT + 2 * EPI_SLOT_BYTES;     // [8 warps][32 columns] float2 GroupNorm partials + softmax row stats
+    static constexpr int SM_BAR = SM_STAT + 2048;                   // mbarriers + TMEM slot
+    static_assert(SM_BAR + 256 <= 227 * 1024, "shared memory budget");
     static constexpr int SMEM_BYTES = SM_BAR + 256;
 };
 
+__device__ __forceinline__ long long gtimer2() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG2(slot) \
+    if (p.dbg_times) p.dbg_times[(long long)blockIdx.x * 8 + (slot)] = gtimer2();
+// cycle-resolution stamps of the epilogue leader for chunk `cidx` of the CTA's second tile (steady state)
+
+
 __device__ __forceinline__ float act2(float v, int act) {
     if (act == ACT_LRELU02) return v > 0.f ? v : 0.2f * v;
-    if (act == ACT_SILU) return v / (1.f + __expf(-v));
+    if (act == ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
     return v;
 }
 
-// lane L ends with the sum over the warp of column L of v[0..31]
-__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+// ------------------------------------------------------------------------------------------------ tile epilogue
+// Per-thread constants of the 8 epilogue warps.
+struct EpiCtx {
+    uint8_t* slot0;     // 2 staging slots of 128 rows x 128 bytes (32 fp32 columns), SWIZZLE_128B pattern
+    float2* sst;        // [8 warps][32 columns] GroupNorm partials / softmax row stats
+    uint32_t taddr;     // TMEM address of this warp's lane quarter (column 0 of accumulator 0)
+    uint32_t stage_off; // byte offset of this thread's staging row + its 4 swizzled 16-byte units base
+    int sw;             // row & 7 (swizzle key) of the staging row this thread writes in phase A
+    int hsel;           // which 16 of the chunk's 32 columns this warp stages
+    int e, ew;          // epilogue thread / warp index
+    int rt0;            // first of the 4 tile rows (rt0 + 4 i) this thread finishes in phase B
+    int bu;             // 16-byte unit (4 columns) of the staging row this thread finishes
+    bool brs0;          // lane owns the per-warp statistics write
+};
+
+enum EpiMode { EPI_BIAS = 0, EPI_ROWVEC = 1, EPI_RESIDUAL = 2, EPI_GENERIC = 3 };
+
+// Drains one 128 x BLOCK_N accumulator tile.
+//   Phase A: raw fp32 accumulators TMEM -> swizzled staging slot. Warp w may only read TMEM lanes 32*(w%4)..+31; the
+//            two warps that share a lane quarter split the chunk's 32 columns.
+//   Phase B: 8 lanes <-> one 128-byte staging row: alpha / bias / row vector / residual / activation / softmax,
+//            conversion, fully coalesced global stores, GroupNorm partial sums - on operands prefetched one chunk
+//            ahead with coalesced loads.  Staging is double buffered: one named barrier per chunk.
+// MODE selects straight-line code for the three hot operator shapes of the U-Nets (bias only, + per-image row vector,
+// + residual); EPI_GENERIC keeps every switch at run time (softmax, activations, per-row bias, fp32 output).
+// (Measured, profiles/r01_cta_timeline_*: the epilogue is issue / latency bound - 2 warps per scheduler - so code
+//  size and dependent chains matter more than bytes.)
+template <int MODE, bool STATS>
+__device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& cx, uint32_t tacc_col, uint64_t* tmem_empty_bar,
+                                         int row0, int col0, int nch, int batch, uint32_t& out_cnt) {
+    constexpr int CH = 32;
+    const int n_total = p.N_total;
+    const float alpha = p.alpha;
+    const bool g_res = MODE == EPI_GENERIC && p.residual != nullptr;
+    const bool g_rv = MODE == EPI_GENERIC && p.rowvec != nullptr;
+    const bool g_bm = MODE == EPI_GENERIC && p.bias != nullptr && p.bias_along_m;
+    const bool g_sm = MODE == EPI_GENERIC && p.softmax != 0;
+    const bool g_f32 = MODE == EPI_GENERIC && p.out_fp32 != 0;
+    const int g_act = MODE == EPI_GENERIC ? p.act : ACT_NONE;
+    const bool has_bias = p.bias != nullptr && !(MODE == EPI_GENERIC && p.bias_along_m);
+    const bool use_rv = MODE == EPI_ROWVEC || g_rv;
+    const bool use_res = MODE == EPI_RESIDUAL || g_res;
+
+    // ---- per-tile invariants: the 4 rows this thread finishes
+    bool rok[4];
+    long long ooff[4], roff[4];
+    const float* rvp[4];
+    float bm[4];
 #pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        const bool up = (lane & w) != 0;
-#pragma unroll
-        for (int j = 0; j < w; ++j) {
-            const float send = up ? v[j] : v[j + w];
-            const float keep = up ? v[j + w] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-        }
+    for (int i = 0; i < 4; ++i) {
+        const long long r = static_cast<long long>(row0) + cx.rt0 + 4 * i;
+        rok[i] = r < p.M_total && p.dbg_mode != 2;
+        ooff[i] = batch * p.out_batch_stride + r * p.ldo;
+        roff[i] = use_res ? batch * p.res_batch_stride + r * p.ldr : 0;
+        rvp[i] = (use_rv && rok[i]) ? p.rowvec + (r / p.rows_per_image) * p.ldrv : nullptr;
+        bm[i] = (g_bm && rok[i]) ? __ldg(p.bias + r) : 0.f;
     }
-    return v[0];
+    float4 pf_bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pf_rv[4];
+    uint2 pf_res[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pf_rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pf_res[i] = make_uint2(0u, 0u);
+    }
+    auto prefetch = [&](int pcc) {
+        const bool pok = pcc < n_total;
+        if (has_bias && pok) pf_bias = __ldg(reinterpret_cast<const float4*>(p.bias + pcc));
+        if (use_rv) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rvp[i] && pok) pf_rv[i] = __ldg(reinterpret_cast<const float4*>(rvp[i] + pcc));
+        }
+        if (use_res) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rok[i] && pok) pf_res[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + roff[i] + pcc));
+        }
+    };
+    prefetch(col0 + cx.bu * 4);
+
+    // ---- accumulator ready?
+    // (the caller has already waited on tmem_full and fenced)
+    if (g_sm) {
+        // row max / sum over the whole accumulator row (N_total == BLOCK_N): one warp per lane quarter
+        if (cx.hsel == 0) {
+            float sm_max = -INFINITY, sm_sum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < n_total; c += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(cx.taddr + tacc_col + c, v);
+                ptx::tmem_ld_wait();
+                float cmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]) * alpha);
+                const float nmax = fmaxf(sm_max, cmax);
+                float part = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) part += __expf(__uint_as_float(v[j]) * alpha - nmax);
+                sm_sum = sm_sum * __expf(sm_max - nmax) + part;
+                sm_max = nmax;
+            }
+            // staging row index of this thread == its accumulator row
+            cx.sst[(cx.stage_off >> 10) * 8 + ((cx.stage_off >> 7) & 7)] = make_float2(sm_max, 1.f / sm_sum);
+        }
+        ptx::named_bar_sync(2, 256);
+    }
+
+    const int stat_seg = STATS ? p.stats_seg : 128;
+    const int stat_nseg = 128 / stat_seg, stat_bps = stat_seg >> 5;
+    const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : 5);
+
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+        const int col = col0 + c * CH;
+        const int cc = col + cx.bu * 4;
+        const bool col_ok = cc < n_total;
+        uint8_t* slot = cx.slot0 + (out_cnt & 1) * EPI_SLOT_BYTES;
+
+        // ---- phase A: 16 accumulator columns of this warp's 32 rows -> staging
+        {
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + (c * CH + cx.hsel * 16), v);
+            ptx::tmem_ld_wait();
+            if (c == nch - 1) {
+                // every accumulator column this warp stages is now in registers: hand the TMEM buffer back
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(tmem_empty_bar);
+            }
+            uint8_t* srow = slot + cx.stage_off;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(srow + (((cx.hsel * 4 + q) ^ cx.sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        ptx::named_bar_sync(1, 256);
+
+        // ---- phase B
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rt = cx.rt0 + 4 * i;
+            const uint4 u = *reinterpret_cast<const uint4*>(slot + (rt >> 3) * 1024 + (rt & 7) * 128 + ((cx.bu ^ (rt & 7)) << 4));
+            float x[4];
+            if (g_sm) {
+                const float2 ms = cx.sst[rt];
+                x[0] = __expf(__uint_as_float(u.x) * alpha - ms.x) * ms.y;
+                x[1] = __expf(__uint_as_float(u.y) * alpha - ms.x) * ms.y;
+                x[2] = __expf(__uint_as_float(u.z) * alpha - ms.x) * ms.y;
+                x[3] = __expf(__uint_as_float(u.w) * alpha - ms.x) * ms.y;
+            } else {
+                float4 ad = pf_bias;
+                if (g_bm) {
+                    ad.x += bm[i];
+                    ad.y += bm[i];
+                    ad.z += bm[i];
+                    ad.w += bm[i];
+                }
+                if (use_rv) {
+                    ad.x += pf_rv[i].x;
+                    ad.y += pf_rv[i].y;
+                    ad.z += pf_rv[i].z;
+                    ad.w += pf_rv[i].w;
+                }
+                x[0] = fmaf(__uint_as_float(u.x), alpha, ad.x);
+                x[1] = fmaf(__uint_as_float(u.y), alpha, ad.y);
+                x[2] = fmaf(__uint_as_float(u.z), alpha, ad.z);
+                x[3] = fmaf(__uint_as_float(u.w), alpha, ad.w);
+                if (use_res) {
+                    x[0] += __uint_as_float(pf_res[i].x << 16);
+                    x[1] += __uint_as_float(pf_res[i].x & 0xffff0000u);
+                    x[2] += __uint_as_float(pf_res[i].y << 16);
+                    x[3] += __uint_as_float(pf_res[i].y & 0xffff0000u);
+                }
+                if (g_act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = act2(x[j], g_act);
+                }
+            }
+            const bool ok = rok[i] && col_ok;
+            if (g_f32) {
+                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff[i] + cc) = make_float4(x[0], x[1], x[2], x[3]);
+            } else {
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(x[2], x[3]);
+                uint32_t w0 = *reinterpret_cast<uint32_t*>(&b0), w1 = *reinterpret_cast<uint32_t*>(&b1);
+                if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + cc) = make_uint2(w0, w1);
+                if (STATS) {
+                    // statistics of the values the consumer will read (bf16-rounded); masked rows / columns add zero
+                    w0 = ok ? w0 : 0u;
+                    w1 = ok ? w1 : 0u;
+                    const float a0 = __uint_as_float(w0 << 16), a1 = __uint_as_float(w0 & 0xffff0000u);
+                    const float a2 = __uint_as_float(w1 << 16), a3 = __uint_as_float(w1 & 0xffff0000u);
+                    s1[0] += a0; s2[0] = fmaf(a0, a0, s2[0]);
+                    s1[1] += a1; s2[1] = fmaf(a1, a1, s2[1]);
+                    s1[2] += a2; s2[2] = fmaf(a2, a2, s2[2]);
+                    s1[3] += a3; s2[3] = fmaf(a3, a3, s2[3]);
+                }
+            }
+        }
+        if (c + 1 < nch) prefetch(cc + CH);  // next chunk's operands fly during the stats tail and phase A
+        if (STATS) {
+            // this warp's 16 rows: fold the 4 row sub-indices (lanes xor 8, 16); then the warps that share a row segment
+            // are combined through smem in a fixed order and one partial per segment is published
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
+                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+            }
+            if (cx.brs0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cx.sst[cx.ew * 32 + cx.bu * 4 + j] = make_float2(s1[j], s2[j]);
+            }
+            ptx::named_bar_sync(2, 256);
+            // (sst is single buffered: the next chunk writes it after its named barrier 1, which every publisher of this
+            //  chunk reaches only after it has read sst)
+            const int sg = cx.e >> 5, j = cx.e & 31;  // thread publishes column j of segment sg
+            if (sg < stat_nseg) {
+                float2 a = make_float2(0.f, 0.f);
+                for (int b2 = sg * stat_bps; b2 < (sg + 1) * stat_bps; ++b2) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float2 b = cx.sst[(hh * 4 + b2) * 32 + j];
+                        a.x += b.x;
+                        a.y += b.y;
+                    }
+                }
+                const int srow = row0 + sg * stat_seg;
+                if (col + j < n_total && srow < p.M_total)
+                    *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(srow >> stat_shift) * n_total + col + j) * 2) = a;
+            }
+        }
+        ++out_cnt;
+    }
 }
 
 template <int BLOCK_N>
@@ -79,6 +313,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles * p.batch_count;
+    if (threadIdx.x == 0) { DBG2(0); }
 
     int k_iters = 0;
 #pragma unroll
@@ -94,15 +329,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
         if (p.nseg > 1) ptx::prefetch_tmap(&p.a_map[1]);
         if (p.nseg > 2) ptx::prefetch_tmap(&p.a_map[2]);
         ptx::prefetch_tmap(&p.b_map);
-        ptx::prefetch_tmap(&p.out_map);
-        if (p.residual) ptx::prefetch_tmap(&p.res_map);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], 128);
+            ptx::mbar_init(&tmem_empty[s], 256);
             ptx::mbar_init(&res_full[s], 1);
         }
         ptx::fence_mbar_init();
@@ -112,6 +345,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) { DBG2(1); }
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -169,6 +403,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                     const uint32_t ph = (it / STAGES) & 1;
                     ptx::mbar_wait(&full_bar[stage], ph);
                     ptx::tc_fence_after();
+                    if (it == 0) { DBG2(2); }
                     const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
                     const uint64_t db = ptx::make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
@@ -180,20 +415,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                     ptx::umma_commit(&empty_bar[stage]);
                 }
                 ptx::umma_commit(&tmem_full[acc]);
+                if (ti == 0) { DBG2(3); }
+                if (ti == 1) { DBG2(4); }
             }
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue (thread <-> output row)
-        const int quarter = warp & 3;
+        // ------------------------------------------------------------ epilogue (8 warps, 256 threads): see epi_tile
+        EpiCtx cx;
+        cx.e = threadIdx.x - 64;
+        cx.ew = cx.e >> 5;
+        const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+        cx.hsel = cx.ew >> 2;
         const int row_in_tile = quarter * 32 + lane;
-        const bool leader = (warp == 2 && lane == 0);
-        const int sw = row_in_tile & 7;
-        const int CH = p.out_fp32 ? 32 : 64;  // output columns per 128-byte staging row
-        uint8_t* out_slot0 = smem + Cfg::SM_OUT;
-        uint8_t* res_slot0 = smem + Cfg::SM_RES;
-        const uint32_t row_off = (row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128;
-        uint32_t ti = 0, out_cnt = 0, res_cnt = 0;
+        cx.sw = row_in_tile & 7;
+        cx.stage_off = (row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128;
+        cx.slot0 = smem + Cfg::SM_OUT;
+        cx.sst = reinterpret_cast<float2*>(smem + Cfg::SM_STAT);
+        cx.taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        cx.rt0 = (cx.ew & 3) * 32 + (cx.ew >> 2) * 16 + (lane >> 3);  // warp -> 16 rows of one 32-row block
+        cx.bu = lane & 7;
+        cx.brs0 = (lane >> 3) == 0;
+        const bool leader = (cx.e == 0);
+        // launch-uniform epilogue shape
+        const bool simple = !p.softmax && p.act == ACT_NONE && !p.out_fp32 && !(p.bias && p.bias_along_m);
+        int mode = EPI_GENERIC;
+        if (simple && !p.residual && !p.rowvec) mode = EPI_BIAS;
+        else if (simple && !p.residual && p.rowvec) mode = EPI_ROWVEC;
+        else if (simple && p.residual && !p.rowvec) mode = EPI_RESIDUAL;
+        const bool has_stats = p.stats != nullptr && !p.out_fp32;
+        uint32_t ti = 0, out_cnt = 0;
 
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
             const int n_tile = t % p.n_tiles;
@@ -201,191 +452,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             const int m_tile = mt % p.m_tiles;
             const int batch = mt / p.m_tiles;
             const int row0 = m_tile * TILE_M;
-            const long long row = static_cast<long long>(row0) + row_in_tile;  // row within this batch entry
-            const bool row_ok = row < p.M_total;
             const int col0 = n_tile * BLOCK_N;
             int ncols = p.N_total - col0;
             if (ncols > BLOCK_N) ncols = BLOCK_N;
-            const int nch = (ncols + CH - 1) / CH;
+            const int nch = (ncols + 31) / 32;
             const uint32_t acc = ti & 1;
 
-            if (p.residual && leader) {
-                ptx::mbar_expect_tx(&res_full[res_cnt & 1], EPI_SLOT_BYTES);
-                ptx::tma_load_3d(res_slot0 + (res_cnt & 1) * EPI_SLOT_BYTES, &p.res_map, &res_full[res_cnt & 1], col0, row0, batch);
-            }
             ptx::mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
             ptx::tc_fence_after();
-            const uint32_t taddr_row = tmem_base + acc * Cfg::ACC_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
-            const float bias_m = (p.bias && p.bias_along_m && row_ok) ? p.bias[row] : 0.f;
-            const float* rowvec = (p.rowvec && row_ok) ? p.rowvec + (row / p.rows_per_image) * p.ldrv : nullptr;
-
-            float sm_max = -INFINITY, sm_inv = 0.f;
-            if (p.softmax) {
-                float sm_sum = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(taddr_row + c, v);
-                    ptx::tmem_ld_wait();
-                    float cmax = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]) * p.alpha);
-                    const float nmax = fmaxf(sm_max, cmax);
-                    float part = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) part += __expf(__uint_as_float(v[j]) * p.alpha - nmax);
-                    sm_sum = sm_sum * __expf(sm_max - nmax) + part;
-                    sm_max = nmax;
+            if (ti == 0 && leader) { DBG2(5); }
+            const uint32_t tcol = acc * Cfg::ACC_COLS;
+            uint64_t* te = &tmem_empty[acc];
+            if (has_stats) {
+                switch (mode) {
+                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
                 }
-                sm_inv = 1.f / sm_sum;
+            } else {
+                switch (mode) {
+                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                }
             }
-
-#pragma unroll 1
-            for (int c = 0; c < nch; ++c) {
-                const int col = col0 + c * CH;
-                const bool last = (c == nch - 1);
-                if (p.residual && leader && !last) {
-                    const uint32_t s = (res_cnt + 1) & 1;
-                    ptx::mbar_expect_tx(&res_full[s], EPI_SLOT_BYTES);
-                    ptx::tma_load_3d(res_slot0 + s * EPI_SLOT_BYTES, &p.res_map, &res_full[s], col + CH, row0, batch);
-                }
-                uint8_t* oslot = out_slot0 + (out_cnt & 1) * EPI_SLOT_BYTES + row_off;
-                const uint8_t* rslot = res_slot0 + (res_cnt & 1) * EPI_SLOT_BYTES + row_off;
-                if (p.residual) ptx::mbar_wait(&res_full[res_cnt & 1], (res_cnt >> 1) & 1);
-                ptx::named_bar_sync(1, 128);  // staging slot (out_cnt & 1) has been read by its previous TMA store
-
-                // two halves of 32 accumulator columns each (one half when the output is fp32)
-                const int halves = p.out_fp32 ? 1 : 2;
-                for (int hf = 0; hf < halves; ++hf) {
-                    const int cc = col + hf * 32;
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(taddr_row + (c * CH + hf * 32), v);
-                    ptx::tmem_ld_wait();
-                    if (last && hf == halves - 1) {
-                        // every accumulator column of this tile is now in registers: hand the TMEM buffer back
-                        ptx::tc_fence_before();
-                        ptx::mbar_arrive(&tmem_empty[acc]);
-                    }
-                    float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-                    if (p.softmax) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __expf(f[j] - sm_max) * sm_inv;
-                    } else {
-                        if (p.bias) {
-                            if (p.bias_along_m) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) f[j] += bias_m;
-                            } else if (cc + 32 <= p.N_total) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cc) + q);
-                                    f[4 * q] += b4.x;
-                                    f[4 * q + 1] += b4.y;
-                                    f[4 * q + 2] += b4.z;
-                                    f[4 * q + 3] += b4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (cc + j < p.N_total) f[j] += __ldg(p.bias + cc + j);
-                            }
-                        }
-                        if (rowvec) {
-                            if (cc + 32 <= p.N_total) {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(rowvec + cc) + q);
-                                    f[4 * q] += b4.x;
-                                    f[4 * q + 1] += b4.y;
-                                    f[4 * q + 2] += b4.z;
-                                    f[4 * q + 3] += b4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (cc + j < p.N_total) f[j] += __ldg(rowvec + cc + j);
-                            }
-                        }
-                        if (p.residual) {
-                            // residual slot: 128-byte rows of 64 bf16, 16-byte units XOR-swizzled by (row & 7)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int unit = (hf * 4 + q) ^ sw;
-                                const uint4 u = *reinterpret_cast<const uint4*>(rslot + unit * 16);
-                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    f[q * 8 + 2 * e] += __uint_as_float(w[e] << 16);
-                                    f[q * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
-                                }
-                            }
-                        }
-                        if (p.act != ACT_NONE) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = act2(f[j], p.act);
-                        }
-                    }
-                    if (p.out_fp32) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int unit = q ^ sw;
-                            *reinterpret_cast<float4*>(oslot + unit * 16) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-                        }
-                    } else {
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int unit = (hf * 4 + q) ^ sw;
-                            *reinterpret_cast<uint4*>(oslot + unit * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                        }
-                        if (p.stats) {
-                            // GroupNorm partials of the values the consumer will read (bf16-rounded), rows past M excluded
-                            float s1[32], s2[32];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float a = row_ok ? __uint_as_float(pk[j] << 16) : 0.f;
-                                const float b = row_ok ? __uint_as_float(pk[j] & 0xffff0000u) : 0.f;
-                                s1[2 * j] = a;
-                                s1[2 * j + 1] = b;
-                                s2[2 * j] = a * a;
-                                s2[2 * j + 1] = b * b;
-                            }
-                            const float tsum = warp_reduce_scatter32(s1, lane);
-                            const float tsq = warp_reduce_scatter32(s2, lane);
-                            const long long seg = (static_cast<long long>(row0) + quarter * 32) >> 5;
-                            if (cc + lane < p.N_total && static_cast<long long>(row0) + quarter * 32 < p.M_total)
-                                *reinterpret_cast<float2*>(p.stats + (seg * p.N_total + cc + lane) * 2) = make_float2(tsum, tsq);
-                        }
-                    }
-                }
-                if (p.residual) ++res_cnt;
-                ptx::fence_proxy_async_smem();
-                ptx::named_bar_sync(2, 128);
-                if (leader) {
-                    if (p.dbg_mode != 2)
-                        ptx::tma_store_3d(&p.out_map, out_slot0 + (out_cnt & 1) * EPI_SLOT_BYTES, col, row0, batch);
-                    ptx::bulk_commit();
-                    ptx::bulk_wait_read<1>();  // the store issued one chunk earlier has finished reading its slot
-                }
-                ++out_cnt;
-            }
+            if (ti == 0 && leader) { DBG2(6); }
             if (nch == 0) {  // cannot happen (n tiles are clipped on the host), but never leave the MMA warp waiting
                 ptx::tc_fence_before();
                 ptx::mbar_arrive(&tmem_empty[acc]);
             }
         }
-        if (leader) ptx::bulk_wait<0>();
     }
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) { DBG2(7); }
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -402,7 +505,8 @@ bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n) {
     if ((static_cast<long long>(p.ldo) * eb) % 16 || (reinterpret_cast<uintptr_t>(p.out) & 15)) return false;
     if (p.out_batch_stride && (p.out_batch_stride * eb) % 16) return false;
     if (p.N_total % 8 || p.out_nchw) return false;
-    if (p.residual && ((static_cast<long long>(p.ldr) * 2) % 16 || (reinterpret_cast<uintptr_t>(p.residual) & 15) || p.out_fp32))
+    if (p.residual && ((static_cast<long long>(p.ldr) * 2) % 16 || (reinterpret_cast<uintptr_t>(p.residual) & 15) ||
+                       (p.res_batch_stride * 2) % 16))
         return false;
     if (p.softmax && p.N_total != block_n) return false;
     return true;

@@ -8,7 +8,7 @@ namespace dxmi {
 
 namespace {
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 __device__ __forceinline__ float act_f(float v, int act) {
     if (act == 1) return v > 0.f ? v : 0.2f * v;
     if (act == 2) return silu_f(v);
@@ -381,34 +381,46 @@ void gn_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, 
 }
 
 // GroupNorm apply with the statistics taken from the producer GEMMs' fused partials (gemm_tc2.cu):
-// st1 / st2 = [rows/32][C1 or C2][2] (sum, sumsq) of the two concatenated sources. Thread (g = tid/8, sub = tid%8)
-// sums its share of (segment, channel) pairs in a fixed order, then a fixed-order shuffle tree: deterministic.
+// st1 / st2 = [N][P1 | P2][C1 | C2][2] (sum, sumsq) per row segment of the two concatenated sources.
+// All reductions run in a fixed order: deterministic.
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __restrict__ x1, int C1, int ld1,
                                                               const bf16* __restrict__ x2, int C2, int ld2, int HW,
                                                               int groups, float eps, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta,
                                                               const float* __restrict__ film, int film_ld, int silu,
-                                                              const float* __restrict__ st1,
-                                                              const float* __restrict__ st2, int slabs,
+                                                              const float* __restrict__ st1, int P1,
+                                                              const float* __restrict__ st2, int P2, int slabs,
                                                               bf16* __restrict__ out) {
     __shared__ float s_mean[32], s_rstd[32];
+    __shared__ float2 s_ch[2048];  // per-channel (sum, sumsq) of this image
     const int C = C1 + C2;
     const int CV = C / 8;
     const int PL = GN_THREADS / CV;
     const int n = blockIdx.x, slab = blockIdx.y;
     const int pix_per_slab = HW / slabs;
     const int cpg = C / groups;
+    // (1) per-channel totals over the P1 / P2 row-segment partials of this image (coalesced, fixed order)
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        const bool first = c < C1;
+        const float* base = first ? st1 + ((long long)n * P1 * C1 + c) * 2 : st2 + ((long long)n * P2 * C2 + (c - C1)) * 2;
+        const int P = first ? P1 : P2;
+        const long long stride = (long long)(first ? C1 : C2) * 2;
+        float s = 0.f, q = 0.f;
+        for (int seg = 0; seg < P; ++seg) {
+            const float2 v = *reinterpret_cast<const float2*>(base + seg * stride);
+            s += v.x;
+            q += v.y;
+        }
+        s_ch[c] = make_float2(s, q);
+    }
+    __syncthreads();
+    // (2) channels -> groups: thread (g, sub) sums every 8th channel of group g, then a fixed shuffle tree
     {
-        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;  // 32 groups x 8 partial lanes
-        const int P = HW / 32;
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
         float s = 0.f, q = 0.f;
         if (g < groups) {
-            const int pairs = P * cpg;
-            for (int i = sub; i < pairs; i += 8) {
-                const int seg = i / cpg, c = g * cpg + i % cpg;
-                const float2 v = (c < C1)
-                    ? *reinterpret_cast<const float2*>(st1 + (((long long)n * P + seg) * C1 + c) * 2)
-                    : *reinterpret_cast<const float2*>(st2 + (((long long)n * P + seg) * C2 + (c - C1)) * 2);
+            for (int i = sub; i < cpg; i += 8) {
+                const float2 v = s_ch[g * cpg + i];
                 s += v.x;
                 q += v.y;
             }
@@ -479,17 +491,37 @@ int gn_apply_slabs(int N, int HW, int C) {
     // enough CTAs for ~16 per SM, but keep >= 4 pixels per pixel-lane per slab so the unrolled loop has work
     const int PL = GN_THREADS / (C / 8) > 0 ? GN_THREADS / (C / 8) : 1;
     int slabs = 1;
-    while (N * slabs < 2368 && HW / (slabs * 2) >= 4 * PL && HW % (slabs * 2) == 0) slabs *= 2;
+    while (N * slabs < 1184 && HW / (slabs * 2) >= 4 * PL && HW % (slabs * 2) == 0) slabs *= 2;
     return slabs;
 }
 
 void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups, float eps,
                     const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* st1,
-                    const float* st2, bf16* out, cudaStream_t st) {
+                    int P1, const float* st2, int P2, bf16* out, cudaStream_t st) {
     const int slabs = gn_apply_slabs(N, HW, C1 + C2);
     dim3 grid(N, slabs);
     gn_apply_fused_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, groups, eps, gamma, beta, film, film_ld, silu,
-                                                   st1, st2, slabs, out);
+                                                   st1, P1, st2, P2, slabs, out);
+}
+
+// [N][P][C][2] -> [N][1][C][2]: collapses many row-segment partials (large feature maps) so that the apply kernel's
+// per-CTA prologue stays small.  Fixed summation order.
+__global__ void gn_collapse_k(const float* __restrict__ in, float* __restrict__ out, int P, int C) {
+    const int n = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float* base = in + ((long long)n * P * C + c) * 2;
+    float s = 0.f, q = 0.f;
+    for (int seg = 0; seg < P; ++seg) {
+        const float2 v = *reinterpret_cast<const float2*>(base + (long long)seg * C * 2);
+        s += v.x;
+        q += v.y;
+    }
+    *reinterpret_cast<float2*>(out + ((long long)n * C + c) * 2) = make_float2(s, q);
+}
+void gn_collapse(const float* in, float* out, int N, int P, int C, cudaStream_t st) {
+    dim3 grid((C + 127) / 128, N);
+    gn_collapse_k<<<grid, 128, 0, st>>>(in, out, P, C);
 }
 
 __global__ void silu_to_bf16_k(const float* __restrict__ x, bf16* __restrict__ y, long long n) {

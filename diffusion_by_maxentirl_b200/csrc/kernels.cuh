@@ -37,10 +37,12 @@ void gn_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, 
               const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* partial,
               int slabs, bf16* out, cudaStream_t st);
 
-// apply with statistics from the producer GEMMs' fused partials st1 / st2 = [N*HW/32][C1|C2][2] (gemm_tc2.cu); needs HW % 32 == 0
+// apply with statistics from the producer GEMMs' fused partials st1 / st2 = [N][P1|P2][C1|C2][2] (gemm_tc2.cu)
 void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups, float eps,
                     const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* st1,
-                    const float* st2, bf16* out, cudaStream_t st);
+                    int P1, const float* st2, int P2, bf16* out, cudaStream_t st);
+// [N][P][C][2] -> [N][1][C][2]
+void gn_collapse(const float* in, float* out, int N, int P, int C, cudaStream_t st);
 // y = bf16(silu(x))  (A operand of the batched temb / emb projection GEMM)
 void silu_to_bf16(const float* x, bf16* y, long long n, cudaStream_t st);
 

@@ -64,6 +64,7 @@ def conv_gemm(
     softmax=False,
     res_batch_stride=0,
     gn_stats=None,
+    gn_seg=32,
 ):
     """srcs: list of (tensor, C_used, ld) NHWC bf16 sources; segs: list of (src_index, taps)."""
     d = L.GemmDesc()
@@ -118,6 +119,7 @@ def conv_gemm(
     if gn_stats is not None:
         assert gn_stats.dtype == torch.float32
         d.gn_stats = gn_stats.data_ptr()
+        d.gn_seg = gn_seg
     L.check(L.lib().dxmi_op_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
 

@@ -141,7 +141,8 @@ typedef struct {
     int softmax;
     int block_n;             /* 0 = auto */
     int out_nchw;            /* fp32 output in [image][b_rows][rows_per_image] order (network output layout) */
-    float* gn_stats;         /* optional: GroupNorm partials of the bf16 output, [rows/32][b_rows][2] (sum, sumsq) */
+    float* gn_stats;         /* optional: GroupNorm partials of the bf16 output, [rows/gn_seg][b_rows][2] (sum, sumsq) */
+    int gn_seg;              /* rows per partial: 32, 64 or 128; must divide the rows of one image */
 } dxmi_gemm_desc;
 
 int dxmi_op_conv_gemm(const dxmi_gemm_desc* d, dxmi_stream_t stream);
@@ -161,7 +162,9 @@ int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, c
 const char* dxmi_last_error(void);
 int dxmi_set_option(const char* name, int value);
 /* profiling only: device buffer of 8 int64 per CTA that the GEMM kernel fills with per-phase globaltimer stamps (NULL = off) */
-int dxmi_set_debug_buffer(void* dev_ptr); /* "block_n_256" (tile width), "time_gemms" (event-time every GEMM), "gemm_version" (1 = one tile per CTA,
+int dxmi_set_debug_buffer(void* dev_ptr);
+/* profiling only: with "time_gemms" on, dxmi_gemm_timing() also appends one CSV row per GEMM launch to this file (NULL = off) */
+int dxmi_set_timing_dump(const char* path); /* "block_n_256" (tile width), "time_gemms" (event-time every GEMM), "gemm_version" (1 = one tile per CTA,
  * 2 = persistent kernel, default), "dbg_mode" (profiling) */
 /* with "time_gemms" on: summed CUDA-event duration / algorithmic FLOPs / count of the tcgen05 GEMM launches since
  * the last call (synchronises on the recorded events) */

@@ -204,10 +204,13 @@ def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
     b = torch.randn(Cout, device=dev)
     wp = ops.pack_conv_weight(w)
     M = N * H * H
-    stats = torch.full((M // 32, Cout, 2), float("nan"), device=dev)
-    y = ops.conv_gemm([(x, Cin, Cin)], [(0, 9)], wp, N, H, H, bias=b, gn_stats=stats)
-    torch.cuda.synchronize()
-    yf = y.float().view(M // 32, 32, Cout)
-    assert torch.isfinite(stats).all()
-    assert torch.allclose(stats[..., 0], yf.sum(1), rtol=1e-4, atol=1e-3)
-    assert torch.allclose(stats[..., 1], (yf * yf).sum(1), rtol=1e-4, atol=1e-3)
+    for seg in (32, 64, 128):
+        if (H * H) % seg:
+            continue
+        stats = torch.full((M // seg, Cout, 2), float("nan"), device=dev)
+        y = ops.conv_gemm([(x, Cin, Cin)], [(0, 9)], wp, N, H, H, bias=b, gn_stats=stats, gn_seg=seg)
+        torch.cuda.synchronize()
+        yf = y.float().view(M // seg, seg, Cout)
+        assert torch.isfinite(stats).all(), seg
+        assert torch.allclose(stats[..., 0], yf.sum(1), rtol=1e-4, atol=2e-3), seg
+        assert torch.allclose(stats[..., 1], (yf * yf).sum(1), rtol=1e-4, atol=2e-3), seg
