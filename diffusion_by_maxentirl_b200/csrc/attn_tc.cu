@@ -1,5 +1,6 @@
 // Fused multi-head self-attention (head dim 64) on tcgen05 tensor cores - QKVAttentionLegacy.forward
-// (models/cm/unet.py:413-441) for sequence lengths that are multiples of 128 (16x16 and 32x32 feature maps).
+// (models/cm/unet.py:413-441) for sequence lengths that are multiples of 128 (16x16 and 32x32 feature maps) and for
+// seq == 64 (8x8 maps: one 64-key tile; the upper 64 query rows of the 128-row MMA tile are zero-filled padding).
 //
 //   grid = (seq / 128, heads, batch); one CTA owns 128 query rows of one (image, head) and streams the keys in
 //   tiles of 128:   S = Q K^T  (tcgen05, M=128 N=128 K=64, fp32 in TMEM)
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-    const int n_tiles = p.seq / ATT_TILE;
+    const int kt = p.seq < ATT_TILE ? p.seq : ATT_TILE;  // keys per tile: 64 or 128
+    const int n_tiles = p.seq / kt;
 
     if (threadIdx.x == 0) {
         if (ptx::smem_u32(smem) & 1023u) {
@@ -83,18 +85,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
                 ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-                ptx::mbar_expect_tx(&kv_full[s], 32 * 1024);
-                ptx::tma_load_3d(smem + SM_K + s * 16384, &p.qk_map, &kv_full[s], p.k_col0 + head * ATT_D, j * ATT_TILE, b);
-                ptx::tma_load_3d(smem + SM_V + s * 16384, &p.vt_map, &kv_full[s], j * ATT_TILE, head * ATT_D, b);
-                ptx::tma_load_3d(smem + SM_V + s * 16384 + 8192, &p.vt_map, &kv_full[s], j * ATT_TILE + 64, head * ATT_D, b);
+                ptx::mbar_expect_tx(&kv_full[s], kt == ATT_TILE ? 32 * 1024 : 24 * 1024);
+                ptx::tma_load_3d(smem + SM_K + s * 16384, &p.qk_map, &kv_full[s], p.k_col0 + head * ATT_D, j * kt, b);
+                ptx::tma_load_3d(smem + SM_V + s * 16384, &p.vt_map, &kv_full[s], j * kt, head * ATT_D, b);
+                if (kt == ATT_TILE)
+                    ptx::tma_load_3d(smem + SM_V + s * 16384 + 8192, &p.vt_map, &kv_full[s], j * kt + 64, head * ATT_D, b);
             }
         }
         __syncwarp();
     } else if (warp == 5) {
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc_s = ptx::make_idesc(1, 128, 128);
+            const uint32_t idesc_s = ptx::make_idesc(1, 128, kt);
             constexpr uint32_t idesc_o = ptx::make_idesc(1, 128, 64);
+            const int pv_steps = kt / 16;
             const uint64_t dq = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + SM_Q));
             const uint32_t sp = ptx::smem_u32(smem + SM_P);
             auto issue_s = [&](int j) {
@@ -113,8 +117,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
                 ptx::mbar_wait(&p_full, j & 1);
                 ptx::tc_fence_after();
                 const uint32_t sv = ptx::smem_u32(smem + SM_V + s * 16384);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < pv_steps; ++k) {
                     const uint64_t da = ptx::make_kmajor_sw128_desc(sp + (k >> 2) * 16384) + 2 * (k & 3);
                     const uint64_t db = ptx::make_kmajor_sw128_desc(sv + (k >> 2) * 8192) + 2 * (k & 3);
                     ptx::umma_f16(tmem + TM_O, da, db, idesc_o, k > 0);
@@ -140,9 +143,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
             ptx::mbar_wait(&s_full, j & 1);
             ptx::tc_fence_after();
             // pass 1: row max of this key tile
+            const int ncol32 = kt >> 5;
             float mx = -INFINITY;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < ncol32; ++c) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
                 ptx::tmem_ld_wait();
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
             // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
             float rs = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < ncol32; ++c) {
                 uint32_t v[32];
                 ptx::tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
                 ptx::tmem_ld_wait();
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
         }
         const float inv = 1.f / l;
         __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.seq + q_tile * ATT_TILE + row) * p.ldo + head * ATT_D;
+        if (q_tile * ATT_TILE + row < p.seq) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             uint4 u;
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
             u.z = *reinterpret_cast<uint32_t*>(&t2);
             u.w = *reinterpret_cast<uint32_t*>(&t3);
             reinterpret_cast<uint4*>(dst)[q] = u;
+        }
         }
     }
 
@@ -223,8 +229,8 @@ const char* attn_last_error() { return g_attn_err; }
 int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
                  int heads, int seq, int d, float scale, AttnOp* op) {
     g_attn_err[0] = 0;
-    if (d != ATT_D || seq % ATT_TILE || (ldo & 7)) {
-        snprintf(g_attn_err, sizeof g_attn_err, "fused attention needs head dim 64 and seq %% 128 == 0 (got d=%d seq=%d)", d, seq);
+    if (d != ATT_D || (seq % ATT_TILE && seq != 64) || (ldo & 7)) {
+        snprintf(g_attn_err, sizeof g_attn_err, "fused attention needs head dim 64 and seq == 64 or seq %% 128 == 0 (got d=%d seq=%d)", d, seq);
         return -30;
     }
     AttnParams& p = op->p;
@@ -247,7 +253,7 @@ int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const 
     p.q_col0 = q_col0;
     p.k_col0 = k_col0;
     p.scale_log2 = scale * 1.4426950408889634f;
-    op->grid = dim3(seq / ATT_TILE, heads, B);
+    op->grid = dim3((seq + ATT_TILE - 1) / ATT_TILE, heads, B);
     op->flops = 4.0 * B * heads * (double)seq * seq * d;
     return 0;
 }

@@ -232,7 +232,7 @@ struct AdmBuilder : Builder {
         group_norm(x, Act{}, p + ".norm", EPS, 0, nullptr, 0, hn);
         bf16* o = (bf16*)scratch(4, (size_t)B * HW * C * 2);
         const float* qkv_bias = f32(p + ".qkv.bias");
-        if (dh == 64 && HW % 128 == 0) {
+        if (dh == 64 && (HW % 128 == 0 || HW == 64)) {
             bf16* qk = (bf16*)scratch(1, (size_t)B * HW * 2 * C * 2);
             bf16* vT = (bf16*)scratch(2, (size_t)B * HW * C * 2);
             {   // q | k = hn . W[0:2C]^T   (channel layout (three, heads, d): q rows first, then k, then v)

@@ -14,6 +14,7 @@ import os as _os
 L.lib().dxmi_set_option(b"dbg_mode", int(_os.environ.get("DBG_MODE", "0")))
 for name, N, H, Cin, Cout, taps, bn, res, stats in [
         ("p16_256_256_1x1", 256, 16, 256, 256, 1, 256, False, False), ("p16_256_256_1x1+res+stats", 256, 16, 256, 256, 1, 256, True, True),
+        ("p16_1x1+res", 256, 16, 256, 256, 1, 256, True, False), ("p16_1x1+stats", 256, 16, 256, 256, 1, 256, False, True),
         ("c16_256_256", 256, 16, 256, 256, 9, 256, False, False), ("c16_256_256+res+stats", 256, 16, 256, 256, 9, 256, True, True),
         ("c32_128_128", 256, 32, 128, 128, 9, 128, False, False), ("c4_256_256", 256, 4, 256, 256, 9, 256, False, False)]:
     x = torch.randn(N, H, H, Cin, device=dev).to(torch.bfloat16)

@@ -20,18 +20,32 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--T", type=int, default=4)
 ap.add_argument("--rollouts", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=1)
+ap.add_argument("--workload", default="cifar")
 args = ap.parse_args()
 
-net, sampler, value, sd, vsd = build_ddpm(args.T, device="cuda")
-noise = torch.randn(args.T + 1, args.batch, 3, 32, 32, device="cuda")
+if args.workload == "cifar":
+    net, sampler, value, sd, vsd = build_ddpm(args.T, device="cuda")
+    noise = torch.randn(args.T + 1, args.batch, 3, 32, 32, device="cuda")
+
+    def run():
+        d = sampler.sample(args.batch, device="cuda", noise=noise)
+        return value(d["sample"], args.T)
+else:
+    from common import EDM_IN64_CFG, build_edm
+
+    unet, sampler, sd = build_edm(EDM_IN64_CFG, args.T)
+    noise = torch.randn(args.T, args.batch, 3, 64, 64, device="cuda")
+    x0 = torch.randn(args.batch, 3, 64, 64, device="cuda") * 80
+    y = torch.randint(0, 1000, (args.batch,), device="cuda")
+
+    def run():
+        return sampler.sample(args.batch, device="cuda", i_class=y, x0=x0, noise=noise)["sample"]
 for _ in range(args.warmup):
-    d = sampler.sample(args.batch, device="cuda", noise=noise)
-    value(d["sample"], args.T)
+    run()
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_push("profiled_rollouts")
 for _ in range(args.rollouts):
-    d = sampler.sample(args.batch, device="cuda", noise=noise)
-    e = value(d["sample"], args.T)
+    e = run()
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
-print("energy mean", float(e.mean()))
+print("output mean", float(e.mean()))
