@@ -6,7 +6,8 @@
 
 A "step" is one rollout of the hot path over one batch of synthetic inputs: T U-Net denoising steps, each followed
 by the Gaussian transition with its learned sigma, then the energy / value net on the final samples.
-Workload (config.workload): BASELINE.json configs[1] - CIFAR-10, T=4, batch 256 per GPU, bf16 tensor-core math.
+Workload (config.workload): BASELINE.json configs[1] - CIFAR-10, T=4, batch 256 per GPU, bf16 tensor-core math
+(--workload in64 runs configs[2]'s per-GPU shard instead: ImageNet-64 EDM, T=10, batch 64 per GPU).
 The DDGAN backbone that config names is not in the reference tree, so the in-tree stand-in
 `VARSampler(n_timesteps=4)` + `unet_small.Model` is used and labelled as such.
 
@@ -35,8 +36,6 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "dxmi_rollout_images_per_sec"
 UNIT = "images/s"
-GF_PER_IMAGE_UNET = 12.444  # algorithmic GFLOP / image / forward
-GF_PER_IMAGE_VALUE = 1.613
 
 
 def peaks():
@@ -96,25 +95,60 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rollout_fn(T):
-    """The reference algorithm on the CPU (oracle port): returns f(B) -> seconds for one rollout + energy."""
+GF = {"cifar": (12.444, 1.613), "in64": (219.314, 6.454)}  # algorithmic GFLOP / image: U-Net forward, value net
+SHAPE = {"cifar": (3, 32, 32), "in64": (3, 64, 64)}
+DEFAULTS = {"cifar": (4, 256), "in64": (10, 64)}  # (T, images per GPU per step)
+
+
+def workload_name(wl, T, B):
+    if wl == "cifar":
+        return (f"CIFAR-10 DDPM U-Net (in-tree stand-in for the absent DDGAN backbone) DxMI T={T} sampler rollout + energy "
+                f"eval, batch {B}/GPU, bf16 tcgen05 (BASELINE.json configs[1])")
+    return (f"ImageNet64 EDM U-Net (models/cm, class-conditional) DxMI T={T} ancestral sampler rollout + energy eval, batch "
+            f"{B}/GPU, bf16 tcgen05 (BASELINE.json configs[2], per-GPU shard of the 512-image batch)")
+
+
+def cpu_oracle_rollout_fn(wl, T):
+    """The reference algorithm on the CPU (oracle port): returns f(B, seed) -> seconds for one rollout + energy."""
     import torch
 
-    from common import DDPM_CFG  # noqa: F401
     from oracle import nets, samplers, synth
 
     torch.set_num_threads(os.cpu_count() or 1)
-    shapes_net = json.load(open(os.path.join(ROOT, "tests", "golden", "ddpm_shapes.json")))
-    sd = synth.synth_state_dict({k: tuple(v) for k, v in shapes_net["net"].items()})
-    vsd = synth.synth_state_dict({k: tuple(v) for k, v in shapes_net["value"].items()}, seed=1)
-    sched = samplers.var_schedule(T)
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "ddpm_shapes.json")))
+    vsd = synth.synth_state_dict({k: tuple(v) for k, v in shapes["value"].items()}, seed=1)
+    if wl == "cifar":
+        sd = synth.synth_state_dict({k: tuple(v) for k, v in shapes["net"].items()})
+        sched = samplers.var_schedule(T)
+        log_betas = sched["log_betas_init"]
+
+        def run(B, seed=0):
+            noise = synth.synth_noise(T, B, SHAPE[wl], seed=seed)
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                d = samplers.var_rollout(lambda x, t: nets.ddpm_unet_forward(sd, x, t), sched, log_betas, noise)
+                nets.value_forward(vsd, d["sample"])
+            return time.perf_counter() - t0
+
+        return run
+    from common import EDM_IN64_CFG, adm_oracle_kwargs
+    from diffusion_by_maxentirl_b200.models.cm.script_util import create_model_and_diffusion
+
+    unet, _ = create_model_and_diffusion(**EDM_IN64_CFG)  # parameter shapes only (no CUDA call)
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()})
+    sd = {k: (v[..., None] if v.dim() == 3 else v) for k, v in sd.items()}
+    akw = adm_oracle_kwargs(EDM_IN64_CFG)
+    sched = samplers.edm_schedule(T)
     log_betas = sched["log_betas_init"]
 
     def run(B, seed=0):
-        noise = synth.synth_noise(T, B, (3, 32, 32), seed=seed)
+        noise = synth.synth_noise(T, B, SHAPE[wl], seed=seed)
+        noise[0] = noise[0] * 80.0
+        y = synth.synth_labels(B, seed=seed)
         t0 = time.perf_counter()
         with torch.no_grad():
-            d = samplers.var_rollout(lambda x, t: nets.ddpm_unet_forward(sd, x, t), sched, log_betas, noise)
+            d = samplers.edm_rollout(lambda x, t, yy: nets.adm_unet_forward(sd, x, t, yy, fp16_torso=False, **akw), sched,
+                                     log_betas, noise, y)
             nets.value_forward(vsd, d["sample"])
         return time.perf_counter() - t0
 
@@ -128,11 +162,13 @@ def run_reference(args):
         return
     import torch
 
-    T, Bs = args.T, 8
-    run = cpu_oracle_rollout_fn(T)
-    for _ in range(max(1, min(args.warmup, 2))):
+    wl = args.workload
+    T = args.T or DEFAULTS[wl][0]
+    Bs = 8 if wl == "cifar" else 1
+    run = cpu_oracle_rollout_fn(wl, T)
+    for _ in range(max(1, min(args.warmup, 2)) if wl == "cifar" else 0):
         run(Bs)
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, min(args.steps, 10 if wl == "cifar" else 2))
     t = [run(Bs, seed=i) for i in range(steps)]
     tot = sum(t)
     v = Bs * steps / tot
@@ -141,9 +177,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CIFAR-10 DDPM U-Net (DDGAN stand-in) DxMI T={T} rollout + energy, CPU oracle port of "
-                               f"the reference algorithm, bounded sample of {Bs} images per step",
-                   "T": T, "batch_per_step": Bs},
+        "config": {"workload": workload_name(wl, T, Bs) + " - CPU oracle port of the reference algorithm, bounded sample of "
+                               f"{Bs} images per step", "T": T, "batch_per_step": Bs},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} rollouts x {Bs} images, torch {torch.__version__} CPU fp32, {cores} threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -158,8 +193,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--T", type=int, default=4)
+    ap.add_argument("--workload", default="cifar", choices=["cifar", "in64"],
+                    help="cifar = BASELINE configs[1] (driver default); in64 = configs[2] per-GPU shard (ImageNet-64 EDM T=10)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step")
+    ap.add_argument("--T", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-n-256", type=int, default=None)
     args = ap.parse_args()
@@ -171,7 +208,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from common import build_ddpm
+    from common import EDM_IN64_CFG, VALUE_CFG, build_ddpm, build_edm, load_synth_into
     from diffusion_by_maxentirl_b200 import _lib as L
 
     rank = int(os.environ.get("RANK", "0"))
@@ -187,10 +224,33 @@ def main():
     if args.block_n_256 is not None:
         lib.dxmi_set_option(b"block_n_256", args.block_n_256)
 
-    T, B, K, W = args.T, args.batch, args.steps, args.warmup
-    net, sampler, value, sd, vsd = build_ddpm(T, device=dev)
-    shape = (3, 32, 32)
+    wl = args.workload
+    T = args.T or DEFAULTS[wl][0]
+    B = args.batch or DEFAULTS[wl][1]
+    K, W = args.steps, args.warmup
+    shape = SHAPE[wl]
     g = torch.Generator().manual_seed(1234 + rank)
+    if wl == "cifar":
+        net, sampler, value, sd, vsd = build_ddpm(T, device=dev)
+        labels = None
+
+        def rollout(noise):  # noise [T+1, B, C, H, W] on the device
+            d = sampler.sample(B, device=dev, noise=noise)
+            return d, value(d["sample"], T)
+    else:
+        from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
+        from diffusion_by_maxentirl_b200.models.value import TimeIndependentValue
+
+        net, sampler, sd = build_edm(EDM_IN64_CFG, T, device=dev)
+        value = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
+        load_synth_into(value, seed=1)
+        value.to(dev).eval()
+        labels = torch.randint(0, 1000, (B,), generator=g).to(dev)
+
+        def rollout(noise):  # noise[0] is x_0 / sigma_max
+            d = sampler.sample(B, device=dev, i_class=labels, x0=noise[0] * 80.0, noise=noise[1:])
+            return d, value(d["sample"], T)
+
     n_host_bufs = 2
     host_noise = [torch.randn(T + 1, B, *shape, generator=g).pin_memory() for _ in range(n_host_bufs)]
     dev_noise = host_noise[0].to(dev)
@@ -198,15 +258,17 @@ def main():
     gathered_s = torch.empty(world, B, *shape, dtype=torch.uint8, device=dev) if world > 1 else None
     gathered_e = torch.empty(world, B, dtype=torch.float32, device=dev) if world > 1 else None
 
+    def gather(d, e):
+        # the path's only collective: all-gather of u8 samples and energies (generate_large.py:43-50)
+        u8 = torch.empty(B, *shape, dtype=torch.uint8, device=dev)
+        L.check(lib.dxmi_quantize_u8(L.ptr(d["sample"]), L.ptr(u8), u8.numel(), L.stream_ptr()))
+        dist.all_gather_into_tensor(gathered_s.view(-1), u8.view(-1))
+        dist.all_gather_into_tensor(gathered_e.view(-1), e.view(-1))
+
     def rollout_resident():
-        d = sampler.sample(B, device=dev, noise=dev_noise)
-        e = value(d["sample"], T)
+        d, e = rollout(dev_noise)
         if world > 1:
-            # the path's only collective: all-gather of u8 samples and energies (generate_large.py:43-50)
-            u8 = torch.empty(B, *shape, dtype=torch.uint8, device=dev)
-            L.check(lib.dxmi_quantize_u8(L.ptr(d["sample"]), L.ptr(u8), u8.numel(), L.stream_ptr()))
-            dist.all_gather_into_tensor(gathered_s.view(-1), u8.view(-1))
-            dist.all_gather_into_tensor(gathered_e.view(-1), e.view(-1))
+            gather(d, e)
         return d, e
 
     def sync_all():
@@ -249,13 +311,9 @@ def main():
     t0 = time.perf_counter()
     for i in range(K):
         nz = host_noise[i % n_host_bufs].to(dev, non_blocking=True)
-        d = sampler.sample(B, device=dev, noise=nz)
-        e = value(d["sample"], T)
+        d, e = rollout(nz)
         if world > 1:
-            u8 = torch.empty(B, *shape, dtype=torch.uint8, device=dev)
-            L.check(lib.dxmi_quantize_u8(L.ptr(d["sample"]), L.ptr(u8), u8.numel(), L.stream_ptr()))
-            dist.all_gather_into_tensor(gathered_s.view(-1), u8.view(-1))
-            dist.all_gather_into_tensor(gathered_e.view(-1), e.view(-1))
+            gather(d, e)
         d2h_samples.copy_(d["sample"], non_blocking=True)
         d2h_energy.copy_(e, non_blocking=True)
         torch.cuda.synchronize()
@@ -274,15 +332,15 @@ def main():
         lib.dxmi_set_option(b"time_gemms", 1)
         kk = max(2, min(K, 5))
         for _ in range(kk):
-            d = sampler.sample(B, device=dev, noise=dev_noise)
-            value(d["sample"], T)
+            rollout(dev_noise)
         torch.cuda.synchronize()
         ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
         L.check(lib.dxmi_gemm_timing(C.byref(ms), C.byref(fl), C.byref(nl)))
         lib.dxmi_set_option(b"time_gemms", 0)
         achieved = fl.value / (ms.value * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all conv / attention GEMM launches)",
+        roof = {"bound": "tensor", "kernel": "conv_gemm2_kernel (persistent tcgen05 implicit GEMM: every conv / 1x1 / attention-"
+                                             "projection GEMM launch of the step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained",
                 "gemm_launches_per_step": nl.value // kk, "gemm_ms_per_step": ms.value / kk,
@@ -292,25 +350,25 @@ def main():
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        run = cpu_oracle_rollout_fn(T)
-        Bs = 8
-        run(Bs)
+        run = cpu_oracle_rollout_fn(wl, T)
+        Bs = 8 if wl == "cifar" else 1
+        if wl == "cifar":
+            run(Bs)
         ts, t_begin = [], time.perf_counter()
-        while len(ts) < 3 or (time.perf_counter() - t_begin < 10 and len(ts) < 20):
+        while len(ts) < (3 if wl == "cifar" else 1) or (time.perf_counter() - t_begin < 10 and len(ts) < 20):
             ts.append(run(Bs, seed=len(ts)))
         cores = torch.get_num_threads()
         cpu = {"value": Bs * len(ts) / sum(ts), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{len(ts)} rollouts x {Bs} images (T={T} + energy), oracle port, torch CPU fp32, {cores} threads"}
 
     if rank == 0:
+        gf_u, gf_v = GF[wl]
         line = {
             "metric": METRIC, "value": value_ips, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"CIFAR-10 DDPM U-Net (in-tree stand-in for the absent DDGAN backbone) DxMI T={T} "
-                                   f"sampler rollout + energy eval, batch {B}/GPU, bf16 tcgen05 (BASELINE.json configs[1])",
-                       "T": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "256 MiB write between timed steps (L2 flush)",
+            "config": {"workload": workload_name(wl, T, B), "T": T, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": f"dp{world}", "l2": "256 MiB write between timed steps (L2 flush)",
                        "collective": "all_gather(u8 samples, fp32 energies) per step" if world > 1 else "none"},
             "e2e": {"value": e2e_ips, "unit": UNIT, "h2d_bytes_per_step": host_noise[0].numel() * 4,
                     "d2h_bytes_per_step": d2h_samples.numel() * 4 + d2h_energy.numel() * 4},
@@ -318,7 +376,7 @@ def main():
             "clocks": clk,
             "roofline": roof,
             "cpu_baseline": cpu,
-            "model_tflops": value_ips * (T * GF_PER_IMAGE_UNET + GF_PER_IMAGE_VALUE) / 1e3,
+            "model_tflops": value_ips * (T * gf_u + gf_v) / 1e3,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
