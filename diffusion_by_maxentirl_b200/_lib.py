@@ -95,8 +95,8 @@ SYMBOLS = {
     "dxmi_value_forward": (_I, [_VP, _VP, _VP, _I, _VP]),
     "dxmi_var_step": (_I, [_VP] * 10 + [_I, _I, _VP]),
     "dxmi_edm_step": (_I, [_VP] * 6 + [_I, _I, _VP]),
-    "dxmi_var_rollout": (_I, [_VP, C.POINTER(_F), _I, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
-    "dxmi_edm_rollout": (_I, [_VP, C.POINTER(_F), _I, _VP, _VP, _VP, _VP, _I, _VP]),
+    "dxmi_var_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "dxmi_edm_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_quantize_u8": (_I, [_VP, _VP, _LL, _VP]),
     "dxmi_op_conv_gemm": (_I, [C.POINTER(GemmDesc), _VP]),
     "dxmi_op_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _LL, _LL, _VP]),

@@ -266,8 +266,8 @@ int dxmi_edm_step(const float* x, const float* F, const float* z, const float* c
     return (int)cudaGetLastError();
 }
 
-int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, float* l_sample, float* mean,
-                     float* control, float* logp, int B, dxmi_stream_t stream) {
+int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_dev, int T, const float* noise,
+                     float* l_sample, float* mean, float* control, float* logp, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized || net->net.a.arch != DXMI_ARCH_DDPM_UNET) {
         set_err("dxmi_var_rollout: needs a finalized DDPM U-Net handle");
         return -1;
@@ -281,13 +281,9 @@ int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, int T, const float
     // x_0 = first noise tensor (var_sampler.py:242)
     cudaMemcpyAsync(l_sample, noise, bchw * sizeof(float), cudaMemcpyDeviceToDevice, st);
     for (int i = 0; i < T; ++i) {
-        const float tau = sched_host[4 * i + 0], a = sched_host[4 * i + 1], c = sched_host[4 * i + 2],
-                    sg = sched_host[4 * i + 3];
-        fill_f32(p->tbuf, tau, B, st);
-        fill_f32(p->coef, a, B, st);
-        fill_f32(p->coef + B, c, B, st);
-        fill_f32(p->coef + 2 * B, sg, B, st);
-        count_launches(4);
+        var_fill(p->tbuf, p->coef, p->coef + B, p->coef + 2 * B, B, sched_host[3 * i + 0], sched_host[3 * i + 1],
+                 sched_host[3 * i + 2], sigma_dev + i, st);
+        count_launches(1);
         const float* xi = l_sample + (long long)i * bchw;
         p->x = xi;
         p->x_scale = nullptr;
@@ -305,8 +301,8 @@ int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, int T, const float
     return (int)cudaGetLastError();
 }
 
-int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, const int64_t* y,
-                     float* l_sample, float* mean, int B, dxmi_stream_t stream) {
+int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_noise_dev, int T, const float* noise,
+                     const int64_t* y, float* l_sample, float* mean, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized || net->net.a.arch != DXMI_ARCH_ADM_UNET) {
         set_err("dxmi_edm_rollout: needs a finalized ADM U-Net handle");
         return -1;
@@ -325,7 +321,7 @@ int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, int T, const float
     for (int i = 0; i < T; ++i) {
         float* coef = p->coef;           // [B, 5]
         float* x_scale = p->coef + 5 * B;  // [B]
-        edm_fill(coef, x_scale, p->tbuf, B, sched_host + 7 * i, st);
+        edm_fill(coef, x_scale, p->tbuf, B, sched_host + 6 * i, sigma_noise_dev + i, st);
         count_launches(1);
         const float* xi = l_sample + (long long)i * bchw;
         p->x = xi;

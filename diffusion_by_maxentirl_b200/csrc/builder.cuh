@@ -358,25 +358,13 @@ struct Builder {
         const float* st2 = x2.stats;
         if (st1 && (C2 == 0 || st2) && stats_seg(HW)) {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
-            int P = HW / stats_seg(HW);
-            if (P > 8) {
-                // large maps: collapse the row-segment partials once so the apply CTAs' prologue stays tiny
-                float* c1 = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
-                float* c2 = c1 ? c1 + (size_t)B * C1 * 2 : nullptr;
-                const int Pin = P;
-                op([=](cudaStream_t st) {
-                    gn_collapse(st1, c1, Bn, Pin, C1, st);
-                    if (C2) gn_collapse(st2, c2, Bn, Pin, C2, st);
-                    return (int)cudaGetLastError();
-                }, C2 ? 2 : 1);
-                st1 = c1;
-                st2 = c2;
-                P = 1;
-            }
+            const int P = HW / stats_seg(HW);
+            float* ab = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
             op([=](cudaStream_t st) {
-                gn_apply_fused(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P, st2, P, out, st);
+                gn_finalize_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P, st2, P, ab,
+                                  out, st);
                 return (int)cudaGetLastError();
-            });
+            }, 2);
             return;
         }
         op([=](cudaStream_t st) {

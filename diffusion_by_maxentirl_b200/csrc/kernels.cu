@@ -487,11 +487,138 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __res
     }
 }
 
+// ---- finalize + apply: statistics -> per-(image, channel) affine (a, b), then a pure streaming pass  y = act(a*x + b)
+// st1 / st2 = [N][P1 | P2][C1 | C2][2] partial (sum, sumsq) from the producer GEMM epilogues. One CTA per image; every
+// reduction runs in a fixed order (deterministic).
+__global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restrict__ st1, int P1, int C1,
+                                                           const float* __restrict__ st2, int P2, int C2, int HW, int groups,
+                                                           float eps, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ film,
+                                                           int film_ld, float2* __restrict__ ab) {
+    __shared__ float s_mean[32], s_rstd[32];
+    __shared__ float2 s_ch[2048];
+    const int C = C1 + C2;
+    const int n = blockIdx.x;
+    const int cpg = C / groups;
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        const bool first = c < C1;
+        const float* base = first ? st1 + ((long long)n * P1 * C1 + c) * 2 : st2 + ((long long)n * P2 * C2 + (c - C1)) * 2;
+        const int P = first ? P1 : P2;
+        const long long stride = (long long)(first ? C1 : C2) * 2;
+        float s = 0.f, q = 0.f;
+        int seg = 0;
+        for (; seg + 4 <= P; seg += 4) {  // 4 independent loads in flight, summed in a fixed order
+            const float2 v0 = *reinterpret_cast<const float2*>(base + (seg + 0) * stride);
+            const float2 v1 = *reinterpret_cast<const float2*>(base + (seg + 1) * stride);
+            const float2 v2 = *reinterpret_cast<const float2*>(base + (seg + 2) * stride);
+            const float2 v3 = *reinterpret_cast<const float2*>(base + (seg + 3) * stride);
+            s += (v0.x + v1.x) + (v2.x + v3.x);
+            q += (v0.y + v1.y) + (v2.y + v3.y);
+        }
+        for (; seg < P; ++seg) {
+            const float2 v = *reinterpret_cast<const float2*>(base + seg * stride);
+            s += v.x;
+            q += v.y;
+        }
+        s_ch[c] = make_float2(s, q);
+    }
+    __syncthreads();
+    {
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        float s = 0.f, q = 0.f;
+        if (g < groups) {
+            for (int i = sub; i < cpg; i += 8) {
+                const float2 v = s_ch[g * cpg + i];
+                s += v.x;
+                q += v.y;
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && sub == 0) {
+            const float cnt = (float)cpg * (float)HW;
+            const float mean = s / cnt;
+            const float var = fmaxf(q / cnt - mean * mean, 0.f);
+            s_mean[g] = mean;
+            s_rstd[g] = rsqrtf(var + eps);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        const int g = c / cpg;
+        float aa = s_rstd[g] * gamma[c];
+        float bb = beta[c] - s_mean[g] * aa;
+        if (film) {
+            const float sc = 1.f + film[(long long)n * film_ld + c];
+            const float sh = film[(long long)n * film_ld + C + c];
+            aa *= sc;
+            bb = bb * sc + sh;
+        }
+        ab[(long long)n * C + c] = make_float2(aa, bb);
+    }
+}
+
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_ab_k(const bf16* __restrict__ x1, int C1, int ld1,
+                                                           const bf16* __restrict__ x2, int C2, int ld2, int HW,
+                                                           const float2* __restrict__ ab, int silu, int slabs,
+                                                           bf16* __restrict__ out) {
+    const int C = C1 + C2;
+    const int CV = C / 8;
+    const int PL = GN_THREADS / CV;
+    const int n = blockIdx.x, slab = blockIdx.y;
+    const int pix_per_slab = HW / slabs;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    if (pl >= PL) return;
+    float a[8], b[8];
+    {
+        const float4* src = reinterpret_cast<const float4*>(ab + (long long)n * C + cv * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = __ldg(src + j);
+            a[2 * j] = v.x;
+            b[2 * j] = v.y;
+            a[2 * j + 1] = v.z;
+            b[2 * j + 1] = v.w;
+        }
+    }
+    const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
+    int p = pl;
+    for (; p + 3 * PL < pix_per_slab; p += 4 * PL) {
+        bf16x8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + p + u * PL, cv * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(f[j], a[j], b[j]);
+                f[j] = silu ? silu_f(t) : t;
+            }
+            st8(out + (base + p + u * PL) * C + cv * 8, pack8(f));
+        }
+    }
+    for (; p < pix_per_slab; p += PL) {
+        float f[8];
+        unpack8(ld8(gn_src(x1, C1, ld1, x2, ld2, base + p, cv * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(f[j], a[j], b[j]);
+            f[j] = silu ? silu_f(t) : t;
+        }
+        st8(out + (base + p) * C + cv * 8, pack8(f));
+    }
+}
+
 int gn_apply_slabs(int N, int HW, int C) {
     // enough CTAs for ~16 per SM, but keep >= 4 pixels per pixel-lane per slab so the unrolled loop has work
     const int PL = GN_THREADS / (C / 8) > 0 ? GN_THREADS / (C / 8) : 1;
     int slabs = 1;
-    while (N * slabs < 1184 && HW / (slabs * 2) >= 4 * PL && HW % (slabs * 2) == 0) slabs *= 2;
+    while (N * slabs < 2368 && HW / (slabs * 2) >= 8 * PL && HW % (slabs * 2) == 0) slabs *= 2;
     return slabs;
 }
 
@@ -502,6 +629,17 @@ void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int
     dim3 grid(N, slabs);
     gn_apply_fused_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, groups, eps, gamma, beta, film, film_ld, silu,
                                                    st1, P1, st2, P2, slabs, out);
+}
+
+void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
+                       float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
+                       const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st) {
+    gn_finalize_k<<<N, GN_THREADS, 0, st>>>(st1, P1, C1, st2, P2, C2, HW, groups, eps, gamma, beta, film, film_ld,
+                                            reinterpret_cast<float2*>(ab_ws));
+    const int slabs = gn_apply_slabs(N, HW, C1 + C2);
+    dim3 grid(N, slabs);
+    gn_apply_ab_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs,
+                                               out);
 }
 
 // [N][P][C][2] -> [N][1][C][2]: collapses many row-segment partials (large feature maps) so that the apply kernel's
@@ -808,21 +946,38 @@ void edm_step(const float* x, const float* F, const float* z, const float* coef,
 }
 
 // per-step coefficient broadcast for the EDM rollout: coef[n] = v[2..6], x_scale[n] = v[0], t[n] = v[1]
-struct Coef7 {
-    float v[7];
+struct Coef6 {
+    float v[6];
 };
-__global__ void edm_fill_k(float* __restrict__ coef, float* __restrict__ x_scale, float* __restrict__ t, int N, Coef7 c) {
+__global__ void edm_fill_k(float* __restrict__ coef, float* __restrict__ x_scale, float* __restrict__ t, int N, Coef6 c,
+                           const float* __restrict__ sigma_noise) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     x_scale[n] = c.v[0];
     t[n] = c.v[1];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) coef[n * 5 + j] = c.v[2 + j];
+    for (int j = 0; j < 4; ++j) coef[n * 5 + j] = c.v[2 + j];
+    coef[n * 5 + 4] = *sigma_noise;
 }
-void edm_fill(float* coef, float* x_scale, float* t, int N, const float* row7, cudaStream_t st) {
-    Coef7 c;
-    for (int j = 0; j < 7; ++j) c.v[j] = row7[j];
-    edm_fill_k<<<(N + 127) / 128, 128, 0, st>>>(coef, x_scale, t, N, c);
+void edm_fill(float* coef, float* x_scale, float* t, int N, const float* row6, const float* sigma_noise_dev, cudaStream_t st) {
+    Coef6 c;
+    for (int j = 0; j < 6; ++j) c.v[j] = row6[j];
+    edm_fill_k<<<(N + 127) / 128, 128, 0, st>>>(coef, x_scale, t, N, c, sigma_noise_dev);
+}
+
+// per-step coefficient broadcast for the VAR rollout: t[n] = tau, a[n] = a, c[n] = c (host scalars), sigma[n] = *sigma_dev
+__global__ void var_fill_k(float* __restrict__ t, float* __restrict__ a, float* __restrict__ c, float* __restrict__ sigma, int N,
+                           float tau, float av, float cv, const float* __restrict__ sigma_dev) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    t[n] = tau;
+    a[n] = av;
+    c[n] = cv;
+    sigma[n] = *sigma_dev;
+}
+void var_fill(float* t, float* a, float* c, float* sigma, int N, float tau, float av, float cv, const float* sigma_dev,
+              cudaStream_t st) {
+    var_fill_k<<<(N + 127) / 128, 128, 0, st>>>(t, a, c, sigma, N, tau, av, cv, sigma_dev);
 }
 
 // ============================================================================================ value head

@@ -41,6 +41,10 @@ void gn_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, 
 void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups, float eps,
                     const float* gamma, const float* beta, const float* film, int film_ld, int silu, const float* st1,
                     int P1, const float* st2, int P2, bf16* out, cudaStream_t st);
+// two launches: per-image finalize (statistics -> per-channel affine, ab_ws = [N][C1+C2][2] floats) + streaming apply
+void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
+                       float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
+                       const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st);
 // [N][P][C][2] -> [N][1][C][2]
 void gn_collapse(const float* in, float* out, int N, int P, int C, cudaStream_t st);
 // y = bf16(silu(x))  (A operand of the batched temb / emb projection GEMM)
@@ -75,8 +79,12 @@ void var_step(const float* x, const float* eps, const float* z, const float* a, 
 void edm_step(const float* x, const float* F, const float* z, const float* coef, float* xn, float* mean, int N, int CHW,
               cudaStream_t st);
 
-// broadcast one EDM schedule row {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down, sigma_noise} to per-sample tables
-void edm_fill(float* coef, float* x_scale, float* t, int N, const float* row7, cudaStream_t st);
+// broadcast one EDM schedule row {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down} (host) + the step's noise scale
+// (device scalar: it derives from the learnable log_betas) to per-sample tables
+void edm_fill(float* coef, float* x_scale, float* t, int N, const float* row6, const float* sigma_noise_dev, cudaStream_t st);
+// same for the VARSampler rollout: {tau, a, c} host scalars + device sigma
+void var_fill(float* t, float* a, float* c, float* sigma, int N, float tau, float av, float cv, const float* sigma_dev,
+              cudaStream_t st);
 
 // ---- value head (modules.py:150-158): relu -> sum over HW -> Linear(C,1) -> Linear(1,1) ---------------------------------
 void value_head(const bf16* h, int N, int HW, int C, const float* lin_w, const float* lin_b, const float* scale_w,

@@ -49,17 +49,19 @@ class OpenAIDiffusion:
         return self.net.parameters()
 
     # ------------------------------------------------------------------ noise scale actually applied (reference :79-92)
-    def _noise_sigma(self, indices):
-        """indices: CPU long tensor [B] -> CPU float tensor [B] of the per-step noise scale."""
-        sigma_up = self.sigma_up[indices]
+    def _noise_sigma(self, indices, device):
+        """indices: CPU long tensor [B] -> float tensor [B] ON `device` of the noise scale applied at those steps.
+        log_betas is read on the device (no host sync; the call stays CUDA-graph capturable)."""
+        sigma_up = self.sigma_up[indices].to(device)
         if not self.trainable_beta:
             return sigma_up
-        sigma = torch.exp(_inner(self.net).log_betas.detach().float().cpu()[indices])
+        idx = indices.to(device)
+        sigma = torch.exp(_inner(self.net).log_betas.detach().float().to(device)[idx])
         if self.trainable_beta == "fix_last":
-            terminal = indices == self.n_timesteps - 1
+            terminal = (indices == self.n_timesteps - 1).to(device)
             sigma = sigma * ~terminal + sigma_up * terminal
         elif self.trainable_beta == "fix_last3":
-            non_terminal = indices < self.n_timesteps - 3
+            non_terminal = (indices < self.n_timesteps - 3).to(device)
             sigma = sigma * non_terminal + sigma_up * (~non_terminal)
         return sigma
 
@@ -72,13 +74,14 @@ class OpenAIDiffusion:
         c_skip, c_out, c_in = self.diffusion.get_scalings(sigma)
         rescaled_t = 1000 * 0.25 * torch.log(sigma + 1e-44)
         F = self.net(x, rescaled_t.to(device), x_scale=c_in.to(device), **model_kwargs)
-        s_noise = self._noise_sigma(indices)
-        coef = torch.stack([c_skip, c_out, sigma, self.sigma_down[indices], s_noise], dim=1).float().contiguous().to(device)
+        s_noise = self._noise_sigma(indices, device).float()
+        coef = torch.cat([torch.stack([c_skip, c_out, sigma, self.sigma_down[indices]], dim=1).float().to(device),
+                          s_noise[:, None]], dim=1).contiguous()
         z = torch.randn_like(x) if noise is None else noise.to(device=device, dtype=torch.float32).contiguous()
         xn, mu = torch.empty_like(x), torch.empty_like(x)
         L.check(L.lib().dxmi_edm_step(L.ptr(x), L.ptr(F), L.ptr(z), L.ptr(coef), L.ptr(xn), L.ptr(mu), B, x[0].numel(),
                                       L.stream_ptr()), "dxmi_edm_step")
-        return {"sample": xn, "mean": mu, "sigma": s_noise.to(device).clamp(1e-4, None)}
+        return {"sample": xn, "mean": mu, "sigma": s_noise.clamp(1e-4, None)}
 
     def sample(self, n_sample, device, i_class=None, enable_grad=False, x0=None, noise=None):
         """Reference OpenAIDiffusion.sample (:101-127).  `noise` (optional, parity contract): the T per-step z tensors
@@ -113,15 +116,16 @@ class OpenAIDiffusion:
         idx = torch.arange(T)
         sigma = self.sigmas[idx]
         c_skip, c_out, c_in = self.diffusion.get_scalings(sigma)
-        s_noise = self._noise_sigma(idx)
-        sched = torch.stack([c_in, 1000 * 0.25 * torch.log(sigma + 1e-44), c_skip, c_out, sigma, self.sigma_down[idx],
-                             s_noise], dim=1).float().contiguous()
+        s_noise = self._noise_sigma(idx, device).float().contiguous()
+        sched = torch.stack([c_in, 1000 * 0.25 * torch.log(sigma + 1e-44), c_skip, c_out, sigma, self.sigma_down[idx]],
+                            dim=1).float().contiguous()
         l_sample = torch.empty(T + 1, B, *shape, device=device)
         mean = torch.empty(T, B, *shape, device=device)
         L.check(
-            L.lib().dxmi_edm_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), T, L.ptr(buf), L.ptr(i_class),
+            L.lib().dxmi_edm_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), L.ptr(s_noise), T, L.ptr(buf),
+                                     L.ptr(i_class),
                                      L.ptr(l_sample), L.ptr(mean), B, L.stream_ptr()),
             "dxmi_edm_rollout")
-        sig_dev = s_noise.clamp(1e-4, None).to(device)
+        sig_dev = s_noise.clamp(1e-4, None)
         return {"sample": l_sample[T], "l_sample": [l_sample[i] for i in range(T + 1)], "y": i_class,
                 "mean": [mean[i] for i in range(T)], "sigma": [sig_dev[i].repeat(B) for i in range(T)]}

@@ -40,15 +40,18 @@ class VARSampler(nn.Module):
         self.register_buffer("diffusion_steps_list", s.diffusion_steps_list)
         if trainable_beta == "fix_last":
             _inner(self.net).register_buffer("std", s.std.clone())
+        # host copy of the constant schedule rows {tau, a, c * adhoc_scale1}: the rollout call needs no device read
+        self._sched_host = torch.stack([s.continuous_steps.float(), s.x_prev_multiplier,
+                                        s.theta_multiplier * adhoc_scale1], dim=1).contiguous()
 
     # ------------------------------------------------------------------ per-step noise scale (reference :268-283)
     def _sigmas(self):
         net = _inner(self.net)
         if self.trainable_beta == "fix_last":
-            return torch.exp(torch.cat([net.log_betas[:-1], net.std[-1].log().unsqueeze(0)])).detach()
+            return torch.exp(torch.cat([net.log_betas[:-1], net.std[-1].log().unsqueeze(0)])).detach().float()
         if self.trainable_beta:
-            return torch.exp(net.log_betas).detach()
-        return self.std
+            return torch.exp(net.log_betas).detach().float()
+        return self.std.float()
 
     def _forward_net(self, x, t):
         # go through self.net (possibly DDP-wrapped) so hooks / wrappers behave as with the reference
@@ -75,18 +78,16 @@ class VARSampler(nn.Module):
             noise_t = (torch.stack(list(noise)) if not torch.is_tensor(noise) else noise).to(device=device, dtype=torch.float32).contiguous()
             assert noise_t.shape == (T + 1, B, *shape)
         h = net._ensure_handle(device)
-        sig = self._sigmas().float().cpu()
-        sched = torch.stack([self.continuous_steps.cpu().float(), self.x_prev_multiplier.cpu(),
-                             self.theta_multiplier.cpu() * self.adhoc_scale1, sig], dim=1).contiguous()
+        sig_dev = self._sigmas().to(device).contiguous()  # device tensor: no host sync (and CUDA-graph capturable)
+        sched = self._sched_host
         l_sample = torch.empty(T + 1, B, *shape, device=device)
         mean = torch.empty(T, B, *shape, device=device)
         control = torch.empty(T, B, *shape, device=device)
         logp = torch.empty(T, B, device=device)
         L.check(
-            L.lib().dxmi_var_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), T, L.ptr(noise_t),
+            L.lib().dxmi_var_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), L.ptr(sig_dev), T, L.ptr(noise_t),
                                      L.ptr(l_sample), L.ptr(mean), L.ptr(control), L.ptr(logp), B, L.stream_ptr()),
             "dxmi_var_rollout")
-        sig_dev = sig.to(device)
         return {
             "sample": l_sample[T],
             "l_sample": [l_sample[i] for i in range(T + 1)],

@@ -91,15 +91,17 @@ int dxmi_edm_step(const float* x, const float* F, const float* z, const float* c
 
 /* -------------------------------------------------------------------------------------------- rollouts */
 /* VARSampler.sample() (var_sampler.py:411-428 -> VAR_sampling :204-297): the whole T-step loop in one call.
- * sched (host) [T,4] fp32 rows {tau_i, a_i, c_i * adhoc_scale1, sigma_i} (Appendix E.1 of SURVEY.md);
+ * sched (host) [T,3] fp32 rows {tau_i, a_i, c_i * adhoc_scale1} (Appendix E.1 of SURVEY.md); sigma (DEVICE) [T] fp32 =
+ * the per-step noise scale (it derives from the learnable log_betas, so it stays on the device: no host sync);
  * noise [T+1,B,C,H,W] fp32: noise[0] = x_0, noise[1+i] = z of step i (host-supplied noise is part of the parity
  * contract); l_sample [T+1,B,C,H,W]; mean, control [T,B,C,H,W] or NULL; logp [T,B] or NULL. */
-int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, float* l_sample, float* mean,
-                     float* control, float* logp, int B, dxmi_stream_t stream);
-/* OpenAIDiffusion.sample() (openai_diffusion.py:101-127). sched (host) [T,7] fp32 rows
- * {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down, sigma_noise}; noise[0] = x_0 (already scaled by sigma_max). */
-int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, int T, const float* noise, const int64_t* y,
-                     float* l_sample, float* mean, int B, dxmi_stream_t stream);
+int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_dev, int T, const float* noise,
+                     float* l_sample, float* mean, float* control, float* logp, int B, dxmi_stream_t stream);
+/* OpenAIDiffusion.sample() (openai_diffusion.py:101-127). sched (host) [T,6] fp32 rows
+ * {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down}; sigma_noise (DEVICE) [T] fp32 = the noise scale actually applied
+ * per step (openai_diffusion.py:79-92); noise[0] = x_0 (already scaled by sigma_max). */
+int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_noise_dev, int T, const float* noise,
+                     const int64_t* y, float* l_sample, float* mean, int B, dxmi_stream_t stream);
 
 /* samples in [-1,1] -> uint8 ((x+1)*127.5 clamp), generate_large.py:43 */
 int dxmi_quantize_u8(const float* x, uint8_t* out, long long n, dxmi_stream_t stream);
