@@ -1,5 +1,6 @@
 // extern "C" surface of libdxmi_b200.so (see include/dxmi_b200.h for the contract of every entry point).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "attn_tc.cuh"
@@ -196,8 +197,14 @@ size_t dxmi_workspace_bytes(dxmi_net_t net, int B) {
 }
 
 static int run_plan(Net& n, Plan* p, cudaStream_t st) {
-    for (auto& f : p->ops) {
+    static const bool debug_sync = getenv("DXMI_DEBUG_SYNC") != nullptr;
+    for (size_t i = 0; i < p->ops.size(); ++i) {
+        auto& f = p->ops[i];
         int r = f(st);
+        if (!r && debug_sync) r = (int)cudaStreamSynchronize(st);
+        if (r && debug_sync)
+            fprintf(stderr, "dxmi: op %zu/%zu '%s' failed with %d\n", i, p->ops.size(),
+                    i < p->op_names.size() ? p->op_names[i].c_str() : "?", r);
         if (r) {
             snprintf(g_api_err, sizeof g_api_err, "kernel launch failed (%d): %s | %s", r,
                      cudaGetErrorString((cudaError_t)r), gemm_op_last_error());

@@ -31,10 +31,8 @@ struct Builder {
     }
     void* scratch(int slot, size_t bytes) {
         bytes = align_up(bytes);
-        if (dry) {
-            if (bytes > scratch_max[slot]) scratch_max[slot] = bytes;
-            return nullptr;
-        }
+        if (bytes > scratch_max[slot]) scratch_max[slot] = bytes;  // tracked in both passes (they must agree)
+        if (dry) return nullptr;
         return plan.arena + scratch_base[slot];
     }
     bf16* act_alloc(int C, int H, int W) { return (bf16*)alloc((size_t)B * H * W * C * sizeof(bf16)); }
@@ -52,7 +50,8 @@ struct Builder {
         a.C = C;
         a.H = H;
         a.W = W;
-        a.stats = want_stats ? stats_alloc(C, H, W) : nullptr;
+        a.has_stats = want_stats && stats_seg(H * W) != 0;
+        a.stats = a.has_stats ? stats_alloc(C, H, W) : nullptr;
         return a;
     }
 
@@ -225,9 +224,11 @@ struct Builder {
     }
 
     // ---------------------------------------------------------------- op emission
+    std::string cur_label;  // set by the network builders before emitting a block
     void op(std::function<int(cudaStream_t)> f, int launches = 1) {
         if (dry) return;
         plan.ops.push_back(std::move(f));
+        plan.op_names.push_back(cur_label);
         plan.launches_per_run += launches;
     }
     void gemm(const dxmi_gemm_desc& d_in) {
@@ -242,7 +243,13 @@ struct Builder {
             return;
         }
         plan.gemm_flops += g.flops;
+        const std::string keep = cur_label;
+        char buf[160];
+        snprintf(buf, sizeof buf, "%s gemm M=%d N=%d bn=%d v2=%d batch=%d", keep.c_str(), g.p.M_total, g.p.N_total, g.block_n, g.use_v2,
+                 g.batch);
+        cur_label = buf;
         op([g](cudaStream_t st) { return run_gemm(g, st); });
+        cur_label = keep;
     }
     // GEMM whose fp32 NCHW output pointer is the per-call network output (plan.out)
     void gemm_to_plan_out(const dxmi_gemm_desc& d) {
@@ -345,6 +352,7 @@ struct Builder {
     // GroupNorm(32) over concat(x1, x2) -> out (scratch slot), optional SiLU / FiLM
     void group_norm(Act x1, Act x2, const std::string& pfx, float eps, int silu, const float* film, int film_ld,
                     bf16* out) {
+        cur_label = pfx;
         const int HW = x1.H * x1.W;
         const int slabs = gn_num_slabs(B, HW);
         float* ws = (float*)scratch(5, (size_t)B * slabs * 64 * sizeof(float));
@@ -356,7 +364,7 @@ struct Builder {
         if ((C1 + C2) % 8 || (C1 % 8) || (C1 + C2) > 2048) fail("group_norm: unsupported channel count");
         const float* st1 = x1.stats;
         const float* st2 = x2.stats;
-        if (st1 && (C2 == 0 || st2) && stats_seg(HW)) {
+        if (x1.has_stats && (C2 == 0 || x2.has_stats) && stats_seg(HW)) {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
             const int P = HW / stats_seg(HW);
             float* ab = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
@@ -402,6 +410,12 @@ int build_two_pass(Net& net, Plan& plan) {
         engine_set_error("internal: dry/real arena mismatch (%zu vs %zu)", dryb.off, b.off);
         return -21;
     }
+    for (int s = 0; s < Builder::NSLOT; ++s)
+        if (b.scratch_max[s] > dryb.scratch_max[s]) {
+            engine_set_error("internal: scratch slot %d grew between the sizing and the real pass (%zu vs %zu bytes)", s,
+                             dryb.scratch_max[s], b.scratch_max[s]);
+            return -23;
+        }
     return 0;
 }
 

@@ -162,6 +162,7 @@ struct DdpmBuilder : Builder {
     std::vector<std::string> tproj_w, tproj_b;
 
     Act resblock(const std::string& p, Act xa, Act xb, int Cout) {
+        cur_label = p;
         const int H = xa.H, W = xa.W, HW = H * W;
         const int Cin = xa.C + xb.C;
         bf16* g1 = (bf16*)scratch(0, (size_t)B * HW * Cin * 2);
@@ -188,7 +189,7 @@ struct DdpmBuilder : Builder {
         }
         tproj_off += Cout;
         bf16* g2 = (bf16*)scratch(0, (size_t)B * HW * Cout * 2);
-        Act h1a{h1, Cout, H, W, h1_stats};
+        Act h1a{h1, Cout, H, W, h1_stats, stats_seg(HW) != 0};
         group_norm(h1a, Act{}, p + ".norm2", 1e-6f, 1, nullptr, 0, g2);
         Act out = new_act(Cout, H, W);
         {
@@ -227,6 +228,7 @@ struct DdpmBuilder : Builder {
     }
 
     Act attn(const std::string& p, Act x) {
+        cur_label = p;
         const int C = x.C, H = x.H, W = x.W, HW = H * W;
         bf16* hn = (bf16*)scratch(0, (size_t)B * HW * C * 2);
         group_norm(x, Act{}, p + ".norm", 1e-6f, 0, nullptr, 0, hn);

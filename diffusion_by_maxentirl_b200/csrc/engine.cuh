@@ -26,12 +26,14 @@ struct Bound {
 struct Act {  // NHWC bf16 activation
     bf16* p = nullptr;
     int C = 0, H = 0, W = 0;
-    float* stats = nullptr;  // GroupNorm partials written by the producing GEMM: [B*H*W/32][C][2], or null
+    float* stats = nullptr;  // GroupNorm partials written by the producing GEMM: [B*H*W/seg][C][2] (null in the dry pass)
+    bool has_stats = false;  // pass-independent: the sizing (dry) pass must take the same branches as the real one
 };
 
 struct Plan {
     int B = 0;
     std::vector<std::function<int(cudaStream_t)>> ops;
+    std::vector<std::string> op_names;  // debug labels (DXMI_DEBUG_SYNC=1 reports the failing op)
     char* arena = nullptr;
     size_t arena_bytes = 0;
     // per-call I/O (read by the closures at launch time)

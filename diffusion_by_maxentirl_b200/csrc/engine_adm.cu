@@ -127,6 +127,7 @@ struct AdmBuilder : Builder {
     static constexpr float EPS = 1e-5f;  // models/cm/nn.py:109-116 (GroupNorm32 default eps)
 
     Act resblock(const std::string& p, Act xa, Act xb, int Cout, LayerKind mode) {
+        cur_label = p;
         const dxmi_arch_desc& a = net.a;
         const int H = xa.H, W = xa.W;
         const int Cin = xa.C + xb.C;
@@ -181,7 +182,7 @@ struct AdmBuilder : Builder {
             gemm(d);
         }
         bf16* g2 = (bf16*)scratch(0, (size_t)B * Ho * Wo * Cout * 2);
-        group_norm(Act{h1, Cout, Ho, Wo, h1_stats}, Act{}, p + ".out_layers.0", EPS, 1, film_mode && film ? film + film_off : nullptr,
+        group_norm(Act{h1, Cout, Ho, Wo, h1_stats, stats_seg(Ho * Wo) != 0}, Act{}, p + ".out_layers.0", EPS, 1, film_mode && film ? film + film_off : nullptr,
                    film_ld, g2);
         film_off += emb_cols;
         Act out = new_act(Cout, Ho, Wo);
@@ -222,6 +223,7 @@ struct AdmBuilder : Builder {
     }
 
     Act attention(const std::string& p, Act x) {
+        cur_label = p;
         const dxmi_arch_desc& a = net.a;
         const int C = x.C, H = x.H, W = x.W, HW = H * W;
         const int heads = a.num_head_channels > 0 ? C / a.num_head_channels : a.num_heads;

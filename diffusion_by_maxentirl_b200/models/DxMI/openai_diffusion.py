@@ -49,6 +49,30 @@ class OpenAIDiffusion:
         return self.net.parameters()
 
     # ------------------------------------------------------------------ noise scale actually applied (reference :79-92)
+    def _tables(self, device):
+        """Device copies of the constant [T] tables (made once per device, outside any CUDA-graph capture)."""
+        key = str(device)
+        cache = self.__dict__.setdefault("_dev_tables", {})
+        if key not in cache:
+            T = self.n_timesteps
+            steps = torch.arange(T)
+            cache[key] = {"sigma_up": self.sigma_up.to(device), "terminal": (steps == T - 1).to(device),
+                          "non_terminal3": (steps < T - 3).to(device)}
+        return cache[key]
+
+    def _noise_sigma_all(self, device):
+        """[T] noise scales of all steps, computed on the device from the live log_betas (capturable, no sync)."""
+        tab = self._tables(device)
+        sigma_up = tab["sigma_up"]
+        if not self.trainable_beta:
+            return sigma_up
+        sigma = torch.exp(_inner(self.net).log_betas.detach().float().to(device))
+        if self.trainable_beta == "fix_last":
+            sigma = sigma * ~tab["terminal"] + sigma_up * tab["terminal"]
+        elif self.trainable_beta == "fix_last3":
+            sigma = sigma * tab["non_terminal3"] + sigma_up * ~tab["non_terminal3"]
+        return sigma
+
     def _noise_sigma(self, indices, device):
         """indices: CPU long tensor [B] -> float tensor [B] ON `device` of the noise scale applied at those steps.
         log_betas is read on the device (no host sync; the call stays CUDA-graph capturable)."""
@@ -116,7 +140,7 @@ class OpenAIDiffusion:
         idx = torch.arange(T)
         sigma = self.sigmas[idx]
         c_skip, c_out, c_in = self.diffusion.get_scalings(sigma)
-        s_noise = self._noise_sigma(idx, device).float().contiguous()
+        s_noise = self._noise_sigma_all(device).float().contiguous()
         sched = torch.stack([c_in, 1000 * 0.25 * torch.log(sigma + 1e-44), c_skip, c_out, sigma, self.sigma_down[idx]],
                             dim=1).float().contiguous()
         l_sample = torch.empty(T + 1, B, *shape, device=device)
