@@ -264,15 +264,12 @@ def main():
     host_noise = [torch.randn(T + 1, B, *shape, generator=g).pin_memory() for _ in range(n_host_bufs)]
     dev_noise = host_noise[0].to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gathered_s = torch.empty(world, B, *shape, dtype=torch.uint8, device=dev) if world > 1 else None
-    gathered_e = torch.empty(world, B, dtype=torch.float32, device=dev) if world > 1 else None
 
     def gather(d, e):
         # the path's only collective: all-gather of u8 samples and energies (generate_large.py:43-50)
-        u8 = torch.empty(B, *shape, dtype=torch.uint8, device=dev)
-        L.check(lib.dxmi_quantize_u8(L.ptr(d["sample"]), L.ptr(u8), u8.numel(), L.stream_ptr()))
-        dist.all_gather_into_tensor(gathered_s.view(-1), u8.view(-1))
-        dist.all_gather_into_tensor(gathered_e.view(-1), e.view(-1))
+        from diffusion_by_maxentirl_b200.dist import gather_rollout, quantize_u8
+
+        return gather_rollout(quantize_u8(d["sample"]), e)
 
     def rollout_resident():
         d, e = rollout(dev_noise)
