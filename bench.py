@@ -218,8 +218,13 @@ def main():
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout at the first collective; stdout must carry the JSON line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
     if args.block_n_256 is not None:
@@ -289,6 +294,10 @@ def main():
     for _ in range(W):
         rollout_resident()
     sync_all()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     # ---------------------------------------------------------------- value: device-timed, inputs resident in HBM
     clocks = ClockSampler(local_rank)
