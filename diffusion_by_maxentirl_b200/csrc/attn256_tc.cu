@@ -1,0 +1,221 @@
+// Fused single-head self-attention with head dim 256 and sequence length 256 on tcgen05 tensor cores - the DDPM
+// AttnBlock at the 16x16 feature map (models/DxMI/unet_small.py:167-191: w = softmax(q k^T * C^-1/2), h = w v).
+//
+//   grid = (2 query tiles, batch); one CTA owns 128 query rows of one image.
+//   S[128 x 256 keys] = Q K^T      16 x tcgen05.mma (M=128, N=256, K=16) over the 4 channel chunks of 64, fp32 in TMEM
+//   P = exp2(S*scale*log2e - max)  4 softmax warps (thread <-> query row <-> TMEM lane); the whole key row sits in TMEM, so
+//                                  the softmax is exact two-pass (no online rescaling); P goes to smem as bf16 in the
+//                                  SWIZZLE_128B K-major layout (into the buffer Q occupied)
+//   O[128 x 256] = P V             16 x tcgen05.mma over the 4 key chunks; V^T (channel-major, keys contiguous) is TMA-loaded
+//                                  into the buffer K occupied as soon as the S MMAs have retired
+//   out = O / rowsum               staged through smem, written with fully coalesced 16-byte stores
+// Replaces two batched GEMM launches (S with softmax epilogue, P V) whose 128 x 256 output tiles were epilogue bound.
+#include "attn_tc.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+
+namespace dxmi {
+
+static constexpr int A2_THREADS = 192;
+static constexpr int A2_SM_Q = 0;                  // 4 chunks x [128 rows x 64 ch] = 64 KB; later P (4 key chunks), later O staging
+static constexpr int A2_SM_K = 64 * 1024;          // 4 chunks x [256 keys x 64 ch] = 128 KB; later V^T (4 key chunks x [256 ch x 64 keys])
+static constexpr int A2_SM_BAR = 192 * 1024;
+static constexpr int A2_SMEM = A2_SM_BAR + 128;
+static constexpr uint32_t A2_TM_S = 0, A2_TM_O = 256, A2_TM_COLS = 512;
+
+__device__ __forceinline__ float a2_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 1) attn256_kernel(const __grid_constant__ Attn256Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_SM_BAR);
+    uint64_t& qk_full = bars[0];   // Q + K landed
+    uint64_t& s_done = bars[1];    // S MMAs retired (S readable, K buffer free)
+    uint64_t& v_full = bars[2];    // V^T landed
+    uint64_t& p_full = bars[3];    // P written by the 128 softmax threads
+    uint64_t& o_done = bars[4];    // P V MMAs retired
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tile = blockIdx.x, b = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        if (ptx::smem_u32(smem) & 1023u) {
+            printf("dxmi attn256: dynamic smem base not 1024-byte aligned\n");
+            __trap();
+        }
+        ptx::prefetch_tmap(&p.qk_map_q);
+        ptx::prefetch_tmap(&p.qk_map_k);
+        ptx::prefetch_tmap(&p.vt_map);
+        ptx::mbar_init(&qk_full, 1);
+        ptx::mbar_init(&s_done, 1);
+        ptx::mbar_init(&v_full, 1);
+        ptx::mbar_init(&p_full, 128);
+        ptx::mbar_init(&o_done, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 5) ptx::tmem_alloc(&tmem_slot, A2_TM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------------ TMA producer
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&qk_full, 192 * 1024);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                ptx::tma_load_3d(smem + A2_SM_Q + c * 16384, &p.qk_map_q, &qk_full, c * 64, q_tile * 128, b);
+                ptx::tma_load_3d(smem + A2_SM_K + c * 32768, &p.qk_map_k, &qk_full, 256 + c * 64, 0, b);
+            }
+            // V^T reuses the K buffer: wait until the S MMAs have consumed K
+            ptx::mbar_wait(&s_done, 0);
+            ptx::mbar_expect_tx(&v_full, 128 * 1024);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ptx::tma_load_3d(smem + A2_SM_K + c * 32768, &p.vt_map, &v_full, c * 64, 0, b);
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc(1, 128, 256);
+            ptx::mbar_wait(&qk_full, 0);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint64_t dq = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + A2_SM_Q + c * 16384));
+                const uint64_t dk = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + A2_SM_K + c * 32768));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + A2_TM_S, dq + 2 * k, dk + 2 * k, idesc, (c | k) ? 1u : 0u);
+            }
+            ptx::umma_commit(&s_done);
+            ptx::mbar_wait(&p_full, 0);
+            ptx::mbar_wait(&v_full, 0);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint64_t dp = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + A2_SM_Q + c * 16384));
+                const uint64_t dv = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + A2_SM_K + c * 32768));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + A2_TM_O, dp + 2 * k, dv + 2 * k, idesc, (c | k) ? 1u : 0u);
+            }
+            ptx::umma_commit(&o_done);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ softmax + output (thread <-> query row)
+        const int row = warp * 32 + lane;
+        const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        uint8_t* prow = smem + A2_SM_Q + (row >> 3) * 1024 + (row & 7) * 128;
+        const int sw = row & 7;
+        ptx::mbar_wait(&s_done, 0);
+        ptx::tc_fence_after();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(t_row + A2_TM_S + c * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        const float m2 = mx * p.scale_log2;
+        float rs = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(t_row + A2_TM_S + c * 32, v);
+            ptx::tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float p0 = a2_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m2));
+                const float p1 = a2_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m2));
+                rs += p0 + p1;
+                __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
+                pk[i] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            // keys c*32 .. +31 -> 64-key chunk (c >> 1), 16-byte units ((c & 1) * 4 + u), XOR-swizzled by row
+            uint8_t* dst = prow + (c >> 1) * 16384;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&p_full);
+        const float inv = 1.f / rs;
+
+        // ---- O -> bf16 -> smem staging (the P buffer is free once the P V MMAs retired) -> coalesced stores
+        ptx::mbar_wait(&o_done, 0);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(t_row + A2_TM_O + c * 32, v);
+            ptx::tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv);
+                pk[i] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            uint8_t* dst = prow + (c >> 1) * 16384;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + u) ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+        ptx::named_bar_sync(1, 128);
+        // 8 lanes <-> one 128-byte staging row (64 channels); a warp instruction writes 4 rows x 128 contiguous bytes
+        const int u8 = lane & 7, rs4 = lane >> 3;
+        __nv_bfloat16* obase = p.out + (static_cast<long long>(b) * 256 + q_tile * 128) * p.ldo;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int idx = warp * 32 + i;        // (chunk, row group) work item: 4 chunks x 32 groups of 4 rows
+            const int c = idx >> 5, r = (idx & 31) * 4 + rs4;
+            const uint4 val = *reinterpret_cast<const uint4*>(smem + A2_SM_Q + c * 16384 + (r >> 3) * 1024 + (r & 7) * 128 + ((u8 ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(obase + static_cast<long long>(r) * p.ldo + c * 64 + u8 * 8) = val;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, A2_TM_COLS);
+    }
+}
+
+int prepare_attn256(const void* qk, const void* vt, void* out, int ldo, int B, float scale, Attn256Op* op) {
+    Attn256Params& p = op->p;
+    // q | k: [B, 256, 512] bf16. Q box = 64 channels x 128 rows, K box = 64 channels x 256 rows.
+    int r = make_mat_map(&p.qk_map_q, qk, 512, 256, B, 512, 256LL * 512, 128);
+    if (!r) r = make_mat_map(&p.qk_map_k, qk, 512, 256, B, 512, 256LL * 512, 256);
+    // V^T: [B, 256 channels, 256 keys] bf16; box = 64 keys x 256 channel rows
+    if (!r) r = make_mat_map(&p.vt_map, vt, 256, 256, B, 256, 256LL * 256, 256);
+    if (r) return r;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    op->grid = dim3(2, B);
+    op->flops = 4.0 * B * 256.0 * 256.0 * 256.0;
+    return 0;
+}
+
+int run_attn256(const Attn256Op& op, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    attn256_kernel<<<op.grid, A2_THREADS, A2_SMEM, st>>>(op.p);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dxmi

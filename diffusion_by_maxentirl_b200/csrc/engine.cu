@@ -3,6 +3,7 @@
 //   IGEBM V2     models/modules.py:104-163 (+ models/value.py:8-12)
 //   ADM U-Net    models/cm/unet.py:523-790            (engine_adm.cu)
 #include "engine.cuh"
+#include "attn_tc.cuh"
 #include "builder.cuh"
 
 #include <cmath>
@@ -300,56 +301,71 @@ struct DdpmBuilder : Builder {
                 d.rows_per_image = 1;
                 gemm(d);
             }
-            {   // P = softmax(scale * q k^T)   (row softmax fused in the epilogue; whole row lives in TMEM)
-                dxmi_gemm_desc d;
-                memset(&d, 0, sizeof d);
-                d.N = B;
-                d.H = 1;
-                d.W = HW;
-                d.out_H = 1;
-                d.out_W = HW;
-                d.stride = 1;
-                set_src(d, 0, qk, C, 2 * C);
-                add_seg(d, 0, 1);
-                d.a_batched = 1;
-                d.b_ptr = qk + C;
-                d.b_rows = HW;
-                d.b_ld = 2 * C;
-                d.b_batch_stride = (long long)HW * 2 * C;
-                d.b_batched = 1;
-                d.batch = B;
-                d.alpha = scale;
-                d.softmax = 1;
-                d.out = P;
-                d.ldo = HW;
-                d.out_batch_stride = (long long)HW * HW;
-                d.rows_per_image = 1;
-                gemm(d);
-            }
-            {   // O = P . V
-                dxmi_gemm_desc d;
-                memset(&d, 0, sizeof d);
-                d.N = B;
-                d.H = 1;
-                d.W = HW;
-                d.out_H = 1;
-                d.out_W = HW;
-                d.stride = 1;
-                set_src(d, 0, P, HW, HW);
-                add_seg(d, 0, 1);
-                d.a_batched = 1;
-                d.b_ptr = vT;
-                d.b_rows = C;
-                d.b_ld = HW;
-                d.b_batch_stride = (long long)C * HW;
-                d.b_batched = 1;
-                d.batch = B;
-                d.alpha = 1.f;
-                d.out = o;
-                d.ldo = C;
-                d.out_batch_stride = (long long)HW * C;
-                d.rows_per_image = 1;
-                gemm(d);
+            if (HW == 256 && C == 256) {
+                // fused S = q k^T -> softmax -> P v on one CTA per 128 queries (attn256_tc.cu)
+                if (!dry && !err) {
+                    Attn256Op aop;
+                    int r = prepare_attn256(qk, vT, o, C, B, scale, &aop);
+                    if (r) {
+                        err = r;
+                        engine_set_error("prepare_attn256: %s", gemm_last_error());
+                    } else {
+                        plan.gemm_flops += aop.flops;
+                        op([aop](cudaStream_t st) { return run_attn256(aop, st); });
+                    }
+                }
+            } else {
+                {   // P = softmax(scale * q k^T)   (row softmax fused in the epilogue; whole row lives in TMEM)
+                    dxmi_gemm_desc d;
+                    memset(&d, 0, sizeof d);
+                    d.N = B;
+                    d.H = 1;
+                    d.W = HW;
+                    d.out_H = 1;
+                    d.out_W = HW;
+                    d.stride = 1;
+                    set_src(d, 0, qk, C, 2 * C);
+                    add_seg(d, 0, 1);
+                    d.a_batched = 1;
+                    d.b_ptr = qk + C;
+                    d.b_rows = HW;
+                    d.b_ld = 2 * C;
+                    d.b_batch_stride = (long long)HW * 2 * C;
+                    d.b_batched = 1;
+                    d.batch = B;
+                    d.alpha = scale;
+                    d.softmax = 1;
+                    d.out = P;
+                    d.ldo = HW;
+                    d.out_batch_stride = (long long)HW * HW;
+                    d.rows_per_image = 1;
+                    gemm(d);
+                }
+                {   // O = P . V
+                    dxmi_gemm_desc d;
+                    memset(&d, 0, sizeof d);
+                    d.N = B;
+                    d.H = 1;
+                    d.W = HW;
+                    d.out_H = 1;
+                    d.out_W = HW;
+                    d.stride = 1;
+                    set_src(d, 0, P, HW, HW);
+                    add_seg(d, 0, 1);
+                    d.a_batched = 1;
+                    d.b_ptr = vT;
+                    d.b_rows = C;
+                    d.b_ld = HW;
+                    d.b_batch_stride = (long long)C * HW;
+                    d.b_batched = 1;
+                    d.batch = B;
+                    d.alpha = 1.f;
+                    d.out = o;
+                    d.ldo = C;
+                    d.out_batch_stride = (long long)HW * C;
+                    d.rows_per_image = 1;
+                    gemm(d);
+                }
             }
         } else {
             fail("DDPM attention: unsupported sequence length");
