@@ -95,15 +95,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-GF = {"cifar": (12.444, 1.613), "in64": (219.314, 6.454)}  # algorithmic GFLOP / image: U-Net forward, value net
-SHAPE = {"cifar": (3, 32, 32), "in64": (3, 64, 64)}
-DEFAULTS = {"cifar": (4, 256), "in64": (10, 64)}  # (T, images per GPU per step)
+GF = {"cifar": (12.444, 1.613), "in64": (219.314, 6.454), "lsun": (2238.707, 0.0)}  # algorithmic GFLOP / image: U-Net forward, value net
+SHAPE = {"cifar": (3, 32, 32), "in64": (3, 64, 64), "lsun": (3, 256, 256)}
+DEFAULTS = {"cifar": (4, 256), "in64": (10, 64), "lsun": (4, 64)}  # (T, images per GPU per step)
 
 
 def workload_name(wl, T, B):
     if wl == "cifar":
         return (f"CIFAR-10 DDPM U-Net (in-tree stand-in for the absent DDGAN backbone) DxMI T={T} sampler rollout + energy "
                 f"eval, batch {B}/GPU, bf16 tcgen05 (BASELINE.json configs[1])")
+    if wl == "lsun":
+        return (f"LSUN Bedroom 256 EDM U-Net (models/cm, unconditional) DxMI T={T} ancestral sampler rollout (rho=4, stochastic "
+                f"last step), batch {B}/GPU, bf16 tcgen05 (BASELINE.json configs[4]; no energy eval: its value net is not in "
+                f"the reference tree, SURVEY F8)")
     return (f"ImageNet64 EDM U-Net (models/cm, class-conditional) DxMI T={T} ancestral sampler rollout + energy eval, batch "
             f"{B}/GPU, bf16 tcgen05 (BASELINE.json configs[2], per-GPU shard of the 512-image batch)")
 
@@ -193,8 +197,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cifar", choices=["cifar", "in64"],
-                    help="cifar = BASELINE configs[1] (driver default); in64 = configs[2] per-GPU shard (ImageNet-64 EDM T=10)")
+    ap.add_argument("--workload", default="cifar", choices=["cifar", "in64", "lsun"],
+                    help="cifar = BASELINE configs[1] (driver default); in64 = configs[2] per-GPU shard (ImageNet-64 EDM T=10); "
+                         "lsun = configs[4] per-GPU shard (LSUN-256 EDM T=4, sampler only)")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step")
     ap.add_argument("--T", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -209,7 +214,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from common import EDM_IN64_CFG, VALUE_CFG, build_ddpm, build_edm, load_synth_into
+    from common import EDM_IN64_CFG, EDM_LSUN_CFG, VALUE_CFG, build_ddpm, build_edm, load_synth_into
     from diffusion_by_maxentirl_b200 import _lib as L
 
     rank = int(os.environ.get("RANK", "0"))
@@ -243,6 +248,12 @@ def main():
         def rollout(noise):  # noise [T+1, B, C, H, W] on the device
             d = sampler.sample(B, device=dev, noise=noise)
             return d, value(d["sample"], T)
+    elif wl == "lsun":
+        net, sampler, sd = build_edm(EDM_LSUN_CFG, T, device=dev, stochastic_last=True, rho=4.0)
+        value, labels = None, None
+
+        def rollout(noise):
+            return sampler.sample(B, device=dev, x0=noise[0] * 80.0, noise=noise[1:]), None
     else:
         from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
         from diffusion_by_maxentirl_b200.models.value import TimeIndependentValue
@@ -332,7 +343,8 @@ def main():
         if world > 1:
             gather(d, e)
         d2h_samples.copy_(d["sample"], non_blocking=True)
-        d2h_energy.copy_(e, non_blocking=True)
+        if e is not None:
+            d2h_energy.copy_(e, non_blocking=True)
         torch.cuda.synchronize()
     sync_all()
     e2e_s = time.perf_counter() - t0
@@ -366,7 +378,7 @@ def main():
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and wl != "lsun":
         run = cpu_oracle_rollout_fn(wl, T)
         Bs = 8 if wl == "cifar" else 1
         if wl == "cifar":
