@@ -253,8 +253,11 @@ void conv3x3_last(const bf16* h, const float* w, const float* b, float* out, int
 // ============================================================================================ GroupNorm
 
 int gn_num_slabs(int N, int HW) {
+    // a function of the image size only: the partial-sum order (hence every bit of the result) must not depend on the
+    // batch size - bf16 rounding downstream amplifies even 1e-7 differences in the statistics to ~1e-3 at the output
+    (void)N;
     int slabs = 1;
-    while (N * slabs < 592 && HW / (slabs * 2) >= 16) slabs *= 2;
+    while (slabs < 16 && HW / (slabs * 2) >= 64) slabs *= 2;
     return slabs;
 }
 
