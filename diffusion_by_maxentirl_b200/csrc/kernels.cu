@@ -8,7 +8,15 @@ namespace dxmi {
 
 namespace {
 
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// silu(v) = v * sigmoid(v) = h + h * tanh(h) with h = v / 2: ONE special-function op (tanh.approx, rel. error ~2^-11, well
+// below the bf16 output rounding) instead of exp + reciprocal - the GroupNorm apply kernels were SFU bound (ncu: XU pipe
+// 62 % vs DRAM 43 %).
+__device__ __forceinline__ float silu_f(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 __device__ __forceinline__ float act_f(float v, int act) {
     if (act == 1) return v > 0.f ? v : 0.2f * v;
     if (act == 2) return silu_f(v);
