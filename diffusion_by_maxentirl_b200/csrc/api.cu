@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "attn_tc.cuh"
 #include "engine.cuh"
@@ -198,6 +199,28 @@ size_t dxmi_workspace_bytes(dxmi_net_t net, int B) {
 
 static int run_plan(Net& n, Plan* p, cudaStream_t st) {
     static const bool debug_sync = getenv("DXMI_DEBUG_SYNC") != nullptr;
+    const char* time_ops = getenv("DXMI_TIME_OPS");  // profiling: CSV path, one CUDA-event-timed row per plan op
+    if (time_ops) {
+        std::vector<cudaEvent_t> ev(p->ops.size() + 1);
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0], st);
+        for (size_t i = 0; i < p->ops.size(); ++i) {
+            int r = p->ops[i](st);
+            if (r) return r;
+            cudaEventRecord(ev[i + 1], st);
+        }
+        cudaEventSynchronize(ev.back());
+        FILE* f = fopen(time_ops, "a");
+        for (size_t i = 0; i < p->ops.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            if (f) fprintf(f, "%s,%.2f\n", i < p->op_names.size() ? p->op_names[i].c_str() : "?", ms * 1e3);
+        }
+        if (f) fclose(f);
+        for (auto& e : ev) cudaEventDestroy(e);
+        count_launches(p->launches_per_run);
+        return 0;
+    }
     for (size_t i = 0; i < p->ops.size(); ++i) {
         auto& f = p->ops[i];
         int r = f(st);

@@ -352,7 +352,7 @@ struct Builder {
     // GroupNorm(32) over concat(x1, x2) -> out (scratch slot), optional SiLU / FiLM
     void group_norm(Act x1, Act x2, const std::string& pfx, float eps, int silu, const float* film, int film_ld,
                     bf16* out) {
-        cur_label = pfx;
+        cur_label = "GN " + pfx;
         const int HW = x1.H * x1.W;
         const int slabs = gn_num_slabs(B, HW);
         float* ws = (float*)scratch(5, (size_t)B * slabs * 64 * sizeof(float));

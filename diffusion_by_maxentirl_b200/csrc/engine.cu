@@ -311,7 +311,12 @@ struct DdpmBuilder : Builder {
                         engine_set_error("prepare_attn256: %s", gemm_last_error());
                     } else {
                         plan.gemm_flops += aop.flops;
-                        op([aop](cudaStream_t st) { return run_attn256(aop, st); });
+                        {
+                            const std::string keep = cur_label;
+                            cur_label = "ATTN " + keep;
+                            op([aop](cudaStream_t st) { return run_attn256(aop, st); });
+                            cur_label = keep;
+                        }
                     }
                 }
             } else {

@@ -284,7 +284,12 @@ struct AdmBuilder : Builder {
                     engine_set_error("prepare_attn: %s", attn_last_error());
                 } else {
                     plan.gemm_flops += aop.flops;
-                    op([aop](cudaStream_t st) { return run_attn(aop, st); });
+                    {
+                        const std::string keep = cur_label;
+                        cur_label = "ATTN " + keep;
+                        op([aop](cudaStream_t st) { return run_attn(aop, st); });
+                        cur_label = keep;
+                    }
                 }
             }
         } else if (HW <= 64) {
