@@ -26,6 +26,10 @@ int dxmi_set_option(const char* name, int value) {
         set_block_n_256(value);
         return 0;
     }
+    if (!strcmp(name, "halo")) {
+        set_halo(value);
+        return 0;
+    }
     if (!strcmp(name, "gemm_version")) {
         set_gemm_version(value);
         return 0;
@@ -396,6 +400,8 @@ int dxmi_op_pack_conv_weight(const void* w, int dtype, int Cout, int Cin, int kh
     count_launches(1);
     return (int)cudaGetLastError();
 }
+
+int dxmi_op_halo_tiles_per_image(int H, int W) { return halo_tiles_per_image(H, W); }
 
 int dxmi_op_gn_ws_floats(int N, int HW, int groups) { return N * gn_num_slabs(N, HW) * 2 * groups; }
 

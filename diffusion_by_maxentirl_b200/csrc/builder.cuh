@@ -40,19 +40,44 @@ struct Builder {
     // cannot be used for this geometry: a 32-row segment must not straddle two images)
     static int stats_seg(int HW) { return HW % 128 == 0 ? 128 : (HW % 64 == 0 ? 64 : (HW % 32 == 0 ? 32 : 0)); }
     static size_t stats_bytes(int rows, int HW, int C) { return (size_t)rows / stats_seg(HW) * C * 2 * sizeof(float); }
-    float* stats_alloc(int C, int H, int W) {
-        if (!stats_seg(H * W)) return nullptr;
-        return (float*)alloc(stats_bytes(B * H * W, H * W, C));
+    // Layout of the GroupNorm partials a GEMM writes for its [B*H*W, C] output: per halo tile for 3x3 stride-1 convs on
+    // 32- / 64-wide maps (gemm_op.cu: halo_tiles_per_image), else per 32/64/128-row segment.
+    struct StatSpec {
+        int P = 0;
+        bool halo = false;
+        size_t bytes = 0;
+    };
+    StatSpec stat_spec(int C, int H, int W, bool conv3x3_s1) const {
+        StatSpec s;
+        const int tpi = conv3x3_s1 ? halo_tiles_per_image(H, W) : 0;
+        if (tpi) {
+            s.P = tpi;
+            s.halo = true;
+        } else if (stats_seg(H * W)) {
+            s.P = H * W / stats_seg(H * W);
+        }
+        s.bytes = (size_t)B * s.P * C * 2 * sizeof(float);
+        return s;
     }
-    Act new_act(int C, int H, int W, bool want_stats = true) {
+    // `conv3x3_s1`: the tensor will be produced by a 3x3 stride-1 convolution GEMM (its partials may be per halo tile)
+    Act new_act(int C, int H, int W, bool want_stats = true, bool conv3x3_s1 = false) {
         Act a;
         a.p = act_alloc(C, H, W);
         a.C = C;
         a.H = H;
         a.W = W;
-        a.has_stats = want_stats && stats_seg(H * W) != 0;
-        a.stats = a.has_stats ? stats_alloc(C, H, W) : nullptr;
+        const StatSpec s = stat_spec(C, H, W, conv3x3_s1);
+        a.has_stats = want_stats && s.P > 0;
+        if (a.has_stats) {
+            a.stats = (float*)alloc(s.bytes);
+            a.stats_P = s.P;
+            a.stats_halo = s.halo;
+        }
         return a;
+    }
+    static void want_stats(dxmi_gemm_desc& d, const Act& out) {
+        d.gn_stats = out.stats;
+        d.gn_halo_P = out.stats_halo ? out.stats_P : 0;
     }
 
     void fail(const char* what) {
@@ -364,12 +389,12 @@ struct Builder {
         if ((C1 + C2) % 8 || (C1 % 8) || (C1 + C2) > 2048) fail("group_norm: unsupported channel count");
         const float* st1 = x1.stats;
         const float* st2 = x2.stats;
-        if (x1.has_stats && (C2 == 0 || x2.has_stats) && stats_seg(HW)) {
+        if (x1.has_stats && (C2 == 0 || x2.has_stats)) {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
-            const int P = HW / stats_seg(HW);
+            const int P1 = x1.stats_P, P2 = x2.stats_P;
             float* ab = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
             op([=](cudaStream_t st) {
-                gn_finalize_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P, st2, P, ab,
+                gn_finalize_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P1, st2, P2, ab,
                                   out, st);
                 return (int)cudaGetLastError();
             }, 2);

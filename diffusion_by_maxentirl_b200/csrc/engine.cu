@@ -169,7 +169,8 @@ struct DdpmBuilder : Builder {
         bf16* g1 = (bf16*)scratch(0, (size_t)B * HW * Cin * 2);
         group_norm(xa, xb, p + ".norm1", 1e-6f, 1, nullptr, 0, g1);
         bf16* h1 = (bf16*)scratch(1, (size_t)B * HW * Cout * 2);
-        float* h1_stats = stats_seg(HW) ? (float*)scratch(6, stats_bytes(B * HW, HW, Cout)) : nullptr;
+        const StatSpec h1s = stat_spec(Cout, H, W, true);
+        float* h1_stats = h1s.P ? (float*)scratch(6, h1s.bytes) : nullptr;
         {
             long long K;
             int rows;
@@ -186,13 +187,14 @@ struct DdpmBuilder : Builder {
             d.out = h1;
             d.ldo = Cout;
             d.gn_stats = h1_stats;
+            d.gn_halo_P = h1s.halo ? h1s.P : 0;
             gemm(d);
         }
         tproj_off += Cout;
         bf16* g2 = (bf16*)scratch(0, (size_t)B * HW * Cout * 2);
-        Act h1a{h1, Cout, H, W, h1_stats, stats_seg(HW) != 0};
+        Act h1a{h1, Cout, H, W, h1_stats, h1s.P, h1s.halo, h1s.P > 0};
         group_norm(h1a, Act{}, p + ".norm2", 1e-6f, 1, nullptr, 0, g2);
-        Act out = new_act(Cout, H, W);
+        Act out = new_act(Cout, H, W, true, /*conv3x3_s1=*/true);
         {
             dxmi_gemm_desc d = conv_desc(H, W);
             set_src(d, 0, g2, Cout, Cout);
@@ -222,7 +224,7 @@ struct DdpmBuilder : Builder {
             d.b_ld = K;
             d.out = out.p;
             d.ldo = Cout;
-            d.gn_stats = out.stats;
+            want_stats(d, out);
             gemm(d);
         }
         return out;
@@ -387,7 +389,7 @@ struct DdpmBuilder : Builder {
             d.ldr = C;
             d.out = out.p;
             d.ldo = C;
-            d.gn_stats = out.stats;
+            want_stats(d, out);
             gemm(d);
         }
         return out;
@@ -409,7 +411,7 @@ struct DdpmBuilder : Builder {
         d.bias = f32(p + ".conv.bias");
         d.out = out.p;
         d.ldo = C;
-        d.gn_stats = out.stats;
+        want_stats(d, out);
         gemm(d);
         return out;
     }
@@ -423,7 +425,7 @@ struct DdpmBuilder : Builder {
             upsample2x(xp, up, Bn, H, W, C, st);
             return (int)cudaGetLastError();
         });
-        Act out = new_act(C, H2, W2);
+        Act out = new_act(C, H2, W2, true, /*conv3x3_s1=*/true);
         dxmi_gemm_desc d = conv_desc(H2, W2);
         set_src(d, 0, up, C, C);
         add_seg(d, 0, 9);
@@ -433,7 +435,7 @@ struct DdpmBuilder : Builder {
         d.bias = f32(p + ".conv.bias");
         d.out = out.p;
         d.ldo = C;
-        d.gn_stats = out.stats;
+        want_stats(d, out);
         gemm(d);
         return out;
     }

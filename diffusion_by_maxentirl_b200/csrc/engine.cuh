@@ -27,6 +27,8 @@ struct Act {  // NHWC bf16 activation
     bf16* p = nullptr;
     int C = 0, H = 0, W = 0;
     float* stats = nullptr;  // GroupNorm partials written by the producing GEMM: [B*H*W/seg][C][2] (null in the dry pass)
+    int stats_P = 0;         // partials per image
+    bool stats_halo = false; // one partial per halo tile (3x3 stride-1 conv on a 32/64-wide map) instead of per row segment
     bool has_stats = false;  // pass-independent: the sizing (dry) pass must take the same branches as the real one
 };
 

@@ -163,7 +163,8 @@ struct AdmBuilder : Builder {
             xs = Act{xp, Cin, Ho, Wo};
         }
         bf16* h1 = (bf16*)scratch(1, (size_t)B * Ho * Wo * Cout * 2);
-        float* h1_stats = stats_seg(Ho * Wo) ? (float*)scratch(6, stats_bytes(B * Ho * Wo, Ho * Wo, Cout)) : nullptr;
+        const StatSpec h1s = stat_spec(Cout, Ho, Wo, true);
+        float* h1_stats = h1s.P ? (float*)scratch(6, h1s.bytes) : nullptr;
         {
             dxmi_gemm_desc d = conv_desc(Ho, Wo);
             set_src(d, 0, conv_in, Cin, Cin);
@@ -179,13 +180,14 @@ struct AdmBuilder : Builder {
             d.out = h1;
             d.ldo = Cout;
             d.gn_stats = h1_stats;
+            d.gn_halo_P = h1s.halo ? h1s.P : 0;
             gemm(d);
         }
         bf16* g2 = (bf16*)scratch(0, (size_t)B * Ho * Wo * Cout * 2);
-        group_norm(Act{h1, Cout, Ho, Wo, h1_stats, stats_seg(Ho * Wo) != 0}, Act{}, p + ".out_layers.0", EPS, 1, film_mode && film ? film + film_off : nullptr,
+        group_norm(Act{h1, Cout, Ho, Wo, h1_stats, h1s.P, h1s.halo, h1s.P > 0}, Act{}, p + ".out_layers.0", EPS, 1, film_mode && film ? film + film_off : nullptr,
                    film_ld, g2);
         film_off += emb_cols;
-        Act out = new_act(Cout, Ho, Wo);
+        Act out = new_act(Cout, Ho, Wo, true, /*conv3x3_s1=*/true);
         {
             dxmi_gemm_desc d = conv_desc(Ho, Wo);
             set_src(d, 0, g2, Cout, Cout);
@@ -216,7 +218,7 @@ struct AdmBuilder : Builder {
             d.b_ld = K;
             d.out = out.p;
             d.ldo = Cout;
-            d.gn_stats = out.stats;
+            want_stats(d, out);
             gemm(d);
         }
         return out;
@@ -324,7 +326,7 @@ struct AdmBuilder : Builder {
             d.ldr = C;
             d.out = out.p;
             d.ldo = C;
-            d.gn_stats = out.stats;
+            want_stats(d, out);
             gemm(d);
         }
         return out;

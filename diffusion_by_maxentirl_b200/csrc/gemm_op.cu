@@ -10,6 +10,18 @@ namespace dxmi {
 static int g_opt_block_n_256 = 1;
 static int g_opt_dbg_mode = 0;
 static int g_opt_gemm_v = 2;
+// Halo-tile A reuse is OFF by default: measured on B200 (profiles/r01_bench_conv_halo.txt) it is correct but 1.2-1.4x
+// slower than nine shifted TMA boxes - the kernel is bound by the per-SM TMA ingest rate and the tile pipeline, not by L2
+// bandwidth, and the 9-vs-8 tiles per 32x32 image plus the pad columns cost more than the saved bytes.
+static int g_opt_halo = 0;
+void set_halo(int v) { g_opt_halo = v; }
+
+// Tiles per image of the halo-mode 3x3 convolution on an H x W map, or 0 when that geometry does not use halo tiles.
+int halo_tiles_per_image(int H, int W) {
+    if (!g_opt_halo || g_opt_gemm_v != 2) return 0;
+    if ((W != 32 && W != 64) || H * W < 128) return 0;
+    return (H * (W + 2) + 127) / 128;
+}
 void set_gemm_version(int v) { g_opt_gemm_v = v; }
 static long long* g_dbg_times = nullptr;
 void set_dbg_times(void* p) { g_dbg_times = (long long*)p; }
@@ -123,8 +135,46 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     p.n_tiles = n_tiles;
     p.batch_count = op->batch;
     p.stats = nullptr;
+    p.halo = 0;
     op->use_v2 = 0;
     if (g_opt_gemm_v == 2 && conv_gemm_v2_supported(p, block_n)) {
+        // ---- halo mode: 3x3 stride-1 convolutions (plus centre-tap 1x1 segments) on 32- / 64-wide maps
+        bool halo = halo_tiles_per_image(d.H, d.W) > 0 && p.stride == 1 && !d.a_batched && op->batch == 1 && d.out_H == d.H &&
+                    d.out_W == d.W && !d.softmax;
+        bool any9 = false;
+        for (int s = 0; s < d.nseg; ++s) any9 |= d.seg_taps[s] == 9;
+        halo = halo && any9;
+        if (halo) {
+            const int Wp = d.W + 2;
+            const int rows = (2 * Wp + 126) / Wp + 2;
+            const int a_stage = (rows * Wp * 128 + 1023) & ~1023;
+            int sb = (conv_gemm_v2_ring_bytes(block_n) - 2 * a_stage) / (block_n * 128);
+            if (sb > 12) sb = 12;
+            if (sb >= 3) {
+                p.halo = 1;
+                p.halo_W = d.W;
+                p.halo_H = d.H;
+                p.halo_rows = rows;
+                p.halo_tpi = halo_tiles_per_image(d.H, d.W);
+                p.halo_a_stage = a_stage;
+                p.halo_sb = sb;
+                p.m_tiles = op->m_tiles = d.N * p.halo_tpi;
+                for (int i = 0; i < 3; ++i) {
+                    if (!used[i]) continue;
+                    const long long ld = d.a_ld[i];
+                    r = make_act_map(&p.a_map[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.N, ld, ld * d.W, ld * d.W * d.H, Wp, rows, 1, 1);
+                    if (r) return r;
+                }
+            }
+        }
+        if (d.gn_stats && d.gn_halo_P > 0 && !(p.halo && p.halo_tpi == d.gn_halo_P)) {
+            snprintf(g_op_err, sizeof g_op_err, "GroupNorm partials were sized for halo tiles but this GEMM cannot run in halo mode");
+            return -14;
+        }
+        if (d.gn_stats && d.gn_halo_P == 0 && p.halo) {
+            snprintf(g_op_err, sizeof g_op_err, "GroupNorm partials were sized for row segments but this GEMM runs in halo mode");
+            return -15;
+        }
         p.stats = p.softmax ? nullptr : d.gn_stats;
         p.stats_seg = d.gn_seg;
         if (p.stats && (p.stats_seg != 32 && p.stats_seg != 64 && p.stats_seg != 128)) {

@@ -16,6 +16,8 @@ int run_gemm(const GemmOp& op, cudaStream_t st);
 void set_block_n_256(int v);
 void set_dbg_mode(int v);
 void set_gemm_version(int v);
+void set_halo(int v);
+int halo_tiles_per_image(int H, int W);
 void set_dbg_times(void* p);
 void set_time_gemms(int v);
 void set_timing_dump(const char* path);

@@ -60,6 +60,15 @@ struct ConvGemmParams {
     CUtensorMap out_map;       // (cols, rows, batch) over `out`, box (128 bytes of columns, 128 rows, 1), SWIZZLE_128B
     CUtensorMap res_map;       // same geometry over `residual` (bf16)
     int m_tiles, n_tiles, batch_count;
+    // halo mode (3x3 stride-1 convs on 32- / 64-wide maps): one TMA load of a [(rows+2) x (W+2) pixels x 64 channels] halo
+    // tile per channel chunk serves all 9 taps through shifted smem descriptors; output rows are positions of the
+    // zero-padded (W+2)-wide grid of one image (m_tiles = images * halo_tpi)
+    int halo;                  // 0 = off
+    int halo_W, halo_H;        // image width / height
+    int halo_rows;             // rows of the TMA box (tile row span + 2)
+    int halo_tpi;              // tiles per image = ceil(H * (W+2) / 128)
+    int halo_a_stage;          // bytes of one A (halo) stage, multiple of 1024
+    int halo_sb;               // B ring depth in halo mode
     float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/stats_seg][N_total][2] (sum, sumsq) or null
     int stats_seg;             // rows per partial: 32, 64 or 128 (a segment never straddles two images)
     long long* dbg_times;      // profiling only: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA, or null
@@ -79,6 +88,7 @@ int make_mat_map(CUtensorMap* out, const void* base, int K, int rows, int batch,
 // Persistent variant (gemm_tc2.cu): TMEM double buffering, TMA-store epilogue, fused GroupNorm partial statistics.
 int launch_conv_gemm_v2(const ConvGemmParams& p, int block_n, cudaStream_t stream);
 bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n);
+int conv_gemm_v2_ring_bytes(int block_n);
 // Host helper: (cols, rows, batch) map with a 128-byte x 128-row box for the epilogue (elem_bytes 2 = bf16, 4 = fp32).
 int make_out_map(CUtensorMap* out, const void* base, int elem_bytes, int cols, int rows, int batch, long long row_stride,
                  long long batch_stride);

@@ -39,8 +39,8 @@ struct Cfg2 {
     static constexpr int SM_OUT = RING_BYTES;                       // 2 output staging slots
     static constexpr int SM_STAT = SM_OUT + 2 * EPI_SLOT_BYTES;     // [8 warps][32 columns] float2 GroupNorm partials + softmax row stats
     static constexpr int SM_BAR = SM_STAT + 2048;                   // mbarriers + TMEM slot
-    static_assert(SM_BAR + 256 <= 227 * 1024, "shared memory budget");
-    static constexpr int SMEM_BYTES = SM_BAR + 256;
+    static_assert(SM_BAR + 512 <= 227 * 1024, "shared memory budget");
+    static constexpr int SMEM_BYTES = SM_BAR + 512;
 };
 
 __device__ __forceinline__ long long gtimer2() {
@@ -88,7 +88,8 @@ enum EpiMode { EPI_BIAS = 0, EPI_ROWVEC = 1, EPI_RESIDUAL = 2, EPI_GENERIC = 3 }
 //  size and dependent chains matter more than bytes.)
 template <int MODE, bool STATS>
 __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& cx, uint32_t tacc_col, uint64_t* tmem_empty_bar,
-                                         int row0, int col0, int nch, int batch, uint32_t& out_cnt) {
+                                         int m_tile, int col0, int nch, int batch, uint32_t& out_cnt) {
+    const int row0 = m_tile * TILE_M;
     constexpr int CH = 32;
     const int n_total = p.N_total;
     const float alpha = p.alpha;
@@ -109,11 +110,26 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     float bm[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const long long r = static_cast<long long>(row0) + cx.rt0 + 4 * i;
-        rok[i] = r < p.M_total && p.dbg_mode != 2;
+        long long r;
+        long long img;
+        bool ok;
+        if (p.halo) {
+            // halo tile: row i <-> position p0 + i of the zero-padded (W+2)-wide grid of image m_tile / tpi
+            const int Wp = p.halo_W + 2;
+            img = m_tile / p.halo_tpi;
+            const int pos = (m_tile - static_cast<int>(img) * p.halo_tpi) * TILE_M + cx.rt0 + 4 * i;
+            const int hh = pos / Wp, ww = pos - hh * Wp;
+            ok = ww < p.halo_W && hh < p.halo_H;
+            r = (img * p.halo_H + hh) * p.halo_W + ww;
+        } else {
+            r = static_cast<long long>(row0) + cx.rt0 + 4 * i;
+            ok = r < p.M_total;
+            img = use_rv ? r / p.rows_per_image : 0;
+        }
+        rok[i] = ok && p.dbg_mode != 2;
         ooff[i] = batch * p.out_batch_stride + r * p.ldo;
         roff[i] = use_res ? batch * p.res_batch_stride + r * p.ldr : 0;
-        rvp[i] = (use_rv && rok[i]) ? p.rowvec + (r / p.rows_per_image) * p.ldrv : nullptr;
+        rvp[i] = (use_rv && rok[i]) ? p.rowvec + img * p.ldrv : nullptr;
         bm[i] = (g_bm && rok[i]) ? __ldg(p.bias + r) : 0.f;
     }
     float4 pf_bias = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -167,7 +183,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         ptx::named_bar_sync(2, 256);
     }
 
-    const int stat_seg = STATS ? p.stats_seg : 128;
+    const int stat_seg = (STATS && !p.halo) ? p.stats_seg : 128;  // halo tiles: one partial per tile (tiles never span images)
     const int stat_nseg = 128 / stat_seg, stat_bps = stat_seg >> 5;
     const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : 5);
 
@@ -288,8 +304,11 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                     }
                 }
                 const int srow = row0 + sg * stat_seg;
-                if (col + j < n_total && srow < p.M_total)
+                if (p.halo) {
+                    if (col + j < n_total) *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(m_tile) * n_total + col + j) * 2) = a;
+                } else if (col + j < n_total && srow < p.M_total) {
                     *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(srow >> stat_shift) * n_total + col + j) * 2) = a;
+                }
             }
         }
         ++out_cnt;
@@ -303,12 +322,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SM_BAR);
-    uint64_t* full_bar = bars;                    // [STAGES]
-    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-    uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
-    uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-    uint64_t* res_full = bars + 2 * STAGES + 4;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    constexpr int MAXB = 12;                      // ring depth upper bound (halo mode re-carves the ring at run time)
+    uint64_t* full_bar = bars;                    // [MAXB]  (A+B stages; B stages in halo mode)
+    uint64_t* empty_bar = bars + MAXB;            // [MAXB]
+    uint64_t* tmem_full = bars + 2 * MAXB;        // [2]
+    uint64_t* tmem_empty = bars + 2 * MAXB + 2;   // [2]
+    uint64_t* afull_bar = bars + 2 * MAXB + 4;    // [2]  halo A stages
+    uint64_t* aempty_bar = bars + 2 * MAXB + 6;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXB + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -329,14 +350,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
         if (p.nseg > 1) ptx::prefetch_tmap(&p.a_map[1]);
         if (p.nseg > 2) ptx::prefetch_tmap(&p.a_map[2]);
         ptx::prefetch_tmap(&p.b_map);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAXB; ++s) {
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);
             ptx::mbar_init(&tmem_empty[s], 256);
-            ptx::mbar_init(&res_full[s], 1);
+            ptx::mbar_init(&afull_bar[s], 1);
+            ptx::mbar_init(&aempty_bar[s], 1);
         }
         ptx::fence_mbar_init();
     }
@@ -349,7 +371,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (ptx::elect_one()) {
+        if (p.halo) {
+            if (ptx::elect_one()) {
+                const int Wp = p.halo_W + 2;
+                const uint32_t a_bytes = static_cast<uint32_t>(p.halo_rows) * Wp * 128u;
+                const int SB = p.halo_sb;
+                uint8_t* sB0 = smem + 2 * p.halo_a_stage;
+                uint32_t ia = 0, ib = 0;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    const int n_tile = t % p.n_tiles;
+                    const int m_tile = t / p.n_tiles;
+                    const int img = m_tile / p.halo_tpi;
+                    const int p0 = (m_tile - img * p.halo_tpi) * TILE_M;
+                    const int h_first = p0 / Wp;
+                    int kbase = 0;
+                    for (int s = 0; s < p.nseg; ++s) {
+                        const GemmSeg sg = p.seg[s];
+                        const CUtensorMap* amap = &p.a_map[sg.map];
+                        const int cseg = sg.nchunks * TILE_K;
+                        for (int ch = 0; ch < sg.nchunks; ++ch, ++ia) {
+                            const uint32_t sa = ia & 1;
+                            ptx::mbar_wait(&aempty_bar[sa], ((ia >> 1) & 1) ^ 1);
+                            ptx::mbar_expect_tx(&afull_bar[sa], a_bytes);
+                            ptx::tma_load_4d(smem + sa * p.halo_a_stage, amap, &afull_bar[sa], ch * TILE_K, -1, h_first - 1, img);
+                            for (int tap = 0; tap < sg.ntaps; ++tap, ++ib) {
+                                const uint32_t sb = ib % SB;
+                                ptx::mbar_wait(&empty_bar[sb], ((ib / SB) & 1) ^ 1);
+                                ptx::mbar_expect_tx(&full_bar[sb], Cfg::B_STAGE_BYTES);
+                                ptx::tma_load_3d(sB0 + sb * Cfg::B_STAGE_BYTES, &p.b_map, &full_bar[sb], kbase + tap * cseg + ch * TILE_K,
+                                                 n_tile * BLOCK_N, 0);
+                            }
+                        }
+                        kbase += sg.ntaps * cseg;
+                    }
+                }
+            }
+        } else if (ptx::elect_one()) {
             const int tiles_per_nblk = p.tiles_w * p.tiles_h;
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -390,7 +447,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (ptx::elect_one()) {
+        if (p.halo) {
+            if (ptx::elect_one()) {
+                constexpr uint32_t idesc = ptx::make_idesc(/*bf16*/ 1, TILE_M, BLOCK_N);
+                const int Wp = p.halo_W + 2;
+                const int SB = p.halo_sb;
+                const uint32_t sB0 = ptx::smem_u32(smem + 2 * p.halo_a_stage);
+                uint32_t ia = 0, ib = 0, ti = 0;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+                    const int m_tile = t / p.n_tiles;
+                    const int p0 = (m_tile % p.halo_tpi) * TILE_M;
+                    const int w0 = p0 % Wp;
+                    const uint32_t acc = ti & 1;
+                    ptx::mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t tacc = tmem_base + acc * Cfg::ACC_COLS;
+                    uint32_t first = 1;
+                    for (int s = 0; s < p.nseg; ++s) {
+                        const GemmSeg sg = p.seg[s];
+                        for (int ch = 0; ch < sg.nchunks; ++ch, ++ia) {
+                            const uint32_t sa = ia & 1;
+                            ptx::mbar_wait(&afull_bar[sa], (ia >> 1) & 1);
+                            ptx::tc_fence_after();
+                            const uint32_t a0 = ptx::smem_u32(smem + sa * p.halo_a_stage) + w0 * 128;
+                            for (int tap = 0; tap < sg.ntaps; ++tap, ++ib) {
+                                const int r = (sg.ntaps == 9) ? tap / 3 : 1;
+                                const int q = (sg.ntaps == 9) ? tap - 3 * r : 1;
+                                const uint32_t sb = ib % SB;
+                                ptx::mbar_wait(&full_bar[sb], (ib / SB) & 1);
+                                ptx::tc_fence_after();
+                                // shifted window of the halo tile: the swizzle is a function of the absolute smem address,
+                                // so a start offset of any multiple of 128 bytes addresses the rows TMA wrote
+                                // (verified on hardware, tools/exp_halo.py)
+                                const uint64_t da = ptx::make_kmajor_sw128_desc(a0 + (r * Wp + q) * 128);
+                                const uint64_t db = ptx::make_kmajor_sw128_desc(sB0 + sb * Cfg::B_STAGE_BYTES);
+                                if (p.dbg_mode != 1) {
+#pragma unroll
+                                    for (int j = 0; j < TILE_K / 16; ++j) ptx::umma_f16(tacc, da + 2 * j, db + 2 * j, idesc, (first && j == 0) ? 0u : 1u);
+                                }
+                                first = 0;
+                                ptx::umma_commit(&empty_bar[sb]);
+                            }
+                            ptx::umma_commit(&aempty_bar[sa]);
+                        }
+                    }
+                    ptx::umma_commit(&tmem_full[acc]);
+                }
+            }
+        } else if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc(/*bf16*/ 1, TILE_M, BLOCK_N);
             uint32_t it = 0, ti = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
@@ -451,7 +555,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             const int mt = t / p.n_tiles;
             const int m_tile = mt % p.m_tiles;
             const int batch = mt / p.m_tiles;
-            const int row0 = m_tile * TILE_M;
             const int col0 = n_tile * BLOCK_N;
             int ncols = p.N_total - col0;
             if (ncols > BLOCK_N) ncols = BLOCK_N;
@@ -465,17 +568,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             uint64_t* te = &tmem_empty[acc];
             if (has_stats) {
                 switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
-                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
                 }
             } else {
                 switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
-                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, row0, col0, nch, batch, out_cnt); break;
+                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
                 }
             }
             if (ti == 0 && leader) { DBG2(6); }
@@ -498,6 +601,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
 // ------------------------------------------------------------------------------------------------ host side
 
 void gemm_set_error(const char* msg);
+
+int conv_gemm_v2_ring_bytes(int block_n) {
+    switch (block_n) {
+        case 32: return Cfg2<32>::RING_BYTES;
+        case 64: return Cfg2<64>::RING_BYTES;
+        case 128: return Cfg2<128>::RING_BYTES;
+        case 192: return Cfg2<192>::RING_BYTES;
+        case 256: return Cfg2<256>::RING_BYTES;
+        default: return 0;
+    }
+}
 
 bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n) {
     if (block_n != 32 && block_n != 64 && block_n != 128 && block_n != 192 && block_n != 256) return false;

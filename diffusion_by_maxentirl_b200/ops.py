@@ -65,6 +65,7 @@ def conv_gemm(
     res_batch_stride=0,
     gn_stats=None,
     gn_seg=32,
+    gn_halo_P=0,
 ):
     """srcs: list of (tensor, C_used, ld) NHWC bf16 sources; segs: list of (src_index, taps)."""
     d = L.GemmDesc()
@@ -120,6 +121,7 @@ def conv_gemm(
         assert gn_stats.dtype == torch.float32
         d.gn_stats = gn_stats.data_ptr()
         d.gn_seg = gn_seg
+        d.gn_halo_P = gn_halo_P
     L.check(L.lib().dxmi_op_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
 

@@ -145,6 +145,8 @@ typedef struct {
     int out_nchw;            /* fp32 output in [image][b_rows][rows_per_image] order (network output layout) */
     float* gn_stats;         /* optional: GroupNorm partials of the bf16 output, [rows/gn_seg][b_rows][2] (sum, sumsq) */
     int gn_seg;              /* rows per partial: 32, 64 or 128; must divide the rows of one image */
+    int gn_halo_P;           /* > 0: the partials buffer is [N][gn_halo_P][b_rows][2], one partial per halo tile (3x3 convs on
+                                32/64-wide maps, see dxmi_op_halo_tiles_per_image); 0: row-segment partials */
 } dxmi_gemm_desc;
 
 int dxmi_op_conv_gemm(const dxmi_gemm_desc* d, dxmi_stream_t stream);
@@ -154,6 +156,8 @@ int dxmi_op_group_norm(const void* x1, int C1, int ld1, const void* x2, int C2, 
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
                        float* partial_ws, void* out, dxmi_stream_t stream);
 int dxmi_op_gn_ws_floats(int N, int HW, int groups);
+/* tiles per image of the halo-mode 3x3 convolution on an H x W map (0: that geometry uses plain 128-pixel tiles) */
+int dxmi_op_halo_tiles_per_image(int H, int W);
 /* Fused d=64 multi-head attention (QKVAttentionLegacy.forward, models/cm/unet.py:413-441): qk bf16 [B, seq, ld_qk] with
  * head h's queries at column q_col0 + 64h and keys at k_col0 + 64h; vt bf16 [B, heads*64, seq] (V transposed);
  * out bf16 [B, seq, ldo], head h at column 64h; scale multiplies the logits (d^-1/2). seq % 128 == 0. */
@@ -167,7 +171,7 @@ int dxmi_set_option(const char* name, int value);
 int dxmi_set_debug_buffer(void* dev_ptr);
 /* profiling only: with "time_gemms" on, dxmi_gemm_timing() also appends one CSV row per GEMM launch to this file (NULL = off) */
 int dxmi_set_timing_dump(const char* path); /* "block_n_256" (tile width), "time_gemms" (event-time every GEMM), "gemm_version" (1 = one tile per CTA,
- * 2 = persistent kernel, default), "dbg_mode" (profiling) */
+ * 2 = persistent kernel, default), "halo" (1 = halo-tile A reuse for 3x3 convs; default 0, measured slower), "dbg_mode" (profiling) */
 /* with "time_gemms" on: summed CUDA-event duration / algorithmic FLOPs / count of the tcgen05 GEMM launches since
  * the last call (synchronises on the recorded events) */
 int dxmi_gemm_timing(double* ms_total, double* flops_total, long long* launches);

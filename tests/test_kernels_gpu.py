@@ -204,6 +204,26 @@ def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
     b = torch.randn(Cout, device=dev)
     wp = ops.pack_conv_weight(w)
     M = N * H * H
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    L.lib().dxmi_set_option(b"halo", 1)
+    tpi = L.lib().dxmi_op_halo_tiles_per_image(H, H)
+    L.lib().dxmi_set_option(b"halo", 0)
+    if tpi:
+        L.lib().dxmi_set_option(b"halo", 1)
+        # halo-mode conv (32- / 64-wide maps): one partial per tile of the zero-padded (W+2)-wide position grid
+        stats = torch.full((N, tpi, Cout, 2), float("nan"), device=dev)
+        try:
+            y = ops.conv_gemm([(x, Cin, Cin)], [(0, 9)], wp, N, H, H, bias=b, gn_stats=stats, gn_halo_P=tpi)
+        finally:
+            L.lib().dxmi_set_option(b"halo", 0)
+        torch.cuda.synchronize()
+        assert rel_l2(y.view(N, H, H, Cout), ref_conv(x, w, b)) < 4e-3
+        yf = y.float().view(N, H * H, Cout)
+        assert torch.isfinite(stats).all()
+        assert torch.allclose(stats[..., 0].sum(1), yf.sum(1), rtol=1e-4, atol=5e-3)
+        assert torch.allclose(stats[..., 1].sum(1), (yf * yf).sum(1), rtol=1e-4, atol=5e-3)
+        return
     for seg in (32, 64, 128):
         if (H * H) % seg:
             continue
@@ -214,3 +234,45 @@ def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
         assert torch.isfinite(stats).all(), seg
         assert torch.allclose(stats[..., 0], yf.sum(1), rtol=1e-4, atol=2e-3), seg
         assert torch.allclose(stats[..., 1], (yf * yf).sum(1), rtol=1e-4, atol=2e-3), seg
+
+
+@pytest.mark.parametrize("N,H,Ca,Cb,Co", [(3, 32, 128, 64, 128), (2, 64, 192, 192, 192), (5, 32, 256, 0, 256)])
+def test_halo_conv_fused_shortcut_residual(ops, N, H, Ca, Cb, Co):
+    """Halo-tile 3x3 conv (one TMA load per channel chunk serves all 9 taps) + centre-tap 1x1 segments over two more
+    sources + bias + per-image row vector + residual, against torch; and halo on/off give the same answer."""
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    torch.manual_seed(9)
+    dev = "cuda"
+    g = nhwc(torch.randn(N, Co, H, H, device=dev))
+    xa = nhwc(torch.randn(N, Ca, H, H, device=dev))
+    w2 = torch.randn(Co, Co, 3, 3, device=dev) / (3 * Co**0.5)
+    b = torch.randn(Co, device=dev)
+    rowvec = torch.randn(N, Co, device=dev)
+    srcs, segs, parts = [(g, Co, Co), (xa, Ca, Ca)], [(0, 9), (1, 1)], None
+    wn = torch.randn(Co, Ca + Cb, 1, 1, device=dev) / (Ca + Cb) ** 0.5
+    parts = [(w2, 0, Co), (wn, 0, Ca)]
+    cat = xa
+    if Cb:
+        xb = nhwc(torch.randn(N, Cb, H, H, device=dev))
+        srcs.append((xb, Cb, Cb))
+        segs.append((2, 1))
+        parts.append((wn, Ca, Cb))
+        cat = torch.cat([xa, xb], -1)
+    wp = ops.pack_conv_weight(None, parts=parts)
+    ref = ref_conv(g, w2, b) + ref_conv(cat, wn, None, pad=0) + rowvec[:, None, None, :]
+    outs = []
+    for halo in (1, 0):
+        L.lib().dxmi_set_option(b"halo", halo)
+        try:
+            y = ops.conv_gemm(srcs, segs, wp, N, H, H, bias=b, rowvec=rowvec, out_fp32=True)
+        finally:
+            L.lib().dxmi_set_option(b"halo", 0)
+        assert rel_l2(y.view(N, H, H, Co), ref) < 2e-5, halo
+        outs.append(y)
+    assert rel_l2(outs[0], outs[1]) < 1e-6
+    res = nhwc(torch.randn(N, Co, H, H, device=dev))
+    wp2 = ops.pack_conv_weight(w2)
+    y2 = ops.conv_gemm([(g, Co, Co)], [(0, 9)], wp2, N, H, H, bias=b, residual=res, act=2)
+    ref2 = F.silu(ref_conv(g, w2, b) + res.float())
+    assert rel_l2(y2.view(N, H, H, Co), ref2) < 4e-3

@@ -16,10 +16,13 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--block-n", type=int, nargs="*", default=[0])
 ap.add_argument("--dbg", type=int, default=0)
 ap.add_argument("--gemm-version", type=int, default=2)
+ap.add_argument("--halo", type=int, default=1)
 args = ap.parse_args()
 
 # (name, N, H, Cin, Cout, taps)
 SHAPES = {
+    "halo": [("c32_128_128", 256, 32, 128, 128, 9), ("c32_256_256", 256, 32, 256, 256, 9), ("i64_192_192", 64, 64, 192, 192, 9),
+             ("i32_384_384", 64, 32, 384, 384, 9)],
     "cifar": [("c32_128_128", 256, 32, 128, 128, 9), ("c32_256_128", 256, 32, 256, 128, 9),
               ("c16_256_256", 256, 16, 256, 256, 9), ("c16_512_256", 256, 16, 512, 256, 9),
               ("c8_256_256", 256, 8, 256, 256, 9), ("c4_256_256", 256, 4, 256, 256, 9),
@@ -31,6 +34,7 @@ SHAPES = {
 from diffusion_by_maxentirl_b200 import _lib as L  # noqa: E402
 L.lib().dxmi_set_option(b"dbg_mode", args.dbg)
 L.lib().dxmi_set_option(b"gemm_version", args.gemm_version)
+L.lib().dxmi_set_option(b"halo", args.halo)
 sets = ["cifar", "in64"] if args.set == "all" else [args.set]
 dev = "cuda"
 for s in sets:
