@@ -93,7 +93,8 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
         if (d.softmax)
             block_n = d.b_rows;
         else if (d.b_rows % 256 == 0 && g_opt_block_n_256)
-            block_n = 256;
+            // few row tiles (4x4 maps): narrower column tiles put more SMs to work (measured 19.3 -> 16.9 us)
+            block_n = (m_tiles * (d.b_rows / 256) <= 37 && d.batch <= 1) ? 128 : 256;
         else if (d.b_rows % 192 == 0)
             block_n = 192;
         else if (d.b_rows >= 128)
