@@ -30,6 +30,14 @@ int dxmi_set_option(const char* name, int value) {
         set_halo(value);
         return 0;
     }
+    if (!strcmp(name, "pair")) {
+        set_pair(value);
+        return 0;
+    }
+    if (!strcmp(name, "pair_min")) {
+        set_pair_min(value);
+        return 0;
+    }
     if (!strcmp(name, "gemm_version")) {
         set_gemm_version(value);
         return 0;

@@ -15,6 +15,11 @@ static int g_opt_gemm_v = 2;
 // bandwidth, and the 9-vs-8 tiles per 32x32 image plus the pad columns cost more than the saved bytes.
 static int g_opt_halo = 0;
 void set_halo(int v) { g_opt_halo = v; }
+// cta_group::2 pair kernel (gemm_tc2p.cu): 0 = off, 1 = when there are at least g_opt_pair_min pair tiles, 2 = whenever supported
+static int g_opt_pair = 1;
+static int g_opt_pair_min = 74;
+void set_pair(int v) { g_opt_pair = v; }
+void set_pair_min(int v) { g_opt_pair_min = v; }
 
 // Tiles per image of the halo-mode 3x3 convolution on an H x W map, or 0 when that geometry does not use halo tiles.
 int halo_tiles_per_image(int H, int W) {
@@ -105,8 +110,16 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             block_n = 32;
     }
     const int n_tiles = (d.b_rows + block_n - 1) / block_n;
+    // pair mode: two CTAs share one 256-row tile, each loads half of the B tile (decided here: it sets the B box height)
+    bool pair = false;
+    if (g_opt_gemm_v == 2 && g_opt_pair && !d.softmax && !d.out_nchw && (block_n == 128 || block_n == 192 || block_n == 256)) {
+        const long long pairs = (long long)((m_tiles + 1) / 2) * n_tiles * (d.batch > 0 ? d.batch : 1);
+        // measured (profiles/r01_pair_conv_bench.txt): +7..12 % on GEMMs with at least one full wave of pairs and a deep K loop;
+        // neutral to -5 % on short-K 1x1 projections and small maps, which stay on the one-CTA kernel
+        pair = g_opt_pair == 2 || (pairs >= g_opt_pair_min && k_total >= 512);
+    }
     int r = make_mat_map(&p.b_map, d.b_ptr, (int)k_total, d.b_rows, d.b_batched ? d.batch : 1, d.b_ld, d.b_batch_stride,
-                         block_n);
+                         pair ? block_n / 2 : block_n);
     if (r) return r;
 
     p.out = d.out;
@@ -140,7 +153,7 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     op->use_v2 = 0;
     if (g_opt_gemm_v == 2 && conv_gemm_v2_supported(p, block_n)) {
         // ---- halo mode: 3x3 stride-1 convolutions (plus centre-tap 1x1 segments) on 32- / 64-wide maps
-        bool halo = halo_tiles_per_image(d.H, d.W) > 0 && p.stride == 1 && !d.a_batched && op->batch == 1 && d.out_H == d.H &&
+        bool halo = !pair && halo_tiles_per_image(d.H, d.W) > 0 && p.stride == 1 && !d.a_batched && op->batch == 1 && d.out_H == d.H &&
                     d.out_W == d.W && !d.softmax;
         bool any9 = false;
         for (int s = 0; s < d.nseg; ++s) any9 |= d.seg_taps[s] == 9;
@@ -182,7 +195,7 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             snprintf(g_op_err, sizeof g_op_err, "gn_seg must be 32, 64 or 128");
             return -13;
         }
-        op->use_v2 = 1;
+        op->use_v2 = pair ? 2 : 1;
     } else if (d.gn_stats) {
         snprintf(g_op_err, sizeof g_op_err, "gn_stats requested but the persistent kernel does not support this GEMM");
         return -12;
@@ -229,6 +242,7 @@ int gemm_timing_collect(double* ms_total, double* flops_total, long long* launch
 }
 
 static int launch_any(const GemmOp& op, cudaStream_t st) {
+    if (op.use_v2 == 2) return launch_conv_gemm_pair(op.p, op.block_n, st);
     if (op.use_v2) return launch_conv_gemm_v2(op.p, op.block_n, st);
     return launch_conv_gemm(op.p, op.block_n, op.m_tiles, op.n_tiles, op.batch, st);
 }

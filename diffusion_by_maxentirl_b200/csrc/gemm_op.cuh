@@ -7,7 +7,7 @@ namespace dxmi {
 struct GemmOp {
     ConvGemmParams p;
     int block_n, m_tiles, n_tiles, batch;
-    int use_v2;  // persistent kernel (gemm_tc2.cu)
+    int use_v2;  // 1: persistent kernel (gemm_tc2.cu), 2: cta_group::2 pair kernel (gemm_tc2p.cu)
     double flops;  // algorithmic 2*M*N*K of this launch
 };
 
@@ -17,6 +17,8 @@ void set_block_n_256(int v);
 void set_dbg_mode(int v);
 void set_gemm_version(int v);
 void set_halo(int v);
+void set_pair(int v);
+void set_pair_min(int v);
 int halo_tiles_per_image(int H, int W);
 void set_dbg_times(void* p);
 void set_time_gemms(int v);

@@ -15,6 +15,7 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2..9 epilogue
 // (warp w may read TMEM lanes 32*(w%4)..+31).
+#include "gemm_epi.cuh"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 
@@ -22,11 +23,7 @@
 
 namespace dxmi {
 
-static constexpr int TILE_M = 128;
-static constexpr int TILE_K = 64;
-static constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;  // 16 KB
 static constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
-static constexpr int EPI_SLOT_BYTES = 128 * 128;  // 128 rows x 128 bytes
 
 template <int BLOCK_N>
 struct Cfg2 {
@@ -52,268 +49,6 @@ __device__ __forceinline__ long long gtimer2() {
     if (p.dbg_times) p.dbg_times[(long long)blockIdx.x * 8 + (slot)] = gtimer2();
 // cycle-resolution stamps of the epilogue leader for chunk `cidx` of the CTA's second tile (steady state)
 
-
-__device__ __forceinline__ float act2(float v, int act) {
-    if (act == ACT_LRELU02) return v > 0.f ? v : 0.2f * v;
-    if (act == ACT_SILU) return __fdividef(v, 1.f + __expf(-v));
-    return v;
-}
-
-// ------------------------------------------------------------------------------------------------ tile epilogue
-// Per-thread constants of the 8 epilogue warps.
-struct EpiCtx {
-    uint8_t* slot0;     // 2 staging slots of 128 rows x 128 bytes (32 fp32 columns), SWIZZLE_128B pattern
-    float2* sst;        // [8 warps][32 columns] GroupNorm partials / softmax row stats
-    uint32_t taddr;     // TMEM address of this warp's lane quarter (column 0 of accumulator 0)
-    uint32_t stage_off; // byte offset of this thread's staging row + its 4 swizzled 16-byte units base
-    int sw;             // row & 7 (swizzle key) of the staging row this thread writes in phase A
-    int hsel;           // which 16 of the chunk's 32 columns this warp stages
-    int e, ew;          // epilogue thread / warp index
-    int rt0;            // first of the 4 tile rows (rt0 + 4 i) this thread finishes in phase B
-    int bu;             // 16-byte unit (4 columns) of the staging row this thread finishes
-    bool brs0;          // lane owns the per-warp statistics write
-};
-
-enum EpiMode { EPI_BIAS = 0, EPI_ROWVEC = 1, EPI_RESIDUAL = 2, EPI_GENERIC = 3 };
-
-// Drains one 128 x BLOCK_N accumulator tile.
-//   Phase A: raw fp32 accumulators TMEM -> swizzled staging slot. Warp w may only read TMEM lanes 32*(w%4)..+31; the
-//            two warps that share a lane quarter split the chunk's 32 columns.
-//   Phase B: 8 lanes <-> one 128-byte staging row: alpha / bias / row vector / residual / activation / softmax,
-//            conversion, fully coalesced global stores, GroupNorm partial sums - on operands prefetched one chunk
-//            ahead with coalesced loads.  Staging is double buffered: one named barrier per chunk.
-// MODE selects straight-line code for the three hot operator shapes of the U-Nets (bias only, + per-image row vector,
-// + residual); EPI_GENERIC keeps every switch at run time (softmax, activations, per-row bias, fp32 output).
-// (Measured, profiles/r01_cta_timeline_*: the epilogue is issue / latency bound - 2 warps per scheduler - so code
-//  size and dependent chains matter more than bytes.)
-template <int MODE, bool STATS>
-__device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& cx, uint32_t tacc_col, uint64_t* tmem_empty_bar,
-                                         int m_tile, int col0, int nch, int batch, uint32_t& out_cnt) {
-    const int row0 = m_tile * TILE_M;
-    constexpr int CH = 32;
-    const int n_total = p.N_total;
-    const float alpha = p.alpha;
-    const bool g_res = MODE == EPI_GENERIC && p.residual != nullptr;
-    const bool g_rv = MODE == EPI_GENERIC && p.rowvec != nullptr;
-    const bool g_bm = MODE == EPI_GENERIC && p.bias != nullptr && p.bias_along_m;
-    const bool g_sm = MODE == EPI_GENERIC && p.softmax != 0;
-    const bool g_f32 = MODE == EPI_GENERIC && p.out_fp32 != 0;
-    const int g_act = MODE == EPI_GENERIC ? p.act : ACT_NONE;
-    const bool has_bias = p.bias != nullptr && !(MODE == EPI_GENERIC && p.bias_along_m);
-    const bool use_rv = MODE == EPI_ROWVEC || g_rv;
-    const bool use_res = MODE == EPI_RESIDUAL || g_res;
-
-    // ---- per-tile invariants: the 4 rows this thread finishes
-    bool rok[4];
-    long long ooff[4], roff[4];
-    const float* rvp[4];
-    float bm[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        long long r;
-        long long img;
-        bool ok;
-        if (p.halo) {
-            // halo tile: row i <-> position p0 + i of the zero-padded (W+2)-wide grid of image m_tile / tpi
-            const int Wp = p.halo_W + 2;
-            img = m_tile / p.halo_tpi;
-            const int pos = (m_tile - static_cast<int>(img) * p.halo_tpi) * TILE_M + cx.rt0 + 4 * i;
-            const int hh = pos / Wp, ww = pos - hh * Wp;
-            ok = ww < p.halo_W && hh < p.halo_H;
-            r = (img * p.halo_H + hh) * p.halo_W + ww;
-        } else {
-            r = static_cast<long long>(row0) + cx.rt0 + 4 * i;
-            ok = r < p.M_total;
-            img = use_rv ? r / p.rows_per_image : 0;
-        }
-        rok[i] = ok && p.dbg_mode != 2;
-        ooff[i] = batch * p.out_batch_stride + r * p.ldo;
-        roff[i] = use_res ? batch * p.res_batch_stride + r * p.ldr : 0;
-        rvp[i] = (use_rv && rok[i]) ? p.rowvec + img * p.ldrv : nullptr;
-        bm[i] = (g_bm && rok[i]) ? __ldg(p.bias + r) : 0.f;
-    }
-    float4 pf_bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 pf_rv[4];
-    uint2 pf_res[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        pf_rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pf_res[i] = make_uint2(0u, 0u);
-    }
-    auto prefetch = [&](int pcc) {
-        const bool pok = pcc < n_total;
-        if (has_bias && pok) pf_bias = __ldg(reinterpret_cast<const float4*>(p.bias + pcc));
-        if (use_rv) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (rvp[i] && pok) pf_rv[i] = __ldg(reinterpret_cast<const float4*>(rvp[i] + pcc));
-        }
-        if (use_res) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (rok[i] && pok) pf_res[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + roff[i] + pcc));
-        }
-    };
-    prefetch(col0 + cx.bu * 4);
-
-    // ---- accumulator ready?
-    // (the caller has already waited on tmem_full and fenced)
-    if (g_sm) {
-        // row max / sum over the whole accumulator row (N_total == BLOCK_N): one warp per lane quarter
-        if (cx.hsel == 0) {
-            float sm_max = -INFINITY, sm_sum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < n_total; c += 32) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(cx.taddr + tacc_col + c, v);
-                ptx::tmem_ld_wait();
-                float cmax = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]) * alpha);
-                const float nmax = fmaxf(sm_max, cmax);
-                float part = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) part += __expf(__uint_as_float(v[j]) * alpha - nmax);
-                sm_sum = sm_sum * __expf(sm_max - nmax) + part;
-                sm_max = nmax;
-            }
-            // staging row index of this thread == its accumulator row
-            cx.sst[(cx.stage_off >> 10) * 8 + ((cx.stage_off >> 7) & 7)] = make_float2(sm_max, 1.f / sm_sum);
-        }
-        ptx::named_bar_sync(2, 256);
-    }
-
-    const int stat_seg = (STATS && !p.halo) ? p.stats_seg : 128;  // halo tiles: one partial per tile (tiles never span images)
-    const int stat_nseg = 128 / stat_seg, stat_bps = stat_seg >> 5;
-    const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : 5);
-
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-        const int col = col0 + c * CH;
-        const int cc = col + cx.bu * 4;
-        const bool col_ok = cc < n_total;
-        uint8_t* slot = cx.slot0 + (out_cnt & 1) * EPI_SLOT_BYTES;
-
-        // ---- phase A: 16 accumulator columns of this warp's 32 rows -> staging
-        {
-            uint32_t v[16];
-            ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + (c * CH + cx.hsel * 16), v);
-            ptx::tmem_ld_wait();
-            if (c == nch - 1) {
-                // every accumulator column this warp stages is now in registers: hand the TMEM buffer back
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(tmem_empty_bar);
-            }
-            uint8_t* srow = slot + cx.stage_off;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(srow + (((cx.hsel * 4 + q) ^ cx.sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        ptx::named_bar_sync(1, 256);
-
-        // ---- phase B
-        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int rt = cx.rt0 + 4 * i;
-            const uint4 u = *reinterpret_cast<const uint4*>(slot + (rt >> 3) * 1024 + (rt & 7) * 128 + ((cx.bu ^ (rt & 7)) << 4));
-            float x[4];
-            if (g_sm) {
-                const float2 ms = cx.sst[rt];
-                x[0] = __expf(__uint_as_float(u.x) * alpha - ms.x) * ms.y;
-                x[1] = __expf(__uint_as_float(u.y) * alpha - ms.x) * ms.y;
-                x[2] = __expf(__uint_as_float(u.z) * alpha - ms.x) * ms.y;
-                x[3] = __expf(__uint_as_float(u.w) * alpha - ms.x) * ms.y;
-            } else {
-                float4 ad = pf_bias;
-                if (g_bm) {
-                    ad.x += bm[i];
-                    ad.y += bm[i];
-                    ad.z += bm[i];
-                    ad.w += bm[i];
-                }
-                if (use_rv) {
-                    ad.x += pf_rv[i].x;
-                    ad.y += pf_rv[i].y;
-                    ad.z += pf_rv[i].z;
-                    ad.w += pf_rv[i].w;
-                }
-                x[0] = fmaf(__uint_as_float(u.x), alpha, ad.x);
-                x[1] = fmaf(__uint_as_float(u.y), alpha, ad.y);
-                x[2] = fmaf(__uint_as_float(u.z), alpha, ad.z);
-                x[3] = fmaf(__uint_as_float(u.w), alpha, ad.w);
-                if (use_res) {
-                    x[0] += __uint_as_float(pf_res[i].x << 16);
-                    x[1] += __uint_as_float(pf_res[i].x & 0xffff0000u);
-                    x[2] += __uint_as_float(pf_res[i].y << 16);
-                    x[3] += __uint_as_float(pf_res[i].y & 0xffff0000u);
-                }
-                if (g_act != ACT_NONE) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] = act2(x[j], g_act);
-                }
-            }
-            const bool ok = rok[i] && col_ok;
-            if (g_f32) {
-                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff[i] + cc) = make_float4(x[0], x[1], x[2], x[3]);
-            } else {
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]);
-                __nv_bfloat162 b1 = __floats2bfloat162_rn(x[2], x[3]);
-                uint32_t w0 = *reinterpret_cast<uint32_t*>(&b0), w1 = *reinterpret_cast<uint32_t*>(&b1);
-                if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + cc) = make_uint2(w0, w1);
-                if (STATS) {
-                    // statistics of the values the consumer will read (bf16-rounded); masked rows / columns add zero
-                    w0 = ok ? w0 : 0u;
-                    w1 = ok ? w1 : 0u;
-                    const float a0 = __uint_as_float(w0 << 16), a1 = __uint_as_float(w0 & 0xffff0000u);
-                    const float a2 = __uint_as_float(w1 << 16), a3 = __uint_as_float(w1 & 0xffff0000u);
-                    s1[0] += a0; s2[0] = fmaf(a0, a0, s2[0]);
-                    s1[1] += a1; s2[1] = fmaf(a1, a1, s2[1]);
-                    s1[2] += a2; s2[2] = fmaf(a2, a2, s2[2]);
-                    s1[3] += a3; s2[3] = fmaf(a3, a3, s2[3]);
-                }
-            }
-        }
-        if (c + 1 < nch) prefetch(cc + CH);  // next chunk's operands fly during the stats tail and phase A
-        if (STATS) {
-            // this warp's 16 rows: fold the 4 row sub-indices (lanes xor 8, 16); then the warps that share a row segment
-            // are combined through smem in a fixed order and one partial per segment is published
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
-                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
-                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
-            }
-            if (cx.brs0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) cx.sst[cx.ew * 32 + cx.bu * 4 + j] = make_float2(s1[j], s2[j]);
-            }
-            ptx::named_bar_sync(2, 256);
-            // (sst is single buffered: the next chunk writes it after its named barrier 1, which every publisher of this
-            //  chunk reaches only after it has read sst)
-            const int sg = cx.e >> 5, j = cx.e & 31;  // thread publishes column j of segment sg
-            if (sg < stat_nseg) {
-                float2 a = make_float2(0.f, 0.f);
-                for (int b2 = sg * stat_bps; b2 < (sg + 1) * stat_bps; ++b2) {
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const float2 b = cx.sst[(hh * 4 + b2) * 32 + j];
-                        a.x += b.x;
-                        a.y += b.y;
-                    }
-                }
-                const int srow = row0 + sg * stat_seg;
-                if (p.halo) {
-                    if (col + j < n_total) *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(m_tile) * n_total + col + j) * 2) = a;
-                } else if (col + j < n_total && srow < p.M_total) {
-                    *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(srow >> stat_shift) * n_total + col + j) * 2) = a;
-                }
-            }
-        }
-        ++out_cnt;
-    }
-}
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -565,7 +300,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             ptx::tc_fence_after();
             if (ti == 0 && leader) { DBG2(5); }
             const uint32_t tcol = acc * Cfg::ACC_COLS;
-            uint64_t* te = &tmem_empty[acc];
+            const uint32_t te = ptx::smem_u32(&tmem_empty[acc]);  // own CTA: shared::cta addresses are valid shared::cluster ones
             if (has_stats) {
                 switch (mode) {
                     case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;

@@ -1,0 +1,328 @@
+// Persistent tcgen05 implicit-GEMM convolution kernel for CTA PAIRS (cta_group::2). Same operator contract as gemm_tc2.cu.
+//
+// Why: the single-CTA kernel is bound by the per-SM TMA ingest rate (~140 GB/s): a 128 x BLOCK_N tile needs 16 KB of A
+// and BLOCK_N/4 KB of B per 64-deep K step.  Two CTAs of a cluster (two SMs of one TPC) compute a 256 x BLOCK_N tile
+// together: each loads its own 128 A rows and only HALF of the B tile; one tcgen05.mma.cta_group::2 (M = 256, issued by the
+// leader CTA) reads A from each CTA's shared memory and the two B halves from both, and writes 128 accumulator rows into
+// each CTA's TMEM.  Per-SM ingest per K step drops from 16 + BLOCK_N/4 KB to 16 + BLOCK_N/8 KB.
+// (Mechanics verified first in isolation on hardware: csrc/exp_2cta.cu, tools/exp_2cta.py.)
+//
+// Barriers: full[s] lives in the LEADER (2 arrivals + the bytes of both CTAs; the peer's TMA loads signal it through the
+// cluster window), empty[s] / tmem_full[a] live in BOTH CTAs (multicast tcgen05.commit), tmem_empty[a] lives in the leader
+// (2 x 256 epilogue threads arrive, the peer's remotely).
+#include "gemm_epi.cuh"
+
+#include <cstdio>
+
+namespace dxmi {
+
+static constexpr int NUM_THREADS_P = 320;
+
+template <int BLOCK_N>
+struct Cfg2P {
+    static constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * TILE_K * 2;  // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = BLOCK_N > 128 ? 6 : 8;
+    static constexpr int ACC_COLS = BLOCK_N <= 128 ? 128 : 256;
+    static constexpr int TMEM_COLS = 2 * ACC_COLS;
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SM_OUT = RING_BYTES;
+    static constexpr int SM_STAT = SM_OUT + 2 * EPI_SLOT_BYTES;
+    static constexpr int SM_BAR = SM_STAT + 2048;
+    static constexpr int SMEM_BYTES = SM_BAR + 512;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(RING_BYTES % 1024 == 0, "staging slots must stay 1024-byte aligned");
+};
+
+__device__ __forceinline__ uint32_t ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all previously issued MMAs retired) on the barrier at the same smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(ptx::smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __grid_constant__ ConvGemmParams p) {
+    using Cfg = Cfg2P<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SM_BAR);
+    uint64_t* full_bar = bars;                    // [STAGES]  (used in the leader)
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       (used in the leader)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int n_clusters = gridDim.x >> 1;
+    const int m_pairs = (p.m_tiles + 1) >> 1;
+    const int total_pairs = m_pairs * p.n_tiles * p.batch_count;
+
+    int k_iters = 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+        if (s < p.nseg) k_iters += p.seg[s].ntaps * p.seg[s].nchunks;
+
+    if (threadIdx.x == 0) {
+        if (ptx::smem_u32(smem) & 1023u) {
+            printf("dxmi conv_gemm2p: dynamic smem base not 1024-byte aligned\n");
+            __trap();
+        }
+        ptx::prefetch_tmap(&p.a_map[0]);
+        if (p.nseg > 1) ptx::prefetch_tmap(&p.a_map[1]);
+        if (p.nseg > 2) ptx::prefetch_tmap(&p.a_map[2]);
+        ptx::prefetch_tmap(&p.b_map);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 2);   // one arrival per CTA (+ the transaction bytes of both)
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tmem_full[s], 1);
+            ptx::mbar_init(&tmem_empty[s], 512);  // the 256 epilogue threads of each CTA
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(tmem_slot)),
+                     "r"((uint32_t)Cfg::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    ptx::tc_fence_before();
+    cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (ptx::elect_one()) {
+            const int tiles_per_nblk = p.tiles_w * p.tiles_h;
+            uint32_t it = 0;
+            for (int tp = cluster_id; tp < total_pairs; tp += n_clusters) {
+                const int n_tile = tp % p.n_tiles;
+                const int mp = tp / p.n_tiles;
+                const int m_tile = (mp % m_pairs) * 2 + (int)rank;
+                const int batch = mp / m_pairs;
+                const int n_blk = m_tile / tiles_per_nblk;
+                const int rem = m_tile - n_blk * tiles_per_nblk;
+                const int h_blk = rem / p.tiles_w;
+                const int w_blk = rem - h_blk * p.tiles_w;
+                const int w0 = w_blk * p.bw * p.stride;
+                const int h0 = h_blk * p.bh * p.stride;
+                const int n0 = p.a_batched ? batch : n_blk * p.bn;   // past the tensor for an odd last tile: zero fill
+                const int bcoord_n = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                const int bcoord_b = p.b_batched ? batch : 0;
+                int kk = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const GemmSeg sg = p.seg[s];
+                    const CUtensorMap* amap = &p.a_map[sg.map];
+                    for (int tap = 0; tap < sg.ntaps; ++tap) {
+                        const int r = (sg.ntaps == 9) ? tap / 3 : 0;
+                        const int q = (sg.ntaps == 9) ? tap - 3 * r : 0;
+                        for (int ch = 0; ch < sg.nchunks; ++ch, ++it, ++kk) {
+                            const uint32_t stage = it % STAGES;
+                            const uint32_t ph = (it / STAGES) & 1;
+                            ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+                            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                            uint8_t* sb = sa + A_STAGE_BYTES;
+                            const uint32_t full_leader = mapa(ptx::smem_u32(&full_bar[stage]), 0);
+                            if (rank == 0) {
+                                ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                            } else {
+                                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
+                            }
+                            tma2_load_4d(sa, amap, full_leader, ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
+                            tma2_load_3d(sb, &p.b_map, full_leader, kk * TILE_K, bcoord_n, bcoord_b);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_idesc(/*bf16*/ 1, 256, BLOCK_N);
+            uint32_t it = 0, ti = 0;
+            for (int tp = cluster_id; tp < total_pairs; tp += n_clusters, ++ti) {
+                const uint32_t acc = ti & 1;
+                ptx::mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * Cfg::ACC_COLS;
+                for (int k = 0; k < k_iters; ++k, ++it) {
+                    const uint32_t stage = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    ptx::mbar_wait(&full_bar[stage], ph);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+                    if (p.dbg_mode != 1) {
+#pragma unroll
+                        for (int j = 0; j < TILE_K / 16; ++j) umma2_f16(tacc, da + 2 * j, db + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
+                    }
+                    umma2_commit_both(&empty_bar[stage]);
+                }
+                umma2_commit_both(&tmem_full[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue (8 warps per CTA): see gemm_epi.cuh
+        EpiCtx cx;
+        cx.e = threadIdx.x - 64;
+        cx.ew = cx.e >> 5;
+        const int quarter = warp & 3;
+        cx.hsel = cx.ew >> 2;
+        const int row_in_tile = quarter * 32 + lane;
+        cx.sw = row_in_tile & 7;
+        cx.stage_off = (row_in_tile >> 3) * 1024 + (row_in_tile & 7) * 128;
+        cx.slot0 = smem + Cfg::SM_OUT;
+        cx.sst = reinterpret_cast<float2*>(smem + Cfg::SM_STAT);
+        cx.taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        cx.rt0 = (cx.ew & 3) * 32 + (cx.ew >> 2) * 16 + (lane >> 3);
+        cx.bu = lane & 7;
+        cx.brs0 = (lane >> 3) == 0;
+        const bool simple = !p.softmax && p.act == ACT_NONE && !p.out_fp32 && !(p.bias && p.bias_along_m);
+        int mode = EPI_GENERIC;
+        if (simple && !p.residual && !p.rowvec) mode = EPI_BIAS;
+        else if (simple && !p.residual && p.rowvec) mode = EPI_ROWVEC;
+        else if (simple && p.residual && !p.rowvec) mode = EPI_RESIDUAL;
+        const bool has_stats = p.stats != nullptr && !p.out_fp32;
+        uint32_t ti = 0, out_cnt = 0;
+
+        for (int tp = cluster_id; tp < total_pairs; tp += n_clusters, ++ti) {
+            const int n_tile = tp % p.n_tiles;
+            const int mp = tp / p.n_tiles;
+            const int m_tile = (mp % m_pairs) * 2 + (int)rank;
+            const int batch = mp / m_pairs;
+            const int col0 = n_tile * BLOCK_N;
+            int ncols = p.N_total - col0;
+            if (ncols > BLOCK_N) ncols = BLOCK_N;
+            const int nch = (ncols + 31) / 32;
+            const uint32_t acc = ti & 1;
+
+            ptx::mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t tcol = acc * Cfg::ACC_COLS;
+            const uint32_t te = mapa(ptx::smem_u32(&tmem_empty[acc]), 0);  // the leader's barrier
+            if (has_stats) {
+                switch (mode) {
+                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                }
+            } else {
+                switch (mode) {
+                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    cluster_sync();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+void gemm_set_error(const char* msg);
+
+bool conv_gemm_pair_supported(const ConvGemmParams& p, int block_n) {
+    return (block_n == 128 || block_n == 192 || block_n == 256) && !p.halo && !p.softmax;
+}
+
+template <int BLOCK_N>
+static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
+    using Cfg = Cfg2P<BLOCK_N>;
+    static bool configured = false;
+    static int num_sms = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm2p_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            gemm_set_error(cudaGetErrorString(e));
+            return (int)e;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    const int total_pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.batch_count;
+    int clusters = num_sms / 2;
+    if (total_pairs < clusters) clusters = total_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS_P);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm2p_kernel<BLOCK_N>, p);
+    if (e != cudaSuccess) {
+        gemm_set_error(cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+int launch_conv_gemm_pair(const ConvGemmParams& p, int block_n, cudaStream_t stream) {
+    switch (block_n) {
+        case 128: return launch2p_t<128>(p, stream);
+        case 192: return launch2p_t<192>(p, stream);
+        case 256: return launch2p_t<256>(p, stream);
+        default: gemm_set_error("pair kernel: unsupported block_n"); return -4;
+    }
+}
+
+}  // namespace dxmi

@@ -29,13 +29,20 @@ def ref_conv(x_bf, w, b=None, stride=1, pad=1, asym=False):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.fixture(scope="module")
-def ops():
+@pytest.fixture(scope="module", params=[0, 2], ids=["single", "pair"])
+def ops(request):
+    """Every test of this module runs twice: with the one-CTA-per-tile persistent kernel and with the cta_group::2
+    pair kernel forced on for every GEMM it supports (block_n 128 / 192 / 256)."""
+    from diffusion_by_maxentirl_b200 import _lib as L
     from diffusion_by_maxentirl_b200 import ops as o
 
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    return o
+    L.lib().dxmi_set_option(b"pair", request.param)
+    o.pair_mode = request.param
+    yield o
+    L.lib().dxmi_set_option(b"pair", 0)
+    o.pair_mode = 0
 
 
 @pytest.mark.parametrize(
@@ -209,7 +216,7 @@ def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
     L.lib().dxmi_set_option(b"halo", 1)
     tpi = L.lib().dxmi_op_halo_tiles_per_image(H, H)
     L.lib().dxmi_set_option(b"halo", 0)
-    if tpi:
+    if tpi and not ops.pair_mode:  # (the pair kernel has no halo mode)
         L.lib().dxmi_set_option(b"halo", 1)
         # halo-mode conv (32- / 64-wide maps): one partial per tile of the zero-padded (W+2)-wide position grid
         stats = torch.full((N, tpi, Cout, 2), float("nan"), device=dev)

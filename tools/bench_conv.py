@@ -16,7 +16,8 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--block-n", type=int, nargs="*", default=[0])
 ap.add_argument("--dbg", type=int, default=0)
 ap.add_argument("--gemm-version", type=int, default=2)
-ap.add_argument("--halo", type=int, default=1)
+ap.add_argument("--halo", type=int, default=0)
+ap.add_argument("--pair", type=int, default=0)
 args = ap.parse_args()
 
 # (name, N, H, Cin, Cout, taps)
@@ -35,6 +36,7 @@ from diffusion_by_maxentirl_b200 import _lib as L  # noqa: E402
 L.lib().dxmi_set_option(b"dbg_mode", args.dbg)
 L.lib().dxmi_set_option(b"gemm_version", args.gemm_version)
 L.lib().dxmi_set_option(b"halo", args.halo)
+L.lib().dxmi_set_option(b"pair", args.pair)
 sets = ["cifar", "in64"] if args.set == "all" else [args.set]
 dev = "cuda"
 for s in sets:
