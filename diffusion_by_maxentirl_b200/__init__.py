@@ -21,6 +21,13 @@ _BINDINGS = [
 ]
 
 
+def set_default_precision(mode):
+    """See native.set_default_precision: "bf16" (default) or "fp32"."""
+    from . import native
+
+    native.set_default_precision(mode)
+
+
 def install():
     """Rebind the hot-path classes of the reference's `models` package (which must be importable, i.e. the reference
     checkout is on sys.path) to the B200 drop-ins, in place.  Everything else in the reference (trainer, CLIs, FID,

@@ -32,6 +32,7 @@ class ArchDesc(C.Structure):
         ("use_scale_shift_norm", C.c_int),
         ("resblock_updown", C.c_int),
         ("learn_out_scale", C.c_int),
+        ("precision", C.c_int),
     ]
 
 

@@ -656,7 +656,14 @@ struct IgebmBuilder : Builder {
 
 int build_adm_plan(Net& net, Plan& plan);  // engine_adm.cu
 
+int build_plan_f32(Net& net, Plan& plan);  // engine_f32.cu
+
 int build_plan(Net& net, Plan& plan) {
+    if (net.a.precision == 1) return build_plan_f32(net, plan);
+    if (net.a.precision != 0) {
+        engine_set_error("dxmi_arch_desc.precision must be 0 (bf16) or 1 (fp32), got %d", net.a.precision);
+        return -25;
+    }
     switch (net.a.arch) {
         case DXMI_ARCH_DDPM_UNET: return build_two_pass<DdpmBuilder>(net, plan);
         case DXMI_ARCH_IGEBM_V2: return build_two_pass<IgebmBuilder>(net, plan);

@@ -9,6 +9,7 @@ re-packs weights whose version counter changed.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -34,12 +35,29 @@ def _init_like_torch(key, p):
             p.zero_()
 
 
+_PRECISIONS = {"bf16": 0, "fp32": 1}
+_default_precision = os.environ.get("DXMI_PRECISION", "bf16")
+
+
+def set_default_precision(mode):
+    """Precision of networks constructed from now on: "bf16" (tcgen05 tensor-core path, rel-L2 <= 2e-2 against the
+    reference) or "fp32" (CUDA-core FFMA validation mode, rel-L2 <= 1e-5 per step; DDPM U-Net and value net only).
+    Also settable with the environment variable DXMI_PRECISION.  Not part of the reference's surface."""
+    global _default_precision
+    if mode not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, got {mode!r}")
+    _default_precision = mode
+
+
 class NativeNet(nn.Module):
     """nn.Module facade over a dxmi_net_t handle."""
 
     def __init__(self, desc):
         super().__init__()
         self._desc = desc
+        if _default_precision not in _PRECISIONS:
+            raise ValueError(f"DXMI_PRECISION must be one of {sorted(_PRECISIONS)}, got {_default_precision!r}")
+        self._desc.precision = _PRECISIONS[_default_precision]
         self._handle = None
         self._handle_device = None
         self._bound_sig = None
@@ -131,6 +149,19 @@ class NativeNet(nn.Module):
             L.check(lib.dxmi_repack(self._handle, L.stream_ptr()), "dxmi_repack")
             self._packed_version = version
         return self._handle
+
+    def set_precision(self, mode):
+        """Switch this network between the "bf16" and "fp32" paths (the handle and its plans are rebuilt lazily)."""
+        if mode not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, got {mode!r}")
+        if self._desc.precision != _PRECISIONS[mode]:
+            self.release()
+            self._desc.precision = _PRECISIONS[mode]
+        return self
+
+    @property
+    def precision(self):
+        return "fp32" if self._desc.precision == 1 else "bf16"
 
     def release(self):
         if self._handle is not None:

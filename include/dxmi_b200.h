@@ -52,6 +52,8 @@ typedef struct {
     int use_scale_shift_norm;
     int resblock_updown;
     int learn_out_scale;    /* IGEBM: out_scale Linear(1,1) present */
+    int precision;          /* 0: bf16 tcgen05 path (rel-L2 <= 2e-2 vs the reference); 1: fp32 mode - CUDA-core FFMA kernels on fp32
+                               activations, rel-L2 <= 1e-5 per step (DDPM U-Net and IGEBM, the reference's fp32 networks) */
 } dxmi_arch_desc;
 
 /* -------------------------------------------------------------------------------------------- lifecycle */

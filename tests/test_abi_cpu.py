@@ -136,3 +136,27 @@ def test_install_rebinds_reference_symbols():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip().endswith("8")
+
+
+def test_precision_switch_is_host_state_only():
+    """"bf16" / "fp32" selection (dxmi_arch_desc.precision) needs no GPU: it is carried in the descriptor."""
+    import pytest
+
+    from diffusion_by_maxentirl_b200 import native
+    from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
+
+    v = IGEBMEncoderV2(in_chan=3, out_chan=1, use_spectral_norm=False, keepdim=False, out_activation="linear",
+                       avg_pool_dim=1, learn_out_scale=True, nh=128)
+    assert v.precision == "bf16" and v._desc.precision == 0
+    assert v.set_precision("fp32") is v and v.precision == "fp32" and v._desc.precision == 1
+    with pytest.raises(ValueError):
+        v.set_precision("fp64")
+    native.set_default_precision("fp32")
+    try:
+        w = IGEBMEncoderV2(in_chan=3, out_chan=1, use_spectral_norm=False, keepdim=False, out_activation="linear",
+                           avg_pool_dim=1, learn_out_scale=True, nh=128)
+        assert w.precision == "fp32"
+    finally:
+        native.set_default_precision("bf16")
+    with pytest.raises(ValueError):
+        native.set_default_precision("tf32")
