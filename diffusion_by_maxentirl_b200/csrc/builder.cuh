@@ -38,7 +38,7 @@ struct Builder {
     bf16* act_alloc(int C, int H, int W) { return (bf16*)alloc((size_t)B * H * W * C * sizeof(bf16)); }
     // GroupNorm partial-statistics buffer for a GEMM output of B*H*W rows x C columns (null when the fused path
     // cannot be used for this geometry: a 32-row segment must not straddle two images)
-    static int stats_seg(int HW) { return HW % 128 == 0 ? 128 : (HW % 64 == 0 ? 64 : (HW % 32 == 0 ? 32 : 0)); }
+    static int stats_seg(int HW) { return HW % 128 == 0 ? 128 : (HW % 64 == 0 ? 64 : (HW % 32 == 0 ? 32 : (HW % 16 == 0 ? 16 : 0))); }
     static size_t stats_bytes(int rows, int HW, int C) { return (size_t)rows / stats_seg(HW) * C * 2 * sizeof(float); }
     // Layout of the GroupNorm partials a GEMM writes for its [B*H*W, C] output: per halo tile for 3x3 stride-1 convs on
     // 32- / 64-wide maps (gemm_op.cu: halo_tiles_per_image), else per 32/64/128-row segment.

@@ -504,15 +504,17 @@ struct DdpmBuilder : Builder {
             batched_emb_projection(temb, temb_ch, "temb_proj", wk, bk, tproj, TP);
         }
         // ---- conv_in
-        if (a.in_channels != 3 || ch % 32 || ch > 512 || (R * R) % 128) fail("DDPM conv_in: unsupported geometry");
-        Act h0 = new_act(ch, R, R, /*want_stats=*/false);
+        Act h0 = new_act(ch, R, R, /*want_stats=*/true);  // conv_in writes its GroupNorm partials itself (one per 128-pixel tile)
+        if (a.in_channels != 3 || ch % 32 || ch > 256 || (R * R) % 128 || h0.stats_P != R * R / 128 || h0.stats_halo)
+            fail("DDPM conv_in: unsupported geometry");
         {
             const float* w = f32("conv_in.weight");
             const float* b = f32("conv_in.bias");
             bf16* o = h0.p;
+            float* hst = h0.stats;
             const int Cin = a.in_channels;
             op([=](cudaStream_t st) {
-                conv3x3_first(pl->x, pl->x_scale, w, b, o, Bn, Cin, R, R, ch, 0, st);
+                conv3x3_first(pl->x, pl->x_scale, w, b, o, hst, Bn, Cin, R, R, ch, 0, st);
                 return (int)cudaGetLastError();
             });
         }
@@ -569,7 +571,7 @@ struct IgebmBuilder : Builder {
         const int nh = a.ch, R = a.resolution;
         Plan* pl = &plan;
         const int Bn = B;
-        if (a.in_channels != 3 || nh % 32 || nh > 512 || (R * R) % 128) fail("IGEBM conv1: unsupported geometry");
+        if (a.in_channels != 3 || nh % 32 || nh > 256 || (R * R) % 128) fail("IGEBM conv1: unsupported geometry");
         Act h = new_act(nh, R, R, false);
         {
             const float* w = f32("conv1.weight");
@@ -577,7 +579,7 @@ struct IgebmBuilder : Builder {
             bf16* o = h.p;
             const int Cin = a.in_channels;
             op([=](cudaStream_t st) {
-                conv3x3_first(pl->x, nullptr, w, b, o, Bn, Cin, R, R, nh, ACT_LRELU02, st);
+                conv3x3_first(pl->x, nullptr, w, b, o, nullptr, Bn, Cin, R, R, nh, ACT_LRELU02, st);
                 return (int)cudaGetLastError();
             });
         }

@@ -406,15 +406,17 @@ struct AdmBuilder : Builder {
             batched_emb_projection(emb, ted, "emb_layers", wk, bk, film, TP);
         }
         // ---- input conv (x * c_in folded into the load, karras_diffusion.py:349)
-        Act h = new_act(inputs[0][0].cout, R, R, /*want_stats=*/false);
+        Act h = new_act(inputs[0][0].cout, R, R, /*want_stats=*/true);  // the input conv writes its GroupNorm partials itself
         {
             const float* w = f32("input_blocks.0.0.weight");
             const float* b = f32("input_blocks.0.0.bias");
             bf16* o = h.p;
+            float* hst = h.stats;
             const int Cin = a.in_channels, Co = h.C;
-            if (Cin != 3 || Co % 32 || Co > 512 || (R * R) % 128) fail("ADM input conv: unsupported geometry");
+            if (Cin != 3 || Co % 32 || Co > 256 || (R * R) % 128 || h.stats_P != R * R / 128 || h.stats_halo)
+                fail("ADM input conv: unsupported geometry");
             op([=](cudaStream_t st) {
-                conv3x3_first(pl->x, pl->x_scale, w, b, o, Bn, Cin, R, R, Co, 0, st);
+                conv3x3_first(pl->x, pl->x_scale, w, b, o, hst, Bn, Cin, R, R, Co, 0, st);
                 return (int)cudaGetLastError();
             });
         }

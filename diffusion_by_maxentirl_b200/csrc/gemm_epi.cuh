@@ -142,7 +142,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
 
     const int stat_seg = (STATS && !p.halo) ? p.stats_seg : 128;  // halo tiles: one partial per tile (tiles never span images)
     const int stat_nseg = 128 / stat_seg, stat_bps = stat_seg >> 5;
-    const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : 5);
+    const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : (stat_seg == 32 ? 5 : 4));
 
 #pragma unroll 1
     for (int c = 0; c < nch; ++c) {
@@ -253,12 +253,17 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             const int sg = cx.e >> 5, j = cx.e & 31;  // thread publishes column j of segment sg
             if (sg < stat_nseg) {
                 float2 a = make_float2(0.f, 0.f);
-                for (int b2 = sg * stat_bps; b2 < (sg + 1) * stat_bps; ++b2) {
+                if (stat_seg == 16) {
+                    // a 16-row segment (4x4 maps) is exactly the rows of one epilogue warp
+                    a = cx.sst[((sg & 1) * 4 + (sg >> 1)) * 32 + j];
+                } else {
+                    for (int b2 = sg * stat_bps; b2 < (sg + 1) * stat_bps; ++b2) {
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const float2 b = cx.sst[(hh * 4 + b2) * 32 + j];
-                        a.x += b.x;
-                        a.y += b.y;
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const float2 b = cx.sst[(hh * 4 + b2) * 32 + j];
+                            a.x += b.x;
+                            a.y += b.y;
+                        }
                     }
                 }
                 const int srow = row0 + sg * stat_seg;

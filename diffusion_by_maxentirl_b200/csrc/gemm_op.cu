@@ -191,8 +191,8 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
         }
         p.stats = p.softmax ? nullptr : d.gn_stats;
         p.stats_seg = d.gn_seg;
-        if (p.stats && (p.stats_seg != 32 && p.stats_seg != 64 && p.stats_seg != 128)) {
-            snprintf(g_op_err, sizeof g_op_err, "gn_seg must be 32, 64 or 128");
+        if (p.stats && (p.stats_seg != 16 && p.stats_seg != 32 && p.stats_seg != 64 && p.stats_seg != 128)) {
+            snprintf(g_op_err, sizeof g_op_err, "gn_seg must be 16, 32, 64 or 128");
             return -13;
         }
         op->use_v2 = pair ? 2 : 1;

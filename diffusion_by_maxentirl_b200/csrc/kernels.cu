@@ -106,99 +106,137 @@ void cast_to_f32(const void* src, int src_is_half, float* dst, long long n, cuda
 
 // ============================================================================================ first / last conv
 
-// Tile = 128 consecutive output pixels of one image (th rows x tw columns). The zero-padded fp32 input patch and the
-// weights ([tap*Cin + ci][Cout]) are staged in shared memory; a thread owns 2 pixels x 32 output channels, so every
-// weight vector read from smem (broadcast) feeds 8 FMAs and every input value 32.
+// Persistent CTAs loop over tiles of 128 consecutive output pixels of one image (th rows x tw columns).  The weights
+// ([tap*Cin + ci][Cout], fp32) are staged in shared memory once per CTA, the zero-padded fp32 input patch once per tile.
+// A thread owns 8 consecutive pixels x 8 output channels: the 16 lanes that share a pixel group write one full
+// Cout-wide NHWC line per store (coalesced), every input value read from smem feeds 8 FMAs and every weight vector 32.
+// Optionally emits the GroupNorm partial statistics of its bf16 outputs in the layout of the GEMM epilogues
+// ([N][HW/128][Cout][2], one partial per tile) so that the consumer GroupNorm needs no statistics pass.
 template <int CIN>
-__global__ void conv3x3_first_k(const float* __restrict__ x, const float* __restrict__ in_scale,
-                                const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out, int H,
-                                int W, int Cout, int act, int th, int tw) {
+__global__ void __launch_bounds__(512) conv3x3_first_k(const float* __restrict__ x, const float* __restrict__ in_scale,
+                                                      const float* __restrict__ w, const float* __restrict__ b,
+                                                      bf16* __restrict__ out, float* __restrict__ stats, int H, int W, int Cout,
+                                                      int act, int th, int tw, int ntiles) {
     extern __shared__ float sm[];
-    const int K = 9 * CIN;
-    float* sw = sm;                   // [K][Cout]
-    float* sb = sw + K * Cout;        // [Cout]
-    float* sx = sb + Cout;            // [CIN][th+2][tw+2]
+    constexpr int K = 9 * CIN;
     const int pw = tw + 2, ph = th + 2;
-    const int tiles_w = W / tw, tiles_h = H / th;
-    const int n = blockIdx.x / (tiles_w * tiles_h);
-    const int trem = blockIdx.x % (tiles_w * tiles_h);
-    const int h0 = (trem / tiles_w) * th, w0 = (trem % tiles_w) * tw;
+    float* sw = sm;                        // [K][Cout]
+    float* sb = sw + K * Cout;             // [Cout]
+    float* sx = sb + Cout;                 // [CIN][ph][pw]
+    float2* red = reinterpret_cast<float2*>(sx + ((CIN * ph * pw + 3) & ~3));  // [16][Cout]
+    const int tiles_w = W / tw, tiles_per_img = tiles_w * (H / th);
+    const long long HW = (long long)H * W;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
         const int o = i % Cout, kk = i / Cout;  // kk = tap*CIN + ci
         const int tap = kk / CIN, ci = kk % CIN;
         sw[i] = w[((long long)o * CIN + ci) * 9 + tap];
     }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = b ? b[i] : 0.f;
-    const float sc = in_scale ? in_scale[n] : 1.f;
-    const long long HW = (long long)H * W;
-    for (int i = threadIdx.x; i < CIN * ph * pw; i += blockDim.x) {
-        const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
-        const int hh = h0 + r - 1, ww = w0 + c - 1;
-        sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((long long)n * CIN + ci) * HW + (long long)hh * W + ww] * sc : 0.f;
-    }
-    __syncthreads();
-    const int pp = threadIdx.x & 63;       // pixels pp and pp + 64 of the tile
-    const int cg = threadIdx.x >> 6;       // channels cg*32 .. +31
-    float acc[2][32];
+    const int CG = Cout >> 3;
+    const int cg = threadIdx.x % CG, pg = threadIdx.x / CG;  // channels cg*8..+7, tile pixels pg*8..+7
+    const int pr = (pg * 8) / tw, pc0 = (pg * 8) % tw;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
+        const int h0 = (trem / tiles_w) * th, w0 = (trem % tiles_w) * tw;
+        const float sc = in_scale ? in_scale[n] : 1.f;
+        __syncthreads();  // previous tile's readers of sx / red are done (and sw / sb are staged)
+        for (int i = threadIdx.x; i < CIN * ph * pw; i += blockDim.x) {
+            const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
+            const int hh = h0 + r - 1, ww = w0 + c - 1;
+            sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((long long)n * CIN + ci) * HW + (long long)hh * W + ww] * sc : 0.f;
+        }
+        __syncthreads();
+        float acc[8][8];
+        {
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + cg * 8), b1 = *reinterpret_cast<const float4*>(sb + cg * 8 + 4);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[0][j] = acc[1][j] = sb[cg * 32 + j];
-    int pr[2], pc[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int pix = pp + 64 * q;
-        pr[q] = pix / tw;
-        pc[q] = pix % tw;
-    }
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-        const int dr = tap / 3, dc = tap % 3;
-#pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-            const float x0 = sx[(ci * ph + pr[0] + dr) * pw + pc[0] + dc];
-            const float x1 = sx[(ci * ph + pr[1] + dr) * pw + pc[1] + dc];
-            const float4* wr = reinterpret_cast<const float4*>(sw + (tap * CIN + ci) * Cout + cg * 32);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 w4 = wr[q];
-                acc[0][4 * q] = fmaf(x0, w4.x, acc[0][4 * q]);
-                acc[0][4 * q + 1] = fmaf(x0, w4.y, acc[0][4 * q + 1]);
-                acc[0][4 * q + 2] = fmaf(x0, w4.z, acc[0][4 * q + 2]);
-                acc[0][4 * q + 3] = fmaf(x0, w4.w, acc[0][4 * q + 3]);
-                acc[1][4 * q] = fmaf(x1, w4.x, acc[1][4 * q]);
-                acc[1][4 * q + 1] = fmaf(x1, w4.y, acc[1][4 * q + 1]);
-                acc[1][4 * q + 2] = fmaf(x1, w4.z, acc[1][4 * q + 2]);
-                acc[1][4 * q + 3] = fmaf(x1, w4.w, acc[1][4 * q + 3]);
+            for (int j = 0; j < 8; ++j) {
+                acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b0.z; acc[j][3] = b0.w;
+                acc[j][4] = b1.x; acc[j][5] = b1.y; acc[j][6] = b1.z; acc[j][7] = b1.w;
             }
         }
-    }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const long long p = (long long)n * HW + (long long)(h0 + pr[q]) * W + w0 + pc[q];
-        bf16* o = out + p * Cout + cg * 32;
+        for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+            for (int dr = 0; dr < 3; ++dr) {
+                float xv[10];
+                const float* xr = sx + (ci * ph + pr + dr) * pw + pc0;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) xv[j] = xr[j];
+#pragma unroll
+                for (int dc = 0; dc < 3; ++dc) {
+                    const float* wr = sw + ((dr * 3 + dc) * CIN + ci) * Cout + cg * 8;
+                    const float4 w0v = *reinterpret_cast<const float4*>(wr), w1v = *reinterpret_cast<const float4*>(wr + 4);
+                    const float wv[8] = {w0v.x, w0v.y, w0v.z, w0v.w, w1v.x, w1v.y, w1v.z, w1v.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(xv[j + dc], wv[c], acc[j][c]);
+                }
+            }
+        }
+        float s1[8], s2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s1[c] = s2[c] = 0.f;
+        const long long p0 = (long long)n * HW + (long long)(h0 + pr) * W + w0 + pc0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = act_f(acc[q][v * 8 + j], act);
-            st8(o + v * 8, pack8(f));
+            for (int c = 0; c < 8; ++c) f[c] = act_f(acc[j][c], act);
+            const bf16x8 v = pack8(f);
+            st8(out + (p0 + j) * Cout + cg * 8, v);
+            if (stats) {
+                float r[8];
+                unpack8(v, r);  // statistics of the values the consumer reads (bf16-rounded)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    s1[c] += r[c];
+                    s2[c] = fmaf(r[c], r[c], s2[c]);
+                }
+            }
+        }
+        if (stats) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) red[pg * Cout + cg * 8 + c] = make_float2(s1[c], s2[c]);
+            __syncthreads();
+            for (int c = threadIdx.x; c < Cout; c += blockDim.x) {
+                float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {  // fixed order: deterministic, batch invariant
+                    const float2 v = red[g * Cout + c];
+                    a.x += v.x;
+                    a.y += v.y;
+                }
+                *reinterpret_cast<float2*>(stats + ((long long)tile * Cout + c) * 2) = a;
+            }
         }
     }
 }
 
-void conv3x3_first(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, int N, int Cin,
-                   int H, int W, int Cout, int act, cudaStream_t st) {
-    // requirements (checked by the plan builders): Cin == 3, Cout % 32 == 0, Cout <= 512, H*W % 128 == 0, W power of two
+void conv3x3_first(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, float* stats, int N,
+                   int Cin, int H, int W, int Cout, int act, cudaStream_t st) {
+    // requirements (checked by the plan builders): Cin == 3, Cout % 32 == 0, Cout <= 256, H*W % 128 == 0, W power of two >= 8
     const int tw = W < 128 ? W : 128;
     const int th = 128 / tw;
-    const int threads = 64 * (Cout / 32);
-    const size_t smem = (size_t)(9 * Cin * Cout + Cout + Cin * (th + 2) * (tw + 2)) * sizeof(float);
+    const int threads = 16 * (Cout / 8);
+    const int patch = (Cin * (th + 2) * (tw + 2) + 3) & ~3;
+    const size_t smem = (size_t)(9 * Cin * Cout + Cout + patch) * sizeof(float) + (size_t)16 * Cout * sizeof(float2);
     static bool configured = false;
+    static int num_sms = 148;
     if (!configured) {
         cudaFuncSetAttribute(conv3x3_first_k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    const int blocks = N * (H / th) * (W / tw);
-    conv3x3_first_k<3><<<blocks, threads, smem, st>>>(x, in_scale, w, b, out, H, W, Cout, act, th, tw);
+    const int ntiles = N * (H / th) * (W / tw);
+    const int per_sm = threads <= 256 ? 2 : 1;
+    int blocks = num_sms * per_sm;
+    if (blocks > ntiles) blocks = ntiles;
+    conv3x3_first_k<3><<<blocks, threads, smem, st>>>(x, in_scale, w, b, out, stats, H, W, Cout, act, th, tw, ntiles);
 }
 
 // One warp per output pixel; lanes stride over (tap, 8-channel vector) work items. Weights in smem [o][tap][C].

@@ -19,8 +19,9 @@ void cast_to_f32(const void* src, int src_is_half, float* dst, long long n, cuda
 
 // ---- first / last convolutions (3 <-> C channels; HBM bound) -------------------------------------------------------
 // x fp32 NCHW [N,Cin<=4,H,W] (optionally scaled by in_scale[n]) -> bf16 NHWC [N,H,W,Cout]; w fp32 OIHW; act = GemmAct.
-void conv3x3_first(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, int N, int Cin,
-                   int H, int W, int Cout, int act, cudaStream_t st);
+// stats (optional): GroupNorm partials of the output, [N][H*W/128][Cout][2] (sum, sumsq) like the GEMM epilogues write.
+void conv3x3_first(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, float* stats, int N,
+                   int Cin, int H, int W, int Cout, int act, cudaStream_t st);
 // h bf16 NHWC [N,H,W,C] -> fp32 NCHW [N,Cout<=4,H,W]
 void conv3x3_last(const bf16* h, const float* w, const float* b, float* out, int N, int C, int H, int W, int Cout,
                   cudaStream_t st);

@@ -201,9 +201,10 @@ def test_both_gemm_kernel_versions(ops, version):
         L.lib().dxmi_set_option(b"gemm_version", 2)
 
 
-@pytest.mark.parametrize("N,H,Cin,Cout", [(4, 16, 128, 256), (3, 32, 64, 128), (5, 8, 256, 192)])
+@pytest.mark.parametrize("N,H,Cin,Cout", [(4, 16, 128, 256), (3, 32, 64, 128), (5, 8, 256, 192), (5, 4, 256, 256), (24, 4, 128, 128)])
 def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
-    """The persistent kernel's fused statistics: per 32-row segment and column, (sum, sumsq) of the bf16 outputs."""
+    """The persistent kernel's fused statistics: per 16/32/64/128-row segment and column, (sum, sumsq) of the bf16 outputs
+    (16-row segments = one 4x4 image; ragged last tile at N=5)."""
     torch.manual_seed(8)
     dev = "cuda"
     x = nhwc(torch.randn(N, Cin, H, H, device=dev))
@@ -231,7 +232,7 @@ def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
         assert torch.allclose(stats[..., 0].sum(1), yf.sum(1), rtol=1e-4, atol=5e-3)
         assert torch.allclose(stats[..., 1].sum(1), (yf * yf).sum(1), rtol=1e-4, atol=5e-3)
         return
-    for seg in (32, 64, 128):
+    for seg in (16, 32, 64, 128):
         if (H * H) % seg:
             continue
         stats = torch.full((M // seg, Cout, 2), float("nan"), device=dev)
