@@ -77,6 +77,8 @@ class GemmDesc(C.Structure):
         ("gn_stats", C.c_void_p),
         ("gn_seg", C.c_int),
         ("gn_halo_P", C.c_int),
+        ("gate", C.c_void_p),
+        ("ldg", C.c_int),
     ]
 
 
@@ -106,6 +108,9 @@ SYMBOLS = {
     "dxmi_op_gn_ws_floats": (_I, [_I, _I, _I]),
     "dxmi_op_halo_tiles_per_image": (_I, [_I, _I]),
     "dxmi_op_attention": (_I, [_VP, _LL, _I, _I, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
+    "dxmi_op_pack_conv_weight_dgrad": (_I, [_VP, _I, _I, _I, _I, _VP, _LL, _LL, _VP]),
+    "dxmi_op_wgrad_ws_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
+    "dxmi_op_conv_wgrad": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _I, _I, _F, _VP, _VP]),
     "dxmi_last_error": (C.c_char_p, []),
     "dxmi_set_option": (_I, [C.c_char_p, _I]),
     "dxmi_set_debug_buffer": (_I, [_VP]),

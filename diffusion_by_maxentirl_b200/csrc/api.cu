@@ -6,6 +6,7 @@
 
 #include "attn_tc.cuh"
 #include "engine.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace dxmi;
 
@@ -435,6 +436,33 @@ int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, c
     if (!r) r = run_attn(op, (cudaStream_t)stream);
     if (r) set_err(attn_last_error());
     count_launches(1);
+    return r;
+}
+
+int dxmi_op_pack_conv_weight_dgrad(const void* w, int dtype, int Cout, int Cin, int taps, void* dst_bf16, long long ldk,
+                                   long long k_off, dxmi_stream_t stream) {
+    pack_conv_weight_dgrad(w, dtype == DXMI_F16, Cout, Cin, taps, (bf16*)dst_bf16, ldk, k_off, (cudaStream_t)stream);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+long long dxmi_op_wgrad_ws_floats(int N, int H, int W, int Cout, int Cin, int taps) {
+    WgradOp op;
+    // geometry only: the tensor maps are encoded over a dummy (aligned, never dereferenced) base address
+    if (prepare_wgrad((const void*)0x1000, (const void*)0x1000, N, H, W, Cout, Cin, taps, &op)) {
+        set_err(gemm_last_error());
+        return -1;
+    }
+    return (long long)op.partial_floats;
+}
+
+int dxmi_op_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, int Cin, int taps, float* grad_oihw,
+                       int Cin_total, int ci_off, float scale, float* ws, dxmi_stream_t stream) {
+    WgradOp op;
+    int r = prepare_wgrad(dy, x, N, H, W, Cout, Cin, taps, &op);
+    if (!r) r = run_wgrad(op, ws, grad_oihw, Cin_total, ci_off, scale, (cudaStream_t)stream);
+    if (r) set_err(gemm_last_error());
+    count_launches(2);
     return r;
 }
 

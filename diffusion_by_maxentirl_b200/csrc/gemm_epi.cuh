@@ -55,6 +55,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     const bool g_bm = MODE == EPI_GENERIC && p.bias != nullptr && p.bias_along_m;
     const bool g_sm = MODE == EPI_GENERIC && p.softmax != 0;
     const bool g_f32 = MODE == EPI_GENERIC && p.out_fp32 != 0;
+    const bool g_gate = MODE == EPI_GENERIC && p.gate != nullptr;
     const int g_act = MODE == EPI_GENERIC ? p.act : ACT_NONE;
     const bool has_bias = p.bias != nullptr && !(MODE == EPI_GENERIC && p.bias_along_m);
     const bool use_rv = MODE == EPI_ROWVEC || g_rv;
@@ -62,7 +63,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
 
     // ---- per-tile invariants: the 4 rows this thread finishes
     bool rok[4];
-    long long ooff[4], roff[4];
+    long long ooff[4], roff[4], goff[4];
     const float* rvp[4];
     float bm[4];
 #pragma unroll
@@ -86,16 +87,18 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         rok[i] = ok && p.dbg_mode != 2;
         ooff[i] = batch * p.out_batch_stride + r * p.ldo;
         roff[i] = use_res ? batch * p.res_batch_stride + r * p.ldr : 0;
+        goff[i] = g_gate ? r * p.ldg : 0;
         rvp[i] = (use_rv && rok[i]) ? p.rowvec + img * p.ldrv : nullptr;
         bm[i] = (g_bm && rok[i]) ? __ldg(p.bias + r) : 0.f;
     }
     float4 pf_bias = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 pf_rv[4];
-    uint2 pf_res[4];
+    uint2 pf_res[4], pf_gate[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         pf_rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         pf_res[i] = make_uint2(0u, 0u);
+        pf_gate[i] = make_uint2(0u, 0u);
     }
     auto prefetch = [&](int pcc) {
         const bool pok = pcc < n_total;
@@ -109,6 +112,11 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (rok[i] && pok) pf_res[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + roff[i] + pcc));
+        }
+        if (g_gate) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rok[i] && pok) pf_gate[i] = __ldg(reinterpret_cast<const uint2*>(p.gate + goff[i] + pcc));
         }
     };
     prefetch(col0 + cx.bu * 4);
@@ -209,6 +217,13 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 if (g_act != ACT_NONE) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) x[j] = act2(x[j], g_act);
+                }
+                if (g_gate) {
+                    // sign of the saved bf16 activation: positive -> slope 1, else 0.2
+                    x[0] *= __uint_as_float(pf_gate[i].x << 16) > 0.f ? 1.f : 0.2f;
+                    x[1] *= __uint_as_float(pf_gate[i].x & 0xffff0000u) > 0.f ? 1.f : 0.2f;
+                    x[2] *= __uint_as_float(pf_gate[i].y << 16) > 0.f ? 1.f : 0.2f;
+                    x[3] *= __uint_as_float(pf_gate[i].y & 0xffff0000u) > 0.f ? 1.f : 0.2f;
                 }
             }
             const bool ok = rok[i] && col_ok;

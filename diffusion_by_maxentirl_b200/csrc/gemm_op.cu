@@ -135,6 +135,8 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     p.residual = reinterpret_cast<const __nv_bfloat16*>(d.residual);
     p.ldr = d.ldr;
     p.res_batch_stride = d.res_batch_stride;
+    p.gate = reinterpret_cast<const __nv_bfloat16*>(d.gate);
+    p.ldg = d.ldg;
     p.act = d.act;
     p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
     p.softmax = d.softmax;
@@ -196,8 +198,8 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             return -13;
         }
         op->use_v2 = pair ? 2 : 1;
-    } else if (d.gn_stats) {
-        snprintf(g_op_err, sizeof g_op_err, "gn_stats requested but the persistent kernel does not support this GEMM");
+    } else if (d.gn_stats || d.gate) {
+        snprintf(g_op_err, sizeof g_op_err, "gn_stats / gate requested but the persistent kernel does not support this GEMM");
         return -12;
     }
     op->flops = 2.0 * (double)p.M_total * op->batch * (double)d.b_rows * (double)k_total;

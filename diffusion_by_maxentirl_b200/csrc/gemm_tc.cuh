@@ -51,6 +51,8 @@ struct ConvGemmParams {
     int ldrv;
     int rows_per_image;
     const __nv_bfloat16* residual;  // same indexing as out (ld = ldr), may be null
+    const __nv_bfloat16* gate;      // optional [rows, ldg]: out *= (gate > 0 ? 1 : 0.2)  (leaky-relu backward; generic epilogue)
+    int ldg;
     long long res_batch_stride;
     int ldr;
     int act;

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
         cx.brs0 = (lane >> 3) == 0;
         const bool leader = (cx.e == 0);
         // launch-uniform epilogue shape
-        const bool simple = !p.softmax && p.act == ACT_NONE && !p.out_fp32 && !(p.bias && p.bias_along_m);
+        const bool simple = !p.softmax && p.act == ACT_NONE && !p.out_fp32 && !(p.bias && p.bias_along_m) && !p.gate;
         int mode = EPI_GENERIC;
         if (simple && !p.residual && !p.rowvec) mode = EPI_BIAS;
         else if (simple && !p.residual && p.rowvec) mode = EPI_ROWVEC;

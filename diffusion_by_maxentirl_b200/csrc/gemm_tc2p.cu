@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
         cx.rt0 = (cx.ew & 3) * 32 + (cx.ew >> 2) * 16 + (lane >> 3);
         cx.bu = lane & 7;
         cx.brs0 = (lane >> 3) == 0;
-        const bool simple = !p.softmax && p.act == ACT_NONE && !p.out_fp32 && !(p.bias && p.bias_along_m);
+        const bool simple = !p.softmax && p.act == ACT_NONE && !p.out_fp32 && !(p.bias && p.bias_along_m) && !p.gate;
         int mode = EPI_GENERIC;
         if (simple && !p.residual && !p.rowvec) mode = EPI_BIAS;
         else if (simple && !p.residual && p.rowvec) mode = EPI_ROWVEC;

@@ -91,6 +91,30 @@ void pack_conv_weight(const void* w, int w_is_half, int Cout, int Cin, int kh, i
         pack_conv_weight_k<float><<<blocks, 256, 0, st>>>((const float*)w, Cout, Cin, kh * kw, c_off, c_cnt, dst, ldk, k_off);
 }
 
+// transposed + tap-flipped packing for the data gradient: dX = conv(dY, W') with W'[ci][tap'][co] = W[co][ci][taps-1-tap']
+template <typename T>
+__global__ void pack_conv_weight_dgrad_k(const T* __restrict__ w, int Cout, int Cin, int taps, bf16* __restrict__ dst,
+                                         long long ldk, long long k_off) {
+    const long long total = (long long)Cin * taps * Cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const long long r = i / Cout;
+        const int tap = (int)(r % taps);
+        const int ci = (int)(r / taps);
+        const float v = (float)w[((long long)co * Cin + ci) * taps + (taps - 1 - tap)];
+        dst[ci * ldk + k_off + (long long)tap * Cout + co] = __float2bfloat16_rn(v);
+    }
+}
+void pack_conv_weight_dgrad(const void* w, int w_is_half, int Cout, int Cin, int taps, bf16* dst, long long ldk, long long k_off,
+                            cudaStream_t st) {
+    const long long total = (long long)Cout * taps * Cin;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    if (w_is_half)
+        pack_conv_weight_dgrad_k<__half><<<blocks, 256, 0, st>>>((const __half*)w, Cout, Cin, taps, dst, ldk, k_off);
+    else
+        pack_conv_weight_dgrad_k<float><<<blocks, 256, 0, st>>>((const float*)w, Cout, Cin, taps, dst, ldk, k_off);
+}
+
 template <typename T>
 __global__ void cast_to_f32_k(const T* __restrict__ s, float* __restrict__ d, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)

@@ -15,6 +15,10 @@ typedef __nv_bfloat16 bf16;
 // for input channels c in [c_off, c_off + c_cnt).  tap = r * kw + s.
 void pack_conv_weight(const void* w, int w_is_half, int Cout, int Cin, int kh, int kw, int c_off, int c_cnt, bf16* dst,
                       long long ldk, long long k_off, cudaStream_t st);
+// data-gradient packing: dst[ci][k_off + tap' * Cout + co] = W[co][ci][taps-1-tap']  (transposed, taps flipped), so that
+// dX = the forward implicit-GEMM convolution of dY with these rows (3x3 pad 1 stride 1, or 1x1)
+void pack_conv_weight_dgrad(const void* w, int w_is_half, int Cout, int Cin, int taps, bf16* dst, long long ldk, long long k_off,
+                            cudaStream_t st);
 void cast_to_f32(const void* src, int src_is_half, float* dst, long long n, cudaStream_t st);
 
 // ---- first / last convolutions (3 <-> C channels; HBM bound) -------------------------------------------------------

@@ -66,6 +66,7 @@ def conv_gemm(
     gn_stats=None,
     gn_seg=32,
     gn_halo_P=0,
+    gate=None,
 ):
     """srcs: list of (tensor, C_used, ld) NHWC bf16 sources; segs: list of (src_index, taps)."""
     d = L.GemmDesc()
@@ -122,8 +123,47 @@ def conv_gemm(
         d.gn_stats = gn_stats.data_ptr()
         d.gn_seg = gn_seg
         d.gn_halo_P = gn_halo_P
+    if gate is not None:
+        assert gate.dtype == torch.bfloat16
+        d.gate = gate.data_ptr()
+        d.ldg = gate.shape[-1]
     L.check(L.lib().dxmi_op_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
+
+
+def pack_conv_weight_dgrad(parts):
+    """Data-gradient packing of OIHW conv weights: bf16 [Cin, K] with K = sum over parts of taps * Cout, taps flipped and
+    O/I transposed, so that dX = conv_gemm(dY sources, these rows).  `parts`: list of OIHW weights sharing Cin."""
+    cin = parts[0].shape[1]
+    K = sum(w.shape[2] * w.shape[3] * w.shape[0] for w in parts)
+    dst = torch.empty(cin, K, dtype=torch.bfloat16, device=parts[0].device)
+    k_off = 0
+    for w in parts:
+        w = w.contiguous()
+        assert w.shape[1] == cin and w.dtype in (torch.float16, torch.float32)
+        taps = w.shape[2] * w.shape[3]
+        dt = L.F16 if w.dtype == torch.float16 else L.F32
+        L.check(L.lib().dxmi_op_pack_conv_weight_dgrad(L.ptr(w), dt, w.shape[0], cin, taps, L.ptr(dst), K, k_off, L.stream_ptr()),
+                "pack_conv_weight_dgrad")
+        k_off += taps * w.shape[0]
+    return dst
+
+
+def conv_wgrad(dy, x, k, scale=1.0, grad=None, ci_off=0):
+    """Weight gradient of a k x k (k = 3: pad 1, stride 1; k = 1) convolution: dy NHWC bf16 [N,H,W,Cout], x NHWC bf16
+    [N,H,W,Cin] -> fp32 OIHW [Cout, Cin_total, k, k] (input channels ci_off .. ci_off + Cin of `grad` when given)."""
+    N, H, W, Cout = dy.shape
+    Cin = x.shape[-1]
+    assert dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and dy.is_contiguous() and x.is_contiguous()
+    if grad is None:
+        grad = torch.empty(Cout, Cin, k, k, dtype=torch.float32, device=dy.device)
+    n_ws = L.lib().dxmi_op_wgrad_ws_floats(N, H, W, Cout, Cin, k * k)
+    if n_ws < 0:
+        raise RuntimeError(L.lib().dxmi_last_error().decode())
+    ws = torch.empty(n_ws, dtype=torch.float32, device=dy.device)
+    L.check(L.lib().dxmi_op_conv_wgrad(L.ptr(dy), L.ptr(x), N, H, W, Cout, Cin, k * k, L.ptr(grad), grad.shape[1], ci_off,
+                                        float(scale), L.ptr(ws), L.stream_ptr()), "conv_wgrad")
+    return grad
 
 
 def group_norm(x1, gamma, beta, eps, silu, x2=None, film=None, groups=32):

@@ -149,6 +149,9 @@ typedef struct {
     int gn_seg;              /* rows per partial: 32, 64 or 128; must divide the rows of one image */
     int gn_halo_P;           /* > 0: the partials buffer is [N][gn_halo_P][b_rows][2], one partial per halo tile (3x3 convs on
                                 32/64-wide maps, see dxmi_op_halo_tiles_per_image); 0: row-segment partials */
+    const void* gate;        /* optional bf16 [rows, ldg]: out *= (gate > 0 ? 1 : 0.2) after everything else - the backward of
+                                leaky-relu(0.2) through the saved activation (modules.py:81,99 under autograd) */
+    int ldg;
 } dxmi_gemm_desc;
 
 int dxmi_op_conv_gemm(const dxmi_gemm_desc* d, dxmi_stream_t stream);
@@ -165,6 +168,20 @@ int dxmi_op_halo_tiles_per_image(int H, int W);
  * out bf16 [B, seq, ldo], head h at column 64h; scale multiplies the logits (d^-1/2). seq % 128 == 0. */
 int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
                       int heads, int seq, float scale, dxmi_stream_t stream);
+
+/* ---- backward operators (the training step differentiates through the value net, trainer.py:252-264,
+ * :320-326, :369-389) ---- */
+/* Packs an OIHW conv weight for the DATA gradient: dst[ci][k_off + tap' * Cout + co] = W[co][ci][taps-1-tap'] (bf16), so that
+ * dX = dxmi_op_conv_gemm(dY, these rows) for a 3x3 pad-1 stride-1 (taps = 9) or 1x1 (taps = 1) convolution. */
+int dxmi_op_pack_conv_weight_dgrad(const void* w, int dtype, int Cout, int Cin, int taps, void* dst_bf16, long long ldk,
+                                   long long k_off, dxmi_stream_t stream);
+/* WEIGHT gradient on the tensor cores: grad[co][ci_off + ci][tap] = scale * sum_p dY[p, co] * X[p + tap, ci]  (fp32 OIHW
+ * tensor with Cin_total input channels; dy bf16 NHWC [N,H,W,Cout], x bf16 NHWC [N,H,W,Cin]; Cout % 128 == 0,
+ * Cin in {64,128,192,256}; taps 9 (3x3, pad 1) or 1).  ws: dxmi_op_wgrad_ws_floats(...) fp32 scratch (split-K partials,
+ * reduced in a fixed order: deterministic). */
+long long dxmi_op_wgrad_ws_floats(int N, int H, int W, int Cout, int Cin, int taps);
+int dxmi_op_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, int Cin, int taps, float* grad_oihw,
+                       int Cin_total, int ci_off, float scale, float* ws, dxmi_stream_t stream);
 
 /* -------------------------------------------------------------------------------------------- misc */
 const char* dxmi_last_error(void);

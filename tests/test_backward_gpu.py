@@ -1,0 +1,93 @@
+"""Backward operators of the training step against torch autograd on the same bf16-rounded operands:
+tensor-core weight gradient (MN-major UMMA operands, split-K), data gradient (forward implicit GEMM on transposed, tap-flipped
+weights) with the fused leaky-relu gate.  fp32 outputs must agree to fp32 accumulation round-off (rel-L2 <= 2e-5); bf16
+outputs to the bf16 rounding floor (4e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffusion_by_maxentirl_b200 import ops as o
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return o
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,k", [(4, 32, 128, 128, 3), (6, 16, 128, 256, 3), (5, 8, 256, 256, 3), (7, 4, 256, 256, 3),
+                                            (3, 32, 128, 128, 1), (4, 16, 128, 256, 1), (2, 64, 192, 128, 3), (128, 4, 64, 128, 3)])
+def test_conv_wgrad(ops, N, H, Cin, Cout, k):
+    torch.manual_seed(20)
+    dev = "cuda"
+    x = nhwc(torch.randn(N, Cin, H, H, device=dev))
+    dy = nhwc(torch.randn(N, Cout, H, H, device=dev))
+    g = ops.conv_wgrad(dy, x, k, scale=0.5)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    w = torch.zeros(Cout, Cin, k, k, device=dev, requires_grad=True)
+    y = F.conv2d(xr, w, None, padding=k // 2)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    err = rel_l2(g, 0.5 * w.grad)
+    print(f"wgrad N={N} H={H} {Cin}->{Cout} k={k}: rel-L2 {err:.2e}")
+    assert err < 2e-5
+    # deterministic (fixed split-K reduction order)
+    g2 = ops.conv_wgrad(dy, x, k, scale=0.5)
+    assert torch.equal(g, g2)
+
+
+def test_conv_wgrad_channel_slice(ops):
+    """Two sources (torch.cat along channels): each fills its slice of the OIHW gradient."""
+    torch.manual_seed(21)
+    dev = "cuda"
+    N, H, Ca, Cb, Cout = 3, 16, 128, 64, 128
+    xa, xb = nhwc(torch.randn(N, Ca, H, H, device=dev)), nhwc(torch.randn(N, Cb, H, H, device=dev))
+    dy = nhwc(torch.randn(N, Cout, H, H, device=dev))
+    g = torch.full((Cout, Ca + Cb, 1, 1), float("nan"), device=dev)
+    ops.conv_wgrad(dy, xa, 1, grad=g, ci_off=0)
+    ops.conv_wgrad(dy, xb, 1, grad=g, ci_off=Ca)
+    ref = torch.einsum("nhwo,nhwi->oi", dy.float(), torch.cat([xa, xb], -1).float())
+    assert rel_l2(g.view(Cout, -1), ref) < 2e-5
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout", [(4, 32, 128, 128), (5, 8, 128, 256), (6, 4, 256, 256)])
+def test_conv_dgrad_with_skip_and_gate(ops, N, H, Cin, Cout):
+    """dX = conv3x3^T(dZ1, W1) + conv1x1^T(dO, Ws), then the leaky-relu gate of the saved block input - one GEMM."""
+    torch.manual_seed(22)
+    dev = "cuda"
+    w1 = torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin**0.5)
+    ws = torch.randn(Cout, Cin, 1, 1, device=dev) / Cin**0.5
+    dz1 = nhwc(torch.randn(N, Cout, H, H, device=dev))
+    do = nhwc(torch.randn(N, Cout, H, H, device=dev))
+    h_in = nhwc(torch.randn(N, Cin, H, H, device=dev))
+    wp = ops.pack_conv_weight_dgrad([w1, ws])
+    srcs, segs = [(dz1, Cout, Cout), (do, Cout, Cout)], [(0, 9), (1, 1)]
+    y32 = ops.conv_gemm(srcs, segs, wp, N, H, H, out_fp32=True)
+    w1q, wsq = w1.to(torch.bfloat16).float(), ws.to(torch.bfloat16).float()
+    ref = F.conv_transpose2d(dz1.float().permute(0, 3, 1, 2), w1q, padding=1) + F.conv_transpose2d(do.float().permute(0, 3, 1, 2), wsq)
+    ref = ref.permute(0, 2, 3, 1)
+    assert rel_l2(y32.view(N, H, H, Cin), ref) < 2e-5
+    yg = ops.conv_gemm(srcs, segs, wp, N, H, H, gate=h_in)
+    gate = torch.where(h_in.float() > 0, 1.0, 0.2)
+    assert rel_l2(yg.view(N, H, H, Cin), ref * gate) < 4e-3
+    # identity skip: residual = dO, same gate, with column sums (bias gradient of the next wgrad) from the fused statistics
+    if Cin == Cout:
+        wp1 = ops.pack_conv_weight_dgrad([w1])
+        seg = 16 if H == 4 else 64
+        stats = torch.zeros(N * H * H // seg, Cin, 2, device=dev)
+        yr = ops.conv_gemm([(dz1, Cout, Cout)], [(0, 9)], wp1, N, H, H, residual=do, gate=h_in, gn_stats=stats, gn_seg=seg)
+        ref2 = (F.conv_transpose2d(dz1.float().permute(0, 3, 1, 2), w1q, padding=1).permute(0, 2, 3, 1) + do.float()) * gate
+        assert rel_l2(yr.view(N, H, H, Cin), ref2) < 4e-3
+        assert torch.allclose(stats[..., 0].sum(0), yr.float().sum(0), rtol=1e-4, atol=2e-2)
