@@ -245,6 +245,7 @@ def main():
         net, sampler, value, sd, vsd = build_ddpm(T, device=dev)
         labels = None
 
+        @torch.no_grad()
         def rollout(noise):  # noise [T+1, B, C, H, W] on the device
             d = sampler.sample(B, device=dev, noise=noise)
             return d, value(d["sample"], T)
@@ -252,6 +253,7 @@ def main():
         net, sampler, sd = build_edm(EDM_LSUN_CFG, T, device=dev, stochastic_last=True, rho=4.0)
         value, labels = None, None
 
+        @torch.no_grad()
         def rollout(noise):
             return sampler.sample(B, device=dev, x0=noise[0] * 80.0, noise=noise[1:]), None
     else:
@@ -264,6 +266,7 @@ def main():
         value.to(dev).eval()
         labels = torch.randint(0, 1000, (B,), generator=g).to(dev)
 
+        @torch.no_grad()
         def rollout(noise):  # noise[0] is x_0 / sigma_max
             d = sampler.sample(B, device=dev, i_class=labels, x0=noise[0] * 80.0, noise=noise[1:])
             return d, value(d["sample"], T)

@@ -287,6 +287,88 @@ int dxmi_value_forward(dxmi_net_t net, const float* x, float* out, int B, dxmi_s
     return run_plan(net->net, p, (cudaStream_t)stream);
 }
 
+// ---- value-net training (engine_train.cu)
+static int run_ops(const std::vector<std::function<int(cudaStream_t)>>& ops, const std::vector<std::string>& names, long long launches,
+                   cudaStream_t st) {
+    static const bool debug_sync = getenv("DXMI_DEBUG_SYNC") != nullptr;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        int r = ops[i](st);
+        if (!r && debug_sync) r = (int)cudaStreamSynchronize(st);
+        if (r) {
+            snprintf(g_api_err, sizeof g_api_err, "op %zu/%zu '%s' failed (%d): %s | %s", i, ops.size(),
+                     i < names.size() ? names[i].c_str() : "?", r, cudaGetErrorString((cudaError_t)r), gemm_op_last_error());
+            return r;
+        }
+    }
+    count_launches(launches);
+    return 0;
+}
+
+static Plan* get_train_plan(Net& n, int B, cudaStream_t st) {
+    auto it = n.train_plans.find(B);
+    if (it != n.train_plans.end()) return it->second.get();
+    cudaSetDevice(n.device);
+    std::unique_ptr<Plan> p(new Plan());
+    p->B = B;
+    const size_t jobs_before = n.pack_jobs.size();
+    int r = build_train_plan(n, *p);
+    if (r) {
+        set_err(engine_last_error());
+        if (p->arena) cudaFree(p->arena);
+        return nullptr;
+    }
+    // the backward introduces new packed (transposed) weights: pack them now
+    for (size_t j = jobs_before; j < n.pack_jobs.size(); ++j) n.pack_jobs[j](st);
+    Plan* raw = p.get();
+    n.train_plans[B] = std::move(p);
+    return raw;
+}
+
+int dxmi_bind_grad(dxmi_net_t net, const char* key, float* dev_ptr) {
+    if (!net || !key) return -1;
+    Net& n = net->net;
+    if (n.expect.find(key) == n.expect.end()) {
+        snprintf(g_api_err, sizeof g_api_err, "dxmi_bind_grad: '%s' is not a state_dict key of this architecture", key);
+        return -5;
+    }
+    n.grad[key] = dev_ptr;
+    return 0;
+}
+
+int dxmi_value_forward_train(dxmi_net_t net, const float* x, float* out, int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_value_forward_train: handle not finalized");
+        return -1;
+    }
+    Plan* p = get_train_plan(net->net, B, (cudaStream_t)stream);
+    if (!p) return -3;
+    p->x = x;
+    p->out = out;
+    int r = run_ops(p->ops, p->op_names, p->launches_per_run, (cudaStream_t)stream);
+    p->fwd_valid = r == 0;
+    return r;
+}
+
+int dxmi_value_backward(dxmi_net_t net, const float* x, const float* dout, float* dx, int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_value_backward: handle not finalized");
+        return -1;
+    }
+    auto it = net->net.train_plans.find(B);
+    if (it == net->net.train_plans.end() || !it->second->fwd_valid) {
+        set_err("dxmi_value_backward: no saved activations for this batch size (call dxmi_value_forward_train first; one "
+                "backward per forward)");
+        return -4;
+    }
+    Plan* p = it->second.get();
+    p->x = x;
+    p->dout = dout;
+    p->dx = dx;
+    int r = run_ops(p->bwd_ops, p->bwd_names, p->bwd_launches, (cudaStream_t)stream);
+    p->fwd_valid = false;
+    return r;
+}
+
 int dxmi_var_step(const float* x, const float* eps, const float* z, const float* a, const float* c, const float* sigma,
                   float* x_next, float* mean, float* control, float* logp, int B, int chw, dxmi_stream_t stream) {
     if (chw % 4) {

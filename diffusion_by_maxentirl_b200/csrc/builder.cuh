@@ -250,8 +250,15 @@ struct Builder {
 
     // ---------------------------------------------------------------- op emission
     std::string cur_label;  // set by the network builders before emitting a block
+    bool emit_bwd = false;  // training plans: ops go to the backward list
     void op(std::function<int(cudaStream_t)> f, int launches = 1) {
         if (dry) return;
+        if (emit_bwd) {
+            plan.bwd_ops.push_back(std::move(f));
+            plan.bwd_names.push_back(cur_label);
+            plan.bwd_launches += launches;
+            return;
+        }
         plan.ops.push_back(std::move(f));
         plan.op_names.push_back(cur_label);
         plan.launches_per_run += launches;

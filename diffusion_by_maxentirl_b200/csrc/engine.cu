@@ -29,6 +29,8 @@ Net::~Net() {
     for (void* p : owned) cudaFree(p);
     for (auto& kv : plans)
         if (kv.second && kv.second->arena) cudaFree(kv.second->arena);
+    for (auto& kv : train_plans)
+        if (kv.second && kv.second->arena) cudaFree(kv.second->arena);
 }
 
 // ================================================================================================ specs

@@ -44,6 +44,13 @@ struct Plan {
     const float* t = nullptr;
     const int64_t* y = nullptr;
     float* out = nullptr;
+    // training plans (engine_train.cu): backward launch list + its per-call I/O
+    std::vector<std::function<int(cudaStream_t)>> bwd_ops;
+    std::vector<std::string> bwd_names;
+    long long bwd_launches = 0;
+    const float* dout = nullptr;  // [B] gradient of the network output
+    float* dx = nullptr;          // optional [B,Cin,H,W] fp32 gradient w.r.t. the input
+    bool fwd_valid = false;       // a training forward has filled the saved activations
     long long launches_per_run = 0;
     double gemm_flops = 0;
     // rollout scratch (allocated with the plan)
@@ -64,6 +71,8 @@ struct Net {
     std::vector<void*> owned;
     bool finalized = false;
     std::map<int, std::unique_ptr<Plan>> plans;
+    std::map<int, std::unique_ptr<Plan>> train_plans;      // forward-with-saved-activations + backward, per batch size
+    std::unordered_map<std::string, float*> grad;          // dxmi_bind_grad: fp32 gradient buffer per state_dict key (or null)
     ~Net();
 };
 
@@ -74,6 +83,7 @@ void spec_adm(Net& net);
 
 // plan builders (dry = size-only pass)
 int build_plan(Net& net, Plan& plan);
+int build_train_plan(Net& net, Plan& plan);  // engine_train.cu (IGEBM value net)
 
 const char* engine_last_error();
 void engine_set_error(const char* fmt, ...);

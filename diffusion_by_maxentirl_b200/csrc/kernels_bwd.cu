@@ -1,0 +1,230 @@
+#include "kernels_bwd.cuh"
+
+namespace dxmi {
+
+namespace {
+struct alignas(16) bf16x8 {
+    __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(p.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+    bf16x8 p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return p;
+}
+}  // namespace
+
+// ================================================================================================ value head
+// one CTA per image; thread = 8-channel vector x pixel lane
+__global__ void __launch_bounds__(256) value_head_bwd_k(const bf16* __restrict__ h, const float* __restrict__ dout,
+                                                       const float* __restrict__ lin_w, const float* __restrict__ scale_w,
+                                                       bf16* __restrict__ dz, float* __restrict__ S, int HW, int C) {
+    extern __shared__ float sred[];  // [PL][C]
+    const int n = blockIdx.x;
+    const int CV = C / 8, PL = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const float g = dout[n] * (scale_w ? scale_w[0] : 1.f);
+    float s[8], w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s[j] = 0.f;
+        w[j] = g * lin_w[cv * 8 + j];
+    }
+    if (pl < PL) {
+        for (int p = pl; p < HW; p += PL) {
+            const long long off = ((long long)n * HW + p) * C + cv * 8;
+            float f[8], d[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(h + off), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += fmaxf(f[j], 0.f);
+                d[j] = f[j] > 0.f ? w[j] : 0.f;
+            }
+            *reinterpret_cast<bf16x8*>(dz + off) = pack8(d);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sred[pl * C + cv * 8 + j] = s[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int q = 0; q < PL; ++q) a += sred[q * C + c];
+        S[(long long)n * C + c] = a;
+    }
+}
+void value_head_bwd(const bf16* h, const float* dout, const float* lin_w, const float* scale_w, bf16* dz, float* S, int N, int HW,
+                    int C, cudaStream_t st) {
+    const int PL = 256 / (C / 8);
+    value_head_bwd_k<<<N, 256, (size_t)PL * C * sizeof(float), st>>>(h, dout, lin_w, scale_w, dz, S, HW, C);
+}
+
+// one CTA; thread c loops over the images in order
+__global__ void __launch_bounds__(256) value_head_param_grads_k(const float* __restrict__ S, const float* __restrict__ dout,
+                                                               const float* __restrict__ lin_w, const float* __restrict__ lin_b,
+                                                               const float* __restrict__ scale_w, float* g_lin_w, float* g_lin_b,
+                                                               float* g_scale_w, float* g_scale_b, int N, int C) {
+    __shared__ float spre[1024];
+    const float sw = scale_w ? scale_w[0] : 1.f;
+    // pre[n] = S[n,:] . lin_w + lin_b  (one warp per image, fixed lane order)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = warp; n < N; n += 8) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(S[(long long)n * C + c], lin_w[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) spre[n] = a + lin_b[0];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int n = 0; n < N; ++n) a = fmaf(dout[n] * sw, S[(long long)n * C + c], a);
+        if (g_lin_w) g_lin_w[c] = a;
+    }
+    if (threadIdx.x == 0) {
+        float gb = 0.f, gsw = 0.f, gsb = 0.f;
+        for (int n = 0; n < N; ++n) {
+            gb += dout[n] * sw;
+            gsw = fmaf(dout[n], spre[n], gsw);
+            gsb += dout[n];
+        }
+        if (g_lin_b) g_lin_b[0] = gb;
+        if (g_scale_w) g_scale_w[0] = gsw;
+        if (g_scale_b) g_scale_b[0] = gsb;
+    }
+}
+void value_head_param_grads(const float* S, const float* dout, const float* lin_w, const float* lin_b, const float* scale_w,
+                            float* g_lin_w, float* g_lin_b, float* g_scale_w, float* g_scale_b, int N, int C, cudaStream_t st) {
+    value_head_param_grads_k<<<1, 256, 0, st>>>(S, dout, lin_w, lin_b, scale_w, g_lin_w, g_lin_b, g_scale_w, g_scale_b, N, C);
+}
+
+// ================================================================================================ pooling
+__global__ void avgpool2_bwd_k(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int CV) {
+    const long long total = (long long)N * H * W * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long r = i / CV;
+        const int x = (int)(r % W);
+        r /= W;
+        const int y = (int)(r % H);
+        const int n = (int)(r / H);
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(dy + ((((long long)n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * CV + cv) * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= 0.25f;
+        *reinterpret_cast<bf16x8*>(dx + i * 8) = pack8(f);
+    }
+}
+void avgpool2_bwd(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaStream_t st) {
+    const long long total = (long long)N * H * W * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 2368) blocks = 2368;
+    avgpool2_bwd_k<<<(int)blocks, 256, 0, st>>>(dy, dx, N, H, W, C / 8);
+}
+
+// ================================================================================================ column sums
+static int colsum_ctas(long long rows) {
+    long long c = (rows + 255) / 256;
+    if (c > 296) c = 296;
+    if (c < 1) c = 1;
+    return (int)c;
+}
+long long colsum_ws_floats(long long rows, int C) { return (long long)colsum_ctas(rows) * C; }
+
+__global__ void __launch_bounds__(256) colsum_bf16_k(const bf16* __restrict__ x, long long rows, int C, float* __restrict__ ws) {
+    extern __shared__ float sred[];  // [PL][C]
+    const int CV = C / 8, PL = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const long long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = blockIdx.x * per;
+    long long r1 = r0 + per;
+    if (r1 > rows) r1 = rows;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (pl < PL) {
+        for (long long r = r0 + pl; r < r1; r += PL) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(x + r * C + cv * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sred[pl * C + cv * 8 + j] = s[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int q = 0; q < PL; ++q) a += sred[q * C + c];
+        ws[(long long)blockIdx.x * C + c] = a;
+    }
+}
+// out[m] = sum_r ws[r][m]
+__global__ void reduce_rows_f32_k(const float* __restrict__ ws, int R, int M, float* __restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float a = 0.f;
+    for (int r = 0; r < R; ++r) a += ws[(long long)r * M + m];
+    out[m] = a;
+}
+void colsum_bf16(const bf16* x, long long rows, int C, float* ws, float* out, cudaStream_t st) {
+    const int ctas = colsum_ctas(rows);
+    const int PL = 256 / (C / 8);
+    colsum_bf16_k<<<ctas, 256, (size_t)PL * C * sizeof(float), st>>>(x, rows, C, ws);
+    reduce_rows_f32_k<<<(C + 127) / 128, 128, 0, st>>>(ws, ctas, C, out);
+}
+
+// ================================================================================================ first conv wgrad
+// one CTA per image, one thread per output channel: 27 running sums over the image's pixels; x patch in smem (zero padded)
+__global__ void conv_first_wgrad_k(const bf16* __restrict__ dz, const float* __restrict__ x, float* __restrict__ ws, int H, int W,
+                                   int Cout) {
+    extern __shared__ float sx[];  // [3][H+2][W+2]
+    const int n = blockIdx.x;
+    const int pw = W + 2, ph = H + 2;
+    for (int i = threadIdx.x; i < 3 * ph * pw; i += blockDim.x) {
+        const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
+        const int hh = r - 1, ww = c - 1;
+        sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)n * 3 + ci) * H + hh) * W + ww] : 0.f;
+    }
+    __syncthreads();
+    const int co = threadIdx.x;
+    if (co >= Cout) return;
+    float acc[27];
+#pragma unroll
+    for (int j = 0; j < 27; ++j) acc[j] = 0.f;
+    const bf16* dp = dz + (long long)n * H * W * Cout + co;
+    for (int h = 0; h < H; ++h) {
+        for (int w = 0; w < W; ++w) {
+            const float d = __bfloat162float(dp[(long long)(h * W + w) * Cout]);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) acc[ci * 9 + r * 3 + q] = fmaf(d, sx[(ci * ph + h + r) * pw + w + q], acc[ci * 9 + r * 3 + q]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 27; ++j) ws[((long long)n * Cout + co) * 27 + j] = acc[j];
+}
+void conv_first_wgrad(const bf16* dz, const float* x, float* ws, float* grad, int N, int H, int W, int Cout, cudaStream_t st) {
+    const size_t smem = (size_t)3 * (H + 2) * (W + 2) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_first_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        configured = true;
+    }
+    const int threads = (Cout + 31) / 32 * 32;
+    conv_first_wgrad_k<<<N, threads, smem, st>>>(dz, x, ws, H, W, Cout);
+    const int M = Cout * 27;
+    reduce_rows_f32_k<<<(M + 127) / 128, 128, 0, st>>>(ws, N, M, grad);
+}
+
+}  // namespace dxmi

@@ -30,6 +30,7 @@ class GraphedRollout:
         with torch.cuda.graph(self.graph):
             self.out = self._run()
 
+    @torch.no_grad()
     def _run(self):
         if self.edm:
             d = self.sampler.sample(self.B, self.device, i_class=self.labels, x0=self.noise[0] * self.sampler.sigma_max,

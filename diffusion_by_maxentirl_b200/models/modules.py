@@ -13,6 +13,54 @@ def process_single_t(x, t):
     return t
 
 
+class _ValueNetFunction(torch.autograd.Function):
+    """`loss.backward()` through the value net on the B200 path (trainer.py:252-264, :320-326, :369-389): forward keeps the
+    activations inside the handle's training plan (dxmi_value_forward_train), backward is one dxmi_value_backward call that
+    writes every parameter gradient (tensor-core wgrad / dgrad kernels) and, if the input requires it, d loss / d x."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        h = module._ensure_handle(x.device)
+        B = x.shape[0]
+        xc = x.detach().contiguous().float()
+        out = torch.empty(B, 1, device=x.device)
+        L.check(L.lib().dxmi_value_forward_train(h, L.ptr(xc), L.ptr(out), B, L.stream_ptr()), "dxmi_value_forward_train")
+        ctx.module, ctx.B = module, B
+        ctx.x = xc
+        ctx.token = module._train_token = object()  # identifies the forward whose activations the plan holds
+        ctx.need_dx = x.requires_grad
+        ctx.need_param = [p.requires_grad for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        m = ctx.module
+        if m._train_token is not ctx.token:
+            raise RuntimeError(
+                "B200 value net: backward() of a forward whose saved activations were overwritten by a later grad-enabled "
+                "forward at the same batch size (the plan keeps one set per batch size; run forward/backward pairs in order)")
+        h = m._ensure_handle(ctx.x.device)
+        lib = L.lib()
+        keys = m._keys
+        sizes = [m._param(k).numel() for k in keys]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=ctx.x.device)
+        grads, off = [], 0
+        for k, n, need in zip(keys, sizes, ctx.need_param):
+            g = flat[off:off + n]
+            off += n
+            L.check(lib.dxmi_bind_grad(h, k.encode(), L.ptr(g) if need else None), f"bind_grad {k}")
+            grads.append(g.view(m._param(k).shape) if need else None)
+        dx = torch.empty_like(ctx.x) if ctx.need_dx else None
+        d = dout.detach().contiguous().float().view(-1)
+        L.check(lib.dxmi_value_backward(h, L.ptr(ctx.x), L.ptr(d), L.ptr(dx) if dx is not None else None, ctx.B,
+                                        L.stream_ptr()), "dxmi_value_backward")
+        m._train_token = None
+        for k in keys:
+            lib.dxmi_bind_grad(h, k.encode(), None)
+        grads = [g.to(m._param(k).dtype) if g is not None else None for g, k in zip(grads, keys)]
+        return (None, dx, *grads)
+
+
 class IGEBMEncoderV2(NativeNet):
     """conv3 -> lrelu -> 6 ResBlockV2 -> relu -> sum over HW -> Linear(2nh, 1) -> Linear(1, 1); `forward(x)` -> [B, 1].
     Only the configuration every DxMI YAML uses is built (no spectral norm, no class embedding, keepdim=False,
@@ -33,6 +81,7 @@ class IGEBMEncoderV2(NativeNet):
         self.keepdim = keepdim
         self.learn_out_scale = learn_out_scale
         self.pre_activation = None
+        self._train_token = None
         self._by_res = {}
 
     def forward(self, input, y=None):
@@ -44,6 +93,14 @@ class IGEBMEncoderV2(NativeNet):
             # the plan is resolution specific: (re)create the handle for this input size
             self.release()
             self._desc.resolution = H
+        params = [self._param(k) for k in self._keys]
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
+            if self._desc.resolution != H:
+                self.release()
+                self._desc.resolution = H
+            out = _ValueNetFunction.apply(self, input, *params)
+            self.pre_activation = out
+            return out
         h = self._ensure_handle(input.device)
         x = input.detach().contiguous().float()
         out = torch.empty(B, 1, device=x.device)

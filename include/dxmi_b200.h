@@ -169,6 +169,15 @@ int dxmi_op_halo_tiles_per_image(int H, int W);
 int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
                       int heads, int seq, float scale, dxmi_stream_t stream);
 
+/* ---- value-net training (trainer.py:244-264 energy update, :276-326 TD updates, :369-389 value term of the
+ * sampler loss): what `loss.backward()` does underneath TimeIndependentValue.  bf16 mode only. ---- */
+/* fp32 gradient buffer (state_dict shape) for one key; the backward WRITES it (the caller accumulates); NULL = skip this key. */
+int dxmi_bind_grad(dxmi_net_t net, const char* key, float* dev_ptr);
+/* dxmi_value_forward that keeps the activations of this batch for one dxmi_value_backward call (same B, same x). */
+int dxmi_value_forward_train(dxmi_net_t net, const float* x, float* out, int B, dxmi_stream_t stream);
+/* dout [B] fp32 = d loss / d out; fills every bound gradient and, if dx != NULL, dx [B,3,H,W] fp32 = d loss / d x. */
+int dxmi_value_backward(dxmi_net_t net, const float* x, const float* dout, float* dx, int B, dxmi_stream_t stream);
+
 /* ---- backward operators (the training step differentiates through the value net, trainer.py:252-264,
  * :320-326, :369-389) ---- */
 /* Packs an OIHW conv weight for the DATA gradient: dst[ci][k_off + tap' * Cout + co] = W[co][ci][taps-1-tap'] (bf16), so that

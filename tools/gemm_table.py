@@ -12,6 +12,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
+torch.set_grad_enabled(False)
+
 from common import EDM_IN64_CFG, build_ddpm, build_edm  # noqa: E402
 from diffusion_by_maxentirl_b200 import _lib as L  # noqa: E402
 

@@ -13,6 +13,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 
+torch.set_grad_enabled(False)
+
 from common import build_ddpm  # noqa: E402
 
 ap = argparse.ArgumentParser()
