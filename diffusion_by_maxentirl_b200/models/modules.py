@@ -95,9 +95,9 @@ class IGEBMEncoderV2(NativeNet):
             self._desc.resolution = H
         params = [self._param(k) for k in self._keys]
         if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params)):
-            if self._desc.resolution != H:
-                self.release()
-                self._desc.resolution = H
+            if self.precision != "bf16":
+                raise RuntimeError("B200 value net: the fp32 mode is inference-only (validation against the reference's fp32 "
+                                   "path); call it under torch.no_grad(), or use set_precision('bf16') to train")
             out = _ValueNetFunction.apply(self, input, *params)
             self.pre_activation = out
             return out

@@ -18,6 +18,18 @@ TOL_STEP = 1e-5
 TOL_ROLLOUT = 1e-5
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    with torch.no_grad():  # the fp32 mode is inference-only
+        yield
+
+
+def test_fp32_value_net_refuses_autograd(ddpm10_fp32):
+    net, sampler, value, sd, vsd = ddpm10_fp32
+    with torch.enable_grad(), pytest.raises(RuntimeError, match="inference-only"):
+        value(torch.randn(2, 3, 32, 32, device="cuda"), 0)
+
+
 @pytest.fixture(scope="module")
 def ddpm10_fp32():
     net, sampler, value, sd, vsd = build_ddpm(10)

@@ -122,3 +122,19 @@ def test_input_gradient_only_and_stale_forward():
     b.sum().backward()
     with pytest.raises(RuntimeError, match="saved activations"):
         a.sum().backward()
+
+
+def test_ddp_gradient_allreduce_two_gpus():
+    """configs[3] 'DDP all-reduce': needs >= 2 GPUs on the box (skipped on the single-GPU tier; run with gpurun --gpus 2)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "ddp_value_train.py")], capture_output=True, text=True,
+                       timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "OK" in r.stdout
