@@ -56,9 +56,9 @@ struct IgebmTrainBuilder : Builder {
 
     void wgrad(const bf16* dy, const bf16* x, int H, int W, int Cout, int Cin, int taps, const std::string& wkey) {
         if (dry) {
-            // worst-case workspace: S * Cout * taps * Cin floats with S <= ceil(296 / base items) + 1
+            // worst-case workspace: S * Cout * taps * Cin floats with S <= 148 / base items (prepare_wgrad)
             const int base = (Cout / 128) * taps;
-            const size_t S = (296 + base - 1) / base + 1;
+            const size_t S = 148 / base + 1;
             scratch(4, S * Cout * taps * Cin * sizeof(float));
             return;
         }
@@ -281,7 +281,7 @@ struct IgebmTrainBuilder : Builder {
         cur_label = "bwd conv1";
         bias_grad(dZ, (long long)B * R * R, nh, "conv1.bias");
         {
-            float* ws = (float*)scratch(4, (size_t)B * nh * 27 * sizeof(float));
+            float* ws = (float*)scratch(4, (size_t)B * (R / 4) * nh * 27 * sizeof(float));
             float** g = gslot("conv1.weight");
             const bf16* dz = dZ;
             op([=](cudaStream_t st) {

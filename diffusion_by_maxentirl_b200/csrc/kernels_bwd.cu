@@ -83,10 +83,16 @@ __global__ void __launch_bounds__(256) value_head_param_grads_k(const float* __r
         if (lane == 0) spre[n] = a + lin_b[0];
     }
     __syncthreads();
+    // d lin_w: 4 independent partial sums per channel (images n = j mod 4), combined in a fixed order
     for (int c = threadIdx.x; c < C; c += 256) {
-        float a = 0.f;
-        for (int n = 0; n < N; ++n) a = fmaf(dout[n] * sw, S[(long long)n * C + c], a);
-        if (g_lin_w) g_lin_w[c] = a;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        int n = 0;
+        for (; n + 4 <= N; n += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = fmaf(dout[n + j] * sw, S[(long long)(n + j) * C + c], a[j]);
+        }
+        for (; n < N; ++n) a[0] = fmaf(dout[n] * sw, S[(long long)n * C + c], a[0]);
+        if (g_lin_w) g_lin_w[c] = (a[0] + a[1]) + (a[2] + a[3]);
     }
     if (threadIdx.x == 0) {
         float gb = 0.f, gsw = 0.f, gsb = 0.f;
@@ -166,31 +172,43 @@ __global__ void __launch_bounds__(256) colsum_bf16_k(const bf16* __restrict__ x,
         ws[(long long)blockIdx.x * C + c] = a;
     }
 }
-// out[m] = sum_r ws[r][m]
-__global__ void reduce_rows_f32_k(const float* __restrict__ ws, int R, int M, float* __restrict__ out) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= M) return;
+// out[m] = sum_r ws[r][m].  Block = 32 columns x 8 row lanes: row lane j sums rows j, j+8, ... (coalesced 128-byte reads),
+// then the 8 lanes are combined through smem in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) reduce_rows_f32_k(const float* __restrict__ ws, int R, int M, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int col = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int m = blockIdx.x * 32 + col;
     float a = 0.f;
-    for (int r = 0; r < R; ++r) a += ws[(long long)r * M + m];
-    out[m] = a;
+    if (m < M)
+        for (int r = rl; r < R; r += 8) a += ws[(long long)r * M + m];
+    red[rl][col] = a;
+    __syncthreads();
+    if (rl == 0 && m < M) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += red[j][col];
+        out[m] = s;
+    }
 }
 void colsum_bf16(const bf16* x, long long rows, int C, float* ws, float* out, cudaStream_t st) {
     const int ctas = colsum_ctas(rows);
     const int PL = 256 / (C / 8);
     colsum_bf16_k<<<ctas, 256, (size_t)PL * C * sizeof(float), st>>>(x, rows, C, ws);
-    reduce_rows_f32_k<<<(C + 127) / 128, 128, 0, st>>>(ws, ctas, C, out);
+    reduce_rows_f32_k<<<(C + 31) / 32, 256, 0, st>>>(ws, ctas, C, out);
 }
 
 // ================================================================================================ first conv wgrad
-// one CTA per image, one thread per output channel: 27 running sums over the image's pixels; x patch in smem (zero padded)
+// one CTA per (image, slab of FW_ROWS rows), one thread per output channel: 27 running sums over the slab's pixels; the
+// zero-padded x patch of the slab sits in smem
+static constexpr int FW_ROWS = 4;
 __global__ void conv_first_wgrad_k(const bf16* __restrict__ dz, const float* __restrict__ x, float* __restrict__ ws, int H, int W,
                                    int Cout) {
-    extern __shared__ float sx[];  // [3][H+2][W+2]
-    const int n = blockIdx.x;
-    const int pw = W + 2, ph = H + 2;
+    extern __shared__ float sx[];  // [3][FW_ROWS+2][W+2]
+    const int n = blockIdx.x, h0 = blockIdx.y * FW_ROWS;
+    const int pw = W + 2, ph = FW_ROWS + 2;
     for (int i = threadIdx.x; i < 3 * ph * pw; i += blockDim.x) {
         const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
-        const int hh = r - 1, ww = c - 1;
+        const int hh = h0 + r - 1, ww = c - 1;
         sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((long long)n * 3 + ci) * H + hh) * W + ww] : 0.f;
     }
     __syncthreads();
@@ -199,8 +217,8 @@ __global__ void conv_first_wgrad_k(const bf16* __restrict__ dz, const float* __r
     float acc[27];
 #pragma unroll
     for (int j = 0; j < 27; ++j) acc[j] = 0.f;
-    const bf16* dp = dz + (long long)n * H * W * Cout + co;
-    for (int h = 0; h < H; ++h) {
+    const bf16* dp = dz + ((long long)n * H + h0) * W * Cout + co;
+    for (int h = 0; h < FW_ROWS; ++h) {
         for (int w = 0; w < W; ++w) {
             const float d = __bfloat162float(dp[(long long)(h * W + w) * Cout]);
 #pragma unroll
@@ -212,19 +230,15 @@ __global__ void conv_first_wgrad_k(const bf16* __restrict__ dz, const float* __r
         }
     }
 #pragma unroll
-    for (int j = 0; j < 27; ++j) ws[((long long)n * Cout + co) * 27 + j] = acc[j];
+    for (int j = 0; j < 27; ++j) ws[(((long long)n * gridDim.y + blockIdx.y) * Cout + co) * 27 + j] = acc[j];
 }
 void conv_first_wgrad(const bf16* dz, const float* x, float* ws, float* grad, int N, int H, int W, int Cout, cudaStream_t st) {
-    const size_t smem = (size_t)3 * (H + 2) * (W + 2) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(conv_first_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        configured = true;
-    }
+    const size_t smem = (size_t)3 * (FW_ROWS + 2) * (W + 2) * sizeof(float);
     const int threads = (Cout + 31) / 32 * 32;
-    conv_first_wgrad_k<<<N, threads, smem, st>>>(dz, x, ws, H, W, Cout);
+    dim3 grid(N, H / FW_ROWS);
+    conv_first_wgrad_k<<<grid, threads, smem, st>>>(dz, x, ws, H, W, Cout);
     const int M = Cout * 27;
-    reduce_rows_f32_k<<<(M + 127) / 128, 128, 0, st>>>(ws, N, M, grad);
+    reduce_rows_f32_k<<<(M + 31) / 32, 256, 0, st>>>(ws, N * (H / FW_ROWS), M, grad);
 }
 
 }  // namespace dxmi

@@ -20,7 +20,7 @@ void avgpool2_bwd(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaStre
 long long colsum_ws_floats(long long rows, int C);
 void colsum_bf16(const bf16* x, long long rows, int C, float* ws, float* out, cudaStream_t st);
 // first convolution (Cin = 3, fp32 NCHW input x) weight gradient: grad[co][ci][tap] = sum_p dz[p, co] * x[p + tap, ci]
-// ws: N * Cout * 27 floats (one partial per image, summed in image order)
+// ws: N * (H/4) * Cout * 27 floats (one partial per 4-row slab of an image, summed in a fixed order); H % 4 == 0
 void conv_first_wgrad(const bf16* dz, const float* x, float* ws, float* grad, int N, int H, int W, int Cout, cudaStream_t st);
 
 }  // namespace dxmi

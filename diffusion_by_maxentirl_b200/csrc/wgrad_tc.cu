@@ -200,9 +200,10 @@ int prepare_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, 
     p.tiles_w = W / bw;
     p.tiles_h = H / bh;
     p.nchunks = ((N + bn - 1) / bn) * p.tiles_w * p.tiles_h;
-    // split-K: about two waves of CTAs, at least 4 K steps each
+    // split-K: one wave of CTAs (the smem ring allows one CTA per SM and a CTA's prologue / TMEM drain are not overlapped
+    // with anything, so a second partial wave only adds fixed cost), at least 4 K steps each
     const int base_items = (Cout / 128) * taps;
-    int S = (2 * 148 + base_items - 1) / base_items;
+    int S = 148 / base_items;
     if (S > p.nchunks / 4) S = p.nchunks / 4;
     if (S < 1) S = 1;
     p.chunks_per_split = (p.nchunks + S - 1) / S;
