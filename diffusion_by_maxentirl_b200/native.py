@@ -178,5 +178,10 @@ class NativeNet(nn.Module):
         if self.training and getattr(self, "dropout_p", 0.0) > 0:
             raise RuntimeError(
                 "the B200 path implements the sampler rollout (inference); call .eval() first - training-mode "
-                "dropout (trainer.py:352) belongs to the training config, which is not built yet"
+                "dropout (trainer.py:352) belongs to the sampler update, whose U-Net backward is not built yet"
+            )
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "B200 U-Net: forward in train() mode under autograd (trainer.py:348-389, update_sampler) needs the U-Net "
+                "backward, which is not built yet; the result would carry no graph. Use .eval() / torch.no_grad() for sampling."
             )
