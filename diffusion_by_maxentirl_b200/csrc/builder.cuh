@@ -400,6 +400,15 @@ struct Builder {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
             const int P1 = x1.stats_P, P2 = x2.stats_P;
             float* ab = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
+            if (HW <= 64 && !x1.stats_halo && !x2.stats_halo) {
+                // small maps (8x8, 4x4) are launch-latency bound: one kernel that derives the statistics in its prologue
+                // (at most 2 partials per channel, one CTA per image) instead of finalize + apply
+                op([=](cudaStream_t st) {
+                    gn_apply_fused(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P1, st2, P2, out, st);
+                    return (int)cudaGetLastError();
+                });
+                return;
+            }
             op([=](cudaStream_t st) {
                 gn_finalize_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P1, st2, P2, ab,
                                   out, st);
