@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--T", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-n-256", type=int, default=None)
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="dxmi_set_option before the plans are built (A/B switches)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -234,6 +235,9 @@ def main():
     lib = L.lib()
     if args.block_n_256 is not None:
         lib.dxmi_set_option(b"block_n_256", args.block_n_256)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        L.check(lib.dxmi_set_option(name.encode(), int(val)), f"option {name}")
 
     wl = args.workload
     T = args.T or DEFAULTS[wl][0]

@@ -31,6 +31,14 @@ int dxmi_set_option(const char* name, int value) {
         set_halo(value);
         return 0;
     }
+    if (!strcmp(name, "gn_fused")) {  // read when a plan is built
+        set_gn_fused(value);
+        return 0;
+    }
+    if (!strcmp(name, "pair_resident_b")) {
+        set_pair_resident_b(value);
+        return 0;
+    }
     if (!strcmp(name, "pair")) {
         set_pair(value);
         return 0;

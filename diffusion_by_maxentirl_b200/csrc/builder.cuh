@@ -10,6 +10,8 @@
 
 namespace dxmi {
 
+int gn_fused_option();  // engine.cu: 1 = every GroupNorm with producer statistics is ONE kernel (prologue + streaming apply)
+
 struct Builder {
     Net& net;
     Plan& plan;
@@ -400,7 +402,7 @@ struct Builder {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
             const int P1 = x1.stats_P, P2 = x2.stats_P;
             float* ab = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
-            if (HW <= 64 && !x1.stats_halo && !x2.stats_halo) {
+            if ((HW <= 64 || gn_fused_option()) && !x1.stats_halo && !x2.stats_halo) {
                 // small maps (8x8, 4x4) are launch-latency bound: one kernel that derives the statistics in its prologue
                 // (at most 2 partials per channel, one CTA per image) instead of finalize + apply
                 op([=](cudaStream_t st) {

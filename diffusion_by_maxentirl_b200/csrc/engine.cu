@@ -25,6 +25,10 @@ static long long g_launches = 0;
 void count_launches(long long n) { g_launches += n; }
 long long total_launches() { return g_launches; }
 
+static int g_opt_gn_fused = 0;
+int gn_fused_option() { return g_opt_gn_fused; }
+void set_gn_fused(int v) { g_opt_gn_fused = v; }
+
 Net::~Net() {
     for (void* p : owned) cudaFree(p);
     for (auto& kv : plans)

@@ -85,6 +85,7 @@ void spec_adm(Net& net);
 int build_plan(Net& net, Plan& plan);
 int build_train_plan(Net& net, Plan& plan);  // engine_train.cu (IGEBM value net)
 
+void set_gn_fused(int v);
 const char* engine_last_error();
 void engine_set_error(const char* fmt, ...);
 void count_launches(long long n);

@@ -92,6 +92,7 @@ int launch_conv_gemm_v2(const ConvGemmParams& p, int block_n, cudaStream_t strea
 bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n);
 // cta_group::2 pair variant (gemm_tc2p.cu); the B tensor map's box must hold block_n / 2 rows
 int launch_conv_gemm_pair(const ConvGemmParams& p, int block_n, cudaStream_t stream);
+void set_pair_resident_b(int v);  // 0 disables the weights-stationary variant of the pair kernel
 int conv_gemm_v2_ring_bytes(int block_n);
 // Host helper: (cols, rows, batch) map with a 128-byte x 128-row box for the epilogue (elem_bytes 2 = bf16, 4 = fp32).
 int make_out_map(CUtensorMap* out, const void* base, int elem_bytes, int cols, int rows, int batch, long long row_stride,

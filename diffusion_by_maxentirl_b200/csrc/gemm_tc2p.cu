@@ -18,14 +18,23 @@ namespace dxmi {
 
 static constexpr int NUM_THREADS_P = 320;
 
-template <int BLOCK_N>
+// RESB ("weights stationary"): when the whole B operand of this CTA (its BLOCK_N/2 rows x K) fits next to a shallow A
+// ring, it is loaded ONCE per CTA and stays in shared memory for every tile the persistent CTA processes; the ring then
+// carries only A.  The N=128 3x3 convs on 32x32 maps are bound by aggregate L2 -> SM bandwidth (14.5 TB/s measured: the
+// same number for the one-CTA and the pair kernel, with the MMAs switched off), so removing B from the per-K-step traffic
+// (24 KB -> 16 KB per SM) looked attractive.  MEASURED NEGATIVE (profiles/r01_pair_resident_b.txt): the 147 KB resident
+// operand leaves room for only 3 A stages, and with 48 KB instead of 192 KB in flight per SM the loop becomes latency bound
+// (32x32 128->128: 91 us vs 72 us streaming).  Off by default (option "pair_resident_b").
+static constexpr int RESB_MAX_KITERS = 18;  // K <= 1152 (one 3x3 conv over 128 channels)
+template <int BLOCK_N, bool RESB = false>
 struct Cfg2P {
     static constexpr int B_STAGE_BYTES = (BLOCK_N / 2) * TILE_K * 2;  // this CTA's half of the B tile
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = BLOCK_N > 128 ? 6 : 8;
+    static constexpr int STAGE_BYTES = RESB ? A_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = RESB ? 3 : (BLOCK_N > 128 ? 6 : 8);
     static constexpr int ACC_COLS = BLOCK_N <= 128 ? 128 : 256;
     static constexpr int TMEM_COLS = 2 * ACC_COLS;
-    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SM_RESB = STAGES * STAGE_BYTES;  // resident B: RESB_MAX_KITERS boxes of B_STAGE_BYTES
+    static constexpr int RING_BYTES = SM_RESB + (RESB ? RESB_MAX_KITERS * B_STAGE_BYTES : 0);
     static constexpr int SM_OUT = RING_BYTES;
     static constexpr int SM_STAT = SM_OUT + 2 * EPI_SLOT_BYTES;
     static constexpr int SM_BAR = SM_STAT + 2048;
@@ -74,9 +83,9 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
                  : "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool RESB>
 __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __grid_constant__ ConvGemmParams p) {
-    using Cfg = Cfg2P<BLOCK_N>;
+    using Cfg = Cfg2P<BLOCK_N, RESB>;
     constexpr int STAGES = Cfg::STAGES;
 
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -86,6 +95,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
     uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
     uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]       (used in the leader)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* resb_full = bars + 2 * STAGES + 5;  // RESB: the resident B operand of both CTAs has landed (leader's barrier)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -117,6 +127,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
             ptx::mbar_init(&tmem_full[s], 1);
             ptx::mbar_init(&tmem_empty[s], 512);  // the 256 epilogue threads of each CTA
         }
+        ptx::mbar_init(resb_full, 2);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
@@ -135,6 +146,18 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
         if (ptx::elect_one()) {
             const int tiles_per_nblk = p.tiles_w * p.tiles_h;
             uint32_t it = 0;
+            if (RESB) {
+                // one n tile, unbatched B: this CTA's half of every K slice, once
+                const uint32_t rb_leader = mapa(ptx::smem_u32(resb_full), 0);
+                if (rank == 0) {
+                    ptx::mbar_expect_tx(resb_full, 2 * k_iters * Cfg::B_STAGE_BYTES);
+                } else {
+                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rb_leader) : "memory");
+                }
+                for (int kk = 0; kk < k_iters; ++kk)
+                    tma2_load_3d(smem + Cfg::SM_RESB + kk * Cfg::B_STAGE_BYTES, &p.b_map, rb_leader, kk * TILE_K,
+                                 (int)rank * (BLOCK_N / 2), 0);
+            }
             for (int tp = cluster_id; tp < total_pairs; tp += n_clusters) {
                 const int n_tile = tp % p.n_tiles;
                 const int mp = tp / p.n_tiles;
@@ -169,7 +192,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                                 asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
                             }
                             tma2_load_4d(sa, amap, full_leader, ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
-                            tma2_load_3d(sb, &p.b_map, full_leader, kk * TILE_K, bcoord_n, bcoord_b);
+                            if (!RESB) tma2_load_3d(sb, &p.b_map, full_leader, kk * TILE_K, bcoord_n, bcoord_b);
                         }
                     }
                 }
@@ -181,6 +204,10 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
         if (rank == 0 && ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::make_idesc(/*bf16*/ 1, 256, BLOCK_N);
             uint32_t it = 0, ti = 0;
+            if (RESB) {
+                ptx::mbar_wait(resb_full, 0);
+                ptx::tc_fence_after();
+            }
             for (int tp = cluster_id; tp < total_pairs; tp += n_clusters, ++ti) {
                 const uint32_t acc = ti & 1;
                 ptx::mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
@@ -193,7 +220,8 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + A_STAGE_BYTES);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(
+                        RESB ? ptx::smem_u32(smem + Cfg::SM_RESB + k * Cfg::B_STAGE_BYTES) : sa + A_STAGE_BYTES);
                     if (p.dbg_mode != 1) {
 #pragma unroll
                         for (int j = 0; j < TILE_K / 16; ++j) umma2_f16(tacc, da + 2 * j, db + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
@@ -277,13 +305,13 @@ bool conv_gemm_pair_supported(const ConvGemmParams& p, int block_n) {
     return (block_n == 128 || block_n == 192 || block_n == 256) && !p.halo && !p.softmax;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool RESB>
 static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
-    using Cfg = Cfg2P<BLOCK_N>;
+    using Cfg = Cfg2P<BLOCK_N, RESB>;
     static bool configured = false;
     static int num_sms = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm2p_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm2p_kernel<BLOCK_N, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             gemm_set_error(cudaGetErrorString(e));
             return (int)e;
@@ -308,7 +336,7 @@ static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm2p_kernel<BLOCK_N>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm2p_kernel<BLOCK_N, RESB>, p);
     if (e != cudaSuccess) {
         gemm_set_error(cudaGetErrorString(e));
         return (int)e;
@@ -316,11 +344,20 @@ static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
     return 0;
 }
 
+static int g_opt_resb = 0;  // measured slower (see RESB comment): kept as an A/B switch
+void set_pair_resident_b(int v) { g_opt_resb = v; }
+
 int launch_conv_gemm_pair(const ConvGemmParams& p, int block_n, cudaStream_t stream) {
+    int k_iters = 0;
+    for (int s = 0; s < p.nseg; ++s) k_iters += p.seg[s].ntaps * p.seg[s].nchunks;
+    // weights-stationary variant: one column tile, unbatched B, K <= 1152, and enough tiles per CTA pair to amortise the preload
+    if (g_opt_resb && block_n == 128 && p.n_tiles == 1 && !p.b_batched && k_iters <= RESB_MAX_KITERS &&
+        ((p.m_tiles + 1) / 2) * p.batch_count >= 4 * 74)
+        return launch2p_t<128, true>(p, stream);
     switch (block_n) {
-        case 128: return launch2p_t<128>(p, stream);
-        case 192: return launch2p_t<192>(p, stream);
-        case 256: return launch2p_t<256>(p, stream);
+        case 128: return launch2p_t<128, false>(p, stream);
+        case 192: return launch2p_t<192, false>(p, stream);
+        case 256: return launch2p_t<256, false>(p, stream);
         default: gemm_set_error("pair kernel: unsupported block_n"); return -4;
     }
 }

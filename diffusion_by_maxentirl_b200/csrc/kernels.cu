@@ -472,6 +472,16 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __res
     const int n = blockIdx.x, slab = blockIdx.y;
     const int pix_per_slab = HW / slabs;
     const int cpg = C / groups;
+    // (0) start streaming: the first 4 pixel vectors of this thread are requested BEFORE the statistics prologue, whose
+    //     latency (two barriers, dependent loads of the partials) then hides behind them
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
+    const bool pre = pl < PL && pl + 3 * PL < pix_per_slab;
+    bf16x8 v0[4];
+    if (pre) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v0[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + pl + u * PL, cv * 8));
+    }
     // (1) per-channel totals over the P1 / P2 row-segment partials of this image (coalesced, fixed order)
     for (int c = threadIdx.x; c < C; c += GN_THREADS) {
         const bool first = c < C1;
@@ -512,7 +522,6 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __res
         }
     }
     __syncthreads();
-    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
     if (pl >= PL) return;
     float a[8], b[8];
 #pragma unroll
@@ -530,8 +539,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __res
         a[j] = aa;
         b[j] = bb;
     }
-    const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
     int p = pl;
+    if (pre) {
+        // the 4 vectors fetched before the statistics prologue
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v0[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = fmaf(f[j], a[j], b[j]);
+                f[j] = silu ? silu_f(t) : t;
+            }
+            st8(out + (base + p + u * PL) * C + cv * 8, pack8(f));
+        }
+        p += 4 * PL;
+    }
     for (; p + 3 * PL < pix_per_slab; p += 4 * PL) {
         bf16x8 v[4];
 #pragma unroll

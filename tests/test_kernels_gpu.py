@@ -284,3 +284,35 @@ def test_halo_conv_fused_shortcut_residual(ops, N, H, Ca, Cb, Co):
     y2 = ops.conv_gemm([(g, Co, Co)], [(0, 9)], wp2, N, H, H, bias=b, residual=res, act=2)
     ref2 = F.silu(ref_conv(g, w2, b) + res.float())
     assert rel_l2(y2.view(N, H, H, Co), ref2) < 4e-3
+
+
+def test_pair_kernel_weights_stationary(ops):
+    """Large-M 128->128 3x3 conv: the pair kernel keeps its half of the packed weights resident in shared memory for all tiles
+    (gemm_tc2p.cu RESB).  Same accumulation order as the streaming variant -> bitwise equal; both match torch."""
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    if not ops.pair_mode:
+        pytest.skip("pair kernel only")
+    torch.manual_seed(12)
+    dev = "cuda"
+    N, H, C = 80, 32, 128  # 640 row tiles = 320 pair tiles >= 4 per CTA pair
+    x = nhwc(torch.randn(N, C, H, H, device=dev))
+    w = torch.randn(C, C, 3, 3, device=dev) / (3 * C**0.5)
+    b = torch.randn(C, device=dev)
+    rowvec = torch.randn(N, C, device=dev)
+    res = nhwc(torch.randn(N, C, H, H, device=dev))
+    wp = ops.pack_conv_weight(w)
+    outs = []
+    for resb in (1, 0):
+        L.lib().dxmi_set_option(b"pair_resident_b", resb)
+        try:
+            stats = torch.zeros(N * H * H // 128, C, 2, device=dev)
+            y = ops.conv_gemm([(x, C, C)], [(0, 9)], wp, N, H, H, bias=b, rowvec=rowvec, residual=res, gn_stats=stats, gn_seg=128)
+        finally:
+            L.lib().dxmi_set_option(b"pair_resident_b", 0)
+        outs.append((y, stats))
+    ref = ref_conv(x, w, b) + rowvec[:, None, None, :] + res.float()
+    assert rel_l2(outs[0][0].view(N, H, H, C), ref) < 4e-3
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    yf = outs[0][0].float().view(-1, 128, C)
+    assert torch.allclose(outs[0][1][..., 0], yf.sum(1), rtol=1e-4, atol=2e-3)

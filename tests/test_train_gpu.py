@@ -138,3 +138,23 @@ def test_ddp_gradient_allreduce_two_gpus():
                        timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "OK" in r.stdout
+
+
+def test_value_guidance_gradient_pattern():
+    """trainer.py:830-843 (sample_guidance): grad = torch.autograd.grad(v(next_x, t+1).squeeze().sum(), next_x)[0] inside
+    torch.enable_grad() under an outer no_grad - the call pattern of value-guided sampling."""
+    value, vsd = build_value()
+    value.eval()
+    x = torch.randn(4, 3, 32, 32, device="cuda")
+    with torch.no_grad():
+        nx = x.detach()
+        with torch.enable_grad():
+            nx = nx.requires_grad_(True)
+            val = value(nx, torch.full((4,), 3, device="cuda")).squeeze()
+            grad = torch.autograd.grad(val.sum(), nx)[0]
+    assert grad.shape == x.shape and torch.isfinite(grad).all() and grad.abs().max() > 0
+    x2 = x.clone().requires_grad_(True)
+    value(x2, 3).sum().backward()
+    assert torch.equal(grad, x2.grad)  # deterministic: same launch list, fixed reduction orders
+    for p in value.parameters():
+        p.grad = None

@@ -18,6 +18,7 @@ ap.add_argument("--dbg", type=int, default=0)
 ap.add_argument("--gemm-version", type=int, default=2)
 ap.add_argument("--halo", type=int, default=0)
 ap.add_argument("--pair", type=int, default=0)
+ap.add_argument("--resb", type=int, default=0)
 args = ap.parse_args()
 
 # (name, N, H, Cin, Cout, taps)
@@ -37,6 +38,7 @@ L.lib().dxmi_set_option(b"dbg_mode", args.dbg)
 L.lib().dxmi_set_option(b"gemm_version", args.gemm_version)
 L.lib().dxmi_set_option(b"halo", args.halo)
 L.lib().dxmi_set_option(b"pair", args.pair)
+L.lib().dxmi_set_option(b"pair_resident_b", args.resb)
 sets = ["cifar", "in64"] if args.set == "all" else [args.set]
 dev = "cuda"
 for s in sets:
