@@ -375,8 +375,8 @@ def main():
         lib.dxmi_set_option(b"time_gemms", 0)
         achieved = fl.value / (ms.value * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "conv_gemm2_kernel (persistent tcgen05 implicit GEMM: every conv / 1x1 / attention-"
-                                             "projection GEMM launch of the step)",
+        roof = {"bound": "tensor", "kernel": "conv_gemm2p_kernel / conv_gemm2_kernel (persistent tcgen05 implicit GEMM, cta_group::2 pair and "
+                                             "one-CTA variants: every conv / 1x1 / attention-projection GEMM launch of the step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained",
                 "gemm_launches_per_step": nl.value // kk, "gemm_ms_per_step": ms.value / kk,

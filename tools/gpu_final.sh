@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end style validation: all GPU suites, smoke(), default bench (both arms), ncu launch list of the bench command.
 mkdir -p gpurun_out
-bash tools/gpu_check.sh 2>&1 | grep -E "passed|failed|rc="
+bash tools/gpu_check.sh tests/test_kernels_gpu.py tests/test_ddpm_gpu.py tests/test_edm_gpu.py tests/test_fullsize_gpu.py tests/test_fp32_gpu.py tests/test_backward_gpu.py tests/test_train_gpu.py 2>&1 | grep -E "passed|failed|rc="
 timeout -s KILL 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
 timeout -s KILL 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err; echo "ref rc=$?"
 timeout -s KILL 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; echo "bench rc=$?"; cat gpurun_out/final_bench.json; tail -3 gpurun_out/final_bench.err
