@@ -31,6 +31,10 @@ int dxmi_set_option(const char* name, int value) {
         set_halo(value);
         return 0;
     }
+    if (!strcmp(name, "gn_unroll")) {
+        set_gn_unroll(value);
+        return 0;
+    }
     if (!strcmp(name, "gn_fused")) {  // read when a plan is built
         set_gn_fused(value);
         return 0;

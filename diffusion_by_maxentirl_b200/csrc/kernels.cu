@@ -657,6 +657,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restr
     }
 }
 
+template <int U>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_ab_k(const bf16* __restrict__ x1, int C1, int ld1,
                                                            const bf16* __restrict__ x2, int C2, int ld2, int HW,
                                                            const float2* __restrict__ ab, int silu, int slabs,
@@ -682,12 +683,12 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_ab_k(const bf16* __restri
     }
     const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
     int p = pl;
-    for (; p + 3 * PL < pix_per_slab; p += 4 * PL) {
-        bf16x8 v[4];
+    for (; p + (U - 1) * PL < pix_per_slab; p += U * PL) {
+        bf16x8 v[U];  // U independent 16-byte loads in flight per thread
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + p + u * PL, cv * 8));
+        for (int u = 0; u < U; ++u) v[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + p + u * PL, cv * 8));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             float f[8];
             unpack8(v[u], f);
 #pragma unroll
@@ -709,6 +710,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_ab_k(const bf16* __restri
         st8(out + (base + p) * C + cv * 8, pack8(f));
     }
 }
+
+static int g_gn_unroll = 4;
+void set_gn_unroll(int v) { g_gn_unroll = v; }
 
 int gn_apply_slabs(int N, int HW, int C) {
     // enough CTAs for ~16 per SM, but keep >= 4 pixels per pixel-lane per slab so the unrolled loop has work
@@ -734,8 +738,12 @@ void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, 
                                             reinterpret_cast<float2*>(ab_ws));
     const int slabs = gn_apply_slabs(N, HW, C1 + C2);
     dim3 grid(N, slabs);
-    gn_apply_ab_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs,
-                                               out);
+    if (g_gn_unroll == 8)
+        gn_apply_ab_k<8><<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs,
+                                                      out);
+    else
+        gn_apply_ab_k<4><<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs,
+                                                      out);
 }
 
 // [N][P][C][2] -> [N][1][C][2]: collapses many row-segment partials (large feature maps) so that the apply kernel's

@@ -50,6 +50,7 @@ void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int
 void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
                        const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st);
+void set_gn_unroll(int v);  // 4 | 8 independent 16-byte loads per thread in the streaming apply kernel
 // [N][P][C][2] -> [N][1][C][2]
 void gn_collapse(const float* in, float* out, int N, int P, int C, cudaStream_t st);
 // y = bf16(silu(x))  (A operand of the batched temb / emb projection GEMM)
