@@ -111,6 +111,8 @@ SYMBOLS = {
     "dxmi_bind_grad": (_I, [_VP, C.c_char_p, _VP]),
     "dxmi_value_forward_train": (_I, [_VP, _VP, _VP, _I, _VP]),
     "dxmi_value_backward": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
+    "dxmi_op_gn_bwd_ws_floats": (_LL, [_I, _I, _I]),
+    "dxmi_op_group_norm_bwd": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "dxmi_op_pack_conv_weight_dgrad": (_I, [_VP, _I, _I, _I, _I, _VP, _LL, _LL, _VP]),
     "dxmi_op_wgrad_ws_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
     "dxmi_op_conv_wgrad": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _I, _I, _F, _VP, _VP]),

@@ -6,6 +6,7 @@
 
 #include "attn_tc.cuh"
 #include "engine.cuh"
+#include "kernels_bwd.cuh"
 #include "wgrad_tc.cuh"
 
 using namespace dxmi;
@@ -531,6 +532,20 @@ int dxmi_op_attention(const void* qk, long long ld_qk, int q_col0, int k_col0, c
     if (r) set_err(attn_last_error());
     count_launches(1);
     return r;
+}
+
+long long dxmi_op_gn_bwd_ws_floats(int N, int HW, int C) { return gn_bwd_ws_floats(N, HW, C); }
+int dxmi_op_group_norm_bwd(const void* x1, int C1, const void* x2, int C2, const void* dy, const float* ab, const float* mr, int N, int HW,
+                           int groups, int silu, float* ws, void* dx, float* dgamma, float* dbeta, dxmi_stream_t stream) {
+    const int C = C1 + C2;
+    if (C % 8 || C1 % 8 || C > 2048 || groups != 32 || C % groups) {
+        set_err("dxmi_op_group_norm_bwd: needs 32 groups, channel counts that are multiples of 8, C <= 2048");
+        return -1;
+    }
+    group_norm_bwd((const bf16*)x1, C1, (const bf16*)x2, C2, (const bf16*)dy, ab, mr, N, HW, groups, silu, ws, (bf16*)dx, dgamma, dbeta,
+                   (cudaStream_t)stream);
+    count_launches(3);
+    return (int)cudaGetLastError();
 }
 
 int dxmi_op_pack_conv_weight_dgrad(const void* w, int dtype, int Cout, int Cin, int taps, void* dst_bf16, long long ldk,

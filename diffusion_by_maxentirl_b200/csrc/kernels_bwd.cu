@@ -241,4 +241,168 @@ void conv_first_wgrad(const bf16* dz, const float* x, float* ws, float* grad, in
     reduce_rows_f32_k<<<(M + 31) / 32, 256, 0, st>>>(ws, N * (H / FW_ROWS), M, grad);
 }
 
+// ================================================================================================ GroupNorm backward
+static constexpr int GNB_THREADS = 256;
+static int gnb_slabs(int HW, int C) {
+    // a function of the geometry only (fixed summation order for every batch size)
+    const int PL = GNB_THREADS / (C / 8) > 0 ? GNB_THREADS / (C / 8) : 1;
+    int slabs = 1;
+    while (slabs < 16 && HW / (slabs * 2) >= 4 * PL && HW % (slabs * 2) == 0) slabs *= 2;
+    return slabs;
+}
+long long gn_bwd_ws_floats(int N, int HW, int C) { return (long long)N * gnb_slabs(HW, C) * C * 2 + (long long)N * C * 2; }
+
+__device__ __forceinline__ float silu_grad(float z) {
+    const float s = __fdividef(1.f, 1.f + __expf(-z));
+    return s * fmaf(z, 1.f - s, 1.f);
+}
+__device__ __forceinline__ const bf16* gnb_src(const bf16* x1, int C1, const bf16* x2, int C2, long long pix, int c) {
+    return (c < C1) ? x1 + pix * C1 + c : x2 + pix * C2 + (c - C1);
+}
+
+// pass 1: partial[(n * slabs + slab)][c] = (sum dz, sum dz * xh) over the slab's pixels
+__global__ void __launch_bounds__(GNB_THREADS) gn_bwd_stats_k(const bf16* __restrict__ x1, int C1, const bf16* __restrict__ x2, int C2,
+                                                              const bf16* __restrict__ dy, const float2* __restrict__ ab,
+                                                              const float2* __restrict__ mr, int HW, int groups, int silu, int slabs,
+                                                              float2* __restrict__ partial) {
+    extern __shared__ float2 sred2[];  // [PL][C]
+    const int C = C1 + C2, CV = C / 8, PL = GNB_THREADS / CV, cpg = C / groups;
+    const int n = blockIdx.x, slab = blockIdx.y, pps = HW / slabs;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    if (pl < PL) {
+        float a[8], b[8], mu[8], rs[8], sA[8], sB[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            const float2 v = ab[(long long)n * C + c], m = mr[(long long)n * groups + c / cpg];
+            a[j] = v.x; b[j] = v.y; mu[j] = m.x; rs[j] = m.y;
+            sA[j] = sB[j] = 0.f;
+        }
+        const long long base = (long long)n * HW + (long long)slab * pps;
+        for (int p = pl; p < pps; p += PL) {
+            float xf[8], df[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(gnb_src(x1, C1, x2, C2, base + p, cv * 8)), xf);
+            unpack8(*reinterpret_cast<const bf16x8*>(dy + (base + p) * C + cv * 8), df);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float dz = silu ? df[j] * silu_grad(fmaf(a[j], xf[j], b[j])) : df[j];
+                sA[j] += dz;
+                sB[j] = fmaf(dz, (xf[j] - mu[j]) * rs[j], sB[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sred2[pl * C + cv * 8 + j] = make_float2(sA[j], sB[j]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GNB_THREADS) {
+        float2 t = make_float2(0.f, 0.f);
+        for (int q = 0; q < PL; ++q) {
+            const float2 v = sred2[q * C + c];
+            t.x += v.x;
+            t.y += v.y;
+        }
+        partial[((long long)n * slabs + slab) * C + c] = t;
+    }
+}
+
+// pass 2: per-image totals -> group sums -> dx; the slab-0 CTA also publishes AB[n][c] for the parameter gradients
+__global__ void __launch_bounds__(GNB_THREADS) gn_bwd_apply_k(const bf16* __restrict__ x1, int C1, const bf16* __restrict__ x2, int C2,
+                                                              const bf16* __restrict__ dy, const float2* __restrict__ ab,
+                                                              const float2* __restrict__ mr, int HW, int groups, int silu, int slabs,
+                                                              const float2* __restrict__ partial, float2* __restrict__ AB,
+                                                              bf16* __restrict__ dx) {
+    __shared__ float2 s_ch[2048];
+    __shared__ float s_SA[32], s_SB[32];
+    const int C = C1 + C2, CV = C / 8, PL = GNB_THREADS / CV, cpg = C / groups;
+    const int n = blockIdx.x, slab = blockIdx.y, pps = HW / slabs;
+    for (int c = threadIdx.x; c < C; c += GNB_THREADS) {
+        float2 t = make_float2(0.f, 0.f);
+        for (int s = 0; s < slabs; ++s) {
+            const float2 v = partial[((long long)n * slabs + s) * C + c];
+            t.x += v.x;
+            t.y += v.y;
+        }
+        if (slab == 0) AB[(long long)n * C + c] = t;
+        // weight by gamma_c = a / rstd for the group sums
+        const float gam = ab[(long long)n * C + c].x / mr[(long long)n * groups + c / cpg].y;
+        s_ch[c] = make_float2(t.x * gam, t.y * gam);
+    }
+    __syncthreads();
+    {
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        float s = 0.f, q = 0.f;
+        if (g < groups)
+            for (int i = sub; i < cpg; i += 8) {
+                const float2 v = s_ch[g * cpg + i];
+                s += v.x;
+                q += v.y;
+            }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && sub == 0) {
+            const float inv_m = 1.f / ((float)cpg * (float)HW);
+            s_SA[g] = s * inv_m;
+            s_SB[g] = q * inv_m;
+        }
+    }
+    __syncthreads();
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    if (pl >= PL) return;
+    float a[8], b[8], mu[8], rs[8], sa[8], sb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j, g = c / cpg;
+        const float2 v = ab[(long long)n * C + c], m = mr[(long long)n * groups + g];
+        a[j] = v.x; b[j] = v.y; mu[j] = m.x; rs[j] = m.y;
+        sa[j] = s_SA[g]; sb[j] = s_SB[g];
+    }
+    const long long base = (long long)n * HW + (long long)slab * pps;
+    for (int p = pl; p < pps; p += PL) {
+        float xf[8], df[8], o[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(gnb_src(x1, C1, x2, C2, base + p, cv * 8)), xf);
+        unpack8(*reinterpret_cast<const bf16x8*>(dy + (base + p) * C + cv * 8), df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float dz = silu ? df[j] * silu_grad(fmaf(a[j], xf[j], b[j])) : df[j];
+            const float xh = (xf[j] - mu[j]) * rs[j];
+            // rstd * (gamma dz - SA/m - xh SB/m) with a = rstd * gamma
+            o[j] = fmaf(a[j], dz, -rs[j] * fmaf(xh, sb[j], sa[j]));
+        }
+        *reinterpret_cast<bf16x8*>(dx + (base + p) * C + cv * 8) = pack8(o);
+    }
+}
+
+// dgamma[c] = sum_n AB[n][c].y, dbeta[c] = sum_n AB[n][c].x
+__global__ void gn_bwd_param_k(const float2* __restrict__ AB, int N, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sa = 0.f, sb = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float2 v = AB[(long long)n * C + c];
+        sa += v.x;
+        sb += v.y;
+    }
+    if (dbeta) dbeta[c] = sa;
+    if (dgamma) dgamma[c] = sb;
+}
+
+void group_norm_bwd(const bf16* x1, int C1, const bf16* x2, int C2, const bf16* dy, const float* ab, const float* mr, int N, int HW,
+                    int groups, int silu, float* ws, bf16* dx, float* dgamma, float* dbeta, cudaStream_t st) {
+    const int C = C1 + C2;
+    const int slabs = gnb_slabs(HW, C);
+    const int PL = GNB_THREADS / (C / 8) > 0 ? GNB_THREADS / (C / 8) : 1;
+    float2* partial = reinterpret_cast<float2*>(ws);
+    float2* AB = partial + (long long)N * slabs * C;
+    dim3 grid(N, slabs);
+    gn_bwd_stats_k<<<grid, GNB_THREADS, (size_t)PL * C * sizeof(float2), st>>>(x1, C1, x2, C2, dy, reinterpret_cast<const float2*>(ab),
+                                                                              reinterpret_cast<const float2*>(mr), HW, groups, silu,
+                                                                              slabs, partial);
+    gn_bwd_apply_k<<<grid, GNB_THREADS, 0, st>>>(x1, C1, x2, C2, dy, reinterpret_cast<const float2*>(ab),
+                                                 reinterpret_cast<const float2*>(mr), HW, groups, silu, slabs, partial, AB, dx);
+    if (dgamma || dbeta) gn_bwd_param_k<<<(C + 127) / 128, 128, 0, st>>>(AB, N, C, dgamma, dbeta);
+}
+
 }  // namespace dxmi

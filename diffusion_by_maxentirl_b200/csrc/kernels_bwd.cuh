@@ -23,4 +23,15 @@ void colsum_bf16(const bf16* x, long long rows, int C, float* ws, float* out, cu
 // ws: N * (H/4) * Cout * 27 floats (one partial per 4-row slab of an image, summed in a fixed order); H % 4 == 0
 void conv_first_wgrad(const bf16* dz, const float* x, float* ws, float* grad, int N, int H, int W, int Cout, cudaStream_t st);
 
+// ---- GroupNorm(+SiLU) backward (groundwork for the U-Net backward) -------------------------
+// Forward:  xh = (x - mean[n,g]) * rstd[n,g];  z = a[n,c] * x + b[n,c]  (a = rstd * gamma, b = beta - mean * a);  y = silu ? z*sigmoid(z) : z.
+// Inputs: x = channel concat of x1 | x2 (NHWC bf16), dy [N,HW,C] bf16, ab [N][C] float2 (the forward's affine), mr [N][groups] float2
+// (mean, rstd).  Outputs: dx [N,HW,C] bf16 (concat layout), dgamma / dbeta [C] fp32 (written; null = skip).
+//   dz = dy * silu'(z);  A[n,c] = sum_p dz;  B[n,c] = sum_p dz * xh;  per group: SA = sum_c gamma_c A, SB = sum_c gamma_c B, m = cpg*HW
+//   dx = rstd * (gamma_c dz - SA/m - xh SB/m);   dgamma_c = sum_n B[n,c];  dbeta_c = sum_n A[n,c]
+// ws: gn_bwd_ws_floats(N, HW, C) floats.  All reductions in a fixed order.
+long long gn_bwd_ws_floats(int N, int HW, int C);
+void group_norm_bwd(const bf16* x1, int C1, const bf16* x2, int C2, const bf16* dy, const float* ab, const float* mr, int N, int HW,
+                    int groups, int silu, float* ws, bf16* dx, float* dgamma, float* dbeta, cudaStream_t st);
+
 }  // namespace dxmi

@@ -191,3 +191,22 @@ def attention(qk, vt, heads, scale, q_col0=0, k_col0=None):
     L.check(L.lib().dxmi_op_attention(L.ptr(qk), ld, q_col0, Cc if k_col0 is None else k_col0, L.ptr(vt), L.ptr(out), Cc, B,
                                       heads, seq, scale, L.stream_ptr()), "attention")
     return out
+
+
+def group_norm_bwd(x1, dy, ab, mr, silu, x2=None, groups=32, want_param_grads=True):
+    """GroupNorm(32)(+SiLU) backward.  x1 (| x2): NHWC bf16, dy: [N, HW, C] bf16, ab: [N, C, 2] fp32 forward affine, mr: [N, 32, 2]
+    fp32 (mean, rstd).  Returns (dx [N, HW, C] bf16, dgamma [C], dbeta [C])."""
+    N = x1.shape[0]
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    C = C1 + C2
+    HW = x1.numel() // (N * C1)
+    assert dy.dtype == torch.bfloat16 and x1.dtype == torch.bfloat16 and ab.dtype == torch.float32 and mr.dtype == torch.float32
+    ws = torch.empty(L.lib().dxmi_op_gn_bwd_ws_floats(N, HW, C), dtype=torch.float32, device=x1.device)
+    dx = torch.empty(N, HW, C, dtype=torch.bfloat16, device=x1.device)
+    dg = torch.empty(C, dtype=torch.float32, device=x1.device) if want_param_grads else None
+    db = torch.empty(C, dtype=torch.float32, device=x1.device) if want_param_grads else None
+    L.check(L.lib().dxmi_op_group_norm_bwd(L.ptr(x1), C1, L.ptr(x2) if x2 is not None else None, C2, L.ptr(dy), L.ptr(ab), L.ptr(mr), N,
+                                            HW, groups, int(silu), L.ptr(ws), L.ptr(dx), L.ptr(dg) if dg is not None else None,
+                                            L.ptr(db) if db is not None else None, L.stream_ptr()), "group_norm_bwd")
+    return dx, dg, db

@@ -192,6 +192,13 @@ long long dxmi_op_wgrad_ws_floats(int N, int H, int W, int Cout, int Cin, int ta
 int dxmi_op_conv_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, int Cin, int taps, float* grad_oihw,
                        int Cin_total, int ci_off, float scale, float* ws, dxmi_stream_t stream);
 
+/* GroupNorm(32)(+SiLU) backward (groundwork for the U-Net backward; unet_small.py:119-126 under autograd).  x = concat(x1 | x2)
+ * NHWC bf16, dy [N,HW,C] bf16, ab [N][C][2] = the forward's per-(image, channel) affine (a = rstd*gamma, b = beta - mean*a), mr
+ * [N][32][2] = (mean, rstd).  Writes dx [N,HW,C] bf16 and, when not NULL, dgamma / dbeta [C] fp32.  ws: dxmi_op_gn_bwd_ws_floats. */
+long long dxmi_op_gn_bwd_ws_floats(int N, int HW, int C);
+int dxmi_op_group_norm_bwd(const void* x1, int C1, const void* x2, int C2, const void* dy, const float* ab, const float* mr, int N, int HW,
+                           int groups, int silu, float* ws, void* dx, float* dgamma, float* dbeta, dxmi_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------- misc */
 const char* dxmi_last_error(void);
 int dxmi_set_option(const char* name, int value);

@@ -91,3 +91,39 @@ def test_conv_dgrad_with_skip_and_gate(ops, N, H, Cin, Cout):
         ref2 = (F.conv_transpose2d(dz1.float().permute(0, 3, 1, 2), w1q, padding=1).permute(0, 2, 3, 1) + do.float()) * gate
         assert rel_l2(yr.view(N, H, H, Cin), ref2) < 4e-3
         assert torch.allclose(stats[..., 0].sum(0), yr.float().sum(0), rtol=1e-4, atol=2e-2)
+
+
+@pytest.mark.parametrize("N,H,C1,C2,silu", [(4, 32, 128, 0, 1), (3, 16, 256, 128, 1), (5, 8, 256, 256, 0), (2, 4, 256, 0, 1)])
+def test_group_norm_backward(ops, N, H, C1, C2, silu):
+    """GroupNorm(32, eps 1e-6)(+SiLU) backward over a channel concat, vs torch autograd on the same bf16 inputs.  dx is a
+    cancellation (mean-subtracted) quantity rounded to bf16: rel-L2 <= 1e-2; the fp32 parameter gradients <= 2e-3."""
+    torch.manual_seed(30)
+    dev = "cuda"
+    C = C1 + C2
+    x = torch.randn(N, C, H, H, device=dev) * 1.7 + 0.3
+    gamma, beta = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    xb = nhwc(x)  # NHWC bf16
+    dy = nhwc(torch.randn(N, C, H, H, device=dev))
+    xr = xb.float().permute(0, 3, 1, 2).requires_grad_(True)
+    g, b = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xr, 32, g, b, 1e-6)
+    if silu:
+        y = F.silu(y)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    # the forward's saved quantities
+    xg = xb.float().view(N, H * H, 32, C // 32)
+    mean = xg.mean(dim=(1, 3))
+    var = xg.var(dim=(1, 3), unbiased=False)
+    rstd = torch.rsqrt(var + 1e-6)
+    mr = torch.stack([mean, rstd], -1).contiguous()
+    a = rstd.repeat_interleave(C // 32, dim=1) * gamma[None]
+    bb = beta[None] - mean.repeat_interleave(C // 32, dim=1) * a
+    ab = torch.stack([a, bb], -1).contiguous()
+    x1 = xb[..., :C1].contiguous()
+    x2 = xb[..., C1:].contiguous() if C2 else None
+    dx, dg, db = ops.group_norm_bwd(x1, dy.view(N, H * H, C), ab, mr, silu, x2=x2)
+    torch.cuda.synchronize()
+    e = rel_l2(dx.view(N, H, H, C), xr.grad.permute(0, 2, 3, 1))
+    eg, eb = rel_l2(dg, g.grad), rel_l2(db, b.grad)
+    print(f"GN bwd N={N} H={H} C={C1}+{C2} silu={silu}: dx {e:.2e} dgamma {eg:.2e} dbeta {eb:.2e}")
+    assert e < 1e-2 and eg < 2e-3 and eb < 2e-3
