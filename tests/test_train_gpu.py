@@ -43,11 +43,12 @@ def oracle_grads(vsd, x, coef, autocast=False):
     return out.detach(), {k: v.grad for k, v in sd.items()}, xr.grad
 
 
-@pytest.mark.parametrize("B", [6, 16])
-def test_value_backward_matches_autograd(B):
+@pytest.mark.parametrize("B,R", [(6, 32), (16, 32), (3, 64)])
+def test_value_backward_matches_autograd(B, R):
+    """R = 64: the ImageNet-64 value net (value@64^2); B = 3 / 6: ragged row tiles on the small maps."""
     value, vsd = build_value()
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(B, 3, 32, 32, generator=g)
+    x = torch.randn(B, 3, R, R, generator=g)
     coef = torch.randn(B, generator=g)
     ref_out, ref_g, ref_dx = oracle_grads(vsd, x, coef)
     _, ac_g, ac_dx = oracle_grads(vsd, x, coef, autocast=True)
