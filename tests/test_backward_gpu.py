@@ -127,3 +127,87 @@ def test_group_norm_backward(ops, N, H, C1, C2, silu):
     eg, eb = rel_l2(dg, g.grad), rel_l2(db, b.grad)
     print(f"GN bwd N={N} H={H} C={C1}+{C2} silu={silu}: dx {e:.2e} dgamma {eg:.2e} dbeta {eb:.2e}")
     assert e < 1e-2 and eg < 2e-3 and eb < 2e-3
+
+
+def _gn_saved(xb, gamma, beta, eps):
+    """(ab, mr) the forward keeps for the backward, from the bf16 input the kernels read."""
+    N, H, W, C = xb.shape
+    xg = xb.float().view(N, H * W, 32, C // 32)
+    mean = xg.mean(dim=(1, 3))
+    rstd = torch.rsqrt(xg.var(dim=(1, 3), unbiased=False) + eps)
+    a = rstd.repeat_interleave(C // 32, dim=1) * gamma[None]
+    b = beta[None] - mean.repeat_interleave(C // 32, dim=1) * a
+    return torch.stack([a, b], -1).contiguous(), torch.stack([mean, rstd], -1).contiguous()
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout", [(4, 16, 256, 256), (3, 32, 256, 128)])
+def test_ddpm_resblock_backward_composed_from_operators(ops, N, H, Cin, Cout):
+    """Groundwork for the U-Net backward (row a9): a whole DDPM ResnetBlock (unet_small.py:117-136: GN-swish-conv3x3 + temb,
+    GN-swish-conv3x3, + identity | nin_shortcut) differentiated with the product operators only - GroupNorm backward, dgrad
+    GEMMs on transposed weights, tensor-core wgrad, column sums - against torch autograd of the same block in fp32.
+    Tolerance 3e-2 per gradient tensor (bf16 activations and activation gradients)."""
+    torch.manual_seed(40)
+    dev = "cuda"
+    eps = 1e-6
+    x = torch.randn(N, Cin, H, H, device=dev)
+    temb_act = torch.randn(N, 512, device=dev)  # = swish(temb)
+    P = {
+        "g1": torch.randn(Cin, device=dev) * 0.3 + 1, "b1": torch.randn(Cin, device=dev) * 0.3,
+        "w1": torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin**0.5), "c1": torch.randn(Cout, device=dev) * 0.1,
+        "wt": torch.randn(Cout, 512, device=dev) / 512**0.5, "ct": torch.randn(Cout, device=dev) * 0.1,
+        "g2": torch.randn(Cout, device=dev) * 0.3 + 1, "b2": torch.randn(Cout, device=dev) * 0.3,
+        "w2": torch.randn(Cout, Cout, 3, 3, device=dev) / (3 * Cout**0.5), "c2": torch.randn(Cout, device=dev) * 0.1,
+    }
+    if Cin != Cout:
+        P["ws"] = torch.randn(Cout, Cin, 1, 1, device=dev) / Cin**0.5
+        P["cs"] = torch.randn(Cout, device=dev) * 0.1
+    d_out = torch.randn(N, Cout, H, H, device=dev)
+
+    # ---- reference: fp32 autograd (weights rounded to bf16 like the packed copies)
+    R = {k: (v.to(torch.bfloat16).float() if v.dim() == 4 else v.clone()).requires_grad_(True) for k, v in P.items()}
+    xr = nhwc(x).float().permute(0, 3, 1, 2).requires_grad_(True)
+    h = F.conv2d(F.silu(F.group_norm(xr, 32, R["g1"], R["b1"], eps)), R["w1"], R["c1"], padding=1)
+    h = h + F.linear(temb_act, R["wt"], R["ct"])[:, :, None, None]
+    h = F.conv2d(F.silu(F.group_norm(h, 32, R["g2"], R["b2"], eps)), R["w2"], R["c2"], padding=1)
+    sc = F.conv2d(xr, R["ws"], R["cs"]) if Cin != Cout else xr
+    (sc + h).backward(nhwc(d_out).float().permute(0, 3, 1, 2))
+
+    # ---- forward with the product operators, keeping what the backward needs
+    xb = nhwc(x)
+    g1 = ops.group_norm(xb, P["g1"], P["b1"], eps, 1)
+    tproj = (temb_act @ P["wt"].t() + P["ct"]).contiguous()
+    h1 = ops.conv_gemm([(g1, Cin, Cin)], [(0, 9)], ops.pack_conv_weight(P["w1"]), N, H, H, bias=P["c1"], rowvec=tproj).view(N, H, H, Cout)
+    g2 = ops.group_norm(h1, P["g2"], P["b2"], eps, 1)
+    ab1, mr1 = _gn_saved(xb, P["g1"], P["b1"], eps)
+    ab2, mr2 = _gn_saved(h1, P["g2"], P["b2"], eps)
+
+    # ---- backward with the product operators
+    dO = nhwc(d_out)
+    G = {}
+    G["c2"] = dO.float().sum((0, 1, 2))
+    G["w2"] = ops.conv_wgrad(dO, g2, 3)
+    dG2 = ops.conv_gemm([(dO, Cout, Cout)], [(0, 9)], ops.pack_conv_weight_dgrad([P["w2"]]), N, H, H)
+    dH1, G["g2"], G["b2"] = ops.group_norm_bwd(h1, dG2.view(N, H * H, Cout), ab2, mr2, 1)
+    dH1 = dH1.view(N, H, H, Cout)
+    d_tproj = dH1.float().sum((1, 2))  # per-image column sums (host-side here; a tiny reduction kernel in the plan)
+    G["wt"], G["ct"] = d_tproj.t() @ temb_act, d_tproj.sum(0)
+    G["c1"] = dH1.float().sum((0, 1, 2))
+    G["w1"] = ops.conv_wgrad(dH1, g1, 3)
+    dG1 = ops.conv_gemm([(dH1, Cout, Cout)], [(0, 9)], ops.pack_conv_weight_dgrad([P["w1"]]), N, H, H)
+    dXa, G["g1"], G["b1"] = ops.group_norm_bwd(xb, dG1.view(N, H * H, Cin), ab1, mr1, 1)
+    if Cin != Cout:
+        G["ws"] = ops.conv_wgrad(dO, xb, 1)
+        G["cs"] = G["c2"]
+        dX = ops.conv_gemm([(dO, Cout, Cout)], [(0, 1)], ops.pack_conv_weight_dgrad([P["ws"]]), N, H, H, residual=dXa.view(N * H * H, Cin))
+    else:
+        dX = dXa.float().view(N, H, H, Cin) + dO.float()
+    torch.cuda.synchronize()
+    worst = 0.0
+    for k in P:
+        e = rel_l2(G[k], R[k].grad)
+        worst = max(worst, e)
+        print(f"resblock {Cin}->{Cout} grad {k}: {e:.2e}")
+        assert e < 3e-2, (k, e)
+    e = rel_l2(dX.float().view(N, H, H, Cin), xr.grad.permute(0, 2, 3, 1))
+    print(f"resblock {Cin}->{Cout} dX: {e:.2e} (worst parameter {worst:.2e})")
+    assert e < 3e-2
