@@ -353,12 +353,56 @@ int dxmi_value_forward_train(dxmi_net_t net, const float* x, float* out, int B, 
         set_err("dxmi_value_forward_train: handle not finalized");
         return -1;
     }
+    if (net->net.a.arch != DXMI_ARCH_IGEBM_V2) {
+        set_err("dxmi_value_forward_train called on a U-Net handle");
+        return -2;
+    }
     Plan* p = get_train_plan(net->net, B, (cudaStream_t)stream);
     if (!p) return -3;
     p->x = x;
     p->out = out;
     int r = run_ops(p->ops, p->op_names, p->launches_per_run, (cudaStream_t)stream);
     p->fwd_valid = r == 0;
+    return r;
+}
+
+int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, float* out, int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_unet_forward_train: handle not finalized");
+        return -1;
+    }
+    if (net->net.a.arch != DXMI_ARCH_DDPM_UNET) {
+        set_err("dxmi_unet_forward_train: the U-Net backward is built for the DDPM U-Net only");
+        return -2;
+    }
+    Plan* p = get_train_plan(net->net, B, (cudaStream_t)stream);
+    if (!p) return -3;
+    p->x = x;
+    p->x_scale = nullptr;
+    p->t = t;
+    p->y = nullptr;
+    p->out = out;
+    int r = run_ops(p->ops, p->op_names, p->launches_per_run, (cudaStream_t)stream);
+    p->fwd_valid = r == 0;
+    return r;
+}
+
+int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_unet_backward: handle not finalized");
+        return -1;
+    }
+    auto it = net->net.train_plans.find(B);
+    if (it == net->net.train_plans.end() || !it->second->fwd_valid) {
+        set_err("dxmi_unet_backward: no saved activations for this batch size (call dxmi_unet_forward_train first; one backward "
+                "per forward)");
+        return -4;
+    }
+    Plan* p = it->second.get();
+    p->x = x;
+    p->dout = dout;
+    int r = run_ops(p->bwd_ops, p->bwd_names, p->bwd_launches, (cudaStream_t)stream);
+    p->fwd_valid = false;
     return r;
 }
 

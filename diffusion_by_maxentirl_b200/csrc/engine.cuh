@@ -30,6 +30,7 @@ struct Act {  // NHWC bf16 activation
     int stats_P = 0;         // partials per image
     bool stats_halo = false; // one partial per halo tile (3x3 stride-1 conv on a 32/64-wide map) instead of per row segment
     bool has_stats = false;  // pass-independent: the sizing (dry) pass must take the same branches as the real one
+    int id = -1;             // training plans: pass-independent identity (pointers are null in the sizing pass)
 };
 
 struct Plan {
@@ -83,7 +84,8 @@ void spec_adm(Net& net);
 
 // plan builders (dry = size-only pass)
 int build_plan(Net& net, Plan& plan);
-int build_train_plan(Net& net, Plan& plan);  // engine_train.cu (IGEBM value net)
+int build_train_plan(Net& net, Plan& plan);       // engine_train.cu (IGEBM value net; dispatches the DDPM U-Net)
+int build_unet_train_plan(Net& net, Plan& plan);  // engine_train_unet.cu
 
 void set_gn_fused(int v);
 const char* engine_last_error();

@@ -327,8 +327,9 @@ struct IgebmTrainBuilder : Builder {
 };
 
 int build_train_plan(Net& net, Plan& plan) {
+    if (net.a.arch == DXMI_ARCH_DDPM_UNET) return build_unet_train_plan(net, plan);
     if (net.a.arch != DXMI_ARCH_IGEBM_V2) {
-        engine_set_error("training plans exist for the IGEBM value net only (U-Net backward is not built yet)");
+        engine_set_error("training plans exist for the IGEBM value net and the DDPM U-Net (the ADM U-Net backward is not built)");
         return -26;
     }
     if (net.a.precision != 0) {

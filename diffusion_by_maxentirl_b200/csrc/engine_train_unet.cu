@@ -1,0 +1,801 @@
+// Training plan of the DDPM U-Net (models/DxMI/unet_small.py:194-332 under autograd; SURVEY 8a row a9, trainer.py:348-389
+// update_sampler): a forward pass that keeps what the backward needs, and the backward pass from d loss / d eps to every
+// parameter gradient, as two static launch lists.  Dropout must be 0 ("dropout forced to 0 for parity").
+//
+// Reverse-mode structure: the forward records a tape (conv_in, ResnetBlocks, AttnBlocks, Downsample, Upsample, head); the
+// backward walks it in reverse.  Every activation that other ops consume owns a bf16 gradient buffer; contributions (next op,
+// skip-connection concat, residual) are accumulated with accum_bf16 - all consumers of an activation come later in the forward,
+// so its gradient is complete when the reverse walk reaches its producer.
+//   dense parts : data gradients = forward implicit-GEMM kernels on transposed, tap-flipped weights; weight gradients = the
+//                 MN-major split-K tcgen05 kernel (wgrad_tc.cu), per channel slice for concatenated inputs
+//   GroupNorm   : gn_bwd_* (kernels_bwd.cu) from the forward's saved per-(image, channel) affine and (mean, rstd)
+//   attention   : P = softmax(q k^T) is kept; dP = dO V^T, dV = P^T dO, dQ = dS K, dK = dS^T Q as batched tensor-core GEMMs on
+//                 explicitly transposed operands (seq 256), or one SIMT CTA per image (seq <= 64)
+//   Downsample  : stride-2 pad-(0,1,0,1) conv: dgrad and wgrad are the standard pad-1 operators on dY zero-inserted at odd positions
+//   conv_out    : dgrad = the first-conv kernel on transposed weights, wgrad = the first-conv wgrad with taps flipped
+//   temb path   : per-image column sums -> fp32 Linear backward kernels
+#include <map>
+
+#include "builder.cuh"
+#include "kernels_bwd.cuh"
+#include "wgrad_tc.cuh"
+
+namespace dxmi {
+
+namespace {
+bool has_attn_t(const dxmi_arch_desc& a, int v) {
+    for (int i = 0; i < a.n_attn; ++i)
+        if (a.attn_resolutions[i] == v) return true;
+    return false;
+}
+}  // namespace
+
+struct DdpmTrainBuilder : Builder {
+    using Builder::Builder;
+
+    struct GnSave {
+        float* ab = nullptr;  // [B][C][2]
+        float* mr = nullptr;  // [B][32][2]
+    };
+    struct Rec {
+        int kind = 0;  // 0 conv_in, 1 resblock, 2 attn, 3 down, 4 up, 5 head
+        std::string p;
+        Act xa, xb, out;
+        int Cout = 0;
+        bf16 *g1 = nullptr, *h1 = nullptr, *g2 = nullptr;
+        GnSave n1, n2;
+        int tp_off = 0;
+        // attention
+        bf16 *hn = nullptr, *qkv = nullptr, *P = nullptr, *o = nullptr;
+        // up
+        bf16* up = nullptr;
+    };
+    std::vector<Rec> tape;
+    std::map<int, std::pair<bf16*, bool>> gbuf;  // activation id -> (gradient buffer, initialised)
+    int next_id = 0;
+    Act mk(int C, int H, int W, bool stats = true) {
+        Act a = new_act(C, H, W, stats, false);
+        a.id = next_id++;
+        return a;
+    }
+    float *tproj = nullptr, *temb = nullptr, *t1 = nullptr, *te = nullptr;
+    int TP = 0, temb_ch = 0;
+
+    float** gslot(const std::string& key) { return &net.grad[key]; }
+
+    // ---------------------------------------------------------------- gradient buffers
+    bf16* grad_of(const Act& a) {
+        if (a.id < 0) fail("internal: gradient requested for an activation without identity");
+        auto it = gbuf.find(a.id);
+        if (it != gbuf.end()) return it->second.first;
+        bf16* g = (bf16*)alloc((size_t)B * a.H * a.W * a.C * sizeof(bf16));
+        gbuf[a.id] = {g, false};
+        return g;
+    }
+    // grad(a) (+)= src[rows, 0:a.C] with row stride ld
+    void accumulate(const Act& a, const bf16* src, long long ld) {
+        bf16* g = grad_of(a);
+        auto& e = gbuf[a.id];
+        const int init = e.second ? 0 : 1;
+        e.second = true;
+        const long long rows = (long long)B * a.H * a.W;
+        const int C = a.C;
+        op([=](cudaStream_t st) {
+            accum_bf16(g, src, ld, rows, C, init, st);
+            return (int)cudaGetLastError();
+        });
+    }
+    const bf16* complete_grad(const Act& a) {
+        auto it = gbuf.find(a.id);
+        if (it == gbuf.end() || !it->second.second) {
+            fail("internal: activation without gradient contributions in the backward walk");
+            return grad_of(a);
+        }
+        return it->second.first;
+    }
+
+    // ---------------------------------------------------------------- forward helpers
+    GnSave gn_fwd(Act x1, Act x2, const std::string& pfx, int silu, bf16* out) {
+        cur_label = "GN " + pfx;
+        GnSave s;
+        const int C1 = x1.C, C2 = x2.C, HW = x1.H * x1.W;
+        s.ab = (float*)alloc((size_t)B * (C1 + C2) * 2 * sizeof(float));
+        s.mr = (float*)alloc((size_t)B * 32 * 2 * sizeof(float));
+        if (!x1.has_stats || (C2 && !x2.has_stats) || x1.stats_halo || x2.stats_halo) fail("training GroupNorm needs producer statistics");
+        const float* gamma = f32(pfx + ".weight");
+        const float* beta = f32(pfx + ".bias");
+        const bf16 *p1 = x1.p, *p2 = x2.p;
+        const float *st1 = x1.stats, *st2 = x2.stats;
+        const int P1 = x1.stats_P, P2 = x2.stats_P, Bn = B;
+        float *ab = s.ab, *mr = s.mr;
+        op([=](cudaStream_t st) {
+            gn_finalize_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, 1e-6f, gamma, beta, nullptr, 0, silu, st1, P1, st2, P2, ab, out, st, mr);
+            return (int)cudaGetLastError();
+        }, 2);
+        return s;
+    }
+    Act conv3(const std::string& key, const bf16* src, int Cin, int H, int W, int Cout, const float* rowvec, int ldrv,
+              const bf16* residual, bool stats = true) {
+        Act out = mk(Cout, H, W, stats);
+        dxmi_gemm_desc d = conv_desc(H, W);
+        set_src(d, 0, src, Cin, Cin);
+        add_seg(d, 0, 9);
+        d.b_ptr = packed_rows(key, {{{key + ".weight", 0, Cin}}}, nullptr, nullptr);
+        d.b_rows = Cout;
+        d.b_ld = 9LL * Cin;
+        d.bias = f32(key + ".bias");
+        d.rowvec = rowvec;
+        d.ldrv = ldrv;
+        d.residual = residual;
+        d.ldr = Cout;
+        d.out = out.p;
+        d.ldo = Cout;
+        if (stats) want_stats(d, out);
+        gemm(d);
+        return out;
+    }
+    // batched GEMM per image: out[b] (M x N) = alpha * A[b] (M x K, row stride a_ld) . B[b] (N x K, row stride b_ld)^T
+    void bgemm(const bf16* A, int K, int a_ld, int M, const bf16* Bm, int N, long long b_ld, long long b_bs, void* out, int ldo,
+               long long out_bs, bool fp32, float alpha, bool softmax) {
+        dxmi_gemm_desc d;
+        memset(&d, 0, sizeof d);
+        d.N = B;
+        d.H = 1;
+        d.W = M;
+        d.out_H = 1;
+        d.out_W = M;
+        d.stride = 1;
+        set_src(d, 0, A, K, a_ld);
+        add_seg(d, 0, 1);
+        d.a_batched = 1;
+        d.b_ptr = Bm;
+        d.b_rows = N;
+        d.b_ld = b_ld;
+        d.b_batch_stride = b_bs;
+        d.b_batched = 1;
+        d.batch = B;
+        d.alpha = alpha;
+        d.softmax = softmax ? 1 : 0;
+        d.out = out;
+        d.ldo = ldo;
+        d.out_batch_stride = out_bs;
+        d.out_fp32 = fp32 ? 1 : 0;
+        d.rows_per_image = 1;
+        gemm(d);
+    }
+
+    Act resblock(const std::string& p, Act xa, Act xb, int Cout, int tp_off) {
+        cur_label = p;
+        Rec r;
+        r.kind = 1;
+        r.p = p;
+        r.xa = xa;
+        r.xb = xb;
+        r.Cout = Cout;
+        r.tp_off = tp_off;
+        const int H = xa.H, W = xa.W, Cin = xa.C + xb.C;
+        r.g1 = act_alloc(Cin, H, W);
+        r.n1 = gn_fwd(xa, xb, p + ".norm1", 1, r.g1);
+        Act h1 = conv3(p + ".conv1", r.g1, Cin, H, W, Cout, tproj + tp_off, TP, nullptr);
+        r.h1 = h1.p;
+        r.g2 = act_alloc(Cout, H, W);
+        r.n2 = gn_fwd(h1, Act{}, p + ".norm2", 1, r.g2);
+        Act out = mk(Cout, H, W);
+        {
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, r.g2, Cout, Cout);
+            add_seg(d, 0, 9);
+            long long K = 9LL * Cout;
+            if (Cin != Cout) {
+                std::vector<PackPart> parts = {{p + ".conv2.weight", 0, Cout}, {p + ".nin_shortcut.weight", 0, xa.C}};
+                set_src(d, 1, xa.p, xa.C, xa.C);
+                add_seg(d, 1, 1);
+                K += xa.C;
+                if (xb.C) {
+                    parts.push_back({p + ".nin_shortcut.weight", xa.C, xb.C});
+                    set_src(d, 2, xb.p, xb.C, xb.C);
+                    add_seg(d, 2, 1);
+                    K += xb.C;
+                }
+                d.b_ptr = packed_rows(p + ".conv2+nin", {parts}, nullptr, nullptr);
+                d.bias = sum_f32(p + ".conv2+nin.bias", p + ".conv2.bias", p + ".nin_shortcut.bias", Cout);
+            } else {
+                d.b_ptr = packed_rows(p + ".conv2", {{{p + ".conv2.weight", 0, Cout}}}, nullptr, nullptr);
+                d.bias = f32(p + ".conv2.bias");
+                d.residual = xa.p;
+                d.ldr = Cout;
+            }
+            d.b_rows = Cout;
+            d.b_ld = K;
+            d.out = out.p;
+            d.ldo = Cout;
+            want_stats(d, out);
+            gemm(d);
+        }
+        r.out = out;
+        tape.push_back(r);
+        return out;
+    }
+
+    Act attn(const std::string& p, Act x) {
+        cur_label = p;
+        Rec r;
+        r.kind = 2;
+        r.p = p;
+        r.xa = x;
+        const int C = x.C, H = x.H, W = x.W, S = H * W;
+        const float scale = 1.f / sqrtf((float)C);
+        r.hn = act_alloc(C, H, W);
+        r.n1 = gn_fwd(x, Act{}, p + ".norm", 0, r.hn);
+        r.qkv = (bf16*)alloc((size_t)B * S * 3 * C * sizeof(bf16));
+        {
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, r.hn, C, C);
+            add_seg(d, 0, 1);
+            d.b_ptr = packed_rows(p + ".qkv", {{{p + ".q.weight", 0, C}}, {{p + ".k.weight", 0, C}}, {{p + ".v.weight", 0, C}}}, nullptr,
+                                  nullptr);
+            d.b_rows = 3 * C;
+            d.b_ld = C;
+            d.bias = concat_f32(p + ".qkv.bias", {p + ".q.bias", p + ".k.bias", p + ".v.bias"});
+            d.out = r.qkv;
+            d.ldo = 3 * C;
+            gemm(d);
+        }
+        r.o = act_alloc(C, H, W);
+        const int Bn = B;
+        bf16 *qkv = r.qkv, *o = r.o;
+        if (S <= 64) {
+            op([=](cudaStream_t st) {
+                attn_small(qkv, qkv + C, qkv + 2 * C, 3 * C, o, C, Bn, 1, S, C, scale, st);
+                return (int)cudaGetLastError();
+            });
+        } else if (S == 256 || S == 128) {
+            r.P = (bf16*)alloc((size_t)B * S * S * sizeof(bf16));
+            bf16* vT = (bf16*)scratch(1, (size_t)B * C * S * sizeof(bf16));
+            op([=](cudaStream_t st) {
+                transpose_bf16_batched(qkv + 2 * C, 3 * C, (long long)S * 3 * C, vT, S, C, Bn, st);
+                return (int)cudaGetLastError();
+            });
+            bgemm(qkv, C, 3 * C, S, qkv + C, S, 3 * C, (long long)S * 3 * C, r.P, S, (long long)S * S, false, scale, true);
+            bgemm(r.P, S, S, S, vT, C, S, (long long)C * S, o, C, (long long)S * C, false, 1.f, false);
+        } else {
+            fail("DDPM training attention: unsupported sequence length");
+        }
+        Act out = mk(C, H, W);
+        {
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, r.o, C, C);
+            add_seg(d, 0, 1);
+            d.b_ptr = packed_rows(p + ".proj_out", {{{p + ".proj_out.weight", 0, C}}}, nullptr, nullptr);
+            d.b_rows = C;
+            d.b_ld = C;
+            d.bias = f32(p + ".proj_out.bias");
+            d.residual = x.p;
+            d.ldr = C;
+            d.out = out.p;
+            d.ldo = C;
+            want_stats(d, out);
+            gemm(d);
+        }
+        r.out = out;
+        tape.push_back(r);
+        return out;
+    }
+
+    // ---------------------------------------------------------------- backward helpers
+    bf16* packed_dgrad(const std::string& name, const std::vector<std::string>& keys, int rows) {
+        if (dry) return nullptr;
+        long long K = 0;
+        for (auto& k : keys) {
+            const Bound* b = get(k);
+            if (!b) return nullptr;
+            K += b->shape[0] * b->shape[2] * b->shape[3];
+        }
+        bool fresh = false;
+        bf16* d = (bf16*)derived_buf("wT:" + name, (size_t)rows * K * sizeof(bf16), &fresh);
+        if (!d || !fresh) return d;
+        Net* np = &net;
+        long long k_off = 0;
+        for (auto& k : keys) {
+            const Bound* b = get(k);
+            const int Cout = (int)b->shape[0], Cin = (int)b->shape[1], taps = (int)(b->shape[2] * b->shape[3]);
+            const std::string key = k;
+            net.pack_jobs.push_back([np, key, Cout, Cin, taps, d, K, k_off](cudaStream_t st) {
+                const Bound& bb = np->bound[key];
+                pack_conv_weight_dgrad(bb.ptr, bb.dtype == DXMI_F16, Cout, Cin, taps, d, K, k_off, st);
+                count_launches(1);
+            });
+            k_off += (long long)taps * Cout;
+        }
+        return d;
+    }
+    // grad[wkey][:, ci_off : ci_off + Cin] = wgrad(dy [rows, Cout] (stride dy_ld), x [rows, Cin] (stride x_ld))
+    void wgrad(const bf16* dy, long long dy_ld, const bf16* x, long long x_ld, int H, int W, int Cout, int Cin, int taps,
+               const std::string& wkey, int Cin_total, int ci_off) {
+        const int base = (Cout / 128) * taps;
+        if (dry) {
+            scratch(4, (size_t)(148 / (base > 0 ? base : 1) + 1) * Cout * taps * Cin * sizeof(float));
+            return;
+        }
+        if (err) return;
+        WgradOp w;
+        int r = prepare_wgrad(dy, x, B, H, W, Cout, Cin, taps, &w, dy_ld, x_ld);
+        if (r) {
+            err = r;
+            engine_set_error("prepare_wgrad(%s): %s", wkey.c_str(), gemm_last_error());
+            return;
+        }
+        float* ws = (float*)scratch(4, w.partial_floats * sizeof(float));
+        float** g = gslot(wkey);
+        plan.gemm_flops += w.flops;
+        op([w, ws, g, Cin_total, ci_off](cudaStream_t st) {
+            if (!*g) return 0;
+            return run_wgrad(w, ws, *g, Cin_total, ci_off, 1.f, st);
+        }, 2);
+    }
+    // weight gradient of a conv whose input has Cin channels (row stride x_ld), in slices of at most 256 channels
+    void wgrad_sliced(const bf16* dy, long long dy_ld, const bf16* x, long long x_ld, int H, int W, int Cout, int Cin, int taps,
+                      const std::string& wkey, int Cin_total, int ci_off) {
+        for (int c0 = 0; c0 < Cin;) {
+            int c = Cin - c0;
+            if (c > 256) c = 256;
+            wgrad(dy, dy_ld, x + c0, x_ld, H, W, Cout, c, taps, wkey, Cin_total, ci_off + c0);
+            c0 += c;
+        }
+    }
+    void bias_grad(const bf16* dy, long long rows, int C, const std::string& bkey, const std::string& bkey2 = "") {
+        float* ws = (float*)scratch(5, (size_t)colsum_ws_floats(rows, C) * sizeof(float));
+        float* tmp = (float*)alloc((size_t)C * sizeof(float));
+        float** g = gslot(bkey);
+        float** g2 = bkey2.empty() ? nullptr : gslot(bkey2);
+        op([=](cudaStream_t st) {
+            if (!*g && !(g2 && *g2)) return 0;
+            colsum_bf16(dy, rows, C, ws, tmp, st);
+            if (*g) cudaMemcpyAsync(*g, tmp, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            if (g2 && *g2) cudaMemcpyAsync(*g2, tmp, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            return (int)cudaGetLastError();
+        }, 2);
+    }
+    // dX [rows, Cin_rows] = sum over segments conv^T(src_i, W_i)  (+ residual)
+    bf16* dgrad(const std::string& name, const std::vector<std::string>& keys, const std::vector<const bf16*>& srcs,
+                const std::vector<int>& src_C, const std::vector<int>& taps, int H, int W, int rows_out, bf16* out, const bf16* residual) {
+        dxmi_gemm_desc d = conv_desc(H, W);
+        long long K = 0;
+        for (size_t i = 0; i < srcs.size(); ++i) {
+            set_src(d, (int)i, srcs[i], src_C[i], src_C[i]);
+            add_seg(d, (int)i, taps[i]);
+            K += (long long)taps[i] * src_C[i];
+        }
+        d.b_ptr = packed_dgrad(name, keys, rows_out);
+        d.b_rows = rows_out;
+        d.b_ld = K;
+        d.residual = residual;
+        d.ldr = rows_out;
+        d.out = out;
+        d.ldo = rows_out;
+        gemm(d);
+        return out;
+    }
+    void gn_bwd(const std::string& pfx, Act x1, Act x2, const bf16* dy, const GnSave& s, int silu, bf16* dx) {
+        const int C = x1.C + x2.C, HW = x1.H * x1.W, Bn = B;
+        float* ws = (float*)scratch(6, (size_t)gn_bwd_ws_floats(B, HW, C) * sizeof(float));
+        float** gg = gslot(pfx + ".weight");
+        float** gb = gslot(pfx + ".bias");
+        const bf16 *p1 = x1.p, *p2 = x2.p;
+        const int C1 = x1.C, C2 = x2.C;
+        const float *ab = s.ab, *mr = s.mr;
+        op([=](cudaStream_t st) {
+            group_norm_bwd(p1, C1, p2, C2, dy, ab, mr, Bn, HW, 32, silu, ws, dx, *gg, *gb, st);
+            return (int)cudaGetLastError();
+        }, 3);
+    }
+
+    void resblock_bwd(const Rec& r, float* d_tproj) {
+        cur_label = "bwd " + r.p;
+        const Act &xa = r.xa, &xb = r.xb;
+        const int H = xa.H, W = xa.W, Cin = xa.C + xb.C, Cout = r.Cout, Bn = B;
+        const long long rows = (long long)B * H * W;
+        const bf16* dO = complete_grad(r.out);
+        const bool nin = Cin != Cout;
+        bias_grad(dO, rows, Cout, r.p + ".conv2.bias", nin ? r.p + ".nin_shortcut.bias" : "");
+        wgrad_sliced(dO, Cout, r.g2, Cout, H, W, Cout, Cout, 9, r.p + ".conv2.weight", Cout, 0);
+        if (nin) {
+            wgrad_sliced(dO, Cout, xa.p, xa.C, H, W, Cout, xa.C, 1, r.p + ".nin_shortcut.weight", Cin, 0);
+            if (xb.C) wgrad_sliced(dO, Cout, xb.p, xb.C, H, W, Cout, xb.C, 1, r.p + ".nin_shortcut.weight", Cin, xa.C);
+        }
+        bf16* dG2 = (bf16*)scratch(0, (size_t)rows * Cout * 2);
+        dgrad(r.p + ".conv2", {r.p + ".conv2.weight"}, {dO}, {Cout}, {9}, H, W, Cout, dG2, nullptr);
+        bf16* dH1 = (bf16*)scratch(1, (size_t)rows * Cout * 2);
+        gn_bwd(r.p + ".norm2", Act{r.h1, Cout, H, W}, Act{}, dG2, r.n2, 1, dH1);
+        {
+            float* dst = d_tproj + r.tp_off;
+            const int ld = TP, HW = H * W;
+            op([=](cudaStream_t st) {
+                colsum_per_image(dH1, Bn, HW, Cout, dst, ld, st);
+                return (int)cudaGetLastError();
+            });
+        }
+        bias_grad(dH1, rows, Cout, r.p + ".conv1.bias");
+        wgrad_sliced(dH1, Cout, r.g1, Cin, H, W, Cout, Cin, 9, r.p + ".conv1.weight", Cin, 0);
+        bf16* dG1 = (bf16*)scratch(2, (size_t)rows * Cin * 2);
+        dgrad(r.p + ".conv1", {r.p + ".conv1.weight"}, {dH1}, {Cout}, {9}, H, W, Cin, dG1, nullptr);
+        bf16* dX = (bf16*)scratch(3, (size_t)rows * Cin * 2);
+        gn_bwd(r.p + ".norm1", xa, xb, dG1, r.n1, 1, dX);
+        if (nin) {
+            // + nin_shortcut^T(dO), accumulated in place (every element is read, then written, by the same thread)
+            dgrad(r.p + ".nin_shortcut", {r.p + ".nin_shortcut.weight"}, {dO}, {Cout}, {1}, H, W, Cin, dX, dX);
+        } else {
+            op([=](cudaStream_t st) {
+                accum_bf16(dX, dO, Cout, rows, Cout, 0, st);
+                return (int)cudaGetLastError();
+            });
+        }
+        accumulate(xa, dX, Cin);
+        if (xb.C) accumulate(xb, dX + xa.C, Cin);
+    }
+
+    void attn_bwd(const Rec& r) {
+        cur_label = "bwd " + r.p;
+        const Act& x = r.xa;
+        const int C = x.C, H = x.H, W = x.W, S = H * W, Bn = B;
+        const long long rows = (long long)B * S;
+        const float scale = 1.f / sqrtf((float)C);
+        const bf16* dO = complete_grad(r.out);
+        accumulate(x, dO, C);  // residual path
+        bias_grad(dO, rows, C, r.p + ".proj_out.bias");
+        wgrad_sliced(dO, C, r.o, C, H, W, C, C, 1, r.p + ".proj_out.weight", C, 0);
+        bf16* d_o = (bf16*)scratch(0, (size_t)rows * C * 2);
+        dgrad(r.p + ".proj_out", {r.p + ".proj_out.weight"}, {dO}, {C}, {1}, H, W, C, d_o, nullptr);
+        bf16* dqkv = (bf16*)scratch(1, (size_t)rows * 3 * C * 2);
+        bf16* qkv = r.qkv;
+        if (S <= 64) {
+            op([=](cudaStream_t st) {
+                attn_small_bwd(qkv, d_o, dqkv, Bn, S, C, scale, st);
+                return (int)cudaGetLastError();
+            });
+        } else {
+            float* dP = (float*)scratch(2, (size_t)B * S * S * sizeof(float));
+            bf16* dS = (bf16*)scratch(3, (size_t)B * S * S * 2);
+            bf16* T1 = (bf16*)scratch(6, (size_t)B * S * (S > C ? S : C) * 2);  // transposed operand #1
+            bf16* T2 = (bf16*)scratch(7, (size_t)B * S * (S > C ? S : C) * 2);  // transposed operand #2
+            bf16* P = r.P;
+            // dP = dO . V^T
+            bgemm(d_o, C, C, S, qkv + 2 * C, S, 3 * C, (long long)S * 3 * C, dP, S, (long long)S * S, true, 1.f, false);
+            op([=](cudaStream_t st) {
+                softmax_bwd_rows(P, dP, dS, (long long)Bn * S, S, scale, st);
+                // dV = P^T . dO : A = P^T, B = dO^T
+                transpose_bf16_batched(P, S, (long long)S * S, T1, S, S, Bn, st);
+                transpose_bf16_batched(d_o, C, (long long)S * C, T2, S, C, Bn, st);
+                return (int)cudaGetLastError();
+            }, 3);
+            bgemm(T1, S, S, S, T2, C, S, (long long)C * S, dqkv + 2 * C, 3 * C, (long long)S * 3 * C, false, 1.f, false);
+            // dQ = dS . K : B = K^T
+            op([=](cudaStream_t st) {
+                transpose_bf16_batched(qkv + C, 3 * C, (long long)S * 3 * C, T2, S, C, Bn, st);
+                return (int)cudaGetLastError();
+            });
+            bgemm(dS, S, S, S, T2, C, S, (long long)C * S, dqkv, 3 * C, (long long)S * 3 * C, false, 1.f, false);
+            // dK = dS^T . Q : A = dS^T, B = Q^T
+            op([=](cudaStream_t st) {
+                transpose_bf16_batched(dS, S, (long long)S * S, T1, S, S, Bn, st);
+                transpose_bf16_batched(qkv, 3 * C, (long long)S * 3 * C, T2, S, C, Bn, st);
+                return (int)cudaGetLastError();
+            }, 2);
+            bgemm(T1, S, S, S, T2, C, S, (long long)C * S, dqkv + C, 3 * C, (long long)S * 3 * C, false, 1.f, false);
+        }
+        // q / k / v projections
+        {
+            float* ws = (float*)scratch(5, (size_t)colsum_ws_floats(rows, 3 * C) * sizeof(float));
+            float* tmp = (float*)alloc((size_t)3 * C * sizeof(float));
+            float **gq = gslot(r.p + ".q.bias"), **gk = gslot(r.p + ".k.bias"), **gv = gslot(r.p + ".v.bias");
+            op([=](cudaStream_t st) {
+                colsum_bf16(dqkv, rows, 3 * C, ws, tmp, st);
+                if (*gq) cudaMemcpyAsync(*gq, tmp, (size_t)C * 4, cudaMemcpyDeviceToDevice, st);
+                if (*gk) cudaMemcpyAsync(*gk, tmp + C, (size_t)C * 4, cudaMemcpyDeviceToDevice, st);
+                if (*gv) cudaMemcpyAsync(*gv, tmp + 2 * C, (size_t)C * 4, cudaMemcpyDeviceToDevice, st);
+                return (int)cudaGetLastError();
+            }, 2);
+        }
+        wgrad_sliced(dqkv, 3 * C, r.hn, C, H, W, C, C, 1, r.p + ".q.weight", C, 0);
+        wgrad_sliced(dqkv + C, 3 * C, r.hn, C, H, W, C, C, 1, r.p + ".k.weight", C, 0);
+        wgrad_sliced(dqkv + 2 * C, 3 * C, r.hn, C, H, W, C, C, 1, r.p + ".v.weight", C, 0);
+        bf16* d_hn = (bf16*)scratch(0, (size_t)rows * C * 2);
+        dgrad(r.p + ".qkv", {r.p + ".q.weight", r.p + ".k.weight", r.p + ".v.weight"}, {dqkv}, {3 * C}, {1}, H, W, C, d_hn, nullptr);
+        bf16* dX = (bf16*)scratch(2, (size_t)rows * C * 2);
+        gn_bwd(r.p + ".norm", x, Act{}, d_hn, r.n1, 0, dX);
+        accumulate(x, dX, C);
+    }
+
+    void build() {
+        const dxmi_arch_desc& a = net.a;
+        const int ch = a.ch, R = a.resolution;
+        temb_ch = 4 * ch;
+        Plan* pl = &plan;
+        const int Bn = B;
+        if (a.in_channels != 3 || a.out_channels != 3 || ch % 128 || ch > 256 || (R * R) % 128 || B > 1024)
+            fail("DDPM training plan: needs 3 -> 3 channels, ch in {128, 256}, H*W % 128 == 0, batch <= 1024");
+        plan.eps = (float*)alloc((size_t)B * a.out_channels * R * R * sizeof(float));
+        plan.tbuf = (float*)alloc((size_t)B * sizeof(float));
+        plan.coef = (float*)alloc((size_t)B * 8 * sizeof(float));
+
+        // ================================================================= forward
+        emit_bwd = false;
+        std::vector<std::string> rb;
+        for (int l = 0; l < a.n_levels; ++l)
+            for (int b = 0; b < a.num_res_blocks; ++b) rb.push_back("down." + std::to_string(l) + ".block." + std::to_string(b));
+        rb.push_back("mid.block_1");
+        rb.push_back("mid.block_2");
+        for (int l = a.n_levels - 1; l >= 0; --l)
+            for (int b = 0; b <= a.num_res_blocks; ++b) rb.push_back("up." + std::to_string(l) + ".block." + std::to_string(b));
+        std::vector<int> rb_cout;
+        for (int l = 0; l < a.n_levels; ++l)
+            for (int b = 0; b < a.num_res_blocks; ++b) rb_cout.push_back(ch * a.ch_mult[l]);
+        rb_cout.push_back(ch * a.ch_mult[a.n_levels - 1]);
+        rb_cout.push_back(ch * a.ch_mult[a.n_levels - 1]);
+        for (int l = a.n_levels - 1; l >= 0; --l)
+            for (int b = 0; b <= a.num_res_blocks; ++b) rb_cout.push_back(ch * a.ch_mult[l]);
+        TP = 0;
+        std::vector<int> tp_offs;
+        for (int c : rb_cout) {
+            tp_offs.push_back(TP);
+            TP += c;
+        }
+        te = (float*)alloc((size_t)B * ch * 4);
+        t1 = (float*)alloc((size_t)B * temb_ch * 4);
+        temb = (float*)alloc((size_t)B * temb_ch * 4);
+        tproj = (float*)alloc((size_t)B * TP * 4);
+        const float* w0 = f32("temb.dense.0.weight");
+        const float* b0 = f32("temb.dense.0.bias");
+        const float* w1 = f32("temb.dense.1.weight");
+        const float* b1 = f32("temb.dense.1.bias");
+        {
+            std::vector<std::string> wk, bk;
+            for (auto& p : rb) {
+                wk.push_back(p + ".temb_proj.weight");
+                bk.push_back(p + ".temb_proj.bias");
+            }
+            float *te_ = te, *t1_ = t1, *temb_ = temb;
+            const int tc = temb_ch;
+            cur_label = "temb";
+            op([=](cudaStream_t st) {
+                timestep_embedding(pl->t, te_, Bn, ch, 0, st);
+                linear_f32(te_, ch, w0, b0, t1_, tc, Bn, ch, tc, 0, 0, st);
+                linear_f32(t1_, tc, w1, b1, temb_, tc, Bn, tc, tc, 2, 0, st);
+                return (int)cudaGetLastError();
+            }, 3);
+            batched_emb_projection(temb, temb_ch, "temb_proj", wk, bk, tproj, TP);
+        }
+        Act h0 = mk(ch, R, R);
+        if (h0.stats_P != R * R / 128 || h0.stats_halo) fail("DDPM conv_in: unsupported geometry");
+        {
+            const float* w = f32("conv_in.weight");
+            const float* b = f32("conv_in.bias");
+            bf16* o = h0.p;
+            float* hst = h0.stats;
+            cur_label = "conv_in";
+            op([=](cudaStream_t st) {
+                conv3x3_first(pl->x, nullptr, w, b, o, hst, Bn, 3, R, R, ch, 0, st);
+                return (int)cudaGetLastError();
+            });
+            Rec r;
+            r.kind = 0;
+            r.out = h0;
+            tape.push_back(r);
+        }
+        std::vector<Act> hs{h0};
+        int res = R, ri = 0;
+        for (int l = 0; l < a.n_levels; ++l) {
+            const int cout = ch * a.ch_mult[l];
+            const std::string lp = "down." + std::to_string(l);
+            for (int b = 0; b < a.num_res_blocks; ++b, ++ri) {
+                Act h = resblock(lp + ".block." + std::to_string(b), hs.back(), Act{}, cout, tp_offs[ri]);
+                if (has_attn_t(a, res)) h = attn(lp + ".attn." + std::to_string(b), h);
+                hs.push_back(h);
+            }
+            if (l != a.n_levels - 1) {
+                Act x = hs.back();
+                const std::string p = lp + ".downsample";
+                cur_label = p;
+                Act out = mk(x.C, x.H / 2, x.W / 2);
+                dxmi_gemm_desc d = conv_desc(x.H, x.W);
+                d.out_H = x.H / 2;
+                d.out_W = x.W / 2;
+                d.stride = 2;
+                d.rows_per_image = (x.H / 2) * (x.W / 2);
+                set_src(d, 0, x.p, x.C, x.C);
+                add_seg(d, 0, 9);
+                d.b_ptr = packed_rows(p + ".conv", {{{p + ".conv.weight", 0, x.C}}}, nullptr, nullptr);
+                d.b_rows = x.C;
+                d.b_ld = 9LL * x.C;
+                d.bias = f32(p + ".conv.bias");
+                d.out = out.p;
+                d.ldo = x.C;
+                want_stats(d, out);
+                gemm(d);
+                Rec r;
+                r.kind = 3;
+                r.p = p;
+                r.xa = x;
+                r.out = out;
+                tape.push_back(r);
+                hs.push_back(out);
+                res /= 2;
+            }
+        }
+        Act h = hs.back();
+        h = resblock("mid.block_1", h, Act{}, h.C, tp_offs[ri++]);
+        h = attn("mid.attn_1", h);
+        h = resblock("mid.block_2", h, Act{}, h.C, tp_offs[ri++]);
+        for (int l = a.n_levels - 1; l >= 0; --l) {
+            const int cout = ch * a.ch_mult[l];
+            const std::string lp = "up." + std::to_string(l);
+            for (int b = 0; b <= a.num_res_blocks; ++b, ++ri) {
+                Act skip = hs.back();
+                hs.pop_back();
+                h = resblock(lp + ".block." + std::to_string(b), h, skip, cout, tp_offs[ri]);
+                if (has_attn_t(a, res)) h = attn(lp + ".attn." + std::to_string(b), h);
+            }
+            if (l != 0) {
+                const std::string p = lp + ".upsample";
+                cur_label = p;
+                const int C = h.C, H2 = h.H * 2, W2 = h.W * 2, H = h.H, W = h.W;
+                bf16* up = act_alloc(C, H2, W2);
+                const bf16* xp = h.p;
+                op([=](cudaStream_t st) {
+                    upsample2x(xp, up, Bn, H, W, C, st);
+                    return (int)cudaGetLastError();
+                });
+                Act out = conv3(p + ".conv", up, C, H2, W2, C, nullptr, 0, nullptr);
+                Rec r;
+                r.kind = 4;
+                r.p = p;
+                r.xa = h;
+                r.up = up;
+                r.out = out;
+                tape.push_back(r);
+                h = out;
+                res *= 2;
+            }
+        }
+        Rec head;
+        head.kind = 5;
+        head.xa = h;
+        head.g1 = act_alloc(h.C, R, R);
+        head.n1 = gn_fwd(h, Act{}, "norm_out", 1, head.g1);
+        cur_label = "conv_out";
+        conv_out_nchw(head.g1, h.C, R, R, "conv_out.weight", "conv_out.bias", a.out_channels);
+        tape.push_back(head);
+
+        // ================================================================= backward
+        emit_bwd = true;
+        float* d_tproj = (float*)alloc((size_t)B * TP * sizeof(float));
+        for (int i = (int)tape.size() - 1; i >= 0; --i) {
+            const Rec& r = tape[i];
+            if (r.kind == 5) {
+                cur_label = "bwd head";
+                const int C = r.xa.C;
+                // conv_out: dgrad through the first-conv kernel on transposed weights; wgrad through the first-conv wgrad
+                float* w_t = nullptr;
+                if (!dry) {
+                    bool fresh = false;
+                    w_t = (float*)derived_buf("wT:conv_out.first", (size_t)C * 27 * sizeof(float), &fresh);
+                    if (fresh) {
+                        Net* np = &net;
+                        net.pack_jobs.push_back([np, w_t, C](cudaStream_t st) {
+                            const Bound& bb = np->bound["conv_out.weight"];
+                            conv_out_transpose_weights((const float*)bb.ptr, w_t, C, st);
+                            count_launches(1);
+                        });
+                        const Bound* bw = get("conv_out.weight");
+                        if (bw && bw->dtype != DXMI_F32) fail("conv_out.weight must be fp32 for training");
+                    }
+                }
+                bf16* dG = (bf16*)scratch(0, (size_t)B * R * R * C * 2);
+                float* wsf = (float*)scratch(4, (size_t)B * (R / 4) * C * 27 * sizeof(float));
+                float* T = (float*)alloc((size_t)C * 27 * sizeof(float));
+                float **gw = gslot("conv_out.weight"), **gb = gslot("conv_out.bias");
+                const bf16* g = r.g1;
+                op([=](cudaStream_t st) {
+                    if (*gb) sum_nchw_channels(pl->dout, Bn, 3, R * R, *gb, st);
+                    if (*gw) {
+                        conv_first_wgrad(g, pl->dout, wsf, T, Bn, R, R, C, st);
+                        conv_out_wgrad_fix(T, *gw, C, st);
+                    }
+                    conv3x3_first(pl->dout, nullptr, w_t, nullptr, dG, nullptr, Bn, 3, R, R, C, 0, st);
+                    return (int)cudaGetLastError();
+                }, 5);
+                bf16* dH = (bf16*)scratch(1, (size_t)B * R * R * C * 2);
+                gn_bwd("norm_out", r.xa, Act{}, dG, r.n1, 1, dH);
+                accumulate(r.xa, dH, C);
+            } else if (r.kind == 1) {
+                resblock_bwd(r, d_tproj);
+            } else if (r.kind == 2) {
+                attn_bwd(r);
+            } else if (r.kind == 4) {
+                cur_label = "bwd " + r.p;
+                const int C = r.xa.C, H2 = r.out.H, W2 = r.out.W, H = r.xa.H, W = r.xa.W;
+                const long long rows2 = (long long)B * H2 * W2;
+                const bf16* dO = complete_grad(r.out);
+                bias_grad(dO, rows2, C, r.p + ".conv.bias");
+                wgrad_sliced(dO, C, r.up, C, H2, W2, C, C, 9, r.p + ".conv.weight", C, 0);
+                bf16* dUp = (bf16*)scratch(0, (size_t)rows2 * C * 2);
+                dgrad(r.p + ".conv", {r.p + ".conv.weight"}, {dO}, {C}, {9}, H2, W2, C, dUp, nullptr);
+                bf16* dX = (bf16*)scratch(1, (size_t)B * H * W * C * 2);
+                op([=](cudaStream_t st) {
+                    sumpool2(dUp, dX, Bn, H, W, C, st);
+                    return (int)cudaGetLastError();
+                });
+                accumulate(r.xa, dX, C);
+            } else if (r.kind == 3) {
+                cur_label = "bwd " + r.p;
+                const int C = r.xa.C, H = r.xa.H, W = r.xa.W, h = r.out.H, w = r.out.W;
+                const bf16* dO = complete_grad(r.out);
+                bias_grad(dO, (long long)B * h * w, C, r.p + ".conv.bias");
+                bf16* dz = (bf16*)scratch(0, (size_t)B * H * W * C * 2);
+                op([=](cudaStream_t st) {
+                    zero_insert2x(dO, dz, Bn, h, w, C, st);
+                    return (int)cudaGetLastError();
+                });
+                wgrad_sliced(dz, C, r.xa.p, C, H, W, C, C, 9, r.p + ".conv.weight", C, 0);
+                bf16* dX = (bf16*)scratch(1, (size_t)B * H * W * C * 2);
+                dgrad(r.p + ".conv", {r.p + ".conv.weight"}, {dz}, {C}, {9}, H, W, C, dX, nullptr);
+                accumulate(r.xa, dX, C);
+            } else if (r.kind == 0) {
+                cur_label = "bwd conv_in";
+                const bf16* dZ = complete_grad(r.out);
+                bias_grad(dZ, (long long)B * R * R, ch, "conv_in.bias");
+                float* wsf = (float*)scratch(4, (size_t)B * (R / 4) * ch * 27 * sizeof(float));
+                float** g = gslot("conv_in.weight");
+                op([=](cudaStream_t st) {
+                    if (!*g) return 0;
+                    conv_first_wgrad(dZ, pl->x, wsf, *g, Bn, R, R, ch, st);
+                    return (int)cudaGetLastError();
+                }, 2);
+            }
+        }
+        // ---- time-embedding path: d_tproj [B, TP] -> temb_proj, dense.1, dense.0
+        cur_label = "bwd temb";
+        float* d_st = (float*)alloc((size_t)B * temb_ch * sizeof(float));   // grad w.r.t. swish(temb)
+        float* d_s1 = (float*)alloc((size_t)B * temb_ch * sizeof(float));   // grad w.r.t. swish(t1)
+        {
+            const int tc = temb_ch, tp = TP;
+            float *temb_ = temb, *t1_ = t1, *te_ = te;
+            for (size_t i = 0; i < rb.size(); ++i) {
+                const int off = tp_offs[i], co = rb_cout[i];
+                const float* wtp = f32(rb[i] + ".temb_proj.weight");
+                float **gw = gslot(rb[i] + ".temb_proj.weight"), **gb = gslot(rb[i] + ".temb_proj.bias");
+                const int first = i == 0;
+                op([=](cudaStream_t st) {
+                    linear_bwd_w(d_tproj + off, tp, temb_, tc, 2, *gw, *gb, Bn, co, tc, st);
+                    linear_bwd_x(d_tproj + off, tp, wtp, d_st, tc, Bn, co, tc, first ? 0 : 1, st);
+                    return (int)cudaGetLastError();
+                }, 2);
+            }
+            float **g1w = gslot("temb.dense.1.weight"), **g1b = gslot("temb.dense.1.bias");
+            float **g0w = gslot("temb.dense.0.weight"), **g0b = gslot("temb.dense.0.bias");
+            op([=](cudaStream_t st) {
+                silu_bwd_mul(d_st, temb_, (long long)Bn * tc, st);            // -> grad w.r.t. temb
+                linear_bwd_w(d_st, tc, t1_, tc, 2, *g1w, *g1b, Bn, tc, tc, st);
+                linear_bwd_x(d_st, tc, w1, d_s1, tc, Bn, tc, tc, 0, st);
+                silu_bwd_mul(d_s1, t1_, (long long)Bn * tc, st);             // -> grad w.r.t. t1
+                linear_bwd_w(d_s1, tc, te_, ch, 0, *g0w, *g0b, Bn, tc, ch, st);
+                return (int)cudaGetLastError();
+            }, 5);
+        }
+        emit_bwd = false;
+    }
+};
+
+int build_unet_train_plan(Net& net, Plan& plan) {
+    if (net.a.arch != DXMI_ARCH_DDPM_UNET) {
+        engine_set_error("U-Net training plans exist for the DDPM U-Net only");
+        return -28;
+    }
+    if (net.a.precision != 0) {
+        engine_set_error("training plans run in bf16 mode only");
+        return -27;
+    }
+    return build_two_pass<DdpmTrainBuilder>(net, plan);
+}
+
+}  // namespace dxmi

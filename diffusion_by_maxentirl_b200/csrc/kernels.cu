@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restr
                                                            const float* __restrict__ st2, int P2, int C2, int HW, int groups,
                                                            float eps, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ film,
-                                                           int film_ld, float2* __restrict__ ab) {
+                                                           int film_ld, float2* __restrict__ ab, float2* __restrict__ mr) {
     __shared__ float s_mean[32], s_rstd[32];
     __shared__ float2 s_ch[2048];
     const int C = C1 + C2;
@@ -655,6 +655,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restr
         }
         ab[(long long)n * C + c] = make_float2(aa, bb);
     }
+    if (mr && threadIdx.x < groups) mr[(long long)n * groups + threadIdx.x] = make_float2(s_mean[threadIdx.x], s_rstd[threadIdx.x]);
 }
 
 template <int U>
@@ -733,9 +734,9 @@ void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int
 
 void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
-                       const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st) {
+                       const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st, float* mr) {
     gn_finalize_k<<<N, GN_THREADS, 0, st>>>(st1, P1, C1, st2, P2, C2, HW, groups, eps, gamma, beta, film, film_ld,
-                                            reinterpret_cast<float2*>(ab_ws));
+                                            reinterpret_cast<float2*>(ab_ws), reinterpret_cast<float2*>(mr));
     const int slabs = gn_apply_slabs(N, HW, C1 + C2);
     dim3 grid(N, slabs);
     if (g_gn_unroll == 8)

@@ -49,7 +49,8 @@ void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int
 // two launches: per-image finalize (statistics -> per-channel affine, ab_ws = [N][C1+C2][2] floats) + streaming apply
 void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
-                       const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st);
+                       const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st,
+                       float* mr = nullptr);  // mr (optional): [N][groups][2] (mean, rstd), kept by training plans
 void set_gn_unroll(int v);  // 4 | 8 independent 16-byte loads per thread in the streaming apply kernel
 // [N][P][C][2] -> [N][1][C][2]
 void gn_collapse(const float* in, float* out, int N, int P, int C, cudaStream_t st);

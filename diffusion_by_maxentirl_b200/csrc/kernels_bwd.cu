@@ -405,4 +405,313 @@ void group_norm_bwd(const bf16* x1, int C1, const bf16* x2, int C2, const bf16* 
     if (dgamma || dbeta) gn_bwd_param_k<<<(C + 127) / 128, 128, 0, st>>>(AB, N, C, dgamma, dbeta);
 }
 
+// ================================================================================================ U-Net backward helpers
+__global__ void transpose_bf16_k(const bf16* __restrict__ src, long long ld_src, long long bs_src, bf16* __restrict__ dst, int R, int C) {
+    __shared__ bf16 tile[32][33];
+    const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const bf16* s = src + (long long)b * bs_src;
+    bf16* d = dst + (long long)b * R * C;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && c < C) ? s[(long long)r * ld_src + c] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < R && c < C) d[(long long)c * R + r] = tile[threadIdx.x][i];
+    }
+}
+void transpose_bf16_batched(const bf16* src, long long ld_src, long long bs_src, bf16* dst, int R, int C, int B, cudaStream_t st) {
+    dim3 grid((C + 31) / 32, (R + 31) / 32, B), block(32, 8);
+    transpose_bf16_k<<<grid, block, 0, st>>>(src, ld_src, bs_src, dst, R, C);
+}
+
+// one warp per row
+__global__ void softmax_bwd_rows_k(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS, long long rows, int S,
+                                   float scale) {
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const bf16* p = P + row * S;
+    const float* g = dP + row * S;
+    float t = 0.f;
+    for (int j = lane; j < S; j += 32) t = fmaf(__bfloat162float(p[j]), g[j], t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    for (int j = lane; j < S; j += 32) dS[row * S + j] = __float2bfloat16_rn(__bfloat162float(p[j]) * (g[j] - t) * scale);
+}
+void softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, long long rows, int S, float scale, cudaStream_t st) {
+    const long long threads = rows * 32;
+    softmax_bwd_rows_k<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, dP, dS, rows, S, scale);
+}
+
+__global__ void __launch_bounds__(256) attn_small_bwd_k(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o, bf16* __restrict__ dqkv,
+                                                       int S, int C, float scale) {
+    extern __shared__ uint8_t smb[];
+    bf16* sq = reinterpret_cast<bf16*>(smb);  // [S][C]
+    bf16* sk = sq + S * C;
+    bf16* sv = sk + S * C;
+    bf16* sdo = sv + S * C;
+    float* sp = reinterpret_cast<float*>(sdo + S * C);  // [S][S] probabilities
+    float* sds = sp + S * S;                             // [S][S] dP, then dS
+    const int n = blockIdx.x;
+    const long long b3 = (long long)n * S * 3 * C, b1 = (long long)n * S * C;
+    for (int i = threadIdx.x; i < S * C; i += 256) {
+        const int t = i / C, c = i % C;
+        sq[i] = qkv[b3 + (long long)t * 3 * C + c];
+        sk[i] = qkv[b3 + (long long)t * 3 * C + C + c];
+        sv[i] = qkv[b3 + (long long)t * 3 * C + 2 * C + c];
+        sdo[i] = d_o[b1 + i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * S; i += 256) {
+        const int a = i / S, b = i % S;
+        float s = 0.f, g = 0.f;
+        for (int c = 0; c < C; ++c) {
+            s = fmaf(__bfloat162float(sq[a * C + c]), __bfloat162float(sk[b * C + c]), s);
+            g = fmaf(__bfloat162float(sdo[a * C + c]), __bfloat162float(sv[b * C + c]), g);
+        }
+        sp[i] = s * scale;
+        sds[i] = g;  // dP
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int a = threadIdx.x >> 5; a < S; a += 8) {
+        float m = -INFINITY;
+        for (int b = lane; b < S; b += 32) m = fmaxf(m, sp[a * S + b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float l = 0.f;
+        for (int b = lane; b < S; b += 32) {
+            const float e = __expf(sp[a * S + b] - m);
+            sp[a * S + b] = e;
+            l += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        const float inv = 1.f / l;
+        float t = 0.f;
+        for (int b = lane; b < S; b += 32) {
+            const float p = sp[a * S + b] * inv;
+            sp[a * S + b] = p;
+            t = fmaf(p, sds[a * S + b], t);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        for (int b = lane; b < S; b += 32) sds[a * S + b] = sp[a * S + b] * (sds[a * S + b] - t) * scale;  // dS
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * C; i += 256) {
+        const int t = i / C, c = i % C;
+        float dq = 0.f, dk = 0.f, dv = 0.f;
+        for (int j = 0; j < S; ++j) {
+            dq = fmaf(sds[t * S + j], __bfloat162float(sk[j * C + c]), dq);   // dQ[t] = sum_j dS[t,j] K[j]
+            dk = fmaf(sds[j * S + t], __bfloat162float(sq[j * C + c]), dk);   // dK[t] = sum_i dS[i,t] Q[i]
+            dv = fmaf(sp[j * S + t], __bfloat162float(sdo[j * C + c]), dv);   // dV[t] = sum_i P[i,t] dO[i]
+        }
+        dqkv[b3 + (long long)t * 3 * C + c] = __float2bfloat16_rn(dq);
+        dqkv[b3 + (long long)t * 3 * C + C + c] = __float2bfloat16_rn(dk);
+        dqkv[b3 + (long long)t * 3 * C + 2 * C + c] = __float2bfloat16_rn(dv);
+    }
+}
+void attn_small_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int N, int S, int C, float scale, cudaStream_t st) {
+    const size_t smem = (size_t)4 * S * C * sizeof(bf16) + (size_t)2 * S * S * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(attn_small_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    attn_small_bwd_k<<<N, 256, smem, st>>>(qkv, d_o, dqkv, S, C, scale);
+}
+
+__global__ void zero_insert2x_k(const bf16* __restrict__ dy, bf16* __restrict__ out, int N, int h, int w, int CV) {
+    const long long total = (long long)N * (2 * h) * (2 * w) * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long r = i / CV;
+        const int x = (int)(r % (2 * w));
+        r /= 2 * w;
+        const int y = (int)(r % (2 * h));
+        const int n = (int)(r / (2 * h));
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((x & 1) && (y & 1)) v = *reinterpret_cast<const uint4*>(dy + ((((long long)n * h + (y >> 1)) * w + (x >> 1)) * CV + cv) * 8);
+        *reinterpret_cast<uint4*>(out + i * 8) = v;
+    }
+}
+void zero_insert2x(const bf16* dy, bf16* out, int N, int h, int w, int C, cudaStream_t st) {
+    const long long total = (long long)N * 4 * h * w * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 2368) blocks = 2368;
+    zero_insert2x_k<<<(int)blocks, 256, 0, st>>>(dy, out, N, h, w, C / 8);
+}
+
+__global__ void sumpool2_k(const bf16* __restrict__ dy, bf16* __restrict__ out, int N, int h, int w, int CV) {
+    const long long total = (long long)N * h * w * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long r = i / CV;
+        const int x = (int)(r % w);
+        r /= w;
+        const int y = (int)(r % h);
+        const int n = (int)(r / h);
+        const bf16* p = dy + ((((long long)n * 2 * h + 2 * y) * 2 * w + 2 * x) * CV + cv) * 8;
+        float a[8], b[8], c[8], d[8], o[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(p), a);
+        unpack8(*reinterpret_cast<const bf16x8*>(p + CV * 8), b);
+        unpack8(*reinterpret_cast<const bf16x8*>(p + (long long)2 * w * CV * 8), c);
+        unpack8(*reinterpret_cast<const bf16x8*>(p + (long long)2 * w * CV * 8 + CV * 8), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (a[j] + b[j]) + (c[j] + d[j]);
+        *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(o);
+    }
+}
+void sumpool2(const bf16* dy, bf16* out, int N, int h, int w, int C, cudaStream_t st) {
+    const long long total = (long long)N * h * w * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 2368) blocks = 2368;
+    sumpool2_k<<<(int)blocks, 256, 0, st>>>(dy, out, N, h, w, C / 8);
+}
+
+__global__ void accum_bf16_k(bf16* __restrict__ dst, const bf16* __restrict__ src, long long ld_src, long long rows, int CV, int init) {
+    const long long total = rows * CV;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        const long long r = i / CV;
+        float s[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(src + r * ld_src + cv * 8), s);
+        if (!init) {
+            float d[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(dst + i * 8), d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += d[j];
+        }
+        *reinterpret_cast<bf16x8*>(dst + i * 8) = pack8(s);
+    }
+}
+void accum_bf16(bf16* dst, const bf16* src, long long ld_src, long long rows, int C, int init, cudaStream_t st) {
+    const long long total = rows * (C / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 2368) blocks = 2368;
+    accum_bf16_k<<<(int)blocks, 256, 0, st>>>(dst, src, ld_src, rows, C / 8, init);
+}
+
+// one CTA per image
+__global__ void __launch_bounds__(256) colsum_per_image_k(const bf16* __restrict__ x, int HW, int C, float* __restrict__ out, int ld_out) {
+    extern __shared__ float sred[];
+    const int n = blockIdx.x;
+    const int CV = C / 8, PL = 256 / CV;
+    const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    if (pl < PL) {
+        for (int p = pl; p < HW; p += PL) {
+            float f[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(x + ((long long)n * HW + p) * C + cv * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sred[pl * C + cv * 8 + j] = s[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float a = 0.f;
+        for (int q = 0; q < PL; ++q) a += sred[q * C + c];
+        out[(long long)n * ld_out + c] = a;
+    }
+}
+void colsum_per_image(const bf16* x, int N, int HW, int C, float* out, int ld_out, cudaStream_t st) {
+    const int PL = 256 / (C / 8);
+    colsum_per_image_k<<<N, 256, (size_t)PL * C * sizeof(float), st>>>(x, HW, C, out, ld_out);
+}
+
+__device__ __forceinline__ float silu_exact_f(float v) { return v / (1.f + expf(-v)); }
+__global__ void linear_bwd_w_k(const float* __restrict__ dy, int ld_dy, const float* __restrict__ x, int ld_x, int act_x,
+                               float* __restrict__ dW, float* __restrict__ db, int N, int O, int K) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)O * K) return;
+    const int o = (int)(i / K), k = (int)(i % K);
+    float a = 0.f, b = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float g = dy[(long long)n * ld_dy + o];
+        float xv = x[(long long)n * ld_x + k];
+        if (act_x == 2) xv = silu_exact_f(xv);
+        a = fmaf(g, xv, a);
+        b += g;
+    }
+    if (dW) dW[i] = a;
+    if (db && k == 0) db[o] = b;
+}
+void linear_bwd_w(const float* dy, int ld_dy, const float* x, int ld_x, int act_x, float* dW, float* db, int N, int O, int K,
+                  cudaStream_t st) {
+    const long long total = (long long)O * K;
+    linear_bwd_w_k<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dy, ld_dy, x, ld_x, act_x, dW, db, N, O, K);
+}
+__global__ void linear_bwd_x_k(const float* __restrict__ dy, int ld_dy, const float* __restrict__ W, float* __restrict__ dx, int ld_dx,
+                               int N, int O, int K, int accumulate) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)N * K) return;
+    const int n = (int)(i / K), k = (int)(i % K);
+    float a = 0.f;
+    for (int o = 0; o < O; ++o) a = fmaf(dy[(long long)n * ld_dy + o], W[(long long)o * K + k], a);
+    float* d = dx + (long long)n * ld_dx + k;
+    *d = accumulate ? *d + a : a;
+}
+void linear_bwd_x(const float* dy, int ld_dy, const float* W, float* dx, int ld_dx, int N, int O, int K, int accumulate, cudaStream_t st) {
+    const long long total = (long long)N * K;
+    linear_bwd_x_k<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dy, ld_dy, W, dx, ld_dx, N, O, K, accumulate);
+}
+__global__ void silu_bwd_mul_k(float* __restrict__ d, const float* __restrict__ x, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float z = x[i];
+    const float s = 1.f / (1.f + expf(-z));
+    d[i] *= s * (1.f + z * (1.f - s));
+}
+void silu_bwd_mul(float* d, const float* x, long long n, cudaStream_t st) {
+    silu_bwd_mul_k<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, x, n);
+}
+
+__global__ void conv_out_transpose_weights_k(const float* __restrict__ w, float* __restrict__ w_t, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [c][o][tap]
+    if (i >= C * 27) return;
+    const int tap = i % 9, o = (i / 9) % 3, c = i / 27;
+    w_t[i] = w[((long long)o * C + c) * 9 + (8 - tap)];
+}
+void conv_out_transpose_weights(const float* w, float* w_t, int C, cudaStream_t st) {
+    conv_out_transpose_weights_k<<<(C * 27 + 255) / 256, 256, 0, st>>>(w, w_t, C);
+}
+__global__ void conv_out_wgrad_fix_k(const float* __restrict__ t, float* __restrict__ grad, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over grad [o][c][tap]
+    if (i >= C * 27) return;
+    const int tap = i % 9, c = (i / 9) % C, o = i / (9 * C);
+    grad[i] = t[((long long)c * 3 + o) * 9 + (8 - tap)];
+}
+void conv_out_wgrad_fix(const float* t, float* grad, int C, cudaStream_t st) {
+    conv_out_wgrad_fix_k<<<(C * 27 + 255) / 256, 256, 0, st>>>(t, grad, C);
+}
+// one CTA per channel, fixed order
+__global__ void __launch_bounds__(256) sum_nchw_channels_k(const float* __restrict__ x, int N, int C, int HW, float* __restrict__ out) {
+    __shared__ float red[8];
+    const int c = blockIdx.x;
+    float a = 0.f;
+    for (long long i = threadIdx.x; i < (long long)N * HW; i += 256) {
+        const long long n = i / HW, p = i % HW;
+        a += x[(n * C + c) * HW + p];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int j = 0; j < 8; ++j) s += red[j];
+        out[c] = s;
+    }
+}
+void sum_nchw_channels(const float* x, int N, int C, int HW, float* out, cudaStream_t st) {
+    sum_nchw_channels_k<<<C, 256, 0, st>>>(x, N, C, HW, out);
+}
+
 }  // namespace dxmi

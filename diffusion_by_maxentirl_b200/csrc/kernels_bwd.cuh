@@ -34,4 +34,33 @@ long long gn_bwd_ws_floats(int N, int HW, int C);
 void group_norm_bwd(const bf16* x1, int C1, const bf16* x2, int C2, const bf16* dy, const float* ab, const float* mr, int N, int HW,
                     int groups, int silu, float* ws, bf16* dx, float* dgamma, float* dbeta, cudaStream_t st);
 
+// ---- small helpers of the U-Net backward (engine_train_unet.cu) -----------------------------------------------------------
+// dst[b][c][r] = src[b][r][c]: src = B matrices of R rows x C columns, row stride ld_src, batch stride bs_src (elements); dst dense
+void transpose_bf16_batched(const bf16* src, long long ld_src, long long bs_src, bf16* dst, int R, int C, int B, cudaStream_t st);
+// softmax backward per row: dS = P * (dP - sum_j P_j dP_j) * scale;  P bf16 [rows,S], dP fp32 [rows,S] -> dS bf16 [rows,S]
+void softmax_bwd_rows(const bf16* P, const float* dP, bf16* dS, long long rows, int S, float scale, cudaStream_t st);
+// whole single-head attention backward for short sequences (S <= 64), one CTA per image: qkv bf16 [N,S,3C] (q | k | v),
+// d_o bf16 [N,S,C] -> dqkv bf16 [N,S,3C] (dq | dk | dv);  P = softmax(scale q k^T) is recomputed
+void attn_small_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int N, int S, int C, float scale, cudaStream_t st);
+// out[n, 2i+1, 2j+1, :] = dy[n, i, j, :], zero elsewhere (data / weight gradient of the stride-2 pad-(0,1,0,1) Downsample conv
+// become the standard pad-1 operators on this tensor)
+void zero_insert2x(const bf16* dy, bf16* out, int N, int h, int w, int C, cudaStream_t st);
+// nearest-2x upsample backward: out[n,i,j,:] = sum of the 2x2 block of dy [N,2h,2w,C]
+void sumpool2(const bf16* dy, bf16* out, int N, int h, int w, int C, cudaStream_t st);
+// dst[r, 0:C] (+)= src[r*ld_src + 0:C]  (gradient fan-in of skip connections / residuals); init = 1 overwrites
+void accum_bf16(bf16* dst, const bf16* src, long long ld_src, long long rows, int C, int init, cudaStream_t st);
+// out[n*ld_out + c] = sum_p x[n, p, c]   (x bf16 [N,HW,C]): gradient of the per-image temb row vector
+void colsum_per_image(const bf16* x, int N, int HW, int C, float* out, int ld_out, cudaStream_t st);
+// fp32 Linear backward: dW[o,k] = sum_n dy[n,o] * act(x[n,k]), db[o] = sum_n dy[n,o]   (act: 0 none, 2 exact silu)
+void linear_bwd_w(const float* dy, int ld_dy, const float* x, int ld_x, int act_x, float* dW, float* db, int N, int O, int K, cudaStream_t st);
+// dx[n,k] (+)= sum_o dy[n,o] * W[o,k]
+void linear_bwd_x(const float* dy, int ld_dy, const float* W, float* dx, int ld_dx, int N, int O, int K, int accumulate, cudaStream_t st);
+// d[i] *= silu'(x[i])
+void silu_bwd_mul(float* d, const float* x, long long n, cudaStream_t st);
+// conv_out (C -> 3, 3x3) backward helpers: w_t[c][o][tap] = w[o][c][8-tap] (fp32, feeds conv3x3_first as a 3 -> C convolution);
+// grad[o][c][tap] = t[c][o][8-tap] (t = conv_first_wgrad of (g, d_eps));  gb[o] = sum over n, pixels of d_eps[n,o,:]
+void conv_out_transpose_weights(const float* w, float* w_t, int C, cudaStream_t st);
+void conv_out_wgrad_fix(const float* t, float* grad, int C, cudaStream_t st);
+void sum_nchw_channels(const float* x, int N, int C, int HW, float* out, cudaStream_t st);
+
 }  // namespace dxmi

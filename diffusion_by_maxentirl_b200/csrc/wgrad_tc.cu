@@ -172,7 +172,10 @@ __global__ void wgrad_reduce_k(const float* __restrict__ partial, float* __restr
 
 void gemm_set_error(const char* msg);
 
-int prepare_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, int Cin, int taps, WgradOp* op) {
+int prepare_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, int Cin, int taps, WgradOp* op, long long dy_ld,
+                  long long x_ld) {
+    if (dy_ld <= 0) dy_ld = Cout;
+    if (x_ld <= 0) x_ld = Cin;
     if (Cout % 128 || (Cin != 64 && Cin != 128 && Cin != 192 && Cin != 256) || (taps != 1 && taps != 9)) {
         gemm_set_error("wgrad: need Cout % 128 == 0, Cin in {64,128,192,256}, taps 1 or 9");
         return -30;
@@ -187,9 +190,9 @@ int prepare_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, 
     }
     WgradParams& p = *reinterpret_cast<WgradParams*>(op->params);
     static_assert(sizeof(WgradParams) <= sizeof(op->params), "WgradOp::params too small");
-    int r = make_act_map(&p.dy_map, dy, Cout, W, H, N, Cout, (long long)Cout * W, (long long)Cout * W * H, bw, bh, bn, 1);
+    int r = make_act_map(&p.dy_map, dy, Cout, W, H, N, dy_ld, dy_ld * W, dy_ld * W * H, bw, bh, bn, 1);
     if (r) return r;
-    r = make_act_map(&p.x_map, x, Cin, W, H, N, Cin, (long long)Cin * W, (long long)Cin * W * H, bw, bh, bn, 1);
+    r = make_act_map(&p.x_map, x, Cin, W, H, N, x_ld, x_ld * W, x_ld * W * H, bw, bh, bn, 1);
     if (r) return r;
     p.Cout = Cout;
     p.Cin = Cin;

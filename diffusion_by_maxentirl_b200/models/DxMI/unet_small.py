@@ -5,6 +5,50 @@ from diffusion_by_maxentirl_b200 import _lib as L
 from diffusion_by_maxentirl_b200.native import NativeNet
 
 
+class _UNetFunction(torch.autograd.Function):
+    """eps = net(x, t) under autograd on the B200 path (trainer.py:348-389, update_sampler): forward keeps the activations in
+    the handle's training plan (dxmi_unet_forward_train), backward is one dxmi_unet_backward call that writes every parameter
+    gradient.  The state x is not differentiated (the sampler update detaches it)."""
+
+    @staticmethod
+    def forward(ctx, module, x, t, *params):
+        h = module._ensure_handle(x.device)
+        B = x.shape[0]
+        xc = x.detach().contiguous().float()
+        tc = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        out = torch.empty(B, module.out_ch, module.resolution, module.resolution, device=x.device)
+        L.check(L.lib().dxmi_unet_forward_train(h, L.ptr(xc), L.ptr(tc), L.ptr(out), B, L.stream_ptr()), "dxmi_unet_forward_train")
+        ctx.module, ctx.B, ctx.x = module, B, xc
+        ctx.token = module._train_token = object()
+        ctx.need_param = [p.requires_grad for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        m = ctx.module
+        if m._train_token is not ctx.token:
+            raise RuntimeError(
+                "B200 U-Net: backward() of a forward whose saved activations were overwritten by a later grad-enabled forward at "
+                "the same batch size (the plan keeps one set per batch size; run forward/backward pairs in order)")
+        h = m._ensure_handle(ctx.x.device)
+        lib = L.lib()
+        keys = m._keys
+        sizes = [m._param(k).numel() for k in keys]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=ctx.x.device)
+        grads, off = [], 0
+        for k, n, need in zip(keys, sizes, ctx.need_param):
+            g = flat[off:off + n]
+            off += n
+            L.check(lib.dxmi_bind_grad(h, k.encode(), L.ptr(g) if need else None), f"bind_grad {k}")
+            grads.append(g.view(m._param(k).shape) if need else None)
+        d = dout.detach().contiguous().float()
+        L.check(lib.dxmi_unet_backward(h, L.ptr(ctx.x), L.ptr(d), ctx.B, L.stream_ptr()), "dxmi_unet_backward")
+        m._train_token = None
+        for k in keys:
+            lib.dxmi_bind_grad(h, k.encode(), None)
+        return (None, None, None, *grads)
+
+
 class Model(NativeNet):
     """Same constructor and `forward(x, t)` contract as the reference; parameters carry the reference's state_dict keys
     (`temb.dense.0.weight`, `down.0.block.0.conv1.weight`, ...).  The forward is one `dxmi_unet_forward` call:
@@ -36,10 +80,22 @@ class Model(NativeNet):
         self.in_channels = in_channels
         self.out_ch = out_ch
         self.dropout_p = float(dropout)
+        self._train_token = None
 
     def forward(self, x, t):
         assert x.shape[2] == x.shape[3] == self.resolution
         assert t.dim() == 1 and t.shape[0] == x.shape[0]
+        if self.training and torch.is_grad_enabled():
+            # update_sampler (trainer.py:348-389): backward through the U-Net
+            if self.dropout_p > 0:
+                raise RuntimeError(
+                    "B200 U-Net training path: dropout masks are not built - construct the net with dropout=0 (SURVEY 8d, config C4 "
+                    "parity runs with dropout forced to 0), or call .eval() for sampling")
+            if x.requires_grad:
+                raise NotImplementedError("B200 U-Net training path: the gradient w.r.t. the input state is not built")
+            if self.precision != "bf16":
+                raise RuntimeError("B200 U-Net training path runs in bf16 mode only")
+            return _UNetFunction.apply(self, x, t, *[self._param(k) for k in self._keys])
         self._check_eval()
         h = self._ensure_handle(x.device)
         x = x.detach().contiguous().float()

@@ -98,12 +98,40 @@ class VARSampler(nn.Module):
             "control": [control[i] for i in range(T)],
         }
 
+    def _sample_step_autograd(self, x, t, noise):
+        """Training form of sample_step (trainer.py:357-389 differentiates it w.r.t. the U-Net parameters and log_betas): eps
+        comes from the B200 U-Net under autograd; the transition itself is a handful of elementwise torch ops so that autograd
+        also reaches the learnable log_betas (reference var_sampler.py:375-408)."""
+        device = x.device
+        net = _inner(self.net)
+        eps = self._forward_net(x, self.continuous_steps.to(device)[t])
+        a = self.x_prev_multiplier.to(device)[t][:, None, None, None]
+        c = (self.theta_multiplier.to(device)[t] * self.adhoc_scale1)[:, None, None, None]
+        control = c * eps
+        pred_mean = x * a + control
+        if self.trainable_beta == "fix_last":
+            log_betas_all = torch.cat([net.log_betas[:-1], net.std[-1].log().unsqueeze(0)])
+            sigma = torch.exp(log_betas_all[t])
+        elif self.trainable_beta:
+            sigma = torch.exp(net.log_betas[t])
+        else:
+            sigma = self.std.to(device)[t].float()
+        sigma = sigma[:, None, None, None]
+        z = torch.randn_like(x) if noise is None else noise.to(device=device, dtype=torch.float32)
+        xn = pred_mean + sigma * z
+        logp = torch.distributions.Normal(pred_mean, sigma).log_prob(xn.detach().clone()).mean(-1).mean(-1).mean(-1)
+        return {"sample": xn, "logp": logp, "logp_terminal": torch.zeros(len(x), device=device), "mean": pred_mean, "sigma": sigma,
+                "entropy": torch.log(sigma), "control": control}
+
     def sample_step(self, x, t, y=None, noise=None):
         """Reference VARSampler.sample_step (:357-408): per-sample integer step index t."""
         device = x.device
         t = process_single_t(x, t).to(device)
         B = x.shape[0]
         x = x.detach().contiguous().float()
+        net = _inner(self.net)
+        if torch.is_grad_enabled() and net.training:
+            return self._sample_step_autograd(x, t, noise)
         eps = self._forward_net(x, self.continuous_steps.to(device)[t])
         sig = self._sigmas().to(device)[t].float().contiguous()
         a = self.x_prev_multiplier.to(device)[t].contiguous()

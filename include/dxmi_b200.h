@@ -178,6 +178,13 @@ int dxmi_value_forward_train(dxmi_net_t net, const float* x, float* out, int B, 
 /* dout [B] fp32 = d loss / d out; fills every bound gradient and, if dx != NULL, dx [B,3,H,W] fp32 = d loss / d x. */
 int dxmi_value_backward(dxmi_net_t net, const float* x, const float* dout, float* dx, int B, dxmi_stream_t stream);
 
+/* ---- DDPM U-Net training (trainer.py:348-389 update_sampler: eps = net(x, t) under autograd).  Dropout must be 0.
+ * dxmi_unet_forward_train = dxmi_unet_forward (DDPM, no x_scale / labels) that keeps the activations of this batch; dxmi_unet_backward
+ * takes dout [B,3,H,W] fp32 = d loss / d eps and writes every gradient bound with dxmi_bind_grad (no input gradient: the sampler
+ * update detaches the state). ---- */
+int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, float* out, int B, dxmi_stream_t stream);
+int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, int B, dxmi_stream_t stream);
+
 /* ---- backward operators (the training step differentiates through the value net, trainer.py:252-264,
  * :320-326, :369-389) ---- */
 /* Packs an OIHW conv weight for the DATA gradient: dst[ci][k_off + tap' * Cout + co] = W[co][ci][taps-1-tap'] (bf16), so that

@@ -159,3 +159,114 @@ def test_value_guidance_gradient_pattern():
     assert torch.equal(grad, x2.grad)  # deterministic: same launch list, fixed reduction orders
     for p in value.parameters():
         p.grad = None
+
+
+# ------------------------------------------------------------------------------------------------ DDPM U-Net backward
+def _build_ddpm_train(T=10):
+    from common import DDPM_CFG
+    from diffusion_by_maxentirl_b200.models.DxMI.unet_small import Model
+    from diffusion_by_maxentirl_b200.models.DxMI.var_sampler import VARSampler
+
+    net = Model(**dict(DDPM_CFG, dropout=0.0))
+    sampler = VARSampler(net, n_timesteps=T, sample_shape=[3, 32, 32], trainable_beta="fix_last")
+    sd = load_synth_into(net)
+    sampler.cuda()
+    return net, sampler, sd
+
+
+def test_unet_backward_matches_autograd():
+    """eps = net(x, t) in train() mode under autograd (trainer.py:348-389): every one of the 328 parameter gradients of the DDPM
+    U-Net against fp32 CPU autograd over the oracle, for a random linear functional of eps."""
+    from oracle import nets
+
+    net, sampler, sd = _build_ddpm_train()
+    net.train()
+    B = 3
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([616.7, 170.3, 28.3])
+    coef = torch.randn(B, 3, 32, 32, generator=g)
+    rsd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = nets.ddpm_unet_forward(rsd, x, t)
+    (ref * coef).sum().backward()
+    out = net(x.cuda(), t.cuda())
+    assert out.requires_grad
+    assert rel_l2(out, ref) < 2e-2
+    (out * coef.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    errs = {}
+    for k, p in net.named_parameters():
+        if k in ("log_betas",):
+            continue
+        assert p.grad is not None, k
+        if k.endswith(".k.bias"):
+            # softmax is invariant to a constant added to every key's score: this gradient is exactly zero in exact arithmetic
+            assert p.grad.abs().max().item() < 1e-2 * max(rsd[k.replace(".k.bias", ".q.bias")].grad.abs().max().item(), 1e-6), k
+            continue
+        errs[k] = rel_l2(p.grad, rsd[k].grad)
+    import os
+
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/unet_grad_errors.txt", "w") as f:
+            for k, e in errs.items():
+                f.write(f"{e:.3e} {k}\n")
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:12]
+    print("worst U-Net gradient errors:", [(k, "%.2e" % e) for k, e in worst])
+    import statistics
+
+    print("median %.2e over %d tensors" % (statistics.median(errs.values()), len(errs)))
+    for k, e in errs.items():
+        assert e < 5e-2, (k, e)
+
+
+def test_sampler_update_step_like_the_trainer():
+    """trainer.py:348-389: d = sampler.sample_step(state, t) with grad; loss = mean(v(next) + running cost - log sigma); backward
+    into the U-Net and log_betas; clip_grad_norm_(0.1); Adam step.  Loss and post-step log_betas against the oracle on the CPU."""
+    from oracle import nets, samplers
+
+    net, sampler, sd = _build_ddpm_train()
+    value, vsd = build_value()
+    for p in value.parameters():
+        p.requires_grad_(False)
+    sampler.train()
+    B, T = 4, 10
+    g = torch.Generator().manual_seed(10)
+    state = torch.randn(B, 3, 32, 32, generator=g)
+    z = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([0, 3, 7, 9])
+    opt = torch.optim.Adam(sampler.parameters(), lr=1e-4)
+
+    def loss_fn(d, v_next, tt):
+        non_terminal = (tt < T - 1).float()
+        running = (d["control"] ** 2).flatten(1).mean(1) / (2 * d["sigma"].flatten() ** 2)
+        return (v_next.flatten() + (0.1 * running - 0.01 * d["entropy"].flatten()) * non_terminal).mean()
+
+    d = sampler.sample_step(state.cuda(), t.cuda(), noise=z.cuda())
+    loss = loss_fn(d, value(d["sample"], t.cuda() + 1), t.cuda())
+    opt.zero_grad()
+    loss.backward()
+    lb_grad = net.log_betas.grad.detach().clone().cpu()
+    gn = torch.nn.utils.clip_grad_norm_(sampler.parameters(), 0.1)
+    opt.step()
+    # oracle: the same step with fp32 autograd on the CPU
+    rsd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    sched = samplers.var_schedule(T)
+    tau = sched["continuous_steps"][t]
+    eps = nets.ddpm_unet_forward(rsd, state, tau)
+    a = sched["x_prev_multiplier"][t][:, None, None, None]
+    c = sched["theta_multiplier"][t][:, None, None, None]
+    control = c * eps
+    mean = state * a + control
+    lb = rsd["log_betas"]
+    sigma = torch.exp(torch.cat([lb[:-1], rsd["std"][-1].log().unsqueeze(0)])[t])[:, None, None, None]
+    xn = mean + sigma * z
+    rvsd = {k: v.clone() for k, v in vsd.items()}
+    rd = {"control": control, "sigma": sigma, "entropy": torch.log(sigma)}
+    rloss = loss_fn(rd, nets.value_forward(rvsd, xn), t)
+    rloss.backward()
+    print(f"sampler loss {loss.item():.6f} vs oracle {rloss.item():.6f}; grad norm {float(gn):.4f}")
+    assert abs(loss.item() - rloss.item()) < 2e-2 * max(1.0, abs(rloss.item()))
+    e_lb = rel_l2(lb_grad, lb.grad)
+    print(f"log_betas grad rel-L2 {e_lb:.2e}")
+    assert e_lb < 5e-2
+    assert torch.isfinite(net.log_betas).all() and float(gn) > 0
