@@ -366,7 +366,14 @@ int dxmi_value_forward_train(dxmi_net_t net, const float* x, float* out, int B, 
     return r;
 }
 
-int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, float* out, int B, dxmi_stream_t stream) {
+int dxmi_op_dropout_mask(void* mask_bf16, long long n, float p, unsigned long long seed, unsigned stream_id, dxmi_stream_t stream) {
+    dropout_bf16(nullptr, n, p, seed, stream_id, (bf16*)mask_bf16, (cudaStream_t)stream);
+    count_launches(1);
+    return (int)cudaGetLastError();
+}
+
+int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, float* out, float dropout_p,
+                            unsigned long long dropout_seed, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized) {
         set_err("dxmi_unet_forward_train: handle not finalized");
         return -1;
@@ -382,6 +389,12 @@ int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, floa
     p->t = t;
     p->y = nullptr;
     p->out = out;
+    if (dropout_p < 0.f || dropout_p >= 1.f) {
+        set_err("dxmi_unet_forward_train: dropout_p must be in [0, 1)");
+        return -5;
+    }
+    p->dropout_p = dropout_p;
+    p->dropout_seed = dropout_seed;
     int r = run_ops(p->ops, p->op_names, p->launches_per_run, (cudaStream_t)stream);
     p->fwd_valid = r == 0;
     return r;

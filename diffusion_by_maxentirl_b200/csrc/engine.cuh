@@ -52,6 +52,8 @@ struct Plan {
     const float* dout = nullptr;  // [B] gradient of the network output
     float* dx = nullptr;          // optional [B,Cin,H,W] fp32 gradient w.r.t. the input
     bool fwd_valid = false;       // a training forward has filled the saved activations
+    float dropout_p = 0.f;        // training-mode dropout of this forward/backward pair (DDPM U-Net)
+    unsigned long long dropout_seed = 0;
     long long launches_per_run = 0;
     double gemm_flops = 0;
     // rollout scratch (allocated with the plan)

@@ -45,6 +45,7 @@ struct DdpmTrainBuilder : Builder {
         bf16 *g1 = nullptr, *h1 = nullptr, *g2 = nullptr;
         GnSave n1, n2;
         int tp_off = 0;
+        unsigned drop_stream = 0;
         // attention
         bf16 *hn = nullptr, *qkv = nullptr, *P = nullptr, *o = nullptr;
         // up
@@ -180,6 +181,18 @@ struct DdpmTrainBuilder : Builder {
         r.h1 = h1.p;
         r.g2 = act_alloc(Cout, H, W);
         r.n2 = gn_fwd(h1, Act{}, p + ".norm2", 1, r.g2);
+        {
+            // self.dropout(h) between swish(norm2) and conv2 (unet_small.py:126-127): in place, mask regenerated in the backward
+            Plan* pl = &plan;
+            bf16* g2 = r.g2;
+            const long long n = (long long)B * H * W * Cout;
+            const unsigned sid = (unsigned)tape.size();
+            r.drop_stream = sid;
+            op([=](cudaStream_t st) {
+                if (pl->dropout_p > 0.f) dropout_bf16(g2, n, pl->dropout_p, pl->dropout_seed, sid, nullptr, st);
+                return (int)cudaGetLastError();
+            });
+        }
         Act out = mk(Cout, H, W);
         {
             dxmi_gemm_desc d = conv_desc(H, W);
@@ -405,6 +418,15 @@ struct DdpmTrainBuilder : Builder {
         }
         bf16* dG2 = (bf16*)scratch(0, (size_t)rows * Cout * 2);
         dgrad(r.p + ".conv2", {r.p + ".conv2.weight"}, {dO}, {Cout}, {9}, H, W, Cout, dG2, nullptr);
+        {
+            Plan* pl = &plan;
+            const long long n = rows * Cout;
+            const unsigned sid = r.drop_stream;
+            op([=](cudaStream_t st) {
+                if (pl->dropout_p > 0.f) dropout_bf16(dG2, n, pl->dropout_p, pl->dropout_seed, sid, nullptr, st);
+                return (int)cudaGetLastError();
+            });
+        }
         bf16* dH1 = (bf16*)scratch(1, (size_t)rows * Cout * 2);
         gn_bwd(r.p + ".norm2", Act{r.h1, Cout, H, W}, Act{}, dG2, r.n2, 1, dH1);
         {

@@ -714,4 +714,31 @@ void sum_nchw_channels(const float* x, int N, int C, int HW, float* out, cudaStr
     sum_nchw_channels_k<<<C, 256, 0, st>>>(x, N, C, HW, out);
 }
 
+// ================================================================================================ dropout
+__device__ __forceinline__ unsigned mix32(unsigned h) {  // murmur3 finaliser
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+__global__ void dropout_bf16_k(bf16* __restrict__ x, long long n, float p, unsigned s0, unsigned s1, bf16* __restrict__ mask_out) {
+    const float keep_scale = 1.f / (1.f - p);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned lo = (unsigned)i, hi = (unsigned)(i >> 32);
+        const unsigned h = mix32(mix32(lo ^ s0) + (hi ^ s1) * 0x9e3779b9u);
+        const float u = (float)(h >> 8) * (1.f / 16777216.f);  // uniform in [0, 1)
+        const float m = u >= p ? keep_scale : 0.f;
+        if (x) x[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * m);
+        if (mask_out) mask_out[i] = __float2bfloat16_rn(m);
+    }
+}
+void dropout_bf16(bf16* x, long long n, float p, unsigned long long seed, unsigned stream, bf16* mask_out, cudaStream_t st) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 4736) blocks = 4736;
+    const unsigned s0 = (unsigned)seed ^ (stream * 0x9e3779b9u), s1 = (unsigned)(seed >> 32) + stream * 0x85ebca6bu;
+    dropout_bf16_k<<<(int)blocks, 256, 0, st>>>(x, n, p, s0, s1, mask_out);
+}
+
 }  // namespace dxmi

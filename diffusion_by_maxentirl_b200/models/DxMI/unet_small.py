@@ -17,7 +17,12 @@ class _UNetFunction(torch.autograd.Function):
         xc = x.detach().contiguous().float()
         tc = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
         out = torch.empty(B, module.out_ch, module.resolution, module.resolution, device=x.device)
-        L.check(L.lib().dxmi_unet_forward_train(h, L.ptr(xc), L.ptr(tc), L.ptr(out), B, L.stream_ptr()), "dxmi_unet_forward_train")
+        # training-mode dropout: a fresh seed per forward from torch's CPU generator (reproducible under torch.manual_seed); the
+        # masks are counter-based functions of (seed, block, element) and are regenerated in the backward
+        seed = int(torch.randint(0, 2**62, (1,)).item()) if module.dropout_p > 0 else 0
+        module._last_dropout_seed = seed
+        L.check(L.lib().dxmi_unet_forward_train(h, L.ptr(xc), L.ptr(tc), L.ptr(out), float(module.dropout_p), seed, B,
+                                                L.stream_ptr()), "dxmi_unet_forward_train")
         ctx.module, ctx.B, ctx.x = module, B, xc
         ctx.token = module._train_token = object()
         ctx.need_param = [p.requires_grad for p in params]
@@ -81,16 +86,41 @@ class Model(NativeNet):
         self.out_ch = out_ch
         self.dropout_p = float(dropout)
         self._train_token = None
+        self._last_dropout_seed = 0
+
+    def dropout_streams(self):
+        """{ResnetBlock prefix: stream id} of the training-mode dropout masks = the block's position on the forward tape of the
+        training plan (conv_in = 0, then ResnetBlocks, AttnBlocks, Downsample / Upsample in execution order).  With
+        `_last_dropout_seed` and `dxmi_op_dropout_mask` this reproduces the exact masks of the last training forward."""
+        ids, pos = {}, 1
+        d = self._desc
+        attn = {d.attn_resolutions[i] for i in range(d.n_attn)}
+        res = d.resolution
+        for lvl in range(d.n_levels):
+            for b in range(d.num_res_blocks):
+                ids[f"down.{lvl}.block.{b}"] = pos
+                pos += 2 if res in attn else 1
+            if lvl != d.n_levels - 1:
+                pos += 1
+                res //= 2
+        ids["mid.block_1"] = pos
+        pos += 2
+        ids["mid.block_2"] = pos
+        pos += 1
+        for lvl in reversed(range(d.n_levels)):
+            for b in range(d.num_res_blocks + 1):
+                ids[f"up.{lvl}.block.{b}"] = pos
+                pos += 2 if res in attn else 1
+            if lvl != 0:
+                pos += 1
+                res *= 2
+        return ids
 
     def forward(self, x, t):
         assert x.shape[2] == x.shape[3] == self.resolution
         assert t.dim() == 1 and t.shape[0] == x.shape[0]
         if self.training and torch.is_grad_enabled():
             # update_sampler (trainer.py:348-389): backward through the U-Net
-            if self.dropout_p > 0:
-                raise RuntimeError(
-                    "B200 U-Net training path: dropout masks are not built - construct the net with dropout=0 (SURVEY 8d, config C4 "
-                    "parity runs with dropout forced to 0), or call .eval() for sampling")
             if x.requires_grad:
                 raise NotImplementedError("B200 U-Net training path: the gradient w.r.t. the input state is not built")
             if self.precision != "bf16":

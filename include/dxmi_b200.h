@@ -178,11 +178,16 @@ int dxmi_value_forward_train(dxmi_net_t net, const float* x, float* out, int B, 
 /* dout [B] fp32 = d loss / d out; fills every bound gradient and, if dx != NULL, dx [B,3,H,W] fp32 = d loss / d x. */
 int dxmi_value_backward(dxmi_net_t net, const float* x, const float* dout, float* dx, int B, dxmi_stream_t stream);
 
-/* ---- DDPM U-Net training (trainer.py:348-389 update_sampler: eps = net(x, t) under autograd).  Dropout must be 0.
+/* ---- DDPM U-Net training (trainer.py:348-389 update_sampler: eps = net(x, t) under autograd), including training-mode dropout (unet_small.py:126-127; counter-based masks).
  * dxmi_unet_forward_train = dxmi_unet_forward (DDPM, no x_scale / labels) that keeps the activations of this batch; dxmi_unet_backward
  * takes dout [B,3,H,W] fp32 = d loss / d eps and writes every gradient bound with dxmi_bind_grad (no input gradient: the sampler
  * update detaches the state). ---- */
-int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, float* out, int B, dxmi_stream_t stream);
+int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, float* out, float dropout_p,
+                            unsigned long long dropout_seed, int B, dxmi_stream_t stream);
+/* The scaled keep mask (0 or 1/(1-p), bf16, NHWC order of swish(norm2(h))) that ResnetBlock number `stream_id` (position on the
+ * forward tape: conv_in = 0, then blocks / attention / resampling in execution order) applies for (p, seed) - lets a reference
+ * implementation replay the exact dropout pattern (tests). */
+int dxmi_op_dropout_mask(void* mask_bf16, long long n, float p, unsigned long long seed, unsigned stream_id, dxmi_stream_t stream);
 int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, int B, dxmi_stream_t stream);
 
 /* ---- backward operators (the training step differentiates through the value net, trainer.py:252-264,

@@ -37,11 +37,15 @@ def ddpm_timestep_embedding(t, dim):
     return torch.cat([torch.sin(ang), torch.cos(ang)], dim=1)
 
 
-def _ddpm_resblock(sd, p, x, temb):
-    """models/DxMI/unet_small.py:117-136 (eval mode: dropout is the identity)."""
+def _ddpm_resblock(sd, p, x, temb, dropout_masks=None):
+    """models/DxMI/unet_small.py:117-136.  Eval mode: dropout is the identity.  Training mode (:126-127, `self.dropout(h)` between
+    swish(norm2) and conv2): the caller supplies the scaled keep mask per block (`dropout_masks[p]`, values 0 or 1/(1-p))."""
     h = _conv(sd, p + ".conv1", _swish(_gn(sd, p + ".norm1", x, 1e-6)), padding=1)
     h = h + _lin(sd, p + ".temb_proj", _swish(temb))[:, :, None, None]
-    h = _conv(sd, p + ".conv2", _swish(_gn(sd, p + ".norm2", h, 1e-6)), padding=1)
+    h = _swish(_gn(sd, p + ".norm2", h, 1e-6))
+    if dropout_masks is not None:
+        h = h * dropout_masks[p]
+    h = _conv(sd, p + ".conv2", h, padding=1)
     if (p + ".nin_shortcut.weight") in sd:
         x = _conv(sd, p + ".nin_shortcut", x)
     return x + h
@@ -61,7 +65,7 @@ def _ddpm_attn(sd, p, x):
 
 
 def ddpm_unet_forward(sd, x, t, *, ch=128, ch_mult=(1, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,),
-                      resolution=32):
+                      resolution=32, dropout_masks=None):
     """models/DxMI/unet_small.py:292-332 (Model.forward)."""
     assert x.shape[2] == x.shape[3] == resolution
     temb = ddpm_timestep_embedding(t, ch)
@@ -71,7 +75,7 @@ def ddpm_unet_forward(sd, x, t, *, ch=128, ch_mult=(1, 2, 2, 2), num_res_blocks=
     res = resolution
     for lvl in range(n_levels):
         for blk in range(num_res_blocks):
-            h = _ddpm_resblock(sd, f"down.{lvl}.block.{blk}", hs[-1], temb)
+            h = _ddpm_resblock(sd, f"down.{lvl}.block.{blk}", hs[-1], temb, dropout_masks)
             if res in attn_resolutions:
                 h = _ddpm_attn(sd, f"down.{lvl}.attn.{blk}", h)
             hs.append(h)
@@ -80,12 +84,12 @@ def ddpm_unet_forward(sd, x, t, *, ch=128, ch_mult=(1, 2, 2, 2), num_res_blocks=
             hs.append(_conv(sd, f"down.{lvl}.downsample.conv", F.pad(hs[-1], (0, 1, 0, 1)), stride=2))
             res //= 2
     h = hs[-1]
-    h = _ddpm_resblock(sd, "mid.block_1", h, temb)
+    h = _ddpm_resblock(sd, "mid.block_1", h, temb, dropout_masks)
     h = _ddpm_attn(sd, "mid.attn_1", h)
-    h = _ddpm_resblock(sd, "mid.block_2", h, temb)
+    h = _ddpm_resblock(sd, "mid.block_2", h, temb, dropout_masks)
     for lvl in reversed(range(n_levels)):
         for blk in range(num_res_blocks + 1):
-            h = _ddpm_resblock(sd, f"up.{lvl}.block.{blk}", torch.cat([h, hs.pop()], dim=1), temb)
+            h = _ddpm_resblock(sd, f"up.{lvl}.block.{blk}", torch.cat([h, hs.pop()], dim=1), temb, dropout_masks)
             if res in attn_resolutions:
                 h = _ddpm_attn(sd, f"up.{lvl}.attn.{blk}", h)
         if lvl != 0:

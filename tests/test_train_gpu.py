@@ -219,6 +219,59 @@ def test_unet_backward_matches_autograd():
         assert e < 5e-2, (k, e)
 
 
+def test_unet_backward_with_training_mode_dropout():
+    """configs/cifar10/T10.yaml trains with dropout 0.1 (unet_small.py:126-127).  The B200 masks are counter-based; replaying the
+    exact masks (dxmi_op_dropout_mask) in the oracle must reproduce output and gradients like the dropout-free case."""
+    from common import DDPM_CFG
+    from diffusion_by_maxentirl_b200 import _lib as L
+    from diffusion_by_maxentirl_b200.models.DxMI.unet_small import Model
+    from oracle import nets
+
+    p_drop = 0.3
+    net = Model(**dict(DDPM_CFG, dropout=p_drop))
+    sd = load_synth_into(net)
+    net.cuda().train()
+    B = 2
+    g = torch.Generator().manual_seed(19)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([394.1, 66.9])
+    coef = torch.randn(B, 3, 32, 32, generator=g)
+    torch.manual_seed(123)
+    out = net(x.cuda(), t.cuda())
+    (out * coef.cuda()).sum().backward()
+    seed = net._last_dropout_seed
+    assert seed != 0
+    # replay the masks in the oracle
+    masks = {}
+    for pfx, sid in net.dropout_streams().items():
+        cout, hw = getattr_path(net, pfx + ".conv2.weight").shape[0], None
+        res = {"0": 32, "1": 16, "2": 8, "3": 4}[pfx.split(".")[1]] if not pfx.startswith("mid") else 4
+        m = torch.empty(B, res, res, cout, dtype=torch.bfloat16, device="cuda")
+        L.check(L.lib().dxmi_op_dropout_mask(L.ptr(m), m.numel(), p_drop, seed, sid, L.stream_ptr()), "dropout_mask")
+        masks[pfx] = m.float().permute(0, 3, 1, 2).cpu()
+    keep = torch.cat([(m > 0).float().flatten() for m in masks.values()]).mean().item()
+    print(f"dropout keep fraction {keep:.4f} (expected {1 - p_drop:.4f})")
+    assert abs(keep - (1 - p_drop)) < 5e-3
+    rsd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = nets.ddpm_unet_forward(rsd, x, t, dropout_masks=masks)
+    (ref * coef).sum().backward()
+    e_out = rel_l2(out, ref)
+    errs = {k: rel_l2(p.grad, rsd[k].grad) for k, p in net.named_parameters() if not k.endswith(".k.bias")}
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print(f"dropout {p_drop}: eps rel-L2 {e_out:.2e}; worst gradient {worst[0]} {worst[1]:.2e}")
+    assert e_out < 2e-2 and worst[1] < 5e-2
+    # a second forward draws a new seed -> different masks
+    out2 = net(x.cuda(), t.cuda())
+    assert net._last_dropout_seed != seed and rel_l2(out2, out) > 1e-2
+    out2.sum().backward()
+
+
+def getattr_path(obj, path):
+    for part in path.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
 def test_sampler_update_step_like_the_trainer():
     """trainer.py:348-389: d = sampler.sample_step(state, t) with grad; loss = mean(v(next) + running cost - log sigma); backward
     into the U-Net and log_betas; clip_grad_norm_(0.1); Adam step.  Loss and post-step log_betas against the oracle on the CPU."""
