@@ -175,13 +175,16 @@ class NativeNet(nn.Module):
             pass
 
     def _check_eval(self):
+        """Guards of the inference entry points (the DDPM `Model.forward` handles train() mode under autograd itself)."""
         if self.training and getattr(self, "dropout_p", 0.0) > 0:
             raise RuntimeError(
-                "the B200 path implements the sampler rollout (inference); call .eval() first - training-mode "
-                "dropout (trainer.py:352) belongs to the sampler update, whose U-Net backward is not built yet"
+                "the B200 inference path has no dropout: a train()-mode forward without autograd (where the reference would apply "
+                "dropout) is not built - call .eval() for sampling (generate_*.py, trainer.py:179 do), or run under autograd for "
+                "the sampler update"
             )
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError(
-                "B200 U-Net: forward in train() mode under autograd (trainer.py:348-389, update_sampler) needs the U-Net "
-                "backward, which is not built yet; the result would carry no graph. Use .eval() / torch.no_grad() for sampling."
+                "B200 U-Net: forward in train() mode under autograd needs a backward, which is built for the DDPM U-Net only "
+                "(the ADM U-Net backward / EDM training is not built); the result would carry no graph. Use .eval() / "
+                "torch.no_grad() for sampling."
             )
