@@ -61,7 +61,62 @@ with torch.no_grad():
 ok = worst < 1e-6 and (hi - lo).abs().item() == 0.0 and torch.isfinite(after).all().item()
 flag = torch.tensor([1.0 if ok else 0.0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+# ---- sampler update (trainer.py:348-389) with the DDPM U-Net under DDP: sample_step with grad, value term, clip, Adam
+from common import DDPM_CFG  # noqa: E402
+from diffusion_by_maxentirl_b200.models.DxMI.unet_small import Model  # noqa: E402
+from diffusion_by_maxentirl_b200.models.DxMI.var_sampler import VARSampler  # noqa: E402
+
+
+def build_sampler():
+    net = Model(**dict(DDPM_CFG, dropout=0.0))
+    smp = VARSampler(net, n_timesteps=10, sample_shape=[3, 32, 32], trainable_beta="fix_last")
+    load_synth_into(net)
+    return smp.to(dev)
+
+
+Bs = 4
+state = torch.randn(Bs, 3, 32, 32, generator=g).to(dev)
+zn = torch.randn(Bs, 3, 32, 32, generator=g).to(dev)
+tt = torch.tensor([1, 4, 8, 9], device=dev)
+vfix = build()
+for p_ in vfix.parameters():
+    p_.requires_grad_(False)
+
+
+def sampler_loss(smp):
+    d = smp.sample_step(state, tt, noise=zn)
+    nt = (tt < 9).float()
+    run = (d["control"] ** 2).flatten(1).mean(1) / (2 * d["sigma"].flatten() ** 2)
+    return (vfix(d["sample"], tt + 1).flatten() + (0.1 * run - 0.01 * d["entropy"].flatten()) * nt).mean()
+
+
+smp_ddp, smp_loc = build_sampler(), build_sampler()
+smp_ddp.net = DDP(smp_ddp.net, device_ids=[dev.index])
+smp_ddp.train()
+smp_loc.train()
+opt_s = torch.optim.Adam(smp_ddp.parameters(), lr=1e-4)
+ls = sampler_loss(smp_ddp)
+ls.backward()
+sampler_loss(smp_loc).backward()
+worst_s = 0.0
+for (k, p), q in zip(smp_ddp.net.module.named_parameters(), smp_loc.net.parameters()):
+    avg = q.grad.clone()
+    dist.all_reduce(avg)
+    avg /= world
+    worst_s = max(worst_s, ((p.grad - avg).norm() / avg.norm().clamp_min(1e-30)).item())
+torch.nn.utils.clip_grad_norm_(smp_ddp.parameters(), 0.1)
+opt_s.step()
+chk_s = torch.stack([p.detach().double().sum() for p in smp_ddp.parameters()]).sum()
+lo_s, hi_s = chk_s.clone(), chk_s.clone()
+dist.all_reduce(lo_s, op=dist.ReduceOp.MIN)
+dist.all_reduce(hi_s, op=dist.ReduceOp.MAX)
+ok_s = worst_s < 1e-6 and (hi_s - lo_s).abs().item() == 0.0
+flag_s = torch.tensor([1.0 if ok_s else 0.0], device=dev)
+dist.all_reduce(flag_s, op=dist.ReduceOp.MIN)
+flag = torch.minimum(flag, flag_s)
 if rank == 0:
+    print(f"DDP sampler update (DDPM U-Net) on {world} GPUs: loss {ls.item():.5f}, worst |ddp grad - mean(local grads)| rel {worst_s:.2e}, "
+          f"replica checksum spread {(hi_s - lo_s).abs().item():.1e} -> {'OK' if flag_s.item() == 1.0 else 'FAILED'}")
     print(f"DDP value-net step on {world} GPUs: loss {loss.item():.5f}, worst |ddp grad - mean(local grads)| rel {worst:.2e}, "
           f"replica checksum spread {(hi - lo).abs().item():.1e} -> {'OK' if flag.item() == 1.0 else 'FAILED'}")
 dist.destroy_process_group()
