@@ -160,3 +160,21 @@ def test_precision_switch_is_host_state_only():
         native.set_default_precision("bf16")
     with pytest.raises(ValueError):
         native.set_default_precision("tf32")
+
+
+def test_dropout_stream_ids_follow_the_forward_tape():
+    """Training-mode dropout masks are keyed by the ResnetBlock's position on the training plan's forward tape
+    (csrc/engine_train_unet.cu): conv_in = 0, then blocks / attention / resampling in execution order.  Host-side mirror."""
+    from diffusion_by_maxentirl_b200.models.DxMI.unet_small import Model
+
+    net = Model(resolution=32, in_channels=3, out_ch=3, ch=128, ch_mult=(1, 2, 2, 2), num_res_blocks=2, attn_resolutions=[16],
+                dropout=0.1)
+    ids = net.dropout_streams()
+    assert len(ids) == 8 + 2 + 12  # down, mid, up ResnetBlocks
+    order = sorted(ids, key=ids.get)
+    assert order[0] == "down.0.block.0" and ids["down.0.block.0"] == 1 and ids["down.0.block.1"] == 2
+    # level 1 has attention after every block (+1), a Downsample sits between levels (+1)
+    assert ids["down.1.block.0"] == 4 and ids["down.1.block.1"] == 6 and ids["down.2.block.0"] == 9
+    assert ids["mid.block_1"] < ids["mid.block_2"] == ids["mid.block_1"] + 2  # mid attention in between
+    assert order[-1] == "up.0.block.2" and len(set(ids.values())) == len(ids)
+    assert net.dropout_p == 0.1 and net._last_dropout_seed == 0
