@@ -715,10 +715,11 @@ struct DdpmTrainBuilder : Builder {
                 bf16* dG = (bf16*)scratch(0, (size_t)B * R * R * C * 2);
                 float* wsf = (float*)scratch(4, (size_t)B * (R / 4) * C * 27 * sizeof(float));
                 float* T = (float*)alloc((size_t)C * 27 * sizeof(float));
+                float* wsb = (float*)alloc((size_t)B * 3 * sizeof(float));
                 float **gw = gslot("conv_out.weight"), **gb = gslot("conv_out.bias");
                 const bf16* g = r.g1;
                 op([=](cudaStream_t st) {
-                    if (*gb) sum_nchw_channels(pl->dout, Bn, 3, R * R, *gb, st);
+                    if (*gb) sum_nchw_channels(pl->dout, Bn, 3, R * R, wsb, *gb, st);
                     if (*gw) {
                         conv_first_wgrad(g, pl->dout, wsf, T, Bn, R, R, C, st);
                         conv_out_wgrad_fix(T, *gw, C, st);
@@ -782,13 +783,21 @@ struct DdpmTrainBuilder : Builder {
         {
             const int tc = temb_ch, tp = TP;
             float *temb_ = temb, *t1_ = t1, *te_ = te;
+            // swish(temb) / swish(t1) once (the Linear-backward kernels would otherwise re-evaluate expf per output row)
+            float* s_temb = (float*)alloc((size_t)B * temb_ch * sizeof(float));
+            float* s_t1 = (float*)alloc((size_t)B * temb_ch * sizeof(float));
+            op([=](cudaStream_t st) {
+                silu_f32(temb_, s_temb, (long long)Bn * tc, st);
+                silu_f32(t1_, s_t1, (long long)Bn * tc, st);
+                return (int)cudaGetLastError();
+            }, 2);
             for (size_t i = 0; i < rb.size(); ++i) {
                 const int off = tp_offs[i], co = rb_cout[i];
                 const float* wtp = f32(rb[i] + ".temb_proj.weight");
                 float **gw = gslot(rb[i] + ".temb_proj.weight"), **gb = gslot(rb[i] + ".temb_proj.bias");
                 const int first = i == 0;
                 op([=](cudaStream_t st) {
-                    linear_bwd_w(d_tproj + off, tp, temb_, tc, 2, *gw, *gb, Bn, co, tc, st);
+                    linear_bwd_w(d_tproj + off, tp, s_temb, tc, 0, *gw, *gb, Bn, co, tc, st);
                     linear_bwd_x(d_tproj + off, tp, wtp, d_st, tc, Bn, co, tc, first ? 0 : 1, st);
                     return (int)cudaGetLastError();
                 }, 2);
@@ -797,7 +806,7 @@ struct DdpmTrainBuilder : Builder {
             float **g0w = gslot("temb.dense.0.weight"), **g0b = gslot("temb.dense.0.bias");
             op([=](cudaStream_t st) {
                 silu_bwd_mul(d_st, temb_, (long long)Bn * tc, st);            // -> grad w.r.t. temb
-                linear_bwd_w(d_st, tc, t1_, tc, 2, *g1w, *g1b, Bn, tc, tc, st);
+                linear_bwd_w(d_st, tc, s_t1, tc, 0, *g1w, *g1b, Bn, tc, tc, st);
                 linear_bwd_x(d_st, tc, w1, d_s1, tc, Bn, tc, tc, 0, st);
                 silu_bwd_mul(d_s1, t1_, (long long)Bn * tc, st);             // -> grad w.r.t. t1
                 linear_bwd_w(d_s1, tc, te_, ch, 0, *g0w, *g0b, Bn, tc, ch, st);

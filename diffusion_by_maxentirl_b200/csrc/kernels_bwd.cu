@@ -375,18 +375,32 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_apply_k(const bf16* __rest
     }
 }
 
-// dgamma[c] = sum_n AB[n][c].y, dbeta[c] = sum_n AB[n][c].x
-__global__ void gn_bwd_param_k(const float2* __restrict__ AB, int N, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float sa = 0.f, sb = 0.f;
-    for (int n = 0; n < N; ++n) {
-        const float2 v = AB[(long long)n * C + c];
-        sa += v.x;
-        sb += v.y;
+// dgamma[c] = sum_n AB[n][c].y, dbeta[c] = sum_n AB[n][c].x.  Block = 32 channels x 8 image lanes (lane j sums images j, j+8, ...),
+// combined through smem in a fixed order.
+__global__ void __launch_bounds__(256) gn_bwd_param_k(const float2* __restrict__ AB, int N, int C, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta) {
+    __shared__ float2 red[8][33];
+    const int col = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + col;
+    float2 a = make_float2(0.f, 0.f);
+    if (c < C)
+        for (int n = rl; n < N; n += 8) {
+            const float2 v = AB[(long long)n * C + c];
+            a.x += v.x;
+            a.y += v.y;
+        }
+    red[rl][col] = a;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sa += red[j][col].x;
+            sb += red[j][col].y;
+        }
+        if (dbeta) dbeta[c] = sa;
+        if (dgamma) dgamma[c] = sb;
     }
-    if (dbeta) dbeta[c] = sa;
-    if (dgamma) dgamma[c] = sb;
 }
 
 void group_norm_bwd(const bf16* x1, int C1, const bf16* x2, int C2, const bf16* dy, const float* ab, const float* mr, int N, int HW,
@@ -402,7 +416,7 @@ void group_norm_bwd(const bf16* x1, int C1, const bf16* x2, int C2, const bf16* 
                                                                               slabs, partial);
     gn_bwd_apply_k<<<grid, GNB_THREADS, 0, st>>>(x1, C1, x2, C2, dy, reinterpret_cast<const float2*>(ab),
                                                  reinterpret_cast<const float2*>(mr), HW, groups, silu, slabs, partial, AB, dx);
-    if (dgamma || dbeta) gn_bwd_param_k<<<(C + 127) / 128, 128, 0, st>>>(AB, N, C, dgamma, dbeta);
+    if (dgamma || dbeta) gn_bwd_param_k<<<(C + 31) / 32, 256, 0, st>>>(AB, N, C, dgamma, dbeta);
 }
 
 // ================================================================================================ U-Net backward helpers
@@ -669,6 +683,11 @@ __global__ void silu_bwd_mul_k(float* __restrict__ d, const float* __restrict__ 
     const float s = 1.f / (1.f + expf(-z));
     d[i] *= s * (1.f + z * (1.f - s));
 }
+__global__ void silu_f32_k(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = silu_exact_f(x[i]);
+}
+void silu_f32(const float* x, float* y, long long n, cudaStream_t st) { silu_f32_k<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, n); }
 void silu_bwd_mul(float* d, const float* x, long long n, cudaStream_t st) {
     silu_bwd_mul_k<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, x, n);
 }
@@ -691,15 +710,12 @@ __global__ void conv_out_wgrad_fix_k(const float* __restrict__ t, float* __restr
 void conv_out_wgrad_fix(const float* t, float* grad, int C, cudaStream_t st) {
     conv_out_wgrad_fix_k<<<(C * 27 + 255) / 256, 256, 0, st>>>(t, grad, C);
 }
-// one CTA per channel, fixed order
+// one CTA per (channel, image): out[c] accumulates over images in a second, fixed-order pass (sum_nchw_finish_k)
 __global__ void __launch_bounds__(256) sum_nchw_channels_k(const float* __restrict__ x, int N, int C, int HW, float* __restrict__ out) {
     __shared__ float red[8];
-    const int c = blockIdx.x;
+    const int c = blockIdx.x, n = blockIdx.y;
     float a = 0.f;
-    for (long long i = threadIdx.x; i < (long long)N * HW; i += 256) {
-        const long long n = i / HW, p = i % HW;
-        a += x[(n * C + c) * HW + p];
-    }
+    for (int p = threadIdx.x; p < HW; p += 256) a += x[((long long)n * C + c) * HW + p];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
@@ -707,11 +723,13 @@ __global__ void __launch_bounds__(256) sum_nchw_channels_k(const float* __restri
     if (threadIdx.x == 0) {
         float s = 0.f;
         for (int j = 0; j < 8; ++j) s += red[j];
-        out[c] = s;
+        out[(long long)n * C + c] = s;  // partial [N][C]
     }
 }
-void sum_nchw_channels(const float* x, int N, int C, int HW, float* out, cudaStream_t st) {
-    sum_nchw_channels_k<<<C, 256, 0, st>>>(x, N, C, HW, out);
+void sum_nchw_channels(const float* x, int N, int C, int HW, float* ws, float* out, cudaStream_t st) {
+    dim3 grid(C, N);
+    sum_nchw_channels_k<<<grid, 256, 0, st>>>(x, N, C, HW, ws);
+    reduce_rows_f32_k<<<(C + 31) / 32, 256, 0, st>>>(ws, N, C, out);
 }
 
 // ================================================================================================ dropout

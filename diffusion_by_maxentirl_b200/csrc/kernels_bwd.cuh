@@ -61,7 +61,10 @@ void silu_bwd_mul(float* d, const float* x, long long n, cudaStream_t st);
 // grad[o][c][tap] = t[c][o][8-tap] (t = conv_first_wgrad of (g, d_eps));  gb[o] = sum over n, pixels of d_eps[n,o,:]
 void conv_out_transpose_weights(const float* w, float* w_t, int C, cudaStream_t st);
 void conv_out_wgrad_fix(const float* t, float* grad, int C, cudaStream_t st);
-void sum_nchw_channels(const float* x, int N, int C, int HW, float* out, cudaStream_t st);
+// ws: N * C floats
+void sum_nchw_channels(const float* x, int N, int C, int HW, float* ws, float* out, cudaStream_t st);
+// y = x * sigmoid(x) (exact expf)
+void silu_f32(const float* x, float* y, long long n, cudaStream_t st);
 // training-mode dropout (unet_small.py:126-127): x[i] *= keep(i) / (1 - p) with a counter-based keep mask that depends only on
 // (seed, stream, element index) - the backward regenerates it instead of storing it.  mask_out (optional): the scaled mask itself.
 void dropout_bf16(bf16* x, long long n, float p, unsigned long long seed, unsigned stream, bf16* mask_out, cudaStream_t st);
