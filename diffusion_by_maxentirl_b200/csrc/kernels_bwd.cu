@@ -156,7 +156,20 @@ __global__ void __launch_bounds__(256) colsum_bf16_k(const bf16* __restrict__ x,
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = 0.f;
     if (pl < PL) {
-        for (long long r = r0 + pl; r < r1; r += PL) {
+        long long r = r0 + pl;
+        for (; r + 3LL * PL < r1; r += 4LL * PL) {  // 4 independent 16-byte loads in flight per thread
+            bf16x8 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(x + (r + (long long)u * PL) * C + cv * 8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] += f[j];
+            }
+        }
+        for (; r < r1; r += PL) {
             float f[8];
             unpack8(*reinterpret_cast<const bf16x8*>(x + r * C + cv * 8), f);
 #pragma unroll
