@@ -188,6 +188,87 @@ EDM_CFGS = {
 }
 
 
+def ddpm_resblock_order(n_levels=4, num_res_blocks=2):
+    """ResnetBlock prefixes in execution order (= the order of the reference's nn.Dropout calls in train() mode)."""
+    order = [f"down.{l}.block.{b}" for l in range(n_levels) for b in range(num_res_blocks)]
+    order += ["mid.block_1", "mid.block_2"]
+    order += [f"up.{l}.block.{b}" for l in reversed(range(n_levels)) for b in range(num_res_blocks + 1)]
+    return order
+
+
+def train_dropout_masks(shapes, p, seed):
+    """Deterministic scaled keep masks (0 or 1/(1-p)), one per ResnetBlock, NCHW fp32 - shared by the generator and the CPU test."""
+    g = torch.Generator().manual_seed(seed)
+    return {k: (torch.rand(shp, generator=g) >= p).float() / (1.0 - p) for k, shp in shapes.items()}
+
+
+def gen_ddpm_train(B=2, p_drop=0.3):
+    """Row a9 (training mode): the reference Model in train() mode, its nn.Dropout replaced by host-supplied masks, forward +
+    backward of a fixed linear functional of eps; the oracle with the same masks must reproduce eps and every gradient.
+    Writes tests/golden/ddpm_train_B2.npz (eps and a few gradient tensors of the reference)."""
+    import_reference()
+    from models.DxMI.unet_small import Model
+
+    torch.manual_seed(0)
+    net = Model(**dict(DDPM_CFG, dropout=p_drop))
+    sd = load_synth(net, skip=())
+    net.train()
+    cm = {"0": 128, "1": 256, "2": 256, "3": 256}
+    res = {"0": 32, "1": 16, "2": 8, "3": 4}
+    shapes = {}
+    for k in ddpm_resblock_order():
+        lvl = k.split(".")[1] if not k.startswith("mid") else "3"
+        shapes[k] = (B, cm[lvl], res[lvl], res[lvl])
+    masks = train_dropout_masks(shapes, p_drop, seed=77)
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([394.07648, 66.86534])[:B]
+    coef = torch.randn(B, 3, 32, 32, generator=g)
+    it = iter([masks[k] for k in ddpm_resblock_order()])
+    orig = torch.nn.functional.dropout
+
+    def dropout(inp, p=0.5, training=True, inplace=False):
+        assert training and abs(p - p_drop) < 1e-12
+        m = next(it)
+        assert m.shape == inp.shape, (m.shape, inp.shape)
+        return inp * m
+
+    torch.nn.functional.dropout = dropout
+    try:
+        ref = net(x, t)
+    finally:
+        torch.nn.functional.dropout = orig
+    (ref * coef).sum().backward()
+    rsd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = nets.ddpm_unet_forward(rsd, x, t, dropout_masks=masks)
+    (out * coef).sum().backward()
+    e = rel_l2(out, ref)
+    worst = max((rel_l2(rsd[k].grad, p_.grad), k) for k, p_ in net.named_parameters() if not k.endswith(".k.bias"))
+    print(f"[ddpm train B={B} p={p_drop}] oracle vs reference: eps {e:.2e}, worst gradient {worst[1]} {worst[0]:.2e}")
+    assert e < 1e-5 and worst[0] < 1e-4
+    keep = ["conv_out.weight", "conv_in.weight", "mid.attn_1.q.weight", "down.1.downsample.conv.weight", "up.1.block.0.nin_shortcut.weight",
+            "up.2.upsample.conv.weight", "temb.dense.0.weight", "down.0.block.0.temb_proj.weight", "mid.block_1.norm2.weight"]
+    grads = dict(net.named_parameters())
+    # ---- value net under autograd (trainer.py:244-326): reference vs oracle, asserted here (no fixture: no randomness involved)
+    from models.modules import IGEBMEncoderV2
+    from models.value import TimeIndependentValue
+
+    value = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
+    vsd = load_synth(value, seed=1)
+    xv = torch.randn(4, 3, 32, 32, generator=g).requires_grad_(True)
+    cv = torch.randn(4, generator=g)
+    (value(xv, 3).flatten() * cv).sum().backward()
+    rv = {k: v.clone().requires_grad_(True) for k, v in vsd.items()}
+    xo = xv.detach().clone().requires_grad_(True)
+    (nets.value_forward(rv, xo).flatten() * cv).sum().backward()
+    wv = max(rel_l2(rv[k].grad, p_.grad) for k, p_ in value.named_parameters())
+    print(f"[value train] oracle vs reference: worst parameter gradient {wv:.2e}, input gradient {rel_l2(xo.grad, xv.grad):.2e}")
+    assert wv < 1e-5 and rel_l2(xo.grad, xv.grad) < 1e-5
+    # big tensors: the first 8 output channels only (fixture size)
+    np.savez_compressed(os.path.join(GOLD, "ddpm_train_B2.npz"), eps=ref.detach().numpy(), p_drop=np.float64(p_drop),
+                        **{"grad:" + k: grads[k].grad.numpy()[:8] for k in keep})
+
+
 def gen_edm(name, B, T=None, small=None):
     import_reference()
     from models.cm.script_util import create_model_and_diffusion
@@ -265,12 +346,15 @@ if __name__ == "__main__":
     ap.add_argument("--edm", action="store_true")
     ap.add_argument("--edm-full", action="store_true")
     ap.add_argument("--skip-ddpm", action="store_true")
+    ap.add_argument("--train", action="store_true", help="row a9: pin the training-mode (dropout + autograd) oracle")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     if not args.skip_ddpm:
         gen_ddpm(T=10, B=2)
         gen_ddpm(T=4, B=2)
+    if args.train:
+        gen_ddpm_train()
     if args.edm:
         gen_edm("in64", B=2, T=4, small=dict(image_size=32, num_channels=64, num_res_blocks=1,
                                              channel_mult="1,2,3,4", attention_resolutions="16,8,4"))

@@ -229,3 +229,44 @@ def test_edm_noise_sigma_modes():
     assert torch.allclose(samplers.edm_noise_sigma(sched, lb, 3, 10, "fix_last"), torch.exp(lb[3]))
     assert torch.equal(samplers.edm_noise_sigma(sched, lb, 7, 10, "fix_last3"), sched["sigma_up"][7])
     assert torch.equal(samplers.edm_noise_sigma(sched, lb, 2, 10, False), sched["sigma_up"][2])
+
+
+def test_training_mode_oracle_reproduces_reference_gradients():
+    """Row a9: tests/golden/ddpm_train_B2.npz holds eps and gradient slices of the *reference* unet_small.Model in train() mode
+    (dropout 0.3 replaced by host-supplied masks, oracle/gen_golden.py::gen_ddpm_train, where the full comparison was bit-exact).
+    The oracle with the same masks + torch autograd must reproduce them - this is the yardstick of the CUDA backward tests."""
+    import json
+    import os
+
+    import numpy as np
+
+    from oracle import nets, synth
+    from oracle.gen_golden import ddpm_resblock_order, train_dropout_masks
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddpm_train_B2.npz"))
+    shapes = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ddpm_shapes.json")))["net"]
+    sd = synth.synth_state_dict({k: tuple(v) for k, v in shapes.items()})
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    B, p_drop = 2, float(gold["p_drop"])
+    cm, res = {"0": 128, "1": 256, "2": 256, "3": 256}, {"0": 32, "1": 16, "2": 8, "3": 4}
+    mshapes = {}
+    for k in ddpm_resblock_order():
+        lvl = k.split(".")[1] if not k.startswith("mid") else "3"
+        mshapes[k] = (B, cm[lvl], res[lvl], res[lvl])
+    masks = train_dropout_masks(mshapes, p_drop, seed=77)
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([394.07648, 66.86534])
+    coef = torch.randn(B, 3, 32, 32, generator=g)
+    out = nets.ddpm_unet_forward(sd, x, t, dropout_masks=masks)
+    (out * coef).sum().backward()
+    assert torch.allclose(out.detach(), torch.from_numpy(gold["eps"]), rtol=1e-5, atol=1e-5)
+    n = 0
+    for key in gold.files:
+        if key.startswith("grad:"):
+            ref = torch.from_numpy(gold[key])
+            got = sd[key[5:]].grad[:8]
+            err = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+            assert err < 1e-4, (key, err)
+            n += 1
+    assert n >= 8
