@@ -18,6 +18,9 @@ _BINDINGS = [
     ("models.cm.script_util", "create_model", "models.cm.script_util", "create_model"),
     ("models.cm.script_util", "create_model_and_diffusion", "models.cm.script_util", "create_model_and_diffusion"),
     ("models.modules", "IGEBMEncoderV2", "models.modules", "IGEBMEncoderV2"),
+    # callers either side of the path: the replay-buffer helpers of the trainer
+    ("models.DxMI.trainer", "append_buffer", "models.DxMI.trainer", "append_buffer"),
+    ("models.DxMI.trainer", "reset_buffer", "models.DxMI.trainer", "reset_buffer"),
 ]
 
 

@@ -135,7 +135,7 @@ def test_install_rebinds_reference_symbols():
     )
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
-    assert r.stdout.strip().endswith("8")
+    assert r.stdout.strip().endswith("10")
 
 
 def test_precision_switch_is_host_state_only():
