@@ -264,6 +264,11 @@ def gen_ddpm_train(B=2, p_drop=0.3):
     wv = max(rel_l2(rv[k].grad, p_.grad) for k, p_ in value.named_parameters())
     print(f"[value train] oracle vs reference: worst parameter gradient {wv:.2e}, input gradient {rel_l2(xo.grad, xv.grad):.2e}")
     assert wv < 1e-5 and rel_l2(xo.grad, xv.grad) < 1e-5
+    vg = dict(value.named_parameters())
+    np.savez_compressed(os.path.join(GOLD, "value_train_B4.npz"), x=xv.detach().numpy(), coef=cv.numpy(), dx=xv.grad.numpy(),
+                        **{"grad:" + k: vg[k].grad.numpy()[:8] for k in ("net.conv1.weight", "net.blocks.0.conv2.weight",
+                                                                          "net.blocks.2.skip.0.weight", "net.blocks.5.conv1.weight",
+                                                                          "net.linear.weight", "net.out_scale.weight")})
     # big tensors: the first 8 output channels only (fixture size)
     np.savez_compressed(os.path.join(GOLD, "ddpm_train_B2.npz"), eps=ref.detach().numpy(), p_drop=np.float64(p_drop),
                         **{"grad:" + k: grads[k].grad.numpy()[:8] for k in keep})

@@ -270,3 +270,27 @@ def test_training_mode_oracle_reproduces_reference_gradients():
             assert err < 1e-4, (key, err)
             n += 1
     assert n >= 8
+
+
+def test_value_net_oracle_reproduces_reference_gradients():
+    """tests/golden/value_train_B4.npz: parameter-gradient slices and the input gradient of the *reference* TimeIndependentValue under
+    autograd (oracle/gen_golden.py::gen_ddpm_train, bit-exact there); the oracle must reproduce them without /root/reference."""
+    import json
+    import os
+
+    import numpy as np
+
+    from oracle import nets, synth
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.load(os.path.join(here, "golden", "value_train_B4.npz"))
+    shapes = json.load(open(os.path.join(here, "golden", "ddpm_shapes.json")))["value"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.synth_state_dict({k: tuple(v) for k, v in shapes.items()}, seed=1).items()}
+    x = torch.from_numpy(gold["x"]).requires_grad_(True)
+    (nets.value_forward(sd, x).flatten() * torch.from_numpy(gold["coef"])).sum().backward()
+    assert torch.allclose(x.grad, torch.from_numpy(gold["dx"]), rtol=1e-4, atol=1e-7)
+    for key in gold.files:
+        if key.startswith("grad:"):
+            ref = torch.from_numpy(gold[key])
+            err = float((sd[key[5:]].grad[:8] - ref).norm() / ref.norm().clamp_min(1e-30))
+            assert err < 1e-4, (key, err)
