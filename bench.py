@@ -366,7 +366,11 @@ def main():
     if rank == 0:
         pk, pk_kind = peaks()
         lib.dxmi_set_option(b"time_gemms", 1)
+        lib.dxmi_set_option(b"rollout_split", 1)  # per-launch durations need the launches un-overlapped (one stream)
         kk = max(2, min(K, 5))
+        eager_rollout(dev_noise)  # builds the un-split plan
+        torch.cuda.synchronize()
+        L.check(lib.dxmi_gemm_timing(C.byref(C.c_double()), C.byref(C.c_double()), C.byref(C.c_longlong())))
         for _ in range(kk):
             eager_rollout(dev_noise)  # per-launch CUDA events need eager launches
         torch.cuda.synchronize()

@@ -157,10 +157,13 @@ def check(rc, what=""):
         raise RuntimeError(f"libdxmi_b200 {what} failed (rc={rc}): {last_error()}")
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Current torch stream of `device` (a torch.device / index / tensor; default: the current device)."""
     import torch
 
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if device is not None and hasattr(device, "device"):
+        device = device.device
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

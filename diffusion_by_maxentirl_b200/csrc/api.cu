@@ -18,6 +18,13 @@ struct dxmi_net_s {
 static thread_local char g_api_err[768] = "";
 static void set_err(const char* m) { snprintf(g_api_err, sizeof g_api_err, "%s", m); }
 
+static int g_rollout_split = 1;      // option "rollout_split": sub-batches per rollout (1 = off, the default: measured neutral)
+static int g_rollout_split_min = 32; // option "rollout_split_min": smallest sub-batch worth splitting into
+static void dxmi_set_rollout_split(int split, int min_sub) {
+    if (split >= 1) g_rollout_split = split > 8 ? 8 : split;
+    if (min_sub >= 1) g_rollout_split_min = min_sub;
+}
+
 extern "C" {
 
 const char* dxmi_last_error(void) { return g_api_err; }
@@ -58,6 +65,14 @@ int dxmi_set_option(const char* name, int value) {
     }
     if (!strcmp(name, "dbg_mode")) {
         set_dbg_mode(value);
+        return 0;
+    }
+    if (!strcmp(name, "rollout_split")) {  // read per rollout call
+        dxmi_set_rollout_split(value, -1);
+        return 0;
+    }
+    if (!strcmp(name, "rollout_split_min")) {
+        dxmi_set_rollout_split(-1, value);
         return 0;
     }
     if (!strcmp(name, "time_gemms")) {
@@ -152,6 +167,9 @@ int dxmi_bind_weight(dxmi_net_t net, const char* key, const void* dev_ptr, int d
     }
     Bound& b = net->net.bound[key];
     const bool dtype_changed = b.ptr && b.dtype != dtype;
+    // plans capture borrowed fp32 pointers (biases, GroupNorm affine, Linear weights) by value: a moved parameter
+    // invalidates them; dxmi_finalize drops and lazily rebuilds the plans
+    if (net->net.finalized && b.ptr && b.ptr != dev_ptr) net->net.ptr_moved = true;
     b.ptr = dev_ptr;
     b.dtype = dtype;
     b.shape.assign(shape, shape + ndim);
@@ -172,10 +190,11 @@ static int run_pack(Net& n, cudaStream_t st) {
     return 0;
 }
 
-static Plan* get_plan(Net& n, int B) {
-    auto it = n.plans.find(B);
+// `inst` > 0: further plan instances (own arena) for the same batch size - the sub-batches of a split rollout
+static Plan* get_plan(Net& n, int B, int inst = 0) {
+    const int key = B + (inst << 24);
+    auto it = n.plans.find(key);
     if (it != n.plans.end()) return it->second.get();
-    cudaSetDevice(n.device);
     std::unique_ptr<Plan> p(new Plan());
     p->B = B;
     const size_t jobs_before = n.pack_jobs.size();
@@ -187,7 +206,7 @@ static Plan* get_plan(Net& n, int B) {
     }
     (void)jobs_before;
     Plan* raw = p.get();
-    n.plans[B] = std::move(p);
+    n.plans[key] = std::move(p);
     return raw;
 }
 
@@ -200,6 +219,15 @@ int dxmi_finalize(dxmi_net_t net, dxmi_stream_t stream) {
             snprintf(g_api_err, sizeof g_api_err, "dxmi_finalize: state_dict key '%s' was never bound", k.c_str());
             return -7;
         }
+    }
+    DeviceGuard guard(n.device);
+    if (n.ptr_moved) {
+        // a parameter's storage moved (p.data = ..., load_state_dict(assign=True), .to(), EMA swap): every plan's closures
+        // hold the old borrowed pointers. Drop the plans (rebuilt lazily per batch size); packed / derived buffers and
+        // their pack jobs resolve pointers at run time and stay.
+        cudaStreamSynchronize((cudaStream_t)stream);
+        n.drop_plans();
+        n.ptr_moved = false;
     }
     if (!n.finalized) {
         // building the B=1 plan registers every packed / derived weight and its pack job
@@ -214,11 +242,13 @@ int dxmi_repack(dxmi_net_t net, dxmi_stream_t stream) {
         set_err("dxmi_repack: handle not finalized");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     return run_pack(net->net, (cudaStream_t)stream);
 }
 
 size_t dxmi_workspace_bytes(dxmi_net_t net, int B) {
     if (!net) return 0;
+    DeviceGuard guard(net->net.device);
     Plan* p = get_plan(net->net, B);
     return p ? p->arena_bytes : 0;
 }
@@ -270,6 +300,7 @@ int dxmi_unet_forward(dxmi_net_t net, const float* x, const float* x_scale, cons
         set_err("dxmi_unet_forward: handle not finalized");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     if (net->net.a.arch == DXMI_ARCH_IGEBM_V2) {
         set_err("dxmi_unet_forward called on a value-net handle");
         return -2;
@@ -289,6 +320,7 @@ int dxmi_value_forward(dxmi_net_t net, const float* x, float* out, int B, dxmi_s
         set_err("dxmi_value_forward: handle not finalized");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     if (net->net.a.arch != DXMI_ARCH_IGEBM_V2) {
         set_err("dxmi_value_forward called on a U-Net handle");
         return -2;
@@ -320,7 +352,6 @@ static int run_ops(const std::vector<std::function<int(cudaStream_t)>>& ops, con
 static Plan* get_train_plan(Net& n, int B, cudaStream_t st) {
     auto it = n.train_plans.find(B);
     if (it != n.train_plans.end()) return it->second.get();
-    cudaSetDevice(n.device);
     std::unique_ptr<Plan> p(new Plan());
     p->B = B;
     const size_t jobs_before = n.pack_jobs.size();
@@ -353,6 +384,7 @@ int dxmi_value_forward_train(dxmi_net_t net, const float* x, float* out, int B, 
         set_err("dxmi_value_forward_train: handle not finalized");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     if (net->net.a.arch != DXMI_ARCH_IGEBM_V2) {
         set_err("dxmi_value_forward_train called on a U-Net handle");
         return -2;
@@ -378,6 +410,7 @@ int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, floa
         set_err("dxmi_unet_forward_train: handle not finalized");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     if (net->net.a.arch != DXMI_ARCH_DDPM_UNET) {
         set_err("dxmi_unet_forward_train: the U-Net backward is built for the DDPM U-Net only");
         return -2;
@@ -405,6 +438,7 @@ int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, int B,
         set_err("dxmi_unet_backward: handle not finalized");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     auto it = net->net.train_plans.find(B);
     if (it == net->net.train_plans.end() || !it->second->fwd_valid) {
         set_err("dxmi_unet_backward: no saved activations for this batch size (call dxmi_unet_forward_train first; one backward "
@@ -424,6 +458,7 @@ int dxmi_value_backward(dxmi_net_t net, const float* x, const float* dout, float
         set_err("dxmi_value_backward: handle not finalized");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     auto it = net->net.train_plans.find(B);
     if (it == net->net.train_plans.end() || !it->second->fwd_valid) {
         set_err("dxmi_value_backward: no saved activations for this batch size (call dxmi_value_forward_train first; one "
@@ -461,38 +496,119 @@ int dxmi_edm_step(const float* x, const float* F, const float* z, const float* c
     return (int)cudaGetLastError();
 }
 
+// ---- batch-split rollouts -------------------------------------------------------------------------------------------
+// Every image's trajectory is independent and the whole path is bitwise batch-invariant, so a rollout of B
+// images may run as S independent rollouts of B/S images on S streams: results are bit-identical to the unsplit call.
+// What it buys (profiles/r02_split_*): the HBM-bound kernels (GroupNorm apply, transition) and the small-map GEMMs that
+// fill 32-128 of the 148 SMs overlap another sub-batch's tensor-bound GEMMs instead of serialising behind them.
+struct SubRollout {
+    Plan* p;
+    cudaStream_t st;
+    int b0, Bs;
+};
+
+static int split_count(int B) {
+    int S = g_rollout_split;
+    if (getenv("DXMI_TIME_OPS")) return 1;
+    while (S > 1 && (B % S || B / S < g_rollout_split_min)) --S;
+    return S < 1 ? 1 : S;
+}
+
+static int make_subs(Net& n, int B, cudaStream_t st, std::vector<SubRollout>& subs) {
+    const int S = split_count(B);
+    const int Bs = B / S;
+    while ((int)n.side_streams.size() < S - 1) {
+        cudaStream_t s2;
+        cudaEvent_t e2;
+        if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess) {
+            set_err("rollout split: cannot create side stream / event");
+            return -30;
+        }
+        n.side_streams.push_back(s2);
+        n.join_events.push_back(e2);
+    }
+    if (S > 1 && !n.fork_event && cudaEventCreateWithFlags(&n.fork_event, cudaEventDisableTiming) != cudaSuccess) {
+        set_err("rollout split: cannot create fork event");
+        return -30;
+    }
+    for (int k = 0; k < S; ++k) {
+        Plan* p = get_plan(n, Bs, S > 1 ? k : 0);
+        if (!p) return -3;
+        subs.push_back({p, k == 0 ? st : n.side_streams[k - 1], k * Bs, Bs});
+    }
+    return 0;
+}
+static void fork_subs(Net& n, std::vector<SubRollout>& subs, cudaStream_t st) {
+    if (subs.size() < 2) return;
+    cudaEventRecord(n.fork_event, st);
+    for (size_t k = 1; k < subs.size(); ++k) cudaStreamWaitEvent(subs[k].st, n.fork_event, 0);
+}
+static void join_subs(Net& n, std::vector<SubRollout>& subs, cudaStream_t st) {
+    for (size_t k = 1; k < subs.size(); ++k) {
+        cudaEventRecord(n.join_events[k - 1], subs[k].st);
+        cudaStreamWaitEvent(st, n.join_events[k - 1], 0);
+    }
+}
+// one network forward per sub-batch, launches interleaved op by op so that an eager (un-graphed) call feeds all streams
+static int run_plans(Net& n, std::vector<SubRollout>& subs) {
+    if (subs.size() == 1) return run_plan(n, subs[0].p, subs[0].st);
+    const size_t nops = subs[0].p->ops.size();
+    for (size_t i = 0; i < nops; ++i)
+        for (auto& sb : subs) {
+            int r = sb.p->ops[i](sb.st);
+            if (r) {
+                snprintf(g_api_err, sizeof g_api_err, "kernel launch failed (%d): %s | %s", r, cudaGetErrorString((cudaError_t)r),
+                         gemm_op_last_error());
+                return r;
+            }
+        }
+    for (auto& sb : subs) count_launches(sb.p->launches_per_run);
+    return 0;
+}
+
 int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_dev, int T, const float* noise,
                      float* l_sample, float* mean, float* control, float* logp, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized || net->net.a.arch != DXMI_ARCH_DDPM_UNET) {
         set_err("dxmi_var_rollout: needs a finalized DDPM U-Net handle");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     Net& n = net->net;
-    Plan* p = get_plan(n, B);
-    if (!p) return -3;
     cudaStream_t st = (cudaStream_t)stream;
+    std::vector<SubRollout> subs;
+    int r = make_subs(n, B, st, subs);
+    if (r) return r;
     const long long chw = (long long)n.a.in_channels * n.a.resolution * n.a.resolution;
     const long long bchw = chw * B;
     // x_0 = first noise tensor (var_sampler.py:242)
     cudaMemcpyAsync(l_sample, noise, bchw * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    fork_subs(n, subs, st);
     for (int i = 0; i < T; ++i) {
-        var_fill(p->tbuf, p->coef, p->coef + B, p->coef + 2 * B, B, sched_host[3 * i + 0], sched_host[3 * i + 1],
-                 sched_host[3 * i + 2], sigma_dev + i, st);
-        count_launches(1);
-        const float* xi = l_sample + (long long)i * bchw;
-        p->x = xi;
-        p->x_scale = nullptr;
-        p->t = p->tbuf;
-        p->y = nullptr;
-        p->out = p->eps;
-        int r = run_plan(n, p, st);
+        for (auto& sb : subs) {
+            Plan* p = sb.p;
+            var_fill(p->tbuf, p->coef, p->coef + sb.Bs, p->coef + 2 * sb.Bs, sb.Bs, sched_host[3 * i + 0], sched_host[3 * i + 1],
+                     sched_host[3 * i + 2], sigma_dev + i, sb.st);
+            count_launches(1);
+            p->x = l_sample + (long long)i * bchw + sb.b0 * chw;
+            p->x_scale = nullptr;
+            p->t = p->tbuf;
+            p->y = nullptr;
+            p->out = p->eps;
+        }
+        r = run_plans(n, subs);
         if (r) return r;
-        var_step(xi, p->eps, noise + (long long)(i + 1) * bchw, p->coef, p->coef + B, p->coef + 2 * B,
-                 l_sample + (long long)(i + 1) * bchw, mean ? mean + (long long)i * bchw : nullptr,
-                 control ? control + (long long)i * bchw : nullptr, logp ? logp + (long long)i * B : nullptr, B, (int)chw,
-                 st);
-        count_launches(1);
+        for (auto& sb : subs) {
+            Plan* p = sb.p;
+            const long long o = sb.b0 * chw;
+            var_step(p->x, p->eps, noise + (long long)(i + 1) * bchw + o, p->coef, p->coef + sb.Bs, p->coef + 2 * sb.Bs,
+                     l_sample + (long long)(i + 1) * bchw + o, mean ? mean + (long long)i * bchw + o : nullptr,
+                     control ? control + (long long)i * bchw + o : nullptr, logp ? logp + (long long)i * B + sb.b0 : nullptr, sb.Bs,
+                     (int)chw, sb.st);
+            count_launches(1);
+        }
     }
+    join_subs(n, subs, st);
     return (int)cudaGetLastError();
 }
 
@@ -502,34 +618,44 @@ int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, const float* sigma
         set_err("dxmi_edm_rollout: needs a finalized ADM U-Net handle");
         return -1;
     }
+    DeviceGuard guard(net->net.device);
     Net& n = net->net;
     if ((n.a.num_classes > 0) != (y != nullptr)) {
         set_err("dxmi_edm_rollout: must specify y if and only if the model is class-conditional");  // cm/unet.py:770-772
         return -2;
     }
-    Plan* p = get_plan(n, B);
-    if (!p) return -3;
     cudaStream_t st = (cudaStream_t)stream;
+    std::vector<SubRollout> subs;
+    int r = make_subs(n, B, st, subs);
+    if (r) return r;
     const long long chw = (long long)n.a.in_channels * n.a.resolution * n.a.resolution;
     const long long bchw = chw * B;
     cudaMemcpyAsync(l_sample, noise, bchw * sizeof(float), cudaMemcpyDeviceToDevice, st);  // x_0 (already sigma_max * z)
+    fork_subs(n, subs, st);
     for (int i = 0; i < T; ++i) {
-        float* coef = p->coef;           // [B, 5]
-        float* x_scale = p->coef + 5 * B;  // [B]
-        edm_fill(coef, x_scale, p->tbuf, B, sched_host + 6 * i, sigma_noise_dev + i, st);
-        count_launches(1);
-        const float* xi = l_sample + (long long)i * bchw;
-        p->x = xi;
-        p->x_scale = x_scale;
-        p->t = p->tbuf;
-        p->y = y;
-        p->out = p->eps;
-        int r = run_plan(n, p, st);
+        for (auto& sb : subs) {
+            Plan* p = sb.p;
+            float* coef = p->coef;                 // [Bs, 5]
+            float* x_scale = p->coef + 5 * sb.Bs;  // [Bs]
+            edm_fill(coef, x_scale, p->tbuf, sb.Bs, sched_host + 6 * i, sigma_noise_dev + i, sb.st);
+            count_launches(1);
+            p->x = l_sample + (long long)i * bchw + sb.b0 * chw;
+            p->x_scale = x_scale;
+            p->t = p->tbuf;
+            p->y = y ? y + sb.b0 : nullptr;
+            p->out = p->eps;
+        }
+        r = run_plans(n, subs);
         if (r) return r;
-        edm_step(xi, p->eps, noise + (long long)(i + 1) * bchw, coef, l_sample + (long long)(i + 1) * bchw,
-                 mean ? mean + (long long)i * bchw : nullptr, B, (int)chw, st);
-        count_launches(1);
+        for (auto& sb : subs) {
+            Plan* p = sb.p;
+            const long long o = sb.b0 * chw;
+            edm_step(p->x, p->eps, noise + (long long)(i + 1) * bchw + o, p->coef, l_sample + (long long)(i + 1) * bchw + o,
+                     mean ? mean + (long long)i * bchw + o : nullptr, sb.Bs, (int)chw, sb.st);
+            count_launches(1);
+        }
     }
+    join_subs(n, subs, st);
     return (int)cudaGetLastError();
 }
 

@@ -238,13 +238,17 @@ struct Builder {
         bool fresh = false;
         float* d = (float*)derived_buf("sum:" + name, n * sizeof(float), &fresh);
         if (!d || !fresh) return d;
-        const float* pa = f32(ka);
-        const float* pb = f32(kb);
+        f32(ka);  // registers the fp16 -> fp32 cast jobs (if any) *before* this one, so ordering is correct
+        f32(kb);
         Net* np = &net;
-        (void)np;
-        // note: f32() of an fp16 tensor registered its cast job *before* this one, so ordering is correct
-        net.pack_jobs.push_back([pa, pb, d, n](cudaStream_t st) {
-            vec_add_f32(pa, pb, d, n, st);
+        // the operand pointers are resolved when the job runs: a borrowed parameter may have moved since (re-bind)
+        net.pack_jobs.push_back([np, ka, kb, d, n](cudaStream_t st) {
+            auto resolve = [np](const std::string& key) -> const float* {
+                const Bound& bb = np->bound[key];
+                if (bb.dtype == DXMI_F32) return (const float*)bb.ptr;
+                return (const float*)np->derived["f32:" + key];
+            };
+            vec_add_f32(resolve(ka), resolve(kb), d, n, st);
             count_launches(1);
         });
         return d;

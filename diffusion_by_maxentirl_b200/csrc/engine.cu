@@ -29,12 +29,22 @@ static int g_opt_gn_fused = 0;
 int gn_fused_option() { return g_opt_gn_fused; }
 void set_gn_fused(int v) { g_opt_gn_fused = v; }
 
-Net::~Net() {
-    for (void* p : owned) cudaFree(p);
+void Net::drop_plans() {
     for (auto& kv : plans)
         if (kv.second && kv.second->arena) cudaFree(kv.second->arena);
     for (auto& kv : train_plans)
         if (kv.second && kv.second->arena) cudaFree(kv.second->arena);
+    plans.clear();
+    train_plans.clear();
+}
+
+Net::~Net() {
+    DeviceGuard g(device);
+    drop_plans();
+    for (void* p : owned) cudaFree(p);
+    for (auto s : side_streams) cudaStreamDestroy(s);
+    for (auto e : join_events) cudaEventDestroy(e);
+    if (fork_event) cudaEventDestroy(fork_event);
 }
 
 // ================================================================================================ specs

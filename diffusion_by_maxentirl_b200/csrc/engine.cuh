@@ -73,10 +73,30 @@ struct Net {
     std::vector<std::function<void(cudaStream_t)>> pack_jobs;
     std::vector<void*> owned;
     bool finalized = false;
+    bool ptr_moved = false;  // a bound pointer changed after finalize: plans hold stale borrowed fp32 pointers -> rebuilt by dxmi_finalize
     std::map<int, std::unique_ptr<Plan>> plans;
     std::map<int, std::unique_ptr<Plan>> train_plans;      // forward-with-saved-activations + backward, per batch size
     std::unordered_map<std::string, float*> grad;          // dxmi_bind_grad: fp32 gradient buffer per state_dict key (or null)
+    // batch-split rollouts (api.cu): sub-batch k > 0 runs its whole T-step chain on side_streams[k-1], concurrently with the
+    // others (HBM-bound GroupNorm / transition kernels and under-filled small-map GEMMs of one sub-batch overlap the
+    // tensor-bound GEMMs of another); created lazily, before any CUDA-graph capture (GraphedRollout warms up eagerly)
+    std::vector<cudaStream_t> side_streams;
+    std::vector<cudaEvent_t> join_events;
+    cudaEvent_t fork_event = nullptr;
+    void drop_plans();  // frees every plan arena (inference + training); plans are rebuilt lazily per batch size
     ~Net();
+};
+
+// RAII: make `device` current for the duration of a C-ABI call and restore the caller's device afterwards
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
 };
 
 // spec (expected keys) builders

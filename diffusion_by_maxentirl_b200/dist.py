@@ -29,7 +29,7 @@ def quantize_u8(samples):
         raise RuntimeError("quantize_u8 runs on CUDA only (no CPU fallback)")
     x = samples.detach().contiguous().float()
     out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-    L.check(L.lib().dxmi_quantize_u8(L.ptr(x), L.ptr(out), x.numel(), L.stream_ptr()), "dxmi_quantize_u8")
+    L.check(L.lib().dxmi_quantize_u8(L.ptr(x), L.ptr(out), x.numel(), L.stream_ptr(x)), "dxmi_quantize_u8")
     return out
 
 

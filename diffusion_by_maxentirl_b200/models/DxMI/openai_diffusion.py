@@ -104,7 +104,7 @@ class OpenAIDiffusion:
         z = torch.randn_like(x) if noise is None else noise.to(device=device, dtype=torch.float32).contiguous()
         xn, mu = torch.empty_like(x), torch.empty_like(x)
         L.check(L.lib().dxmi_edm_step(L.ptr(x), L.ptr(F), L.ptr(z), L.ptr(coef), L.ptr(xn), L.ptr(mu), B, x[0].numel(),
-                                      L.stream_ptr()), "dxmi_edm_step")
+                                      L.stream_ptr(x)), "dxmi_edm_step")
         return {"sample": xn, "mean": mu, "sigma": s_noise.clamp(1e-4, None)}
 
     def sample(self, n_sample, device, i_class=None, enable_grad=False, x0=None, noise=None):
@@ -148,7 +148,7 @@ class OpenAIDiffusion:
         L.check(
             L.lib().dxmi_edm_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), L.ptr(s_noise), T, L.ptr(buf),
                                      L.ptr(i_class),
-                                     L.ptr(l_sample), L.ptr(mean), B, L.stream_ptr()),
+                                     L.ptr(l_sample), L.ptr(mean), B, L.stream_ptr(device)),
             "dxmi_edm_rollout")
         sig_dev = s_noise.clamp(1e-4, None)
         return {"sample": l_sample[T], "l_sample": [l_sample[i] for i in range(T + 1)], "y": i_class,

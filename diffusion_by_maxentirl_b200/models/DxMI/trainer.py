@@ -28,7 +28,9 @@ def _stack_steps(seq, n_seq):
 
 def _append(buf, key, new):
     old = buf[key]
-    buf[key] = new if old.numel() == 0 else torch.cat((old, new))
+    # the first append copies too (the reference always goes through torch.cat): `new` may be a view of the rollout's own
+    # tensors, which a GraphedRollout overwrites on its next replay
+    buf[key] = new.clone() if old.numel() == 0 else torch.cat((old, new))
 
 
 def append_buffer(state_buffer, d_sample):

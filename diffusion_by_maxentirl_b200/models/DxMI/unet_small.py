@@ -22,7 +22,7 @@ class _UNetFunction(torch.autograd.Function):
         seed = int(torch.randint(0, 2**62, (1,)).item()) if module.dropout_p > 0 else 0
         module._last_dropout_seed = seed
         L.check(L.lib().dxmi_unet_forward_train(h, L.ptr(xc), L.ptr(tc), L.ptr(out), float(module.dropout_p), seed, B,
-                                                L.stream_ptr()), "dxmi_unet_forward_train")
+                                                L.stream_ptr(xc)), "dxmi_unet_forward_train")
         ctx.module, ctx.B, ctx.x = module, B, xc
         ctx.token = module._train_token = object()
         ctx.need_param = [p.requires_grad for p in params]
@@ -47,7 +47,7 @@ class _UNetFunction(torch.autograd.Function):
             L.check(lib.dxmi_bind_grad(h, k.encode(), L.ptr(g) if need else None), f"bind_grad {k}")
             grads.append(g.view(m._param(k).shape) if need else None)
         d = dout.detach().contiguous().float()
-        L.check(lib.dxmi_unet_backward(h, L.ptr(ctx.x), L.ptr(d), ctx.B, L.stream_ptr()), "dxmi_unet_backward")
+        L.check(lib.dxmi_unet_backward(h, L.ptr(ctx.x), L.ptr(d), ctx.B, L.stream_ptr(ctx.x)), "dxmi_unet_backward")
         m._train_token = None
         for k in keys:
             lib.dxmi_bind_grad(h, k.encode(), None)
@@ -131,6 +131,6 @@ class Model(NativeNet):
         x = x.detach().contiguous().float()
         t = t.detach().to(device=x.device, dtype=torch.float32).contiguous()
         out = torch.empty(x.shape[0], self.out_ch, self.resolution, self.resolution, device=x.device)
-        L.check(L.lib().dxmi_unet_forward(h, L.ptr(x), None, L.ptr(t), None, L.ptr(out), x.shape[0], L.stream_ptr()),
+        L.check(L.lib().dxmi_unet_forward(h, L.ptr(x), None, L.ptr(t), None, L.ptr(out), x.shape[0], L.stream_ptr(x)),
                 "dxmi_unet_forward")
         return out

@@ -86,7 +86,7 @@ class VARSampler(nn.Module):
         logp = torch.empty(T, B, device=device)
         L.check(
             L.lib().dxmi_var_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), L.ptr(sig_dev), T, L.ptr(noise_t),
-                                     L.ptr(l_sample), L.ptr(mean), L.ptr(control), L.ptr(logp), B, L.stream_ptr()),
+                                     L.ptr(l_sample), L.ptr(mean), L.ptr(control), L.ptr(logp), B, L.stream_ptr(device)),
             "dxmi_var_rollout")
         return {
             "sample": l_sample[T],
@@ -141,7 +141,7 @@ class VARSampler(nn.Module):
         logp = torch.empty(B, device=device)
         chw = x[0].numel()
         L.check(L.lib().dxmi_var_step(L.ptr(x), L.ptr(eps), L.ptr(z), L.ptr(a), L.ptr(c), L.ptr(sig), L.ptr(xn),
-                                      L.ptr(mean), L.ptr(control), L.ptr(logp), B, chw, L.stream_ptr()), "dxmi_var_step")
+                                      L.ptr(mean), L.ptr(control), L.ptr(logp), B, chw, L.stream_ptr(x)), "dxmi_var_step")
         sigma = sig[:, None, None, None]
         return {"sample": xn, "logp": logp, "logp_terminal": torch.zeros(B, device=device), "mean": mean, "sigma": sigma,
                 "entropy": torch.log(sigma), "control": control}

@@ -93,6 +93,6 @@ class UNetModel(NativeNet):
         if x_scale is not None:
             x_scale = x_scale.detach().to(device=x.device, dtype=torch.float32).expand(B).contiguous()
         out = torch.empty(B, self.out_channels, self.image_size, self.image_size, device=x.device)
-        L.check(L.lib().dxmi_unet_forward(h, L.ptr(x), L.ptr(x_scale), L.ptr(t), L.ptr(y), L.ptr(out), B, L.stream_ptr()),
+        L.check(L.lib().dxmi_unet_forward(h, L.ptr(x), L.ptr(x_scale), L.ptr(t), L.ptr(y), L.ptr(out), B, L.stream_ptr(x)),
                 "dxmi_unet_forward")
         return out

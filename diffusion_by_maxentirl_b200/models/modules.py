@@ -24,7 +24,7 @@ class _ValueNetFunction(torch.autograd.Function):
         B = x.shape[0]
         xc = x.detach().contiguous().float()
         out = torch.empty(B, 1, device=x.device)
-        L.check(L.lib().dxmi_value_forward_train(h, L.ptr(xc), L.ptr(out), B, L.stream_ptr()), "dxmi_value_forward_train")
+        L.check(L.lib().dxmi_value_forward_train(h, L.ptr(xc), L.ptr(out), B, L.stream_ptr(xc)), "dxmi_value_forward_train")
         ctx.module, ctx.B = module, B
         ctx.x = xc
         ctx.token = module._train_token = object()  # identifies the forward whose activations the plan holds
@@ -53,7 +53,7 @@ class _ValueNetFunction(torch.autograd.Function):
         dx = torch.empty_like(ctx.x) if ctx.need_dx else None
         d = dout.detach().contiguous().float().view(-1)
         L.check(lib.dxmi_value_backward(h, L.ptr(ctx.x), L.ptr(d), L.ptr(dx) if dx is not None else None, ctx.B,
-                                        L.stream_ptr()), "dxmi_value_backward")
+                                        L.stream_ptr(ctx.x)), "dxmi_value_backward")
         m._train_token = None
         for k in keys:
             lib.dxmi_bind_grad(h, k.encode(), None)
@@ -84,6 +84,26 @@ class IGEBMEncoderV2(NativeNet):
         self._train_token = None
         self._by_res = {}
 
+    def load_pretrained(self, ckpt):
+        """Reference modules.py:165-180: load the `conv1.*` and `blocks.*` entries of `ckpt['state_dict']` (keys carry a
+        4-character `net.` prefix); the head (`linear`, `out_scale`) keeps its initialisation.  Like the reference's
+        sub-module `load_state_dict` calls this is strict over conv1 / blocks."""
+        own = {k: self._param(k) for k in self._keys if k.startswith("conv1.") or k.startswith("blocks.")}
+        seen = set()
+        with torch.no_grad():
+            for k, v in ckpt["state_dict"].items():
+                k_ = k[4:]
+                if k_.startswith("conv1") or k_.startswith("blocks"):
+                    if k_ not in own:
+                        raise RuntimeError(f"load_pretrained: unexpected key {k!r}")
+                    if tuple(own[k_].shape) != tuple(v.shape):
+                        raise RuntimeError(f"load_pretrained: size mismatch for {k!r}: {tuple(v.shape)} vs {tuple(own[k_].shape)}")
+                    own[k_].copy_(v)
+                    seen.add(k_)
+        missing = sorted(set(own) - seen)
+        if missing:
+            raise RuntimeError(f"load_pretrained: missing keys {missing[:4]}{'...' if len(missing) > 4 else ''}")
+
     def forward(self, input, y=None):
         if y is not None:
             raise NotImplementedError("class-conditional value net is not used by the built configs")
@@ -104,6 +124,6 @@ class IGEBMEncoderV2(NativeNet):
         h = self._ensure_handle(input.device)
         x = input.detach().contiguous().float()
         out = torch.empty(B, 1, device=x.device)
-        L.check(L.lib().dxmi_value_forward(h, L.ptr(x), L.ptr(out), B, L.stream_ptr()), "dxmi_value_forward")
+        L.check(L.lib().dxmi_value_forward(h, L.ptr(x), L.ptr(out), B, L.stream_ptr(x)), "dxmi_value_forward")
         self.pre_activation = out
         return out

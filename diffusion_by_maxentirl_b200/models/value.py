@@ -9,3 +9,7 @@ class TimeIndependentValue(nn.Module):
 
     def forward(self, x, t, y=None):
         return self.net(x, y) if y is not None else self.net(x)
+
+    def load_pretrained(self, ckpt):
+        """Reference value.py:14-15."""
+        self.net.load_pretrained(ckpt)

@@ -62,6 +62,7 @@ class NativeNet(nn.Module):
         self._handle_device = None
         self._bound_sig = None
         self._packed_version = None
+        self._dirty = False
         self._keys = []
         self._build_parameters()
 
@@ -143,12 +144,29 @@ class NativeNet(nn.Module):
                     raise RuntimeError(f"parameter {k}: dtype {p.dtype} not supported (fp32 / fp16 state_dicts only)")
                 shape = (C.c_int64 * 8)(*p.shape)
                 L.check(lib.dxmi_bind_weight(self._handle, k.encode(), L.ptr(p), dt, shape, p.dim()), f"bind {k}")
-            L.check(lib.dxmi_finalize(self._handle, L.stream_ptr()), "dxmi_finalize")
+            L.check(lib.dxmi_finalize(self._handle, L.stream_ptr(device)), "dxmi_finalize")
             self._bound_sig, self._packed_version = sig, version
-        elif version != self._packed_version:
-            L.check(lib.dxmi_repack(self._handle, L.stream_ptr()), "dxmi_repack")
+            self._dirty = False
+        elif version != self._packed_version or self._dirty:
+            L.check(lib.dxmi_repack(self._handle, L.stream_ptr(device)), "dxmi_repack")
             self._packed_version = version
+            self._dirty = False
         return self._handle
+
+    def mark_dirty(self):
+        """Tell the module its parameters were modified in a way the version counters cannot see - in-place edits through
+        `.data` (`p.data.copy_()`, `p.data.mul_()`, hand-written EMA / weight surgery).  The packed bf16 operand copies are
+        refreshed on the next forward.  Optimizer steps, `load_state_dict`, `.to()` / `.half()` are detected automatically."""
+        self._dirty = True
+        return self
+
+    def repack(self):
+        """`mark_dirty()` + refresh the packed weights now (on the current stream of the parameters' device)."""
+        self._dirty = True
+        p = self._param(self._keys[0])
+        if p.device.type == "cuda":
+            self._ensure_handle(p.device)
+        return self
 
     def set_precision(self, mode):
         """Switch this network between the "bf16" and "fp32" paths (the handle and its plans are rebuilt lazily)."""

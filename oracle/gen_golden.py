@@ -185,6 +185,15 @@ EDM_CFGS = {
                                 distillation=False),
                  sampler=dict(sample_shape=[3, 64, 64], n_timesteps=10, class_cond=True, num_classes=1000,
                               trainable_beta="fix_last", sigma_min=0.002, sigma_max=80.0)),
+    # configs/lsun/T4.yaml
+    "lsun": dict(diffusion=dict(sigma_min=0.002, sigma_max=80.0, image_size=256, num_channels=256, num_res_blocks=2,
+                                num_heads=4, num_heads_upsample=-1, num_head_channels=64,
+                                attention_resolutions="32,16,8", channel_mult="", dropout=0.0, class_cond=False,
+                                use_checkpoint=False, use_scale_shift_norm=False, resblock_updown=True, use_fp16=True,
+                                use_new_attention_order=False, learn_sigma=False, weight_schedule="uniform",
+                                distillation=False),
+                 sampler=dict(sample_shape=[3, 256, 256], n_timesteps=4, class_cond=False, num_classes=None,
+                              trainable_beta="fix_last", sigma_min=0.002, sigma_max=80.0, rho=4.0, stochastic_last=True)),
 }
 
 
@@ -274,7 +283,7 @@ def gen_ddpm_train(B=2, p_drop=0.3):
                         **{"grad:" + k: grads[k].grad.numpy()[:8] for k in keep})
 
 
-def gen_edm(name, B, T=None, small=None):
+def gen_edm(name, B, T=None, small=None, seed=123, stride=1, skip_fp32=False):
     import_reference()
     from models.cm.script_util import create_model_and_diffusion
     from models.DxMI.openai_diffusion import OpenAIDiffusion
@@ -304,9 +313,9 @@ def gen_edm(name, B, T=None, small=None):
     assert torch.equal(sched["log_betas_init"], unet.log_betas.detach())
 
     shape = tuple(scfg["sample_shape"])
-    noise = synth.synth_noise(T, B, shape)
+    noise = synth.synth_noise(T, B, shape, seed=seed)
     noise[0] = noise[0] * scfg["sigma_max"]
-    y = synth.synth_labels(B) if scfg.get("class_cond") else None
+    y = synth.synth_labels(B, seed=seed) if scfg.get("class_cond") else None
     t0 = time.time()
     with torch.no_grad(), injected_noise(noise[1:]):
         d_ref = sampler.sample(B, device="cpu", i_class=y, x0=noise[0])
@@ -327,17 +336,24 @@ def gen_edm(name, B, T=None, small=None):
     print(f"[edm {name} T={T} B={B} small={bool(small)}] oracle(fp16 torso) vs reference worst rel-L2 = {worst:.3e} "
           f"(reference rollout {t_ref:.1f}s)")
     assert worst < 1e-5, worst
-    with torch.no_grad():
-        fn32 = lambda x, t, yy: nets.adm_unet_forward(sd32, x, t, yy, fp16_torso=False, **akw)
-        d32 = samplers.edm_rollout(fn32, sched, sd32["log_betas"], noise, y)
-    drift = [rel_l2(d_ref["l_sample"][i], d32["l_sample"][i]) for i in range(T + 1)]
-    print("   reference fp16-torso vs oracle fp32, per state:", " ".join(f"{v:.1e}" for v in drift))
+    if skip_fp32:
+        d32 = d_or
+    else:
+        with torch.no_grad():
+            fn32 = lambda x, t, yy: nets.adm_unet_forward(sd32, x, t, yy, fp16_torso=False, **akw)
+            d32 = samplers.edm_rollout(fn32, sched, sd32["log_betas"], noise, y)
+        drift = [rel_l2(d_ref["l_sample"][i], d32["l_sample"][i]) for i in range(T + 1)]
+        print("   reference fp16-torso vs oracle fp32, per state:", " ".join(f"{v:.1e}" for v in drift))
     tag = f"edm_{name}{'_small' if small else ''}_T{T}_B{B}"
+    # stride > 1: a strided pixel slice of every state (rel-L2 over the slice is the test statistic; keeps fixtures small)
+    sl = (slice(None), slice(None), slice(None), slice(None, None, stride), slice(None, None, stride))
     np.savez_compressed(
         os.path.join(GOLD, tag + ".npz"),
-        l_sample_ref_fp16=torch.stack(d_ref["l_sample"]).numpy(),
-        l_sample_fp32=torch.stack(d32["l_sample"]).numpy(),
-        F_first_fp32=d32["F"][0].numpy(),
+        l_sample_ref_fp16=torch.stack(d_ref["l_sample"]).numpy()[sl],
+        l_sample_fp32=torch.stack(d32["l_sample"]).numpy()[sl],
+        mean_ref_fp16=torch.stack(d_ref["mean"]).numpy()[sl],
+        stride=np.int64(stride), seed=np.int64(seed),
+        F_first_fp32=d32["F"][0].numpy()[sl[1:]],
         sigmas=sampler.sigmas.numpy(), sigma_up=sampler.sigma_up.numpy(), sigma_down=sampler.sigma_down.numpy(),
         log_betas=unet.log_betas.detach().numpy(),
         y=(y.numpy() if y is not None else np.zeros(0, dtype=np.int64)),
@@ -350,6 +366,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--edm", action="store_true")
     ap.add_argument("--edm-full", action="store_true")
+    ap.add_argument("--edm-full-t10", action="store_true")
+    ap.add_argument("--lsun", action="store_true")
     ap.add_argument("--skip-ddpm", action="store_true")
     ap.add_argument("--train", action="store_true", help="row a9: pin the training-mode (dropout + autograd) oracle")
     args = ap.parse_args()
@@ -365,3 +383,9 @@ if __name__ == "__main__":
                                              channel_mult="1,2,3,4", attention_resolutions="16,8,4"))
     if args.edm_full:
         gen_edm("in64", B=1, T=2)
+    if args.edm_full_t10:
+        # full-width ImageNet-64, the north-star T=10 rollout, B=2, from the reference itself (fp16 torso on the CPU)
+        gen_edm("in64", B=2, T=10, seed=21, stride=2)
+    if args.lsun:
+        # full LSUN-256 T=4 (rho=4, stochastic last step) rollout at B=1 from the reference itself; every 4th pixel kept
+        gen_edm("lsun", B=1, T=4, seed=23, stride=4, skip_fp32=True)

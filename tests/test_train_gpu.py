@@ -216,7 +216,7 @@ def test_unet_backward_matches_autograd():
 
     print("median %.2e over %d tensors" % (statistics.median(errs.values()), len(errs)))
     for k, e in errs.items():
-        assert e < 5e-2, (k, e)
+        assert e < 3e-2, (k, e)  # measured worst 2.24e-2 (bf16 operands, fp32 accumulation)
 
 
 def test_unet_backward_with_training_mode_dropout():
@@ -259,7 +259,7 @@ def test_unet_backward_with_training_mode_dropout():
     errs = {k: rel_l2(p.grad, rsd[k].grad) for k, p in net.named_parameters() if not k.endswith(".k.bias")}
     worst = max(errs.items(), key=lambda kv: kv[1])
     print(f"dropout {p_drop}: eps rel-L2 {e_out:.2e}; worst gradient {worst[0]} {worst[1]:.2e}")
-    assert e_out < 2e-2 and worst[1] < 5e-2
+    assert e_out < 2e-2 and worst[1] < 3.5e-2  # measured 2.75e-2 at p = 0.3
     # a second forward draws a new seed -> different masks
     out2 = net(x.cuda(), t.cuda())
     assert net._last_dropout_seed != seed and rel_l2(out2, out) > 1e-2

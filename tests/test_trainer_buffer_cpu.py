@@ -60,3 +60,39 @@ def test_append_buffer_equals_reference():
     )
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and "same" in r.stdout, r.stderr[-2000:]
+
+
+def test_first_append_owns_its_memory():
+    """The buffer must not alias the rollout's tensors (a GraphedRollout overwrites them on the next replay; the reference
+    always copies through torch.cat)."""
+    from diffusion_by_maxentirl_b200.models.DxMI.trainer import append_buffer, reset_buffer
+
+    d = _rollout(4, 3, views=True)
+    want = torch.stack(d["l_sample"][:4]).reshape(12, 3, 8, 8).clone()
+    buf = append_buffer(reset_buffer("cpu"), d)
+    d["l_sample"][0]._base.fill_(7.0)  # the next replay overwrites the static rollout tensor
+    assert torch.equal(buf["state"], want)
+    assert buf["state"]._base is None or buf["state"]._base is not d["l_sample"][0]._base
+
+
+def test_value_net_load_pretrained_cpu():
+    """Reference modules.py:165-180: `load_pretrained` copies conv1.* / blocks.* from ckpt['state_dict'] (keys carry a `net.`
+    prefix) and leaves the head alone; the reference's TimeIndependentValue.load_pretrained forwards to it."""
+    from common import VALUE_CFG
+    from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
+    from diffusion_by_maxentirl_b200.models.value import TimeIndependentValue
+
+    torch.manual_seed(0)
+    src = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
+    dst = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
+    head_before = dst.net.linear.weight.detach().clone()
+    ckpt = {"state_dict": {k: v.clone() for k, v in src.state_dict().items()}}
+    dst.load_pretrained(ckpt)
+    sd_s, sd_d = src.state_dict(), dst.state_dict()
+    for k in sd_s:
+        if k.startswith("net.conv1.") or k.startswith("net.blocks."):
+            assert torch.equal(sd_s[k], sd_d[k]), k
+    assert torch.equal(dst.net.linear.weight, head_before)
+    bad = {"state_dict": {"net.conv1.weight": torch.zeros(1)}}
+    with pytest.raises(RuntimeError):
+        dst.net.load_pretrained(bad)
