@@ -191,6 +191,330 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def eager_cuda_baseline(wl, T, B, dev):
+    """The honest bar: the reference's arithmetic in eager PyTorch on the same GPU - the oracle's functional
+    networks moved to CUDA (cuDNN / cuBLAS / ATen), best of fp32-with-TF32 and autocast-bf16 for the DDPM U-Net, the
+    reference's own fp16 torso for the ADM U-Net. Baseline only: nothing here is on the product path."""
+    import torch
+
+    from oracle import nets, samplers, synth
+
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "ddpm_shapes.json")))
+    vsd = {k: v.to(dev) for k, v in synth.synth_state_dict({k: tuple(v) for k, v in shapes["value"].items()}, seed=1).items()}
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    noise = [torch.randn(B, *SHAPE[wl], device=dev) for _ in range(T + 1)]
+    if wl == "cifar":
+        sd = {k: v.to(dev) for k, v in synth.synth_state_dict({k: tuple(v) for k, v in shapes["net"].items()}).items()}
+        sched = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in samplers.var_schedule(T).items()}
+        lb = sched["log_betas_init"]
+
+        def work(autocast):
+            def net(x, t):
+                if autocast:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return nets.ddpm_unet_forward(sd, x, t).float()
+                return nets.ddpm_unet_forward(sd, x, t)
+
+            with torch.no_grad():
+                d = samplers.var_rollout(net, sched, lb, noise)
+                return nets.value_forward(vsd, d["sample"])
+
+        modes = (("fp32/TF32", False), ("autocast-bf16", True))
+    else:
+        from common import EDM_IN64_CFG, adm_oracle_kwargs, build_edm
+
+        # synthetic weights with the reference's convert_to_fp16() applied (fp16 torso convs incl. biases; fp32 norms / embeddings)
+        unet, _, _ = build_edm(EDM_IN64_CFG, T, device=dev)
+        sd = {k: (v[..., None] if v.dim() == 3 else v).detach().clone() for k, v in unet.state_dict().items()}
+        del unet
+        akw = adm_oracle_kwargs(EDM_IN64_CFG)
+        sched = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in samplers.edm_schedule(T).items()}
+        lb = sched["log_betas_init"]
+        y = torch.randint(0, 1000, (B,), device=dev)
+        noise[0] = noise[0] * 80.0
+
+        def work(autocast):
+            with torch.no_grad():
+                d = samplers.edm_rollout(lambda x, t, yy: nets.adm_unet_forward(sd, x, t, yy, fp16_torso=True, **akw), sched, lb, noise, y)
+                return nets.value_forward(vsd, d["sample"])
+
+        modes = (("fp16 torso (reference convert_to_fp16)", False),)
+    best = None
+    with torch.device(dev):  # the oracle's factory calls (torch.ones, arange, ...) land on the GPU
+        for name, ac in modes:
+            for _ in range(2):
+                work(ac)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 3
+            e0.record()
+            for _ in range(n):
+                work(ac)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            if best is None or ms < best[1]:
+                best = (name, ms)
+    del sd, vsd
+    torch.cuda.empty_cache()
+    return {"value": B / best[1] * 1e3, "unit": UNIT, "ms_per_step": best[1], "mode": best[0],
+            "what": f"oracle functional networks in eager PyTorch {torch.__version__} on the same GPU (cuDNN/cuBLAS), same rollout, "
+                    f"batch {B}, device-timed, 3 steps after 2 warm-ups"}
+
+
+def traffic_table():
+    """dram__bytes per launch of the hot kernels from the committed ncu --set full capture (profiles/r02_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
+def measure(wl, T, B, K, W, args, ctx, full):
+    """One workload on this rank: device-timed value, e2e through the public API, roofline legs. `full`: the main line
+    (clock sampling, CPU baseline); secondary workloads use fewer steps."""
+    import torch
+    import torch.distributed as dist
+
+    from common import EDM_IN64_CFG, EDM_LSUN_CFG, VALUE_CFG, build_ddpm, build_edm, load_synth_into
+    from diffusion_by_maxentirl_b200 import _lib as L
+    from diffusion_by_maxentirl_b200.dist import PackedRollout
+
+    rank, world, dev, lib = ctx["rank"], ctx["world"], ctx["dev"], ctx["lib"]
+    shape = SHAPE[wl]
+    g = torch.Generator().manual_seed(1234 + rank)
+    if wl == "cifar":
+        net, sampler, value, sd, vsd = build_ddpm(T, device=dev)
+        labels = None
+
+        @torch.no_grad()
+        def rollout(noise):  # noise [T+1, B, C, H, W] on the device
+            d = sampler.sample(noise.shape[1], device=dev, noise=noise)
+            return d, value(d["sample"], T)
+    elif wl == "lsun":
+        net, sampler, sd = build_edm(EDM_LSUN_CFG, T, device=dev, stochastic_last=True, rho=4.0)
+        value, labels = None, None
+
+        @torch.no_grad()
+        def rollout(noise):
+            return sampler.sample(noise.shape[1], device=dev, x0=noise[0] * 80.0, noise=noise[1:]), None
+    else:
+        from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
+        from diffusion_by_maxentirl_b200.models.value import TimeIndependentValue
+
+        net, sampler, sd = build_edm(EDM_IN64_CFG, T, device=dev)
+        value = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
+        load_synth_into(value, seed=1)
+        value.to(dev).eval()
+        labels = torch.randint(0, 1000, (B,), generator=g).to(dev)
+
+        @torch.no_grad()
+        def rollout(noise):  # noise[0] is x_0 / sigma_max
+            d = sampler.sample(noise.shape[1], device=dev, i_class=labels[:noise.shape[1]], x0=noise[0] * 80.0, noise=noise[1:])
+            return d, value(d["sample"], T)
+
+    eager_rollout = rollout
+    # N > 1: the last transition kernel writes u8 samples and the value head the energies into ONE packed buffer
+    packed = PackedRollout(B, shape, dev, world=world, with_energy=value is not None) if world > 1 else None
+    graph_gather = bool(int(os.environ.get("DXMI_GRAPH_GATHER", "0")))
+    if not args.no_graph:
+        # capture the public-API call once (diffusion_by_maxentirl_b200.graph.GraphedRollout) and replay it per step
+        from diffusion_by_maxentirl_b200.graph import GraphedRollout
+
+        rollout = GraphedRollout(sampler, B, dev, value=value, labels=labels, packed=packed,
+                                 capture_gather=graph_gather)  # same signature: rollout(noise) -> (d_sample, energies)
+
+    n_host_bufs = 2
+    host_noise = [torch.randn(T + 1, B, *shape, generator=g).pin_memory() for _ in range(n_host_bufs)]
+    dev_noise = host_noise[0].to(dev)
+    flush = ctx["flush"]
+
+    def gather(d, e):
+        # the path's only collective: ONE all-gather of the packed (u8 samples | fp32 energies) buffer (generate_large.py:43-50)
+        if args.no_graph:
+            from diffusion_by_maxentirl_b200.dist import gather_packed
+
+            return gather_packed(d["sample"], e)
+        if graph_gather:
+            return packed.unpack()  # the collective ran inside the graph
+        return packed.all_gather()
+
+    def rollout_resident():
+        d, e = rollout(dev_noise)
+        if world > 1:
+            gather(d, e)
+        return d, e
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- warm-up
+    l0 = lib.dxmi_launch_count()
+    eager_rollout(dev_noise)
+    launches_per_rollout = lib.dxmi_launch_count() - l0  # kernels of ours in one rollout (a graph replay launches the same set)
+    for _ in range(W):
+        rollout_resident()
+    sync_all()
+
+    # ---------------------------------------------------------------- parity of the sharded run (N > 1): bit for bit
+    shard_check = None
+    if world > 1:
+        d, e = rollout(dev_noise)
+        s_all, e_all = gather(d, e)
+        torch.cuda.synchronize()
+        from diffusion_by_maxentirl_b200.dist import quantize_u8
+
+        own = quantize_u8(d["sample"])
+        ok = torch.equal(s_all[rank * B:(rank + 1) * B], own)
+        if e is not None:
+            ok = ok and torch.equal(e_all[rank * B:(rank + 1) * B], e.reshape(-1).float())
+        # rank 0 re-runs rank 1's shard on ITS noise: N ranks' shards must equal a 1-GPU run on the same noise
+        peer = 1
+        gp = torch.Generator().manual_seed(1234 + peer)
+        peer_labels = torch.randint(0, 1000, (B,), generator=gp) if wl == "in64" else None
+        peer_noise = torch.randn(T + 1, B, *shape, generator=gp)
+        ok1 = True
+        if rank == 0:
+            nb = min(B, 8)
+            if wl == "in64":
+                dd = sampler.sample(nb, device=dev, i_class=peer_labels[:nb].to(dev), x0=peer_noise[0, :nb].to(dev) * 80.0,
+                                    noise=peer_noise[1:, :nb].contiguous().to(dev))
+            elif wl == "lsun":
+                dd = sampler.sample(nb, device=dev, x0=peer_noise[0, :nb].to(dev) * 80.0, noise=peer_noise[1:, :nb].contiguous().to(dev))
+            else:
+                dd = sampler.sample(nb, device=dev, noise=peer_noise[:, :nb].contiguous().to(dev))
+            ok1 = torch.equal(quantize_u8(dd["sample"]), s_all[peer * B:peer * B + nb])
+        flag = torch.tensor([int(ok), int(ok1)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        shard_check = {"gather_equals_local_outputs": bool(flag[0].item()),
+                       "rank1_shard_equals_single_gpu_rerun_on_rank0": bool(flag[1].item())}
+        assert flag.min().item() == 1, f"sharded rollout differs from the single-GPU run: {shard_check}"
+
+    # ---------------------------------------------------------------- value: device-timed, inputs resident in HBM
+    clocks = ClockSampler(ctx["local_rank"]) if (full and rank == 0) else None
+    if clocks:
+        clocks.start()
+    evs = []
+    sync_all()
+    for _ in range(K):
+        flush.fill_(1)  # L2 flush between timed iterations (untimed)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rollout_resident()
+        b.record()
+        evs.append((a, b))
+    sync_all()
+    launches = launches_per_rollout * K
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value_ips = world * B * K / (ms_total / 1e3)
+
+    # ---------------------------------------------------------------- e2e: public API from pinned host noise
+    # two-deep pipeline: the H2D copy of step i+1 (copy stream) overlaps rollout i; results are read back every step
+    d2h_samples = torch.empty(B, *shape).pin_memory()
+    d2h_energy = torch.empty(B, 1).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    dev_bufs = [torch.empty_like(dev_noise) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            dev_bufs[i % 2].copy_(host_noise[i % n_host_bufs], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    sync_all()
+    for ev in consumed:
+        ev.record(main_stream)
+    t0 = time.perf_counter()
+    prefetch(0)
+    for i in range(K):
+        if i + 1 < K:
+            prefetch(i + 1)
+        main_stream.wait_event(ready[i % 2])
+        d, e = rollout(dev_bufs[i % 2])
+        consumed[i % 2].record(main_stream)
+        if world > 1:
+            gather(d, e)
+        d2h_samples.copy_(d["sample"], non_blocking=True)
+        if e is not None:
+            d2h_energy.copy_(e, non_blocking=True)
+        torch.cuda.synchronize()  # the step's result is on the host before the next step is issued
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ips = world * B * K / float(t.item())
+    clk = clocks.stop() if clocks else None
+
+    # ---------------------------------------------------------------- rooflines (rank 0, live, eager launches on one stream)
+    roof = None
+    if rank == 0:
+        pk, pk_kind = peaks()
+        traffic = traffic_table()
+        lib.dxmi_set_option(b"time_gemms", 1)
+        kk = max(2, min(K, 4))
+        eager_rollout(dev_noise)
+        torch.cuda.synchronize()
+        ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
+        L.check(lib.dxmi_gemm_timing(C.byref(ms), C.byref(fl), C.byref(nl)))  # drop the warm-up records
+        for cat in (1, 2):
+            L.check(lib.dxmi_aux_timing(cat, C.byref(ms), C.byref(fl), C.byref(nl)))
+        for _ in range(kk):
+            eager_rollout(dev_noise)  # per-launch CUDA events need eager launches
+        torch.cuda.synchronize()
+        L.check(lib.dxmi_gemm_timing(C.byref(ms), C.byref(fl), C.byref(nl)))
+        achieved = fl.value / (ms.value * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        step_ms = ms_total / K
+        roof = {"bound": "tensor",
+                "kernel": "every tcgen05 contraction launch of the step: conv_gemm2p_kernel / conv_gemm2_kernel (persistent implicit GEMM, "
+                          "cta_group::2 pair and one-CTA variants) + the fused attention kernels (attnblk256_kernel / attn_fwd_kernel)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic.get("conv_gemm2p_kernel"),
+                "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained",
+                "launches_per_step": nl.value // kk, "ms_per_step": ms.value / kk,
+                "share_of_step": (ms.value / kk) / step_ms, "algorithmic_gflop_per_step": fl.value / kk / 1e9,
+                "whole_step_frac": None}
+        roof["whole_step_frac"] = ((T * GF[wl][0] + (GF[wl][1] if value is not None else 0.0)) * B / 1e3) / (step_ms * 1e-3) / peak
+        hbm = []
+        for cat, name, key in ((1, "GroupNorm family: gn_finalize_k + gn_apply_ab_k / gn_apply_fused_k (normalise + SiLU, one bf16 read + "
+                                   "one bf16 write per element)", "gn_apply_ab_k"),
+                               (2, "transition step var_step_k / edm_step_k (x' = mu + sigma z, logp; fp32 tensors)", "step_k")):
+            bms, by, bn = C.c_double(), C.c_double(), C.c_longlong()
+            L.check(lib.dxmi_aux_timing(cat, C.byref(bms), C.byref(by), C.byref(bn)))
+            if bn.value:
+                ach = by.value / (bms.value * 1e-3) / 1e9
+                hbm.append({"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(key), "launches_per_step": bn.value // kk,
+                            "ms_per_step": bms.value / kk, "share_of_step": (bms.value / kk) / step_ms,
+                            "algorithmic_mb_per_step": by.value / kk / 1e6})
+        roof["hbm_kernels"] = hbm
+        lib.dxmi_set_option(b"time_gemms", 0)
+
+    res = {"wl": wl, "T": T, "B": B, "K": K, "W": W, "value": value_ips, "ms_per_step": ms_total / K, "e2e": e2e_ips,
+           "h2d": host_noise[0].numel() * 4, "d2h": d2h_samples.numel() * 4 + (d2h_energy.numel() * 4 if value is not None else 0),
+           "launches": int(launches), "clocks": clk, "roofline": roof, "shard_check": shard_check, "has_value": value is not None}
+    # free this workload's plans / graphs before the next one is built
+    del rollout, eager_rollout, sampler, net, value
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +527,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step")
     ap.add_argument("--T", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the north-star target workloads in `secondary`")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--block-n-256", type=int, default=None)
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=INT", help="dxmi_set_option before the plans are built (A/B switches)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
@@ -215,7 +541,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from common import EDM_IN64_CFG, EDM_LSUN_CFG, VALUE_CFG, build_ddpm, build_edm, load_synth_into
     from diffusion_by_maxentirl_b200 import _lib as L
 
     rank = int(os.environ.get("RANK", "0"))
@@ -243,181 +568,69 @@ def main():
     T = args.T or DEFAULTS[wl][0]
     B = args.batch or DEFAULTS[wl][1]
     K, W = args.steps, args.warmup
-    shape = SHAPE[wl]
-    g = torch.Generator().manual_seed(1234 + rank)
-    if wl == "cifar":
-        net, sampler, value, sd, vsd = build_ddpm(T, device=dev)
-        labels = None
+    ctx = {"rank": rank, "local_rank": local_rank, "world": world, "dev": dev, "lib": lib,
+           "flush": torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)}  # > 126 MB L2
 
-        @torch.no_grad()
-        def rollout(noise):  # noise [T+1, B, C, H, W] on the device
-            d = sampler.sample(B, device=dev, noise=noise)
-            return d, value(d["sample"], T)
-    elif wl == "lsun":
-        net, sampler, sd = build_edm(EDM_LSUN_CFG, T, device=dev, stochastic_last=True, rho=4.0)
-        value, labels = None, None
+    main_res = measure(wl, T, B, K, W, args, ctx, full=True)
 
-        @torch.no_grad()
-        def rollout(noise):
-            return sampler.sample(B, device=dev, x0=noise[0] * 80.0, noise=noise[1:]), None
-    else:
-        from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
-        from diffusion_by_maxentirl_b200.models.value import TimeIndependentValue
+    # ---------------------------------------------------------------- secondary: the north-star TARGET workloads
+    secondary = []
+    if not args.no_secondary and wl == "cifar" and args.T is None and args.batch is None:
+        for swl, sT, sB, sK in (("cifar", 10, 256, max(3, min(K, 8))), ("in64", 10, 64, max(3, min(K, 5)))):
+            r = measure(swl, sT, sB, sK, 3, args, ctx, full=False)
+            secondary.append(r)
 
-        net, sampler, sd = build_edm(EDM_IN64_CFG, T, device=dev)
-        value = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
-        load_synth_into(value, seed=1)
-        value.to(dev).eval()
-        labels = torch.randint(0, 1000, (B,), generator=g).to(dev)
+    # ---------------------------------------------------------------- eager-CUDA bar + CPU baseline (rank 0, N = 1 only)
+    eager = None
+    cpu = None
+    if rank == 0 and world == 1 and wl != "lsun":
+        if not args.no_eager_baseline:
+            eager = eager_cuda_baseline(wl, T, B, dev)
+            for r in secondary:
+                r["eager"] = eager_cuda_baseline(r["wl"], r["T"], r["B"], dev)
+        if not args.no_cpu_baseline:
+            run = cpu_oracle_rollout_fn(wl, T)
+            Bs = 8 if wl == "cifar" else 1
+            if wl == "cifar":
+                run(Bs)
+            ts, t_begin = [], time.perf_counter()
+            while len(ts) < (3 if wl == "cifar" else 1) or (time.perf_counter() - t_begin < 10 and len(ts) < 20):
+                ts.append(run(Bs, seed=len(ts)))
+            cores = torch.get_num_threads()
+            cpu = {"value": Bs * len(ts) / sum(ts), "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{len(ts)} rollouts x {Bs} images (T={T} + energy), oracle port, torch CPU fp32, {cores} threads; "
+                             "images/s is per-image normalised (the CPU arm runs a bounded batch, not the GPU batch)"}
 
-        @torch.no_grad()
-        def rollout(noise):  # noise[0] is x_0 / sigma_max
-            d = sampler.sample(B, device=dev, i_class=labels, x0=noise[0] * 80.0, noise=noise[1:])
-            return d, value(d["sample"], T)
-
-    eager_rollout = rollout
-    if not args.no_graph:
-        # capture the public-API call once (diffusion_by_maxentirl_b200.graph.GraphedRollout) and replay it per step
-        from diffusion_by_maxentirl_b200.graph import GraphedRollout
-
-        graphed = GraphedRollout(sampler, B, dev, value=value, labels=labels)
-        rollout = graphed  # same signature: rollout(noise) -> (d_sample, energies)
-
-    n_host_bufs = 2
-    host_noise = [torch.randn(T + 1, B, *shape, generator=g).pin_memory() for _ in range(n_host_bufs)]
-    dev_noise = host_noise[0].to(dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def gather(d, e):
-        # the path's only collective: all-gather of u8 samples and energies (generate_large.py:43-50)
-        from diffusion_by_maxentirl_b200.dist import gather_rollout, quantize_u8
-
-        return gather_rollout(quantize_u8(d["sample"]), e)
-
-    def rollout_resident():
-        d, e = rollout(dev_noise)
-        if world > 1:
-            gather(d, e)
-        return d, e
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------------------------------------------------------- warm-up
-    l0 = lib.dxmi_launch_count()
-    eager_rollout(dev_noise)
-    launches_per_rollout = lib.dxmi_launch_count() - l0  # kernels of ours in one rollout (a graph replay launches the same set)
-    for _ in range(W):
-        rollout_resident()
-    sync_all()
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         os.close(saved_stdout)
 
-    # ---------------------------------------------------------------- value: device-timed, inputs resident in HBM
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    evs = []
-    sync_all()
-    for _ in range(K):
-        flush.fill_(1)  # L2 flush between timed iterations (untimed)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        rollout_resident()
-        b.record()
-        evs.append((a, b))
-    sync_all()
-    launches = launches_per_rollout * K + (K if world > 1 else 0)
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value_ips = world * B * K / (ms_total / 1e3)
+    def cfg(r):
+        return {"workload": workload_name(r["wl"], r["T"], r["B"]), "T": r["T"], "batch_per_gpu": r["B"], "global_batch": r["B"] * world,
+                "parallelism": f"dp{world}", "l2": "256 MiB write between timed steps (L2 flush)",
+                "launch": "eager" if args.no_graph else "CUDA graph replay of the public-API call (graph.GraphedRollout)",
+                "collective": "one all_gather of the packed (u8 samples | fp32 energies) buffer per step" if world > 1 else "none"}
 
-    # ---------------------------------------------------------------- e2e: public API from pinned host noise
-    d2h_samples = torch.empty(B, *shape).pin_memory()
-    d2h_energy = torch.empty(B, 1).pin_memory()
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(K):
-        nz = host_noise[i % n_host_bufs].to(dev, non_blocking=True)
-        d, e = rollout(nz)
-        if world > 1:
-            gather(d, e)
-        d2h_samples.copy_(d["sample"], non_blocking=True)
-        if e is not None:
-            d2h_energy.copy_(e, non_blocking=True)
-        torch.cuda.synchronize()
-    sync_all()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ips = world * B * K / float(t.item())
-    clk = clocks.stop() if rank == 0 else None
-
-    # ---------------------------------------------------------------- roofline of the dominant kernel (rank 0, live)
-    roof = None
-    if rank == 0:
-        pk, pk_kind = peaks()
-        lib.dxmi_set_option(b"time_gemms", 1)
-        lib.dxmi_set_option(b"rollout_split", 1)  # per-launch durations need the launches un-overlapped (one stream)
-        kk = max(2, min(K, 5))
-        eager_rollout(dev_noise)  # builds the un-split plan
-        torch.cuda.synchronize()
-        L.check(lib.dxmi_gemm_timing(C.byref(C.c_double()), C.byref(C.c_double()), C.byref(C.c_longlong())))
-        for _ in range(kk):
-            eager_rollout(dev_noise)  # per-launch CUDA events need eager launches
-        torch.cuda.synchronize()
-        ms, fl, nl = C.c_double(), C.c_double(), C.c_longlong()
-        L.check(lib.dxmi_gemm_timing(C.byref(ms), C.byref(fl), C.byref(nl)))
-        lib.dxmi_set_option(b"time_gemms", 0)
-        achieved = fl.value / (ms.value * 1e-3) / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "conv_gemm2p_kernel / conv_gemm2_kernel (persistent tcgen05 implicit GEMM, cta_group::2 pair and "
-                                             "one-CTA variants: every conv / 1x1 / attention-projection GEMM launch of the step)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16_tflops_sustained",
-                "gemm_launches_per_step": nl.value // kk, "gemm_ms_per_step": ms.value / kk,
-                "gemm_share_of_step": (ms.value / kk) / (ms_total / K),
-                "algorithmic_gflop_per_step": fl.value / kk / 1e9}
-
-    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and wl != "lsun":
-        run = cpu_oracle_rollout_fn(wl, T)
-        Bs = 8 if wl == "cifar" else 1
-        if wl == "cifar":
-            run(Bs)
-        ts, t_begin = [], time.perf_counter()
-        while len(ts) < (3 if wl == "cifar" else 1) or (time.perf_counter() - t_begin < 10 and len(ts) < 20):
-            ts.append(run(Bs, seed=len(ts)))
-        cores = torch.get_num_threads()
-        cpu = {"value": Bs * len(ts) / sum(ts), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{len(ts)} rollouts x {Bs} images (T={T} + energy), oracle port, torch CPU fp32, {cores} threads"}
+    def e2e(r):
+        return {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "pipeline": "H2D of step i+1 on a copy stream overlaps rollout i; samples + energies read back every step"}
 
     if rank == 0:
+        r = main_res
         gf_u, gf_v = GF[wl]
         line = {
-            "metric": METRIC, "value": value_ips, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(wl, T, B), "T": T, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"dp{world}", "l2": "256 MiB write between timed steps (L2 flush)",
-                       "launch": "eager" if args.no_graph else "CUDA graph replay of the public-API call (graph.GraphedRollout)",
-                       "collective": "all_gather(u8 samples, fp32 energies) per step" if world > 1 else "none"},
-            "e2e": {"value": e2e_ips, "unit": UNIT, "h2d_bytes_per_step": host_noise[0].numel() * 4,
-                    "d2h_bytes_per_step": d2h_samples.numel() * 4 + d2h_energy.numel() * 4},
-            "gpu_launches": int(launches),
-            "clocks": clk,
-            "roofline": roof,
-            "cpu_baseline": cpu,
-            "model_tflops": value_ips * (T * gf_u + gf_v) / 1e3,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": cfg(r), "e2e": e2e(r),
+            "gpu_launches": r["launches"] + sum(x["launches"] for x in secondary),
+            "clocks": r["clocks"], "roofline": r["roofline"], "cpu_baseline": cpu, "eager_cuda_baseline": eager,
+            "model_tflops": r["value"] * (T * gf_u + (gf_v if r["has_value"] else 0.0)) / 1e3,
+            "shard_check": r["shard_check"],
+            "secondary": [{"metric": METRIC, "value": x["value"], "unit": UNIT, "steps": x["K"], "warmup": x["W"],
+                           "ms_per_step": x["ms_per_step"], "config": cfg(x), "e2e": e2e(x), "roofline": x["roofline"],
+                           "eager_cuda_baseline": x.get("eager"), "shard_check": x["shard_check"],
+                           "model_tflops": x["value"] * (x["T"] * GF[x["wl"]][0] + GF[x["wl"]][1]) / 1e3} for x in secondary],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -99,8 +99,8 @@ SYMBOLS = {
     "dxmi_value_forward": (_I, [_VP, _VP, _VP, _I, _VP]),
     "dxmi_var_step": (_I, [_VP] * 10 + [_I, _I, _VP]),
     "dxmi_edm_step": (_I, [_VP] * 6 + [_I, _I, _VP]),
-    "dxmi_var_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
-    "dxmi_edm_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _I, _VP]),
+    "dxmi_var_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "dxmi_edm_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_quantize_u8": (_I, [_VP, _VP, _LL, _VP]),
     "dxmi_op_conv_gemm": (_I, [C.POINTER(GemmDesc), _VP]),
     "dxmi_op_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _LL, _LL, _VP]),
@@ -125,6 +125,7 @@ SYMBOLS = {
     "dxmi_set_timing_dump": (_I, [C.c_char_p]),
     "dxmi_launch_count": (_LL, []),
     "dxmi_gemm_timing": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL)]),
+    "dxmi_aux_timing": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL)]),
     "dxmi_plan_gemm_flops": (C.c_double, [_VP, _I]),
     "dxmi_workspace_bytes": (C.c_size_t, [_VP, _I]),
 }

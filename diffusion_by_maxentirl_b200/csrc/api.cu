@@ -47,6 +47,10 @@ int dxmi_set_option(const char* name, int value) {
         set_gn_fused(value);
         return 0;
     }
+    if (!strcmp(name, "attnblk")) {  // read when a plan is built
+        set_attnblk(value);
+        return 0;
+    }
     if (!strcmp(name, "pair_resident_b")) {
         set_pair_resident_b(value);
         return 0;
@@ -89,12 +93,19 @@ int dxmi_set_timing_dump(const char* path) {
 }
 
 int dxmi_set_debug_buffer(void* dev_ptr) {
-    set_dbg_times(dev_ptr);
+    // one buffer, one consumer: DXMI_DBG_ATTNBLK=1 routes it to the fused attention-block kernel (read when a plan is
+    // built, tools/attnblk_timeline.py), otherwise to the persistent GEMM kernels (tools/cta_timeline.py)
+    if (getenv("DXMI_DBG_ATTNBLK")) set_attnblk_dbg(dev_ptr);
+    else set_dbg_times(dev_ptr);
     return 0;
 }
 
 int dxmi_gemm_timing(double* ms_total, double* flops_total, long long* launches) {
     return gemm_timing_collect(ms_total, flops_total, launches);
+}
+
+int dxmi_aux_timing(int category, double* ms_total, double* bytes_total, long long* launches) {
+    return aux_timing_collect(category, ms_total, bytes_total, launches);
 }
 
 double dxmi_plan_gemm_flops(dxmi_net_t net, int B) {
@@ -480,7 +491,7 @@ int dxmi_var_step(const float* x, const float* eps, const float* z, const float*
         set_err("dxmi_var_step: C*H*W must be a multiple of 4");
         return -1;
     }
-    var_step(x, eps, z, a, c, sigma, x_next, mean, control, logp, B, chw, (cudaStream_t)stream);
+    var_step(x, eps, z, a, c, sigma, x_next, mean, control, logp, nullptr, B, chw, (cudaStream_t)stream);
     count_launches(1);
     return (int)cudaGetLastError();
 }
@@ -491,7 +502,7 @@ int dxmi_edm_step(const float* x, const float* F, const float* z, const float* c
         set_err("dxmi_edm_step: C*H*W must be a multiple of 4");
         return -1;
     }
-    edm_step(x, F, z, coef, x_next, mean, B, chw, (cudaStream_t)stream);
+    edm_step(x, F, z, coef, x_next, mean, nullptr, B, chw, (cudaStream_t)stream);
     count_launches(1);
     return (int)cudaGetLastError();
 }
@@ -568,7 +579,7 @@ static int run_plans(Net& n, std::vector<SubRollout>& subs) {
 }
 
 int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_dev, int T, const float* noise,
-                     float* l_sample, float* mean, float* control, float* logp, int B, dxmi_stream_t stream) {
+                     float* l_sample, float* mean, float* control, float* logp, uint8_t* sample_u8, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized || net->net.a.arch != DXMI_ARCH_DDPM_UNET) {
         set_err("dxmi_var_rollout: needs a finalized DDPM U-Net handle");
         return -1;
@@ -601,10 +612,13 @@ int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma
         for (auto& sb : subs) {
             Plan* p = sb.p;
             const long long o = sb.b0 * chw;
-            var_step(p->x, p->eps, noise + (long long)(i + 1) * bchw + o, p->coef, p->coef + sb.Bs, p->coef + 2 * sb.Bs,
-                     l_sample + (long long)(i + 1) * bchw + o, mean ? mean + (long long)i * bchw + o : nullptr,
-                     control ? control + (long long)i * bchw + o : nullptr, logp ? logp + (long long)i * B + sb.b0 : nullptr, sb.Bs,
-                     (int)chw, sb.st);
+            // algorithmic bytes: read x, eps, z; write x' (+ mean, control when requested), fp32
+            run_timed_aux(2, 4.0 * sb.Bs * chw * (4 + (mean ? 1 : 0) + (control ? 1 : 0)), sb.st, [&] {
+                var_step(p->x, p->eps, noise + (long long)(i + 1) * bchw + o, p->coef, p->coef + sb.Bs, p->coef + 2 * sb.Bs,
+                         l_sample + (long long)(i + 1) * bchw + o, mean ? mean + (long long)i * bchw + o : nullptr,
+                         control ? control + (long long)i * bchw + o : nullptr, logp ? logp + (long long)i * B + sb.b0 : nullptr,
+                         (sample_u8 && i == T - 1) ? sample_u8 + o : nullptr, sb.Bs, (int)chw, sb.st);
+            });
             count_launches(1);
         }
     }
@@ -613,7 +627,7 @@ int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma
 }
 
 int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_noise_dev, int T, const float* noise,
-                     const int64_t* y, float* l_sample, float* mean, int B, dxmi_stream_t stream) {
+                     const int64_t* y, float* l_sample, float* mean, uint8_t* sample_u8, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized || net->net.a.arch != DXMI_ARCH_ADM_UNET) {
         set_err("dxmi_edm_rollout: needs a finalized ADM U-Net handle");
         return -1;
@@ -650,8 +664,11 @@ int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, const float* sigma
         for (auto& sb : subs) {
             Plan* p = sb.p;
             const long long o = sb.b0 * chw;
-            edm_step(p->x, p->eps, noise + (long long)(i + 1) * bchw + o, p->coef, l_sample + (long long)(i + 1) * bchw + o,
-                     mean ? mean + (long long)i * bchw + o : nullptr, sb.Bs, (int)chw, sb.st);
+            run_timed_aux(2, 4.0 * sb.Bs * chw * (4 + (mean ? 1 : 0)), sb.st, [&] {
+                edm_step(p->x, p->eps, noise + (long long)(i + 1) * bchw + o, p->coef, l_sample + (long long)(i + 1) * bchw + o,
+                         mean ? mean + (long long)i * bchw + o : nullptr, (sample_u8 && i == T - 1) ? sample_u8 + o : nullptr, sb.Bs,
+                         (int)chw, sb.st);
+            });
             count_launches(1);
         }
     }

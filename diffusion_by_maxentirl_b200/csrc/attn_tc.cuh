@@ -41,6 +41,33 @@ struct Attn256Op {
 int prepare_attn256(const void* qk, const void* vt, void* out, int ldo, int B, float scale, Attn256Op* op);
 int run_attn256(const Attn256Op& op, cudaStream_t st);
 
+// Whole DDPM AttnBlock (GroupNorm -> q,k,v -> softmax(q k^T) v -> proj_out + residual) at seq 256, C = 256 (attnblk_tc.cu)
+struct AttnBlkParams {
+    CUtensorMap x_map;       // [B, 256 pixels, 256 channels] bf16, box 64 x 128
+    CUtensorMap w_map;       // k | v | q | proj_out weights stacked as [1024, 256] bf16 (K-major), box 64 x 128
+    const __nv_bfloat16* x;  // block input (residual)
+    __nv_bfloat16* out;      // [B, 256, 256]
+    const float* stats_in;   // GroupNorm partials of x from its producer: [B][P_in][256][2] (sum, sumsq)
+    int P_in;
+    float* stats_out;        // GroupNorm partials of out: [B][2][256][2] (one per 128-row half), or null
+    const float* gamma;      // norm.weight / norm.bias
+    const float* beta;
+    const float* bias;       // k | v | q | proj_out biases, [1024]
+    float eps;
+    float scale_log2;
+    long long* dbg;          // optional phase stamps [CTA][16] (globaltimer ns), tools/attnblk_timeline.py
+};
+void set_attnblk_dbg(void* p);
+long long* attnblk_dbg_buffer();
+struct AttnBlkOp {
+    AttnBlkParams p;
+    int B;
+    double flops;
+};
+int prepare_attnblk256(const void* x, const void* w_kvqp, const float* bias_kvqp, const float* gamma, const float* beta,
+                       const float* stats_in, int P_in, float eps, float scale, void* out, float* stats_out, int B, AttnBlkOp* op);
+int run_attnblk256(const AttnBlkOp& op, cudaStream_t st);
+
 int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
                  int heads, int seq, int d, float scale, AttnOp* op);
 int run_attn(const AttnOp& op, cudaStream_t st);

@@ -10,6 +10,7 @@
 
 namespace dxmi {
 
+int attnblk_option();   // engine.cu: 1 = DDPM AttnBlock at 16x16 as one fused kernel
 int gn_fused_option();  // engine.cu: 1 = every GroupNorm with producer statistics is ONE kernel (prologue + streaming apply)
 
 struct Builder {
@@ -402,6 +403,7 @@ struct Builder {
         if ((C1 + C2) % 8 || (C1 % 8) || (C1 + C2) > 2048) fail("group_norm: unsupported channel count");
         const float* st1 = x1.stats;
         const float* st2 = x2.stats;
+        const double gn_bytes = 4.0 * (double)B * HW * (C1 + C2);  // algorithmic: one bf16 read + one bf16 write per element
         if (x1.has_stats && (C2 == 0 || x2.has_stats)) {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
             const int P1 = x1.stats_P, P2 = x2.stats_P;
@@ -410,21 +412,26 @@ struct Builder {
                 // small maps (8x8, 4x4) are launch-latency bound: one kernel that derives the statistics in its prologue
                 // (at most 2 partials per channel, one CTA per image) instead of finalize + apply
                 op([=](cudaStream_t st) {
-                    gn_apply_fused(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P1, st2, P2, out, st);
+                    run_timed_aux(1, gn_bytes, st, [&] {
+                        gn_apply_fused(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P1, st2, P2, out, st);
+                    });
                     return (int)cudaGetLastError();
                 });
                 return;
             }
             op([=](cudaStream_t st) {
-                gn_finalize_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P1, st2, P2, ab,
-                                  out, st);
+                run_timed_aux(1, gn_bytes, st, [&] {
+                    gn_finalize_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, st1, P1, st2, P2, ab, out, st);
+                });
                 return (int)cudaGetLastError();
             }, 2);
             return;
         }
         op([=](cudaStream_t st) {
-            gn_stats(p1, C1, C1, p2, C2, C2, Bn, HW, 32, ws, slabs, st);
-            gn_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, ws, slabs, out, st);
+            run_timed_aux(1, 1.5 * gn_bytes, st, [&] {  // two-pass form: the statistics pass reads the tensor once more
+                gn_stats(p1, C1, C1, p2, C2, C2, Bn, HW, 32, ws, slabs, st);
+                gn_apply(p1, C1, C1, p2, C2, C2, Bn, HW, 32, eps, gamma, beta, film, film_ld, silu, ws, slabs, out, st);
+            });
             return (int)cudaGetLastError();
         },
            2);

@@ -25,6 +25,9 @@ static long long g_launches = 0;
 void count_launches(long long n) { g_launches += n; }
 long long total_launches() { return g_launches; }
 
+static int g_opt_attnblk = 1;  // DDPM AttnBlock at 16x16 as one kernel (attnblk_tc.cu); 0 = the round-1 five-launch form
+int attnblk_option() { return g_opt_attnblk; }
+void set_attnblk(int v) { g_opt_attnblk = v; }
 static int g_opt_gn_fused = 0;
 int gn_fused_option() { return g_opt_gn_fused; }
 void set_gn_fused(int v) { g_opt_gn_fused = v; }
@@ -249,6 +252,33 @@ struct DdpmBuilder : Builder {
     Act attn(const std::string& p, Act x) {
         cur_label = p;
         const int C = x.C, H = x.H, W = x.W, HW = H * W;
+        if (HW == 256 && C == 256 && x.has_stats && !x.stats_halo && attnblk_option()) {
+            // the whole block as one kernel per image pair-cluster (attnblk_tc.cu)
+            Act out = new_act(C, H, W);
+            if (!out.has_stats || out.stats_P != 2) fail("attnblk: unexpected GroupNorm partial layout of the output");
+            bf16* w = packed_rows(p + ".kvqp", {{{p + ".k.weight", 0, C}}, {{p + ".v.weight", 0, C}}, {{p + ".q.weight", 0, C}},
+                                                {{p + ".proj_out.weight", 0, C}}}, nullptr, nullptr);
+            const float* bias = concat_f32(p + ".kvqp.bias", {p + ".k.bias", p + ".v.bias", p + ".q.bias", p + ".proj_out.bias"});
+            const float* gamma = f32(p + ".norm.weight");
+            const float* beta = f32(p + ".norm.bias");
+            if (!dry && !err) {
+                AttnBlkOp aop;
+                int r = prepare_attnblk256(x.p, w, bias, gamma, beta, x.stats, x.stats_P, 1e-6f, 1.f / sqrtf((float)C), out.p, out.stats, B, &aop);
+                if (r) {
+                    err = r;
+                    engine_set_error("prepare_attnblk256: %s", gemm_last_error());
+                } else {
+                    plan.gemm_flops += aop.flops;
+                    const std::string keep = cur_label;
+                    cur_label = "ATTNBLK " + keep;
+                    op([aop](cudaStream_t st) {
+                        return run_timed_tensor(aop.flops, 256, 256, 256, 6 * aop.B, st, [&] { return run_attnblk256(aop, st); });
+                    });
+                    cur_label = keep;
+                }
+            }
+            return out;
+        }
         bf16* hn = (bf16*)scratch(0, (size_t)B * HW * C * 2);
         group_norm(x, Act{}, p + ".norm", 1e-6f, 0, nullptr, 0, hn);
         Act out = new_act(C, H, W);
@@ -332,7 +362,9 @@ struct DdpmBuilder : Builder {
                         {
                             const std::string keep = cur_label;
                             cur_label = "ATTN " + keep;
-                            op([aop](cudaStream_t st) { return run_attn256(aop, st); });
+                            op([aop](cudaStream_t st) {
+                                return run_timed_tensor(aop.flops, 256, 256, 256, 2 * (int)aop.grid.y, st, [&] { return run_attn256(aop, st); });
+                            });
                             cur_label = keep;
                         }
                     }

@@ -289,7 +289,10 @@ struct AdmBuilder : Builder {
                     {
                         const std::string keep = cur_label;
                         cur_label = "ATTN " + keep;
-                        op([aop](cudaStream_t st) { return run_attn(aop, st); });
+                        op([aop](cudaStream_t st) {
+                            return run_timed_tensor(aop.flops, aop.p.seq, aop.p.seq, 64, 2 * (int)(aop.grid.y * aop.grid.z), st,
+                                                    [&] { return run_attn(aop, st); });
+                        });
                         cur_label = keep;
                     }
                 }

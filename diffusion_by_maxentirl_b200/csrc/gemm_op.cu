@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 namespace dxmi {
@@ -240,6 +241,74 @@ int gemm_timing_collect(double* ms_total, double* flops_total, long long* launch
     *launches = (long long)g_timed.size();
     g_timed.clear();
     if (g_timing_dump) fflush(g_timing_dump);
+    return 0;
+}
+
+// other tcgen05 contraction launches (fused attention kernels): timed into the same list as the GEMMs
+int run_timed_tensor(double flops, int M, int N, int K, int batch, cudaStream_t st, const std::function<int()>& launch) {
+    if (!g_time_gemms) return launch();
+    TimedLaunch t;
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    t.flops = flops;
+    t.M = M;
+    t.N = N;
+    t.K = K;
+    t.batch = batch;
+    t.block_n = 0;
+    t.v2 = 9;  // marks a fused attention kernel in the per-shape dump
+    cudaEventRecord(t.a, st);
+    int r = launch();
+    cudaEventRecord(t.b, st);
+    g_timed.push_back(t);
+    return r;
+}
+
+// HBM-bound kernel families (GroupNorm finalize + apply, the transition step): CUDA events + algorithmic bytes per launch
+struct TimedAux {
+    cudaEvent_t a, b;
+    int cat;
+    double bytes;
+};
+static std::vector<TimedAux> g_aux;
+void run_timed_aux(int cat, double bytes, cudaStream_t st, const std::function<void()>& launch) {
+    if (!g_time_gemms) {
+        launch();
+        return;
+    }
+    TimedAux t;
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    t.cat = cat;
+    t.bytes = bytes;
+    cudaEventRecord(t.a, st);
+    launch();
+    cudaEventRecord(t.b, st);
+    g_aux.push_back(t);
+}
+int aux_timing_collect(int cat, double* ms_total, double* bytes_total, long long* launches) {
+    double ms = 0, by = 0;
+    long long n = 0;
+    std::vector<TimedAux> keep;
+    for (auto& t : g_aux) {
+        if (t.cat != cat) {
+            keep.push_back(t);
+            continue;
+        }
+        cudaError_t e = cudaEventSynchronize(t.b);
+        if (e != cudaSuccess) return (int)e;
+        float m = 0.f;
+        cudaEventElapsedTime(&m, t.a, t.b);
+        ms += m;
+        by += t.bytes;
+        ++n;
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    g_aux.swap(keep);
+    *ms_total = ms;
+    *bytes_total = by;
+    *launches = n;
     return 0;
 }
 

@@ -1,4 +1,5 @@
 #pragma once
+#include <functional>
 #include "../../include/dxmi_b200.h"
 #include "gemm_tc.cuh"
 
@@ -25,5 +26,10 @@ void set_time_gemms(int v);
 void set_timing_dump(const char* path);
 int gemm_timing_collect(double* ms_total, double* flops_total, long long* launches);
 const char* gemm_op_last_error();
+// "time_gemms" profiling (bench.py roofline legs): other tcgen05 launches join the GEMM list; HBM-bound families are kept
+// per category (1 = GroupNorm finalize + apply, 2 = transition step) with their algorithmic bytes
+int run_timed_tensor(double flops, int M, int N, int K, int batch, cudaStream_t st, const std::function<int()>& launch);
+void run_timed_aux(int cat, double bytes, cudaStream_t st, const std::function<void()>& launch);
+int aux_timing_collect(int cat, double* ms_total, double* bytes_total, long long* launches);
 
 }  // namespace dxmi

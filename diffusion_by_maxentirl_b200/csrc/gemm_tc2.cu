@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                                 ptx::tc_fence_after();
                                 // shifted window of the halo tile: the swizzle is a function of the absolute smem address,
                                 // so a start offset of any multiple of 128 bytes addresses the rows TMA wrote
-                                // (verified on hardware, tools/exp_halo.py)
+                                // (verified on hardware, tools/exp_halo.py + tools/csrc/exp_halo.cu)
                                 const uint64_t da = ptx::make_kmajor_sw128_desc(a0 + (r * Wp + q) * 128);
                                 const uint64_t db = ptx::make_kmajor_sw128_desc(sB0 + sb * Cfg::B_STAGE_BYTES);
                                 if (p.dbg_mode != 1) {

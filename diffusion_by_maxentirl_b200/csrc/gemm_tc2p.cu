@@ -5,7 +5,7 @@
 // together: each loads its own 128 A rows and only HALF of the B tile; one tcgen05.mma.cta_group::2 (M = 256, issued by the
 // leader CTA) reads A from each CTA's shared memory and the two B halves from both, and writes 128 accumulator rows into
 // each CTA's TMEM.  Per-SM ingest per K step drops from 16 + BLOCK_N/4 KB to 16 + BLOCK_N/8 KB.
-// (Mechanics verified first in isolation on hardware: csrc/exp_2cta.cu, tools/exp_2cta.py.)
+// (Mechanics verified first in isolation on hardware: tools/csrc/exp_2cta.cu, tools/exp_2cta.py.)
 //
 // Barriers: full[s] lives in the LEADER (2 arrivals + the bytes of both CTAs; the peer's TMA loads signal it through the
 // cluster window), empty[s] / tmem_full[a] live in BOTH CTAs (multicast tcgen05.commit), tmem_empty[a] lives in the leader

@@ -979,11 +979,20 @@ void attn_small(const bf16* q, const bf16* k, const bf16* v, int ld, bf16* out, 
 
 // ============================================================================================ sampler transitions
 
+// fp32 sample in [-1, 1] -> uint8: ((x + 1) * 127.5).clamp(0, 255) truncated (generate_large.py:43, generate_cifar10.py:205-209);
+// the same expression as quantize_u8_k, so the fused and the stand-alone forms agree bit for bit
+__device__ __forceinline__ uint8_t quant1(float x) {
+    float v = (x + 1.f) * 127.5f;
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    return (uint8_t)v;
+}
+__device__ __forceinline__ uchar4 quant4(const float (&v)[4]) { return make_uchar4(quant1(v[0]), quant1(v[1]), quant1(v[2]), quant1(v[3])); }
+
 // one CTA per sample (logp is a per-sample reduction).
 __global__ void var_step_k(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z,
                            const float* __restrict__ a, const float* __restrict__ c, const float* __restrict__ sigma,
                            float* __restrict__ xn, float* __restrict__ mean, float* __restrict__ control,
-                           float* __restrict__ logp, int CHW) {
+                           float* __restrict__ logp, uint8_t* __restrict__ u8, int CHW) {
     __shared__ float sh[32];
     const int n = blockIdx.x;
     const float an = a[n], cn = c[n], sn = sigma[n];
@@ -1007,6 +1016,7 @@ __global__ void var_step_k(const float* __restrict__ x, const float* __restrict_
             acc += -(dlt * dlt) * inv2var + cst;
         }
         *reinterpret_cast<float4*>(xn + base + i) = make_float4(nx[0], nx[1], nx[2], nx[3]);
+        if (u8) *reinterpret_cast<uchar4*>(u8 + base + i) = quant4(nx);
         if (mean) *reinterpret_cast<float4*>(mean + base + i) = make_float4(mu[0], mu[1], mu[2], mu[3]);
         if (control) *reinterpret_cast<float4*>(control + base + i) = make_float4(ctl[0], ctl[1], ctl[2], ctl[3]);
     }
@@ -1014,13 +1024,13 @@ __global__ void var_step_k(const float* __restrict__ x, const float* __restrict_
     if (threadIdx.x == 0 && logp) logp[n] = tot / (float)CHW;
 }
 void var_step(const float* x, const float* eps, const float* z, const float* a, const float* c, const float* sigma,
-              float* xn, float* mean, float* control, float* logp, int N, int CHW, cudaStream_t st) {
-    var_step_k<<<N, 256, 0, st>>>(x, eps, z, a, c, sigma, xn, mean, control, logp, CHW);
+              float* xn, float* mean, float* control, float* logp, uint8_t* u8, int N, int CHW, cudaStream_t st) {
+    var_step_k<<<N, 256, 0, st>>>(x, eps, z, a, c, sigma, xn, mean, control, logp, u8, CHW);
 }
 
 __global__ void edm_step_k(const float* __restrict__ x, const float* __restrict__ F, const float* __restrict__ z,
-                           const float* __restrict__ coef, float* __restrict__ xn, float* __restrict__ mean, int CHW4,
-                           long long total4) {
+                           const float* __restrict__ coef, float* __restrict__ xn, float* __restrict__ mean,
+                           uint8_t* __restrict__ u8, int CHW4, long long total4) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i / CHW4);
         const float c_skip = coef[n * 5 + 0], c_out = coef[n * 5 + 1], sg = coef[n * 5 + 2], sd = coef[n * 5 + 3],
@@ -1039,15 +1049,16 @@ __global__ void edm_step_k(const float* __restrict__ x, const float* __restrict_
             nx[j] = mu[j] + zs[j] * sn;
         }
         reinterpret_cast<float4*>(xn)[i] = make_float4(nx[0], nx[1], nx[2], nx[3]);
+        if (u8) reinterpret_cast<uchar4*>(u8)[i] = quant4(nx);
         if (mean) reinterpret_cast<float4*>(mean)[i] = make_float4(mu[0], mu[1], mu[2], mu[3]);
     }
 }
-void edm_step(const float* x, const float* F, const float* z, const float* coef, float* xn, float* mean, int N, int CHW,
-              cudaStream_t st) {
+void edm_step(const float* x, const float* F, const float* z, const float* coef, float* xn, float* mean, uint8_t* u8, int N,
+              int CHW, cudaStream_t st) {
     const long long total4 = (long long)N * CHW / 4;
     long long blocks = (total4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    edm_step_k<<<(int)blocks, 256, 0, st>>>(x, F, z, coef, xn, mean, CHW / 4, total4);
+    edm_step_k<<<(int)blocks, 256, 0, st>>>(x, F, z, coef, xn, mean, u8, CHW / 4, total4);
 }
 
 // per-step coefficient broadcast for the EDM rollout: coef[n] = v[2..6], x_scale[n] = v[0], t[n] = v[1]
@@ -1164,11 +1175,8 @@ void nchw_f32_to_nhwc_bf16(const float* x, bf16* out, int N, int C, int HW, cuda
 }
 
 __global__ void quantize_u8_k(const float* __restrict__ x, uint8_t* __restrict__ out, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        float v = (x[i] + 1.f) * 127.5f;
-        v = fminf(fmaxf(v, 0.f), 255.f);
-        out[i] = (uint8_t)v;  // truncation == torch .to(uint8)
-    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = quant1(x[i]);  // truncation == torch .to(uint8)
 }
 void quantize_u8(const float* x, uint8_t* out, long long n, cudaStream_t st) {
     long long blocks = (n + 255) / 256;

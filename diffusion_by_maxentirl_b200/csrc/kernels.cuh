@@ -79,11 +79,11 @@ void attn_small(const bf16* q, const bf16* k, const bf16* v, int ld, bf16* out, 
 // VARSampler step (var_sampler.py:250-295 / :357-408): per-sample coefficients a,c,sigma [N].
 //   mean = a*x + c*eps ; xn = mean + sigma*z ; control = c*eps ; logp[n] = mean_CHW N(xn; mean, sigma).log_prob
 void var_step(const float* x, const float* eps, const float* z, const float* a, const float* c, const float* sigma,
-              float* xn, float* mean, float* control, float* logp, int N, int CHW, cudaStream_t st);
+              float* xn, float* mean, float* control, float* logp, uint8_t* u8, int N, int CHW, cudaStream_t st);
 // EDM ancestral step (openai_diffusion.py:67-99, karras_diffusion.py:336-351): per-sample coefficient table
 // coef[n] = {c_skip, c_out, sigma, sigma_down, sigma_noise}; F = raw network output.
 //   D = c_out*F + c_skip*x ; mu = x + (x - D)/sigma * (sigma_down - sigma) ; xn = mu + sigma_noise * z
-void edm_step(const float* x, const float* F, const float* z, const float* coef, float* xn, float* mean, int N, int CHW,
+void edm_step(const float* x, const float* F, const float* z, const float* coef, float* xn, float* mean, uint8_t* u8, int N, int CHW,
               cudaStream_t st);
 
 // broadcast one EDM schedule row {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down} (host) + the step's noise scale

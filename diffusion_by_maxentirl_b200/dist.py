@@ -49,3 +49,48 @@ def gather_rollout(samples_u8, energies=None, group=None):
         out_e = torch.empty(world * e.shape[0], dtype=torch.float32, device=e.device)
         dist.all_gather_into_tensor(out_e, e, group=group)
     return out_s, out_e
+
+
+class PackedRollout:
+    """The rank's end-of-rollout payload as ONE contiguous uint8 buffer: [B*C*H*W bytes of u8 samples | B fp32 energies].
+    The last transition kernel writes the quantised samples straight into `samples_u8` (sampler.sample(u8_out=...)) and the
+    value head writes into `energies` (value(x, t, out=...)), so the post-rollout step (generate_large.py:36-50 + the energy
+    statistics) is a single all-gather of this buffer with no quantise / pack kernels in between."""
+
+    def __init__(self, B, sample_shape, device, world=None, with_energy=True):
+        self.B, self.shape = int(B), tuple(sample_shape)
+        self.n_u8 = self.B * int(torch.tensor(self.shape).prod())
+        assert self.n_u8 % 4 == 0
+        self.with_energy = with_energy
+        self.nbytes = self.n_u8 + (4 * self.B if with_energy else 0)
+        self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else world
+        self.local = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        self.samples_u8 = self.local[: self.n_u8].view(self.B, *self.shape)
+        self.energies = self.local[self.n_u8:].view(torch.float32) if with_energy else None
+        self.gathered = torch.zeros(self.world, self.nbytes, dtype=torch.uint8, device=device) if self.world > 1 else None
+
+    def all_gather(self, group=None):
+        """One collective; returns (samples [world*B, C, H, W] u8, energies [world*B] fp32 or None) in rank order."""
+        if self.world == 1:
+            return self.samples_u8, self.energies
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.local, group=group)
+        return self.unpack()
+
+    def unpack(self):
+        g = self.gathered
+        s = g[:, : self.n_u8].reshape(self.world * self.B, *self.shape)
+        e = g[:, self.n_u8:].contiguous().view(torch.float32).reshape(-1) if self.with_energy else None
+        return s, e
+
+
+def gather_packed(samples, energies=None, group=None):
+    """Convenience form for un-graphed callers: quantise + pack + ONE all-gather (instead of two)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    u8 = samples if samples.dtype == torch.uint8 else quantize_u8(samples)
+    if world == 1:
+        return u8, (energies.reshape(-1) if energies is not None else None)
+    pk = PackedRollout(u8.shape[0], u8.shape[1:], u8.device, world=world, with_energy=energies is not None)
+    pk.samples_u8.copy_(u8)
+    if energies is not None:
+        pk.energies.copy_(energies.reshape(-1).float())
+    return pk.all_gather(group)

@@ -11,8 +11,11 @@ import torch
 
 
 class GraphedRollout:
-    def __init__(self, sampler, n_sample, device, value=None, labels=None, warmup=2):
+    def __init__(self, sampler, n_sample, device, value=None, labels=None, warmup=2, packed=None, capture_gather=False):
+        """packed: a dist.PackedRollout - the last transition kernel then writes the u8 samples and the value head the energies
+        straight into its buffer; capture_gather: also capture the single NCCL all-gather of that buffer inside the graph."""
         self.sampler, self.value = sampler, value
+        self.packed, self.capture_gather = packed, capture_gather and packed is not None and packed.world > 1
         self.B, self.T = int(n_sample), sampler.n_timesteps
         self.device = torch.device(device)
         shape = tuple(sampler.sample_shape)
@@ -32,12 +35,20 @@ class GraphedRollout:
 
     @torch.no_grad()
     def _run(self):
+        u8 = self.packed.samples_u8 if self.packed is not None else None
         if self.edm:
             d = self.sampler.sample(self.B, self.device, i_class=self.labels, x0=self.noise[0] * self.sampler.sigma_max,
-                                    noise=self.noise[1:])
+                                    noise=self.noise[1:], u8_out=u8)
         else:
-            d = self.sampler.sample(self.B, device=self.device, noise=self.noise)
-        e = self.value(d["sample"], self.T) if self.value is not None else None
+            d = self.sampler.sample(self.B, device=self.device, noise=self.noise, u8_out=u8)
+        e = None
+        if self.value is not None:
+            if self.packed is not None and self.packed.with_energy:
+                e = self.value(d["sample"], self.T, out=self.packed.energies)
+            else:
+                e = self.value(d["sample"], self.T)
+        if self.capture_gather:
+            self.packed.all_gather()
         return d, e
 
     def __call__(self, noise=None):

@@ -107,9 +107,11 @@ class OpenAIDiffusion:
                                       L.stream_ptr(x)), "dxmi_edm_step")
         return {"sample": xn, "mean": mu, "sigma": s_noise.clamp(1e-4, None)}
 
-    def sample(self, n_sample, device, i_class=None, enable_grad=False, x0=None, noise=None):
+    def sample(self, n_sample, device, i_class=None, enable_grad=False, x0=None, noise=None, u8_out=None):
         """Reference OpenAIDiffusion.sample (:101-127).  `noise` (optional, parity contract): the T per-step z tensors
-        ([T, B, C, H, W] or a list); without it, `torch.randn_like` draws are made in the reference's order."""
+        ([T, B, C, H, W] or a list); without it, `torch.randn_like` draws are made in the reference's order.
+        `u8_out` (optional, not in the reference): uint8 [B, C, H, W] CUDA tensor filled by the last transition kernel with
+        `((x + 1) * 127.5).clamp(0, 255)` (generate_large.py:43); also returned as d["sample_u8"]."""
         if enable_grad:
             raise NotImplementedError("enable_grad=True (backward through the rollout) is not built on the B200 path")
         device = torch.device(device)
@@ -145,11 +147,14 @@ class OpenAIDiffusion:
                             dim=1).float().contiguous()
         l_sample = torch.empty(T + 1, B, *shape, device=device)
         mean = torch.empty(T, B, *shape, device=device)
+        if u8_out is not None:
+            assert u8_out.dtype == torch.uint8 and u8_out.is_contiguous() and u8_out.numel() == B * l_sample[0, 0].numel() and u8_out.is_cuda
         L.check(
             L.lib().dxmi_edm_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), L.ptr(s_noise), T, L.ptr(buf),
                                      L.ptr(i_class),
-                                     L.ptr(l_sample), L.ptr(mean), B, L.stream_ptr(device)),
+                                     L.ptr(l_sample), L.ptr(mean), L.ptr(u8_out), B, L.stream_ptr(device)),
             "dxmi_edm_rollout")
         sig_dev = s_noise.clamp(1e-4, None)
-        return {"sample": l_sample[T], "l_sample": [l_sample[i] for i in range(T + 1)], "y": i_class,
+        extra = {"sample_u8": u8_out} if u8_out is not None else {}
+        return {**extra, "sample": l_sample[T], "l_sample": [l_sample[i] for i in range(T + 1)], "y": i_class,
                 "mean": [mean[i] for i in range(T)], "sigma": [sig_dev[i].repeat(B) for i in range(T)]}

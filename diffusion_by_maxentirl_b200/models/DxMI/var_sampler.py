@@ -58,9 +58,12 @@ class VARSampler(nn.Module):
         return self.net(x, t)
 
     # ------------------------------------------------------------------ rollout
-    def sample(self, n_sample, device="cpu", enable_grad=False, noise=None):
+    def sample(self, n_sample, device="cpu", enable_grad=False, noise=None, u8_out=None):
         """Reference VARSampler.sample (:411-428).  `noise` (optional, parity contract): [T+1, B, C, H, W] or a list of
-        T+1 tensors; noise[0] is x_0.  Without it, T+1 `torch.randn` draws are made in the reference's order."""
+        T+1 tensors; noise[0] is x_0.  Without it, T+1 `torch.randn` draws are made in the reference's order.
+        `u8_out` (optional, not in the reference): a uint8 [B, C, H, W] CUDA tensor that the last transition kernel fills with
+        the quantised samples (the callers' `((x + 1) * 127.5).clamp(0, 255).to(uint8)`, generate_cifar10.py:205-209);
+        also returned as d["sample_u8"]."""
         if enable_grad:
             raise NotImplementedError("enable_grad=True (backward through the rollout) is not built on the B200 path")
         device = torch.device(device)
@@ -84,11 +87,15 @@ class VARSampler(nn.Module):
         mean = torch.empty(T, B, *shape, device=device)
         control = torch.empty(T, B, *shape, device=device)
         logp = torch.empty(T, B, device=device)
+        if u8_out is not None:
+            assert u8_out.dtype == torch.uint8 and u8_out.is_contiguous() and u8_out.numel() == B * l_sample[0, 0].numel() and u8_out.is_cuda
         L.check(
             L.lib().dxmi_var_rollout(h, sched.numpy().ctypes.data_as(C.POINTER(C.c_float)), L.ptr(sig_dev), T, L.ptr(noise_t),
-                                     L.ptr(l_sample), L.ptr(mean), L.ptr(control), L.ptr(logp), B, L.stream_ptr(device)),
+                                     L.ptr(l_sample), L.ptr(mean), L.ptr(control), L.ptr(logp), L.ptr(u8_out), B, L.stream_ptr(device)),
             "dxmi_var_rollout")
+        extra = {"sample_u8": u8_out} if u8_out is not None else {}
         return {
+            **extra,
             "sample": l_sample[T],
             "l_sample": [l_sample[i] for i in range(T + 1)],
             "logp": [logp[i] for i in range(T)],

@@ -104,7 +104,9 @@ class IGEBMEncoderV2(NativeNet):
         if missing:
             raise RuntimeError(f"load_pretrained: missing keys {missing[:4]}{'...' if len(missing) > 4 else ''}")
 
-    def forward(self, input, y=None):
+    def forward(self, input, y=None, out=None):
+        """`out` (optional, not in the reference): a contiguous fp32 CUDA tensor of B elements the energies are written into
+        (e.g. the energy slot of a packed gather buffer); inference only."""
         if y is not None:
             raise NotImplementedError("class-conditional value net is not used by the built configs")
         B, _, H, W = input.shape
@@ -123,7 +125,11 @@ class IGEBMEncoderV2(NativeNet):
             return out
         h = self._ensure_handle(input.device)
         x = input.detach().contiguous().float()
-        out = torch.empty(B, 1, device=x.device)
+        if out is None:
+            out = torch.empty(B, 1, device=x.device)
+        else:
+            assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == B and out.device == x.device
+            out = out.view(B, 1)
         L.check(L.lib().dxmi_value_forward(h, L.ptr(x), L.ptr(out), B, L.stream_ptr(x)), "dxmi_value_forward")
         self.pre_activation = out
         return out

@@ -7,7 +7,9 @@ class TimeIndependentValue(nn.Module):
         super().__init__()
         self.net = net
 
-    def forward(self, x, t, y=None):
+    def forward(self, x, t, y=None, out=None):
+        if out is not None:  # B200 extension: write the energies into a caller-provided buffer (packed gather)
+            return self.net(x, y, out=out)
         return self.net(x, y) if y is not None else self.net(x)
 
     def load_pretrained(self, ckpt):

@@ -96,14 +96,17 @@ int dxmi_edm_step(const float* x, const float* F, const float* z, const float* c
  * sched (host) [T,3] fp32 rows {tau_i, a_i, c_i * adhoc_scale1} (Appendix E.1 of SURVEY.md); sigma (DEVICE) [T] fp32 =
  * the per-step noise scale (it derives from the learnable log_betas, so it stays on the device: no host sync);
  * noise [T+1,B,C,H,W] fp32: noise[0] = x_0, noise[1+i] = z of step i (host-supplied noise is part of the parity
- * contract); l_sample [T+1,B,C,H,W]; mean, control [T,B,C,H,W] or NULL; logp [T,B] or NULL. */
+ * contract); l_sample [T+1,B,C,H,W]; mean, control [T,B,C,H,W] or NULL; logp [T,B] or NULL.
+ * sample_u8 [B,C,H,W] or NULL: the final samples quantised to uint8 by the LAST transition kernel itself
+ * (((x+1)*127.5).clamp(0,255), generate_cifar10.py:205-209 / generate_large.py:43) - the post-rollout step fused in. */
 int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_dev, int T, const float* noise,
-                     float* l_sample, float* mean, float* control, float* logp, int B, dxmi_stream_t stream);
+                     float* l_sample, float* mean, float* control, float* logp, uint8_t* sample_u8, int B,
+                     dxmi_stream_t stream);
 /* OpenAIDiffusion.sample() (openai_diffusion.py:101-127). sched (host) [T,6] fp32 rows
  * {c_in, rescaled_t, c_skip, c_out, sigma, sigma_down}; sigma_noise (DEVICE) [T] fp32 = the noise scale actually applied
- * per step (openai_diffusion.py:79-92); noise[0] = x_0 (already scaled by sigma_max). */
+ * per step (openai_diffusion.py:79-92); noise[0] = x_0 (already scaled by sigma_max). sample_u8: as above (or NULL). */
 int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_noise_dev, int T, const float* noise,
-                     const int64_t* y, float* l_sample, float* mean, int B, dxmi_stream_t stream);
+                     const int64_t* y, float* l_sample, float* mean, uint8_t* sample_u8, int B, dxmi_stream_t stream);
 
 /* samples in [-1,1] -> uint8 ((x+1)*127.5 clamp), generate_large.py:43 */
 int dxmi_quantize_u8(const float* x, uint8_t* out, long long n, dxmi_stream_t stream);
@@ -222,6 +225,9 @@ int dxmi_set_timing_dump(const char* path); /* "block_n_256" (tile width), "time
 /* with "time_gemms" on: summed CUDA-event duration / algorithmic FLOPs / count of the tcgen05 GEMM launches since
  * the last call (synchronises on the recorded events) */
 int dxmi_gemm_timing(double* ms_total, double* flops_total, long long* launches);
+/* with "time_gemms" on: the same for the HBM-bound kernel families, with their ALGORITHMIC bytes (one read + one write of the
+ * tensor in its storage type). category 1 = GroupNorm finalize + apply, 2 = transition step x' = mu + sigma z (K6) */
+int dxmi_aux_timing(int category, double* ms_total, double* bytes_total, long long* launches);
 /* algorithmic 2*M*N*K FLOPs of all tcgen05 GEMM launches of one forward at batch B (0 if that plan is not built) */
 double dxmi_plan_gemm_flops(dxmi_net_t net, int B);
 /* number of kernels launched by this library since process start (bench.py "gpu_launches") */

@@ -34,6 +34,15 @@ def _worker(rank, world, port, T, B_global):
     want_u8 = ((want_x + 1) * 127.5).clamp(0, 255).to(torch.uint8)
     assert all_u8.shape == (B_global, 3, 8, 8) and torch.equal(all_u8, want_u8)
     assert torch.allclose(all_e, want_x.flatten(1).sum(1))
+    # the packed form: ONE collective for (u8 samples | fp32 energies); bit-identical payload
+    from diffusion_by_maxentirl_b200.dist import PackedRollout
+
+    pk = PackedRollout(hi - lo, (3, 8, 8), "cpu", world=world)
+    pk.samples_u8.copy_(u8)
+    pk.energies.copy_(energy.reshape(-1))
+    p_u8, p_e = pk.all_gather()
+    assert torch.equal(p_u8, want_u8) and torch.equal(p_e, all_e)
+    assert pk.local.numel() == (hi - lo) * (3 * 8 * 8 + 4)
     dist.destroy_process_group()
 
 

@@ -154,3 +154,28 @@ def test_net_on_non_current_device():
         b = net0(x.cuda(0), t.cuda(0))
     assert torch.cuda.current_device() == 0
     assert a.device.index == 1 and torch.equal(a.cpu(), b.cpu())
+
+
+def test_fused_u8_of_last_step_equals_standalone_quantise(ddpm4):
+    """f3: the last transition kernel writes the u8 samples itself; must equal quantize_u8(sample) == the reference's
+    ((x + 1) * 127.5).clamp(0, 255).to(uint8), bit for bit (VARSampler and OpenAIDiffusion)."""
+    from common import EDM_SMALL_CFG, build_edm
+    from diffusion_by_maxentirl_b200.dist import PackedRollout, quantize_u8
+
+    net, sampler, value, sd, vsd = ddpm4
+    B = 6
+    pk = PackedRollout(B, (3, 32, 32), "cuda", world=1)
+    with torch.no_grad():
+        d = sampler.sample(B, device="cuda", u8_out=pk.samples_u8)
+        e = value(d["sample"], 4, out=pk.energies)
+    torch.cuda.synchronize()
+    want = ((d["sample"] + 1) * 127.5).clamp(0, 255).to(torch.uint8)
+    assert torch.equal(d["sample_u8"], want) and torch.equal(quantize_u8(d["sample"]), want)
+    assert torch.equal(pk.energies, e.reshape(-1)) and e.data_ptr() == pk.energies.data_ptr()
+    unet, esampler, _ = build_edm(EDM_SMALL_CFG, 4)
+    u8 = torch.empty(B, 3, 32, 32, dtype=torch.uint8, device="cuda")
+    y = torch.arange(B, device="cuda")
+    with torch.no_grad():
+        d = esampler.sample(B, "cuda", i_class=y, u8_out=u8)
+    torch.cuda.synchronize()
+    assert torch.equal(u8, ((d["sample"] + 1) * 127.5).clamp(0, 255).to(torch.uint8))

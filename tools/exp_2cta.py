@@ -9,7 +9,8 @@ import torch  # noqa: E402
 
 from diffusion_by_maxentirl_b200 import _lib as L  # noqa: E402
 
-lib = C.CDLL(L.LIB_PATH)
+C.CDLL(L.LIB_PATH, mode=C.RTLD_GLOBAL)
+lib = C.CDLL(os.path.join(ROOT, "tools", "libdxmi_exp.so"))  # make -C tools/csrc
 lib.dxmi_exp_2cta_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 torch.manual_seed(0)
 for M, K in ((256, 64), (512, 256), (256 * 148, 256)):

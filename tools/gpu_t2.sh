@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 600 python -m pytest tests/test_ddpm_gpu.py -x -q -m gpu -s 2>&1 | grep -v "^$" | tail -15
+timeout -s KILL 300 python tools/op_profile.py cifar 256 > gpurun_out/r2_opprof_cifar.log 2>&1; echo "opprof cifar rc=$?"; tail -2 gpurun_out/r2_opprof_cifar.log
+python tools/op_times.py gpurun_out/ops_cifar.csv | head -20
+grep ATTNBLK gpurun_out/ops_cifar.csv | head
