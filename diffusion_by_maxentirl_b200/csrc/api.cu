@@ -47,6 +47,18 @@ int dxmi_set_option(const char* name, int value) {
         set_gn_fused(value);
         return 0;
     }
+    if (!strcmp(name, "shift3")) {  // read when a plan is built
+        set_shift3(value);
+        return 0;
+    }
+    if (!strcmp(name, "small_map_bn")) {  // read when a plan is built
+        set_small_map_bn(value);
+        return 0;
+    }
+    if (!strcmp(name, "pdl")) {  // read at every launch
+        set_pdl(value);
+        return 0;
+    }
     if (!strcmp(name, "attnblk")) {  // read when a plan is built
         set_attnblk(value);
         return 0;

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attnblk256_kernel(const __grid_
     ab_cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    ptx::pdl_wait();  // PDL: the prologue overlapped the previous kernel's tail
+    ptx::pdl_trigger();
 
     if (warp == 8) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -544,13 +546,15 @@ int run_attnblk256(const AttnBlkOp& op, cudaStream_t st) {
     cfg.blockDim = dim3(AB_THREADS);
     cfg.dynamicSmemBytes = AB_SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, attnblk256_kernel, op.p);
     return (int)e;
 }

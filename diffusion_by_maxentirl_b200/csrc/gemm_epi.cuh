@@ -43,9 +43,18 @@ enum EpiMode { EPI_BIAS = 0, EPI_ROWVEC = 1, EPI_RESIDUAL = 2, EPI_GENERIC = 3 }
 // + residual); EPI_GENERIC keeps every switch at run time (softmax, activations, per-row bias, fp32 output).
 // (Measured, profiles/r01_cta_timeline_*: the epilogue is issue / latency bound - 2 warps per scheduler - so code
 //  size and dependent chains matter more than bytes.)
+template <int V>
+struct EpiSlot {
+    static constexpr int value = V;
+};
+
+// `acc_full` / `acc_parity`: the accumulator-ready barrier of this tile.  The epilogue issues its operand prefetches (the
+// residual up to four 32-column chunks ahead: ncu round 2 showed the N = 128 convolutions epilogue bound on exactly these
+// L2-latency loads) BEFORE it waits for the accumulator, so they fly during the tile's main loop.
 template <int MODE, bool STATS>
 __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& cx, uint32_t tacc_col, uint32_t tmem_empty_addr,
-                                         int m_tile, int col0, int nch, int batch, uint32_t& out_cnt) {
+                                         int m_tile, int col0, int nch, int batch, uint32_t& out_cnt, uint64_t* acc_full,
+                                         uint32_t acc_parity, int next_m_tile = -1, int next_col0 = 0, int next_batch = 0) {
     const int row0 = m_tile * TILE_M;
     constexpr int CH = 32;
     const int n_total = p.N_total;
@@ -80,9 +89,10 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             ok = ww < p.halo_W && hh < p.halo_H;
             r = (img * p.halo_H + hh) * p.halo_W + ww;
         } else {
-            r = static_cast<long long>(row0) + cx.rt0 + 4 * i;
-            ok = r < p.M_total;
-            img = use_rv ? r / p.rows_per_image : 0;
+            const int r32 = row0 + cx.rt0 + 4 * i;  // rows are ints (M_total is); a 64-bit division here cost ~1 us per tile
+            r = r32;
+            ok = r32 < p.M_total;
+            img = (use_rv && !((p.rows_per_image & 127) == 0)) ? r32 / p.rows_per_image : 0;
         }
         rok[i] = ok && p.dbg_mode != 2;
         ooff[i] = batch * p.out_batch_stride + r * p.ldo;
@@ -91,27 +101,40 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         rvp[i] = (use_rv && rok[i]) ? p.rowvec + img * p.ldrv : nullptr;
         bm[i] = (g_bm && rok[i]) ? __ldg(p.bias + r) : 0.f;
     }
+    constexpr int RD = (MODE == EPI_RESIDUAL) ? 4 : 1;  // residual prefetch depth in chunks
     float4 pf_bias = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 pf_rv[4];
-    uint2 pf_res[4], pf_gate[4];
+    uint2 pf_res[RD][4], pf_gate[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         pf_rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pf_res[i] = make_uint2(0u, 0u);
         pf_gate[i] = make_uint2(0u, 0u);
+#pragma unroll
+        for (int s = 0; s < RD; ++s) pf_res[s][i] = make_uint2(0u, 0u);
     }
+    auto prefetch_res = [&](auto slot_c, int pcc) {
+        constexpr int slot = decltype(slot_c)::value;
+        if (use_res && pcc < n_total) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rok[i]) pf_res[slot][i] = __ldg(reinterpret_cast<const uint2*>(p.residual + roff[i] + pcc));
+        }
+    };
+    // a 128-row tile of a map with >= 128 pixels lies inside ONE image: the per-image row vector (the ResBlock's time-embedding
+    // projection) is then just a second bias - one load and no per-row adds (it cost ~1.1 us per 128 x 128 tile as 4 loads + 16
+    // adds per thread and chunk: tools/bench_n128.py)
+    const bool rv_uniform = use_rv && !p.halo && (p.rows_per_image & 127) == 0;
     auto prefetch = [&](int pcc) {
         const bool pok = pcc < n_total;
         if (has_bias && pok) pf_bias = __ldg(reinterpret_cast<const float4*>(p.bias + pcc));
         if (use_rv) {
+            if (rv_uniform) {
+                if (pok) pf_rv[0] = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(row0 / p.rows_per_image) * p.ldrv + pcc));
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (rvp[i] && pok) pf_rv[i] = __ldg(reinterpret_cast<const float4*>(rvp[i] + pcc));
-        }
-        if (use_res) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (rok[i] && pok) pf_res[i] = __ldg(reinterpret_cast<const uint2*>(p.residual + roff[i] + pcc));
+                for (int i = 0; i < 4; ++i)
+                    if (rvp[i] && pok) pf_rv[i] = __ldg(reinterpret_cast<const float4*>(rvp[i] + pcc));
+            }
         }
         if (g_gate) {
 #pragma unroll
@@ -120,9 +143,33 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         }
     };
     prefetch(col0 + cx.bu * 4);
+    prefetch_res(EpiSlot<0>{}, col0 + cx.bu * 4);
+    // The NEXT tile's first operands go to L1 now (fire and forget): in the epilogue-bound regime there is no slack before the
+    // accumulator wait, and the first chunks of every tile otherwise eat a full L2 round trip (tools/bench_n128.py:
+    // +1.0 .. 1.4 us per 128 x 128 tile for the row vector / residual)
+    if (next_m_tile >= 0 && !p.halo && (MODE == EPI_ROWVEC || MODE == EPI_RESIDUAL)) {
+        const int nrow0 = next_m_tile * TILE_M;
+        if (MODE == EPI_ROWVEC) {
+            if (rv_uniform && cx.e < 2 * nch) {  // 128-byte lines of this tile's slice of the row vector
+                const float* a = p.rowvec + static_cast<long long>(nrow0 / p.rows_per_image) * p.ldrv + next_col0 + cx.e * 32;
+                if (next_col0 + cx.e * 32 < n_total) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+            }
+        } else {
+            const int prow = nrow0 + (cx.e & 127);  // one 128-byte line (64 bf16 columns) per thread: chunks 0..3 of 128 rows
+            const int pcol = next_col0 + (cx.e >> 7) * 64;
+            if (prow < p.M_total && pcol < n_total)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.residual + next_batch * p.res_batch_stride + static_cast<long long>(prow) * p.ldr + pcol));
+        }
+    }
+    if (RD == 4) {
+        if (1 < nch) prefetch_res(EpiSlot<1 % RD>{}, col0 + cx.bu * 4 + CH);
+        if (2 < nch) prefetch_res(EpiSlot<2 % RD>{}, col0 + cx.bu * 4 + 2 * CH);
+        if (3 < nch) prefetch_res(EpiSlot<3 % RD>{}, col0 + cx.bu * 4 + 3 * CH);
+    }
 
     // ---- accumulator ready?
-    // (the caller has already waited on tmem_full and fenced)
+    ptx::mbar_wait(acc_full, acc_parity);
+    ptx::tc_fence_after();
     if (g_sm) {
         // row max / sum over the whole accumulator row (N_total == BLOCK_N): one warp per lane quarter
         if (cx.hsel == 0) {
@@ -152,8 +199,8 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     const int stat_nseg = 128 / stat_seg, stat_bps = stat_seg >> 5;
     const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : (stat_seg == 32 ? 5 : 4));
 
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
+    auto do_chunk = [&](int c, auto slot_c) {
+        constexpr int rs = decltype(slot_c)::value;  // residual prefetch slot of this chunk
         const int col = col0 + c * CH;
         const int cc = col + cx.bu * 4;
         const bool col_ok = cc < n_total;
@@ -192,13 +239,19 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 x[3] = __expf(__uint_as_float(u.w) * alpha - ms.x) * ms.y;
             } else {
                 float4 ad = pf_bias;
+                if (rv_uniform) {
+                    ad.x += pf_rv[0].x;
+                    ad.y += pf_rv[0].y;
+                    ad.z += pf_rv[0].z;
+                    ad.w += pf_rv[0].w;
+                }
                 if (g_bm) {
                     ad.x += bm[i];
                     ad.y += bm[i];
                     ad.z += bm[i];
                     ad.w += bm[i];
                 }
-                if (use_rv) {
+                if (use_rv && !rv_uniform) {
                     ad.x += pf_rv[i].x;
                     ad.y += pf_rv[i].y;
                     ad.z += pf_rv[i].z;
@@ -209,10 +262,10 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 x[2] = fmaf(__uint_as_float(u.z), alpha, ad.z);
                 x[3] = fmaf(__uint_as_float(u.w), alpha, ad.w);
                 if (use_res) {
-                    x[0] += __uint_as_float(pf_res[i].x << 16);
-                    x[1] += __uint_as_float(pf_res[i].x & 0xffff0000u);
-                    x[2] += __uint_as_float(pf_res[i].y << 16);
-                    x[3] += __uint_as_float(pf_res[i].y & 0xffff0000u);
+                    x[0] += __uint_as_float(pf_res[rs][i].x << 16);
+                    x[1] += __uint_as_float(pf_res[rs][i].x & 0xffff0000u);
+                    x[2] += __uint_as_float(pf_res[rs][i].y << 16);
+                    x[3] += __uint_as_float(pf_res[rs][i].y & 0xffff0000u);
                 }
                 if (g_act != ACT_NONE) {
 #pragma unroll
@@ -248,6 +301,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             }
         }
         if (c + 1 < nch) prefetch(cc + CH);  // next chunk's operands fly during the stats tail and phase A
+        if (c + RD < nch) prefetch_res(slot_c, cc + RD * CH);
         if (STATS) {
             // this warp's 16 rows: fold the 4 row sub-indices (lanes xor 8, 16); then the warps that share a row segment
             // are combined through smem in a fixed order and one partial per segment is published
@@ -290,6 +344,18 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             }
         }
         ++out_cnt;
+    };
+    if (RD == 4) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < nch; c0 += 4) {
+            do_chunk(c0, EpiSlot<0>{});
+            if (c0 + 1 < nch) do_chunk(c0 + 1, EpiSlot<1 % RD>{});
+            if (c0 + 2 < nch) do_chunk(c0 + 2, EpiSlot<2 % RD>{});
+            if (c0 + 3 < nch) do_chunk(c0 + 3, EpiSlot<3 % RD>{});
+        }
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) do_chunk(c, EpiSlot<0>{});
     }
 }
 

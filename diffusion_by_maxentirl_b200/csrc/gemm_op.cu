@@ -9,6 +9,10 @@
 namespace dxmi {
 
 static int g_opt_block_n_256 = 1;
+static int g_opt_small_bn = 1;
+static int g_opt_shift3 = 1;
+void set_shift3(int v) { g_opt_shift3 = v; }
+void set_small_map_bn(int v) { g_opt_small_bn = v; }
 static int g_opt_dbg_mode = 0;
 static int g_opt_gemm_v = 2;
 // Halo-tile A reuse is OFF by default: measured on B200 (profiles/r01_bench_conv_halo.txt) it is correct but 1.2-1.4x
@@ -98,9 +102,20 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     if (block_n == 0) {
         if (d.softmax)
             block_n = d.b_rows;
-        else if (d.b_rows % 256 == 0 && g_opt_block_n_256)
-            // few row tiles (4x4 maps): narrower column tiles put more SMs to work (measured 19.3 -> 16.9 us)
-            block_n = (m_tiles * (d.b_rows / 256) <= 37 && d.batch <= 1) ? 128 : 256;
+        else if (d.b_rows % 256 == 0 && g_opt_block_n_256) {
+            // Small maps (8x8 / 4x4 at batch 256: 128 / 32 row tiles) do not fill the 148 SMs with 256-wide tiles, and a CTA
+            // with a single tile exposes its whole epilogue.  Narrower column tiles give every SM work and a second tile to
+            // overlap the first one's epilogue with (option "small_map_bn": 0 = round-1 rule).
+            const long long t256 = (long long)m_tiles * (d.b_rows / 256) * (d.batch > 0 ? d.batch : 1);
+            if (!g_opt_small_bn)
+                block_n = (t256 <= 37 && d.batch <= 1) ? 128 : 256;
+            else if (t256 >= 148 || d.batch > 1)
+                block_n = 256;
+            else if (t256 >= 74)
+                block_n = 128;
+            else
+                block_n = 64;
+        }
         else if (d.b_rows % 192 == 0)
             block_n = 192;
         else if (d.b_rows >= 128)
@@ -199,6 +214,30 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             return -13;
         }
         op->use_v2 = pair ? 2 : 1;
+        // ---- shift-3 A reuse (pair kernel, BLOCK_N = 128): 3x3 stride-1 convs whose tile is bh full rows of ONE image
+        p.shift3 = 0;
+        if (pair && g_opt_shift3 && !pair_resident_b_enabled() && block_n == 128 && p.stride == 1 && !d.a_batched && op->batch == 1 && d.out_H == d.H &&
+            d.out_W == d.W && bw == d.W && bn == 1 && bh + 2 <= 256 && (d.W * 128) % 1024 == 0) {
+            bool any9 = false;
+            for (int s = 0; s < d.nseg; ++s) any9 |= d.seg_taps[s] == 9;
+            const int a_bytes = (bh + 2) * d.W * 128;
+            const int stage = a_bytes + 3 * (block_n / 2) * 128;
+            const int ring = conv_gemm_pair_ring_bytes(block_n);
+            int st = ring / stage;
+            if (st > 8) st = 8;
+            if (any9 && st >= 3) {
+                p.shift3 = 1;
+                p.s3_a_bytes = a_bytes;
+                p.s3_row_bytes = d.W * 128;
+                p.s3_stages = st;
+                for (int i = 0; i < 3; ++i) {
+                    if (!used[i]) continue;
+                    const long long ld = d.a_ld[i];
+                    r = make_act_map(&p.s3_map[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.N, ld, ld * d.W, ld * d.W * d.H, d.W, bh + 2, 1, 1);
+                    if (r) return r;
+                }
+            }
+        }
     } else if (d.gn_stats || d.gate) {
         snprintf(g_op_err, sizeof g_op_err, "gn_stats / gate requested but the persistent kernel does not support this GEMM");
         return -12;

@@ -15,6 +15,8 @@ struct GemmOp {
 int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op);
 int run_gemm(const GemmOp& op, cudaStream_t st);
 void set_block_n_256(int v);
+void set_small_map_bn(int v);
+void set_shift3(int v);
 void set_dbg_mode(int v);
 void set_gemm_version(int v);
 void set_halo(int v);

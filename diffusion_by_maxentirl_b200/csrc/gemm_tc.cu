@@ -15,6 +15,11 @@
 
 namespace dxmi {
 
+static int g_opt_pdl = 1;
+int pdl_enabled() { return g_opt_pdl; }
+void set_pdl(int v) { g_opt_pdl = v; }
+
+
 static constexpr int TILE_M = 128;
 static constexpr int TILE_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
 static constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;  // 16 KB

@@ -19,6 +19,11 @@
 
 namespace dxmi {
 
+// option "pdl": launch the hot kernels with programmatic stream serialization (see ptx.cuh); read at launch time
+int pdl_enabled();
+void set_pdl(int v);
+
+
 struct GemmSeg {
     int map;      // index into a_map[]
     int ntaps;    // 1 or 9
@@ -71,6 +76,15 @@ struct ConvGemmParams {
     int halo_tpi;              // tiles per image = ceil(H * (W+2) / 128)
     int halo_a_stage;          // bytes of one A (halo) stage, multiple of 1024
     int halo_sb;               // B ring depth in halo mode
+    // shift-3 mode (pair kernel, BLOCK_N = 128, 3x3 stride-1 convs whose 128-pixel tile is bh full image rows): per channel
+    // chunk, THREE loads of a [(bh+2) rows x W x 64 ch] box - one per column shift s = -1, 0, +1 - serve the nine taps: tap
+    // (r, s) is rows r*W .. r*W+127 of box s, a 1024-byte-aligned offset, so plain descriptors apply.  A bytes per tile and
+    // chunk drop from 9 x 16 KB to 3 x (bh+2)*W*128 B: the SM's 64 B/clk ingest port, not the tensor pipe, bounds these layers.
+    int shift3;                // 0 = off
+    int s3_a_bytes;            // bytes of one A box = (bh+2) * W * 128
+    int s3_row_bytes;          // W * 128: smem offset between vertically adjacent taps
+    int s3_stages;             // ring depth in this mode
+    CUtensorMap s3_map[3];     // per source: (c, w, h, n) map with box (64, W, bh+2, 1)
     float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/stats_seg][N_total][2] (sum, sumsq) or null
     int stats_seg;             // rows per partial: 32, 64 or 128 (a segment never straddles two images)
     long long* dbg_times;      // profiling only: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA, or null
@@ -92,8 +106,10 @@ int launch_conv_gemm_v2(const ConvGemmParams& p, int block_n, cudaStream_t strea
 bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n);
 // cta_group::2 pair variant (gemm_tc2p.cu); the B tensor map's box must hold block_n / 2 rows
 int launch_conv_gemm_pair(const ConvGemmParams& p, int block_n, cudaStream_t stream);
-void set_pair_resident_b(int v);  // 0 disables the weights-stationary variant of the pair kernel
+void set_pair_resident_b(int v);
+int pair_resident_b_enabled();  // 0 disables the weights-stationary variant of the pair kernel
 int conv_gemm_v2_ring_bytes(int block_n);
+int conv_gemm_pair_ring_bytes(int block_n);
 // Host helper: (cols, rows, batch) map with a 128-byte x 128-row box for the epilogue (elem_bytes 2 = bf16, 4 = fp32).
 int make_out_map(CUtensorMap* out, const void* base, int elem_bytes, int cols, int rows, int batch, long long row_stride,
                  long long batch_stride);

@@ -69,8 +69,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles * p.batch_count;
-    if (threadIdx.x == 0) { DBG2(0); }
-
     int k_iters = 0;
 #pragma unroll
     for (int s = 0; s < 3; ++s)
@@ -102,7 +100,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (threadIdx.x == 0) { DBG2(1); }
+    // PDL: the prologue above overlapped the previous kernel's tail; from here on its outputs are visible
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
+    if (threadIdx.x == 0) { DBG2(0); DBG2(1); }
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -296,24 +297,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             const int nch = (ncols + 31) / 32;
             const uint32_t acc = ti & 1;
 
-            ptx::mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
-            ptx::tc_fence_after();
             if (ti == 0 && leader) { DBG2(5); }
             const uint32_t tcol = acc * Cfg::ACC_COLS;
             const uint32_t te = ptx::smem_u32(&tmem_empty[acc]);  // own CTA: shared::cta addresses are valid shared::cluster ones
+            int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next tile (operand prefetch)
+            if (t + (int)gridDim.x < total_tiles) {
+                const int tn = t + gridDim.x;
+                const int mtn = tn / p.n_tiles;
+                nx_col0 = (tn % p.n_tiles) * BLOCK_N;
+                nx_m = mtn % p.m_tiles;
+                nx_batch = mtn / p.m_tiles;
+            }
             if (has_stats) {
                 switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
                 }
             } else {
                 switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
                 }
             }
             if (ti == 0 && leader) { DBG2(6); }
@@ -379,8 +386,17 @@ static int launch2_t(const ConvGemmParams& p, cudaStream_t stream) {
     }
     const int total = p.m_tiles * p.n_tiles * p.batch_count;
     const int grid = total < num_sms ? total : num_sms;
-    conv_gemm2_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<BLOCK_N>, p);
     if (e != cudaSuccess) {
         gemm_set_error(cudaGetErrorString(e));
         return (int)e;

@@ -87,6 +87,7 @@ template <int BLOCK_N, bool RESB>
 __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __grid_constant__ ConvGemmParams p) {
     using Cfg = Cfg2P<BLOCK_N, RESB>;
     constexpr int STAGES = Cfg::STAGES;
+    const bool S3 = BLOCK_N == 128 && !RESB && p.shift3;  // launch-uniform
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SM_BAR);
@@ -119,6 +120,11 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
         if (p.nseg > 1) ptx::prefetch_tmap(&p.a_map[1]);
         if (p.nseg > 2) ptx::prefetch_tmap(&p.a_map[2]);
         ptx::prefetch_tmap(&p.b_map);
+        if (S3) {
+            ptx::prefetch_tmap(&p.s3_map[0]);
+            if (p.nseg > 1) ptx::prefetch_tmap(&p.s3_map[1]);
+            if (p.nseg > 2) ptx::prefetch_tmap(&p.s3_map[2]);
+        }
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full_bar[s], 2);   // one arrival per CTA (+ the transaction bytes of both)
             ptx::mbar_init(&empty_bar[s], 1);
@@ -140,6 +146,9 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
     cluster_sync();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: the prologue above overlapped the previous kernel's tail; from here on its outputs are visible
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -173,6 +182,53 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 const int bcoord_n = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
                 const int bcoord_b = p.b_batched ? batch : 0;
                 int kk = 0;
+                if (S3) {
+                    // shift-3 ring: stage = [A box | 3 B tiles] for 3x3 segments, [A tile | B tile] for 1x1 segments
+                    const int stage_bytes = p.s3_a_bytes + 3 * Cfg::B_STAGE_BYTES;
+                    for (int s = 0; s < p.nseg; ++s) {
+                        const GemmSeg sg = p.seg[s];
+                        if (sg.ntaps == 9) {
+                            for (int ch = 0; ch < sg.nchunks; ++ch) {
+                                for (int q = 0; q < 3; ++q, ++it) {
+                                    const uint32_t stage = it % p.s3_stages;
+                                    const uint32_t ph = (it / p.s3_stages) & 1;
+                                    ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+                                    uint8_t* sa = smem + stage * stage_bytes;
+                                    uint8_t* sb = sa + p.s3_a_bytes;
+                                    const uint32_t full_leader = mapa(ptx::smem_u32(&full_bar[stage]), 0);
+                                    if (rank == 0) {
+                                        ptx::mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                                    } else {
+                                        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
+                                    }
+                                    tma2_load_4d(sa, &p.s3_map[sg.map], full_leader, ch * TILE_K, q - 1, h0 - 1, n0);
+#pragma unroll
+                                    for (int r = 0; r < 3; ++r)
+                                        tma2_load_3d(sb + r * Cfg::B_STAGE_BYTES, &p.b_map, full_leader,
+                                                     (kk + (r * 3 + q) * sg.nchunks + ch) * TILE_K, bcoord_n, bcoord_b);
+                                }
+                            }
+                            kk += 9 * sg.nchunks;
+                        } else {
+                            for (int ch = 0; ch < sg.nchunks; ++ch, ++it, ++kk) {
+                                const uint32_t stage = it % p.s3_stages;
+                                const uint32_t ph = (it / p.s3_stages) & 1;
+                                ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+                                uint8_t* sa = smem + stage * stage_bytes;
+                                uint8_t* sb = sa + p.s3_a_bytes;
+                                const uint32_t full_leader = mapa(ptx::smem_u32(&full_bar[stage]), 0);
+                                if (rank == 0) {
+                                    ptx::mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+                                } else {
+                                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
+                                }
+                                tma2_load_4d(sa, &p.a_map[sg.map], full_leader, ch * TILE_K, w0, h0, n0);
+                                tma2_load_3d(sb, &p.b_map, full_leader, kk * TILE_K, bcoord_n, bcoord_b);
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (int s = 0; s < p.nseg; ++s) {
                     const GemmSeg sg = p.seg[s];
                     const CUtensorMap* amap = &p.a_map[sg.map];
@@ -213,6 +269,35 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 ptx::mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t tacc = tmem_base + acc * Cfg::ACC_COLS;
+                if (S3) {
+                    const int stage_bytes = p.s3_a_bytes + 3 * Cfg::B_STAGE_BYTES;
+                    uint32_t first = 1;
+                    for (int s = 0; s < p.nseg; ++s) {
+                        const GemmSeg sg = p.seg[s];
+                        const int nst = sg.ntaps == 9 ? 3 * sg.nchunks : sg.nchunks;
+                        for (int k = 0; k < nst; ++k, ++it) {
+                            const uint32_t stage = it % p.s3_stages;
+                            const uint32_t ph = (it / p.s3_stages) & 1;
+                            ptx::mbar_wait(&full_bar[stage], ph);
+                            ptx::tc_fence_after();
+                            const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+                            const uint32_t sb = sa + p.s3_a_bytes;
+                            const int nr = sg.ntaps == 9 ? 3 : 1;
+                            for (int r = 0; r < nr; ++r) {
+                                const uint64_t da = ptx::make_kmajor_sw128_desc(sa + r * p.s3_row_bytes);
+                                const uint64_t db = ptx::make_kmajor_sw128_desc(sb + r * Cfg::B_STAGE_BYTES);
+                                if (p.dbg_mode != 1) {
+#pragma unroll
+                                    for (int j = 0; j < TILE_K / 16; ++j) umma2_f16(tacc, da + 2 * j, db + 2 * j, idesc, (first && j == 0) ? 0u : 1u);
+                                }
+                                first = 0;
+                            }
+                            umma2_commit_both(&empty_bar[stage]);
+                        }
+                    }
+                    umma2_commit_both(&tmem_full[acc]);
+                    continue;
+                }
                 for (int k = 0; k < k_iters; ++k, ++it) {
                     const uint32_t stage = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -267,23 +352,29 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
             const int nch = (ncols + 31) / 32;
             const uint32_t acc = ti & 1;
 
-            ptx::mbar_wait(&tmem_full[acc], (ti >> 1) & 1);
-            ptx::tc_fence_after();
             const uint32_t tcol = acc * Cfg::ACC_COLS;
             const uint32_t te = mapa(ptx::smem_u32(&tmem_empty[acc]), 0);  // the leader's barrier
+            int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next tile (operand prefetch)
+            if (tp + n_clusters < total_pairs) {
+                const int tn = tp + n_clusters;
+                const int mpn = tn / p.n_tiles;
+                nx_col0 = (tn % p.n_tiles) * BLOCK_N;
+                nx_m = (mpn % m_pairs) * 2 + (int)rank;
+                nx_batch = mpn / m_pairs;
+            }
             if (has_stats) {
                 switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
                 }
             } else {
                 switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
-                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt); break;
+                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
                 }
             }
         }
@@ -300,6 +391,15 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
 // ------------------------------------------------------------------------------------------------ host side
 
 void gemm_set_error(const char* msg);
+
+int conv_gemm_pair_ring_bytes(int block_n) {
+    switch (block_n) {
+        case 128: return Cfg2P<128, false>::RING_BYTES;
+        case 192: return Cfg2P<192, false>::RING_BYTES;
+        case 256: return Cfg2P<256, false>::RING_BYTES;
+        default: return 0;
+    }
+}
 
 bool conv_gemm_pair_supported(const ConvGemmParams& p, int block_n) {
     return (block_n == 128 || block_n == 192 || block_n == 256) && !p.halo && !p.softmax;
@@ -329,13 +429,15 @@ static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(NUM_THREADS_P);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm2p_kernel<BLOCK_N, RESB>, p);
     if (e != cudaSuccess) {
         gemm_set_error(cudaGetErrorString(e));
@@ -346,6 +448,7 @@ static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
 
 static int g_opt_resb = 0;  // measured slower (see RESB comment): kept as an A/B switch
 void set_pair_resident_b(int v) { g_opt_resb = v; }
+int pair_resident_b_enabled() { return g_opt_resb; }
 
 int launch_conv_gemm_pair(const ConvGemmParams& p, int block_n, cudaStream_t stream) {
     int k_iters = 0;

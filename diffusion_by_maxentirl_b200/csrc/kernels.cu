@@ -1,5 +1,7 @@
 // HBM-bound / small kernels of the DxMI sampler path. See kernels.cuh for contracts.
 #include "kernels.cuh"
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
 
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -40,8 +42,32 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
     for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return p;
 }
-__device__ __forceinline__ bf16x8 ld8(const bf16* p) { return *reinterpret_cast<const bf16x8*>(p); }
-__device__ __forceinline__ void st8(bf16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+// 16-byte vector access. (Copying the struct member-wise - what `*reinterpret_cast<const bf16x8*>(p)` compiles to, because
+// __nv_bfloat162 has user-provided copy operations - became FOUR 4-byte LDG / STG per thread: ncu round 2 showed 8.9 of 32
+// bytes used per sector in the GroupNorm kernels.  Go through uint4 so it is one LDG.128 / STG.128.)
+__device__ __forceinline__ bf16x8 ld8(const bf16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    bf16x8 r;
+    *reinterpret_cast<uint4*>(&r) = u;
+    return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const bf16x8& v) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v); }
+
+// launch with programmatic stream serialization (PDL, ptx.cuh): the kernel MUST call ptx::pdl_wait() before its first global access
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -472,6 +498,8 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __res
     const int n = blockIdx.x, slab = blockIdx.y;
     const int pix_per_slab = HW / slabs;
     const int cpg = C / groups;
+    ptx::pdl_wait();  // PDL: x and the partials come from the predecessor (the producer GEMM)
+    ptx::pdl_trigger();
     // (0) start streaming: the first 4 pixel vectors of this thread are requested BEFORE the statistics prologue, whose
     //     latency (two barriers, dependent loads of the partials) then hides behind them
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -596,6 +624,10 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restr
     const int C = C1 + C2;
     const int n = blockIdx.x;
     const int cpg = C / groups;
+    // PDL: wait for the producer of the partials, THEN let the apply kernel's CTAs be scheduled: an apply CTA that starts
+    // early therefore knows the producer GEMM has completed and may prefetch x before its own wait (gn_apply_ab_k)
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
     for (int c = threadIdx.x; c < C; c += GN_THREADS) {
         const bool first = c < C1;
         const float* base = first ? st1 + ((long long)n * P1 * C1 + c) * 2 : st2 + ((long long)n * P2 * C2 + (c - C1)) * 2;
@@ -669,25 +701,40 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_ab_k(const bf16* __restri
     const int n = blockIdx.x, slab = blockIdx.y;
     const int pix_per_slab = HW / slabs;
     const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-    if (pl >= PL) return;
+    const bool active = pl < PL;
+    const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
+    // PDL: this kernel is only ever launched right after gn_finalize_k, which triggers its dependents AFTER its own wait - so
+    // the producer of x has completed by the time any CTA of this kernel runs: the first batch of x is requested before the
+    // wait for the affine table (hides gn_finalize_k's latency and the launch gap)
+    int p = pl;
+    bf16x8 v[U];
+    const bool pre = active && p + (U - 1) * PL < pix_per_slab;
+    if (pre) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + p + u * PL, cv * 8));
+    }
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
+    if (!active) return;
     float a[8], b[8];
     {
         const float4* src = reinterpret_cast<const float4*>(ab + (long long)n * C + cv * 8);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4 v = __ldg(src + j);
-            a[2 * j] = v.x;
-            b[2 * j] = v.y;
-            a[2 * j + 1] = v.z;
-            b[2 * j + 1] = v.w;
+            const float4 t = src[j];
+            a[2 * j] = t.x;
+            b[2 * j] = t.y;
+            a[2 * j + 1] = t.z;
+            b[2 * j + 1] = t.w;
         }
     }
-    const long long base = (long long)n * HW + (long long)slab * pix_per_slab;
-    int p = pl;
+    bool have = pre;
     for (; p + (U - 1) * PL < pix_per_slab; p += U * PL) {
-        bf16x8 v[U];  // U independent 16-byte loads in flight per thread
+        if (!have) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + p + u * PL, cv * 8));
+            for (int u = 0; u < U; ++u) v[u] = ld8(gn_src(x1, C1, ld1, x2, ld2, base + p + u * PL, cv * 8));
+        }
+        have = false;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             float f[8];
@@ -728,23 +775,21 @@ void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int
                     int P1, const float* st2, int P2, bf16* out, cudaStream_t st) {
     const int slabs = gn_apply_slabs(N, HW, C1 + C2);
     dim3 grid(N, slabs);
-    gn_apply_fused_k<<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, groups, eps, gamma, beta, film, film_ld, silu,
-                                                   st1, P1, st2, P2, slabs, out);
+    launch_pdl(gn_apply_fused_k, grid, dim3(GN_THREADS), st, x1, C1, ld1, x2, C2, ld2, HW, groups, eps, gamma, beta, film, film_ld, silu, st1, P1,
+               st2, P2, slabs, out);
 }
 
 void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
                        const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st, float* mr) {
-    gn_finalize_k<<<N, GN_THREADS, 0, st>>>(st1, P1, C1, st2, P2, C2, HW, groups, eps, gamma, beta, film, film_ld,
-                                            reinterpret_cast<float2*>(ab_ws), reinterpret_cast<float2*>(mr));
+    launch_pdl(gn_finalize_k, dim3(N), dim3(GN_THREADS), st, st1, P1, C1, st2, P2, C2, HW, groups, eps, gamma, beta, film, film_ld,
+               reinterpret_cast<float2*>(ab_ws), reinterpret_cast<float2*>(mr));
     const int slabs = gn_apply_slabs(N, HW, C1 + C2);
     dim3 grid(N, slabs);
     if (g_gn_unroll == 8)
-        gn_apply_ab_k<8><<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs,
-                                                      out);
+        launch_pdl(gn_apply_ab_k<8>, grid, dim3(GN_THREADS), st, x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs, out);
     else
-        gn_apply_ab_k<4><<<grid, GN_THREADS, 0, st>>>(x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs,
-                                                      out);
+        launch_pdl(gn_apply_ab_k<4>, grid, dim3(GN_THREADS), st, x1, C1, ld1, x2, C2, ld2, HW, reinterpret_cast<const float2*>(ab_ws), silu, slabs, out);
 }
 
 // [N][P][C][2] -> [N][1][C][2]: collapses many row-segment partials (large feature maps) so that the apply kernel's

@@ -14,6 +14,14 @@ __device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
         f[2 * i + 1] = t.y;
     }
 }
+// one LDG.128 / STG.128 (a member-wise struct copy compiles to four 4-byte accesses, see kernels.cu)
+__device__ __forceinline__ bf16x8 ld8(const bf16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    bf16x8 r;
+    *reinterpret_cast<uint4*>(&r) = u;
+    return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const bf16x8& v) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v); }
 __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
     bf16x8 p;
 #pragma unroll
@@ -42,13 +50,13 @@ __global__ void __launch_bounds__(256) value_head_bwd_k(const bf16* __restrict__
         for (int p = pl; p < HW; p += PL) {
             const long long off = ((long long)n * HW + p) * C + cv * 8;
             float f[8], d[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(h + off), f);
+            unpack8(ld8(h + off), f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s[j] += fmaxf(f[j], 0.f);
                 d[j] = f[j] > 0.f ? w[j] : 0.f;
             }
-            *reinterpret_cast<bf16x8*>(dz + off) = pack8(d);
+            st8(dz + off, pack8(d));
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) sred[pl * C + cv * 8 + j] = s[j];
@@ -122,10 +130,10 @@ __global__ void avgpool2_bwd_k(const bf16* __restrict__ dy, bf16* __restrict__ d
         const int y = (int)(r % H);
         const int n = (int)(r / H);
         float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(dy + ((((long long)n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * CV + cv) * 8), f);
+        unpack8(ld8(dy + ((((long long)n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * CV + cv) * 8), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] *= 0.25f;
-        *reinterpret_cast<bf16x8*>(dx + i * 8) = pack8(f);
+        st8(dx + i * 8, pack8(f));
     }
 }
 void avgpool2_bwd(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaStream_t st) {
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_k(const bf16* __restrict__ x,
         for (; r + 3LL * PL < r1; r += 4LL * PL) {  // 4 independent 16-byte loads in flight per thread
             bf16x8 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const bf16x8*>(x + (r + (long long)u * PL) * C + cv * 8);
+            for (int u = 0; u < 4; ++u) v[u] = ld8(x + (r + (long long)u * PL) * C + cv * 8);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float f[8];
@@ -171,7 +179,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_k(const bf16* __restrict__ x,
         }
         for (; r < r1; r += PL) {
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(x + r * C + cv * 8), f);
+            unpack8(ld8(x + r * C + cv * 8), f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[j] += f[j];
         }
@@ -294,8 +302,8 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_stats_k(const bf16* __rest
         const long long base = (long long)n * HW + (long long)slab * pps;
         for (int p = pl; p < pps; p += PL) {
             float xf[8], df[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(gnb_src(x1, C1, x2, C2, base + p, cv * 8)), xf);
-            unpack8(*reinterpret_cast<const bf16x8*>(dy + (base + p) * C + cv * 8), df);
+            unpack8(ld8(gnb_src(x1, C1, x2, C2, base + p, cv * 8)), xf);
+            unpack8(ld8(dy + (base + p) * C + cv * 8), df);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float dz = silu ? df[j] * silu_grad(fmaf(a[j], xf[j], b[j])) : df[j];
@@ -375,8 +383,8 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_apply_k(const bf16* __rest
     const long long base = (long long)n * HW + (long long)slab * pps;
     for (int p = pl; p < pps; p += PL) {
         float xf[8], df[8], o[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(gnb_src(x1, C1, x2, C2, base + p, cv * 8)), xf);
-        unpack8(*reinterpret_cast<const bf16x8*>(dy + (base + p) * C + cv * 8), df);
+        unpack8(ld8(gnb_src(x1, C1, x2, C2, base + p, cv * 8)), xf);
+        unpack8(ld8(dy + (base + p) * C + cv * 8), df);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float dz = silu ? df[j] * silu_grad(fmaf(a[j], xf[j], b[j])) : df[j];
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_apply_k(const bf16* __rest
             // rstd * (gamma dz - SA/m - xh SB/m) with a = rstd * gamma
             o[j] = fmaf(a[j], dz, -rs[j] * fmaf(xh, sb[j], sa[j]));
         }
-        *reinterpret_cast<bf16x8*>(dx + (base + p) * C + cv * 8) = pack8(o);
+        st8(dx + (base + p) * C + cv * 8, pack8(o));
     }
 }
 
@@ -583,13 +591,13 @@ __global__ void sumpool2_k(const bf16* __restrict__ dy, bf16* __restrict__ out, 
         const int n = (int)(r / h);
         const bf16* p = dy + ((((long long)n * 2 * h + 2 * y) * 2 * w + 2 * x) * CV + cv) * 8;
         float a[8], b[8], c[8], d[8], o[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(p), a);
-        unpack8(*reinterpret_cast<const bf16x8*>(p + CV * 8), b);
-        unpack8(*reinterpret_cast<const bf16x8*>(p + (long long)2 * w * CV * 8), c);
-        unpack8(*reinterpret_cast<const bf16x8*>(p + (long long)2 * w * CV * 8 + CV * 8), d);
+        unpack8(ld8(p), a);
+        unpack8(ld8(p + CV * 8), b);
+        unpack8(ld8(p + (long long)2 * w * CV * 8), c);
+        unpack8(ld8(p + (long long)2 * w * CV * 8 + CV * 8), d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (a[j] + b[j]) + (c[j] + d[j]);
-        *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(o);
+        st8(out + i * 8, pack8(o));
     }
 }
 void sumpool2(const bf16* dy, bf16* out, int N, int h, int w, int C, cudaStream_t st) {
@@ -605,14 +613,14 @@ __global__ void accum_bf16_k(bf16* __restrict__ dst, const bf16* __restrict__ sr
         const int cv = (int)(i % CV);
         const long long r = i / CV;
         float s[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(src + r * ld_src + cv * 8), s);
+        unpack8(ld8(src + r * ld_src + cv * 8), s);
         if (!init) {
             float d[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(dst + i * 8), d);
+            unpack8(ld8(dst + i * 8), d);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[j] += d[j];
         }
-        *reinterpret_cast<bf16x8*>(dst + i * 8) = pack8(s);
+        st8(dst + i * 8, pack8(s));
     }
 }
 void accum_bf16(bf16* dst, const bf16* src, long long ld_src, long long rows, int C, int init, cudaStream_t st) {
@@ -634,7 +642,7 @@ __global__ void __launch_bounds__(256) colsum_per_image_k(const bf16* __restrict
     if (pl < PL) {
         for (int p = pl; p < HW; p += PL) {
             float f[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(x + ((long long)n * HW + p) * C + cv * 8), f);
+            unpack8(ld8(x + ((long long)n * HW + p) * C + cv * 8), f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[j] += f[j];
         }

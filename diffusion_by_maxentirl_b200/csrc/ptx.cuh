@@ -66,6 +66,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running: everything before pdl_wait() (barrier init, TMEM alloc, descriptor prefetch) overlaps the
+// predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its memory is visible.  Every kernel
+// launched that way MUST call pdl_wait() before its first global access (and before finishing), which also keeps the
+// completion order of the stream transitive.  pdl_trigger() lets the successor's CTAs be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -303,6 +303,7 @@ def test_pair_kernel_weights_stationary(ops):
     res = nhwc(torch.randn(N, C, H, H, device=dev))
     wp = ops.pack_conv_weight(w)
     outs = []
+    L.lib().dxmi_set_option(b"shift3", 0)  # the shift-3 A-reuse mode accumulates the taps in another order (tested below)
     for resb in (1, 0):
         L.lib().dxmi_set_option(b"pair_resident_b", resb)
         try:
@@ -311,8 +312,52 @@ def test_pair_kernel_weights_stationary(ops):
         finally:
             L.lib().dxmi_set_option(b"pair_resident_b", 0)
         outs.append((y, stats))
+    L.lib().dxmi_set_option(b"shift3", 1)
     ref = ref_conv(x, w, b) + rowvec[:, None, None, :] + res.float()
     assert rel_l2(outs[0][0].view(N, H, H, C), ref) < 4e-3
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     yf = outs[0][0].float().view(-1, 128, C)
+    assert torch.allclose(outs[0][1][..., 0], yf.sum(1), rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("H,Cin,extra", [(32, 128, 0), (32, 256, 128), (16, 128, 0), (64, 64, 64)])
+def test_pair_kernel_shift3_a_reuse(ops, H, Cin, extra):
+    """Shift-3 mode of the pair kernel (BLOCK_N = 128, 3x3 stride-1, tile = full image rows): three [(bh+2) x W x 64] boxes per
+    channel chunk serve the nine taps.  Must match torch and the nine-box form (same math, another accumulation order); with an
+    extra 1x1 K segment (conv2 + nin_shortcut) the two stage kinds share the ring."""
+    from diffusion_by_maxentirl_b200 import _lib as L
+
+    if not ops.pair_mode:
+        pytest.skip("pair kernel only")
+    torch.manual_seed(21)
+    dev = "cuda"
+    N, Co = (160 if H <= 32 else 40), 128
+    if H == 16:
+        N = 640
+    x = nhwc(torch.randn(N, Cin, H, H, device=dev))
+    w = torch.randn(Co, Cin, 3, 3, device=dev) / (3 * Cin**0.5)
+    b = torch.randn(Co, device=dev)
+    srcs, segs, parts = [(x, Cin, Cin)], [(0, 9)], [(w, 0, Cin)]
+    ref = ref_conv(x, w, b)
+    if extra:
+        x2 = nhwc(torch.randn(N, extra, H, H, device=dev))
+        w2 = torch.randn(Co, extra, 1, 1, device=dev) / extra**0.5
+        srcs.append((x2, extra, extra))
+        segs.append((1, 1))
+        parts.append((w2, 0, extra))
+        ref = ref + F.conv2d(x2.float().permute(0, 3, 1, 2), w2.to(torch.bfloat16).float()).permute(0, 2, 3, 1)
+    wp = ops.pack_conv_weight(None, parts=parts)
+    outs = []
+    for s3 in (1, 0):
+        L.lib().dxmi_set_option(b"shift3", s3)
+        try:
+            seg = 128
+            stats = torch.zeros(N * H * H // seg, Co, 2, device=dev)
+            y = ops.conv_gemm(srcs, segs, wp, N, H, H, bias=b, gn_stats=stats, gn_seg=seg, block_n=128)
+        finally:
+            L.lib().dxmi_set_option(b"shift3", 1)
+        outs.append((y, stats))
+    assert rel_l2(outs[0][0].view(N, H, H, Co), ref) < 4e-3
+    assert rel_l2(outs[0][0].float(), outs[1][0].float()) < 4e-3
+    yf = outs[0][0].float().view(-1, 128, Co)
     assert torch.allclose(outs[0][1][..., 0], yf.sum(1), rtol=1e-4, atol=2e-3)
