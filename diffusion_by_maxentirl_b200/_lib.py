@@ -36,6 +36,11 @@ class ArchDesc(C.Structure):
     ]
 
 
+class OptTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_longlong), ("lr", C.c_float), ("reserved", C.c_int)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("a_ptr", C.c_void_p * 3),
@@ -102,6 +107,11 @@ SYMBOLS = {
     "dxmi_var_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_edm_rollout": (_I, [_VP, C.POINTER(_F), _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_quantize_u8": (_I, [_VP, _VP, _LL, _VP]),
+    "dxmi_running_cost_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _VP]),
+    "dxmi_running_cost_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _VP]),
+    "dxmi_opt_chunk_elems": (_I, []),
+    "dxmi_opt_grad_norm": (_I, [_VP, _VP, _VP, _I, _F, _VP, _VP, _I, _VP]),
+    "dxmi_opt_adam_step": (_I, [_VP, _VP, _VP, _I, _VP, _F, _F, _F, _I, _I, _VP]),
     "dxmi_op_conv_gemm": (_I, [C.POINTER(GemmDesc), _VP]),
     "dxmi_op_pack_conv_weight": (_I, [_VP, _I, _I, _I, _I, _I, _I, _I, _VP, _LL, _LL, _VP]),
     "dxmi_op_group_norm": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I, _I, _F, _VP, _VP, _VP, _I, _I, _VP, _VP, _VP]),

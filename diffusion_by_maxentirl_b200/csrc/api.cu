@@ -47,6 +47,10 @@ int dxmi_set_option(const char* name, int value) {
         set_gn_fused(value);
         return 0;
     }
+    if (!strcmp(name, "stats16")) {  // read when a plan is built
+        set_stats16(value);
+        return 0;
+    }
     if (!strcmp(name, "shift3")) {  // read when a plan is built
         set_shift3(value);
         return 0;

@@ -11,6 +11,7 @@
 namespace dxmi {
 
 int attnblk_option();   // engine.cu: 1 = DDPM AttnBlock at 16x16 as one fused kernel
+int stats16_option();   // engine.cu
 int gn_fused_option();  // engine.cu: 1 = every GroupNorm with producer statistics is ONE kernel (prologue + streaming apply)
 
 struct Builder {
@@ -41,7 +42,13 @@ struct Builder {
     bf16* act_alloc(int C, int H, int W) { return (bf16*)alloc((size_t)B * H * W * C * sizeof(bf16)); }
     // GroupNorm partial-statistics buffer for a GEMM output of B*H*W rows x C columns (null when the fused path
     // cannot be used for this geometry: a 32-row segment must not straddle two images)
-    static int stats_seg(int HW) { return HW % 128 == 0 ? 128 : (HW % 64 == 0 ? 64 : (HW % 32 == 0 ? 32 : (HW % 16 == 0 ? 16 : 0))); }
+    // rows per GroupNorm partial of a GEMM output.  16 (option "stats16", off by default - measured slower): a segment is exactly the 16 rows one
+    // epilogue warp finishes, so the partial goes straight to global memory - no shared-memory combine and no second named
+    // barrier per 32-column chunk in the epilogue (gemm_epi.cuh); the finalize then sums HW/16 partials per image.
+    static int stats_seg(int HW) {
+        if (stats16_option() && HW % 16 == 0) return 16;
+        return HW % 128 == 0 ? 128 : (HW % 64 == 0 ? 64 : (HW % 32 == 0 ? 32 : (HW % 16 == 0 ? 16 : 0)));
+    }
     static size_t stats_bytes(int rows, int HW, int C) { return (size_t)rows / stats_seg(HW) * C * 2 * sizeof(float); }
     // Layout of the GroupNorm partials a GEMM writes for its [B*H*W, C] output: per halo tile for 3x3 stride-1 convs on
     // 32- / 64-wide maps (gemm_op.cu: halo_tiles_per_image), else per 32/64/128-row segment.

@@ -28,6 +28,9 @@ long long total_launches() { return g_launches; }
 static int g_opt_attnblk = 1;  // DDPM AttnBlock at 16x16 as one kernel (attnblk_tc.cu); 0 = the round-1 five-launch form
 int attnblk_option() { return g_opt_attnblk; }
 void set_attnblk(int v) { g_opt_attnblk = v; }
+static int g_opt_stats16 = 0;  // measured (round 2): 16-row direct partials save the 2nd epilogue barrier but cost more in the finalize: -1 % end to end
+int stats16_option() { return g_opt_stats16; }
+void set_stats16(int v) { g_opt_stats16 = v; }
 static int g_opt_gn_fused = 0;
 int gn_fused_option() { return g_opt_gn_fused; }
 void set_gn_fused(int v) { g_opt_gn_fused = v; }
@@ -255,7 +258,8 @@ struct DdpmBuilder : Builder {
         if (HW == 256 && C == 256 && x.has_stats && !x.stats_halo && attnblk_option()) {
             // the whole block as one kernel per image pair-cluster (attnblk_tc.cu)
             Act out = new_act(C, H, W);
-            if (!out.has_stats || out.stats_P != 2) fail("attnblk: unexpected GroupNorm partial layout of the output");
+            if (!out.has_stats || out.stats_P < 2) fail("attnblk: unexpected GroupNorm partial layout of the output");
+            out.stats_P = 2;  // the kernel publishes one partial per 128-row half (the buffer may be sized for more)
             bf16* w = packed_rows(p + ".kvqp", {{{p + ".k.weight", 0, C}}, {{p + ".v.weight", 0, C}}, {{p + ".q.weight", 0, C}},
                                                 {{p + ".proj_out.weight", 0, C}}}, nullptr, nullptr);
             const float* bias = concat_f32(p + ".kvqp.bias", {p + ".k.bias", p + ".v.bias", p + ".q.bias", p + ".proj_out.bias"});
@@ -553,8 +557,9 @@ struct DdpmBuilder : Builder {
         }
         // ---- conv_in
         Act h0 = new_act(ch, R, R, /*want_stats=*/true);  // conv_in writes its GroupNorm partials itself (one per 128-pixel tile)
-        if (a.in_channels != 3 || ch % 32 || ch > 256 || (R * R) % 128 || h0.stats_P != R * R / 128 || h0.stats_halo)
+        if (a.in_channels != 3 || ch % 32 || ch > 256 || (R * R) % 128 || h0.stats_P < R * R / 128 || h0.stats_halo)
             fail("DDPM conv_in: unsupported geometry");
+        h0.stats_P = R * R / 128;  // conv3x3_first_k publishes one partial per 128-pixel tile
         {
             const float* w = f32("conv_in.weight");
             const float* b = f32("conv_in.bias");

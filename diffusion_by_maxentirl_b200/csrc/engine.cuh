@@ -110,6 +110,7 @@ int build_train_plan(Net& net, Plan& plan);       // engine_train.cu (IGEBM valu
 int build_unet_train_plan(Net& net, Plan& plan);  // engine_train_unet.cu
 
 void set_gn_fused(int v);
+void set_stats16(int v);
 void set_attnblk(int v);
 const char* engine_last_error();
 void engine_set_error(const char* fmt, ...);

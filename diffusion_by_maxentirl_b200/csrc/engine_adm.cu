@@ -416,8 +416,9 @@ struct AdmBuilder : Builder {
             bf16* o = h.p;
             float* hst = h.stats;
             const int Cin = a.in_channels, Co = h.C;
-            if (Cin != 3 || Co % 32 || Co > 256 || (R * R) % 128 || h.stats_P != R * R / 128 || h.stats_halo)
+            if (Cin != 3 || Co % 32 || Co > 256 || (R * R) % 128 || h.stats_P < R * R / 128 || h.stats_halo)
                 fail("ADM input conv: unsupported geometry");
+            h.stats_P = R * R / 128;  // conv3x3_first_k publishes one partial per 128-pixel tile
             op([=](cudaStream_t st) {
                 conv3x3_first(pl->x, pl->x_scale, w, b, o, hst, Bn, Cin, R, R, Co, 0, st);
                 return (int)cudaGetLastError();

@@ -196,8 +196,32 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     }
 
     const int stat_seg = (STATS && !p.halo) ? p.stats_seg : 128;  // halo tiles: one partial per tile (tiles never span images)
+    const bool stat_direct = STATS && !p.halo && p.stats_seg == 16;
     const int stat_nseg = 128 / stat_seg, stat_bps = stat_seg >> 5;
     const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : (stat_seg == 32 ? 5 : 4));
+
+    // ---- phase A: 16 accumulator columns of this warp's 32 rows -> staging slot of chunk c
+    const uint32_t cnt0 = out_cnt;
+    auto phase_a = [&](int c) {
+        uint8_t* slot = cx.slot0 + ((cnt0 + c) & 1) * EPI_SLOT_BYTES;
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + (c * CH + cx.hsel * 16), v);
+        ptx::tmem_ld_wait();
+        if (c == nch - 1) {
+            // every accumulator column this warp stages is now in registers: hand the TMEM buffer back
+            ptx::tc_fence_before();
+            // (shared::cluster address: the CTA's own barrier, or the leader CTA's in a cta_group::2 pair)
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tmem_empty_addr) : "memory");
+        }
+        uint8_t* srow = slot + cx.stage_off;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(srow + (((cx.hsel * 4 + q) ^ cx.sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    };
+    // One barrier per chunk: chunk c+1 is staged (other slot) BEFORE chunk c is finished, so the TMEM-load latency of some warps
+    // overlaps the phase-B arithmetic of others; the barrier at the end of iteration c orders both "c+1 staged" and "slot of c free".
+    phase_a(0);
+    ptx::named_bar_sync(1, 256);
 
     auto do_chunk = [&](int c, auto slot_c) {
         constexpr int rs = decltype(slot_c)::value;  // residual prefetch slot of this chunk
@@ -205,24 +229,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         const int cc = col + cx.bu * 4;
         const bool col_ok = cc < n_total;
         uint8_t* slot = cx.slot0 + (out_cnt & 1) * EPI_SLOT_BYTES;
-
-        // ---- phase A: 16 accumulator columns of this warp's 32 rows -> staging
-        {
-            uint32_t v[16];
-            ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + (c * CH + cx.hsel * 16), v);
-            ptx::tmem_ld_wait();
-            if (c == nch - 1) {
-                // every accumulator column this warp stages is now in registers: hand the TMEM buffer back
-                ptx::tc_fence_before();
-                // (shared::cluster address: the CTA's own barrier, or the leader CTA's in a cta_group::2 pair)
-                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tmem_empty_addr) : "memory");
-            }
-            uint8_t* srow = slot + cx.stage_off;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(srow + (((cx.hsel * 4 + q) ^ cx.sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-        }
-        ptx::named_bar_sync(1, 256);
+        if (c + 1 < nch) phase_a(c + 1);
 
         // ---- phase B
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -312,6 +319,17 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
                 s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
             }
+        }
+        if (STATS && stat_direct) {
+            // 16-row segments: a segment is exactly the 16 rows of this warp - publish straight to global memory (no shared
+            // memory round trip, no second barrier; the consumer's finalize sums HW/16 partials per image in a fixed order)
+            const int srow = row0 + ((cx.ew & 3) * 2 + (cx.ew >> 2)) * 16;
+            if (cx.brs0 && col_ok && srow < p.M_total) {
+                float4* dst = reinterpret_cast<float4*>(p.stats + (static_cast<long long>(srow >> 4) * n_total + cc) * 2);
+                dst[0] = make_float4(s1[0], s2[0], s1[1], s2[1]);
+                dst[1] = make_float4(s1[2], s2[2], s1[3], s2[3]);
+            }
+        } else if (STATS) {
             if (cx.brs0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) cx.sst[cx.ew * 32 + cx.bu * 4 + j] = make_float2(s1[j], s2[j]);
@@ -344,6 +362,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             }
         }
         ++out_cnt;
+        ptx::named_bar_sync(1, 256);
     };
     if (RD == 4) {
 #pragma unroll 1

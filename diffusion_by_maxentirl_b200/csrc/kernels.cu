@@ -614,13 +614,15 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_fused_k(const bf16* __res
 // ---- finalize + apply: statistics -> per-(image, channel) affine (a, b), then a pure streaming pass  y = act(a*x + b)
 // st1 / st2 = [N][P1 | P2][C1 | C2][2] partial (sum, sumsq) from the producer GEMM epilogues. One CTA per image; every
 // reduction runs in a fixed order (deterministic).
-__global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restrict__ st1, int P1, int C1,
-                                                           const float* __restrict__ st2, int P2, int C2, int HW, int groups,
-                                                           float eps, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, const float* __restrict__ film,
-                                                           int film_ld, float2* __restrict__ ab, float2* __restrict__ mr) {
+static constexpr int GN_FIN_THREADS = 1024;
+__global__ void __launch_bounds__(GN_FIN_THREADS) gn_finalize_k(const float* __restrict__ st1, int P1, int C1,
+                                                               const float* __restrict__ st2, int P2, int C2, int HW, int groups,
+                                                               float eps, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ film,
+                                                               int film_ld, float2* __restrict__ ab, float2* __restrict__ mr) {
     __shared__ float s_mean[32], s_rstd[32];
     __shared__ float2 s_ch[2048];
+    __shared__ float2 s_part[2048];
     const int C = C1 + C2;
     const int n = blockIdx.x;
     const int cpg = C / groups;
@@ -628,14 +630,19 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restr
     // early therefore knows the producer GEMM has completed and may prefetch x before its own wait (gn_apply_ab_k)
     ptx::pdl_wait();
     ptx::pdl_trigger();
-    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    // per-channel totals over the P1 / P2 partials of this image (HW/16 per image with 16-row segments): `parts` thread
+    // groups split a channel's partial list, then a fixed-order combine - the order depends on (C, P) only, never on the batch
+    const int parts = C >= GN_FIN_THREADS ? 1 : GN_FIN_THREADS / C;
+    for (int idx = threadIdx.x; idx < C * parts; idx += GN_FIN_THREADS) {
+        const int c = idx % C, part = idx / C;
         const bool first = c < C1;
         const float* base = first ? st1 + ((long long)n * P1 * C1 + c) * 2 : st2 + ((long long)n * P2 * C2 + (c - C1)) * 2;
         const int P = first ? P1 : P2;
         const long long stride = (long long)(first ? C1 : C2) * 2;
         float s = 0.f, q = 0.f;
-        int seg = 0;
-        for (; seg + 4 <= P; seg += 4) {  // 4 independent loads in flight, summed in a fixed order
+        int seg = (int)((long long)part * P / parts);
+        const int seg_end = (int)((long long)(part + 1) * P / parts);
+        for (; seg + 4 <= seg_end; seg += 4) {  // 4 independent loads in flight, summed in a fixed order
             const float2 v0 = *reinterpret_cast<const float2*>(base + (seg + 0) * stride);
             const float2 v1 = *reinterpret_cast<const float2*>(base + (seg + 1) * stride);
             const float2 v2 = *reinterpret_cast<const float2*>(base + (seg + 2) * stride);
@@ -643,12 +650,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restr
             s += (v0.x + v1.x) + (v2.x + v3.x);
             q += (v0.y + v1.y) + (v2.y + v3.y);
         }
-        for (; seg < P; ++seg) {
+        for (; seg < seg_end; ++seg) {
             const float2 v = *reinterpret_cast<const float2*>(base + seg * stride);
             s += v.x;
             q += v.y;
         }
-        s_ch[c] = make_float2(s, q);
+        s_part[idx] = make_float2(s, q);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += GN_FIN_THREADS) {
+        float2 a = s_part[c];
+        for (int part = 1; part < parts; ++part) {
+            const float2 v = s_part[part * C + c];
+            a.x += v.x;
+            a.y += v.y;
+        }
+        s_ch[c] = a;
     }
     __syncthreads();
     {
@@ -675,7 +692,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_finalize_k(const float* __restr
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    for (int c = threadIdx.x; c < C; c += GN_FIN_THREADS) {
         const int g = c / cpg;
         float aa = s_rstd[g] * gamma[c];
         float bb = beta[c] - s_mean[g] * aa;
@@ -782,7 +799,7 @@ void gn_apply_fused(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int
 void gn_finalize_apply(const bf16* x1, int C1, int ld1, const bf16* x2, int C2, int ld2, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
                        const float* st1, int P1, const float* st2, int P2, float* ab_ws, bf16* out, cudaStream_t st, float* mr) {
-    launch_pdl(gn_finalize_k, dim3(N), dim3(GN_THREADS), st, st1, P1, C1, st2, P2, C2, HW, groups, eps, gamma, beta, film, film_ld,
+    launch_pdl(gn_finalize_k, dim3(N), dim3(GN_FIN_THREADS), st, st1, P1, C1, st2, P2, C2, HW, groups, eps, gamma, beta, film, film_ld,
                reinterpret_cast<float2*>(ab_ws), reinterpret_cast<float2*>(mr));
     const int slabs = gn_apply_slabs(N, HW, C1 + C2);
     dim3 grid(N, slabs);

@@ -108,6 +108,36 @@ int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma
 int dxmi_edm_rollout(dxmi_net_t net, const float* sched_host, const float* sigma_noise_dev, int T, const float* noise,
                      const int64_t* y, float* l_sample, float* mean, uint8_t* sample_u8, int B, dxmi_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------- trainer-side fused ops (8f rank 1) */
+/* DxMI_Trainer.get_running_cost (trainer.py:163-169): rc[n] = mean_CHW((next_state - state)^2) / (2 beta_next[n]); all fp32,
+ * beta_next [B] = betas_for_q gathered at n_timesteps - t - 1 by the caller. */
+int dxmi_running_cost_fwd(const float* state, const float* next_state, const float* beta_next, float* rc, int B, int chw,
+                          dxmi_stream_t stream);
+/* its backward: d_next_state = grad_rc[n] (next_state - state) / (beta_next[n] CHW), d_state = -that (either may be NULL) */
+int dxmi_running_cost_bwd(const float* state, const float* next_state, const float* beta_next, const float* grad_rc,
+                          float* d_next_state, float* d_state, int B, int chw, dxmi_stream_t stream);
+/* Multi-tensor optimizer step (torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step(), trainer.py:324-327 / :388-389,
+ * train_cifar10.py:283-296). One device table row per fp32 parameter tensor; the caller splits every tensor into chunks of
+ * dxmi_opt_chunk_elems() elements: chunk_tensor[k] = table row, chunk_first[k] = first element of chunk k in that tensor. */
+typedef struct dxmi_opt_tensor {
+    float* param;
+    float* grad;       /* NULL: tensor skipped (no gradient this step) */
+    float* exp_avg;
+    float* exp_avg_sq;
+    long long numel;
+    float lr;          /* per tensor: the two-LR parameter groups of train_cifar10.py:287-290 */
+    int reserved;
+} dxmi_opt_tensor;
+int dxmi_opt_chunk_elems(void);
+/* global L2 norm of all gradients -> norm_coef_out[0] = norm, [1] = min(1, max_norm / (norm + 1e-6)) (device, no host sync);
+ * partial_ws: n_chunks floats. scale_grads != 0 also multiplies the gradients in place like clip_grad_norm_ does. */
+int dxmi_opt_grad_norm(const dxmi_opt_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_first_dev, int n_chunks,
+                       float max_norm, float* partial_ws, float* norm_coef_out, int scale_grads, dxmi_stream_t stream);
+/* Adam (weight_decay 0, amsgrad off) on grad * coef, coef = norm_coef[1] (or 1 when NULL); step counts from 1 */
+int dxmi_opt_adam_step(const dxmi_opt_tensor* table_dev, const int* chunk_tensor_dev, const long long* chunk_first_dev, int n_chunks,
+                       const float* norm_coef_or_null, float beta1, float beta2, float eps, int step, int scale_grads_in_place,
+                       dxmi_stream_t stream);
+
 /* samples in [-1,1] -> uint8 ((x+1)*127.5 clamp), generate_large.py:43 */
 int dxmi_quantize_u8(const float* x, uint8_t* out, long long n, dxmi_stream_t stream);
 
