@@ -97,7 +97,7 @@ class ClockSampler:
 
 GF = {"cifar": (12.444, 1.613), "in64": (219.314, 6.454), "lsun": (2238.707, 0.0)}  # algorithmic GFLOP / image: U-Net forward, value net
 SHAPE = {"cifar": (3, 32, 32), "in64": (3, 64, 64), "lsun": (3, 256, 256)}
-DEFAULTS = {"cifar": (4, 256), "in64": (10, 64), "lsun": (4, 64)}  # (T, images per GPU per step)
+DEFAULTS = {"cifar": (4, 256), "in64": (10, 64), "lsun": (4, 64), "c4": (10, 128)}  # (T, images per GPU per step)
 
 
 def workload_name(wl, T, B):
@@ -515,13 +515,137 @@ def measure(wl, T, B, K, W, args, ctx, full):
     return res
 
 
+def measure_c4(B, K, W, args, ctx):
+    """BASELINE.json configs[3]: one DxMI training iteration of the CIFAR-10 DDPM T=10 configuration, batch B per GPU, under
+    DistributedDataParallel when N > 1 (trainer.py:230-408 / train_cifar10.py:141-205): rollout (eval, no grad) -> energy update of
+    the value net on cat(real, x_T) -> T TD updates of the value net -> sampler update (train mode, dropout 0.1, sample_step with
+    grad on B buffer rows; value term + running cost - entropy).  Clip-by-global-norm 0.1 + Adam run as the fused multi-tensor
+    kernels (train_ops.FusedAdam), the running cost as its fused forward / backward kernel.  Synthetic "real" images."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from common import DDPM_CFG, VALUE_CFG, load_synth_into
+    from diffusion_by_maxentirl_b200.models.DxMI.unet_small import Model
+    from diffusion_by_maxentirl_b200.models.DxMI.var_sampler import VARSampler
+    from diffusion_by_maxentirl_b200.models.modules import IGEBMEncoderV2
+    from diffusion_by_maxentirl_b200.models.value import TimeIndependentValue
+    from diffusion_by_maxentirl_b200.train_ops import FusedAdam, running_cost
+
+    rank, world, dev, lib = ctx["rank"], ctx["world"], ctx["dev"], ctx["lib"]
+    T = 10
+    net = Model(**DDPM_CFG)  # dropout 0.1 as in configs/cifar10/T10.yaml
+    sampler = VARSampler(net, n_timesteps=T, sample_shape=[3, 32, 32], trainable_beta="fix_last")
+    load_synth_into(net)
+    sampler.to(dev)
+    v = TimeIndependentValue(IGEBMEncoderV2(**VALUE_CFG))
+    load_synth_into(v, seed=1)
+    v.to(dev)
+    inner_net = net
+    if world > 1:
+        sampler.net = DDP(sampler.net, device_ids=[dev.index], output_device=dev.index)  # train_cifar10.py:303-309
+        v = DDP(v, device_ids=[dev.index], output_device=dev.index)
+    params_not_beta = [p for n_, p in inner_net.named_parameters() if "log_betas" not in n_]
+    opt_s = FusedAdam([{"params": [inner_net.log_betas], "lr": 1e-4}, {"params": params_not_beta, "lr": 1e-6}])  # train_cifar10.py:287-290
+    opt_v = FusedAdam(v.parameters(), lr=1e-5)
+    g = torch.Generator().manual_seed(77 + rank)
+    images = (torch.rand(B, 3, 32, 32, generator=g) * 2 - 1).to(dev)
+    betas_q = torch.linspace(1e-4, 2e-2, T).to(dev)
+    tau1, tau2 = 0.01, 0.1
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+
+    def iteration(timed):
+        if timed:
+            ev[0].record()
+        sampler.eval()
+        with torch.no_grad():
+            d = sampler.sample(B, device=dev)
+        if timed:
+            ev[1].record()
+        xs = torch.stack(d["l_sample"])  # [T+1, B, ...]
+        out = v(torch.cat([images, xs[-1]]), T)  # energy update (trainer.py:244-264)
+        pos, neg = out[:B], out[B:]
+        d_loss = pos.mean() - neg.mean() + 0.05 * ((pos ** 2).mean() + (neg ** 2).mean())
+        opt_v.zero_grad(set_to_none=True)
+        d_loss.backward()
+        opt_v.step()
+        if timed:
+            ev[2].record()
+        for i in range(T):  # T TD updates (trainer.py:276-326)
+            tt = T - 1 - i
+            state, nxt = xs[tt], xs[tt + 1]
+            tvec = torch.full((B,), tt, device=dev, dtype=torch.long)
+            with torch.no_grad():
+                rc = running_cost(state, nxt, betas_q[T - tvec - 1])
+                target = v(nxt, tt + 1).flatten() + tau2 * rc - tau1 * torch.log(d["sigma"][tt].flatten())
+            v_loss = F.mse_loss(v(state, tt).flatten(), target)
+            opt_v.zero_grad(set_to_none=True)
+            v_loss.backward()
+            opt_v.step(max_norm=0.1)
+        if timed:
+            ev[3].record()
+        sampler.train()  # sampler update (trainer.py:348-389)
+        idx_t = torch.randint(0, T, (B,), device=dev)
+        state = xs[idx_t, torch.arange(B, device=dev)]
+        ds = sampler.sample_step(state, idx_t)
+        nt = (idx_t < T - 1).float()
+        rc = running_cost(state, ds["sample"], betas_q[T - idx_t - 1])
+        for p_ in v.parameters():
+            p_.requires_grad_(False)
+        s_loss = (v(ds["sample"], idx_t + 1).flatten() + (tau2 * rc - tau1 * ds["entropy"].flatten()) * nt).mean()
+        for p_ in v.parameters():
+            p_.requires_grad_(True)
+        opt_s.zero_grad(set_to_none=True)
+        s_loss.backward()
+        opt_s.step(max_norm=0.1)
+        if timed:
+            ev[4].record()
+        return d_loss, v_loss, s_loss
+
+    l0 = lib.dxmi_launch_count()
+    iteration(False)
+    launches_per_iter = lib.dxmi_launch_count() - l0
+    for _ in range(max(W - 1, 1)):
+        iteration(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    acc = [0.0] * 4
+    for _ in range(K):
+        losses = iteration(True)
+        torch.cuda.synchronize()
+        for j in range(4):
+            acc[j] += ev[j].elapsed_time(ev[j + 1])
+    tot = torch.tensor([sum(acc)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms = float(tot.item()) / K
+    res = {"metric": "dxmi_training_images_per_sec", "value": world * B / ms * 1e3, "unit": UNIT, "steps": K, "warmup": W,
+           "ms_per_step": ms,
+           "phases_ms": {"rollout": acc[0] / K, "energy_update": acc[1] / K, "td_updates_x10": acc[2] / K, "sampler_update": acc[3] / K},
+           "model_tflops": 30.8 * B / 128 * world / ms * 1e3,  # SURVEY 3.3: 30.8 TFLOP per iteration per GPU at B = 128
+           "config": {"workload": f"CIFAR-10 DDPM T=10 DxMI training iteration (rollout + energy update + 10 TD updates + sampler update, "
+                                  f"dropout 0.1), batch {B}/GPU, bf16 tcgen05 forward + backward (BASELINE.json configs[3])",
+                      "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"ddp{world}",
+                      "collective": ("DDP gradient all-reduce (NCCL): 1 x 143 MB U-Net + 11 x 20.5 MB value net per iteration" if world > 1 else "none"),
+                      "launch": "eager (training lists are not graph-captured)", "optimizer": "train_ops.FusedAdam (clip 0.1 folded in)"},
+           "gpu_launches": int(launches_per_iter * K), "losses": [float(x) for x in losses]}
+    del sampler, v, net, opt_s, opt_v
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cifar", choices=["cifar", "in64", "lsun"],
+    ap.add_argument("--workload", default="cifar", choices=["cifar", "in64", "lsun", "c4"],
                     help="cifar = BASELINE configs[1] (driver default); in64 = configs[2] per-GPU shard (ImageNet-64 EDM T=10); "
                          "lsun = configs[4] per-GPU shard (LSUN-256 EDM T=4, sampler only)")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step")
@@ -571,6 +695,18 @@ def main():
     ctx = {"rank": rank, "local_rank": local_rank, "world": world, "dev": dev, "lib": lib,
            "flush": torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)}  # > 126 MB L2
 
+    if wl == "c4":  # the training configuration on its own (also part of `secondary` of the default run)
+        r = measure_c4(args.batch or 128, max(2, min(K, 5)), 3, args, ctx)
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+        if rank == 0:
+            r.update({"n_gpus": world, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
+            print(json.dumps(r), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     main_res = measure(wl, T, B, K, W, args, ctx, full=True)
 
     # ---------------------------------------------------------------- secondary: the north-star TARGET workloads
@@ -579,6 +715,10 @@ def main():
         for swl, sT, sB, sK in (("cifar", 10, 256, max(3, min(K, 8))), ("in64", 10, 64, max(3, min(K, 5)))):
             r = measure(swl, sT, sB, sK, 3, args, ctx, full=False)
             secondary.append(r)
+
+    c4 = None
+    if not args.no_secondary and wl == "cifar" and args.T is None and args.batch is None:
+        c4 = measure_c4(128, 3, 3, args, ctx)
 
     # ---------------------------------------------------------------- eager-CUDA bar + CPU baseline (rank 0, N = 1 only)
     eager = None
@@ -623,7 +763,8 @@ def main():
             "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": cfg(r), "e2e": e2e(r),
-            "gpu_launches": r["launches"] + sum(x["launches"] for x in secondary),
+            "gpu_launches": r["launches"] + sum(x["launches"] for x in secondary) + (c4["gpu_launches"] if c4 else 0),
+            "training_config": c4,
             "clocks": r["clocks"], "roofline": r["roofline"], "cpu_baseline": cpu, "eager_cuda_baseline": eager,
             "model_tflops": r["value"] * (T * gf_u + (gf_v if r["has_value"] else 0.0)) / 1e3,
             "shard_check": r["shard_check"],

@@ -121,7 +121,7 @@ SYMBOLS = {
     "dxmi_bind_grad": (_I, [_VP, C.c_char_p, _VP]),
     "dxmi_unet_forward_train": (_I, [_VP, _VP, _VP, _VP, _F, C.c_ulonglong, _I, _VP]),
     "dxmi_op_dropout_mask": (_I, [_VP, _LL, _F, C.c_ulonglong, C.c_uint, _VP]),
-    "dxmi_unet_backward": (_I, [_VP, _VP, _VP, _I, _VP]),
+    "dxmi_unet_backward": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_value_forward_train": (_I, [_VP, _VP, _VP, _I, _VP]),
     "dxmi_value_backward": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_op_gn_bwd_ws_floats": (_LL, [_I, _I, _I]),

@@ -460,7 +460,7 @@ int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, floa
     return r;
 }
 
-int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, int B, dxmi_stream_t stream) {
+int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, float* dx, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized) {
         set_err("dxmi_unet_backward: handle not finalized");
         return -1;
@@ -475,6 +475,7 @@ int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, int B,
     Plan* p = it->second.get();
     p->x = x;
     p->dout = dout;
+    p->dx = dx;
     int r = run_ops(p->bwd_ops, p->bwd_names, p->bwd_launches, (cudaStream_t)stream);
     p->fwd_valid = false;
     return r;

@@ -775,6 +775,38 @@ struct DdpmTrainBuilder : Builder {
                     conv_first_wgrad(dZ, pl->x, wsf, *g, Bn, R, R, ch, st);
                     return (int)cudaGetLastError();
                 }, 2);
+                {
+                    // gradient w.r.t. the input state x (only when the caller asks for it: backward through a whole rollout,
+                    // VARSampler.sample(enable_grad=True)): 3-row data-gradient GEMM of conv_in, fp32 NCHW output
+                    dxmi_gemm_desc d = conv_desc(R, R);
+                    set_src(d, 0, dZ, ch, ch);
+                    add_seg(d, 0, 9);
+                    d.b_ptr = packed_dgrad("conv_in", {"conv_in.weight"}, 3);
+                    d.b_rows = 3;
+                    d.b_ld = 9LL * ch;
+                    d.out = (void*)16;  // patched per call
+                    d.ldo = 3;
+                    d.out_fp32 = 1;
+                    d.out_nchw = 1;
+                    d.block_n = 32;
+                    if (!dry && !err) {
+                        GemmOp g2;
+                        int rr = prepare_gemm(d, &g2);
+                        if (rr) {
+                            err = rr;
+                            engine_set_error("prepare_gemm(dx): %s", gemm_op_last_error());
+                        } else if (g2.use_v2) {
+                            fail("internal: dx GEMM must use the direct-store kernel");
+                        } else {
+                            op([g2, pl](cudaStream_t st) {
+                                if (!pl->dx) return 0;
+                                GemmOp g3 = g2;
+                                g3.p.out = pl->dx;
+                                return run_gemm(g3, st);
+                            });
+                        }
+                    }
+                }
             }
         }
         // ---- time-embedding path: d_tproj [B, TP] -> temb_proj, dense.1, dense.0
@@ -792,14 +824,27 @@ struct DdpmTrainBuilder : Builder {
                 silu_f32(t1_, s_t1, (long long)Bn * tc, st);
                 return (int)cudaGetLastError();
             }, 2);
-            for (size_t i = 0; i < rb.size(); ++i) {
-                const int off = tp_offs[i], co = rb_cout[i];
-                const float* wtp = f32(rb[i] + ".temb_proj.weight");
-                float **gw = gslot(rb[i] + ".temb_proj.weight"), **gb = gslot(rb[i] + ".temb_proj.bias");
-                const int first = i == 0;
+            {
+                // every ResBlock's temb_proj backward in TWO launches (was 2 per block): the layers share their input swish(temb)
+                LinearStack base{};
+                std::vector<float**> gws, gbs;
+                if ((int)rb.size() > LinearStack::MAX) fail("too many ResBlocks for the stacked temb_proj backward");
+                base.n_layers = (int)rb.size();
+                for (size_t i = 0; i < rb.size() && i < (size_t)LinearStack::MAX; ++i) {
+                    base.off[i] = tp_offs[i];
+                    base.W[i] = f32(rb[i] + ".temb_proj.weight");
+                    gws.push_back(gslot(rb[i] + ".temb_proj.weight"));
+                    gbs.push_back(gslot(rb[i] + ".temb_proj.bias"));
+                }
+                base.off[base.n_layers] = tp;
                 op([=](cudaStream_t st) {
-                    linear_bwd_w(d_tproj + off, tp, s_temb, tc, 0, *gw, *gb, Bn, co, tc, st);
-                    linear_bwd_x(d_tproj + off, tp, wtp, d_st, tc, Bn, co, tc, first ? 0 : 1, st);
+                    LinearStack ls = base;
+                    for (int i = 0; i < ls.n_layers; ++i) {  // gradient destinations are bound per backward call
+                        ls.dW[i] = *gws[i];
+                        ls.db[i] = *gbs[i];
+                    }
+                    linear_stack_bwd_w(d_tproj, tp, s_temb, tc, ls, Bn, tc, st);
+                    linear_stack_bwd_x(d_tproj, tp, ls, d_st, tc, Bn, tc, st);
                     return (int)cudaGetLastError();
                 }, 2);
             }

@@ -697,6 +697,82 @@ void linear_bwd_x(const float* dy, int ld_dy, const float* W, float* dx, int ld_
     const long long total = (long long)N * K;
     linear_bwd_x_k<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dy, ld_dy, W, dx, ld_dx, N, O, K, accumulate);
 }
+// ---- the whole temb_proj stack in one launch each (24 tiny per-layer launches of ~60 us were 11 % of the U-Net training step)
+__global__ void __launch_bounds__(256) linear_stack_bwd_w_k(const float* __restrict__ dy, int ld_dy, const float* __restrict__ x, int ld_x,
+                                                            const __grid_constant__ LinearStack ls, int N, int K) {
+    // one CTA = 8 output rows (stacked row index) x 256 k; the 8 dy columns of a sample are broadcast loads
+    __shared__ float s_dy[8][128];
+    const int total = ls.off[ls.n_layers];
+    const int r0 = blockIdx.x * 8;
+    for (int n0 = 0; n0 < N; n0 += 128) {  // stage dy[n0 .. n0+127][r0 .. r0+7] (N <= 128 per pass)
+        __syncthreads();
+        for (int i = threadIdx.x; i < 8 * 128; i += 256) {
+            const int rr = i & 7, n = n0 + (i >> 3);
+            s_dy[rr][i >> 3] = (n < N && r0 + rr < total) ? dy[(long long)n * ld_dy + r0 + rr] : 0.f;
+        }
+        __syncthreads();
+        for (int k = blockIdx.y * 256 + threadIdx.x; k < K; k += gridDim.y * 256) {
+            float acc[8], bs[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) acc[rr] = bs[rr] = 0.f;
+            const int nn = N - n0 < 128 ? N - n0 : 128;
+            for (int n = 0; n < nn; ++n) {
+                const float xv = x[(long long)(n0 + n) * ld_x + k];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    acc[rr] = fmaf(s_dy[rr][n], xv, acc[rr]);
+                    bs[rr] += s_dy[rr][n];
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const int r = r0 + rr;
+                if (r >= total) break;
+                int l = 0;
+                while (r >= ls.off[l + 1]) ++l;
+                const int o = r - ls.off[l];
+                if (ls.dW[l]) {
+                    float* d = ls.dW[l] + (long long)o * K + k;
+                    *d = n0 == 0 ? acc[rr] : *d + acc[rr];
+                }
+                if (ls.db[l] && k == 0) ls.db[l][o] = n0 == 0 ? bs[rr] : ls.db[l][o] + bs[rr];
+            }
+        }
+    }
+}
+void linear_stack_bwd_w(const float* dy, int ld_dy, const float* x, int ld_x, const LinearStack& ls, int N, int K, cudaStream_t st) {
+    const int total = ls.off[ls.n_layers];
+    dim3 grid((total + 7) / 8, (K + 255) / 256);
+    linear_stack_bwd_w_k<<<grid, 256, 0, st>>>(dy, ld_dy, x, ld_x, ls, N, K);
+}
+// dx[n, k] = sum over stacked rows r of dy[n, r] * W_l(r)[o(r), k]; grid (N, K / 256), the row loop unrolled by 4
+__global__ void __launch_bounds__(256) linear_stack_bwd_x_k(const float* __restrict__ dy, int ld_dy, const __grid_constant__ LinearStack ls,
+                                                            float* __restrict__ dx, int ld_dx, int K) {
+    const int n = blockIdx.x;
+    const int k = blockIdx.y * 256 + threadIdx.x;
+    if (k >= K) return;
+    const float* dyn = dy + (long long)n * ld_dy;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int l = 0; l < ls.n_layers; ++l) {
+        const float* W = ls.W[l] + k;
+        const float* g = dyn + ls.off[l];
+        const int O = ls.off[l + 1] - ls.off[l];
+        int o = 0;
+        for (; o + 4 <= O; o += 4) {
+            a0 = fmaf(g[o], W[(long long)o * K], a0);
+            a1 = fmaf(g[o + 1], W[(long long)(o + 1) * K], a1);
+            a2 = fmaf(g[o + 2], W[(long long)(o + 2) * K], a2);
+            a3 = fmaf(g[o + 3], W[(long long)(o + 3) * K], a3);
+        }
+        for (; o < O; ++o) a0 = fmaf(g[o], W[(long long)o * K], a0);
+    }
+    dx[(long long)n * ld_dx + k] = (a0 + a1) + (a2 + a3);
+}
+void linear_stack_bwd_x(const float* dy, int ld_dy, const LinearStack& ls, float* dx, int ld_dx, int N, int K, cudaStream_t st) {
+    dim3 grid(N, (K + 255) / 256);
+    linear_stack_bwd_x_k<<<grid, 256, 0, st>>>(dy, ld_dy, ls, dx, ld_dx, K);
+}
+
 __global__ void silu_bwd_mul_k(float* __restrict__ d, const float* __restrict__ x, long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -55,6 +55,19 @@ void colsum_per_image(const bf16* x, int N, int HW, int C, float* out, int ld_ou
 void linear_bwd_w(const float* dy, int ld_dy, const float* x, int ld_x, int act_x, float* dW, float* db, int N, int O, int K, cudaStream_t st);
 // dx[n,k] (+)= sum_o dy[n,o] * W[o,k]
 void linear_bwd_x(const float* dy, int ld_dy, const float* W, float* dx, int ld_dx, int N, int O, int K, int accumulate, cudaStream_t st);
+// Backward of a ROW-STACK of Linear layers that share one input x [N, K] (every ResBlock's temb_proj, unet_small.py:123): dy [N, ld_dy]
+// holds the layers' output gradients side by side (layer l: columns off[l] .. off[l] + O[l]).  One launch each for all layers:
+//   dW_l = dy_l^T x,  db_l = column sums of dy_l      (separate destination tensors)       and      dx = sum_l dy_l W_l
+struct LinearStack {
+    static constexpr int MAX = 32;
+    int n_layers;
+    int off[MAX + 1];        // column offsets, off[n_layers] = total columns
+    float* dW[MAX];          // [O_l, K] fp32 or null
+    float* db[MAX];          // [O_l] or null
+    const float* W[MAX];     // [O_l, K] fp32
+};
+void linear_stack_bwd_w(const float* dy, int ld_dy, const float* x, int ld_x, const LinearStack& ls, int N, int K, cudaStream_t st);
+void linear_stack_bwd_x(const float* dy, int ld_dy, const LinearStack& ls, float* dx, int ld_dx, int N, int K, cudaStream_t st);
 // d[i] *= silu'(x[i])
 void silu_bwd_mul(float* d, const float* x, long long n, cudaStream_t st);
 // conv_out (C -> 3, 3x3) backward helpers: w_t[c][o][tap] = w[o][c][8-tap] (fp32, feeds conv3x3_first as a 3 -> C convolution);

@@ -8,10 +8,13 @@ from diffusion_by_maxentirl_b200.native import NativeNet
 class _UNetFunction(torch.autograd.Function):
     """eps = net(x, t) under autograd on the B200 path (trainer.py:348-389, update_sampler): forward keeps the activations in
     the handle's training plan (dxmi_unet_forward_train), backward is one dxmi_unet_backward call that writes every parameter
-    gradient.  The state x is not differentiated (the sampler update detaches it)."""
+    gradient and, when x requires grad (backward through a rollout), the gradient w.r.t. the input state."""
 
     @staticmethod
-    def forward(ctx, module, x, t, *params):
+    def forward(ctx, module, x, t, recompute, *params):
+        """recompute=False: the training plan keeps this forward's activations for ONE pending backward (update_sampler).
+        recompute=True (activation checkpointing, used by VARSampler.sample(enable_grad=True) where T forwards are pending at
+        once): only (x, t, dropout seed) are kept and the backward re-runs the training forward right before it walks the tape."""
         h = module._ensure_handle(x.device)
         B = x.shape[0]
         xc = x.detach().contiguous().float()
@@ -19,24 +22,37 @@ class _UNetFunction(torch.autograd.Function):
         out = torch.empty(B, module.out_ch, module.resolution, module.resolution, device=x.device)
         # training-mode dropout: a fresh seed per forward from torch's CPU generator (reproducible under torch.manual_seed); the
         # masks are counter-based functions of (seed, block, element) and are regenerated in the backward
-        seed = int(torch.randint(0, 2**62, (1,)).item()) if module.dropout_p > 0 else 0
+        p_drop = float(module.dropout_p) if module.training else 0.0
+        seed = int(torch.randint(0, 2**62, (1,)).item()) if p_drop > 0 else 0
         module._last_dropout_seed = seed
-        L.check(L.lib().dxmi_unet_forward_train(h, L.ptr(xc), L.ptr(tc), L.ptr(out), float(module.dropout_p), seed, B,
-                                                L.stream_ptr(xc)), "dxmi_unet_forward_train")
-        ctx.module, ctx.B, ctx.x = module, B, xc
-        ctx.token = module._train_token = object()
+        if recompute and p_drop == 0.0:
+            L.check(L.lib().dxmi_unet_forward(h, L.ptr(xc), None, L.ptr(tc), None, L.ptr(out), B, L.stream_ptr(xc)), "dxmi_unet_forward")
+        else:
+            L.check(L.lib().dxmi_unet_forward_train(h, L.ptr(xc), L.ptr(tc), L.ptr(out), p_drop, seed, B, L.stream_ptr(xc)),
+                    "dxmi_unet_forward_train")
+        ctx.module, ctx.B, ctx.x, ctx.t = module, B, xc, tc
+        ctx.recompute, ctx.p_drop, ctx.seed = bool(recompute), p_drop, seed
+        ctx.token = None
+        if not recompute:
+            ctx.token = module._train_token = object()
         ctx.need_param = [p.requires_grad for p in params]
+        ctx.need_dx = x.requires_grad
         return out
 
     @staticmethod
     def backward(ctx, dout):
         m = ctx.module
-        if m._train_token is not ctx.token:
+        h = m._ensure_handle(ctx.x.device)
+        lib = L.lib()
+        if ctx.recompute:
+            scratch = torch.empty(ctx.B, m.out_ch, m.resolution, m.resolution, device=ctx.x.device)
+            L.check(lib.dxmi_unet_forward_train(h, L.ptr(ctx.x), L.ptr(ctx.t), L.ptr(scratch), ctx.p_drop, ctx.seed, ctx.B,
+                                                L.stream_ptr(ctx.x)), "dxmi_unet_forward_train (recompute)")
+            m._train_token = None
+        elif m._train_token is not ctx.token:
             raise RuntimeError(
                 "B200 U-Net: backward() of a forward whose saved activations were overwritten by a later grad-enabled forward at "
                 "the same batch size (the plan keeps one set per batch size; run forward/backward pairs in order)")
-        h = m._ensure_handle(ctx.x.device)
-        lib = L.lib()
         keys = m._keys
         sizes = [m._param(k).numel() for k in keys]
         flat = torch.empty(sum(sizes), dtype=torch.float32, device=ctx.x.device)
@@ -47,11 +63,12 @@ class _UNetFunction(torch.autograd.Function):
             L.check(lib.dxmi_bind_grad(h, k.encode(), L.ptr(g) if need else None), f"bind_grad {k}")
             grads.append(g.view(m._param(k).shape) if need else None)
         d = dout.detach().contiguous().float()
-        L.check(lib.dxmi_unet_backward(h, L.ptr(ctx.x), L.ptr(d), ctx.B, L.stream_ptr(ctx.x)), "dxmi_unet_backward")
+        dx = torch.empty_like(ctx.x) if ctx.need_dx else None
+        L.check(lib.dxmi_unet_backward(h, L.ptr(ctx.x), L.ptr(d), L.ptr(dx), ctx.B, L.stream_ptr(ctx.x)), "dxmi_unet_backward")
         m._train_token = None
         for k in keys:
             lib.dxmi_bind_grad(h, k.encode(), None)
-        return (None, None, None, *grads)
+        return (None, dx, None, None, *grads)
 
 
 class Model(NativeNet):
@@ -119,13 +136,12 @@ class Model(NativeNet):
     def forward(self, x, t):
         assert x.shape[2] == x.shape[3] == self.resolution
         assert t.dim() == 1 and t.shape[0] == x.shape[0]
-        if self.training and torch.is_grad_enabled():
-            # update_sampler (trainer.py:348-389): backward through the U-Net
-            if x.requires_grad:
-                raise NotImplementedError("B200 U-Net training path: the gradient w.r.t. the input state is not built")
+        ckpt = getattr(self, "_checkpoint_activations", False)
+        if torch.is_grad_enabled() and (self.training or ckpt):
+            # update_sampler (trainer.py:348-389): backward through the U-Net; sample(enable_grad=True): through a whole rollout
             if self.precision != "bf16":
                 raise RuntimeError("B200 U-Net training path runs in bf16 mode only")
-            return _UNetFunction.apply(self, x, t, *[self._param(k) for k in self._keys])
+            return _UNetFunction.apply(self, x, t, ckpt, *[self._param(k) for k in self._keys])
         self._check_eval()
         h = self._ensure_handle(x.device)
         x = x.detach().contiguous().float()

@@ -64,11 +64,11 @@ class VARSampler(nn.Module):
         `u8_out` (optional, not in the reference): a uint8 [B, C, H, W] CUDA tensor that the last transition kernel fills with
         the quantised samples (the callers' `((x + 1) * 127.5).clamp(0, 255).to(uint8)`, generate_cifar10.py:205-209);
         also returned as d["sample_u8"]."""
-        if enable_grad:
-            raise NotImplementedError("enable_grad=True (backward through the rollout) is not built on the B200 path")
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("VARSampler.sample runs on CUDA only (no CPU fallback)")
+        if enable_grad:
+            return self._sample_with_grad(int(n_sample), device, noise)
         T, B = self.n_timesteps, int(n_sample)
         shape = tuple(self.sample_shape)
         net = _inner(self.net)
@@ -104,6 +104,36 @@ class VARSampler(nn.Module):
             "sigma": [sig_dev[i].repeat(B)[:, None, None, None] for i in range(T)],
             "control": [control[i] for i in range(T)],
         }
+
+    def _sample_with_grad(self, B, device, noise):
+        """Reference VARSampler.sample(enable_grad=True) (var_sampler.py:249, :411-416; train_cifar10.py:186): the rollout keeps its
+        autograd graph - through the U-Net parameters, log_betas and the states.  T U-Net forwards are pending at once, so each is
+        activation-checkpointed: its backward re-runs the training forward of that step before walking the tape."""
+        T, shape = self.n_timesteps, tuple(self.sample_shape)
+        if noise is None:
+            nz = [torch.randn(B, *shape, device=device) for _ in range(T + 1)]
+        else:
+            nz = list(noise) if not torch.is_tensor(noise) else [noise[i] for i in range(T + 1)]
+            nz = [z.to(device=device, dtype=torch.float32) for z in nz]
+        net = _inner(self.net)
+        x = nz[0]
+        l_sample, l_mean, l_logp, l_sigma, l_control = [x], [], [], [], []
+        net._checkpoint_activations = True
+        try:
+            with torch.enable_grad():
+                for i in range(T):
+                    t = torch.full((B,), i, dtype=torch.long, device=device)
+                    d = self._sample_step_autograd(x, t, nz[i + 1])
+                    x = d["sample"]
+                    l_sample.append(x)
+                    l_mean.append(d["mean"])
+                    l_logp.append(d["logp"])
+                    l_sigma.append(d["sigma"])
+                    l_control.append(d["control"])
+        finally:
+            net._checkpoint_activations = False
+        return {"sample": x, "l_sample": l_sample, "logp": l_logp, "logp_terminal": torch.zeros(B, device=device), "mean": l_mean,
+                "sigma": l_sigma, "control": l_control}
 
     def _sample_step_autograd(self, x, t, noise):
         """Training form of sample_step (trainer.py:357-389 differentiates it w.r.t. the U-Net parameters and log_betas): eps

@@ -221,7 +221,8 @@ int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, floa
  * forward tape: conv_in = 0, then blocks / attention / resampling in execution order) applies for (p, seed) - lets a reference
  * implementation replay the exact dropout pattern (tests). */
 int dxmi_op_dropout_mask(void* mask_bf16, long long n, float p, unsigned long long seed, unsigned stream_id, dxmi_stream_t stream);
-int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, int B, dxmi_stream_t stream);
+int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, float* dx /* [B,Cin,H,W] fp32 gradient w.r.t. the input state, or NULL */,
+                       int B, dxmi_stream_t stream);
 
 /* ---- backward operators (the training step differentiates through the value net, trainer.py:252-264,
  * :320-326, :369-389) ---- */

@@ -323,3 +323,117 @@ def test_sampler_update_step_like_the_trainer():
     print(f"log_betas grad rel-L2 {e_lb:.2e}")
     assert e_lb < 5e-2
     assert torch.isfinite(net.log_betas).all() and float(gn) > 0
+
+
+def test_unet_input_state_gradient():
+    """d eps / d x (needed to differentiate through a rollout): conv_in's data gradient, vs fp32 CPU autograd over the oracle."""
+    from oracle import nets
+
+    net, sampler, sd = _build_ddpm_train()
+    net.train()
+    B = 3
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([500.1, 120.0, 3.0])
+    coef = torch.randn(B, 3, 32, 32, generator=g)
+    xg = x.cuda().requires_grad_(True)
+    out = net(xg, t.cuda())
+    (out * coef.cuda()).sum().backward()
+    rsd = {k: v.clone() for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    (nets.ddpm_unet_forward(rsd, xr, t) * coef).sum().backward()
+    e = rel_l2(xg.grad, xr.grad)
+    cos = torch.nn.functional.cosine_similarity(xg.grad.flatten().cpu(), xr.grad.flatten(), dim=0).item()
+    print(f"input-state gradient rel-L2 {e:.2e}, cosine {cos:.5f}")
+    assert e < 5e-2 and cos > 0.998
+
+
+def test_sample_enable_grad_backward_through_rollout():
+    """VARSampler.sample(enable_grad=True) (reference var_sampler.py:249, :411-416; train_cifar10.py:186): a T = 3 rollout that keeps
+    its graph; gradients of a functional of the final sample w.r.t. x_0, log_betas and U-Net parameters vs the oracle rollout
+    under fp32 CPU autograd.  T forwards are pending at once: each is activation-checkpointed (recomputed in its backward)."""
+    from oracle import nets, samplers
+
+    T, B = 3, 2
+    net, sampler, sd = _build_ddpm_train(T)
+    sampler.eval()
+    g = torch.Generator().manual_seed(41)
+    noise = [torch.randn(B, 3, 32, 32, generator=g) for _ in range(T + 1)]
+    coef = torch.randn(B, 3, 32, 32, generator=g)
+    nz = [z.cuda() for z in noise]
+    nz[0].requires_grad_(True)
+    d = sampler.sample(B, device="cuda", enable_grad=True, noise=nz)
+    assert d["sample"].requires_grad and len(d["l_sample"]) == T + 1 and d["sigma"][0].shape == (B, 1, 1, 1)
+    loss = (d["sample"] * coef.cuda()).sum() + sum(lp.sum() for lp in d["logp"])
+    loss.backward()
+    # oracle
+    rsd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rn = [z.clone() for z in noise]
+    rn[0].requires_grad_(True)
+    # the reference's VAR_sampling under enable_grad (var_sampler.py:249-295): the state carries its graph from step to step,
+    # log_prob is evaluated at the DETACHED next state (a REINFORCE-style term: d logp / d mean = (x' - mean) / sigma^2)
+    sched = samplers.var_schedule(T)
+    sig = samplers.var_sigmas(rsd["log_betas"], sched["std"], "fix_last")
+    xr, rlogp = rn[0], []
+    for i in range(T):
+        eps_r = nets.ddpm_unet_forward(rsd, xr, sched["continuous_steps"][i] * torch.ones(B))
+        mean_r = xr * sched["x_prev_multiplier"][i] + sched["theta_multiplier"][i] * eps_r
+        xr = mean_r + sig[i] * rn[i + 1]
+        rlogp.append(torch.distributions.Normal(mean_r, sig[i]).log_prob(xr.detach().clone()).mean(-1).mean(-1).mean(-1))
+    rloss = (xr * coef).sum() + sum(lp.sum() for lp in rlogp)
+    rloss.backward()
+    print(f"rollout loss {loss.item():.5f} vs oracle {rloss.item():.5f}")
+    assert abs(loss.item() - rloss.item()) < 2e-2 * max(1.0, abs(rloss.item()))
+    e_x0 = rel_l2(nz[0].grad, rn[0].grad)
+    e_lb = rel_l2(net.log_betas.grad[:-1], rsd["log_betas"].grad[:-1])  # the last sigma is the fixed std (fix_last)
+    keys = ["conv_out.weight", "mid.block_1.conv1.weight", "down.0.block.0.conv1.weight", "temb.dense.0.weight", "up.1.attn.0.q.weight"]
+    errs = {k: rel_l2(net._param(k).grad, rsd[k].grad) for k in keys}
+    print(f"d/dx0 {e_x0:.2e}, d/dlog_betas {e_lb:.2e}, params", {k: "%.2e" % v for k, v in errs.items()})
+    assert e_x0 < 6e-2 and e_lb < 5e-2 and max(errs.values()) < 6e-2
+    # a second call still works (token / checkpoint state is reset) and the plain no-grad path is unaffected
+    d2 = sampler.sample(B, device="cuda", noise=torch.stack([z.detach() for z in nz]))
+    assert not d2["sample"].requires_grad and rel_l2(d2["sample"], d["sample"].detach()) < 1e-2
+
+
+def test_value_guided_sampling_end_to_end():
+    """DxMI_Trainer.sample_guidance (reference trainer.py:171-216, generate_cifar10.py:182-202) restated over the drop-in modules:
+    per step sample_step without grad, then x <- x' + scale * sigma * grad_x v(x', t+1).  Against the same loop over the CPU oracle."""
+    from oracle import nets, samplers
+    from diffusion_by_maxentirl_b200.models.modules import process_single_t
+
+    T, B, scale = 4, 3, 0.7
+    from common import build_ddpm
+
+    net, sampler, value, sd, vsd = build_ddpm(T)
+    g = torch.Generator().manual_seed(51)
+    x0 = torch.randn(B, 3, 32, 32, generator=g)
+    zs = [torch.randn(B, 3, 32, 32, generator=g) for _ in range(T)]
+
+    def guided(sample_step, vfn, dev):
+        x = x0.to(dev)
+        l_x, l_g = [x.clone()], []
+        for t in range(T):
+            tt = process_single_t(x, t)
+            with torch.no_grad():
+                d_step = sample_step(x, tt, zs[t].to(dev))
+            nx = d_step["sample"].detach().requires_grad_(True)
+            with torch.enable_grad():
+                grad = torch.autograd.grad(vfn(nx, tt + 1).squeeze().sum(), nx)[0]
+            guidance = grad * scale * d_step["sigma"]
+            x = (nx + guidance).detach()
+            l_x.append(x.clone())
+            l_g.append(guidance.detach())
+        return l_x, l_g
+
+    value.eval()
+    lx, lg = guided(lambda x, tt, z: sampler.sample_step(x, tt, noise=z), lambda x, t: value(x, t), "cuda")
+    sched = samplers.var_schedule(T)
+    rx, rg = guided(lambda x, tt, z: samplers.var_sample_step(lambda a, b: nets.ddpm_unet_forward(sd, a, b), sched, sd["log_betas"], x, tt, z),
+                    lambda x, t: nets.value_forward(vsd, x), "cpu")
+    ex = [rel_l2(a, b) for a, b in zip(lx, rx)]
+    eg = [rel_l2(a, b) for a, b in zip(lg, rg)]
+    print("guided x_t rel-L2:", ["%.2e" % v for v in ex], "guidance rel-L2:", ["%.2e" % v for v in eg])
+    assert max(ex) < 2e-2
+    # the guidance itself is the value net's input gradient (ill-conditioned in bf16, DESIGN section 4): direction must agree
+    for a, b in zip(lg, rg):
+        assert torch.nn.functional.cosine_similarity(a.flatten().cpu(), b.flatten(), dim=0).item() > 0.98
