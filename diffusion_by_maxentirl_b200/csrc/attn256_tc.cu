@@ -208,11 +208,11 @@ int prepare_attn256(const void* qk, const void* vt, void* out, int ldo, int B, f
 }
 
 int run_attn256(const Attn256Op& op, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaError_t e = cudaFuncSetAttribute(attn256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     attn256_kernel<<<op.grid, A2_THREADS, A2_SMEM, st>>>(op.p);
     return (int)cudaGetLastError();

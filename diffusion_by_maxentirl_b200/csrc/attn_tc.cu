@@ -259,14 +259,14 @@ int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const 
 }
 
 int run_attn(const AttnOp& op, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
         if (e != cudaSuccess) {
             snprintf(g_attn_err, sizeof g_attn_err, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
             return (int)e;
         }
-        configured = true;
+        configured.set();
     }
     attn_fwd_kernel<<<op.grid, ATT_THREADS, ATT_SMEM, st>>>(op.p);
     cudaError_t e = cudaGetLastError();

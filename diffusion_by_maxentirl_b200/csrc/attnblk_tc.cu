@@ -535,11 +535,11 @@ int prepare_attnblk256(const void* x, const void* w_kvqp, const float* bias_kvqp
 }
 
 int run_attnblk256(const AttnBlkOp& op, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaError_t e = cudaFuncSetAttribute(attnblk256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.set();
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * op.B);

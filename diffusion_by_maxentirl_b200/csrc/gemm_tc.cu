@@ -398,15 +398,15 @@ void gemm_set_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg);
 template <int BLOCK_N>
 static int launch_t(const ConvGemmParams& p, int m_tiles, int n_tiles, int batch, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaError_t e =
             cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             snprintf(g_err, sizeof g_err, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
         }
-        configured = true;
+        configured.set();
     }
     dim3 grid(m_tiles, n_tiles, batch);
     conv_gemm_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(p);

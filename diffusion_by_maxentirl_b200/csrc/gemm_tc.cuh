@@ -19,6 +19,23 @@
 
 namespace dxmi {
 
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a "configured once per process" flag breaks a network living on
+// cuda:1 while cuda:0 was configured first.  Usage: static DevFlags configured; if (!configured.test_and_set()) { set attribute }
+struct DevFlags {
+    bool done[64] = {};
+    bool test() const {
+        int d = 0;
+        cudaGetDevice(&d);
+        return done[d & 63];
+    }
+    void set() {
+        int d = 0;
+        cudaGetDevice(&d);
+        done[d & 63] = true;
+    }
+};
+
 // option "pdl": launch the hot kernels with programmatic stream serialization (see ptx.cuh); read at launch time
 int pdl_enabled();
 void set_pdl(int v);

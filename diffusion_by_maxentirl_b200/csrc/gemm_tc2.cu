@@ -159,24 +159,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                 const int n0 = p.a_batched ? batch : n_blk * p.bn;
                 const int bcoord_n = n_tile * BLOCK_N;
                 const int bcoord_b = p.b_batched ? batch : 0;
-                int kk = 0;
+                int kbase = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const GemmSeg sg = p.seg[s];
                     const CUtensorMap* amap = &p.a_map[sg.map];
-                    for (int tap = 0; tap < sg.ntaps; ++tap) {
-                        const int r = (sg.ntaps == 9) ? tap / 3 : 0;
-                        const int q = (sg.ntaps == 9) ? tap - 3 * r : 0;
-                        for (int ch = 0; ch < sg.nchunks; ++ch, ++it, ++kk) {
-                            const uint32_t stage = it % STAGES;
-                            const uint32_t ph = (it / STAGES) & 1;
-                            ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
-                            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                            uint8_t* sb = sa + A_STAGE_BYTES;
-                            ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                            ptx::tma_load_4d(sa, amap, &full_bar[stage], ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
-                            ptx::tma_load_3d(sb, &p.b_map, &full_bar[stage], kk * TILE_K, bcoord_n, bcoord_b);
+                    // K order of a 3x3 segment: channel chunk, then column shift q, then row shift r - the SAME order as the pair
+                    // kernel's shift-3 mode, so every kernel variant accumulates identically (bitwise batch invariance: which
+                    // variant runs depends on the batch size)
+                    const int nq = sg.ntaps == 9 ? 3 : 1;
+                    for (int ch = 0; ch < sg.nchunks; ++ch) {
+                        for (int q = 0; q < nq; ++q) {
+                            for (int r = 0; r < nq; ++r, ++it) {
+                                const int kk = kbase + (r * 3 + q) * sg.nchunks + ch;
+                                const uint32_t stage = it % STAGES;
+                                const uint32_t ph = (it / STAGES) & 1;
+                                ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+                                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                                uint8_t* sb = sa + A_STAGE_BYTES;
+                                ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                                ptx::tma_load_4d(sa, amap, &full_bar[stage], ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
+                                ptx::tma_load_3d(sb, &p.b_map, &full_bar[stage], kk * TILE_K, bcoord_n, bcoord_b);
+                            }
                         }
                     }
+                    kbase += sg.ntaps * sg.nchunks;
                 }
             }
         }
@@ -371,9 +377,9 @@ bool conv_gemm_v2_supported(const ConvGemmParams& p, int block_n) {
 template <int BLOCK_N>
 static int launch2_t(const ConvGemmParams& p, cudaStream_t stream) {
     using Cfg = Cfg2<BLOCK_N>;
-    static bool configured = false;
+    static DevFlags configured;
     static int num_sms = 0;
-    if (!configured) {
+    if (!configured.test()) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             gemm_set_error(cudaGetErrorString(e));
@@ -382,7 +388,7 @@ static int launch2_t(const ConvGemmParams& p, cudaStream_t stream) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        configured.set();
     }
     const int total = p.m_tiles * p.n_tiles * p.batch_count;
     const int grid = total < num_sms ? total : num_sms;

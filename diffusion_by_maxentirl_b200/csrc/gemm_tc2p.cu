@@ -163,9 +163,18 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 } else {
                     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(rb_leader) : "memory");
                 }
-                for (int kk = 0; kk < k_iters; ++kk)
-                    tma2_load_3d(smem + Cfg::SM_RESB + kk * Cfg::B_STAGE_BYTES, &p.b_map, rb_leader, kk * TILE_K,
-                                 (int)rank * (BLOCK_N / 2), 0);
+                // resident slot j holds the K slice the j-th stage of a tile consumes (chunk, column shift, row shift order)
+                int j = 0, kb = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const GemmSeg sg = p.seg[s];
+                    const int nq = sg.ntaps == 9 ? 3 : 1;
+                    for (int ch = 0; ch < sg.nchunks; ++ch)
+                        for (int q = 0; q < nq; ++q)
+                            for (int r = 0; r < nq; ++r, ++j)
+                                tma2_load_3d(smem + Cfg::SM_RESB + j * Cfg::B_STAGE_BYTES, &p.b_map, rb_leader,
+                                             (kb + (r * 3 + q) * sg.nchunks + ch) * TILE_K, (int)rank * (BLOCK_N / 2), 0);
+                    kb += sg.ntaps * sg.nchunks;
+                }
             }
             for (int tp = cluster_id; tp < total_pairs; tp += n_clusters) {
                 const int n_tile = tp % p.n_tiles;
@@ -232,25 +241,29 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 for (int s = 0; s < p.nseg; ++s) {
                     const GemmSeg sg = p.seg[s];
                     const CUtensorMap* amap = &p.a_map[sg.map];
-                    for (int tap = 0; tap < sg.ntaps; ++tap) {
-                        const int r = (sg.ntaps == 9) ? tap / 3 : 0;
-                        const int q = (sg.ntaps == 9) ? tap - 3 * r : 0;
-                        for (int ch = 0; ch < sg.nchunks; ++ch, ++it, ++kk) {
-                            const uint32_t stage = it % STAGES;
-                            const uint32_t ph = (it / STAGES) & 1;
-                            ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
-                            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                            uint8_t* sb = sa + A_STAGE_BYTES;
-                            const uint32_t full_leader = mapa(ptx::smem_u32(&full_bar[stage]), 0);
-                            if (rank == 0) {
-                                ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                            } else {
-                                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
+                    // K order of a 3x3 segment: chunk, column shift q, row shift r (same as the shift-3 mode above and as gemm_tc2.cu)
+                    const int nq = sg.ntaps == 9 ? 3 : 1;
+                    for (int ch = 0; ch < sg.nchunks; ++ch) {
+                        for (int q = 0; q < nq; ++q) {
+                            for (int r = 0; r < nq; ++r, ++it) {
+                                const int kx = kk + (r * 3 + q) * sg.nchunks + ch;
+                                const uint32_t stage = it % STAGES;
+                                const uint32_t ph = (it / STAGES) & 1;
+                                ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
+                                uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                                uint8_t* sb = sa + A_STAGE_BYTES;
+                                const uint32_t full_leader = mapa(ptx::smem_u32(&full_bar[stage]), 0);
+                                if (rank == 0) {
+                                    ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                                } else {
+                                    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
+                                }
+                                tma2_load_4d(sa, amap, full_leader, ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
+                                if (!RESB) tma2_load_3d(sb, &p.b_map, full_leader, kx * TILE_K, bcoord_n, bcoord_b);
                             }
-                            tma2_load_4d(sa, amap, full_leader, ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
-                            if (!RESB) tma2_load_3d(sb, &p.b_map, full_leader, kk * TILE_K, bcoord_n, bcoord_b);
                         }
                     }
+                    kk += sg.ntaps * sg.nchunks;
                 }
             }
         }
@@ -408,9 +421,9 @@ bool conv_gemm_pair_supported(const ConvGemmParams& p, int block_n) {
 template <int BLOCK_N, bool RESB>
 static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
     using Cfg = Cfg2P<BLOCK_N, RESB>;
-    static bool configured = false;
+    static DevFlags configured;
     static int num_sms = 0;
-    if (!configured) {
+    if (!configured.test()) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm2p_kernel<BLOCK_N, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             gemm_set_error(cudaGetErrorString(e));
@@ -419,7 +432,7 @@ static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        configured.set();
     }
     const int total_pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.batch_count;
     int clusters = num_sms / 2;

@@ -273,14 +273,14 @@ void conv3x3_first(const float* x, const float* in_scale, const float* w, const 
     const int threads = 16 * (Cout / 8);
     const int patch = (Cin * (th + 2) * (tw + 2) + 3) & ~3;
     const size_t smem = (size_t)(9 * Cin * Cout + Cout + patch) * sizeof(float) + (size_t)16 * Cout * sizeof(float2);
-    static bool configured = false;
+    static DevFlags configured;
     static int num_sms = 148;
-    if (!configured) {
+    if (!configured.test()) {
         cudaFuncSetAttribute(conv3x3_first_k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        configured.set();
     }
     const int ntiles = N * (H / th) * (W / tw);
     const int per_sm = threads <= 256 ? 2 : 1;
@@ -338,10 +338,10 @@ void conv3x3_last(const bf16* h, const float* w, const float* b, float* out, int
     long long blocks = (total + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     const size_t smem = (size_t)Cout * 9 * C * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaFuncSetAttribute(conv3x3_last_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        configured = true;
+        configured.set();
     }
     conv3x3_last_k<<<(int)blocks, 256, smem, st>>>(h, w, b, out, N, C, H, W, Cout);
 }
@@ -903,10 +903,10 @@ void linear_f32(const float* x, int ldx, const float* W, const float* b, float* 
                 int act_in, int act_out, cudaStream_t st) {
     dim3 grid((O + 7) / 8, (N + LIN_ROWS - 1) / LIN_ROWS);
     const size_t smem = (size_t)LIN_ROWS * K * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaFuncSetAttribute(linear_f32_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        configured = true;
+        configured.set();
     }
     linear_f32_k<<<grid, 256, smem, st>>>(x, ldx, W, b, y, ldy, N, K, O, act_in, act_out);
 }
@@ -1031,10 +1031,10 @@ __global__ void attn_small_k(const bf16* __restrict__ q, const bf16* __restrict_
 void attn_small(const bf16* q, const bf16* k, const bf16* v, int ld, bf16* out, int ldo, int N, int heads, int seq,
                 int d, float scale, cudaStream_t st) {
     const size_t smem = (size_t)3 * seq * d * sizeof(bf16) + (size_t)seq * seq * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaFuncSetAttribute(attn_small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        configured = true;
+        configured.set();
     }
     attn_small_k<<<N * heads, 256, smem, st>>>(q, k, v, ld, out, ldo, heads, seq, d, scale);
 }

@@ -1,4 +1,5 @@
 #include "kernels_bwd.cuh"
+#include "gemm_tc.cuh"
 
 namespace dxmi {
 
@@ -551,10 +552,10 @@ __global__ void __launch_bounds__(256) attn_small_bwd_k(const bf16* __restrict__
 }
 void attn_small_bwd(const bf16* qkv, const bf16* d_o, bf16* dqkv, int N, int S, int C, float scale, cudaStream_t st) {
     const size_t smem = (size_t)4 * S * C * sizeof(bf16) + (size_t)2 * S * S * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaFuncSetAttribute(attn_small_bwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
+        configured.set();
     }
     attn_small_bwd_k<<<N, 256, smem, st>>>(qkv, d_o, dqkv, S, C, scale);
 }

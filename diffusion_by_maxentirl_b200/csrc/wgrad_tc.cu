@@ -225,14 +225,14 @@ int prepare_wgrad(const void* dy, const void* x, int N, int H, int W, int Cout, 
 }
 
 int run_wgrad(const WgradOp& op, float* partial_ws, float* grad, int Cin_total, int ci_off, float scale, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DevFlags configured;
+    if (!configured.test()) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
             gemm_set_error(cudaGetErrorString(e));
             return (int)e;
         }
-        configured = true;
+        configured.set();
     }
     WgradParams p = *reinterpret_cast<const WgradParams*>(op.params);
     p.partial = partial_ws;

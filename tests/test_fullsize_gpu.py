@@ -34,6 +34,22 @@ def test_cifar_b256_batch_independence_and_determinism(ddpm4):
     assert e.shape == (B, 1) and len(d["logp"]) == 4 and d["logp"][0].shape == (B,)
 
 
+def test_cifar_bitwise_batch_invariance(ddpm4):
+    """Which kernel variant runs (pair / single CTA, shift-3 A reuse, tile width) depends on the batch size; all of them walk K in
+    the same order and every reduction order is a function of the image geometry only - so a trajectory is bit-identical at any
+    batch size (what lets N ranks' shards equal the single-GPU run exactly, bench.py shard_check)."""
+    net, sampler, value, sd, vsd = ddpm4
+    g = torch.Generator().manual_seed(6)
+    noise = torch.randn(5, 256, 3, 32, 32, generator=g).cuda()
+    big = sampler.sample(256, device="cuda", noise=noise)
+    e_big = value(big["sample"], 4)
+    for nb in (8, 64):
+        small = sampler.sample(nb, device="cuda", noise=noise[:, :nb].contiguous())
+        assert torch.equal(small["sample"], big["sample"][:nb]), nb
+        assert torch.equal(torch.stack(small["logp"]), torch.stack(big["logp"])[:, :nb])
+        assert torch.equal(value(small["sample"], 4), e_big[:nb])
+
+
 def test_cifar_b256_sample_equals_looped_sample_step(ddpm4):
     net, sampler, value, sd, vsd = ddpm4
     B = 256
