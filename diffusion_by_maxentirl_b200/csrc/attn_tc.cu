@@ -13,6 +13,9 @@
 // Warp roles (192 threads): warps 0-3 softmax + output, warp 4 TMA producer, warp 5 TMEM allocator + MMA issuer.
 // K/V tiles are double buffered; S_{j+1} is issued right behind P V_j so the tensor pipe works while the softmax
 // warps fold O_j into their registers.
+// (Round 2, measured negative: 8 softmax warps - two per TMEM lane quarter, each half of the key columns, row max exchanged
+//  through shared memory - ran seq 1024 at 343 us instead of 239 us: the per-tile chain softmax -> P V -> fold is bound by its
+//  synchronisation latencies, not by issue slots; the fix is S double-buffering with two query tiles in flight, not more warps.)
 #include "attn_tc.cuh"
 #include "ptx.cuh"
 
@@ -85,6 +88,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
                 ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                if (p.v_col0 >= 0) {
+                    // V straight from the fused q|k|v projection: [keys][64 d] rows of 128 bytes (MN-major B operand of P.V)
+                    ptx::mbar_expect_tx(&kv_full[s], 32 * 1024);
+                    ptx::tma_load_3d(smem + SM_K + s * 16384, &p.qk_map, &kv_full[s], p.k_col0 + head * ATT_D, j * kt, b);
+                    ptx::tma_load_3d(smem + SM_V + s * 16384, &p.qk_map, &kv_full[s], p.v_col0 + head * ATT_D, j * kt, b);
+                    continue;
+                }
                 ptx::mbar_expect_tx(&kv_full[s], kt == ATT_TILE ? 32 * 1024 : 24 * 1024);
                 ptx::tma_load_3d(smem + SM_K + s * 16384, &p.qk_map, &kv_full[s], p.k_col0 + head * ATT_D, j * kt, b);
                 ptx::tma_load_3d(smem + SM_V + s * 16384, &p.vt_map, &kv_full[s], j * kt, head * ATT_D, b);
@@ -117,10 +127,26 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
                 ptx::mbar_wait(&p_full, j & 1);
                 ptx::tc_fence_after();
                 const uint32_t sv = ptx::smem_u32(smem + SM_V + s * 16384);
-                for (int k = 0; k < pv_steps; ++k) {
-                    const uint64_t da = ptx::make_kmajor_sw128_desc(sp + (k >> 2) * 16384) + 2 * (k & 3);
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(sv + (k >> 2) * 8192) + 2 * (k & 3);
-                    ptx::umma_f16(tmem + TM_O, da, db, idesc_o, k > 0);
+                if (p.v_col0 >= 0) {
+                    // B = V tile [kt keys][64 d]: the reduction index (keys) is the ROW index -> MN-major operand (b_major bit 16);
+                    // 16 keys per MMA = 2 KB of rows; SBO = 1 KB between 8-key groups (same encoding as wgrad_tc.cu)
+                    for (int k = 0; k < pv_steps; ++k) {
+                        const uint64_t da = ptx::make_kmajor_sw128_desc(sp + (k >> 2) * 16384) + 2 * (k & 3);
+                        uint64_t db = 0;
+                        const uint32_t addr = sv + k * 2048;
+                        db |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+                        db |= static_cast<uint64_t>(16384 >> 4) << 16;  // LBO (one 64-wide block only)
+                        db |= static_cast<uint64_t>(1024 >> 4) << 32;   // SBO
+                        db |= static_cast<uint64_t>(1) << 46;
+                        db |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
+                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o | (1u << 16), k > 0);
+                    }
+                } else {
+                    for (int k = 0; k < pv_steps; ++k) {
+                        const uint64_t da = ptx::make_kmajor_sw128_desc(sp + (k >> 2) * 16384) + 2 * (k & 3);
+                        const uint64_t db = ptx::make_kmajor_sw128_desc(sv + (k >> 2) * 8192) + 2 * (k & 3);
+                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o, k > 0);
+                    }
                 }
                 ptx::umma_commit(&o_full);
                 ptx::umma_commit(&kv_empty[s]);
@@ -227,7 +253,7 @@ static thread_local char g_attn_err[384] = "";
 const char* attn_last_error() { return g_attn_err; }
 
 int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
-                 int heads, int seq, int d, float scale, AttnOp* op) {
+                 int heads, int seq, int d, float scale, AttnOp* op, int v_col0) {
     g_attn_err[0] = 0;
     if (d != ATT_D || (seq % ATT_TILE && seq != 64) || (ldo & 7)) {
         snprintf(g_attn_err, sizeof g_attn_err, "fused attention needs head dim 64 and seq == 64 or seq %% 128 == 0 (got d=%d seq=%d)", d, seq);
@@ -241,12 +267,22 @@ int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const 
         snprintf(g_attn_err, sizeof g_attn_err, "%s", gemm_last_error());
         return r;
     }
-    // V^T: [B, C, seq] bf16; box = 64 keys x 64 channel rows
-    r = make_mat_map(&p.vt_map, vt, seq, C, B, seq, (long long)C * seq, ATT_D);
-    if (r) {
-        snprintf(g_attn_err, sizeof g_attn_err, "%s", gemm_last_error());
-        return r;
+    if (vt) {
+        // V^T: [B, C, seq] bf16; box = 64 keys x 64 channel rows
+        r = make_mat_map(&p.vt_map, vt, seq, C, B, seq, (long long)C * seq, ATT_D);
+        if (r) {
+            snprintf(g_attn_err, sizeof g_attn_err, "%s", gemm_last_error());
+            return r;
+        }
+        v_col0 = -1;
+    } else {
+        if (v_col0 < 0) {
+            snprintf(g_attn_err, sizeof g_attn_err, "prepare_attn: neither V^T nor a V column offset given");
+            return -31;
+        }
+        p.vt_map = p.qk_map;
     }
+    p.v_col0 = v_col0;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.ldo = ldo;
     p.seq = seq;

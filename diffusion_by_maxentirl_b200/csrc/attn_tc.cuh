@@ -15,6 +15,8 @@ struct AttnParams {
     int ldo;
     int seq;
     int q_col0, k_col0;
+    int v_col0;          // >= 0: V is read from the SAME [batch, seq, ld] tensor at column v_col0 + head*64 (box 64 x 128, keys as
+                         // rows) and enters P.V as an MN-major B operand - no separate V^T GEMM; < 0: vt_map holds V^T
     float scale_log2;    // softmax scale * log2(e)
 };
 
@@ -68,8 +70,9 @@ int prepare_attnblk256(const void* x, const void* w_kvqp, const float* bias_kvqp
                        const float* stats_in, int P_in, float eps, float scale, void* out, float* stats_out, int B, AttnBlkOp* op);
 int run_attnblk256(const AttnBlkOp& op, cudaStream_t st);
 
+// vt == nullptr: V lives in the qk tensor at column v_col0 (one fused q|k|v projection, [B, seq, ld_qk])
 int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const void* vt, void* out, int ldo, int B,
-                 int heads, int seq, int d, float scale, AttnOp* op);
+                 int heads, int seq, int d, float scale, AttnOp* op, int v_col0 = -1);
 int run_attn(const AttnOp& op, cudaStream_t st);
 const char* attn_last_error();
 

@@ -237,50 +237,25 @@ struct AdmBuilder : Builder {
         bf16* o = (bf16*)scratch(4, (size_t)B * HW * C * 2);
         const float* qkv_bias = f32(p + ".qkv.bias");
         if (dh == 64 && (HW % 128 == 0 || HW == 64)) {
-            bf16* qk = (bf16*)scratch(1, (size_t)B * HW * 2 * C * 2);
-            bf16* vT = (bf16*)scratch(2, (size_t)B * HW * C * 2);
-            {   // q | k = hn . W[0:2C]^T   (channel layout (three, heads, d): q rows first, then k, then v)
+            // q | k | v = hn . W^T in ONE GEMM (channel layout (three, heads, d): q rows first, then k, then v); the attention kernel
+            // reads V [keys][d] straight from it as an MN-major operand - round 1 ran a separate batched V^T GEMM (weights as the A
+            // operand) at 0.2-0.3 PFLOP/s: 6 % of the ImageNet-64 forward (profiles/r02_gemm_table_in64_before.txt)
+            bf16* qk = (bf16*)scratch(1, (size_t)B * HW * 3 * C * 2);
+            {
                 dxmi_gemm_desc d = conv_desc(H, W);
                 set_src(d, 0, hn, C, C);
                 add_seg(d, 0, 1);
-                d.b_ptr = packed_rows(p + ".qk", {{{p + ".qkv.weight", 0, C, 0, 2 * C}}}, nullptr, nullptr);
-                d.b_rows = 2 * C;
+                d.b_ptr = packed_rows(p + ".qkv", {{{p + ".qkv.weight", 0, C}}}, nullptr, nullptr);
+                d.b_rows = 3 * C;
                 d.b_ld = C;
                 d.bias = qkv_bias;
                 d.out = qk;
-                d.ldo = 2 * C;
-                gemm(d);
-            }
-            {   // V^T[b] = W[2C:3C] . hn[b]^T  (weights as the A operand -> keys contiguous for the P.V MMA)
-                bf16* wv = packed_rows(p + ".v", {{{p + ".qkv.weight", 0, C, 2 * C, C}}}, nullptr, nullptr);
-                dxmi_gemm_desc d;
-                memset(&d, 0, sizeof d);
-                d.N = 1;
-                d.H = 1;
-                d.W = C;
-                d.out_H = 1;
-                d.out_W = C;
-                d.stride = 1;
-                set_src(d, 0, wv, C, C);
-                add_seg(d, 0, 1);
-                d.b_ptr = hn;
-                d.b_rows = HW;
-                d.b_ld = C;
-                d.b_batch_stride = (long long)HW * C;
-                d.batch = B;
-                d.b_batched = 1;
-                d.bias = qkv_bias ? qkv_bias + 2 * C : nullptr;
-                d.bias_along_m = 1;
-                d.out = vT;
-                d.ldo = HW;
-                d.out_batch_stride = (long long)C * HW;
-                d.alpha = 1.f;
-                d.rows_per_image = 1;
+                d.ldo = 3 * C;
                 gemm(d);
             }
             if (!dry && !err) {
                 AttnOp aop;
-                int r = prepare_attn(qk, 2LL * C, 0, C, vT, o, C, B, heads, HW, dh, scale, &aop);
+                int r = prepare_attn(qk, 3LL * C, 0, C, nullptr, o, C, B, heads, HW, dh, scale, &aop, 2 * C);
                 if (r) {
                     err = r;
                     engine_set_error("prepare_attn: %s", attn_last_error());
