@@ -31,10 +31,14 @@ def set_default_precision(mode):
     native.set_default_precision(mode)
 
 
-def install():
+def install(trainer_ops=False):
     """Rebind the hot-path classes of the reference's `models` package (which must be importable, i.e. the reference
     checkout is on sys.path) to the B200 drop-ins, in place.  Everything else in the reference (trainer, CLIs, FID,
     loaders, `models.value.TimeIndependentValue`, ...) is left untouched and keeps calling the same names.
+    trainer_ops=True additionally binds the fused trainer-side ops of SURVEY 8f rank 1 (`train_ops.py`):
+    `DxMI_Trainer{,_Cond}.get_running_cost` -> the fused forward/backward kernel, and `torch.optim.Adam` AS SEEN BY the
+    reference's train scripts is left alone - pass `diffusion_by_maxentirl_b200.train_ops.FusedAdam` explicitly where the
+    script builds its optimizers (train_cifar10.py:283-296) to get the multi-tensor clip + Adam step.
     Returns the list of rebound `module.attr` names."""
     done = []
     for ref_mod, ref_attr, our_mod, our_attr in _BINDINGS:
@@ -42,4 +46,12 @@ def install():
         ours = importlib.import_module(__name__ + "." + our_mod)
         setattr(ref, ref_attr, getattr(ours, our_attr))
         done.append(f"{ref_mod}.{ref_attr}")
+    if trainer_ops:
+        from . import train_ops
+
+        tr = importlib.import_module("models.DxMI.trainer")
+        for cls in ("DxMI_Trainer", "DxMI_Trainer_Cond"):
+            if hasattr(tr, cls):
+                setattr(getattr(tr, cls), "get_running_cost", train_ops.trainer_get_running_cost)
+                done.append(f"models.DxMI.trainer.{cls}.get_running_cost")
     return done
