@@ -131,6 +131,10 @@ def test_install_rebinds_reference_symbols():
         "val = v.TimeIndependentValue(m.IGEBMEncoderV2(in_chan=3, out_chan=1, use_spectral_norm=False, keepdim=False,"
         " out_activation='linear', avg_pool_dim=1, learn_out_scale=True, nh=128))\n"
         "assert hasattr(m, 'ResBlockV2') and hasattr(m, 'process_single_t')\n"
+        "b2 = pkg.install(trainer_ops=True)\n"
+        "import models.DxMI.trainer as tr\n"
+        "from diffusion_by_maxentirl_b200 import train_ops\n"
+        "assert tr.DxMI_Trainer.get_running_cost is train_ops.trainer_get_running_cost and len(b2) == len(b) + 2\n"
         "print(len(b))\n" % (ref, ROOT)
     )
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
