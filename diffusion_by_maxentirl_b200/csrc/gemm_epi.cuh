@@ -101,6 +101,16 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         rvp[i] = (use_rv && rok[i]) ? p.rowvec + img * p.ldrv : nullptr;
         bm[i] = (g_bm && rok[i]) ? __ldg(p.bias + r) : 0.f;
     }
+    // per-tile base pointers at this thread's first column (the ncu source view charged 8 % of the kernel's instructions to
+    // re-deriving 64-bit addresses per chunk, and 7 % to an integer division inside the row-vector prefetch)
+    const int cc0 = col0 + cx.bu * 4;
+    char* optr[4];
+    const __nv_bfloat16* rptr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        optr[i] = reinterpret_cast<char*>(p.out) + (ooff[i] + cc0) * (g_f32 ? 4 : 2);
+        rptr[i] = use_res ? p.residual + roff[i] + cc0 : nullptr;
+    }
     constexpr int RD = (MODE == EPI_RESIDUAL) ? 4 : 1;  // residual prefetch depth in chunks
     float4 pf_bias = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 pf_rv[4];
@@ -117,19 +127,20 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         if (use_res && pcc < n_total) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (rok[i]) pf_res[slot][i] = __ldg(reinterpret_cast<const uint2*>(p.residual + roff[i] + pcc));
+                if (rok[i]) pf_res[slot][i] = __ldg(reinterpret_cast<const uint2*>(rptr[i] + (pcc - cc0)));
         }
     };
     // a 128-row tile of a map with >= 128 pixels lies inside ONE image: the per-image row vector (the ResBlock's time-embedding
     // projection) is then just a second bias - one load and no per-row adds (it cost ~1.1 us per 128 x 128 tile as 4 loads + 16
     // adds per thread and chunk: tools/bench_n128.py)
     const bool rv_uniform = use_rv && !p.halo && (p.rows_per_image & 127) == 0;
+    const float* rv_base = rv_uniform ? p.rowvec + static_cast<long long>(row0 / p.rows_per_image) * p.ldrv : nullptr;
     auto prefetch = [&](int pcc) {
         const bool pok = pcc < n_total;
         if (has_bias && pok) pf_bias = __ldg(reinterpret_cast<const float4*>(p.bias + pcc));
         if (use_rv) {
             if (rv_uniform) {
-                if (pok) pf_rv[0] = __ldg(reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(row0 / p.rows_per_image) * p.ldrv + pcc));
+                if (pok) pf_rv[0] = __ldg(reinterpret_cast<const float4*>(rv_base + pcc));
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -288,12 +299,12 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             }
             const bool ok = rok[i] && col_ok;
             if (g_f32) {
-                if (ok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + ooff[i] + cc) = make_float4(x[0], x[1], x[2], x[3]);
+                if (ok) *reinterpret_cast<float4*>(optr[i] + static_cast<long long>(c) * (CH * 4)) = make_float4(x[0], x[1], x[2], x[3]);
             } else {
                 __nv_bfloat162 b0 = __floats2bfloat162_rn(x[0], x[1]);
                 __nv_bfloat162 b1 = __floats2bfloat162_rn(x[2], x[3]);
                 uint32_t w0 = *reinterpret_cast<uint32_t*>(&b0), w1 = *reinterpret_cast<uint32_t*>(&b1);
-                if (ok) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ooff[i] + cc) = make_uint2(w0, w1);
+                if (ok) *reinterpret_cast<uint2*>(optr[i] + c * (CH * 2)) = make_uint2(w0, w1);
                 if (STATS) {
                     // statistics of the values the consumer will read (bf16-rounded); masked rows / columns add zero
                     w0 = ok ? w0 : 0u;
