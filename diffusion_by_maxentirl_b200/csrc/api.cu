@@ -47,6 +47,14 @@ int dxmi_set_option(const char* name, int value) {
         set_gn_fused(value);
         return 0;
     }
+    if (!strcmp(name, "s3_stages_max")) {
+        set_s3_stages_max(value);
+        return 0;
+    }
+    if (!strcmp(name, "wave_bn")) {  // read when a plan is built
+        set_wave_bn(value);
+        return 0;
+    }
     if (!strcmp(name, "stats16")) {  // read when a plan is built
         set_stats16(value);
         return 0;

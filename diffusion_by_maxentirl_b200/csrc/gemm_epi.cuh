@@ -48,13 +48,31 @@ struct EpiSlot {
     static constexpr int value = V;
 };
 
+// Epilogue operands prefetched ONE TILE AHEAD (a rolling window of four 32-column chunks that crosses tile boundaries).
+// Why a whole tile: the SM's 64 B/clk return port is shared with the producer's TMA stages - with 100-150 KB of operand tiles
+// queued, ANY load the epilogue issues takes 1.3-2 us (tools/bench_n128.py: a 3-deep instead of a 4-deep operand ring made the
+// row-vector / residual epilogues 5-8 % FASTER).  One chunk of lead (round 1) or the start of the tile (early round 2) is not enough.
+// Measured (tools/bench_n128.py, 128-ch 3x3 conv, B=256): rolling the row vector one tile ahead 86.6 -> 80.8 us; rolling the residual
+// words 85.7 -> 88.6 us (64 carried registers crowd the drain loop), so the residual keeps its one-chunk-ahead prefetch.
+#ifndef EPI_ROLL_RESIDUAL
+#define EPI_ROLL_RESIDUAL 0
+#endif
+template <int MODE>
+struct EpiCarry {  // (templated so that each epilogue shape carries only its own operands across tiles)
+    uint2 res[(MODE == 2 /*EPI_RESIDUAL*/ && EPI_ROLL_RESIDUAL) ? 4 : 1][4];                    // [slot][row]: residual words
+    float4 rv[MODE == 1 /*EPI_ROWVEC*/ ? 4 : 1];                         // [slot]: per-image row vector of a tile inside one image
+    float4 bias[(MODE == 1 || (MODE == 2 && EPI_ROLL_RESIDUAL)) ? 4 : 1];                       // [slot]
+    int tile_key;                                                        // which tile the slots were primed for (-1: none)
+};
+__device__ __forceinline__ int epi_tile_key(int m_tile, int col0, int batch) { return (m_tile * 31 + (col0 >> 5)) * 7 + batch; }
+
 // `acc_full` / `acc_parity`: the accumulator-ready barrier of this tile.  The epilogue issues its operand prefetches (the
 // residual up to four 32-column chunks ahead: ncu round 2 showed the N = 128 convolutions epilogue bound on exactly these
 // L2-latency loads) BEFORE it waits for the accumulator, so they fly during the tile's main loop.
 template <int MODE, bool STATS>
 __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& cx, uint32_t tacc_col, uint32_t tmem_empty_addr,
                                          int m_tile, int col0, int nch, int batch, uint32_t& out_cnt, uint64_t* acc_full,
-                                         uint32_t acc_parity, int next_m_tile = -1, int next_col0 = 0, int next_batch = 0) {
+                                         uint32_t acc_parity, EpiCarry<MODE>& cy, int next_m_tile = -1, int next_col0 = 0, int next_batch = 0) {
     const int row0 = m_tile * TILE_M;
     constexpr int CH = 32;
     const int n_total = p.N_total;
@@ -111,31 +129,53 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         optr[i] = reinterpret_cast<char*>(p.out) + (ooff[i] + cc0) * (g_f32 ? 4 : 2);
         rptr[i] = use_res ? p.residual + roff[i] + cc0 : nullptr;
     }
-    constexpr int RD = (MODE == EPI_RESIDUAL) ? 4 : 1;  // residual prefetch depth in chunks
     float4 pf_bias = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 pf_rv[4];
-    uint2 pf_res[RD][4], pf_gate[4];
+    uint2 pf_res[4], pf_gate[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         pf_rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         pf_gate[i] = make_uint2(0u, 0u);
-#pragma unroll
-        for (int s = 0; s < RD; ++s) pf_res[s][i] = make_uint2(0u, 0u);
+        pf_res[i] = make_uint2(0u, 0u);
     }
-    auto prefetch_res = [&](auto slot_c, int pcc) {
-        constexpr int slot = decltype(slot_c)::value;
-        if (use_res && pcc < n_total) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (rok[i]) pf_res[slot][i] = __ldg(reinterpret_cast<const uint2*>(rptr[i] + (pcc - cc0)));
-        }
-    };
     // a 128-row tile of a map with >= 128 pixels lies inside ONE image: the per-image row vector (the ResBlock's time-embedding
-    // projection) is then just a second bias - one load and no per-row adds (it cost ~1.1 us per 128 x 128 tile as 4 loads + 16
-    // adds per thread and chunk: tools/bench_n128.py)
+    // projection) is then just a second bias - one load and no per-row adds
     const bool rv_uniform = use_rv && !p.halo && (p.rows_per_image & 127) == 0;
     const float* rv_base = rv_uniform ? p.rowvec + static_cast<long long>(row0 / p.rows_per_image) * p.ldrv : nullptr;
-    auto prefetch = [&](int pcc) {
+    // ---- rolling one-tile-ahead window (hot modes, 4 | nch): slot k = chunk & 3
+    const bool roll = (MODE == EPI_ROWVEC || (MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL)) && (nch & 3) == 0 && !p.halo && (MODE != EPI_ROWVEC || rv_uniform);
+    const bool have_next = next_m_tile >= 0;
+    const __nv_bfloat16* rptr_n[4];
+    bool rok_n[4];
+    const float* rv_base_n = nullptr;
+    int cc0_n = 0;
+    if (roll && have_next) {
+        const int nrow0 = next_m_tile * TILE_M;
+        cc0_n = next_col0 + cx.bu * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r32 = nrow0 + cx.rt0 + 4 * i;
+            rok_n[i] = r32 < p.M_total;
+            rptr_n[i] = MODE == EPI_RESIDUAL ? p.residual + next_batch * p.res_batch_stride + static_cast<long long>(r32) * p.ldr + cc0_n : nullptr;
+        }
+        if (MODE == EPI_ROWVEC) rv_base_n = p.rowvec + static_cast<long long>(nrow0 / p.rows_per_image) * p.ldrv;
+    }
+    // load chunk `tc` of THIS tile (next == false) or of the NEXT tile into slot k
+    auto roll_load = [&](auto slot_c, int tc, bool next) {
+        constexpr int k = (MODE == EPI_ROWVEC || (MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL)) ? decltype(slot_c)::value : 0;
+        const int pcc = (next ? cc0_n : cc0) + tc * CH;
+        if (pcc >= n_total) return;
+        if (has_bias) cy.bias[k] = __ldg(reinterpret_cast<const float4*>(p.bias + pcc));
+        if (MODE == EPI_ROWVEC) cy.rv[MODE == EPI_ROWVEC ? k : 0] = __ldg(reinterpret_cast<const float4*>((next ? rv_base_n : rv_base) + pcc));
+        if (MODE == EPI_RESIDUAL) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool okr = next ? rok_n[i] : rok[i];
+                if (okr) cy.res[(MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL) ? k : 0][i] = __ldg(reinterpret_cast<const uint2*>((next ? rptr_n[i] : rptr[i]) + tc * CH));
+            }
+        }
+    };
+    auto prefetch = [&](int pcc) {  // non-rolling modes: one chunk ahead
         const bool pok = pcc < n_total;
         if (has_bias && pok) pf_bias = __ldg(reinterpret_cast<const float4*>(p.bias + pcc));
         if (use_rv) {
@@ -147,35 +187,27 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                     if (rvp[i] && pok) pf_rv[i] = __ldg(reinterpret_cast<const float4*>(rvp[i] + pcc));
             }
         }
+        if (use_res) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (rok[i] && pok) pf_res[i] = __ldg(reinterpret_cast<const uint2*>(rptr[i] + (pcc - cc0)));
+        }
         if (g_gate) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (rok[i] && pok) pf_gate[i] = __ldg(reinterpret_cast<const uint2*>(p.gate + goff[i] + pcc));
         }
     };
-    prefetch(col0 + cx.bu * 4);
-    prefetch_res(EpiSlot<0>{}, col0 + cx.bu * 4);
-    // The NEXT tile's first operands go to L1 now (fire and forget): in the epilogue-bound regime there is no slack before the
-    // accumulator wait, and the first chunks of every tile otherwise eat a full L2 round trip (tools/bench_n128.py:
-    // +1.0 .. 1.4 us per 128 x 128 tile for the row vector / residual)
-    if (next_m_tile >= 0 && !p.halo && (MODE == EPI_ROWVEC || MODE == EPI_RESIDUAL)) {
-        const int nrow0 = next_m_tile * TILE_M;
-        if (MODE == EPI_ROWVEC) {
-            if (rv_uniform && cx.e < 2 * nch) {  // 128-byte lines of this tile's slice of the row vector
-                const float* a = p.rowvec + static_cast<long long>(nrow0 / p.rows_per_image) * p.ldrv + next_col0 + cx.e * 32;
-                if (next_col0 + cx.e * 32 < n_total) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-            }
-        } else {
-            const int prow = nrow0 + (cx.e & 127);  // one 128-byte line (64 bf16 columns) per thread: chunks 0..3 of 128 rows
-            const int pcol = next_col0 + (cx.e >> 7) * 64;
-            if (prow < p.M_total && pcol < n_total)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(p.residual + next_batch * p.res_batch_stride + static_cast<long long>(prow) * p.ldr + pcol));
+    if (roll) {
+        if (cy.tile_key != epi_tile_key(m_tile, col0, batch)) {  // first tile of this CTA: prime the window
+            roll_load(EpiSlot<0>{}, 0, false);
+            roll_load(EpiSlot<1>{}, 1, false);
+            roll_load(EpiSlot<2>{}, 2, false);
+            roll_load(EpiSlot<3>{}, 3, false);
         }
-    }
-    if (RD == 4) {
-        if (1 < nch) prefetch_res(EpiSlot<1 % RD>{}, col0 + cx.bu * 4 + CH);
-        if (2 < nch) prefetch_res(EpiSlot<2 % RD>{}, col0 + cx.bu * 4 + 2 * CH);
-        if (3 < nch) prefetch_res(EpiSlot<3 % RD>{}, col0 + cx.bu * 4 + 3 * CH);
+        cy.tile_key = have_next ? epi_tile_key(next_m_tile, next_col0, next_batch) : -1;
+    } else {
+        prefetch(cc0);
     }
 
     // ---- accumulator ready?
@@ -235,7 +267,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     ptx::named_bar_sync(1, 256);
 
     auto do_chunk = [&](int c, auto slot_c) {
-        constexpr int rs = decltype(slot_c)::value;  // residual prefetch slot of this chunk
+        constexpr int rs = (MODE == EPI_ROWVEC || (MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL)) ? decltype(slot_c)::value : 0;  // rolling-window slot (chunk & 3)
         const int col = col0 + c * CH;
         const int cc = col + cx.bu * 4;
         const bool col_ok = cc < n_total;
@@ -256,12 +288,14 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 x[2] = __expf(__uint_as_float(u.z) * alpha - ms.x) * ms.y;
                 x[3] = __expf(__uint_as_float(u.w) * alpha - ms.x) * ms.y;
             } else {
-                float4 ad = pf_bias;
+                float4 ad = roll ? cy.bias[rs] : pf_bias;
+                if (!has_bias) ad = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (rv_uniform) {
-                    ad.x += pf_rv[0].x;
-                    ad.y += pf_rv[0].y;
-                    ad.z += pf_rv[0].z;
-                    ad.w += pf_rv[0].w;
+                    const float4 rvv = roll ? cy.rv[MODE == EPI_ROWVEC ? rs : 0] : pf_rv[0];
+                    ad.x += rvv.x;
+                    ad.y += rvv.y;
+                    ad.z += rvv.z;
+                    ad.w += rvv.w;
                 }
                 if (g_bm) {
                     ad.x += bm[i];
@@ -280,10 +314,11 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 x[2] = fmaf(__uint_as_float(u.z), alpha, ad.z);
                 x[3] = fmaf(__uint_as_float(u.w), alpha, ad.w);
                 if (use_res) {
-                    x[0] += __uint_as_float(pf_res[rs][i].x << 16);
-                    x[1] += __uint_as_float(pf_res[rs][i].x & 0xffff0000u);
-                    x[2] += __uint_as_float(pf_res[rs][i].y << 16);
-                    x[3] += __uint_as_float(pf_res[rs][i].y & 0xffff0000u);
+                    const uint2 rw = (MODE == EPI_RESIDUAL && roll) ? cy.res[(MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL) ? rs : 0][i] : pf_res[i];
+                    x[0] += __uint_as_float(rw.x << 16);
+                    x[1] += __uint_as_float(rw.x & 0xffff0000u);
+                    x[2] += __uint_as_float(rw.y << 16);
+                    x[3] += __uint_as_float(rw.y & 0xffff0000u);
                 }
                 if (g_act != ACT_NONE) {
 #pragma unroll
@@ -318,8 +353,13 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 }
             }
         }
-        if (c + 1 < nch) prefetch(cc + CH);  // next chunk's operands fly during the stats tail and phase A
-        if (c + RD < nch) prefetch_res(slot_c, cc + RD * CH);
+        if (roll) {
+            // this slot is consumed: refill it with the chunk four ahead - same tile, or the NEXT tile's chunk (c + 4 - nch)
+            if (c + 4 < nch) roll_load(slot_c, c + 4, false);
+            else if (have_next) roll_load(slot_c, c + 4 - nch, true);
+        } else if (c + 1 < nch) {
+            prefetch(cc + CH);  // next chunk's operands fly during the stats tail and phase A
+        }
         if (STATS) {
             // this warp's 16 rows: fold the 4 row sub-indices (lanes xor 8, 16); then the warps that share a row segment
             // are combined through smem in a fixed order and one partial per segment is published
@@ -347,21 +387,17 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             }
             ptx::named_bar_sync(2, 256);
             // (sst is single buffered: the next chunk writes it after its named barrier 1, which every publisher of this
-            //  chunk reaches only after it has read sst)
+            //  chunk reaches only after it has read sst.  Double buffering it to publish after barrier 1 would save this
+            //  barrier, but the 2 KB are not there: the operand ring + staging slots fill the 227 KB)
             const int sg = cx.e >> 5, j = cx.e & 31;  // thread publishes column j of segment sg
             if (sg < stat_nseg) {
                 float2 a = make_float2(0.f, 0.f);
-                if (stat_seg == 16) {
-                    // a 16-row segment (4x4 maps) is exactly the rows of one epilogue warp
-                    a = cx.sst[((sg & 1) * 4 + (sg >> 1)) * 32 + j];
-                } else {
-                    for (int b2 = sg * stat_bps; b2 < (sg + 1) * stat_bps; ++b2) {
+                for (int b2 = sg * stat_bps; b2 < (sg + 1) * stat_bps; ++b2) {
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const float2 b = cx.sst[(hh * 4 + b2) * 32 + j];
-                            a.x += b.x;
-                            a.y += b.y;
-                        }
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float2 b = cx.sst[(hh * 4 + b2) * 32 + j];
+                        a.x += b.x;
+                        a.y += b.y;
                     }
                 }
                 const int srow = row0 + sg * stat_seg;
@@ -375,13 +411,13 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         ++out_cnt;
         ptx::named_bar_sync(1, 256);
     };
-    if (RD == 4) {
+    if (roll) {
 #pragma unroll 1
         for (int c0 = 0; c0 < nch; c0 += 4) {
             do_chunk(c0, EpiSlot<0>{});
-            if (c0 + 1 < nch) do_chunk(c0 + 1, EpiSlot<1 % RD>{});
-            if (c0 + 2 < nch) do_chunk(c0 + 2, EpiSlot<2 % RD>{});
-            if (c0 + 3 < nch) do_chunk(c0 + 3, EpiSlot<3 % RD>{});
+            do_chunk(c0 + 1, EpiSlot<1>{});
+            do_chunk(c0 + 2, EpiSlot<2>{});
+            do_chunk(c0 + 3, EpiSlot<3>{});
         }
     } else {
 #pragma unroll 1

@@ -11,6 +11,10 @@ namespace dxmi {
 static int g_opt_block_n_256 = 1;
 static int g_opt_small_bn = 1;
 static int g_opt_shift3 = 1;
+static int g_opt_wave_bn = 1;
+static int g_opt_s3_stages_max = 8;
+void set_s3_stages_max(int v) { g_opt_s3_stages_max = v; }
+void set_wave_bn(int v) { g_opt_wave_bn = v; }
 void set_shift3(int v) { g_opt_shift3 = v; }
 void set_small_map_bn(int v) { g_opt_small_bn = v; }
 static int g_opt_dbg_mode = 0;
@@ -107,6 +111,19 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             // with a single tile exposes its whole epilogue.  Narrower column tiles give every SM work and a second tile to
             // overlap the first one's epilogue with (option "small_map_bn": 0 = round-1 rule).
             const long long t256 = (long long)m_tiles * (d.b_rows / 256) * (d.batch > 0 ? d.batch : 1);
+            // wave quantisation: B = 256 at 16x16 gives 256 pair tiles on 74 cluster slots (3.46 waves, 13.5 % idle). 128-wide pair
+            // tiles run 6.9 waves of half the size - and with shift-3 A reuse a 128-wide tile is no longer ingest bound.
+            bool s3_ok = g_opt_shift3 && g_opt_wave_bn && g_opt_pair && !pair_resident_b_enabled() && p.stride == 1 && !d.a_batched && d.batch <= 1 &&
+                         d.out_H == d.H && d.out_W == d.W && bw == d.W && bn == 1 && (d.W * 128) % 1024 == 0 && !d.softmax && !d.out_nchw;
+            bool any9 = false;
+            for (int s = 0; s < d.nseg; ++s) any9 |= d.seg_taps[s] == 9;
+            if (s3_ok && any9) {
+                const long long p256 = (long long)((m_tiles + 1) / 2) * (d.b_rows / 256), p128 = 2 * p256;
+                const double e256 = (double)p256 / (double)(((p256 + 73) / 74) * 74), e128 = (double)p128 / (double)(((p128 + 73) / 74) * 74);
+                if (p256 >= 74 && e128 > e256 + 0.08) block_n = 128;
+            }
+            if (block_n == 128) {
+            } else
             if (!g_opt_small_bn)
                 block_n = (t256 <= 37 && d.batch <= 1) ? 128 : 256;
             else if (t256 >= 148 || d.batch > 1)
@@ -225,6 +242,7 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             const int ring = conv_gemm_pair_ring_bytes(block_n);
             int st = ring / stage;
             if (st > 8) st = 8;
+            if (st > g_opt_s3_stages_max) st = g_opt_s3_stages_max;
             if (any9 && st >= 3) {
                 p.shift3 = 1;
                 p.s3_a_bytes = a_bytes;

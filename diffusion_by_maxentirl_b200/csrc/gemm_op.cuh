@@ -17,6 +17,8 @@ int run_gemm(const GemmOp& op, cudaStream_t st);
 void set_block_n_256(int v);
 void set_small_map_bn(int v);
 void set_shift3(int v);
+void set_wave_bn(int v);
+void set_s3_stages_max(int v);
 void set_dbg_mode(int v);
 void set_gemm_version(int v);
 void set_halo(int v);

@@ -290,49 +290,56 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
         else if (simple && !p.residual && p.rowvec) mode = EPI_ROWVEC;
         else if (simple && p.residual && !p.rowvec) mode = EPI_RESIDUAL;
         const bool has_stats = p.stats != nullptr && !p.out_fp32;
-        uint32_t ti = 0, out_cnt = 0;
+        // one instantiation of the whole tile loop per launch-uniform epilogue shape: each carries only its own prefetch state
+        auto run_tiles = [&](auto mode_c, auto stats_c) {
+            constexpr int MODE = decltype(mode_c)::value;
+            constexpr bool ST = decltype(stats_c)::value != 0;
+            uint32_t ti = 0, out_cnt = 0;
+            EpiCarry<MODE> carry;
+            carry.tile_key = -1;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+                const int n_tile = t % p.n_tiles;
+                const int mt = t / p.n_tiles;
+                const int m_tile = mt % p.m_tiles;
+                const int batch = mt / p.m_tiles;
+                const int col0 = n_tile * BLOCK_N;
+                int ncols = p.N_total - col0;
+                if (ncols > BLOCK_N) ncols = BLOCK_N;
+                const int nch = (ncols + 31) / 32;
+                const uint32_t acc = ti & 1;
 
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-            const int n_tile = t % p.n_tiles;
-            const int mt = t / p.n_tiles;
-            const int m_tile = mt % p.m_tiles;
-            const int batch = mt / p.m_tiles;
-            const int col0 = n_tile * BLOCK_N;
-            int ncols = p.N_total - col0;
-            if (ncols > BLOCK_N) ncols = BLOCK_N;
-            const int nch = (ncols + 31) / 32;
-            const uint32_t acc = ti & 1;
-
-            if (ti == 0 && leader) { DBG2(5); }
-            const uint32_t tcol = acc * Cfg::ACC_COLS;
-            const uint32_t te = ptx::smem_u32(&tmem_empty[acc]);  // own CTA: shared::cta addresses are valid shared::cluster ones
-            int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next tile (operand prefetch)
-            if (t + (int)gridDim.x < total_tiles) {
-                const int tn = t + gridDim.x;
-                const int mtn = tn / p.n_tiles;
-                nx_col0 = (tn % p.n_tiles) * BLOCK_N;
-                nx_m = mtn % p.m_tiles;
-                nx_batch = mtn / p.m_tiles;
-            }
-            if (has_stats) {
-                switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                if (ti == 0 && leader) { DBG2(5); }
+                const uint32_t tcol = acc * Cfg::ACC_COLS;
+                const uint32_t te = ptx::smem_u32(&tmem_empty[acc]);  // own CTA: shared::cta addresses are valid shared::cluster ones
+                int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next tile (operand prefetch)
+                if (t + (int)gridDim.x < total_tiles) {
+                    const int tn = t + gridDim.x;
+                    const int mtn = tn / p.n_tiles;
+                    nx_col0 = (tn % p.n_tiles) * BLOCK_N;
+                    nx_m = mtn % p.m_tiles;
+                    nx_batch = mtn / p.m_tiles;
                 }
-            } else {
-                switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
+                epi_tile<MODE, ST>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry, nx_m, nx_col0, nx_batch);
+                if (ti == 0 && leader) { DBG2(6); }
+                if (nch == 0) {  // cannot happen (n tiles are clipped on the host), but never leave the MMA warp waiting
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(&tmem_empty[acc]);
                 }
             }
-            if (ti == 0 && leader) { DBG2(6); }
-            if (nch == 0) {  // cannot happen (n tiles are clipped on the host), but never leave the MMA warp waiting
-                ptx::tc_fence_before();
-                ptx::mbar_arrive(&tmem_empty[acc]);
+        };
+        if (has_stats) {
+            switch (mode) {
+                case EPI_BIAS: run_tiles(EpiSlot<EPI_BIAS>{}, EpiSlot<1>{}); break;
+                case EPI_ROWVEC: run_tiles(EpiSlot<EPI_ROWVEC>{}, EpiSlot<1>{}); break;
+                case EPI_RESIDUAL: run_tiles(EpiSlot<EPI_RESIDUAL>{}, EpiSlot<1>{}); break;
+                default: run_tiles(EpiSlot<EPI_GENERIC>{}, EpiSlot<1>{}); break;
+            }
+        } else {
+            switch (mode) {
+                case EPI_BIAS: run_tiles(EpiSlot<EPI_BIAS>{}, EpiSlot<0>{}); break;
+                case EPI_ROWVEC: run_tiles(EpiSlot<EPI_ROWVEC>{}, EpiSlot<0>{}); break;
+                case EPI_RESIDUAL: run_tiles(EpiSlot<EPI_RESIDUAL>{}, EpiSlot<0>{}); break;
+                default: run_tiles(EpiSlot<EPI_GENERIC>{}, EpiSlot<0>{}); break;
             }
         }
     }

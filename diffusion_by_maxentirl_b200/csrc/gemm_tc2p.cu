@@ -352,43 +352,50 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
         else if (simple && !p.residual && p.rowvec) mode = EPI_ROWVEC;
         else if (simple && p.residual && !p.rowvec) mode = EPI_RESIDUAL;
         const bool has_stats = p.stats != nullptr && !p.out_fp32;
-        uint32_t ti = 0, out_cnt = 0;
+        // one instantiation of the whole tile loop per launch-uniform epilogue shape: each carries only its own prefetch state
+        auto run_tiles = [&](auto mode_c, auto stats_c) {
+            constexpr int MODE = decltype(mode_c)::value;
+            constexpr bool ST = decltype(stats_c)::value != 0;
+            uint32_t ti = 0, out_cnt = 0;
+            EpiCarry<MODE> carry;
+            carry.tile_key = -1;
+            for (int tp = cluster_id; tp < total_pairs; tp += n_clusters, ++ti) {
+                const int n_tile = tp % p.n_tiles;
+                const int mp = tp / p.n_tiles;
+                const int m_tile = (mp % m_pairs) * 2 + (int)rank;
+                const int batch = mp / m_pairs;
+                const int col0 = n_tile * BLOCK_N;
+                int ncols = p.N_total - col0;
+                if (ncols > BLOCK_N) ncols = BLOCK_N;
+                const int nch = (ncols + 31) / 32;
+                const uint32_t acc = ti & 1;
 
-        for (int tp = cluster_id; tp < total_pairs; tp += n_clusters, ++ti) {
-            const int n_tile = tp % p.n_tiles;
-            const int mp = tp / p.n_tiles;
-            const int m_tile = (mp % m_pairs) * 2 + (int)rank;
-            const int batch = mp / m_pairs;
-            const int col0 = n_tile * BLOCK_N;
-            int ncols = p.N_total - col0;
-            if (ncols > BLOCK_N) ncols = BLOCK_N;
-            const int nch = (ncols + 31) / 32;
-            const uint32_t acc = ti & 1;
-
-            const uint32_t tcol = acc * Cfg::ACC_COLS;
-            const uint32_t te = mapa(ptx::smem_u32(&tmem_empty[acc]), 0);  // the leader's barrier
-            int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next tile (operand prefetch)
-            if (tp + n_clusters < total_pairs) {
-                const int tn = tp + n_clusters;
-                const int mpn = tn / p.n_tiles;
-                nx_col0 = (tn % p.n_tiles) * BLOCK_N;
-                nx_m = (mpn % m_pairs) * 2 + (int)rank;
-                nx_batch = mpn / m_pairs;
+                const uint32_t tcol = acc * Cfg::ACC_COLS;
+                const uint32_t te = mapa(ptx::smem_u32(&tmem_empty[acc]), 0);  // the leader's barrier
+                int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next tile (operand prefetch)
+                if (tp + n_clusters < total_pairs) {
+                    const int tn = tp + n_clusters;
+                    const int mpn = tn / p.n_tiles;
+                    nx_col0 = (tn % p.n_tiles) * BLOCK_N;
+                    nx_m = (mpn % m_pairs) * 2 + (int)rank;
+                    nx_batch = mpn / m_pairs;
+                }
+                epi_tile<MODE, ST>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry, nx_m, nx_col0, nx_batch);
             }
-            if (has_stats) {
-                switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    default: epi_tile<EPI_GENERIC, true>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                }
-            } else {
-                switch (mode) {
-                    case EPI_BIAS: epi_tile<EPI_BIAS, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_ROWVEC: epi_tile<EPI_ROWVEC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    case EPI_RESIDUAL: epi_tile<EPI_RESIDUAL, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                    default: epi_tile<EPI_GENERIC, false>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, nx_m, nx_col0, nx_batch); break;
-                }
+        };
+        if (has_stats) {
+            switch (mode) {
+                case EPI_BIAS: run_tiles(EpiSlot<EPI_BIAS>{}, EpiSlot<1>{}); break;
+                case EPI_ROWVEC: run_tiles(EpiSlot<EPI_ROWVEC>{}, EpiSlot<1>{}); break;
+                case EPI_RESIDUAL: run_tiles(EpiSlot<EPI_RESIDUAL>{}, EpiSlot<1>{}); break;
+                default: run_tiles(EpiSlot<EPI_GENERIC>{}, EpiSlot<1>{}); break;
+            }
+        } else {
+            switch (mode) {
+                case EPI_BIAS: run_tiles(EpiSlot<EPI_BIAS>{}, EpiSlot<0>{}); break;
+                case EPI_ROWVEC: run_tiles(EpiSlot<EPI_ROWVEC>{}, EpiSlot<0>{}); break;
+                case EPI_RESIDUAL: run_tiles(EpiSlot<EPI_RESIDUAL>{}, EpiSlot<0>{}); break;
+                default: run_tiles(EpiSlot<EPI_GENERIC>{}, EpiSlot<0>{}); break;
             }
         }
     }
