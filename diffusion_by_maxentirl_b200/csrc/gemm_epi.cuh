@@ -20,7 +20,7 @@ __device__ __forceinline__ float act2(float v, int act) {
 // Per-thread constants of the 8 epilogue warps.
 struct EpiCtx {
     uint8_t* slot0;     // 2 staging slots of 128 rows x 128 bytes (32 fp32 columns), SWIZZLE_128B pattern
-    float2* sst;        // [8 warps][32 columns] GroupNorm partials / softmax row stats
+    float2* sst;        // 2 KB: GroupNorm partials [8 warps][s1 | s2][32 columns] floats, or softmax row stats [128] float2
     uint32_t taddr;     // TMEM address of this warp's lane quarter (column 0 of accumulator 0)
     uint32_t stage_off; // byte offset of this thread's staging row + its 4 swizzled 16-byte units base
     int sw;             // row & 7 (swizzle key) of the staging row this thread writes in phase A
@@ -55,7 +55,7 @@ struct EpiSlot {
 // Measured (tools/bench_n128.py, 128-ch 3x3 conv, B=256): rolling the row vector one tile ahead 86.6 -> 80.8 us; rolling the residual
 // words 85.7 -> 88.6 us (64 carried registers crowd the drain loop), so the residual keeps its one-chunk-ahead prefetch.
 #ifndef EPI_ROLL_RESIDUAL
-#define EPI_ROLL_RESIDUAL 0
+#define EPI_ROLL_RESIDUAL 1
 #endif
 template <int MODE>
 struct EpiCarry {  // (templated so that each epilogue shape carries only its own operands across tiles)
@@ -63,7 +63,18 @@ struct EpiCarry {  // (templated so that each epilogue shape carries only its ow
     float4 rv[MODE == 1 /*EPI_ROWVEC*/ ? 4 : 1];                         // [slot]: per-image row vector of a tile inside one image
     float4 bias[(MODE == 1 || (MODE == 2 && EPI_ROLL_RESIDUAL)) ? 4 : 1];                       // [slot]
     int tile_key;                                                        // which tile the slots were primed for (-1: none)
+#ifdef DXMI_EPI_PROFILE
+    long long prof[8];  // cycles: acc wait | first stage + barrier | stage next | finish + store | prefetch + fold | barrier 2 | publish | barrier 1
+    long long tprev;
+#endif
 };
+#ifdef DXMI_EPI_PROFILE
+#define EPI_T0() cy.tprev = clock64()
+#define EPI_T(k) { const long long now_ = clock64(); cy.prof[k] += now_ - cy.tprev; cy.tprev = now_; }
+#else
+#define EPI_T0()
+#define EPI_T(k)
+#endif
 __device__ __forceinline__ int epi_tile_key(int m_tile, int col0, int batch) { return (m_tile * 31 + (col0 >> 5)) * 7 + batch; }
 
 // `acc_full` / `acc_parity`: the accumulator-ready barrier of this tile.  The epilogue issues its operand prefetches (the
@@ -141,7 +152,9 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     // a 128-row tile of a map with >= 128 pixels lies inside ONE image: the per-image row vector (the ResBlock's time-embedding
     // projection) is then just a second bias - one load and no per-row adds
     const bool rv_uniform = use_rv && !p.halo && (p.rows_per_image & 127) == 0;
-    const float* rv_base = rv_uniform ? p.rowvec + static_cast<long long>(row0 / p.rows_per_image) * p.ldrv : nullptr;
+    // (a tile past the last row - odd tail of a CTA pair - reads the last image's vector: masked at the store, but never out of bounds)
+    const int rv_last = rv_uniform ? (p.M_total - 1) / p.rows_per_image : 0;
+    const float* rv_base = rv_uniform ? p.rowvec + static_cast<long long>(min(row0 / p.rows_per_image, rv_last)) * p.ldrv : nullptr;
     // ---- rolling one-tile-ahead window (hot modes, 4 | nch): slot k = chunk & 3
     const bool roll = (MODE == EPI_ROWVEC || (MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL)) && (nch & 3) == 0 && !p.halo && (MODE != EPI_ROWVEC || rv_uniform);
     const bool have_next = next_m_tile >= 0;
@@ -158,7 +171,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             rok_n[i] = r32 < p.M_total;
             rptr_n[i] = MODE == EPI_RESIDUAL ? p.residual + next_batch * p.res_batch_stride + static_cast<long long>(r32) * p.ldr + cc0_n : nullptr;
         }
-        if (MODE == EPI_ROWVEC) rv_base_n = p.rowvec + static_cast<long long>(nrow0 / p.rows_per_image) * p.ldrv;
+        if (MODE == EPI_ROWVEC) rv_base_n = p.rowvec + static_cast<long long>(min(nrow0 / p.rows_per_image, rv_last)) * p.ldrv;
     }
     // load chunk `tc` of THIS tile (next == false) or of the NEXT tile into slot k
     auto roll_load = [&](auto slot_c, int tc, bool next) {
@@ -211,8 +224,10 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     }
 
     // ---- accumulator ready?
+    EPI_T0();
     ptx::mbar_wait(acc_full, acc_parity);
     ptx::tc_fence_after();
+    EPI_T(0);
     if (g_sm) {
         // row max / sum over the whole accumulator row (N_total == BLOCK_N): one warp per lane quarter
         if (cx.hsel == 0) {
@@ -238,17 +253,15 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         ptx::named_bar_sync(2, 256);
     }
 
-    const int stat_seg = (STATS && !p.halo) ? p.stats_seg : 128;  // halo tiles: one partial per tile (tiles never span images)
     const bool stat_direct = STATS && !p.halo && p.stats_seg == 16;
-    const int stat_nseg = 128 / stat_seg, stat_bps = stat_seg >> 5;
-    const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : (stat_seg == 32 ? 5 : 4));
 
     // ---- phase A: 16 accumulator columns of this warp's 32 rows -> staging slot of chunk c
     const uint32_t cnt0 = out_cnt;
-    auto phase_a = [&](int c) {
+    // tcgen05.ld is asynchronous: the loads of chunk c + 1 are ISSUED before chunk c is finished and waited for after it, so the
+    // TMEM read latency (~500 cycles next to a running MMA: tools/epi_profile.py) hides behind phase B instead of adding to it
+    auto stage_issue = [&](int c, uint32_t (&v)[16]) { ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + (c * CH + cx.hsel * 16), v); };
+    auto stage_finish = [&](int c, uint32_t (&v)[16]) {
         uint8_t* slot = cx.slot0 + ((cnt0 + c) & 1) * EPI_SLOT_BYTES;
-        uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + (c * CH + cx.hsel * 16), v);
         ptx::tmem_ld_wait();
         if (c == nch - 1) {
             // every accumulator column this warp stages is now in registers: hand the TMEM buffer back
@@ -261,10 +274,18 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         for (int q = 0; q < 4; ++q)
             *reinterpret_cast<uint4*>(srow + (((cx.hsel * 4 + q) ^ cx.sw) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     };
-    // One barrier per chunk: chunk c+1 is staged (other slot) BEFORE chunk c is finished, so the TMEM-load latency of some warps
-    // overlaps the phase-B arithmetic of others; the barrier at the end of iteration c orders both "c+1 staged" and "slot of c free".
-    phase_a(0);
+    // One barrier per chunk: chunk c+1 is staged (other slot) BEFORE the barrier that ends chunk c, which orders both
+    // "c+1 staged" and "slot of c free".
+    {
+        uint32_t v0[16];
+        stage_issue(0, v0);
+        stage_finish(0, v0);
+    }
     ptx::named_bar_sync(1, 256);
+    EPI_T(1);
+    // masks only where a tile can be ragged (uniform branch; the statistics add 18 instructions per row otherwise)
+    const bool tile_full = row0 + TILE_M <= p.M_total && col0 + nch * CH <= n_total && p.dbg_mode != 2 && !p.halo;
+    const int lg = (threadIdx.x & 31) >> 3;  // lane's row sub-index
 
     auto do_chunk = [&](int c, auto slot_c) {
         constexpr int rs = (MODE == EPI_ROWVEC || (MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL)) ? decltype(slot_c)::value : 0;  // rolling-window slot (chunk & 3)
@@ -272,7 +293,11 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         const int cc = col + cx.bu * 4;
         const bool col_ok = cc < n_total;
         uint8_t* slot = cx.slot0 + (out_cnt & 1) * EPI_SLOT_BYTES;
-        if (c + 1 < nch) phase_a(c + 1);
+        // (the generic shape carries too many operands to hold 16 more registers across phase B: it issues the load late)
+        constexpr bool AHEAD = MODE != EPI_GENERIC;
+        uint32_t vn[16];
+        if (AHEAD && c + 1 < nch) stage_issue(c + 1, vn);
+        EPI_T(2);
 
         // ---- phase B
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -342,8 +367,10 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 if (ok) *reinterpret_cast<uint2*>(optr[i] + c * (CH * 2)) = make_uint2(w0, w1);
                 if (STATS) {
                     // statistics of the values the consumer will read (bf16-rounded); masked rows / columns add zero
-                    w0 = ok ? w0 : 0u;
-                    w1 = ok ? w1 : 0u;
+                    if (!tile_full) {
+                        w0 = ok ? w0 : 0u;
+                        w1 = ok ? w1 : 0u;
+                    }
                     const float a0 = __uint_as_float(w0 << 16), a1 = __uint_as_float(w0 & 0xffff0000u);
                     const float a2 = __uint_as_float(w1 << 16), a3 = __uint_as_float(w1 & 0xffff0000u);
                     s1[0] += a0; s2[0] = fmaf(a0, a0, s2[0]);
@@ -353,6 +380,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
                 }
             }
         }
+        EPI_T(3);
         if (roll) {
             // this slot is consumed: refill it with the chunk four ahead - same tile, or the NEXT tile's chunk (c + 4 - nch)
             if (c + 4 < nch) roll_load(slot_c, c + 4, false);
@@ -360,56 +388,52 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         } else if (c + 1 < nch) {
             prefetch(cc + CH);  // next chunk's operands fly during the stats tail and phase A
         }
+        // this warp's 16 rows: fold the 4 row sub-indices (lanes xor 8, 16).  Halving butterfly: each round a lane hands half of
+        // its values to its partner and keeps the partner's other half - 6 shuffles instead of 16 (the SM shuffles one warp per
+        // clock) with the SAME association (a0 + a1) + (a2 + a3).  Afterwards lane sub-index g owns, for its column quad:
+        // g = 0: s1 of columns 0,1 | g = 1: s2 of columns 0,1 | g = 2: s1 of columns 2,3 | g = 3: s2 of columns 2,3
+        float u0 = 0.f, u1 = 0.f;
         if (STATS) {
-            // this warp's 16 rows: fold the 4 row sub-indices (lanes xor 8, 16); then the warps that share a row segment
-            // are combined through smem in a fixed order and one partial per segment is published
+            const bool odd = lg & 1, hi = lg >> 1;
+            float t[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);
-                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
-                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16);
-                s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+                const float keep = odd ? s2[j] : s1[j], send = odd ? s1[j] : s2[j];
+                t[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
+            const float k0 = hi ? t[2] : t[0], k1 = hi ? t[3] : t[1];
+            const float d0 = hi ? t[0] : t[2], d1 = hi ? t[1] : t[3];
+            u0 = k0 + __shfl_xor_sync(0xffffffffu, d0, 16);
+            u1 = k1 + __shfl_xor_sync(0xffffffffu, d1, 16);
         }
+        if (c + 1 < nch) {
+            if (!AHEAD) stage_issue(c + 1, vn);
+            stage_finish(c + 1, vn);
+        }
+        EPI_T(4);
+        float* sstf = reinterpret_cast<float*>(cx.sst);  // [8 warps][2: s1 | s2][32 columns]
         if (STATS && stat_direct) {
             // 16-row segments: a segment is exactly the 16 rows of this warp - publish straight to global memory (no shared
             // memory round trip, no second barrier; the consumer's finalize sums HW/16 partials per image in a fixed order)
             const int srow = row0 + ((cx.ew & 3) * 2 + (cx.ew >> 2)) * 16;
-            if (cx.brs0 && col_ok && srow < p.M_total) {
-                float4* dst = reinterpret_cast<float4*>(p.stats + (static_cast<long long>(srow >> 4) * n_total + cc) * 2);
-                dst[0] = make_float4(s1[0], s2[0], s1[1], s2[1]);
-                dst[1] = make_float4(s1[2], s2[2], s1[3], s2[3]);
+            if (col_ok && srow < p.M_total) {
+                float* dst = p.stats + (static_cast<long long>(srow >> 4) * n_total + cc + (lg >> 1) * 2) * 2 + (lg & 1);
+                dst[0] = u0;
+                dst[2] = u1;
             }
         } else if (STATS) {
-            if (cx.brs0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) cx.sst[cx.ew * 32 + cx.bu * 4 + j] = make_float2(s1[j], s2[j]);
-            }
-            ptx::named_bar_sync(2, 256);
-            // (sst is single buffered: the next chunk writes it after its named barrier 1, which every publisher of this
-            //  chunk reaches only after it has read sst.  Double buffering it to publish after barrier 1 would save this
-            //  barrier, but the 2 KB are not there: the operand ring + staging slots fill the 227 KB)
-            const int sg = cx.e >> 5, j = cx.e & 31;  // thread publishes column j of segment sg
-            if (sg < stat_nseg) {
-                float2 a = make_float2(0.f, 0.f);
-                for (int b2 = sg * stat_bps; b2 < (sg + 1) * stat_bps; ++b2) {
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const float2 b = cx.sst[(hh * 4 + b2) * 32 + j];
-                        a.x += b.x;
-                        a.y += b.y;
-                    }
-                }
-                const int srow = row0 + sg * stat_seg;
-                if (p.halo) {
-                    if (col + j < n_total) *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(m_tile) * n_total + col + j) * 2) = a;
-                } else if (col + j < n_total && srow < p.M_total) {
-                    *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(srow >> stat_shift) * n_total + col + j) * 2) = a;
-                }
-            }
+            // hand the warp partials to the publisher warp (epi_publish_tile, an otherwise idle warp of warp group 0): barrier 3
+            // = "the previous chunk's partials have been read" (never waits in practice: the publisher has a whole chunk of time),
+            // barrier 2 = "this chunk's partials are in shared memory" (arrive only - the epilogue warps do not wait for it)
+            ptx::named_bar_sync(3, 288);
+            *reinterpret_cast<float2*>(sstf + cx.ew * 64 + (lg & 1) * 32 + cx.bu * 4 + (lg >> 1) * 2) = make_float2(u0, u1);
+            ptx::named_bar_arrive(2, 288);
+            EPI_T(5);
         }
+        EPI_T(6);
         ++out_cnt;
         ptx::named_bar_sync(1, 256);
+        EPI_T(7);
     };
     if (roll) {
 #pragma unroll 1
@@ -425,5 +449,56 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     }
 }
 
+
+// Statistics publisher (ONE warp, not an epilogue warp): for every chunk of a tile, combines the 8 warp partials per column
+// in a fixed order - per row segment: 32-row blocks ascending, the two 16-row halves of each - and writes one (sum, sum of
+// squares) pair per segment and column.  Keeps 16 shared-memory loads, the adds and the store off the epilogue warps' critical
+// path (tools/epi_profile.py: they cost 450-600 cycles per chunk there, a quarter of the tile's drain time).
+// Must be called for exactly the tiles, in the order, that the epilogue warps process when epi_stats_published(p).
+__device__ __forceinline__ bool epi_stats_published(const ConvGemmParams& p) {
+    return p.stats != nullptr && !p.out_fp32 && (p.halo || p.stats_seg != 16);
+}
+__device__ __forceinline__ void epi_publish_tile(const ConvGemmParams& p, const float* sstf, int m_tile, int col0, int nch, int lane) {
+    const int row0 = m_tile * TILE_M;
+    const int n_total = p.N_total;
+    const int stat_seg = !p.halo ? p.stats_seg : 128;
+    const int bps = stat_seg >> 5;  // 32-row blocks per segment: 1, 2 or 4
+    const int stat_shift = stat_seg == 128 ? 7 : (stat_seg == 64 ? 6 : 5);
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+        const int col = col0 + c * 32 + lane;
+        ptx::named_bar_sync(2, 288);
+        float2 pb[4][2];
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) pb[b2][hh] = make_float2(sstf[(hh * 4 + b2) * 64 + lane], sstf[(hh * 4 + b2) * 64 + 32 + lane]);
+        float2 seg[4];
+        float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) {
+            a.x += pb[b2][0].x;
+            a.y += pb[b2][0].y;
+            a.x += pb[b2][1].x;
+            a.y += pb[b2][1].y;
+            seg[b2] = a;
+            if (((b2 + 1) & (bps - 1)) == 0) a = make_float2(0.f, 0.f);
+        }
+        // the sums above consumed every loaded value: the partials may be overwritten
+        ptx::named_bar_arrive(3, 288);
+        if (col < n_total) {
+            if (p.halo) {
+                *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(m_tile) * n_total + col) * 2) = seg[3];
+            } else {
+#pragma unroll
+                for (int b2 = 0; b2 < 4; ++b2) {
+                    const int srow = row0 + (b2 + 1 - bps) * 32;  // first row of the segment that ends with block b2
+                    if (((b2 + 1) & (bps - 1)) == 0 && srow < p.M_total)
+                        *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(srow >> stat_shift) * n_total + col) * 2) = seg[b2];
+                }
+            }
+        }
+    }
+}
 
 }  // namespace dxmi

@@ -13,6 +13,8 @@ static int g_opt_small_bn = 1;
 static int g_opt_shift3 = 1;
 static int g_opt_wave_bn = 1;
 static int g_opt_s3_stages_max = 8;
+static int g_opt_s3_m2 = 1;  // 0 off, 1 heuristic, 2 whenever possible
+void set_s3_m2(int v) { g_opt_s3_m2 = v; }
 void set_s3_stages_max(int v) { g_opt_s3_stages_max = v; }
 void set_wave_bn(int v) { g_opt_wave_bn = v; }
 void set_shift3(int v) { g_opt_shift3 = v; }
@@ -237,22 +239,39 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             d.out_W == d.W && bw == d.W && bn == 1 && bh + 2 <= 256 && (d.W * 128) % 1024 == 0) {
             bool any9 = false;
             for (int s = 0; s < d.nseg; ++s) any9 |= d.seg_taps[s] == 9;
-            const int a_bytes = (bh + 2) * d.W * 128;
-            const int stage = a_bytes + 3 * (block_n / 2) * 128;
             const int ring = conv_gemm_pair_ring_bytes(block_n);
+            // two tiles per CTA ("s3_m2"): the A box grows to 2*bh+2 rows, the B tiles are shared by both - a third fewer bytes per
+            // output tile into the SM.  Needs an even number of row tiles per image and must not cost more in wave quantisation
+            // (74 cluster slots) than the traffic cut gains.
+            bool m2 = false;
+            if (g_opt_s3_m2 && any9 && p.tiles_w == 1 && p.tiles_h % 2 == 0 && 2 * bh + 2 <= 256) {
+                const int st2 = ring / ((2 * bh + 2) * d.W * 128 + 3 * (block_n / 2) * 128);
+                const long long p1 = (long long)((m_tiles + 1) / 2) * n_tiles, p2 = (long long)((m_tiles + 3) / 4) * n_tiles;
+                const double e1 = (double)p1 / (double)(((p1 + 73) / 74) * 74), e2 = (double)p2 / (double)(((p2 + 73) / 74) * 74);
+                m2 = st2 >= 3 && (g_opt_s3_m2 == 2 || e2 > e1 - 0.10);
+            }
+            const int box_rows = m2 ? 2 * bh + 2 : bh + 2;
+            const int a_bytes = box_rows * d.W * 128;
+            const int stage = a_bytes + 3 * (block_n / 2) * 128;
             int st = ring / stage;
             if (st > 8) st = 8;
             if (st > g_opt_s3_stages_max) st = g_opt_s3_stages_max;
+            p.s3_m2 = 0;
             if (any9 && st >= 3) {
                 p.shift3 = 1;
+                p.s3_m2 = m2 ? 1 : 0;
                 p.s3_a_bytes = a_bytes;
                 p.s3_row_bytes = d.W * 128;
                 p.s3_stages = st;
                 for (int i = 0; i < 3; ++i) {
                     if (!used[i]) continue;
                     const long long ld = d.a_ld[i];
-                    r = make_act_map(&p.s3_map[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.N, ld, ld * d.W, ld * d.W * d.H, d.W, bh + 2, 1, 1);
+                    r = make_act_map(&p.s3_map[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.N, ld, ld * d.W, ld * d.W * d.H, d.W, box_rows, 1, 1);
                     if (r) return r;
+                    if (m2) {  // 1x1 segments: one box of both tiles' rows
+                        r = make_act_map(&p.a_map[i], d.a_ptr[i], d.a_C[i], d.W, d.H, d.N, ld, ld * d.W, ld * d.W * d.H, bw, 2 * bh, bn, p.stride);
+                        if (r) return r;
+                    }
                 }
             }
         }

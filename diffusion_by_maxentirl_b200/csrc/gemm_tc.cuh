@@ -101,6 +101,7 @@ struct ConvGemmParams {
     int s3_a_bytes;            // bytes of one A box = (bh+2) * W * 128
     int s3_row_bytes;          // W * 128: smem offset between vertically adjacent taps
     int s3_stages;             // ring depth in this mode
+    int s3_m2;                 // 1: each CTA owns TWO vertically adjacent 128-row tiles per step (one A box of 2*bh+2 rows, the B tiles shared)
     CUtensorMap s3_map[3];     // per source: (c, w, h, n) map with box (64, W, bh+2, 1)
     float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/stats_seg][N_total][2] (sum, sumsq) or null
     int stats_seg;             // rows per partial: 32, 64 or 128 (a segment never straddles two images)

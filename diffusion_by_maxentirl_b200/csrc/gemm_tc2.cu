@@ -23,7 +23,8 @@
 
 namespace dxmi {
 
-static constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
+// warp group 0: TMA warp, MMA warp, two idle warps (56 registers each after setmaxnreg); warp groups 1-2: 8 epilogue warps (224)
+static constexpr int NUM_THREADS = 384;
 
 template <int BLOCK_N>
 struct Cfg2 {
@@ -105,6 +106,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
     ptx::pdl_trigger();
     if (threadIdx.x == 0) { DBG2(0); DBG2(1); }
 
+    if (warp < 4) {
+    ptx::reg_dec<56>();
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (p.halo) {
@@ -266,10 +269,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             }
         }
         __syncwarp();
+    } else if (warp == 2) {
+        // ------------------------------------------------------------ GroupNorm statistics publisher: see epi_publish_tile
+        if (epi_stats_published(p)) {
+            const float* sstf = reinterpret_cast<const float*>(smem + Cfg::SM_STAT);
+            ptx::named_bar_arrive(3, 288);
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m_tile = (t / p.n_tiles) % p.m_tiles;
+                const int col0 = (t % p.n_tiles) * BLOCK_N;
+                int ncols = p.N_total - col0;
+                if (ncols > BLOCK_N) ncols = BLOCK_N;
+                epi_publish_tile(p, sstf, m_tile, col0, (ncols + 31) / 32, lane);
+            }
+        }
+    }
     } else {
+        ptx::reg_inc<224>();
         // ------------------------------------------------------------ epilogue (8 warps, 256 threads): see epi_tile
         EpiCtx cx;
-        cx.e = threadIdx.x - 64;
+        cx.e = threadIdx.x - 128;
         cx.ew = cx.e >> 5;
         const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
         cx.hsel = cx.ew >> 2;
@@ -297,6 +315,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             uint32_t ti = 0, out_cnt = 0;
             EpiCarry<MODE> carry;
             carry.tile_key = -1;
+#ifdef DXMI_EPI_PROFILE
+            for (int k = 0; k < 8; ++k) carry.prof[k] = 0;
+#endif
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
                 const int n_tile = t % p.n_tiles;
                 const int mt = t / p.n_tiles;

@@ -16,7 +16,8 @@
 
 namespace dxmi {
 
-static constexpr int NUM_THREADS_P = 320;
+// warp group 0: TMA warp, MMA warp, two idle warps (56 registers each after setmaxnreg); warp groups 1-2: 8 epilogue warps (224)
+static constexpr int NUM_THREADS_P = 384;
 
 // RESB ("weights stationary"): when the whole B operand of this CTA (its BLOCK_N/2 rows x K) fits next to a shallow A
 // ring, it is loaded ONCE per CTA and stays in shared memory for every tile the persistent CTA processes; the ring then
@@ -32,7 +33,7 @@ struct Cfg2P {
     static constexpr int STAGE_BYTES = RESB ? A_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = RESB ? 3 : (BLOCK_N > 128 ? 6 : 8);
     static constexpr int ACC_COLS = BLOCK_N <= 128 ? 128 : 256;
-    static constexpr int TMEM_COLS = 2 * ACC_COLS;
+    static constexpr int TMEM_COLS = BLOCK_N == 128 ? 512 : 2 * ACC_COLS;  // (128: room for the two-tiles-per-CTA mode)
     static constexpr int SM_RESB = STAGES * STAGE_BYTES;  // resident B: RESB_MAX_KITERS boxes of B_STAGE_BYTES
     static constexpr int RING_BYTES = SM_RESB + (RESB ? RESB_MAX_KITERS * B_STAGE_BYTES : 0);
     static constexpr int SM_OUT = RING_BYTES;
@@ -88,6 +89,9 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
     using Cfg = Cfg2P<BLOCK_N, RESB>;
     constexpr int STAGES = Cfg::STAGES;
     const bool S3 = BLOCK_N == 128 && !RESB && p.shift3;  // launch-uniform
+    // M2 (shift-3 only): a CTA owns two vertically adjacent tiles (256 rows) per step - one A box of 2*bh+2 image rows and ONE copy
+    // of the B tiles feed both, which cuts the bytes the SM ingests per output tile by a third (these GEMMs are ingest bound)
+    const int msub = (S3 && p.s3_m2) ? 2 : 1;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::SM_BAR);
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
     const uint32_t rank = ctarank();
     const int cluster_id = blockIdx.x >> 1;
     const int n_clusters = gridDim.x >> 1;
-    const int m_pairs = (p.m_tiles + 1) >> 1;
+    const int m_pairs = (p.m_tiles + 2 * msub - 1) / (2 * msub);
     const int total_pairs = m_pairs * p.n_tiles * p.batch_count;
 
     int k_iters = 0;
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(&tmem_full[s], 1);
-            ptx::mbar_init(&tmem_empty[s], 512);  // the 256 epilogue threads of each CTA
+            ptx::mbar_init(&tmem_empty[s], 512 * msub);  // the 256 epilogue threads of each CTA, once per tile they drain
         }
         ptx::mbar_init(resb_full, 2);
         ptx::fence_mbar_init();
@@ -150,6 +154,8 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
     ptx::pdl_wait();
     ptx::pdl_trigger();
 
+    if (warp < 4) {
+    ptx::reg_dec<56>();
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
         if (ptx::elect_one()) {
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
             for (int tp = cluster_id; tp < total_pairs; tp += n_clusters) {
                 const int n_tile = tp % p.n_tiles;
                 const int mp = tp / p.n_tiles;
-                const int m_tile = (mp % m_pairs) * 2 + (int)rank;
+                const int m_tile = ((mp % m_pairs) * 2 + (int)rank) * msub;
                 const int batch = mp / m_pairs;
                 const int n_blk = m_tile / tiles_per_nblk;
                 const int rem = m_tile - n_blk * tiles_per_nblk;
@@ -227,7 +233,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                                 uint8_t* sb = sa + p.s3_a_bytes;
                                 const uint32_t full_leader = mapa(ptx::smem_u32(&full_bar[stage]), 0);
                                 if (rank == 0) {
-                                    ptx::mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
+                                    ptx::mbar_expect_tx(&full_bar[stage], 2 * (msub * A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
                                 } else {
                                     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
                                 }
@@ -281,13 +287,15 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 const uint32_t acc = ti & 1;
                 ptx::mbar_wait(&tmem_empty[acc], ((ti >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t tacc = tmem_base + acc * Cfg::ACC_COLS;
+                const uint32_t tacc = tmem_base + acc * (Cfg::ACC_COLS * msub);
                 if (S3) {
                     const int stage_bytes = p.s3_a_bytes + 3 * Cfg::B_STAGE_BYTES;
                     uint32_t first = 1;
                     for (int s = 0; s < p.nseg; ++s) {
                         const GemmSeg sg = p.seg[s];
                         const int nst = sg.ntaps == 9 ? 3 * sg.nchunks : sg.nchunks;
+                        // smem offset of the second tile's rows inside the stage's A box / tile
+                        const uint32_t sub_off = sg.ntaps == 9 ? (uint32_t)p.bh * p.s3_row_bytes : (uint32_t)A_STAGE_BYTES;
                         for (int k = 0; k < nst; ++k, ++it) {
                             const uint32_t stage = it % p.s3_stages;
                             const uint32_t ph = (it / p.s3_stages) & 1;
@@ -297,11 +305,14 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                             const uint32_t sb = sa + p.s3_a_bytes;
                             const int nr = sg.ntaps == 9 ? 3 : 1;
                             for (int r = 0; r < nr; ++r) {
-                                const uint64_t da = ptx::make_kmajor_sw128_desc(sa + r * p.s3_row_bytes);
                                 const uint64_t db = ptx::make_kmajor_sw128_desc(sb + r * Cfg::B_STAGE_BYTES);
-                                if (p.dbg_mode != 1) {
+                                for (int h = 0; h < msub; ++h) {
+                                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa + r * p.s3_row_bytes + h * sub_off);
+                                    if (p.dbg_mode != 1) {
 #pragma unroll
-                                    for (int j = 0; j < TILE_K / 16; ++j) umma2_f16(tacc, da + 2 * j, db + 2 * j, idesc, (first && j == 0) ? 0u : 1u);
+                                        for (int j = 0; j < TILE_K / 16; ++j)
+                                            umma2_f16(tacc + h * Cfg::ACC_COLS, da + 2 * j, db + 2 * j, idesc, (first && j == 0) ? 0u : 1u);
+                                    }
                                 }
                                 first = 0;
                             }
@@ -330,10 +341,26 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
             }
         }
         __syncwarp();
+    } else if (warp == 2) {
+        // ------------------------------------------------------------ GroupNorm statistics publisher: see epi_publish_tile
+        if (epi_stats_published(p)) {
+            const float* sstf = reinterpret_cast<const float*>(smem + Cfg::SM_STAT);
+            ptx::named_bar_arrive(3, 288);
+            for (int tp = cluster_id; tp < total_pairs; tp += n_clusters) {
+                const int mp = tp / p.n_tiles;
+                const int m_tile0 = ((mp % m_pairs) * 2 + (int)rank) * msub;
+                const int col0 = (tp % p.n_tiles) * BLOCK_N;
+                int ncols = p.N_total - col0;
+                if (ncols > BLOCK_N) ncols = BLOCK_N;
+                for (int h = 0; h < msub; ++h) epi_publish_tile(p, sstf, m_tile0 + h, col0, (ncols + 31) / 32, lane);
+            }
+        }
+    }
     } else {
+        ptx::reg_inc<224>();
         // ------------------------------------------------------------ epilogue (8 warps per CTA): see gemm_epi.cuh
         EpiCtx cx;
-        cx.e = threadIdx.x - 64;
+        cx.e = threadIdx.x - 128;
         cx.ew = cx.e >> 5;
         const int quarter = warp & 3;
         cx.hsel = cx.ew >> 2;
@@ -359,29 +386,39 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
             uint32_t ti = 0, out_cnt = 0;
             EpiCarry<MODE> carry;
             carry.tile_key = -1;
+#ifdef DXMI_EPI_PROFILE
+            for (int k = 0; k < 8; ++k) carry.prof[k] = 0;
+#endif
             for (int tp = cluster_id; tp < total_pairs; tp += n_clusters, ++ti) {
                 const int n_tile = tp % p.n_tiles;
                 const int mp = tp / p.n_tiles;
-                const int m_tile = (mp % m_pairs) * 2 + (int)rank;
+                const int m_tile0 = ((mp % m_pairs) * 2 + (int)rank) * msub;
                 const int batch = mp / m_pairs;
                 const int col0 = n_tile * BLOCK_N;
                 int ncols = p.N_total - col0;
                 if (ncols > BLOCK_N) ncols = BLOCK_N;
                 const int nch = (ncols + 31) / 32;
                 const uint32_t acc = ti & 1;
-
-                const uint32_t tcol = acc * Cfg::ACC_COLS;
                 const uint32_t te = mapa(ptx::smem_u32(&tmem_empty[acc]), 0);  // the leader's barrier
-                int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next tile (operand prefetch)
+                int nx_m = -1, nx_col0 = 0, nx_batch = 0;  // this CTA's next step (operand prefetch)
                 if (tp + n_clusters < total_pairs) {
                     const int tn = tp + n_clusters;
                     const int mpn = tn / p.n_tiles;
                     nx_col0 = (tn % p.n_tiles) * BLOCK_N;
-                    nx_m = (mpn % m_pairs) * 2 + (int)rank;
+                    nx_m = ((mpn % m_pairs) * 2 + (int)rank) * msub;
                     nx_batch = mpn / m_pairs;
                 }
-                epi_tile<MODE, ST>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry, nx_m, nx_col0, nx_batch);
+                for (int h = 0; h < msub; ++h) {
+                    const uint32_t tcol = acc * (Cfg::ACC_COLS * msub) + h * Cfg::ACC_COLS;
+                    const bool last = h == msub - 1;
+                    epi_tile<MODE, ST>(p, cx, tcol, te, m_tile0 + h, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry,
+                                       last ? nx_m : m_tile0 + h + 1, last ? nx_col0 : col0, last ? nx_batch : batch);
+                }
             }
+#ifdef DXMI_EPI_PROFILE
+            if (p.dbg_times && cx.e == 0)
+                for (int k = 0; k < 8; ++k) p.dbg_times[(long long)blockIdx.x * 8 + k] = carry.prof[k];
+#endif
         };
         if (has_stats) {
             switch (mode) {
@@ -441,7 +478,8 @@ static int launch2p_t(const ConvGemmParams& p, cudaStream_t stream) {
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         configured.set();
     }
-    const int total_pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.batch_count;
+    const int msub = (BLOCK_N == 128 && !RESB && p.shift3 && p.s3_m2) ? 2 : 1;
+    const int total_pairs = ((p.m_tiles + 2 * msub - 1) / (2 * msub)) * p.n_tiles * p.batch_count;
     int clusters = num_sms / 2;
     if (total_pairs < clusters) clusters = total_pairs;
     cudaLaunchConfig_t cfg = {};

@@ -128,6 +128,10 @@ __device__ __forceinline__ void bulk_wait() {
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+// non-blocking arrival (producer side of a producer / consumer pair; the consumers bar.sync on the same id and count)
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 // Allocates `ncols` (power of two >= 32) TMEM columns; base address lands in *smem_out. Whole warp.
@@ -194,6 +198,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
         : "r"(taddr)
         : "memory");
 }
+// warp-group register reallocation (all 4 warps of a warp group execute the same one): the TMA / MMA group hands most of its
+// registers to the epilogue groups
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors

@@ -39,6 +39,15 @@ def run(tag, **kw):
     print(f"  {tag:34s} {us:7.1f} us  {flops / us / 1e6:6.0f} TFLOP/s", flush=True)
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "m2":
+    for m2 in (0, 1):
+        lib.dxmi_set_option(b"s3_m2", m2)
+        print(f"two tiles per CTA (s3_m2) = {m2}")
+        run("bias only")
+        run("bias + stats", gn_stats=st, gn_seg=128)
+        run("rowvec + stats (conv1)", rowvec=rv, gn_stats=st, gn_seg=128)
+        run("residual + stats (conv2)", residual=res, gn_stats=st, gn_seg=128)
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     for stg in (4, 3, 2):
         lib.dxmi_set_option(b"s3_stages_max", stg)
