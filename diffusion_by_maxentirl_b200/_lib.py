@@ -120,6 +120,7 @@ SYMBOLS = {
     "dxmi_op_attention": (_I, [_VP, _LL, _I, _I, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
     "dxmi_bind_grad": (_I, [_VP, C.c_char_p, _VP]),
     "dxmi_unet_forward_train": (_I, [_VP, _VP, _VP, _VP, _F, C.c_ulonglong, _I, _VP]),
+    "dxmi_adm_forward_train": (_I, [_VP, _VP, _VP, _VP, _VP, _F, C.c_ulonglong, _I, _VP]),
     "dxmi_op_dropout_mask": (_I, [_VP, _LL, _F, C.c_ulonglong, C.c_uint, _VP]),
     "dxmi_unet_backward": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_value_forward_train": (_I, [_VP, _VP, _VP, _I, _VP]),

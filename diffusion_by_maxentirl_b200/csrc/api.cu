@@ -472,6 +472,39 @@ int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, floa
     return r;
 }
 
+int dxmi_adm_forward_train(dxmi_net_t net, const float* x, const float* t, const int64_t* y, float* out, float dropout_p,
+                           unsigned long long dropout_seed, int B, dxmi_stream_t stream) {
+    if (!net || !net->net.finalized) {
+        set_err("dxmi_adm_forward_train: handle not finalized");
+        return -1;
+    }
+    DeviceGuard guard(net->net.device);
+    if (net->net.a.arch != DXMI_ARCH_ADM_UNET) {
+        set_err("dxmi_adm_forward_train called on a handle that is not an ADM U-Net");
+        return -2;
+    }
+    if (net->net.a.num_classes > 0 && !y) {
+        set_err("dxmi_adm_forward_train: a class-conditional net needs labels");
+        return -6;
+    }
+    if (dropout_p < 0.f || dropout_p >= 1.f) {
+        set_err("dxmi_adm_forward_train: dropout_p must be in [0, 1)");
+        return -5;
+    }
+    Plan* p = get_train_plan(net->net, B, (cudaStream_t)stream);
+    if (!p) return -3;
+    p->x = x;
+    p->x_scale = nullptr;
+    p->t = t;
+    p->y = y;
+    p->out = out;
+    p->dropout_p = dropout_p;
+    p->dropout_seed = dropout_seed;
+    int r = run_ops(p->ops, p->op_names, p->launches_per_run, (cudaStream_t)stream);
+    p->fwd_valid = r == 0;
+    return r;
+}
+
 int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, float* dx, int B, dxmi_stream_t stream) {
     if (!net || !net->net.finalized) {
         set_err("dxmi_unet_backward: handle not finalized");

@@ -20,7 +20,7 @@ struct Builder {
     bool dry;
     int B;
     size_t off = 0;
-    static constexpr int NSLOT = 8;
+    static constexpr int NSLOT = 12;
     size_t scratch_max[NSLOT] = {0};
     size_t scratch_base[NSLOT] = {0};
     int err = 0;

@@ -108,6 +108,7 @@ void spec_adm(Net& net);
 int build_plan(Net& net, Plan& plan);
 int build_train_plan(Net& net, Plan& plan);       // engine_train.cu (IGEBM value net; dispatches the DDPM U-Net)
 int build_unet_train_plan(Net& net, Plan& plan);  // engine_train_unet.cu
+int build_adm_train_plan(Net& net, Plan& plan);   // engine_train_adm.cu
 
 void set_gn_fused(int v);
 void set_stats16(int v);

@@ -328,8 +328,9 @@ struct IgebmTrainBuilder : Builder {
 
 int build_train_plan(Net& net, Plan& plan) {
     if (net.a.arch == DXMI_ARCH_DDPM_UNET) return build_unet_train_plan(net, plan);
+    if (net.a.arch == DXMI_ARCH_ADM_UNET) return build_adm_train_plan(net, plan);
     if (net.a.arch != DXMI_ARCH_IGEBM_V2) {
-        engine_set_error("training plans exist for the IGEBM value net and the DDPM U-Net (the ADM U-Net backward is not built)");
+        engine_set_error("training plans exist for the IGEBM value net, the DDPM U-Net and the ADM U-Net");
         return -26;
     }
     if (net.a.precision != 0) {

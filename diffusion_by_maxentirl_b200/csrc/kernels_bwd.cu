@@ -857,4 +857,172 @@ void dropout_bf16(bf16* x, long long n, float p, unsigned long long seed, unsign
     dropout_bf16_k<<<(int)blocks, 256, 0, st>>>(x, n, p, s0, s1, mask_out);
 }
 
+// ================================================================================================ ADM / EDM backward helpers
+__global__ void __launch_bounds__(256) gn_bwd_film_k(const float2* __restrict__ AB, int N, int C, const float* __restrict__ film, int film_ld,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    float* __restrict__ d_film, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float2 red[8][33];
+    const int col = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + col;
+    float2 a = make_float2(0.f, 0.f);
+    if (c < C) {
+        const float g = gamma[c], b = beta[c];
+        for (int n = rl; n < N; n += 8) {
+            const float2 v = AB[(long long)n * C + c];
+            const float sc = 1.f + film[(long long)n * film_ld + c];
+            d_film[(long long)n * film_ld + c] = fmaf(g, v.y, b * v.x);
+            d_film[(long long)n * film_ld + C + c] = v.x;
+            a.x = fmaf(sc, v.x, a.x);
+            a.y = fmaf(sc, v.y, a.y);
+        }
+    }
+    red[rl][col] = a;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sa += red[j][col].x;
+            sb += red[j][col].y;
+        }
+        if (dbeta) dbeta[c] = sa;
+        if (dgamma) dgamma[c] = sb;
+    }
+}
+void gn_bwd_film_params(const float* ws, int N, int HW, int C, const float* film, int film_ld, const float* gamma, const float* beta,
+                        float* d_film, float* dgamma, float* dbeta, cudaStream_t st) {
+    const float2* AB = reinterpret_cast<const float2*>(ws) + (long long)N * gnb_slabs(HW, C) * C;
+    gn_bwd_film_k<<<(C + 31) / 32, 256, 0, st>>>(AB, N, C, film, film_ld, gamma, beta, d_film, dgamma, dbeta);
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_k(const float* __restrict__ sc, bf16* __restrict__ P, long long rows, int S) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const float* x = sc + r * S;
+    float m = -INFINITY;
+    for (int j = lane; j < S; j += 32) m = fmaxf(m, x[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float l = 0.f;
+    for (int j = lane; j < S; j += 32) l += __expf(x[j] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    const float inv = 1.f / l;
+    for (int j = lane; j < S; j += 32) P[r * S + j] = __float2bfloat16_rn(__expf(x[j] - m) * inv);
+}
+void softmax_rows(const float* scores, bf16* P, long long rows, int S, cudaStream_t st) {
+    softmax_rows_k<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(scores, P, rows, S);
+}
+
+// attn_small_bwd_k with heads: Ct = heads * d columns per q / k / v block
+__global__ void __launch_bounds__(256) attn_small_bwd_heads_k(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
+                                                             bf16* __restrict__ dqkv, int S, int d, int Ct, float scale) {
+    extern __shared__ uint8_t smb[];
+    bf16* sq = reinterpret_cast<bf16*>(smb);  // [S][d]
+    bf16* sk = sq + S * d;
+    bf16* sv = sk + S * d;
+    bf16* sdo = sv + S * d;
+    float* sp = reinterpret_cast<float*>(sdo + S * d);  // [S][S] probabilities
+    float* sds = sp + S * S;                             // [S][S] dP, then dS
+    const int n = blockIdx.x, h = blockIdx.y;
+    const long long b3 = (long long)n * S * 3 * Ct + (long long)h * d, b1 = (long long)n * S * Ct + (long long)h * d;
+    for (int i = threadIdx.x; i < S * d; i += 256) {
+        const int t = i / d, c = i % d;
+        sq[i] = qkv[b3 + (long long)t * 3 * Ct + c];
+        sk[i] = qkv[b3 + (long long)t * 3 * Ct + Ct + c];
+        sv[i] = qkv[b3 + (long long)t * 3 * Ct + 2 * Ct + c];
+        sdo[i] = d_o[b1 + (long long)t * Ct + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * S; i += 256) {
+        const int a = i / S, b = i % S;
+        float s = 0.f, g = 0.f;
+        for (int c = 0; c < d; ++c) {
+            s = fmaf(__bfloat162float(sq[a * d + c]), __bfloat162float(sk[b * d + c]), s);
+            g = fmaf(__bfloat162float(sdo[a * d + c]), __bfloat162float(sv[b * d + c]), g);
+        }
+        sp[i] = s * scale;
+        sds[i] = g;  // dP
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int a = threadIdx.x >> 5; a < S; a += 8) {
+        float m = -INFINITY;
+        for (int b = lane; b < S; b += 32) m = fmaxf(m, sp[a * S + b]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float l = 0.f;
+        for (int b = lane; b < S; b += 32) {
+            const float e = __expf(sp[a * S + b] - m);
+            sp[a * S + b] = e;
+            l += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        const float inv = 1.f / l;
+        float t = 0.f;
+        for (int b = lane; b < S; b += 32) {
+            const float p = sp[a * S + b] * inv;
+            sp[a * S + b] = p;
+            t = fmaf(p, sds[a * S + b], t);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        for (int b = lane; b < S; b += 32) sds[a * S + b] = sp[a * S + b] * (sds[a * S + b] - t) * scale;  // dS
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S * d; i += 256) {
+        const int t = i / d, c = i % d;
+        float dq = 0.f, dk = 0.f, dv = 0.f;
+        for (int j = 0; j < S; ++j) {
+            dq = fmaf(sds[t * S + j], __bfloat162float(sk[j * d + c]), dq);
+            dk = fmaf(sds[j * S + t], __bfloat162float(sq[j * d + c]), dk);
+            dv = fmaf(sp[j * S + t], __bfloat162float(sdo[j * d + c]), dv);
+        }
+        dqkv[b3 + (long long)t * 3 * Ct + c] = __float2bfloat16_rn(dq);
+        dqkv[b3 + (long long)t * 3 * Ct + Ct + c] = __float2bfloat16_rn(dk);
+        dqkv[b3 + (long long)t * 3 * Ct + 2 * Ct + c] = __float2bfloat16_rn(dv);
+    }
+}
+void attn_small_bwd_heads(const bf16* qkv, const bf16* d_o, bf16* dqkv, int N, int heads, int S, int d, float scale, cudaStream_t st) {
+    const size_t smem = (size_t)4 * S * d * sizeof(bf16) + (size_t)2 * S * S * sizeof(float);
+    static DevFlags configured;
+    if (!configured.test()) {
+        cudaFuncSetAttribute(attn_small_bwd_heads_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured.set();
+    }
+    attn_small_bwd_heads_k<<<dim3(N, heads), 256, smem, st>>>(qkv, d_o, dqkv, S, d, heads * d, scale);
+}
+
+__global__ void embedding_grad_k(const float* __restrict__ d_emb, const long long* __restrict__ idx, float* __restrict__ grad, int N, int D,
+                                 int num_classes) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= D) return;
+    for (int n = 0; n < N; ++n) {
+        const long long y = idx[n];
+        if (y >= 0 && y < num_classes) grad[y * D + k] += d_emb[(long long)n * D + k];
+    }
+}
+void embedding_grad(const float* d_emb, const long long* idx, float* grad, int N, int D, int num_classes, cudaStream_t st) {
+    cudaMemsetAsync(grad, 0, (size_t)num_classes * D * sizeof(float), st);
+    embedding_grad_k<<<(D + 127) / 128, 128, 0, st>>>(d_emb, idx, grad, N, D, num_classes);
+}
+
+__global__ void scale_bf16_k(bf16* __restrict__ x, long long n8, float s) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float f[8];
+        unpack8(ld8(x + i * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= s;
+        st8(x + i * 8, pack8(f));
+    }
+}
+void scale_bf16(bf16* x, long long n, float s, cudaStream_t st) {
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > 2368) blocks = 2368;
+    if (blocks < 1) blocks = 1;
+    scale_bf16_k<<<(int)blocks, 256, 0, st>>>(x, n / 8, s);
+}
+
 }  // namespace dxmi

@@ -59,7 +59,7 @@ void linear_bwd_x(const float* dy, int ld_dy, const float* W, float* dx, int ld_
 // holds the layers' output gradients side by side (layer l: columns off[l] .. off[l] + O[l]).  One launch each for all layers:
 //   dW_l = dy_l^T x,  db_l = column sums of dy_l      (separate destination tensors)       and      dx = sum_l dy_l W_l
 struct LinearStack {
-    static constexpr int MAX = 32;
+    static constexpr int MAX = 48;  // (ImageNet-64 ADM: 36 ResBlocks)
     int n_layers;
     int off[MAX + 1];        // column offsets, off[n_layers] = total columns
     float* dW[MAX];          // [O_l, K] fp32 or null
@@ -81,5 +81,23 @@ void silu_f32(const float* x, float* y, long long n, cudaStream_t st);
 // training-mode dropout (unet_small.py:126-127): x[i] *= keep(i) / (1 - p) with a counter-based keep mask that depends only on
 // (seed, stream, element index) - the backward regenerates it instead of storing it.  mask_out (optional): the scaled mask itself.
 void dropout_bf16(bf16* x, long long n, float p, unsigned long long seed, unsigned stream, bf16* mask_out, cudaStream_t st);
+
+// ---- ADM / EDM U-Net backward helpers (engine_train_adm.cu; models/cm/unet.py under autograd) ------------------------------
+// FiLM GroupNorm (use_scale_shift_norm, cm/unet.py:250-254): z = (xh gamma + beta)(1 + scale[n,c]) + shift[n,c].  group_norm_bwd
+// (called with dgamma = dbeta = null) already produces dx with the per-image effective gamma and leaves (A, B)[n,c] in `ws`; this
+// finishes the parameter side:  d_shift = A, d_scale = gamma B + beta A, dgamma = sum_n (1 + scale) B, dbeta = sum_n (1 + scale) A.
+// film / d_film: [N, ld] fp32 with scale at column c and shift at column C + c.
+void gn_bwd_film_params(const float* ws, int N, int HW, int C, const float* film, int film_ld, const float* gamma, const float* beta,
+                        float* d_film, float* dgamma, float* dbeta, cudaStream_t st);
+// P[r, :] = softmax(scores[r, :]) (fp32 [rows, S] -> bf16 [rows, S]); one warp per row, any S
+void softmax_rows(const float* scores, bf16* P, long long rows, int S, cudaStream_t st);
+// multi-head attention backward for short sequences (S <= 64, head dim d <= 64): qkv bf16 [N, S, 3C] with q | k | v blocks of C
+// columns and head h at column h*d of its block; d_o bf16 [N, S, C] -> dqkv (same layout as qkv).  One CTA per (image, head).
+void attn_small_bwd_heads(const bf16* qkv, const bf16* d_o, bf16* dqkv, int N, int heads, int S, int d, float scale, cudaStream_t st);
+// label-embedding gradient (cm/unet.py:778-779, emb = emb + label_emb(y)): grad[y[n], :] += d_emb[n, :] in image order
+// (deterministic: one thread per column walks the batch); grad [num_classes, D] is zeroed first
+void embedding_grad(const float* d_emb, const long long* idx, float* grad, int N, int D, int num_classes, cudaStream_t st);
+// x *= s (bf16, in place)
+void scale_bf16(bf16* x, long long n, float s, cudaStream_t st);
 
 }  // namespace dxmi

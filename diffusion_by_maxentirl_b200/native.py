@@ -202,7 +202,6 @@ class NativeNet(nn.Module):
             )
         if self.training and torch.is_grad_enabled():
             raise NotImplementedError(
-                "B200 U-Net: forward in train() mode under autograd needs a backward, which is built for the DDPM U-Net only "
-                "(the ADM U-Net backward / EDM training is not built); the result would carry no graph. Use .eval() / "
-                "torch.no_grad() for sampling."
+                "B200 net: this entry point does not record a graph (the U-Net `forward`s handle train() mode under autograd "
+                "themselves). Use .eval() / torch.no_grad() for sampling."
             )

@@ -221,6 +221,12 @@ int dxmi_unet_forward_train(dxmi_net_t net, const float* x, const float* t, floa
  * forward tape: conv_in = 0, then blocks / attention / resampling in execution order) applies for (p, seed) - lets a reference
  * implementation replay the exact dropout pattern (tests). */
 int dxmi_op_dropout_mask(void* mask_bf16, long long n, float p, unsigned long long seed, unsigned stream_id, dxmi_stream_t stream);
+/* ---- ADM / EDM U-Net training (trainer.py:693-746 update_sampler_mixed_precision: F = net(c_in x, c_noise, y)
+ * under autograd, models/cm/unet.py:761-790).  dxmi_adm_forward_train = dxmi_unet_forward for the ADM U-Net (labels y or NULL)
+ * that keeps the activations of this batch; the gradients come from dxmi_unet_backward (dx must be NULL: the sampler update
+ * differentiates one step from a replay-buffer state, which is a leaf). ---- */
+int dxmi_adm_forward_train(dxmi_net_t net, const float* x, const float* t, const int64_t* y, float* out, float dropout_p,
+                           unsigned long long dropout_seed, int B, dxmi_stream_t stream);
 int dxmi_unet_backward(dxmi_net_t net, const float* x, const float* dout, float* dx /* [B,Cin,H,W] fp32 gradient w.r.t. the input state, or NULL */,
                        int B, dxmi_stream_t stream);
 
