@@ -89,9 +89,41 @@ class OpenAIDiffusion:
             sigma = sigma * non_terminal + sigma_up * (~non_terminal)
         return sigma
 
+    def _sample_step_with_grad(self, x, indices, noise=None, **model_kwargs):
+        """The reference's sample_step (openai_diffusion.py:66-99) under autograd, for update_sampler_mixed_precision
+        (trainer.py:693-746): F through the B200 U-Net backward plan (models/cm/unet.py `_AdmFunction`), the EDM
+        preconditioning / ancestral-step arithmetic and the learned noise scale exp(log_betas) as elementwise torch ops on
+        [B, C, H, W] fp32 (they carry the graph to log_betas and to F)."""
+        device = x.device
+        x = x.detach().float()
+        sigma = self.sigmas[indices]
+        c_skip, c_out, c_in = [c.float().to(device).reshape(-1, 1, 1, 1) for c in self.diffusion.get_scalings(sigma)]
+        rescaled_t = 1000 * 0.25 * torch.log(sigma + 1e-44)
+        F = self.net(x, rescaled_t.to(device), x_scale=c_in.reshape(-1), **model_kwargs)
+        denoised = c_out * F + c_skip * x
+        sig = sigma.float().to(device).reshape(-1, 1, 1, 1)
+        d = (x - denoised) / sig
+        dt = self.sigma_down[indices].float().to(device).reshape(-1, 1, 1, 1) - sig
+        mu = x + d * dt
+        sigma_up = self.sigma_up[indices].float().to(device)
+        if self.trainable_beta:
+            s = torch.exp(_inner(self.net).log_betas[indices.to(device)])
+            if self.trainable_beta == "fix_last":
+                terminal = (indices == self.n_timesteps - 1).to(device)
+                s = s * ~terminal + sigma_up * terminal
+            elif self.trainable_beta == "fix_last3":
+                non_terminal = (indices < self.n_timesteps - 3).to(device)
+                s = s * non_terminal + sigma_up * (~non_terminal)
+            sigma_up = s
+        z = torch.randn_like(mu) if noise is None else noise.to(device=device, dtype=torch.float32)
+        samples = mu + z * sigma_up.reshape(-1, 1, 1, 1)
+        return {"sample": samples, "mean": mu, "sigma": sigma_up.clamp(1e-4, None)}
+
     def sample_step(self, x, indices, noise=None, **model_kwargs):
         device = x.device
         indices = indices.cpu()
+        if torch.is_grad_enabled() and _inner(self.net).training:
+            return self._sample_step_with_grad(x, indices, noise=noise, **model_kwargs)
         B = x.shape[0]
         x = x.detach().contiguous().float()
         sigma = self.sigmas[indices]

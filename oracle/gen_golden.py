@@ -283,6 +283,60 @@ def gen_ddpm_train(B=2, p_drop=0.3):
                         **{"grad:" + k: grads[k].grad.numpy()[:8] for k in keep})
 
 
+ADM_TRAIN_SMALL = dict(image_size=32, num_channels=64, num_res_blocks=1, channel_mult="1,2,3,4", attention_resolutions="16,8,4")
+
+
+def gen_adm_train(B=2):
+    """Row f4 (EDM training): the reference UNetModel (models/cm/unet.py, reduced width, fp16 torso - the only mode the reference
+    supports) in train() mode under autograd: F = net(x, t, y), backward of a fixed linear functional.  The fp16-torso
+    oracle with torch autograd must reproduce F and every gradient; the fully-fp32 oracle - the yardstick of the CUDA backward
+    tests - must agree within the fp16 noise.
+    Writes tests/golden/adm_train_B2.npz (F and a few gradient tensors of the reference)."""
+    import_reference()
+    from models.cm.script_util import create_model_and_diffusion
+
+    dcfg = dict(EDM_CFGS["in64"]["diffusion"])
+    dcfg.update(ADM_TRAIN_SMALL)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        unet, _ = create_model_and_diffusion(**dcfg)
+    sd32 = load_synth(unet, skip=())
+    unet.convert_to_fp16()
+    unet.train()
+    sd16 = {k: v.detach().clone() for k, v in unet.state_dict().items()}
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, 3, 32, 32, generator=g)
+    t = torch.tensor([1.0954, -0.8327])[:B]
+    y = torch.tensor([17, 803])[:B]
+    coef = torch.randn(B, 3, 32, 32, generator=g)
+    ref = unet(x, t, y)
+    (ref * coef).sum().backward()
+    akw = dict(image_size=32, model_channels=64, channel_mult=(1, 2, 3, 4), num_res_blocks=1, attention_ds=(2, 4, 8),
+               num_head_channels=64, use_scale_shift_norm=True)
+
+    def oracle(fp16):
+        src = sd16 if fp16 else sd32
+        rsd = {k: (v[..., None] if v.dim() == 3 else v).clone().requires_grad_(True) for k, v in src.items()}
+        out = nets.adm_unet_forward(rsd, x, t, y, fp16_torso=fp16, **akw)
+        (out * coef).sum().backward()
+        return out, rsd
+
+    named = dict(unet.named_parameters())
+    for fp16 in (True, False):
+        out, rsd = oracle(fp16)
+        e = rel_l2(out, ref)
+        worst = max((rel_l2(rsd[k].grad.reshape(p_.shape).float(), p_.grad.float()), k) for k, p_ in named.items() if p_.grad is not None)
+        print(f"[adm train B={B}] oracle (fp16 torso={fp16}) vs reference: F {e:.2e}, worst gradient {worst[1]} {worst[0]:.2e}")
+        assert (e < 1e-3 and worst[0] < 2e-2) if fp16 else (e < 1e-2 and worst[0] < 5e-2)
+    keep = ["out.2.weight", "input_blocks.0.0.weight", "input_blocks.3.1.qkv.weight", "input_blocks.3.0.in_layers.2.weight",
+            "input_blocks.3.0.skip_connection.weight", "input_blocks.2.0.in_layers.2.weight", "output_blocks.1.2.out_layers.3.weight",
+            "time_embed.0.weight", "input_blocks.1.0.emb_layers.1.weight", "middle_block.0.out_layers.0.weight",
+            "output_blocks.0.0.skip_connection.weight", "middle_block.1.proj_out.weight"]
+    np.savez_compressed(os.path.join(GOLD, "adm_train_B2.npz"), F=ref.detach().numpy(), x=x.numpy(), coef=coef.numpy(),
+                        t=t.numpy(), y=y.numpy(), label_rows=named["label_emb.weight"].grad[y].float().numpy(),
+                        **{"grad:" + k: named[k].grad.float().numpy()[:8] for k in keep})
+
+
 def gen_edm(name, B, T=None, small=None, seed=123, stride=1, skip_fp32=False):
     import_reference()
     from models.cm.script_util import create_model_and_diffusion
@@ -370,6 +424,7 @@ if __name__ == "__main__":
     ap.add_argument("--lsun", action="store_true")
     ap.add_argument("--skip-ddpm", action="store_true")
     ap.add_argument("--train", action="store_true", help="row a9: pin the training-mode (dropout + autograd) oracle")
+    ap.add_argument("--adm-train", action="store_true", help="row f4: pin the ADM U-Net under autograd")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -378,6 +433,8 @@ if __name__ == "__main__":
         gen_ddpm(T=4, B=2)
     if args.train:
         gen_ddpm_train()
+    if args.adm_train:
+        gen_adm_train()
     if args.edm:
         gen_edm("in64", B=2, T=4, small=dict(image_size=32, num_channels=64, num_res_blocks=1,
                                              channel_mult="1,2,3,4", attention_resolutions="16,8,4"))

@@ -227,10 +227,13 @@ def adm_layout(*, image_size, model_channels, channel_mult, num_res_blocks, atte
 
 
 def adm_unet_forward(sd, x, timesteps, y=None, *, image_size, model_channels, channel_mult, num_res_blocks,
-                     attention_ds, num_head_channels=64, use_scale_shift_norm=True, fp16_torso=True):
+                     attention_ds, num_head_channels=64, use_scale_shift_norm=True, fp16_torso=True, half_softmax=None):
     """models/cm/unet.py:761-790 (UNetModel.forward).  fp16_torso=True is the only mode the reference supports
     (convert_to_fp16 + QKVAttentionLegacy.half()): torso activations/conv weights fp16, GroupNorm and the
-    embedding MLP fp32, head fp32.  fp16_torso=False evaluates the same graph entirely in fp32."""
+    embedding MLP fp32, head fp32.  fp16_torso=False evaluates the same graph entirely in fp32; `half_softmax` (default: follows
+    fp16_torso) = True with fp16_torso=False is the reference built with use_fp16=False, whose attention still runs `.half()`."""
+    if half_softmax is None:
+        half_softmax = fp16_torso
     emb = adm_timestep_embedding(timesteps, model_channels)
     emb = F.linear(F.silu(_lin(sd, "time_embed.0", emb)), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     if "label_emb.weight" in sd:
@@ -248,7 +251,7 @@ def adm_unet_forward(sd, x, timesteps, y=None, *, image_size, model_channels, ch
             elif kind in ("res", "down", "up"):
                 h = _adm_resblock(sd, p, h, emb, up=kind == "up", down=kind == "down", scale_shift=use_scale_shift_norm)
             else:
-                h = _adm_attention(sd, p, h, cout // num_head_channels, half_softmax=fp16_torso)
+                h = _adm_attention(sd, p, h, cout // num_head_channels, half_softmax=half_softmax).type(h.dtype)
         return h
 
     h = x.type(torso)

@@ -120,3 +120,70 @@ def test_mixed_precision_trainer_step():
     assert mp.optimize(opt) is False
     assert mp.lg_loss_scale == 59.0
     assert torch.equal(w1, w.detach())
+
+
+def test_edm_sampler_update_like_the_trainer():
+    """trainer.py:693-746 (update_sampler_mixed_precision): d = sampler.sample_step(state, t, y=y) with grad; loss = mean(v(next,
+    t+1) + (tau2 running_cost - tau1 log sigma) non_terminal); mp_trainer.backward / optimize.  Loss, the log_betas gradient
+    and a torso convolution gradient against the same step in fp32 autograd over the oracle on the CPU."""
+    from test_train_gpu import build_value
+    from diffusion_by_maxentirl_b200.models.cm.fp16_util import MixedPrecisionTrainer
+    from oracle import nets, samplers
+
+    cfg = CFG_A
+    T = 4
+    unet, sampler, sd = build_edm(cfg, T=T, fp16=True)
+    value, vsd = build_value()
+    for p in value.parameters():
+        p.requires_grad_(False)
+    sampler.train()
+    mp = MixedPrecisionTrainer(model=unet, use_fp16=True, initial_lg_loss_scale=0.0, special_key="log_betas")  # (synthetic weights at sigma = 80 give O(100) gradients: larger scales overflow fp16, which test_mixed_precision_trainer_step covers)
+    opt = torch.optim.RAdam([{"params": mp.master_params[1:], "lr": 1e-8}, {"params": mp.master_params[0:1], "lr": 1e-6}])
+    B = 4
+    g = torch.Generator().manual_seed(21)
+    sched = samplers.edm_schedule(T)
+    t = torch.tensor([0, 1, 2, 3])
+    state = torch.randn(B, 3, 32, 32, generator=g) * sched["sigmas"][t].float()[:, None, None, None]
+    z = torch.randn(B, 3, 32, 32, generator=g)
+    y = torch.tensor([3, 500, 77, 999])
+    tau1, tau2, skip_tau = 0.1, 0.01, 1
+    betas_q = torch.exp(unet.log_betas.detach().cpu()) ** 2  # use_sampler_beta: betas_for_q from the sampler's sigmas
+
+    def loss_fn(d, st, v_next, tt):
+        beta_next = betas_q[(T - tt.cpu() - 1)].to(st.device)
+        running = ((d["sample"] - st) ** 2).flatten(1).mean(1) / (2 * beta_next)
+        non_terminal = (tt < T - skip_tau).float().to(st.device)
+        return (v_next.flatten() + (running * tau2 - torch.log(d["sigma"].flatten()) * tau1) * non_terminal).mean()
+
+    mp.zero_grad()
+    d = sampler.sample_step(state.cuda(), t.cuda(), noise=z.cuda(), y=y.cuda())
+    assert d["sample"].requires_grad
+    loss = loss_fn(d, state.cuda(), value(d["sample"], t.cuda() + 1), t)
+    mp.backward(loss)
+    scale = 2 ** mp.lg_loss_scale
+    lb_grad = unet.log_betas.grad.detach().float().cpu() / scale
+    wk = "input_blocks.1.0.in_layers.2.weight"
+    w_grad = unet._param(wk).grad.detach().float().cpu() / scale
+    assert mp.optimize(opt) is True
+    # ---- oracle: the same step, fp32 autograd on the CPU
+    rsd = {k: (v[..., None] if v.dim() == 3 else v).clone().requires_grad_(True) for k, v in sd.items() if k != "log_betas"}
+    lb = sched["log_betas_init"].clone().requires_grad_(True)
+    sigma = sched["sigmas"][t].float()
+    c_skip, c_out, c_in = [c.float()[:, None, None, None] for c in samplers.edm_scalings(sigma)]
+    F = nets.adm_unet_forward(rsd, c_in * state, 1000 * 0.25 * torch.log(sigma + 1e-44), y, fp16_torso=False, **adm_oracle_kwargs(cfg))
+    den = c_out * F + c_skip * state
+    sig = sigma[:, None, None, None]
+    mu = state + (state - den) / sig * (sched["sigma_down"][t].float()[:, None, None, None] - sig)
+    s_up = torch.exp(lb[t])
+    terminal = t == T - 1
+    s_up = s_up * ~terminal + sched["sigma_up"][t].float() * terminal
+    xn = mu + z * s_up[:, None, None, None]
+    rvsd = {k: v.clone() for k, v in vsd.items()}
+    rloss = loss_fn({"sample": xn, "sigma": s_up.clamp(1e-4, None)}, state, nets.value_forward(rvsd, xn), t)
+    rloss.backward()
+    print(f"EDM sampler loss {loss.item():.6f} vs oracle {rloss.item():.6f}")
+    assert abs(loss.item() - rloss.item()) < 2e-2 * max(1.0, abs(rloss.item()))
+    e_lb = rel_l2(lb_grad[:-1], lb.grad[:-1])
+    e_w = rel_l2(w_grad, rsd[wk].grad)
+    print(f"log_betas grad rel-L2 {e_lb:.2e}; {wk} grad rel-L2 {e_w:.2e}")
+    assert e_lb < 5e-2 and e_w < 5e-2

@@ -294,3 +294,45 @@ def test_value_net_oracle_reproduces_reference_gradients():
             ref = torch.from_numpy(gold[key])
             err = float((sd[key[5:]].grad[:8] - ref).norm() / ref.norm().clamp_min(1e-30))
             assert err < 1e-4, (key, err)
+
+
+def test_adm_oracle_reproduces_reference_gradients():
+    """Row f4: tests/golden/adm_train_B2.npz holds F and gradient slices of the *reference* UNetModel (reduced width, fp16 torso -
+    the only mode it supports) in train() mode under autograd (oracle/gen_golden.py::gen_adm_train, where the full comparison
+    was bit-exact).  The fp16-torso oracle + torch autograd must reproduce them without /root/reference; the fp32 oracle - the
+    yardstick of tests/test_adm_train_gpu.py - must agree within the fp16 noise."""
+    import numpy as np
+
+    gold = golden("adm_train_B2.npz")
+    shapes = edm_small_shapes()
+    sd32 = synth.synth_state_dict(shapes)
+    x, coef = torch.from_numpy(gold["x"]), torch.from_numpy(gold["coef"])
+    t, y = torch.from_numpy(gold["t"]), torch.from_numpy(gold["y"])
+    torso = ("input_blocks", "middle_block", "output_blocks")
+    for fp16 in (True, False):
+        sd = {}
+        for k, v in sd32.items():
+            v = v[..., None] if v.dim() == 3 else v
+            # convert_to_fp16 (models/cm/unet.py:745-751): Conv weights / biases of the torso only
+            is_conv = v.dim() == 4 or (k.endswith(".bias") and sd32[k[:-5] + ".weight"].dim() >= 3)
+            if fp16 and k.split(".")[0] in torso and is_conv:
+                v = v.half()
+            sd[k] = v.clone().requires_grad_(True)
+        out = nets.adm_unet_forward(sd, x, t, y, fp16_torso=fp16, **EDM_SMALL)
+        (out * coef).sum().backward()
+        ref = torch.from_numpy(gold["F"])
+        e = float((out.detach().float() - ref).norm() / ref.norm())
+        assert e < (1e-5 if fp16 else 1e-2), e
+        n = 0
+        for key in gold.files:
+            if not key.startswith("grad:"):
+                continue
+            r = torch.from_numpy(gold[key])
+            got = sd[key[5:]].grad.float().reshape(-1, *r.shape[1:])[:8].reshape(r.shape)
+            err = float((got - r).norm() / r.norm().clamp_min(1e-30))
+            assert err < (1e-4 if fp16 else 2e-2), (key, fp16, err)
+            n += 1
+        assert n >= 10
+        rows = torch.from_numpy(gold["label_rows"])
+        got = sd["label_emb.weight"].grad[y]
+        assert float((got - rows).norm() / rows.norm()) < (1e-4 if fp16 else 2e-2)
