@@ -218,7 +218,7 @@ struct AdmTrainBuilder : TrainBuilder {
         r.o = act_alloc(C, H, W);
         bf16 *qkv = r.qkv, *o = r.o;
         if (dh != 64) fail("ADM training attention: head dimension must be 64");
-        if (S % 128 == 0) {
+        if (S % 128 == 0 || S == 64) {
             if (!dry && !err) {
                 AttnOp aop;
                 int rr = prepare_attn(qkv, 3LL * C, 0, C, nullptr, o, C, B, heads, S, dh, scale, &aop, 2 * C);
@@ -230,7 +230,7 @@ struct AdmTrainBuilder : TrainBuilder {
                     op([aop](cudaStream_t st) { return run_attn(aop, st); });
                 }
             }
-        } else if (S <= 64) {
+        } else if (S < 64) {
             op([=](cudaStream_t st) {
                 attn_small(qkv, qkv + C, qkv + 2 * C, 3 * C, o, C, Bn, heads, S, dh, scale, st);
                 return (int)cudaGetLastError();

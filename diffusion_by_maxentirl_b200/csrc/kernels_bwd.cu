@@ -919,28 +919,30 @@ void softmax_rows(const float* scores, bf16* P, long long rows, int S, cudaStrea
 __global__ void __launch_bounds__(256) attn_small_bwd_heads_k(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
                                                              bf16* __restrict__ dqkv, int S, int d, int Ct, float scale) {
     extern __shared__ uint8_t smb[];
-    bf16* sq = reinterpret_cast<bf16*>(smb);  // [S][d]
-    bf16* sk = sq + S * d;
-    bf16* sv = sk + S * d;
-    bf16* sdo = sv + S * d;
-    float* sp = reinterpret_cast<float*>(sdo + S * d);  // [S][S] probabilities
+    // rows padded by one 32-bit word: the score loop reads row b of K / V per lane (stride d would be a 32-way bank conflict)
+    const int dp = d + 2;
+    bf16* sq = reinterpret_cast<bf16*>(smb);  // [S][dp]
+    bf16* sk = sq + S * dp;
+    bf16* sv = sk + S * dp;
+    bf16* sdo = sv + S * dp;
+    float* sp = reinterpret_cast<float*>(sdo + S * dp);  // [S][S] probabilities
     float* sds = sp + S * S;                             // [S][S] dP, then dS
     const int n = blockIdx.x, h = blockIdx.y;
     const long long b3 = (long long)n * S * 3 * Ct + (long long)h * d, b1 = (long long)n * S * Ct + (long long)h * d;
     for (int i = threadIdx.x; i < S * d; i += 256) {
         const int t = i / d, c = i % d;
-        sq[i] = qkv[b3 + (long long)t * 3 * Ct + c];
-        sk[i] = qkv[b3 + (long long)t * 3 * Ct + Ct + c];
-        sv[i] = qkv[b3 + (long long)t * 3 * Ct + 2 * Ct + c];
-        sdo[i] = d_o[b1 + (long long)t * Ct + c];
+        sq[t * dp + c] = qkv[b3 + (long long)t * 3 * Ct + c];
+        sk[t * dp + c] = qkv[b3 + (long long)t * 3 * Ct + Ct + c];
+        sv[t * dp + c] = qkv[b3 + (long long)t * 3 * Ct + 2 * Ct + c];
+        sdo[t * dp + c] = d_o[b1 + (long long)t * Ct + c];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < S * S; i += 256) {
         const int a = i / S, b = i % S;
         float s = 0.f, g = 0.f;
         for (int c = 0; c < d; ++c) {
-            s = fmaf(__bfloat162float(sq[a * d + c]), __bfloat162float(sk[b * d + c]), s);
-            g = fmaf(__bfloat162float(sdo[a * d + c]), __bfloat162float(sv[b * d + c]), g);
+            s = fmaf(__bfloat162float(sq[a * dp + c]), __bfloat162float(sk[b * dp + c]), s);
+            g = fmaf(__bfloat162float(sdo[a * dp + c]), __bfloat162float(sv[b * dp + c]), g);
         }
         sp[i] = s * scale;
         sds[i] = g;  // dP
@@ -976,9 +978,9 @@ __global__ void __launch_bounds__(256) attn_small_bwd_heads_k(const bf16* __rest
         const int t = i / d, c = i % d;
         float dq = 0.f, dk = 0.f, dv = 0.f;
         for (int j = 0; j < S; ++j) {
-            dq = fmaf(sds[t * S + j], __bfloat162float(sk[j * d + c]), dq);
-            dk = fmaf(sds[j * S + t], __bfloat162float(sq[j * d + c]), dk);
-            dv = fmaf(sp[j * S + t], __bfloat162float(sdo[j * d + c]), dv);
+            dq = fmaf(sds[t * S + j], __bfloat162float(sk[j * dp + c]), dq);
+            dk = fmaf(sds[j * S + t], __bfloat162float(sq[j * dp + c]), dk);
+            dv = fmaf(sp[j * S + t], __bfloat162float(sdo[j * dp + c]), dv);
         }
         dqkv[b3 + (long long)t * 3 * Ct + c] = __float2bfloat16_rn(dq);
         dqkv[b3 + (long long)t * 3 * Ct + Ct + c] = __float2bfloat16_rn(dk);
@@ -986,7 +988,7 @@ __global__ void __launch_bounds__(256) attn_small_bwd_heads_k(const bf16* __rest
     }
 }
 void attn_small_bwd_heads(const bf16* qkv, const bf16* d_o, bf16* dqkv, int N, int heads, int S, int d, float scale, cudaStream_t st) {
-    const size_t smem = (size_t)4 * S * d * sizeof(bf16) + (size_t)2 * S * S * sizeof(float);
+    const size_t smem = (size_t)4 * S * (d + 2) * sizeof(bf16) + (size_t)2 * S * S * sizeof(float);
     static DevFlags configured;
     if (!configured.test()) {
         cudaFuncSetAttribute(attn_small_bwd_heads_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
