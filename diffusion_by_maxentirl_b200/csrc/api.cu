@@ -47,6 +47,10 @@ int dxmi_set_option(const char* name, int value) {
         set_gn_fused(value);
         return 0;
     }
+    if (!strcmp(name, "conv_out_padded")) {  // read when a plan is built
+        set_conv_out_padded(value);
+        return 0;
+    }
     if (!strcmp(name, "s3_m2")) {
         set_s3_m2(value);
         return 0;

@@ -12,6 +12,7 @@ namespace dxmi {
 
 int attnblk_option();   // engine.cu: 1 = DDPM AttnBlock at 16x16 as one fused kernel
 int stats16_option();   // engine.cu
+int conv_out_padded_option();
 int gn_fused_option();  // engine.cu: 1 = every GroupNorm with producer statistics is ONE kernel (prologue + streaming apply)
 
 struct Builder {
@@ -321,6 +322,53 @@ struct Builder {
     }
     // last 3x3 convolution of a network: NHWC bf16 -> fp32 NCHW [B, Cout, H, W] at plan.out
     void conv_out_nchw(const bf16* src, int C, int H, int W, const std::string& wkey, const std::string& bkey, int Cout) {
+        if (conv_out_padded_option() && Cout <= 4 && (H * W) % 128 == 0 && (W == 32 || W == 64)) {
+            // Cout = 3 on a 32- / 64-wide map: the persistent kernel's halo mode (every A tile loaded once, not once per tap) with
+            // the weights zero-padded to 8 output rows and a 32-column tile, into a padded NHWC fp32 buffer, then one small
+            // NHWC -> NCHW pass.  (The direct-store kernel below re-reads A nine times: 92 us on the CIFAR map at B = 256.)
+            const long long K = 9LL * C;
+            bf16* wp = nullptr;
+            float* bp = nullptr;
+            if (!dry) {
+                bool fresh = false, fresh_b = false;
+                wp = (bf16*)derived_buf("w:pad8:" + wkey, (size_t)8 * K * sizeof(bf16), &fresh);
+                bp = (float*)derived_buf("b:pad8:" + bkey, 8 * sizeof(float), &fresh_b);
+                if (wp && bp && (fresh || fresh_b)) {
+                    f32(bkey);
+                    Net* np = &net;
+                    net.pack_jobs.push_back([np, wkey, bkey, wp, bp, C, Cout, K](cudaStream_t st) {
+                        const Bound& bw = np->bound[wkey];
+                        const Bound& bb = np->bound[bkey];
+                        cudaMemsetAsync(wp, 0, (size_t)8 * K * sizeof(bf16), st);
+                        cudaMemsetAsync(bp, 0, 8 * sizeof(float), st);
+                        pack_conv_weight(bw.ptr, bw.dtype == DXMI_F16, Cout, C, 3, 3, 0, C, wp, K, 0, st);
+                        const float* bsrc = bb.dtype == DXMI_F32 ? (const float*)bb.ptr : (const float*)np->derived["f32:" + bkey];
+                        cudaMemcpyAsync(bp, bsrc, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st);
+                        count_launches(1);
+                    });
+                }
+            }
+            float* tmp = (float*)scratch(11, (size_t)B * H * W * 8 * sizeof(float));
+            dxmi_gemm_desc d = conv_desc(H, W);
+            set_src(d, 0, src, C, C);
+            add_seg(d, 0, 9);
+            d.b_ptr = wp;
+            d.b_rows = 8;
+            d.b_ld = K;
+            d.bias = bp;
+            d.out = tmp;
+            d.ldo = 8;
+            d.out_fp32 = 1;
+            d.block_n = 32;
+            gemm(d);
+            Plan* pl = &plan;
+            const int Bn = B, HW = H * W;
+            op([=](cudaStream_t st) {
+                nhwc_to_nchw_f32(tmp, 8, (float*)pl->out, Bn, HW, Cout, st);
+                return (int)cudaGetLastError();
+            });
+            return;
+        }
         dxmi_gemm_desc d = conv_desc(H, W);
         set_src(d, 0, src, C, C);
         add_seg(d, 0, 9);

@@ -31,6 +31,9 @@ void set_attnblk(int v) { g_opt_attnblk = v; }
 static int g_opt_stats16 = 0;  // measured (round 2): 16-row direct partials save the 2nd epilogue barrier but cost more in the finalize: -1 % end to end
 int stats16_option() { return g_opt_stats16; }
 void set_stats16(int v) { g_opt_stats16 = v; }
+static int g_opt_conv_out_padded = 1;  // Cout <= 4 output conv through the persistent kernel's halo mode (builder.cuh conv_out_nchw)
+int conv_out_padded_option() { return g_opt_conv_out_padded; }
+void set_conv_out_padded(int v) { g_opt_conv_out_padded = v; }
 static int g_opt_gn_fused = 0;
 int gn_fused_option() { return g_opt_gn_fused; }
 void set_gn_fused(int v) { g_opt_gn_fused = v; }

@@ -938,6 +938,25 @@ __global__ void upsample2x_k(const bf16* __restrict__ x, bf16* __restrict__ out,
         st8(out + i * 8, v);
     }
 }
+__global__ void nhwc_to_nchw_f32_k(const float* __restrict__ src, int ld, float* __restrict__ out, long long total, int HW, int C) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / HW;
+        const int p = (int)(i - n * HW);
+        const float4 v = *reinterpret_cast<const float4*>(src + i * ld);  // ld % 4 == 0, C <= 4
+        float* o = out + n * C * HW + p;
+        o[0] = v.x;
+        if (C > 1) o[HW] = v.y;
+        if (C > 2) o[2LL * HW] = v.z;
+        if (C > 3) o[3LL * HW] = v.w;
+    }
+}
+void nhwc_to_nchw_f32(const float* src, int ld, float* out, int N, int HW, int C, cudaStream_t st) {
+    const long long total = (long long)N * HW;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 2368) blocks = 2368;
+    nhwc_to_nchw_f32_k<<<(int)blocks, 256, 0, st>>>(src, ld, out, total, HW, C);
+}
+
 void upsample2x(const bf16* x, bf16* out, int N, int H, int W, int C, cudaStream_t st) {
     const long long total = (long long)N * 4 * H * W * (C / 8);
     long long blocks = (total + 255) / 256;

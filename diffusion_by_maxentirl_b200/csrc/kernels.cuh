@@ -68,6 +68,8 @@ void embedding_add(float* emb, const float* table, const long long* idx, int N, 
 
 // ---- resampling ----------------------------------------------------------------------------------------------------------
 void upsample2x(const bf16* x, bf16* out, int N, int H, int W, int C, cudaStream_t st);          // nearest
+// out[n][c][p] = src[(n*HW + p)*ld + c] for c < C (fp32): the padded NHWC result of the network-output convolution -> NCHW
+void nhwc_to_nchw_f32(const float* src, int ld, float* out, int N, int HW, int C, cudaStream_t st);
 void avgpool2(const bf16* x, bf16* out, int N, int H, int W, int C, int act, cudaStream_t st);   // 2x2 mean (+act)
 
 // ---- tiny attention (whole sequence in one CTA; seq <= 64) ------------------------------------------------------------
