@@ -18,6 +18,7 @@ struct dxmi_net_s {
 static thread_local char g_api_err[768] = "";
 static void set_err(const char* m) { snprintf(g_api_err, sizeof g_api_err, "%s", m); }
 
+static int g_opt_t_uniform = 1;      // option "t_uniform": DDPM rollout plans evaluate the timestep-embedding path for one row (engine.cuh Plan::t_uniform)
 static int g_rollout_split = 1;      // option "rollout_split": sub-batches per rollout (1 = off, the default: measured neutral)
 static int g_rollout_split_min = 32; // option "rollout_split_min": smallest sub-batch worth splitting into
 static void dxmi_set_rollout_split(int split, int min_sub) {
@@ -45,6 +46,10 @@ int dxmi_set_option(const char* name, int value) {
     }
     if (!strcmp(name, "gn_fused")) {  // read when a plan is built
         set_gn_fused(value);
+        return 0;
+    }
+    if (!strcmp(name, "t_uniform")) {  // DDPM rollouts: one-row timestep-embedding path (read when a rollout fetches its plan)
+        g_opt_t_uniform = value;
         return 0;
     }
     if (!strcmp(name, "conv_out_padded")) {  // read when a plan is built
@@ -234,12 +239,13 @@ static int run_pack(Net& n, cudaStream_t st) {
 }
 
 // `inst` > 0: further plan instances (own arena) for the same batch size - the sub-batches of a split rollout
-static Plan* get_plan(Net& n, int B, int inst = 0) {
-    const int key = B + (inst << 24);
+static Plan* get_plan(Net& n, int B, int inst = 0, bool t_uniform = false) {
+    const int key = B + (inst << 24) + (t_uniform ? (1 << 30) : 0);
     auto it = n.plans.find(key);
     if (it != n.plans.end()) return it->second.get();
     std::unique_ptr<Plan> p(new Plan());
     p->B = B;
+    p->t_uniform = t_uniform;
     const size_t jobs_before = n.pack_jobs.size();
     int r = build_plan(n, *p);
     if (r) {
@@ -591,7 +597,7 @@ static int split_count(int B) {
     return S < 1 ? 1 : S;
 }
 
-static int make_subs(Net& n, int B, cudaStream_t st, std::vector<SubRollout>& subs) {
+static int make_subs(Net& n, int B, cudaStream_t st, std::vector<SubRollout>& subs, bool t_uniform = false) {
     const int S = split_count(B);
     const int Bs = B / S;
     while ((int)n.side_streams.size() < S - 1) {
@@ -610,7 +616,7 @@ static int make_subs(Net& n, int B, cudaStream_t st, std::vector<SubRollout>& su
         return -30;
     }
     for (int k = 0; k < S; ++k) {
-        Plan* p = get_plan(n, Bs, S > 1 ? k : 0);
+        Plan* p = get_plan(n, Bs, S > 1 ? k : 0, t_uniform);
         if (!p) return -3;
         subs.push_back({p, k == 0 ? st : n.side_streams[k - 1], k * Bs, Bs});
     }
@@ -654,7 +660,7 @@ int dxmi_var_rollout(dxmi_net_t net, const float* sched_host, const float* sigma
     Net& n = net->net;
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<SubRollout> subs;
-    int r = make_subs(n, B, st, subs);
+    int r = make_subs(n, B, st, subs, g_opt_t_uniform != 0);
     if (r) return r;
     const long long chw = (long long)n.a.in_channels * n.a.resolution * n.a.resolution;
     const long long bchw = chw * B;

@@ -386,9 +386,9 @@ struct Builder {
     // Y[B, O] (fp32) = silu(X[B, K]) . W^T + b for a row-stack of Linear layers (every ResBlock's time-embedding
     // projection in one tensor-core GEMM; unet_small.py:123, cm/unet.py:203-209)
     void batched_emb_projection(const float* x, int K, const std::string& name, const std::vector<std::string>& wkeys,
-                                const std::vector<std::string>& bkeys, float* y, int O) {
-        bf16* xb = (bf16*)alloc((size_t)B * K * sizeof(bf16));
-        const int Bn = B;
+                                const std::vector<std::string>& bkeys, float* y, int O, int rows = -1) {
+        const int Bn = rows > 0 ? rows : B;
+        bf16* xb = (bf16*)alloc((size_t)Bn * K * sizeof(bf16));
         op([=](cudaStream_t st) {
             silu_to_bf16(x, xb, (long long)Bn * K, st);
             return (int)cudaGetLastError();
@@ -399,9 +399,9 @@ struct Builder {
         memset(&d, 0, sizeof d);
         d.N = 1;
         d.H = 1;
-        d.W = B;
+        d.W = Bn;
         d.out_H = 1;
-        d.out_W = B;
+        d.out_W = Bn;
         d.stride = 1;
         d.batch = 1;
         set_src(d, 0, xb, K, K);

@@ -534,11 +534,13 @@ struct DdpmBuilder : Builder {
             TP = tot;
         }
         // ---- timestep embedding MLP + all temb_proj at once (unet_small.py:296-299, :123)
-        float* te = (float*)alloc((size_t)B * ch * 4);
-        float* t1 = (float*)alloc((size_t)B * temb_ch * 4);
-        float* temb = (float*)alloc((size_t)B * temb_ch * 4);
-        tproj = (float*)alloc((size_t)B * TP * 4);
-        tproj_ld = TP;
+        // (rollout plans: one timestep per step - one row, read by every image with row stride 0)
+        const int Bt = plan.t_uniform ? 1 : B;
+        float* te = (float*)alloc((size_t)Bt * ch * 4);
+        float* t1 = (float*)alloc((size_t)Bt * temb_ch * 4);
+        float* temb = (float*)alloc((size_t)Bt * temb_ch * 4);
+        tproj = (float*)alloc((size_t)Bt * TP * 4);
+        tproj_ld = plan.t_uniform ? 0 : TP;
         {
             std::vector<std::string> wk, bk;
             for (auto& p : rb) {
@@ -550,13 +552,13 @@ struct DdpmBuilder : Builder {
             const float* w1 = f32("temb.dense.1.weight");
             const float* b1 = f32("temb.dense.1.bias");
             op([=](cudaStream_t st) {
-                timestep_embedding(pl->t, te, Bn, ch, 0, st);
-                linear_f32(te, ch, w0, b0, t1, temb_ch, Bn, ch, temb_ch, 0, 0, st);
-                linear_f32(t1, temb_ch, w1, b1, temb, temb_ch, Bn, temb_ch, temb_ch, 2, 0, st);
+                timestep_embedding(pl->t, te, Bt, ch, 0, st);
+                linear_f32(te, ch, w0, b0, t1, temb_ch, Bt, ch, temb_ch, 0, 0, st);
+                linear_f32(t1, temb_ch, w1, b1, temb, temb_ch, Bt, temb_ch, temb_ch, 2, 0, st);
                 return (int)cudaGetLastError();
             },
                3);
-            batched_emb_projection(temb, temb_ch, "temb_proj", wk, bk, tproj, TP);
+            batched_emb_projection(temb, temb_ch, "temb_proj", wk, bk, tproj, TP, Bt);
         }
         // ---- conv_in
         Act h0 = new_act(ch, R, R, /*want_stats=*/true);  // conv_in writes its GroupNorm partials itself (one per 128-pixel tile)

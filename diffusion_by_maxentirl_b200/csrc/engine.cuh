@@ -45,6 +45,9 @@ struct Plan {
     const float* t = nullptr;
     const int64_t* y = nullptr;
     float* out = nullptr;
+    // rollout plans of the DDPM sampler: every image of a step has the SAME timestep (var_sampler.py:262-270), so the embedding MLP and
+    // the temb_proj row-stack are evaluated for ONE row and every convolution reads that row (row stride 0). Set before the plan is built.
+    bool t_uniform = false;
     // training plans (engine_train.cu): backward launch list + its per-call I/O
     std::vector<std::function<int(cudaStream_t)>> bwd_ops;
     std::vector<std::string> bwd_names;
