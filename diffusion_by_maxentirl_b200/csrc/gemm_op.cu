@@ -128,10 +128,8 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
             } else
             if (!g_opt_small_bn)
                 block_n = (t256 <= 37 && d.batch <= 1) ? 128 : 256;
-            else if (t256 >= 148 || d.batch > 1)
-                block_n = 256;
-            else if (t256 >= 74)
-                block_n = 128;
+            else if (t256 >= 74 || d.batch > 1)
+                block_n = 256;  // (74..147 tiles, the 8x8 maps at B = 256: measured 7-8 % faster than 128-wide pair tiles - tools/bench_small_maps.py)
             else
                 block_n = 64;
         }
