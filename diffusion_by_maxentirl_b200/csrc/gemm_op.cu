@@ -26,6 +26,7 @@ static int g_opt_gemm_v = 2;
 // bandwidth, and the 9-vs-8 tiles per 32x32 image plus the pad columns cost more than the saved bytes.
 static int g_opt_halo = 0;
 void set_halo(int v) { g_opt_halo = v; }
+int halo_option() { return g_opt_halo; }
 // cta_group::2 pair kernel (gemm_tc2p.cu): 0 = off, 1 = when there are at least g_opt_pair_min pair tiles, 2 = whenever supported
 static int g_opt_pair = 1;
 static int g_opt_pair_min = 74;
