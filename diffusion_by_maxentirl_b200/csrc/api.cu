@@ -281,6 +281,8 @@ int dxmi_finalize(dxmi_net_t net, dxmi_stream_t stream) {
     if (!n.finalized) {
         // building the B=1 plan registers every packed / derived weight and its pack job
         if (!get_plan(n, 1)) return -8;
+        // the rollout (uniform-timestep) plan variant packs one more derived weight: register its job before the pack jobs run
+        if (n.a.arch == DXMI_ARCH_DDPM_UNET && n.a.precision == 0 && !get_plan(n, 1, 0, true)) return -8;
         n.finalized = true;
     }
     return run_pack(n, (cudaStream_t)stream);

@@ -322,7 +322,8 @@ struct Builder {
     }
     // last 3x3 convolution of a network: NHWC bf16 -> fp32 NCHW [B, Cout, H, W] at plan.out
     void conv_out_nchw(const bf16* src, int C, int H, int W, const std::string& wkey, const std::string& bkey, int Cout) {
-        if (conv_out_padded_option() && Cout <= 4 && (H * W) % 128 == 0 && (W == 32 || W == 64)) {
+        const bool direct = conv_out_padded_option() == 1 && conv3x3_last_supported(H, W, C, Cout);
+        if (direct || (conv_out_padded_option() && Cout <= 4 && (H * W) % 128 == 0 && (W == 32 || W == 64))) {
             // Cout = 3 on a 32- / 64-wide map: the persistent kernel (two-phase coalesced epilogue, 8-stage ring) with the weights
             // zero-padded to 8 output rows and a 32-column tile, into a padded NHWC fp32 buffer, then one small NHWC -> NCHW pass.
             const long long K = 9LL * C;
@@ -346,6 +347,16 @@ struct Builder {
                         count_launches(1);
                     });
                 }
+            }
+            if (direct) {
+                // read-once stream kernel (conv_last.cu): halo tile + weights in shared memory, mma.sync N = 8
+                Plan* pl = &plan;
+                const int Bn = B;
+                op([=](cudaStream_t st) {
+                    conv3x3_last(src, wp, bp, (float*)pl->out, Bn, H, W, C, Cout, st);
+                    return (int)cudaGetLastError();
+                });
+                return;
             }
             float* tmp = (float*)scratch(11, (size_t)B * H * W * 8 * sizeof(float));
             dxmi_gemm_desc d = conv_desc(H, W);
@@ -416,6 +427,7 @@ struct Builder {
         d.alpha = 1.f;
         d.rows_per_image = 1;
         if (K % 64 || O % 8) fail("batched_emb_projection: K must be a multiple of 64 and O of 8");
+        if (Bn == 1 && O % 64 == 0) d.block_n = 64;  // one live row: more, narrower column tiles (same per-element accumulation order)
         gemm(d);
     }
     dxmi_gemm_desc conv_desc(int H, int W) {

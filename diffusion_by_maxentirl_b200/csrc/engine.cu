@@ -558,6 +558,8 @@ struct DdpmBuilder : Builder {
                 return (int)cudaGetLastError();
             },
                3);
+            // (uniform-t plans: one live row; a SIMT fp32 matrix-vector product is 0.1 ms per step faster still, but then `sample()` and a
+            //  loop of `sample_step()` - which cannot assume one timestep per batch - would no longer agree bit for bit)
             batched_emb_projection(temb, temb_ch, "temb_proj", wk, bk, tproj, TP, Bt);
         }
         // ---- conv_in
