@@ -36,7 +36,9 @@ def install(trainer_ops=False):
     checkout is on sys.path) to the B200 drop-ins, in place.  Everything else in the reference (trainer, CLIs, FID,
     loaders, `models.value.TimeIndependentValue`, ...) is left untouched and keeps calling the same names.
     trainer_ops=True additionally binds the fused trainer-side ops of SURVEY 8f rank 1 (`train_ops.py`):
-    `DxMI_Trainer{,_Cond}.get_running_cost` -> the fused forward/backward kernel, and `torch.optim.Adam` AS SEEN BY the
+    `DxMI_Trainer{,_Cond}.get_running_cost` -> the fused forward/backward kernel, `models.cm.fp16_util.MixedPrecisionTrainer`
+    -> the drop-in with device-side norm reductions (the reference's own class also works unchanged on the drop-in U-Net), and
+    `torch.optim.Adam` AS SEEN BY the
     reference's train scripts is left alone - pass `diffusion_by_maxentirl_b200.train_ops.FusedAdam` explicitly where the
     script builds its optimizers (train_cifar10.py:283-296) to get the multi-tensor clip + Adam step.
     Returns the list of rebound `module.attr` names."""
@@ -54,4 +56,10 @@ def install(trainer_ops=False):
             if hasattr(tr, cls):
                 setattr(getattr(tr, cls), "get_running_cost", train_ops.trainer_get_running_cost)
                 done.append(f"models.DxMI.trainer.{cls}.get_running_cost")
+        # EDM training: the same master-parameter / loss-scale contract with device-side norm reductions
+        from .models.cm import fp16_util as ours_fp16
+
+        ref_fp16 = importlib.import_module("models.cm.fp16_util")
+        ref_fp16.MixedPrecisionTrainer = ours_fp16.MixedPrecisionTrainer
+        done.append("models.cm.fp16_util.MixedPrecisionTrainer")
     return done

@@ -134,7 +134,7 @@ def test_install_rebinds_reference_symbols():
         "b2 = pkg.install(trainer_ops=True)\n"
         "import models.DxMI.trainer as tr\n"
         "from diffusion_by_maxentirl_b200 import train_ops\n"
-        "assert tr.DxMI_Trainer.get_running_cost is train_ops.trainer_get_running_cost and len(b2) == len(b) + 2\n"
+        "assert tr.DxMI_Trainer.get_running_cost is train_ops.trainer_get_running_cost and len(b2) == len(b) + 3\n"
         "print(len(b))\n" % (ref, ROOT)
     )
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
