@@ -6,7 +6,7 @@
 // operation is a read-once HBM stream: this kernel stages a (rows + 2) x (W + 2) x C halo tile of the input in shared memory ONCE,
 // keeps the 8 x 9C weights next to it, and contracts with warp-level mma.sync.m16n8k16 - the one place where the legacy tensor-core
 // instruction is the right tool: its N = 8 tile is exactly the (zero-padded) output width, there is no accumulator to drain and
-// no epilogue worth overlapping.  One CTA = 128 output pixels (TH full image rows), one warp = 32 pixels = two m16 tiles.
+// no epilogue worth overlapping.  One CTA = 128 output pixels (TH full image rows), one warp = 32 pixels = two m16 tiles (each inside one image row: 16 | W).
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 
@@ -60,9 +60,14 @@ __global__ void __launch_bounds__(128) conv3x3_last_k(const bf16* __restrict__ x
         *reinterpret_cast<uint4*>(sw + (size_t)co * KP + kv * 8) = *reinterpret_cast<const uint4*>(wp + (size_t)co * 9 * C + kv * 8);
     }
     __syncthreads();
-    // ---- this warp's 32 pixels: row ty of the tile, columns tx0 .. tx0 + 31
-    const int p0 = warp * 32;
-    const int ty = p0 / W, tx0 = p0 - ty * W;
+    // ---- this warp's 32 pixels = two m16 tiles; each m16 tile lies inside ONE image row (16 | W): tile m = row ty[m], columns tx[m] .. + 15
+    int ty[2], tx[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int pm = warp * 32 + m * 16;
+        ty[m] = pm / W;
+        tx[m] = pm - ty[m] * W;
+    }
     float acc[2][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
@@ -76,13 +81,14 @@ __global__ void __launch_bounds__(128) conv3x3_last_k(const bf16* __restrict__ x
     const int cblocks = C / 16;
     for (int tap = 0; tap < 9; ++tap) {
         const int ky = tap / 3, kx = tap - ky * 3;
-        const uint32_t a_base = st_addr + (uint32_t)((((ty + ky) * (W + 2) + tx0 + kx + a_row) * CP + a_k) * 2);
+        const uint32_t a_base0 = st_addr + (uint32_t)((((ty[0] + ky) * (W + 2) + tx[0] + kx + a_row) * CP + a_k) * 2);
+        const uint32_t a_base1 = st_addr + (uint32_t)((((ty[1] + ky) * (W + 2) + tx[1] + kx + a_row) * CP + a_k) * 2);
         const uint32_t b_base = sw_addr + (uint32_t)((b_row * KP + tap * C + b_k) * 2);
 #pragma unroll 4
         for (int cb = 0; cb < cblocks; ++cb) {
             uint32_t a0[4], a1[4], b[2];
-            ldmatrix_x4(a0, a_base + cb * 32);
-            ldmatrix_x4(a1, a_base + 16 * CP * 2 + cb * 32);
+            ldmatrix_x4(a0, a_base0 + cb * 32);
+            ldmatrix_x4(a1, a_base1 + cb * 32);
             ldmatrix_x2(b, b_base + cb * 32);
             mma_bf16_16816(acc[0], a0, b);
             mma_bf16_16816(acc[1], a1, b);
@@ -90,13 +96,13 @@ __global__ void __launch_bounds__(128) conv3x3_last_k(const bf16* __restrict__ x
     }
     // ---- D fragment: rows lane / 4 (+ 8), columns (lane % 4) * 2 + {0, 1} -> out[n][co][y][x]
     const int co0 = (lane & 3) * 2;
-    const int gy = y0 + ty;
     const long long HW = (long long)H * W;
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
+        const int gy = y0 + ty[m];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int gx = tx0 + m * 16 + (lane >> 2) + half * 8;
+            const int gx = tx[m] + (lane >> 2) + half * 8;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 const int co = co0 + j;
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(128) conv3x3_last_k(const bf16* __restrict__ x
 }
 
 bool conv3x3_last_supported(int H, int W, int C, int Cout) {
-    if (Cout > 8 || C % 16 || W > 128 || 128 % W || H % (128 / W)) return false;
+    if (Cout > 8 || C % 16 || W > 128 || W % 16 || 128 % W || H % (128 / W)) return false;
     const int TH = 128 / W;
     const size_t smem = ((size_t)(TH + 2) * (W + 2) * (C + 8) + (size_t)8 * (9 * C + 8)) * sizeof(bf16);
     return smem <= 200 * 1024;
