@@ -84,6 +84,7 @@ class GemmDesc(C.Structure):
         ("gn_halo_P", C.c_int),
         ("gate", C.c_void_p),
         ("ldg", C.c_int),
+        ("up2", C.c_int),
     ]
 
 
@@ -127,6 +128,7 @@ SYMBOLS = {
     "dxmi_value_backward": (_I, [_VP, _VP, _VP, _VP, _I, _VP]),
     "dxmi_op_gn_bwd_ws_floats": (_LL, [_I, _I, _I]),
     "dxmi_op_group_norm_bwd": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "dxmi_op_pack_conv_weight_up2": (_I, [_VP, _I, _I, _I, _VP, _VP]),
     "dxmi_op_pack_conv_weight_dgrad": (_I, [_VP, _I, _I, _I, _I, _VP, _LL, _LL, _VP]),
     "dxmi_op_wgrad_ws_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
     "dxmi_op_conv_wgrad": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _I, _I, _F, _VP, _VP]),

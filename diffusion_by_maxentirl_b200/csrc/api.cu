@@ -84,6 +84,10 @@ int dxmi_set_option(const char* name, int value) {
         set_pdl(value);
         return 0;
     }
+    if (!strcmp(name, "up2")) {  // read when a plan is built
+        set_up2(value);
+        return 0;
+    }
     if (!strcmp(name, "attnblk")) {  // read when a plan is built
         set_attnblk(value);
         return 0;
@@ -819,6 +823,12 @@ int dxmi_op_group_norm_bwd(const void* x1, int C1, const void* x2, int C2, const
     group_norm_bwd((const bf16*)x1, C1, (const bf16*)x2, C2, (const bf16*)dy, ab, mr, N, HW, groups, silu, ws, (bf16*)dx, dgamma, dbeta,
                    (cudaStream_t)stream);
     count_launches(3);
+    return (int)cudaGetLastError();
+}
+
+int dxmi_op_pack_conv_weight_up2(const void* w, int dtype, int Cout, int Cin, void* dst_bf16, dxmi_stream_t stream) {
+    pack_conv_weight_up2(w, dtype == DXMI_F16, Cout, Cin, (bf16*)dst_bf16, (cudaStream_t)stream);
+    count_launches(1);
     return (int)cudaGetLastError();
 }
 

@@ -13,6 +13,7 @@ namespace dxmi {
 int attnblk_option();   // engine.cu: 1 = DDPM AttnBlock at 16x16 as one fused kernel
 int stats16_option();   // engine.cu
 int conv_out_padded_option();
+int up2_option();        // engine.cu: 1 = Upsample + conv3x3 as four phase convolutions of the low-resolution tensor
 int gn_fused_option();  // engine.cu: 1 = every GroupNorm with producer statistics is ONE kernel (prologue + streaming apply)
 
 struct Builder {
@@ -86,6 +87,66 @@ struct Builder {
         }
         return a;
     }
+    // ---- nearest-2x upsample folded into the 3x3 convolution after it (gemm_tc.cuh ConvGemmParams::up2)
+    bool up2_ok(int C, int H, int W) const {
+        return up2_option() && !stats16_option() && C % 64 == 0 && (W & (W - 1)) == 0 && stats_seg(H * W) >= 32;
+    }
+    // partials per OUTPUT image the up2 GEMM writes: [4 phases][segments of the low-resolution image]
+    static int up2_stats_P(int H, int W) { return 4 * (H * W / stats_seg(H * W)); }
+    Act new_act_up2(int C, int H, int W) {
+        Act a;
+        a.p = act_alloc(C, 2 * H, 2 * W);
+        a.C = C;
+        a.H = 2 * H;
+        a.W = 2 * W;
+        a.has_stats = true;
+        a.stats_P = up2_stats_P(H, W);
+        a.stats_halo = false;
+        a.stats = (float*)alloc((size_t)B * a.stats_P * C * 2 * sizeof(float));
+        return a;
+    }
+    // out [B, 2H, 2W, Cout] = conv3x3(nearest_upsample2x(x [B, H, W, C])) + bias (+ per-image row vector); stats (optional): B * up2_stats_P partials
+    void conv_up2(const bf16* x, int C, int H, int W, const std::string& wkey, const std::string& bkey, int Cout, bf16* out, float* stats,
+                  const float* rowvec, int ldrv) {
+        bf16* wp = nullptr;
+        if (!dry) {
+            const Bound* b = get(wkey);
+            if (!b) return;
+            if (b->shape.size() != 4 || b->shape[0] != Cout || b->shape[1] != C || b->shape[2] != 3 || b->shape[3] != 3) {
+                fail("conv_up2: expected a [Cout, C, 3, 3] weight");
+                return;
+            }
+            bool fresh = false;
+            wp = (bf16*)derived_buf("wup2:" + wkey, (size_t)16 * Cout * C * sizeof(bf16), &fresh);
+            if (!wp) return;
+            if (fresh) {
+                Net* np = &net;
+                net.pack_jobs.push_back([np, wkey, Cout, C, wp](cudaStream_t st) {
+                    const Bound& bb = np->bound[wkey];
+                    pack_conv_weight_up2(bb.ptr, bb.dtype == DXMI_F16, Cout, C, wp, st);
+                    count_launches(1);
+                });
+            }
+        }
+        dxmi_gemm_desc d = conv_desc(H, W);
+        d.up2 = 1;
+        set_src(d, 0, x, C, C);
+        add_seg(d, 0, 4);
+        d.batch = 4;
+        d.b_batched = 1;
+        d.b_ptr = wp;
+        d.b_rows = Cout;
+        d.b_ld = 4LL * C;
+        d.b_batch_stride = (long long)Cout * 4 * C;
+        d.bias = f32(bkey);
+        d.rowvec = rowvec;
+        d.ldrv = ldrv;
+        d.out = out;
+        d.ldo = Cout;
+        d.gn_stats = stats;
+        gemm(d);
+    }
+
     static void want_stats(dxmi_gemm_desc& d, const Act& out) {
         d.gn_stats = out.stats;
         d.gn_halo_P = out.stats_halo ? out.stats_P : 0;

@@ -31,6 +31,9 @@ void set_attnblk(int v) { g_opt_attnblk = v; }
 static int g_opt_stats16 = 0;  // measured (round 2): 16-row direct partials save the 2nd epilogue barrier but cost more in the finalize: -1 % end to end
 int stats16_option() { return g_opt_stats16; }
 void set_stats16(int v) { g_opt_stats16 = v; }
+static int g_opt_up2 = 1;  // nearest-2x upsample + 3x3 conv as four 2x2 phase convolutions (builder.cuh conv_up2): 4/9 of the FLOPs, no upsampled tensor
+int up2_option() { return g_opt_up2; }
+void set_up2(int v) { g_opt_up2 = v; }
 static int g_opt_conv_out_padded = 1;  // Cout <= 4 output conv through the persistent kernel's halo mode (builder.cuh conv_out_nchw)
 int conv_out_padded_option() { return g_opt_conv_out_padded; }
 void set_conv_out_padded(int v) { g_opt_conv_out_padded = v; }
@@ -473,6 +476,11 @@ struct DdpmBuilder : Builder {
 
     Act upsample(const std::string& p, Act x) {
         const int C = x.C, H2 = x.H * 2, W2 = x.W * 2;
+        if (up2_ok(C, x.H, x.W)) {
+            Act out = new_act_up2(C, x.H, x.W);
+            conv_up2(x.p, C, x.H, x.W, p + ".conv.weight", p + ".conv.bias", C, out.p, out.stats, nullptr, 0);
+            return out;
+        }
         bf16* up = (bf16*)scratch(1, (size_t)B * H2 * W2 * C * 2);
         const bf16* xp = x.p;
         const int Bn = B, H = x.H, W = x.W;

@@ -116,6 +116,7 @@ int build_adm_train_plan(Net& net, Plan& plan);   // engine_train_adm.cu
 void set_gn_fused(int v);
 void set_stats16(int v);
 void set_conv_out_padded(int v);
+void set_up2(int v);
 void set_attnblk(int v);
 const char* engine_last_error();
 void engine_set_error(const char* fmt, ...);

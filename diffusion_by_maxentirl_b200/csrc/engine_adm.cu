@@ -87,6 +87,7 @@ struct AdmBuilder : Builder {
         int Ho = H, Wo = W;
         const bf16* conv_in = g1;
         Act xs = xa;  // skip-path input (resampled for up / down blocks)
+        const bool up2 = mode == L_UP && up2_ok(Cin, H, W);
         if (mode == L_DOWN || mode == L_UP) {
             if (xb.C) fail("ADM up/down ResBlock with a concatenated input is not a reference configuration");
             Ho = mode == L_DOWN ? H / 2 : H * 2;
@@ -100,6 +101,13 @@ struct AdmBuilder : Builder {
                     avgpool2(xap, xp, Bn, H, W, Cin, ACT_NONE, st);
                     return (int)cudaGetLastError();
                 }, 2);
+            } else if (up2) {
+                // in_layers conv = four phase convolutions straight from the low-resolution g1 (builder.cuh conv_up2); only the skip path
+                // still needs the upsampled x (the residual operand of the out_layers conv)
+                op([=](cudaStream_t st) {
+                    upsample2x(xap, xp, Bn, H, W, Cin, st);
+                    return (int)cudaGetLastError();
+                });
             } else {
                 op([=](cudaStream_t st) {
                     upsample2x(g1, gp, Bn, H, W, Cin, st);
@@ -111,9 +119,17 @@ struct AdmBuilder : Builder {
             xs = Act{xp, Cin, Ho, Wo};
         }
         bf16* h1 = (bf16*)scratch(1, (size_t)B * Ho * Wo * Cout * 2);
-        const StatSpec h1s = stat_spec(Cout, Ho, Wo, true);
+        StatSpec h1s = stat_spec(Cout, Ho, Wo, true);
+        if (up2) {
+            h1s.halo = false;
+            h1s.P = up2_stats_P(H, W);
+            h1s.bytes = (size_t)B * h1s.P * Cout * 2 * sizeof(float);
+        }
         float* h1_stats = h1s.P ? (float*)scratch(6, h1s.bytes) : nullptr;
-        {
+        if (up2) {
+            conv_up2(g1, Cin, H, W, p + ".in_layers.2.weight", p + ".in_layers.2.bias", Cout, h1, h1_stats,
+                     (!film_mode && film) ? film + film_off : nullptr, film_ld);
+        } else {
             dxmi_gemm_desc d = conv_desc(Ho, Wo);
             set_src(d, 0, conv_in, Cin, Cin);
             add_seg(d, 0, 9);

@@ -124,7 +124,9 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
             img = (use_rv && !((p.rows_per_image & 127) == 0)) ? r32 / p.rows_per_image : 0;
         }
         rok[i] = ok && p.dbg_mode != 2;
-        ooff[i] = batch * p.out_batch_stride + r * p.ldo;
+        // up2 mode: tile row (n, y, x) of phase `batch` = (py, px) -> output pixel (n, 2y + py, 2x + px) = 4 r - 2 x + py 2W + px
+        const long long r_out = p.up2 ? 4 * r - 2 * (r & p.up2_wmask) + (batch >> 1) * p.up2_w2 + (batch & 1) : r;
+        ooff[i] = batch * p.out_batch_stride + r_out * p.ldo;
         roff[i] = use_res ? batch * p.res_batch_stride + r * p.ldr : 0;
         goff[i] = g_gate ? r * p.ldg : 0;
         rvp[i] = (use_rv && rok[i]) ? p.rowvec + img * p.ldrv : nullptr;
@@ -458,7 +460,7 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
 __device__ __forceinline__ bool epi_stats_published(const ConvGemmParams& p) {
     return p.stats != nullptr && !p.out_fp32 && (p.halo || p.stats_seg != 16);
 }
-__device__ __forceinline__ void epi_publish_tile(const ConvGemmParams& p, const float* sstf, int m_tile, int col0, int nch, int lane) {
+__device__ __forceinline__ void epi_publish_tile(const ConvGemmParams& p, const float* sstf, int m_tile, int col0, int nch, int lane, int batch = 0) {
     const int row0 = m_tile * TILE_M;
     const int n_total = p.N_total;
     const int stat_seg = !p.halo ? p.stats_seg : 128;
@@ -493,8 +495,14 @@ __device__ __forceinline__ void epi_publish_tile(const ConvGemmParams& p, const 
 #pragma unroll
                 for (int b2 = 0; b2 < 4; ++b2) {
                     const int srow = row0 + (b2 + 1 - bps) * 32;  // first row of the segment that ends with block b2
-                    if (((b2 + 1) & (bps - 1)) == 0 && srow < p.M_total)
-                        *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(srow >> stat_shift) * n_total + col) * 2) = seg[b2];
+                    if (((b2 + 1) & (bps - 1)) == 0 && srow < p.M_total) {
+                        int sidx = srow >> stat_shift;
+                        if (p.up2) {  // partials of one OUTPUT image stay contiguous: [image][phase][segment of the low-resolution image]
+                            const int img = sidx / p.up2_spi;
+                            sidx = (img * 4 + batch) * p.up2_spi + (sidx - img * p.up2_spi);
+                        }
+                        *reinterpret_cast<float2*>(p.stats + (static_cast<long long>(sidx) * n_total + col) * 2) = seg[b2];
+                    }
                 }
             }
         }

@@ -79,12 +79,25 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
         m_tiles = n_blks * p.tiles_w * p.tiles_h;
         p.M_total = d.N * d.out_H * d.out_W;
     }
+    if (d.up2) {
+        // nearest-2x upsample + 3x3 conv as four 2x2 phase convolutions of the low-resolution input (see ConvGemmParams::up2)
+        const bool ok = d.nseg == 1 && d.seg_taps[0] == 4 && p.stride == 1 && !d.a_batched && d.b_batched && d.batch == 4 && d.out_H == d.H &&
+                        d.out_W == d.W && (d.W & (d.W - 1)) == 0 && !d.residual && !d.gate && !d.softmax && !d.out_fp32 &&
+                        !d.out_nchw && !d.bias_along_m && d.out_batch_stride == 0 && !(d.gn_stats && d.gn_seg == 16) && d.gn_halo_P == 0;
+        if (!ok) {
+            snprintf(g_op_err, sizeof g_op_err, "up2 mode: one 4-tap segment, batch = 4 phases with batched weights, bias-only bf16 epilogue, power-of-two width");
+            return -16;
+        }
+        p.up2 = 1;
+        p.up2_wmask = d.W - 1;
+        p.up2_w2 = 2 * d.W;
+    }
     long long k_total = 0;
     p.nseg = d.nseg;
     bool used[3] = {false, false, false};
     for (int s = 0; s < d.nseg; ++s) {
         const int src = d.seg_src[s];
-        if (src < 0 || src > 2 || d.a_C[src] % 64 != 0 || (d.seg_taps[s] != 1 && d.seg_taps[s] != 9)) {
+        if (src < 0 || src > 2 || d.a_C[src] % 64 != 0 || (d.seg_taps[s] != 1 && d.seg_taps[s] != 9 && !(d.up2 && d.seg_taps[s] == 4))) {
             snprintf(g_op_err, sizeof g_op_err, "bad K segment %d (src %d, C %d, taps %d): channels must be a multiple of 64",
                      s, src, src >= 0 && src <= 2 ? d.a_C[src] : -1, d.seg_taps[s]);
             return -11;
@@ -92,7 +105,7 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
         p.seg[s].map = src;
         p.seg[s].ntaps = d.seg_taps[s];
         p.seg[s].nchunks = d.a_C[src] / 64;
-        p.seg[s].pad = (d.seg_taps[s] == 9 && p.stride == 1) ? 1 : 0;
+        p.seg[s].pad = ((d.seg_taps[s] == 9 && p.stride == 1) || d.seg_taps[s] == 4) ? 1 : 0;
         k_total += (long long)d.seg_taps[s] * d.a_C[src];
         used[src] = true;
     }
@@ -227,6 +240,13 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
         }
         p.stats = p.softmax ? nullptr : d.gn_stats;
         p.stats_seg = d.gn_seg;
+        if (p.up2 && p.stats) {
+            if (d.gn_seg <= 0 || (d.H * d.W) % d.gn_seg) {
+                snprintf(g_op_err, sizeof g_op_err, "up2 mode: gn_seg must divide the rows of one low-resolution image");
+                return -17;
+            }
+            p.up2_spi = d.H * d.W / d.gn_seg;
+        }
         if (p.stats && (p.stats_seg != 16 && p.stats_seg != 32 && p.stats_seg != 64 && p.stats_seg != 128)) {
             snprintf(g_op_err, sizeof g_op_err, "gn_seg must be 16, 32, 64 or 128");
             return -13;
@@ -274,6 +294,9 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
                 }
             }
         }
+    } else if (d.up2) {
+        snprintf(g_op_err, sizeof g_op_err, "up2 mode needs the persistent kernels");
+        return -18;
     } else if (d.gn_stats || d.gate) {
         snprintf(g_op_err, sizeof g_op_err, "gn_stats / gate requested but the persistent kernel does not support this GEMM");
         return -12;

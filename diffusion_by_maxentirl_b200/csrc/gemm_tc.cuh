@@ -43,7 +43,7 @@ void set_pdl(int v);
 
 struct GemmSeg {
     int map;      // index into a_map[]
-    int ntaps;    // 1 or 9
+    int ntaps;    // 1, 9 or 4 (up2 mode: 2x2)
     int nchunks;  // channels / 64
     int pad;      // 1 for 3x3 "same", 0 otherwise
 };
@@ -103,6 +103,14 @@ struct ConvGemmParams {
     int s3_stages;             // ring depth in this mode
     int s3_m2;                 // 1: each CTA owns TWO vertically adjacent 128-row tiles per step (one A box of 2*bh+2 rows, the B tiles shared)
     CUtensorMap s3_map[3];     // per source: (c, w, h, n) map with box (64, W, bh+2, 1)
+    // up2 mode (nearest-2x upsample folded into the following 3x3 convolution, unet_small.py:52-64, cm/unet.py:103-118): the four output
+    // phases (py, px) = (Y & 1, X & 1) are four 2x2 convolutions of the LOW-resolution input with pre-summed weights (4/9 of the
+    // FLOPs, no upsampled tensor).  The launch's batch index is the phase: B operand batched, A taps (r, q) in {0,1}^2 read the box
+    // shifted by (r - 1 + py, q - 1 + px), tile row r = (n, y, x) is stored at output pixel (n, 2y + py, 2x + px).
+    int up2;                   // 0 = off
+    int up2_wmask;             // W - 1 (W = low-resolution width, a power of two)
+    int up2_w2;                // 2 * W: output-row offset of phase row py
+    int up2_spi;               // GroupNorm partial segments per low-resolution image (rows_per_image / stats_seg)
     float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/stats_seg][N_total][2] (sum, sumsq) or null
     int stats_seg;             // rows per partial: 32, 64 or 128 (a segment never straddles two images)
     long long* dbg_times;      // profiling only: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA, or null

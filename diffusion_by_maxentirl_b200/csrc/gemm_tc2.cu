@@ -169,18 +169,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                     // K order of a 3x3 segment: channel chunk, then column shift q, then row shift r - the SAME order as the pair
                     // kernel's shift-3 mode, so every kernel variant accumulates identically (bitwise batch invariance: which
                     // variant runs depends on the batch size)
-                    const int nq = sg.ntaps == 9 ? 3 : 1;
+                    const int nq = sg.ntaps == 9 ? 3 : (sg.ntaps == 4 ? 2 : 1);
+                    // up2 mode: the batch index is the output phase (py, px); its 2x2 taps start at (py - 1, px - 1)
+                    const int upx = p.up2 ? (batch & 1) : 0, upy = p.up2 ? (batch >> 1) : 0;
                     for (int ch = 0; ch < sg.nchunks; ++ch) {
                         for (int q = 0; q < nq; ++q) {
                             for (int r = 0; r < nq; ++r, ++it) {
-                                const int kk = kbase + (r * 3 + q) * sg.nchunks + ch;
+                                const int kk = kbase + (r * nq + q) * sg.nchunks + ch;
                                 const uint32_t stage = it % STAGES;
                                 const uint32_t ph = (it / STAGES) & 1;
                                 ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
                                 uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                                 uint8_t* sb = sa + A_STAGE_BYTES;
                                 ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                                ptx::tma_load_4d(sa, amap, &full_bar[stage], ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
+                                ptx::tma_load_4d(sa, amap, &full_bar[stage], ch * TILE_K, w0 + q - sg.pad + upx, h0 + r - sg.pad + upy, n0);
                                 ptx::tma_load_3d(sb, &p.b_map, &full_bar[stage], kk * TILE_K, bcoord_n, bcoord_b);
                             }
                         }
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                 const int col0 = (t % p.n_tiles) * BLOCK_N;
                 int ncols = p.N_total - col0;
                 if (ncols > BLOCK_N) ncols = BLOCK_N;
-                epi_publish_tile(p, sstf, m_tile, col0, (ncols + 31) / 32, lane);
+                epi_publish_tile(p, sstf, m_tile, col0, (ncols + 31) / 32, lane, (t / p.n_tiles) / p.m_tiles);
             }
         }
     }

@@ -248,11 +248,13 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                     const GemmSeg sg = p.seg[s];
                     const CUtensorMap* amap = &p.a_map[sg.map];
                     // K order of a 3x3 segment: chunk, column shift q, row shift r (same as the shift-3 mode above and as gemm_tc2.cu)
-                    const int nq = sg.ntaps == 9 ? 3 : 1;
+                    const int nq = sg.ntaps == 9 ? 3 : (sg.ntaps == 4 ? 2 : 1);
+                    // up2 mode: the batch index is the output phase (py, px); its 2x2 taps start at (py - 1, px - 1)
+                    const int upx = p.up2 ? (batch & 1) : 0, upy = p.up2 ? (batch >> 1) : 0;
                     for (int ch = 0; ch < sg.nchunks; ++ch) {
                         for (int q = 0; q < nq; ++q) {
                             for (int r = 0; r < nq; ++r, ++it) {
-                                const int kx = kk + (r * 3 + q) * sg.nchunks + ch;
+                                const int kx = kk + (r * nq + q) * sg.nchunks + ch;
                                 const uint32_t stage = it % STAGES;
                                 const uint32_t ph = (it / STAGES) & 1;
                                 ptx::mbar_wait(&empty_bar[stage], ph ^ 1);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                                 } else {
                                     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(full_leader) : "memory");
                                 }
-                                tma2_load_4d(sa, amap, full_leader, ch * TILE_K, w0 + q - sg.pad, h0 + r - sg.pad, n0);
+                                tma2_load_4d(sa, amap, full_leader, ch * TILE_K, w0 + q - sg.pad + upx, h0 + r - sg.pad + upy, n0);
                                 if (!RESB) tma2_load_3d(sb, &p.b_map, full_leader, kx * TILE_K, bcoord_n, bcoord_b);
                             }
                         }
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 const int col0 = (tp % p.n_tiles) * BLOCK_N;
                 int ncols = p.N_total - col0;
                 if (ncols > BLOCK_N) ncols = BLOCK_N;
-                for (int h = 0; h < msub; ++h) epi_publish_tile(p, sstf, m_tile0 + h, col0, (ncols + 31) / 32, lane);
+                for (int h = 0; h < msub; ++h) epi_publish_tile(p, sstf, m_tile0 + h, col0, (ncols + 31) / 32, lane, mp / m_pairs);
             }
         }
     }

@@ -117,6 +117,38 @@ void pack_conv_weight(const void* w, int w_is_half, int Cout, int Cin, int kh, i
         pack_conv_weight_k<float><<<blocks, 256, 0, st>>>((const float*)w, Cout, Cin, kh * kw, c_off, c_cnt, dst, ldk, k_off);
 }
 
+// nearest-2x upsample + 3x3 conv = four 2x2 phase convolutions of the low-resolution input: output row Y = 2y + py reads upsampled rows
+// Y - 1 .. Y + 1 = low-resolution rows {y - 1, y, y} (py = 0) or {y, y, y + 1} (py = 1), so tap dy of phase py sums kernel rows
+// ky in {0} | {1, 2} (py = 0) or {0, 1} | {2} (py = 1); columns likewise.  Sums in fp32, one bf16 rounding.
+template <typename T>
+__global__ void pack_conv_weight_up2_k(const T* __restrict__ w, int Cout, int Cin, bf16* __restrict__ dst) {
+    const long long total = 4LL * Cout * 4 * Cin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cin);
+        long long r = i / Cin;
+        const int tap = (int)(r & 3);
+        r >>= 2;
+        const int o = (int)(r % Cout);
+        const int phase = (int)(r / Cout);
+        const int py = phase >> 1, px = phase & 1, dy = tap >> 1, dx = tap & 1;
+        const int ky0 = py == 0 ? (dy == 0 ? 0 : 1) : (dy == 0 ? 0 : 2), ky1 = py == 0 ? (dy == 0 ? 0 : 2) : (dy == 0 ? 1 : 2);
+        const int kx0 = px == 0 ? (dx == 0 ? 0 : 1) : (dx == 0 ? 0 : 2), kx1 = px == 0 ? (dx == 0 ? 0 : 2) : (dx == 0 ? 1 : 2);
+        const T* wp = w + ((long long)o * Cin + c) * 9;
+        float v = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) v += (float)wp[ky * 3 + kx];
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+void pack_conv_weight_up2(const void* w, int w_is_half, int Cout, int Cin, bf16* dst, cudaStream_t st) {
+    const long long total = 16LL * Cout * Cin;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    if (w_is_half)
+        pack_conv_weight_up2_k<__half><<<blocks, 256, 0, st>>>((const __half*)w, Cout, Cin, dst);
+    else
+        pack_conv_weight_up2_k<float><<<blocks, 256, 0, st>>>((const float*)w, Cout, Cin, dst);
+}
+
 // transposed + tap-flipped packing for the data gradient: dX = conv(dY, W') with W'[ci][tap'][co] = W[co][ci][taps-1-tap']
 template <typename T>
 __global__ void pack_conv_weight_dgrad_k(const T* __restrict__ w, int Cout, int Cin, int taps, bf16* __restrict__ dst,

@@ -19,6 +19,8 @@ void pack_conv_weight(const void* w, int w_is_half, int Cout, int Cin, int kh, i
 // dX = the forward implicit-GEMM convolution of dY with these rows (3x3 pad 1 stride 1, or 1x1)
 void pack_conv_weight_dgrad(const void* w, int w_is_half, int Cout, int Cin, int taps, bf16* dst, long long ldk, long long k_off,
                             cudaStream_t st);
+// OIHW 3x3 weight -> bf16 [4 phases][Cout][4 taps * Cin]: the pre-summed 2x2 filters of conv3x3(nearest_upsample2x(.)) (ConvGemmParams::up2)
+void pack_conv_weight_up2(const void* w, int w_is_half, int Cout, int Cin, bf16* dst, cudaStream_t st);
 void cast_to_f32(const void* src, int src_is_half, float* dst, long long n, cudaStream_t st);
 
 // ---- first / last convolutions (3 <-> C channels; HBM bound) -------------------------------------------------------

@@ -33,6 +33,26 @@ def pack_conv_weight(w, parts=None):
     return dst
 
 
+def pack_conv_weight_up2(w):
+    """OIHW 3x3 weight -> bf16 [4, Cout, 4*Cin]: the four pre-summed 2x2 phase filters of conv3x3(nearest_upsample2x(x))."""
+    w = w.contiguous()
+    assert w.dim() == 4 and w.shape[2] == w.shape[3] == 3 and w.dtype in (torch.float16, torch.float32)
+    dst = torch.empty(4, w.shape[0], 4 * w.shape[1], dtype=torch.bfloat16, device=w.device)
+    dt = L.F16 if w.dtype == torch.float16 else L.F32
+    L.check(L.lib().dxmi_op_pack_conv_weight_up2(L.ptr(w), dt, w.shape[0], w.shape[1], L.ptr(dst), L.stream_ptr()), "pack_conv_weight_up2")
+    return dst
+
+
+def conv_up2(x, w_up2, bias=None, rowvec=None, gn_stats=None, gn_seg=32, block_n=0):
+    """conv3x3(nearest_upsample2x(x)) as four phase convolutions: x NHWC bf16 [N,H,W,C] -> NHWC bf16 [N,2H,2W,Cout]."""
+    N, H, W, Cin = x.shape
+    Cout = w_up2.shape[1]
+    out = torch.empty(N, 2 * H, 2 * W, Cout, dtype=torch.bfloat16, device=x.device)
+    conv_gemm([(x, Cin, Cin)], [(0, 4)], w_up2, N, H, W, bias=bias, rowvec=rowvec, out=out, batch=4, b_batched=True,
+              b_batch_stride=Cout * 4 * Cin, gn_stats=gn_stats, gn_seg=gn_seg, block_n=block_n, up2=True)
+    return out
+
+
 def conv_gemm(
     srcs,
     segs,
@@ -67,6 +87,7 @@ def conv_gemm(
     gn_seg=32,
     gn_halo_P=0,
     gate=None,
+    up2=False,
 ):
     """srcs: list of (tensor, C_used, ld) NHWC bf16 sources; segs: list of (src_index, taps)."""
     d = L.GemmDesc()
@@ -118,6 +139,7 @@ def conv_gemm(
     d.alpha = alpha
     d.softmax = int(softmax)
     d.block_n = block_n
+    d.up2 = int(up2)
     if gn_stats is not None:
         assert gn_stats.dtype == torch.float32
         d.gn_stats = gn_stats.data_ptr()

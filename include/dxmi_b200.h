@@ -185,11 +185,19 @@ typedef struct {
     const void* gate;        /* optional bf16 [rows, ldg]: out *= (gate > 0 ? 1 : 0.2) after everything else - the backward of
                                 leaky-relu(0.2) through the saved activation (modules.py:81,99 under autograd) */
     int ldg;
+    int up2;                 /* 1: nearest-2x upsample folded into the 3x3 convolution that follows it (unet_small.py:52-64 Upsample,
+                                cm/unet.py:103-118, ResBlock up=True :186-199) as four 2x2 phase convolutions of the LOW-resolution
+                                input: N/H/W/out_H/out_W = the low-resolution geometry, one 4-tap segment, batch = 4 (phase = py*2+px),
+                                b_ptr = dxmi_op_pack_conv_weight_up2 rows [4][b_rows][4*C] with b_batched = 1; `out` is the
+                                [N, 2H, 2W, ldo] tensor; gn_stats partials are [N][4][H*W/gn_seg][b_rows][2] */
 } dxmi_gemm_desc;
 
 int dxmi_op_conv_gemm(const dxmi_gemm_desc* d, dxmi_stream_t stream);
 int dxmi_op_pack_conv_weight(const void* w, int dtype, int Cout, int Cin, int kh, int kw, int c_off, int c_cnt,
                              void* dst_bf16, long long ldk, long long k_off, dxmi_stream_t stream);
+/* OIHW 3x3 weight -> the four pre-summed 2x2 phase filters of conv3x3(nearest_upsample2x(x)): bf16 [4][Cout][4*Cin], phase =
+ * py*2+px, k = (dy*2+dx)*Cin + c; rows ky in {0},{1,2} (py = 0) or {0,1},{2} (py = 1) are summed in fp32, likewise columns. */
+int dxmi_op_pack_conv_weight_up2(const void* w, int dtype, int Cout, int Cin, void* dst_bf16, dxmi_stream_t stream);
 int dxmi_op_group_norm(const void* x1, int C1, int ld1, const void* x2, int C2, int ld2, int N, int HW, int groups,
                        float eps, const float* gamma, const float* beta, const float* film, int film_ld, int silu,
                        float* partial_ws, void* out, dxmi_stream_t stream);

@@ -244,6 +244,59 @@ def test_fused_groupnorm_partials(ops, N, H, Cin, Cout):
         assert torch.allclose(stats[..., 1], (yf * yf).sum(1), rtol=1e-4, atol=2e-3), seg
 
 
+@pytest.mark.parametrize("N,H,Cin,Cout,bn", [(40, 16, 256, 256, 0), (5, 8, 256, 256, 0), (3, 16, 128, 192, 0), (70, 8, 64, 128, 0), (4, 32, 192, 192, 0),
+                                              (40, 16, 256, 256, 128)])
+def test_up2_phase_convolution(ops, N, H, Cin, Cout, bn):
+    """Nearest-2x upsample + 3x3 conv (unet_small.py:52-64; cm/unet.py:103-118, :186-199) as four 2x2 phase convolutions of the
+    low-resolution tensor with pre-summed weights (up2 mode): against torch on the upsampled tensor; packed phase filters
+    against their closed form; the GroupNorm partials [image][phase][segment] against the stored bf16 outputs; with and
+    without the per-image row vector; pair and one-CTA kernels (ragged batch of 8x8 tiles: two images per tile)."""
+    torch.manual_seed(21)
+    dev = "cuda"
+    x = nhwc(torch.randn(N, Cin, H, H, device=dev))
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) / (3 * Cin**0.5)
+    b = torch.randn(Cout, device=dev)
+    rowvec = torch.randn(N, Cout, device=dev)
+    wp = ops.pack_conv_weight_up2(w)
+    # closed form of the phase filters: rows {0},{1,2} (py = 0) / {0,1},{2} (py = 1), columns likewise
+    sel = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    for py in (0, 1):
+        for px in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    ref_w = w[:, :, sel[py][dy], :][:, :, :, sel[px][dx]].sum((2, 3))
+                    got = wp[py * 2 + px].view(Cout, 4, Cin)[:, dy * 2 + dx].float()
+                    # (fp32 sums in another order may round to the neighbouring bf16 value)
+                    assert torch.allclose(got, ref_w, rtol=2.0**-7, atol=1e-6), (py, px, dy, dx)
+                    assert (got == ref_w.to(torch.bfloat16).float()).float().mean() > 0.99
+    xu = x.permute(0, 3, 1, 2).float()
+    xu = F.interpolate(xu, scale_factor=2, mode="nearest")
+    ref = F.conv2d(xu, w, b, padding=1).permute(0, 2, 3, 1)
+    seg = 128 if (H * H) % 128 == 0 else 64
+    P = 4 * (H * H // seg)
+    stats = torch.full((N, P, Cout, 2), float("nan"), device=dev)
+    y = ops.conv_up2(x, wp, bias=b, gn_stats=stats, gn_seg=seg, block_n=bn)
+    torch.cuda.synchronize()
+    assert y.shape == (N, 2 * H, 2 * H, Cout)
+    assert rel_l2(y, ref) < 6e-3, rel_l2(y, ref)
+    # the same contraction with the bf16 phase filters in torch: only accumulation order differs
+    yf = y.float()
+    for py in (0, 1):
+        for px in (0, 1):
+            wq = wp[py * 2 + px].view(Cout, 2, 2, Cin).permute(0, 3, 1, 2).float()
+            xp = F.pad(x.permute(0, 3, 1, 2).float(), (1 - px, px, 1 - py, py))
+            rp = F.conv2d(xp, wq, b).permute(0, 2, 3, 1)
+            assert rel_l2(yf[:, py::2, px::2], rp) < 4e-3, (py, px)
+    assert torch.isfinite(stats).all()
+    s = stats.view(N, 4, P // 4, Cout, 2)
+    for ph in range(4):
+        yp = yf[:, ph >> 1::2, ph & 1::2].reshape(N, P // 4, seg, Cout)
+        assert torch.allclose(s[:, ph, :, :, 0], yp.sum(2), rtol=1e-4, atol=2e-3), ph
+        assert torch.allclose(s[:, ph, :, :, 1], (yp * yp).sum(2), rtol=1e-4, atol=2e-3), ph
+    y2 = ops.conv_up2(x, wp, bias=b, rowvec=rowvec, block_n=bn)
+    assert rel_l2(y2, ref + rowvec[:, None, None, :]) < 6e-3
+
+
 @pytest.mark.parametrize("N,H,Ca,Cb,Co", [(3, 32, 128, 64, 128), (2, 64, 192, 192, 192), (5, 32, 256, 0, 256)])
 def test_halo_conv_fused_shortcut_residual(ops, N, H, Ca, Cb, Co):
     """Halo-tile 3x3 conv (one TMA load per channel chunk serves all 9 taps) + centre-tap 1x1 segments over two more
