@@ -5,17 +5,23 @@
 //   grid = (seq / 128, heads, batch); one CTA owns 128 query rows of one (image, head) and streams the keys in
 //   tiles of 128:   S = Q K^T  (tcgen05, M=128 N=128 K=64, fp32 in TMEM)
 //                   P = exp2(S * scale*log2e - m)   (4 softmax warps: thread <-> query row <-> TMEM lane)
-//                   O_tile = P V  (tcgen05, M=128 N=64 K=128; P staged bf16 in smem in the SWIZZLE_128B K-major
-//                   layout a TMA load would have produced; V^T comes from the [C, seq] "value-transposed" GEMM)
-//   and the running (m, l, O) online-softmax state lives in registers (O_tile is read back from TMEM per key tile,
-//   so no TMEM read-modify-write is needed).
+//                   O += P V  (tcgen05, M=128 N=64 K=128, accumulated IN TMEM over all key tiles; P staged bf16 in smem in the
+//                   SWIZZLE_128B K-major layout a TMA load would have produced)
 //
 // Warp roles (192 threads): warps 0-3 softmax + output, warp 4 TMA producer, warp 5 TMEM allocator + MMA issuer.
-// K/V tiles are double buffered; S_{j+1} is issued right behind P V_j so the tensor pipe works while the softmax
-// warps fold O_j into their registers.
-// (Round 2, measured negative: 8 softmax warps - two per TMEM lane quarter, each half of the key columns, row max exchanged
-//  through shared memory - ran seq 1024 at 343 us instead of 239 us: the per-tile chain softmax -> P V -> fold is bound by its
-//  synchronisation latencies, not by issue slots; the fix is S double-buffering with two query tiles in flight, not more warps.)
+// Round-2 rework of the per-tile chain (the first version ran seq 1024 at 0.43 PFLOP/s: its softmax threads read S twice from TMEM
+// - a max pass and an exp pass -, waited for P V, read O back and folded it into 64 registers, every tile, all on one serial chain):
+//   * the whole S row (128 fp32) is loaded ONCE into registers - O lives in TMEM now, which frees the registers for it - by four
+//     asynchronous tcgen05.ld and one wait; the thread then releases the S buffer (barrier s_free) BEFORE it computes anything, so
+//     the MMA warp issues S_{j+1} = Q K_{j+1}^T while the exponentials of tile j are still being evaluated;
+//   * lazy rescaling (as in FlashAttention-4): the reference point m of the exponent only moves when the row maximum grew by
+//     more than 2^8 since it was last set (warp-uniform decision), so O (in TMEM) and l are rescaled - a tcgen05.ld / .st round
+//     trip - a handful of times per row instead of once per tile; P <= 256 keeps full bf16 relative precision, the final
+//     O / l is exact;
+//   * P V_j only has to be finished before P_{j+1} is WRITTEN (one tile later), so it overlaps the next tile's load + max.
+// K/V tiles are double buffered.
+// (Round 2, measured negative on the first version: 8 softmax warps - two per TMEM lane quarter - ran seq 1024 at 343 us instead of
+//  239 us: the chain was bound by its synchronisation latencies, not by issue slots.)
 #include "attn_tc.cuh"
 #include "ptx.cuh"
 
@@ -40,21 +46,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
+// KT = keys per tile: 128, or 64 for seq == 64 (compile time: with a run-time tile width the unrolled softmax loops degenerate into
+// one branch + one exposed MUFU latency per pair of exponentials - 4800 instead of ~1100 cycles per tile, measured with clock64)
+template <int KT>
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // barriers live behind the tiles inside the dynamic allocation (no static smem: two CTAs must fit one SM)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    // K and V stages are released separately: a K tile is dead as soon as S_j = Q K_j^T retired, a whole softmax earlier than its V
+    // tile (after P V_j) - so K_{j+2} is requested two tiles ahead although each operand has only two stages
     uint64_t& q_full = bars[0];
-    uint64_t* kv_full = bars + 1;
-    uint64_t* kv_empty = bars + 3;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = bars + 3;
     uint64_t& s_full = bars[5];
     uint64_t& p_full = bars[6];
-    uint64_t& o_full = bars[7];
-    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t& o_full = bars[7];   // P V_j retired (its P tile and the O accumulator may be touched)
+    uint64_t& s_free = bars[8];   // every softmax thread holds its S row in registers: the S accumulator may be overwritten
+    uint64_t* v_full = bars + 9;
+    uint64_t* v_empty = bars + 11;
+    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tile = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-    const int kt = p.seq < ATT_TILE ? p.seq : ATT_TILE;  // keys per tile: 64 or 128
+    constexpr int kt = KT;  // keys per tile: 64 or 128
     const int n_tiles = p.seq / kt;
 
     if (threadIdx.x == 0) {
@@ -66,12 +80,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
         ptx::prefetch_tmap(&p.vt_map);
         ptx::mbar_init(&q_full, 1);
         for (int s = 0; s < 2; ++s) {
-            ptx::mbar_init(&kv_full[s], 1);
-            ptx::mbar_init(&kv_empty[s], 1);
+            ptx::mbar_init(&k_full[s], 1);
+            ptx::mbar_init(&k_empty[s], 1);
+            ptx::mbar_init(&v_full[s], 1);
+            ptx::mbar_init(&v_empty[s], 1);
         }
         ptx::mbar_init(&s_full, 1);
         ptx::mbar_init(&p_full, 128);
         ptx::mbar_init(&o_full, 1);
+        ptx::mbar_init(&s_free, 128);
         ptx::fence_mbar_init();
     }
     if (warp == 5) ptx::tmem_alloc(&tmem_slot, TM_COLS);
@@ -85,46 +102,63 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
         if (ptx::elect_one()) {
             ptx::mbar_expect_tx(&q_full, 16 * 1024);
             ptx::tma_load_3d(smem + SM_Q, &p.qk_map, &q_full, p.q_col0 + head * ATT_D, q_tile * ATT_TILE, b);
-            for (int j = 0; j < n_tiles; ++j) {
+            auto load_k = [&](int j) {
                 const int s = j & 1;
-                ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                ptx::mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+                ptx::mbar_expect_tx(&k_full[s], 16 * 1024);  // (the whole 128-row box counts, rows past seq = 64 are zero-filled)
+                ptx::tma_load_3d(smem + SM_K + s * 16384, &p.qk_map, &k_full[s], p.k_col0 + head * ATT_D, j * kt, b);
+            };
+            auto load_v = [&](int j) {
+                const int s = j & 1;
+                ptx::mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
+                ptx::mbar_expect_tx(&v_full[s], (p.v_col0 >= 0 || kt == ATT_TILE) ? 16 * 1024 : 8 * 1024);
                 if (p.v_col0 >= 0) {
                     // V straight from the fused q|k|v projection: [keys][64 d] rows of 128 bytes (MN-major B operand of P.V)
-                    ptx::mbar_expect_tx(&kv_full[s], 32 * 1024);
-                    ptx::tma_load_3d(smem + SM_K + s * 16384, &p.qk_map, &kv_full[s], p.k_col0 + head * ATT_D, j * kt, b);
-                    ptx::tma_load_3d(smem + SM_V + s * 16384, &p.qk_map, &kv_full[s], p.v_col0 + head * ATT_D, j * kt, b);
-                    continue;
+                    ptx::tma_load_3d(smem + SM_V + s * 16384, &p.qk_map, &v_full[s], p.v_col0 + head * ATT_D, j * kt, b);
+                } else {
+                    ptx::tma_load_3d(smem + SM_V + s * 16384, &p.vt_map, &v_full[s], j * kt, head * ATT_D, b);
+                    if (kt == ATT_TILE)
+                        ptx::tma_load_3d(smem + SM_V + s * 16384 + 8192, &p.vt_map, &v_full[s], j * kt + 64, head * ATT_D, b);
                 }
-                ptx::mbar_expect_tx(&kv_full[s], kt == ATT_TILE ? 32 * 1024 : 24 * 1024);
-                ptx::tma_load_3d(smem + SM_K + s * 16384, &p.qk_map, &kv_full[s], p.k_col0 + head * ATT_D, j * kt, b);
-                ptx::tma_load_3d(smem + SM_V + s * 16384, &p.vt_map, &kv_full[s], j * kt, head * ATT_D, b);
-                if (kt == ATT_TILE)
-                    ptx::tma_load_3d(smem + SM_V + s * 16384 + 8192, &p.vt_map, &kv_full[s], j * kt + 64, head * ATT_D, b);
+            };
+            // issue order = the order in which the stages come free: K runs one tile ahead of V
+            load_k(0);
+            for (int j = 0; j < n_tiles; ++j) {
+                if (j + 1 < n_tiles) load_k(j + 1);
+                load_v(j);
             }
         }
         __syncwarp();
     } else if (warp == 5) {
         // ------------------------------------------------------------------ MMA issuer
         if (ptx::elect_one()) {
-            const uint32_t idesc_s = ptx::make_idesc(1, 128, kt);
+            constexpr uint32_t idesc_s = ptx::make_idesc(1, 128, kt);
             constexpr uint32_t idesc_o = ptx::make_idesc(1, 128, 64);
-            const int pv_steps = kt / 16;
+            constexpr int pv_steps = kt / 16;
             const uint64_t dq = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + SM_Q));
             const uint32_t sp = ptx::smem_u32(smem + SM_P);
             auto issue_s = [&](int j) {
                 const int s = j & 1;
-                ptx::mbar_wait(&kv_full[s], (j >> 1) & 1);
+                ptx::mbar_wait(&k_full[s], (j >> 1) & 1);
                 ptx::tc_fence_after();
                 const uint64_t dk = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + SM_K + s * 16384));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k > 0);
                 ptx::umma_commit(&s_full);
+                ptx::umma_commit(&k_empty[s]);
             };
             ptx::mbar_wait(&q_full, 0);
             issue_s(0);
             for (int j = 0; j < n_tiles; ++j) {
                 const int s = j & 1;
+                if (j + 1 < n_tiles) {
+                    // S_{j+1} as soon as S_j sits in the softmax threads' registers: it runs under their exponentials
+                    ptx::mbar_wait(&s_free, j & 1);
+                    ptx::tc_fence_after();
+                    issue_s(j + 1);
+                }
                 ptx::mbar_wait(&p_full, j & 1);
+                ptx::mbar_wait(&v_full[s], (j >> 1) & 1);
                 ptx::tc_fence_after();
                 const uint32_t sv = ptx::smem_u32(smem + SM_V + s * 16384);
                 if (p.v_col0 >= 0) {
@@ -139,18 +173,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
                         db |= static_cast<uint64_t>(1024 >> 4) << 32;   // SBO
                         db |= static_cast<uint64_t>(1) << 46;
                         db |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
-                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o | (1u << 16), k > 0);
+                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o | (1u << 16), (j > 0 || k > 0) ? 1u : 0u);
                     }
                 } else {
                     for (int k = 0; k < pv_steps; ++k) {
                         const uint64_t da = ptx::make_kmajor_sw128_desc(sp + (k >> 2) * 16384) + 2 * (k & 3);
                         const uint64_t db = ptx::make_kmajor_sw128_desc(sv + (k >> 2) * 8192) + 2 * (k & 3);
-                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o, k > 0);
+                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                     }
                 }
                 ptx::umma_commit(&o_full);
-                ptx::umma_commit(&kv_empty[s]);
-                if (j + 1 < n_tiles) issue_s(j + 1);
+                ptx::umma_commit(&v_empty[s]);
             }
         }
         __syncwarp();
@@ -160,84 +193,144 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const __grid_cons
         const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
         uint8_t* prow = smem + SM_P + (row >> 3) * 1024 + (row & 7) * 128;
         const int sw = row & 7;
-        float m = -INFINITY, l = 0.f;
-        float o[ATT_D];
-#pragma unroll
-        for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+        constexpr float RESCALE_LOG2 = 8.f;  // move the exponent's reference point only when the row maximum grew by more than 2^8
+        float m = -INFINITY, l = 0.f;        // m: reference point of every exponential taken so far (>= row max - 8)
+#ifdef ATT_PROFILE
+        long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64();
+        int n_resc = 0;
+#define ATT_T(k) { const long long now_ = clock64(); prof[k] += now_ - tprev; tprev = now_; }
+#else
+#define ATT_T(k)
+#endif
 
         for (int j = 0; j < n_tiles; ++j) {
             ptx::mbar_wait(&s_full, j & 1);
             ptx::tc_fence_after();
-            // pass 1: row max of this key tile
-            const int ncol32 = kt >> 5;
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < ncol32; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
+            ATT_T(0);
+            // the whole S row of this key tile: four asynchronous TMEM loads, one wait
+            uint32_t v[ATT_TILE];
+            {
+                uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                uint32_t(&v2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[64]);
+                uint32_t(&v3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[96]);
+                ptx::tmem_ld_32x32b_x32(t_row + TM_S, v0);
+                ptx::tmem_ld_32x32b_x32(t_row + TM_S + 32, v1);
+                if (kt == ATT_TILE) {
+                    ptx::tmem_ld_32x32b_x32(t_row + TM_S + 64, v2);
+                    ptx::tmem_ld_32x32b_x32(t_row + TM_S + 96, v3);
+                }
                 ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
             }
-            const float m_new = fmaxf(m, mx * p.scale_log2);
-            const float alpha = fast_exp2(m - m_new);
-            // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
-            float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < ncol32; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(t_row + TM_S + c * 32, v);
-                ptx::tmem_ld_wait();
-                uint32_t pk[16];
+            ATT_T(1);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&s_free);
+            // (eight independent chains: one serial fmax chain over 128 registers is 500 cycles of latency)
+            float mx8[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_new));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_new));
-                    rs += p0 + p1;
+            for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(v[i]);
+#pragma unroll
+            for (int i = 8; i < 64; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
+            if (kt == ATT_TILE) {
+#pragma unroll
+                for (int i = 64; i < ATT_TILE; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(v[i]));
+            }
+            const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
+            ATT_T(2);
+            // P V_{j-1} must have retired before this tile's P overwrites the staging buffer (and before O is rescaled)
+            bool pv_waited = false;
+            if (__any_sync(0xffffffffu, mx > m + RESCALE_LOG2)) {
+                // (warp-uniform: tcgen05.ld / .st are warp collectives; every lane of the warp moves its reference point)
+                const float m_new = fmaxf(m, mx);
+                const float alpha = fast_exp2(m - m_new);  // 0 on the first tile (m = -inf)
+                l *= alpha;
+                m = m_new;
+                if (j > 0) {
+                    ptx::mbar_wait(&o_full, (j - 1) & 1);
+                    ptx::tc_fence_after();
+                    pv_waited = true;
+                    // (8 columns at a time: the 128 S registers stay live across this rare block)
+#pragma unroll 1
+                    for (int c = 0; c < ATT_D / 8; ++c) {
+                        uint32_t o[8];
+                        ptx::tmem_ld_32x32b_x8(t_row + TM_O + c * 8, o);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        ptx::tmem_st_32x32b_x8(t_row + TM_O + c * 8, o);
+                    }
+                    ptx::tmem_st_wait();
+                }
+            }
+            ATT_T(3);
+            // probabilities -> bf16 (in place over the S registers, two per word)
+            float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+            constexpr int nw = kt >> 1;
+#pragma unroll
+            for (int i = 0; i < ATT_TILE / 2; ++i) {
+                if (i < nw) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m));
+                    rs4[i & 3] += p0 + p1;
                     __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&t);
-                }
-                // keys c*32 .. c*32+31 -> 64-key chunk (c >> 1), 16-byte units ((c & 1) * 4 + u), XOR-swizzled by row
-                uint8_t* dst = prow + (c >> 1) * 16384;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int unit = ((c & 1) * 4 + u) ^ sw;
-                    *reinterpret_cast<uint4*>(dst + unit * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    v[i] = *reinterpret_cast<uint32_t*>(&t);
                 }
             }
-            l = l * alpha + rs;
-            m = m_new;
+            l += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+            ATT_T(4);
+            if (j > 0 && !pv_waited) {
+                ptx::mbar_wait(&o_full, (j - 1) & 1);
+                ptx::tc_fence_after();
+            }
+            ATT_T(5);
+            // keys c*32 .. c*32+31 -> 64-key chunk (c >> 1), 16-byte units ((c & 1) * 4 + u), XOR-swizzled by row
+#pragma unroll
+            for (int c = 0; c < ATT_TILE / 32; ++c) {
+                if (c * 32 < kt) {
+                    uint8_t* dst = prow + (c >> 1) * 16384;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int unit = ((c & 1) * 4 + u) ^ sw;
+                        *reinterpret_cast<uint4*>(dst + unit * 16) = make_uint4(v[c * 16 + 4 * u], v[c * 16 + 4 * u + 1], v[c * 16 + 4 * u + 2], v[c * 16 + 4 * u + 3]);
+                    }
+                }
+            }
             ptx::tc_fence_before();
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(&p_full);
-            // fold O_j into the running output
-            ptx::mbar_wait(&o_full, j & 1);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(t_row + TM_O + c * 32, v);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(v[i]));
-            }
+            ATT_T(6);
         }
+#ifdef ATT_PROFILE
+        if (threadIdx.x == 0 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 3)
+            printf("attn profile (cycles over %d tiles): wait S %lld | ld S %lld | max %lld | rescale %lld | exp %lld | wait PV %lld | store P %lld\n", n_tiles,
+                   prof[0], prof[1], prof[2], prof[3], prof[4], prof[5], prof[6]);
+#endif
+        // O = (sum_j P_j V_j) / l
+        ptx::mbar_wait(&o_full, (n_tiles - 1) & 1);
+        ptx::tc_fence_after();
         const float inv = 1.f / l;
         __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.seq + q_tile * ATT_TILE + row) * p.ldo + head * ATT_D;
-        if (q_tile * ATT_TILE + row < p.seq) {
+        const bool row_ok = q_tile * ATT_TILE + row < p.seq;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            uint4 u;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(o[q * 8 + 0] * inv, o[q * 8 + 1] * inv);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(o[q * 8 + 2] * inv, o[q * 8 + 3] * inv);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(o[q * 8 + 4] * inv, o[q * 8 + 5] * inv);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(o[q * 8 + 6] * inv, o[q * 8 + 7] * inv);
-            u.x = *reinterpret_cast<uint32_t*>(&t0);
-            u.y = *reinterpret_cast<uint32_t*>(&t1);
-            u.z = *reinterpret_cast<uint32_t*>(&t2);
-            u.w = *reinterpret_cast<uint32_t*>(&t3);
-            reinterpret_cast<uint4*>(dst)[q] = u;
-        }
+        for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            ptx::tmem_ld_32x32b_x32(t_row + TM_O + c * 32, o);
+            ptx::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 u;
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o[q * 8 + 0]) * inv, __uint_as_float(o[q * 8 + 1]) * inv);
+                    __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o[q * 8 + 2]) * inv, __uint_as_float(o[q * 8 + 3]) * inv);
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o[q * 8 + 4]) * inv, __uint_as_float(o[q * 8 + 5]) * inv);
+                    __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o[q * 8 + 6]) * inv, __uint_as_float(o[q * 8 + 7]) * inv);
+                    u.x = *reinterpret_cast<uint32_t*>(&t0);
+                    u.y = *reinterpret_cast<uint32_t*>(&t1);
+                    u.z = *reinterpret_cast<uint32_t*>(&t2);
+                    u.w = *reinterpret_cast<uint32_t*>(&t3);
+                    reinterpret_cast<uint4*>(dst)[c * 4 + q] = u;
+                }
+            }
         }
     }
 
@@ -297,14 +390,18 @@ int prepare_attn(const void* qk, long long ld_qk, int q_col0, int k_col0, const 
 int run_attn(const AttnOp& op, cudaStream_t st) {
     static DevFlags configured;
     if (!configured.test()) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
         if (e != cudaSuccess) {
             snprintf(g_attn_err, sizeof g_attn_err, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
             return (int)e;
         }
         configured.set();
     }
-    attn_fwd_kernel<<<op.grid, ATT_THREADS, ATT_SMEM, st>>>(op.p);
+    if (op.p.seq < ATT_TILE)
+        attn_fwd_kernel<64><<<op.grid, ATT_THREADS, ATT_SMEM, st>>>(op.p);
+    else
+        attn_fwd_kernel<128><<<op.grid, ATT_THREADS, ATT_SMEM, st>>>(op.p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_attn_err, sizeof g_attn_err, "attn launch: %s", cudaGetErrorString(e));

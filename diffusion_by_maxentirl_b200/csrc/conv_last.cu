@@ -26,6 +26,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+
 }  // namespace
 
 // x [N,H,W,C] bf16; wp [8][9*C] bf16 (row co, k = tap*C + c, rows >= Cout zero); bias8 [8] fp32; out [N,Cout,H,W] fp32.
@@ -44,21 +48,46 @@ __global__ void __launch_bounds__(128) conv3x3_last_k(const bf16* __restrict__ x
     // ---- stage the halo tile (zero outside the image) and the weights: 16-byte vectors
     const int CV = C / 8;
     const int tile_vecs = (TH + 2) * (W + 2) * CV;
-    for (int i = tid; i < tile_vecs; i += 128) {
-        const int cv = i % CV;
-        int r = i / CV;
-        const int xx = r % (W + 2);
-        const int yy = r / (W + 2);
-        const int gy = y0 + yy - 1, gx = xx - 1;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = *reinterpret_cast<const uint4*>(x + (((long long)n * H + gy) * W + gx) * C + cv * 8);
-        *reinterpret_cast<uint4*>(st + ((size_t)yy * (W + 2) + xx) * CP + cv * 8) = v;
+    // (cp.async: every thread issues ALL of its 16-byte copies back to back - ~50 KB in flight per CTA.  The first version staged through
+    // registers, one dependent load per loop trip: 6 KB in flight per SM, 102 us for a 67 MB read-once stream)
+    // (index arithmetic is incremental: the three runtime integer divisions per 16-byte copy of the first version cost more
+    //  issue slots than everything else in the kernel - 56 us of a launch that should be a 67 MB stream)
+    {
+        const int Wp = W + 2;
+        const int dcv = 128 % CV, dr = 128 / CV;
+        int cv = tid % CV, r = tid / CV;
+        int yy = r / Wp, xx = r - yy * Wp;
+        for (int i = tid; i < tile_vecs; i += 128) {
+            const int gy = y0 + yy - 1, gx = xx - 1;
+            const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+            const bf16* src = in ? x + (((long long)n * H + gy) * W + gx) * C + cv * 8 : x;
+            cp_async16(st + ((size_t)yy * Wp + xx) * CP + cv * 8, src, in ? 16 : 0);  // src-size 0: zero fill
+            cv += dcv;
+            xx += dr;
+            if (cv >= CV) {
+                cv -= CV;
+                ++xx;
+            }
+            while (xx >= Wp) {
+                xx -= Wp;
+                ++yy;
+            }
+        }
+        const int KV = 9 * C / 8;
+        const int dkv = 128 % KV, dco = 128 / KV;
+        int co = tid / KV, kv = tid - co * KV;
+        for (int i = tid; i < 8 * KV; i += 128) {
+            cp_async16(sw + (size_t)co * KP + kv * 8, wp + (size_t)co * 9 * C + kv * 8, 16);
+            kv += dkv;
+            co += dco;
+            if (kv >= KV) {
+                kv -= KV;
+                ++co;
+            }
+        }
     }
-    const int KV = 9 * C / 8;
-    for (int i = tid; i < 8 * KV; i += 128) {
-        const int co = i / KV, kv = i - co * KV;
-        *reinterpret_cast<uint4*>(sw + (size_t)co * KP + kv * 8) = *reinterpret_cast<const uint4*>(wp + (size_t)co * 9 * C + kv * 8);
-    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- this warp's 32 pixels = two m16 tiles; each m16 tile lies inside ONE image row (16 | W): tile m = row ty[m], columns tx[m] .. + 15
     int ty[2], tx[2];

@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(512) conv3x3_first_k(const float* __restrict__
     float* sw = sm;                        // [K][Cout]
     float* sb = sw + K * Cout;             // [Cout]
     float* sx = sb + Cout;                 // [CIN][ph][pw]
-    float2* red = reinterpret_cast<float2*>(sx + ((CIN * ph * pw + 3) & ~3));  // [16][Cout]
+    const int patch = (CIN * ph * pw + 3) & ~3;
+    float2* red = reinterpret_cast<float2*>(sx + 2 * patch);  // [16][Cout]  (sx is double buffered)
     const int tiles_w = W / tw, tiles_per_img = tiles_w * (H / th);
     const long long HW = (long long)H * W;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
@@ -218,17 +219,56 @@ __global__ void __launch_bounds__(512) conv3x3_first_k(const float* __restrict__
     const int cg = threadIdx.x % CG, pg = threadIdx.x / CG;  // channels cg*8..+7, tile pixels pg*8..+7
     const int pr = (pg * 8) / tw, pc0 = (pg * 8) % tw;
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // The zero-padded input patch of tile i + 1 is fetched into registers BEFORE tile i is computed and parked in the other half of
+    // sx afterwards: the first version paid one exposed global-load latency per tile (72 us per launch at 32x32, B = 256, against
+    // 25 us of FMA work).
+    constexpr int NPRE = 6;  // >= ceil(CIN * ph * pw / blockDim): 3 (32-wide maps), 4 (64), 5 (256)
+    float nx[NPRE];
+    auto fetch = [&](int tile) {
         const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
         const int h0 = (trem / tiles_w) * th, w0 = (trem % tiles_w) * tw;
         const float sc = in_scale ? in_scale[n] : 1.f;
-        __syncthreads();  // previous tile's readers of sx / red are done (and sw / sb are staged)
-        for (int i = threadIdx.x; i < CIN * ph * pw; i += blockDim.x) {
-            const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
-            const int hh = h0 + r - 1, ww = w0 + c - 1;
-            sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((long long)n * CIN + ci) * HW + (long long)hh * W + ww] * sc : 0.f;
+#pragma unroll
+        for (int u = 0; u < NPRE; ++u) {
+            const int i = threadIdx.x + u * blockDim.x;
+            float v = 0.f;
+            if (i < CIN * ph * pw) {
+                const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
+                const int hh = h0 + r - 1, ww = w0 + c - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((long long)n * CIN + ci) * HW + (long long)hh * W + ww] * sc;
+            }
+            nx[u] = v;
         }
-        __syncthreads();
+    };
+    auto park = [&](float* dst) {
+#pragma unroll
+        for (int u = 0; u < NPRE; ++u) {
+            const int i = threadIdx.x + u * blockDim.x;
+            if (i < CIN * ph * pw) dst[i] = nx[u];
+        }
+    };
+    const bool pre_ok = CIN * ph * pw <= NPRE * (int)blockDim.x;  // (narrow nets: few threads per CTA - stage synchronously)
+    if (pre_ok && blockIdx.x < ntiles) {
+        fetch(blockIdx.x);
+        park(sx);
+    }
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
+        const int h0 = (trem / tiles_w) * th, w0 = (trem % tiles_w) * tw;
+        __syncthreads();  // this tile's patch is parked; the previous tile's readers of the other buffer / red are done (and sw / sb are staged)
+        const float* sxc = sx + buf * patch;
+        const bool more = pre_ok && tile + gridDim.x < ntiles;
+        if (more) fetch(tile + gridDim.x);
+        if (!pre_ok) {
+            const float sc = in_scale ? in_scale[n] : 1.f;
+            for (int i = threadIdx.x; i < CIN * ph * pw; i += blockDim.x) {
+                const int ci = i / (ph * pw), r = (i / pw) % ph, c = i % pw;
+                const int hh = h0 + r - 1, ww = w0 + c - 1;
+                sx[buf * patch + i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((long long)n * CIN + ci) * HW + (long long)hh * W + ww] * sc : 0.f;
+            }
+            __syncthreads();
+        }
         float acc[8][8];
         {
             const float4 b0 = *reinterpret_cast<const float4*>(sb + cg * 8), b1 = *reinterpret_cast<const float4*>(sb + cg * 8 + 4);
@@ -243,7 +283,7 @@ __global__ void __launch_bounds__(512) conv3x3_first_k(const float* __restrict__
 #pragma unroll
             for (int dr = 0; dr < 3; ++dr) {
                 float xv[10];
-                const float* xr = sx + (ci * ph + pr + dr) * pw + pc0;
+                const float* xr = sxc + (ci * ph + pr + dr) * pw + pc0;
 #pragma unroll
                 for (int j = 0; j < 10; ++j) xv[j] = xr[j];
 #pragma unroll
@@ -258,6 +298,7 @@ __global__ void __launch_bounds__(512) conv3x3_first_k(const float* __restrict__
                 }
             }
         }
+        if (more) park(sx + (buf ^ 1) * patch);  // (its last readers finished before this iteration's barrier)
         float s1[8], s2[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) s1[c] = s2[c] = 0.f;
@@ -304,7 +345,7 @@ void conv3x3_first(const float* x, const float* in_scale, const float* w, const 
     const int th = 128 / tw;
     const int threads = 16 * (Cout / 8);
     const int patch = (Cin * (th + 2) * (tw + 2) + 3) & ~3;
-    const size_t smem = (size_t)(9 * Cin * Cout + Cout + patch) * sizeof(float) + (size_t)16 * Cout * sizeof(float2);
+    const size_t smem = (size_t)(9 * Cin * Cout + Cout + 2 * patch) * sizeof(float) + (size_t)16 * Cout * sizeof(float2);
     static DevFlags configured;
     static int num_sms = 148;
     if (!configured.test()) {
@@ -1030,28 +1071,48 @@ void avgpool2(const bf16* x, bf16* out, int N, int H, int W, int C, int act, cud
 
 // ============================================================================================ tiny attention
 
-// one CTA per (image, head); q/k/v tiles in smem as bf16, scores fp32. seq <= 64.
-__global__ void attn_small_k(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, int ld,
-                             bf16* __restrict__ out, int ldo, int heads, int seq, int d, float scale) {
-    extern __shared__ uint8_t smraw[];
+// one CTA per (image, head); q/k/v tiles in smem as bf16, scores fp32. seq <= 64, d % 8 == 0, ld % 8 == 0.
+// Rows are padded to d + 2 elements: the pitch in 32-bit words (d/2 + 1) is odd, so the 16 key rows a warp walks in the score
+// loop fall into distinct banks (the unpadded layout was a 16-way bank conflict: 57 us per launch for a 16-token map at B = 256).
+// Global loads are 16-byte vectors; every dot product walks bf16 pairs.
+__global__ void __launch_bounds__(256) attn_small_k(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, int ld,
+                                                    bf16* __restrict__ out, int ldo, int heads, int seq, int d, float scale) {
+    extern __shared__ __align__(16) uint8_t smraw[];
+    const int dp = d + 2;
     bf16* sq = reinterpret_cast<bf16*>(smraw);
-    bf16* sk = sq + seq * d;
-    bf16* sv = sk + seq * d;
-    float* ss = reinterpret_cast<float*>(sv + seq * d);  // [seq][seq]
+    bf16* sk = sq + seq * dp;
+    bf16* sv = sk + seq * dp;
+    float* ss = reinterpret_cast<float*>(sv + seq * dp);  // [seq][seq]
     const int n = blockIdx.x / heads, h = blockIdx.x % heads;
     const long long base = (long long)n * seq * ld + (long long)h * d;
-    for (int i = threadIdx.x; i < seq * d; i += blockDim.x) {
-        const int t = i / d, c = i % d;
-        sq[i] = q[base + (long long)t * ld + c];
-        sk[i] = k[base + (long long)t * ld + c];
-        sv[i] = v[base + (long long)t * ld + c];
+    const int dv = d >> 3;
+    for (int i = threadIdx.x; i < seq * dv; i += blockDim.x) {
+        const int t = i / dv, c = (i - t * dv) * 8;
+        const long long g = base + (long long)t * ld + c;
+        const uint4 a = *reinterpret_cast<const uint4*>(q + g);
+        const uint4 b = *reinterpret_cast<const uint4*>(k + g);
+        const uint4 e = *reinterpret_cast<const uint4*>(v + g);
+        uint32_t* dq = reinterpret_cast<uint32_t*>(sq + t * dp + c);
+        uint32_t* dk = reinterpret_cast<uint32_t*>(sk + t * dp + c);
+        uint32_t* dw = reinterpret_cast<uint32_t*>(sv + t * dp + c);
+        dq[0] = a.x; dq[1] = a.y; dq[2] = a.z; dq[3] = a.w;
+        dk[0] = b.x; dk[1] = b.y; dk[2] = b.z; dk[3] = b.w;
+        dw[0] = e.x; dw[1] = e.y; dw[2] = e.z; dw[3] = e.w;
     }
     __syncthreads();
+    const int d2 = d >> 1;
     for (int i = threadIdx.x; i < seq * seq; i += blockDim.x) {
-        const int a = i / seq, b = i % seq;
-        float s = 0.f;
-        for (int c = 0; c < d; ++c) s = fmaf(__bfloat162float(sq[a * d + c]), __bfloat162float(sk[b * d + c]), s);
-        ss[i] = s * scale;
+        const int a = i / seq, b = i - a * seq;
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(sq + a * dp);
+        const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(sk + b * dp);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < d2; ++c) {
+            const float2 x = __bfloat1622float2(pa[c]), y = __bfloat1622float2(pb[c]);
+            s0 = fmaf(x.x, y.x, s0);
+            s1 = fmaf(x.y, y.y, s1);
+        }
+        ss[i] = (s0 + s1) * scale;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -1072,16 +1133,21 @@ __global__ void attn_small_k(const bf16* __restrict__ q, const bf16* __restrict_
     }
     __syncthreads();
     const long long obase = (long long)n * seq * ldo + (long long)h * d;
-    for (int i = threadIdx.x; i < seq * d; i += blockDim.x) {
-        const int a = i / d, c = i % d;
-        float s = 0.f;
-        for (int b = 0; b < seq; ++b) s = fmaf(ss[a * seq + b], __bfloat162float(sv[b * d + c]), s);
-        out[obase + (long long)a * ldo + c] = __float2bfloat16_rn(s);
+    for (int i = threadIdx.x; i < seq * d2; i += blockDim.x) {
+        const int a = i / d2, c = i - a * d2;
+        float s0 = 0.f, s1 = 0.f;
+        for (int b = 0; b < seq; ++b) {
+            const float p = ss[a * seq + b];
+            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sv + b * dp + 2 * c));
+            s0 = fmaf(p, y.x, s0);
+            s1 = fmaf(p, y.y, s1);
+        }
+        *reinterpret_cast<__nv_bfloat162*>(out + obase + (long long)a * ldo + 2 * c) = __floats2bfloat162_rn(s0, s1);
     }
 }
 void attn_small(const bf16* q, const bf16* k, const bf16* v, int ld, bf16* out, int ldo, int N, int heads, int seq,
                 int d, float scale, cudaStream_t st) {
-    const size_t smem = (size_t)3 * seq * d * sizeof(bf16) + (size_t)seq * seq * sizeof(float);
+    const size_t smem = (size_t)3 * seq * (d + 2) * sizeof(bf16) + (size_t)seq * seq * sizeof(float);
     static DevFlags configured;
     if (!configured.test()) {
         cudaFuncSetAttribute(attn_small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
