@@ -48,6 +48,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // KT = keys per tile: 128, or 64 for seq == 64 (compile time: with a run-time tile width the unrolled softmax loops degenerate into
 // one branch + one exposed MUFU latency per pair of exponentials - 4800 instead of ~1100 cycles per tile, measured with clock64)
+// 2^x on the FMA / ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, rel. error 2.4e-4 - far below the bf16
+// rounding of P): the MUFU unit evaluates 16 ex2 per clock and SM, which bounds a d = 64 attention tile at 1024 cycles against
+// 512 cycles of tensor work, so a fraction of the exponentials is computed here instead (FlashAttention-4's trick).
+__device__ __forceinline__ float poly_exp2(float x) {
+    x = fmaxf(x, -125.f);
+    const float t = x + 12582912.f;  // 1.5 * 2^23: the integer part n = round(x) lands in the low mantissa bits
+    const float f = x - (t - 12582912.f);  // in [-0.5, 0.5]
+    const float p = fmaf(fmaf(fmaf(0.052731406f, f, 0.24209385f), f, 0.69359708f), f, 0.99996608f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));  // p * 2^n
+}
+#ifndef ATT_POLY_MASK
+#define ATT_POLY_MASK (-1)  // 3: pairs whose index has (i & 3) == 3 take the polynomial (a quarter of the exponentials).  MEASURED on B200:
+// 185.9 us instead of 180.8 us at seq 1024 - the kernel is bound by the serial per-warp chain, not by MUFU throughput; off
+#endif
+
+// (Measured neutral and removed: delaying every second CTA of an SM by half a tile so that one CTA's exponentials run under the
+//  other's load / max / store phases - 183 vs 181 us.)
 template <int KT>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -269,8 +286,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < ATT_TILE / 2; ++i) {
                 if (i < nw) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m));
+                    const float x0 = fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m), x1 = fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m);
+                    const bool poly = ATT_POLY_MASK >= 0 && (i & 3) == ATT_POLY_MASK;
+                    const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
+                    const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
                     rs4[i & 3] += p0 + p1;
                     __nv_bfloat162 t = __floats2bfloat162_rn(p0, p1);
                     v[i] = *reinterpret_cast<uint32_t*>(&t);
