@@ -57,11 +57,14 @@ struct EpiSlot {
 #ifndef EPI_ROLL_RESIDUAL
 #define EPI_ROLL_RESIDUAL 1
 #endif
-template <int MODE>
+// RW = window size in 32-column chunks; it must divide the chunks of a tile: 4 for 128- / 256-wide tiles, 3 for 192-wide tiles (6 chunks -
+// every ImageNet-64 / LSUN width; without a window their operands fell back to one chunk of lead, and the residual epilogue of the
+// short-K 1x1 projections ran at ~10 us per tile: profiles/r02 gemm table, 65536 x 384 x 384 at 0.27 PFLOP/s), 2 for 64-wide tiles.
+template <int MODE, int RW = 4>
 struct EpiCarry {  // (templated so that each epilogue shape carries only its own operands across tiles)
-    uint2 res[(MODE == 2 /*EPI_RESIDUAL*/ && EPI_ROLL_RESIDUAL) ? 4 : 1][4];                    // [slot][row]: residual words
-    float4 rv[MODE == 1 /*EPI_ROWVEC*/ ? 4 : 1];                         // [slot]: per-image row vector of a tile inside one image
-    float4 bias[(MODE == 1 || (MODE == 2 && EPI_ROLL_RESIDUAL)) ? 4 : 1];                       // [slot]
+    uint2 res[(MODE == 2 /*EPI_RESIDUAL*/ && EPI_ROLL_RESIDUAL) ? RW : 1][4];                    // [slot][row]: residual words
+    float4 rv[MODE == 1 /*EPI_ROWVEC*/ ? RW : 1];                         // [slot]: per-image row vector of a tile inside one image
+    float4 bias[(MODE == 1 || (MODE == 2 && EPI_ROLL_RESIDUAL)) ? RW : 1];                       // [slot]
     int tile_key;                                                        // which tile the slots were primed for (-1: none)
 #ifdef DXMI_EPI_PROFILE
     long long prof[8];  // cycles: acc wait | first stage + barrier | stage next | finish + store | prefetch + fold | barrier 2 | publish | barrier 1
@@ -80,10 +83,10 @@ __device__ __forceinline__ int epi_tile_key(int m_tile, int col0, int batch) { r
 // `acc_full` / `acc_parity`: the accumulator-ready barrier of this tile.  The epilogue issues its operand prefetches (the
 // residual up to four 32-column chunks ahead: ncu round 2 showed the N = 128 convolutions epilogue bound on exactly these
 // L2-latency loads) BEFORE it waits for the accumulator, so they fly during the tile's main loop.
-template <int MODE, bool STATS>
+template <int MODE, bool STATS, int RW = 4>
 __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& cx, uint32_t tacc_col, uint32_t tmem_empty_addr,
                                          int m_tile, int col0, int nch, int batch, uint32_t& out_cnt, uint64_t* acc_full,
-                                         uint32_t acc_parity, EpiCarry<MODE>& cy, int next_m_tile = -1, int next_col0 = 0, int next_batch = 0) {
+                                         uint32_t acc_parity, EpiCarry<MODE, RW>& cy, int next_m_tile = -1, int next_col0 = 0, int next_batch = 0) {
     const int row0 = m_tile * TILE_M;
     constexpr int CH = 32;
     const int n_total = p.N_total;
@@ -157,8 +160,8 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     // (a tile past the last row - odd tail of a CTA pair - reads the last image's vector: masked at the store, but never out of bounds)
     const int rv_last = rv_uniform ? (p.M_total - 1) / p.rows_per_image : 0;
     const float* rv_base = rv_uniform ? p.rowvec + static_cast<long long>(min(row0 / p.rows_per_image, rv_last)) * p.ldrv : nullptr;
-    // ---- rolling one-tile-ahead window (hot modes, 4 | nch): slot k = chunk & 3
-    const bool roll = (MODE == EPI_ROWVEC || (MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL)) && (nch & 3) == 0 && !p.halo && (MODE != EPI_ROWVEC || rv_uniform);
+    // ---- rolling one-tile-ahead window (hot modes, RW | nch): slot k = chunk % RW
+    const bool roll = (MODE == EPI_ROWVEC || (MODE == EPI_RESIDUAL && EPI_ROLL_RESIDUAL)) && (nch % RW) == 0 && !p.halo && (MODE != EPI_ROWVEC || rv_uniform);
     const bool have_next = next_m_tile >= 0;
     const __nv_bfloat16* rptr_n[4];
     bool rok_n[4];
@@ -217,8 +220,8 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         if (cy.tile_key != epi_tile_key(m_tile, col0, batch)) {  // first tile of this CTA: prime the window
             roll_load(EpiSlot<0>{}, 0, false);
             roll_load(EpiSlot<1>{}, 1, false);
-            roll_load(EpiSlot<2>{}, 2, false);
-            roll_load(EpiSlot<3>{}, 3, false);
+            if constexpr (RW > 2) roll_load(EpiSlot<2>{}, 2, false);
+            if constexpr (RW > 3) roll_load(EpiSlot<3>{}, 3, false);
         }
         cy.tile_key = have_next ? epi_tile_key(next_m_tile, next_col0, next_batch) : -1;
     } else {
@@ -384,9 +387,9 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
         }
         EPI_T(3);
         if (roll) {
-            // this slot is consumed: refill it with the chunk four ahead - same tile, or the NEXT tile's chunk (c + 4 - nch)
-            if (c + 4 < nch) roll_load(slot_c, c + 4, false);
-            else if (have_next) roll_load(slot_c, c + 4 - nch, true);
+            // this slot is consumed: refill it with the chunk RW ahead - same tile, or the NEXT tile's chunk (c + RW - nch)
+            if (c + RW < nch) roll_load(slot_c, c + RW, false);
+            else if (have_next) roll_load(slot_c, c + RW - nch, true);
         } else if (c + 1 < nch) {
             prefetch(cc + CH);  // next chunk's operands fly during the stats tail and phase A
         }
@@ -439,11 +442,11 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
     };
     if (roll) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < nch; c0 += 4) {
+        for (int c0 = 0; c0 < nch; c0 += RW) {
             do_chunk(c0, EpiSlot<0>{});
             do_chunk(c0 + 1, EpiSlot<1>{});
-            do_chunk(c0 + 2, EpiSlot<2>{});
-            do_chunk(c0 + 3, EpiSlot<3>{});
+            if constexpr (RW > 2) do_chunk(c0 + 2, EpiSlot<2>{});
+            if constexpr (RW > 3) do_chunk(c0 + 3, EpiSlot<3>{});
         }
     } else {
 #pragma unroll 1

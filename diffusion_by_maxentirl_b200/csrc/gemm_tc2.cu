@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
             constexpr int MODE = decltype(mode_c)::value;
             constexpr bool ST = decltype(stats_c)::value != 0;
             uint32_t ti = 0, out_cnt = 0;
-            EpiCarry<MODE> carry;
+            constexpr int RW = BLOCK_N == 192 ? 3 : (BLOCK_N == 64 ? 2 : 4);  // operand window (chunks): must divide BLOCK_N / 32
+            EpiCarry<MODE, RW> carry;
             carry.tile_key = -1;
 #ifdef DXMI_EPI_PROFILE
             for (int k = 0; k < 8; ++k) carry.prof[k] = 0;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                     nx_m = mtn % p.m_tiles;
                     nx_batch = mtn / p.m_tiles;
                 }
-                epi_tile<MODE, ST>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry, nx_m, nx_col0, nx_batch);
+                epi_tile<MODE, ST, RW>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry, nx_m, nx_col0, nx_batch);
                 if (ti == 0 && leader) { DBG2(6); }
                 if (nch == 0) {  // cannot happen (n tiles are clipped on the host), but never leave the MMA warp waiting
                     ptx::tc_fence_before();

@@ -386,7 +386,8 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
             constexpr int MODE = decltype(mode_c)::value;
             constexpr bool ST = decltype(stats_c)::value != 0;
             uint32_t ti = 0, out_cnt = 0;
-            EpiCarry<MODE> carry;
+            constexpr int RW = BLOCK_N == 192 ? 3 : (BLOCK_N == 64 ? 2 : 4);  // operand window (chunks): must divide BLOCK_N / 32
+            EpiCarry<MODE, RW> carry;
             carry.tile_key = -1;
 #ifdef DXMI_EPI_PROFILE
             for (int k = 0; k < 8; ++k) carry.prof[k] = 0;
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 for (int h = 0; h < msub; ++h) {
                     const uint32_t tcol = acc * (Cfg::ACC_COLS * msub) + h * Cfg::ACC_COLS;
                     const bool last = h == msub - 1;
-                    epi_tile<MODE, ST>(p, cx, tcol, te, m_tile0 + h, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry,
+                    epi_tile<MODE, ST, RW>(p, cx, tcol, te, m_tile0 + h, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry,
                                        last ? nx_m : m_tile0 + h + 1, last ? nx_col0 : col0, last ? nx_batch : batch);
                 }
             }
