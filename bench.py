@@ -487,7 +487,14 @@ def measure(wl, T, B, K, W, args, ctx, full):
                 "launches_per_step": nl.value // kk, "ms_per_step": ms.value / kk,
                 "share_of_step": (ms.value / kk) / step_ms, "algorithmic_gflop_per_step": fl.value / kk / 1e9,
                 "whole_step_frac": None}
-        roof["whole_step_frac"] = ((T * GF[wl][0] + (GF[wl][1] if value is not None else 0.0)) * B / 1e3) / (step_ms * 1e-3) / peak
+        model_gflop = (T * GF[wl][0] + (GF[wl][1] if value is not None else 0.0)) * B
+        roof["whole_step_frac"] = (model_gflop / 1e3) / (step_ms * 1e-3) / peak
+        # `frac` counts the FLOPs the tensor pipe EXECUTES (2 M N K of every launch).  The reference model's arithmetic (GF per
+        # image) is larger: the nearest-2x upsample + 3x3 conv layers run as four 2x2 phase convolutions at 4/9 of the reference FLOPs
+        # (gemm up2 mode).  `whole_step_frac` divides the REFERENCE arithmetic by the step time.
+        roof["reference_model_gflop_per_step"] = model_gflop
+        roof["note"] = ("frac = executed tcgen05 FLOPs / kernel time / peak; whole_step_frac = reference-model FLOPs / step time / peak "
+                        "(upsample+conv layers execute 4/9 of their reference FLOPs as phase convolutions)")
         hbm = []
         for cat, name, key in ((1, "GroupNorm family: gn_finalize_k + gn_apply_ab_k / gn_apply_fused_k (normalise + SiLU, one bf16 read + "
                                    "one bf16 write per element)", "gn_apply_ab_k"),

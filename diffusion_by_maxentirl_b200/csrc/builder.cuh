@@ -412,9 +412,13 @@ struct Builder {
             if (direct) {
                 // read-once stream kernel (conv_last.cu): halo tile + weights in shared memory, mma.sync N = 8
                 Plan* pl = &plan;
-                const int Bn = B;
+                ConvLastOp lop;
+                if (!dry && prepare_conv3x3_last(src, B, H, W, C, &lop)) {
+                    fail("conv3x3_last: tensor map encoding failed");
+                    return;
+                }
                 op([=](cudaStream_t st) {
-                    conv3x3_last(src, wp, bp, (float*)pl->out, Bn, H, W, C, Cout, st);
+                    conv3x3_last(lop, wp, bp, (float*)pl->out, Cout, st);
                     return (int)cudaGetLastError();
                 });
                 return;

@@ -2,6 +2,7 @@
 // Activations are NHWC bf16 unless stated; network inputs / outputs and sampler states are NCHW fp32 like the
 // reference (models/DxMI/var_sampler.py, models/DxMI/openai_diffusion.py).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -73,7 +74,12 @@ void upsample2x(const bf16* x, bf16* out, int N, int H, int W, int C, cudaStream
 // last convolution of a U-Net (3x3, pad 1, C -> Cout <= 8) as a read-once stream: conv_last.cu.  wp: bf16 [8][9*C] (k = tap*C + c, rows >= Cout
 // zero), bias8: fp32 [8]; out fp32 NCHW
 bool conv3x3_last_supported(int H, int W, int C, int Cout);
-void conv3x3_last(const bf16* x, const bf16* wp, const float* bias8, float* out, int N, int H, int W, int C, int Cout, cudaStream_t st);
+struct ConvLastOp {
+    CUtensorMap xmap;  // (c, w, h, n) over the input, box (64, W + 2, 128 / W + 2, 1): one halo tile of one 64-channel slice
+    int N, H, W, C;
+};
+int prepare_conv3x3_last(const bf16* x, int N, int H, int W, int C, ConvLastOp* op);  // at plan-build time (the input pointer is fixed)
+void conv3x3_last(const ConvLastOp& op, const bf16* wp, const float* bias8, float* out, int Cout, cudaStream_t st);
 // out[n][c][p] = src[(n*HW + p)*ld + c] for c < C (fp32): the padded NHWC result of the network-output convolution -> NCHW
 void nhwc_to_nchw_f32(const float* src, int ld, float* out, int N, int HW, int C, cudaStream_t st);
 void avgpool2(const bf16* x, bf16* out, int N, int H, int W, int C, int act, cudaStream_t st);   // 2x2 mean (+act)
