@@ -31,6 +31,9 @@ void set_attnblk(int v) { g_opt_attnblk = v; }
 static int g_opt_stats16 = 0;  // measured (round 2): 16-row direct partials save the 2nd epilogue barrier but cost more in the finalize: -1 % end to end
 int stats16_option() { return g_opt_stats16; }
 void set_stats16(int v) { g_opt_stats16 = v; }
+static int g_opt_first_tc = 1;  // inference plans: first convolution on mma.sync (conv_first.cu) instead of the fp32 FMA kernel
+int first_tc_option() { return g_opt_first_tc; }
+void set_first_tc(int v) { g_opt_first_tc = v; }
 static int g_opt_up2 = 1;  // nearest-2x upsample + 3x3 conv as four 2x2 phase convolutions (builder.cuh conv_up2): 4/9 of the FLOPs, no upsampled tensor
 int up2_option() { return g_opt_up2; }
 void set_up2(int v) { g_opt_up2 = v; }
@@ -581,8 +584,12 @@ struct DdpmBuilder : Builder {
             bf16* o = h0.p;
             float* hst = h0.stats;
             const int Cin = a.in_channels;
+            const bool first_tc = first_tc_option() && conv3x3_first_tc_supported(Cin, R, R, ch);
             op([=](cudaStream_t st) {
-                conv3x3_first(pl->x, pl->x_scale, w, b, o, hst, Bn, Cin, R, R, ch, 0, st);
+                if (first_tc)
+                    conv3x3_first_tc(pl->x, pl->x_scale, w, b, o, hst, Bn, R, R, ch, 0, st);
+                else
+                    conv3x3_first(pl->x, pl->x_scale, w, b, o, hst, Bn, Cin, R, R, ch, 0, st);
                 return (int)cudaGetLastError();
             });
         }
@@ -646,8 +653,12 @@ struct IgebmBuilder : Builder {
             const float* b = f32("conv1.bias");
             bf16* o = h.p;
             const int Cin = a.in_channels;
+            const bool first_tc = first_tc_option() && conv3x3_first_tc_supported(Cin, R, R, nh);
             op([=](cudaStream_t st) {
-                conv3x3_first(pl->x, nullptr, w, b, o, nullptr, Bn, Cin, R, R, nh, ACT_LRELU02, st);
+                if (first_tc)
+                    conv3x3_first_tc(pl->x, nullptr, w, b, o, nullptr, Bn, R, R, nh, ACT_LRELU02, st);
+                else
+                    conv3x3_first(pl->x, nullptr, w, b, o, nullptr, Bn, Cin, R, R, nh, ACT_LRELU02, st);
                 return (int)cudaGetLastError();
             });
         }

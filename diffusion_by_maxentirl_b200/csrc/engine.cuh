@@ -117,6 +117,8 @@ void set_gn_fused(int v);
 void set_stats16(int v);
 void set_conv_out_padded(int v);
 void set_up2(int v);
+void set_first_tc(int v);
+int first_tc_option();
 void set_attnblk(int v);
 const char* engine_last_error();
 void engine_set_error(const char* fmt, ...);

@@ -358,8 +358,12 @@ struct AdmBuilder : Builder {
             if (Cin != 3 || Co % 32 || Co > 256 || (R * R) % 128 || h.stats_P < R * R / 128 || h.stats_halo)
                 fail("ADM input conv: unsupported geometry");
             h.stats_P = R * R / 128;  // conv3x3_first_k publishes one partial per 128-pixel tile
+            const bool first_tc = first_tc_option() && conv3x3_first_tc_supported(Cin, R, R, Co);
             op([=](cudaStream_t st) {
-                conv3x3_first(pl->x, pl->x_scale, w, b, o, hst, Bn, Cin, R, R, Co, 0, st);
+                if (first_tc)
+                    conv3x3_first_tc(pl->x, pl->x_scale, w, b, o, hst, Bn, R, R, Co, 0, st);
+                else
+                    conv3x3_first(pl->x, pl->x_scale, w, b, o, hst, Bn, Cin, R, R, Co, 0, st);
                 return (int)cudaGetLastError();
             });
         }

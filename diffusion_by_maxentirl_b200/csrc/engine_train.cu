@@ -103,8 +103,13 @@ struct IgebmTrainBuilder : Builder {
             const float* b = f32("conv1.bias");
             bf16* o = h.p;
             cur_label = "conv1";
+            // (the same kernel choice as the inference plan, engine.cu IgebmBuilder: value(x) is bitwise the same with and without autograd)
+            const bool first_tc = first_tc_option() && conv3x3_first_tc_supported(3, R, R, nh);
             op([=](cudaStream_t st) {
-                conv3x3_first(pl->x, nullptr, w, b, o, nullptr, Bn, 3, R, R, nh, ACT_LRELU02, st);
+                if (first_tc)
+                    conv3x3_first_tc(pl->x, nullptr, w, b, o, nullptr, Bn, R, R, nh, ACT_LRELU02, st);
+                else
+                    conv3x3_first(pl->x, nullptr, w, b, o, nullptr, Bn, 3, R, R, nh, ACT_LRELU02, st);
                 return (int)cudaGetLastError();
             });
         }

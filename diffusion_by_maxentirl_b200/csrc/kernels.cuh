@@ -29,6 +29,11 @@ void cast_to_f32(const void* src, int src_is_half, float* dst, long long n, cuda
 // stats (optional): GroupNorm partials of the output, [N][H*W/128][Cout][2] (sum, sumsq) like the GEMM epilogues write.
 void conv3x3_first(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, float* stats, int N,
                    int Cin, int H, int W, int Cout, int act, cudaStream_t st);
+// the same operator on warp-level tensor-core MMAs (conv_first.cu; inference plans): x and w are rounded to bf16 like every other
+// activation / weight of the path, accumulation in fp32
+bool conv3x3_first_tc_supported(int Cin, int H, int W, int Cout);
+void conv3x3_first_tc(const float* x, const float* in_scale, const float* w, const float* b, bf16* out, float* stats, int N, int H, int W,
+                      int Cout, int act, cudaStream_t st);
 // h bf16 NHWC [N,H,W,C] -> fp32 NCHW [N,Cout<=4,H,W]
 void conv3x3_last(const bf16* h, const float* w, const float* b, float* out, int N, int C, int H, int W, int Cout,
                   cudaStream_t st);
