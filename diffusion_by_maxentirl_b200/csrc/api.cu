@@ -84,6 +84,10 @@ int dxmi_set_option(const char* name, int value) {
         set_pdl(value);
         return 0;
     }
+    if (!strcmp(name, "lean_epi")) {  // read when a GEMM is prepared
+        set_lean_epi(value);
+        return 0;
+    }
     if (!strcmp(name, "first_tc")) {  // read when a plan is built
         set_first_tc(value);
         return 0;

@@ -455,6 +455,77 @@ __device__ __forceinline__ void epi_tile(const ConvGemmParams& p, const EpiCtx& 
 }
 
 
+// Lean drain for bias-only tiles WITHOUT statistics (the q|k|v projections of the ADM attention blocks: M = 65536, N = 1152, K = 384 runs
+// 73 us with the staged epilogue against a 31 us HBM / 41 us tensor floor - short-K GEMMs are bound by the epilogue's output rate, about
+// 1000 cycles per 128 x 32 chunk, tools/bench_1x1.py).  Nothing has to cross rows here, so there is no reason to transpose through shared
+// memory: thread <-> accumulator row, 16 fp32 columns per thread and chunk straight from TMEM (the load of chunk c + 1 is in flight while
+// chunk c is converted), alpha / bias, bf16, one 32-byte row segment = two 16-byte stores.  No staging, no named barriers, ~35 instead of
+// ~110 instructions per thread and chunk.  The row-per-thread stores touch 32 lines per instruction - what made the round-1 epilogue slow
+// with four warps and 16-byte segments - but every sector is written whole by the same thread and eight warps keep the LSU queue full.
+// MEASURED NEGATIVE on B200 (tools/bench_1x1.py, option "lean_epi", off by default): M = 65536, K = 384 bias-only, N = 384: 38.5 us vs 29.9 us
+// staged; N = 1152: 96.0 vs 72.9 us; ImageNet-64 T = 10: 394.9 vs 400.6 img/s.  A third of the instructions, and still slower: a store
+// instruction that touches 32 lines occupies the LSU for 32 cycles however few instructions surround it - the transposing epilogue's
+// full-line stores are what the memory pipe wants.
+__device__ __forceinline__ bool epi_lean_ok(const ConvGemmParams& p) {
+    return p.lean_epi && !p.halo && p.dbg_mode == 0 && (p.N_total & 15) == 0 && (p.ldo & 7) == 0;
+}
+__device__ __forceinline__ void epi_tile_lean(const ConvGemmParams& p, const EpiCtx& cx, uint32_t tacc_col, uint32_t tmem_empty_addr, int m_tile,
+                                              int col0, int nch, int batch, uint64_t* acc_full, uint32_t acc_parity) {
+    const int row_in_tile = (cx.stage_off >> 10) * 8 + ((cx.stage_off >> 7) & 7);
+    const long long r = static_cast<long long>(m_tile) * TILE_M + row_in_tile;
+    const bool ok = r < p.M_total;
+    const long long r_out = p.up2 ? 4 * r - 2 * (r & p.up2_wmask) + (batch >> 1) * p.up2_w2 + (batch & 1) : r;
+    const int cc0 = col0 + cx.hsel * 16;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + batch * p.out_batch_stride + r_out * p.ldo + cc0;
+    const float alpha = p.alpha;
+    const bool has_bias = p.bias != nullptr;
+    const int n_total = p.N_total;
+    ptx::mbar_wait(acc_full, acc_parity);
+    ptx::tc_fence_after();
+    uint32_t va[16], vb[16];
+    ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + cx.hsel * 16, va);
+    auto finish = [&](int c, uint32_t (&v)[16]) {
+        const int cc = cc0 + c * 32;
+        if (cc >= n_total) return;
+        float4 b4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b4[q] = has_bias ? __ldg(reinterpret_cast<const float4*>(p.bias + cc) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t w[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float x0 = fmaf(__uint_as_float(v[4 * q]), alpha, b4[q].x), x1 = fmaf(__uint_as_float(v[4 * q + 1]), alpha, b4[q].y);
+            const float x2 = fmaf(__uint_as_float(v[4 * q + 2]), alpha, b4[q].z), x3 = fmaf(__uint_as_float(v[4 * q + 3]), alpha, b4[q].w);
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(x0, x1), t1 = __floats2bfloat162_rn(x2, x3);
+            w[2 * q] = *reinterpret_cast<uint32_t*>(&t0);
+            w[2 * q + 1] = *reinterpret_cast<uint32_t*>(&t1);
+        }
+        if (ok) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    };
+#pragma unroll 1
+    for (int c = 0; c < nch; c += 2) {
+        ptx::tmem_ld_wait();  // chunk c (va)
+        if (c + 1 < nch) ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + ((c + 1) * 32 + cx.hsel * 16), vb);
+        else {
+            ptx::tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tmem_empty_addr) : "memory");
+        }
+        finish(c, va);
+        if (c + 1 < nch) {
+            ptx::tmem_ld_wait();  // chunk c + 1 (vb)
+            if (c + 2 < nch) ptx::tmem_ld_32x32b_x16(cx.taddr + tacc_col + ((c + 2) * 32 + cx.hsel * 16), va);
+            else {
+                ptx::tc_fence_before();
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tmem_empty_addr) : "memory");
+            }
+            finish(c + 1, vb);
+        }
+    }
+}
+
 // Statistics publisher (ONE warp, not an epilogue warp): for every chunk of a tile, combines the 8 warp partials per column
 // in a fixed order - per row segment: 32-row blocks ascending, the two 16-row halves of each - and writes one (sum, sum of
 // squares) pair per segment and column.  Keeps 16 shared-memory loads, the adds and the store off the epilogue warps' critical

@@ -13,6 +13,8 @@ static int g_opt_small_bn = 1;
 static int g_opt_shift3 = 1;
 static int g_opt_wave_bn = 1;
 static int g_opt_s3_stages_max = 8;
+static int g_opt_lean_epi = 0;  // bias-only GEMMs without GroupNorm partials: direct TMEM -> registers -> global drain. MEASURED SLOWER, off (gemm_epi.cuh)
+void set_lean_epi(int v) { g_opt_lean_epi = v; }
 static int g_opt_s3_m2 = 1;  // 0 off, 1 heuristic, 2 whenever possible
 void set_s3_m2(int v) { g_opt_s3_m2 = v; }
 void set_s3_stages_max(int v) { g_opt_s3_stages_max = v; }
@@ -188,6 +190,7 @@ int prepare_gemm(const dxmi_gemm_desc& d, GemmOp* op) {
     p.alpha = d.alpha == 0.f ? 1.f : d.alpha;
     p.softmax = d.softmax;
     p.dbg_mode = g_opt_dbg_mode;
+    p.lean_epi = g_opt_lean_epi;
     p.dbg_times = g_dbg_times;
 
     op->block_n = block_n;

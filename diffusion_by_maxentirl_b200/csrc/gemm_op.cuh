@@ -20,6 +20,7 @@ void set_shift3(int v);
 void set_wave_bn(int v);
 void set_s3_stages_max(int v);
 void set_s3_m2(int v);
+void set_lean_epi(int v);
 int halo_option();
 void set_dbg_mode(int v);
 void set_gemm_version(int v);

@@ -111,6 +111,7 @@ struct ConvGemmParams {
     int up2_wmask;             // W - 1 (W = low-resolution width, a power of two)
     int up2_w2;                // 2 * W: output-row offset of phase row py
     int up2_spi;               // GroupNorm partial segments per low-resolution image (rows_per_image / stats_seg)
+    int lean_epi;              // 1: bias-only tiles without statistics are drained straight from TMEM (gemm_epi.cuh epi_tile_lean)
     float* stats;              // GroupNorm partial sums of the bf16 outputs: [M_total/stats_seg][N_total][2] (sum, sumsq) or null
     int stats_seg;             // rows per partial: 32, 64 or 128 (a segment never straddles two images)
     long long* dbg_times;      // profiling only: per-CTA phase timestamps (globaltimer ns), 8 slots per CTA, or null

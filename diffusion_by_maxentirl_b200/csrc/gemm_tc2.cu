@@ -343,7 +343,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm2_kernel(const __grid
                     nx_m = mtn % p.m_tiles;
                     nx_batch = mtn / p.m_tiles;
                 }
-                epi_tile<MODE, ST, RW>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry, nx_m, nx_col0, nx_batch);
+                if (MODE == EPI_BIAS && !ST && epi_lean_ok(p))
+                    epi_tile_lean(p, cx, tcol, te, m_tile, col0, nch, batch, &tmem_full[acc], (ti >> 1) & 1);
+                else
+                    epi_tile<MODE, ST, RW>(p, cx, tcol, te, m_tile, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry, nx_m, nx_col0, nx_batch);
                 if (ti == 0 && leader) { DBG2(6); }
                 if (nch == 0) {  // cannot happen (n tiles are clipped on the host), but never leave the MMA warp waiting
                     ptx::tc_fence_before();

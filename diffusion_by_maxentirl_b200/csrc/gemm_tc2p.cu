@@ -414,8 +414,11 @@ __global__ void __launch_bounds__(NUM_THREADS_P, 1) conv_gemm2p_kernel(const __g
                 for (int h = 0; h < msub; ++h) {
                     const uint32_t tcol = acc * (Cfg::ACC_COLS * msub) + h * Cfg::ACC_COLS;
                     const bool last = h == msub - 1;
-                    epi_tile<MODE, ST, RW>(p, cx, tcol, te, m_tile0 + h, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry,
-                                       last ? nx_m : m_tile0 + h + 1, last ? nx_col0 : col0, last ? nx_batch : batch);
+                    if (MODE == EPI_BIAS && !ST && epi_lean_ok(p))
+                        epi_tile_lean(p, cx, tcol, te, m_tile0 + h, col0, nch, batch, &tmem_full[acc], (ti >> 1) & 1);
+                    else
+                        epi_tile<MODE, ST, RW>(p, cx, tcol, te, m_tile0 + h, col0, nch, batch, out_cnt, &tmem_full[acc], (ti >> 1) & 1, carry,
+                                               last ? nx_m : m_tile0 + h + 1, last ? nx_col0 : col0, last ? nx_batch : batch);
                 }
             }
 #ifdef DXMI_EPI_PROFILE
