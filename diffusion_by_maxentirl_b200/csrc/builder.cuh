@@ -540,7 +540,9 @@ struct Builder {
             // statistics come from the producer GEMMs' epilogues: one pass over the tensor instead of two
             const int P1 = x1.stats_P, P2 = x2.stats_P;
             float* ab = (float*)scratch(7, (size_t)B * (C1 + C2) * 2 * sizeof(float));
-            if ((HW <= 64 || gn_fused_option()) && !x1.stats_halo && !x2.stats_halo) {
+            // option gn_fused: 0 = maps up to 8x8, 1 = every map, N > 1 = maps of up to N pixels
+            const int fused_max_hw = gn_fused_option() == 1 ? (1 << 30) : (gn_fused_option() > 1 ? gn_fused_option() : 64);
+            if (HW <= fused_max_hw && !x1.stats_halo && !x2.stats_halo) {
                 // small maps (8x8, 4x4) are launch-latency bound: one kernel that derives the statistics in its prologue
                 // (at most 2 partials per channel, one CTA per image) instead of finalize + apply
                 op([=](cudaStream_t st) {

@@ -262,7 +262,8 @@ int dxmi_op_group_norm_bwd(const void* x1, int C1, const void* x2, int C2, const
 /* -------------------------------------------------------------------------------------------- misc */
 const char* dxmi_last_error(void);
 /* A/B switches read when a plan is built (unless noted): "up2" (1, default: nearest-2x upsample + 3x3 conv as four 2x2 phase
- * convolutions of the low-resolution tensor; 0 = upsample2x_k + 9-tap convolution), "attnblk" (1 = fused DDPM AttnBlock kernel), "pair"
+ * convolutions of the low-resolution tensor; 0 = upsample2x_k + 9-tap convolution), "first_tc" (1, default: first convolution of the inference plans on
+ * mma.sync tiles; 0 = fp32 FMA kernel), "lean_epi" (0, default; 1 = unstaged drain of bias-only GEMMs, measured slower), "attnblk" (1 = fused DDPM AttnBlock kernel), "pair"
  * / "pair_min" (cta_group::2 GEMM: 0 off, 1 when >= pair_min pair tiles, 2 always), "shift3", "s3_m2", "wave_bn", "small_map_bn",
  * "conv_out_padded", "gn_fused", "stats16", "pdl" (read at every launch), and the ones listed at dxmi_set_timing_dump below */
 int dxmi_set_option(const char* name, int value);
