@@ -562,12 +562,22 @@ def measure_c4(B, K, W, args, ctx):
     tau1, tau2 = 0.01, 0.1
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
 
+    from diffusion_by_maxentirl_b200.graph import GraphedRollout
+
+    sampler.eval()
+    # the no-grad rollout is a static launch list: replayed as ONE CUDA graph that follows the optimizer steps (live=True re-packs the
+    # bf16 operands in place before each replay; the learned sigmas are recomputed from log_betas inside the graph)
+    rollout = None if args.no_graph else GraphedRollout(sampler, B, dev, live=True)
+
     def iteration(timed):
         if timed:
             ev[0].record()
         sampler.eval()
-        with torch.no_grad():
-            d = sampler.sample(B, device=dev)
+        if rollout is not None:
+            d, _ = rollout()
+        else:
+            with torch.no_grad():
+                d = sampler.sample(B, device=dev)
         if timed:
             ev[1].record()
         xs = torch.stack(d["l_sample"])  # [T+1, B, ...]
@@ -636,9 +646,10 @@ def measure_c4(B, K, W, args, ctx):
                                   f"dropout 0.1), batch {B}/GPU, bf16 tcgen05 forward + backward (BASELINE.json configs[3])",
                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"ddp{world}",
                       "collective": ("DDP gradient all-reduce (NCCL): 1 x 143 MB U-Net + 11 x 20.5 MB value net per iteration" if world > 1 else "none"),
-                      "launch": "eager (training lists are not graph-captured)", "optimizer": "train_ops.FusedAdam (clip 0.1 folded in)"},
+                      "launch": ("rollout: CUDA graph replay (graph.GraphedRollout(live=True)); " if rollout is not None else "rollout: eager; ") +
+                                "value / U-Net training steps: eager (autograd)", "optimizer": "train_ops.FusedAdam (clip 0.1 folded in)"},
            "gpu_launches": int(launches_per_iter * K), "losses": [float(x) for x in losses]}
-    del sampler, v, net, opt_s, opt_v
+    del rollout, sampler, v, net, opt_s, opt_v
     import gc
 
     gc.collect()
