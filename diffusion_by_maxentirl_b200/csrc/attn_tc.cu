@@ -5,8 +5,8 @@
 //   grid = (seq / 128, heads, batch); one CTA owns 128 query rows of one (image, head) and streams the keys in
 //   tiles of 128:   S = Q K^T  (tcgen05, M=128 N=128 K=64, fp32 in TMEM)
 //                   P = exp2(S * scale*log2e - m)   (4 softmax warps: thread <-> query row <-> TMEM lane)
-//                   O += P V  (tcgen05, M=128 N=64 K=128, accumulated IN TMEM over all key tiles; P staged bf16 in smem in the
-//                   SWIZZLE_128B K-major layout a TMA load would have produced)
+//                   O += P V  (tcgen05, M=128 N=64 K=128, accumulated IN TMEM over all key tiles; P is written back to tensor memory as
+//                   bf16 pairs and enters the MMA as a TMEM A operand - no shared-memory staging, no proxy fence: 181 -> 171 us at seq 1024)
 //
 // Warp roles (192 threads): warps 0-3 softmax + output, warp 4 TMA producer, warp 5 TMEM allocator + MMA issuer.
 // Round-2 rework of the per-tile chain (the first version ran seq 1024 at 0.43 PFLOP/s: its softmax threads read S twice from TMEM
@@ -35,10 +35,9 @@ static constexpr int ATT_TILE = 128;
 static constexpr int SM_Q = 0;
 static constexpr int SM_K = 16 * 1024;            // 2 stages x 16 KB  [128 keys x 64 d]
 static constexpr int SM_V = SM_K + 2 * 16 * 1024; // 2 stages x 16 KB  2 x [64 d x 64 keys]
-static constexpr int SM_P = SM_V + 2 * 16 * 1024; // 32 KB             2 x [128 rows x 64 keys]
-static constexpr int SM_BAR = SM_P + 32 * 1024; // 8 mbarriers + TMEM slot
-static constexpr int ATT_SMEM = SM_BAR + 128;     // 112 KB + 128 B
-static constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;
+static constexpr int SM_BAR = SM_V + 2 * 16 * 1024; // 13 mbarriers + TMEM slot
+static constexpr int ATT_SMEM = SM_BAR + 128;     // 80 KB + 128 B (P lives in tensor memory)
+static constexpr uint32_t TM_S = 0, TM_O = 128, TM_P = 192, TM_COLS = 256;  // P: 128 keys as 64 columns of bf16 pairs (A operand of P V, read from TMEM)
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -153,7 +152,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
             constexpr uint32_t idesc_o = ptx::make_idesc(1, 128, 64);
             constexpr int pv_steps = kt / 16;
             const uint64_t dq = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + SM_Q));
-            const uint32_t sp = ptx::smem_u32(smem + SM_P);
             auto issue_s = [&](int j) {
                 const int s = j & 1;
                 ptx::mbar_wait(&k_full[s], (j >> 1) & 1);
@@ -182,7 +180,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                     // B = V tile [kt keys][64 d]: the reduction index (keys) is the ROW index -> MN-major operand (b_major bit 16);
                     // 16 keys per MMA = 2 KB of rows; SBO = 1 KB between 8-key groups (same encoding as wgrad_tc.cu)
                     for (int k = 0; k < pv_steps; ++k) {
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(sp + (k >> 2) * 16384) + 2 * (k & 3);
                         uint64_t db = 0;
                         const uint32_t addr = sv + k * 2048;
                         db |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
@@ -190,13 +187,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                         db |= static_cast<uint64_t>(1024 >> 4) << 32;   // SBO
                         db |= static_cast<uint64_t>(1) << 46;
                         db |= static_cast<uint64_t>(2) << 61;           // SWIZZLE_128B
-                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o | (1u << 16), (j > 0 || k > 0) ? 1u : 0u);
+                        ptx::umma_f16_ts(tmem + TM_O, tmem + TM_P + k * 8, db, idesc_o | (1u << 16), (j > 0 || k > 0) ? 1u : 0u);
                     }
                 } else {
                     for (int k = 0; k < pv_steps; ++k) {
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(sp + (k >> 2) * 16384) + 2 * (k & 3);
                         const uint64_t db = ptx::make_kmajor_sw128_desc(sv + (k >> 2) * 8192) + 2 * (k & 3);
-                        ptx::umma_f16(tmem + TM_O, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                        ptx::umma_f16_ts(tmem + TM_O, tmem + TM_P + k * 8, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
                     }
                 }
                 ptx::umma_commit(&o_full);
@@ -208,8 +204,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
         // ------------------------------------------------------------------ softmax + output (thread <-> query row)
         const int row = warp * 32 + lane;
         const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-        uint8_t* prow = smem + SM_P + (row >> 3) * 1024 + (row & 7) * 128;
-        const int sw = row & 7;
         constexpr float RESCALE_LOG2 = 8.f;  // move the exponent's reference point only when the row maximum grew by more than 2^8
         float m = -INFINITY, l = 0.f;        // m: reference point of every exponential taken so far (>= row max - 8)
 #ifdef ATT_PROFILE
@@ -302,20 +296,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 ptx::tc_fence_after();
             }
             ATT_T(5);
-            // keys c*32 .. c*32+31 -> 64-key chunk (c >> 1), 16-byte units ((c & 1) * 4 + u), XOR-swizzled by row
-#pragma unroll
-            for (int c = 0; c < ATT_TILE / 32; ++c) {
-                if (c * 32 < kt) {
-                    uint8_t* dst = prow + (c >> 1) * 16384;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int unit = ((c & 1) * 4 + u) ^ sw;
-                        *reinterpret_cast<uint4*>(dst + unit * 16) = make_uint4(v[c * 16 + 4 * u], v[c * 16 + 4 * u + 1], v[c * 16 + 4 * u + 2], v[c * 16 + 4 * u + 3]);
-                    }
+            // P -> tensor memory (columns TM_P ..: word i = keys 2i, 2i+1 of this thread's row), the A operand of P V: no shared-memory
+            // round trip (256 cycles of smem write bandwidth per tile) and no proxy fence
+            {
+                uint32_t(&w0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                ptx::tmem_st_32x32b_x32(t_row + TM_P, w0);
+                if (kt == ATT_TILE) {
+                    uint32_t(&w1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                    ptx::tmem_st_32x32b_x32(t_row + TM_P + 32, w1);
                 }
+                ptx::tmem_st_wait();
             }
             ptx::tc_fence_before();
-            ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(&p_full);
             ATT_T(6);
         }
