@@ -265,7 +265,10 @@ const char* dxmi_last_error(void);
  * convolutions of the low-resolution tensor; 0 = upsample2x_k + 9-tap convolution), "first_tc" (1, default: first convolution of the inference plans on
  * mma.sync tiles; 0 = fp32 FMA kernel), "lean_epi" (0, default; 1 = unstaged drain of bias-only GEMMs, measured slower), "attnblk" (1 = fused DDPM AttnBlock kernel), "pair"
  * / "pair_min" (cta_group::2 GEMM: 0 off, 1 when >= pair_min pair tiles, 2 always), "shift3", "s3_m2", "wave_bn", "small_map_bn",
- * "conv_out_padded", "gn_fused", "stats16", "pdl" (read at every launch), and the ones listed at dxmi_set_timing_dump below */
+ * "conv_out_padded", "gn_fused" (0 = one-kernel GroupNorm for maps up to 8x8, 1 = every map, N > 1 = maps up to N pixels), "gn_unroll",
+ * "stats16", "s3_stages_max", "pair_resident_b" (weights-stationary pair GEMM, measured slower), "t_uniform" (1, default: one-row timestep
+ * embedding in rollouts), "rollout_split" / "rollout_split_min" (batch-split rollouts on side streams, measured neutral), "pdl" (read at
+ * every launch), and the ones listed at dxmi_set_timing_dump below */
 int dxmi_set_option(const char* name, int value);
 /* profiling only: device buffer of 8 int64 per CTA that the GEMM kernel fills with per-phase globaltimer stamps (NULL = off) */
 int dxmi_set_debug_buffer(void* dev_ptr);

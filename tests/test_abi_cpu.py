@@ -182,3 +182,18 @@ def test_dropout_stream_ids_follow_the_forward_tape():
     assert ids["mid.block_1"] < ids["mid.block_2"] == ids["mid.block_1"] + 2  # mid attention in between
     assert order[-1] == "up.0.block.2" and len(set(ids.values())) == len(ids)
     assert net.dropout_p == 0.1 and net._last_dropout_seed == 0
+
+
+def test_every_option_is_documented_in_the_header():
+    """dxmi_set_option names handled by api.cu must appear in include/dxmi_b200.h (the A/B switches behind the measurements in DESIGN.md)."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    api = open(os.path.join(root, "diffusion_by_maxentirl_b200", "csrc", "api.cu")).read()
+    header = open(os.path.join(root, "include", "dxmi_b200.h")).read()
+    names = sorted(set(re.findall(r'strcmp\(name, "([a-z0-9_]+)"\)', api)))
+    assert len(names) > 10
+    missing = [n for n in names if f'"{n}"' not in header]
+    assert not missing, missing
+
